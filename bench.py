@@ -1,0 +1,297 @@
+#!/usr/bin/env python
+"""bench.py -- headline measurement of the plane-sweep hot path (contract: see the task brief / DESIGN.md §Measurement).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload cfg2|cfg1]
+
+Own arm: one "step" = one MVSNet train step (forward + backward + Adam) on one synthetic DTU-shaped batch
+(BASELINE.json configs[1]: bf16, batch 4, 3 views, 640x512 input => 160x128x32 features, D = 192).  `value` is
+depth maps/s with the batch already resident in HBM; `e2e` is the same step fed from pinned HOST buffers with the
+H2D copy of the images and the D2H read of the loss inside the timed region.  `roofline` is for the fused
+warp+variance kernel (K1), timed live with CUDA events on its launching stream inside the timed steps.
+
+Reference arm (--impl reference): the oracle port of the reference's CPU algorithm (oracle/cpu_path.py) on the
+host cores, each step a bounded sample of the same workload (stated in `cpu_baseline.sample`).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "deep-multiview-depth-estimation_b200"))
+
+WORKLOADS = {
+    "cfg2": dict(B=4, V=3, H=512, W=640, D=192, train=True,
+                 desc="MVSNet train step bf16, batch 4/GPU, 3 views, 640x512, D=192 (BASELINE.json configs[1])"),
+    "cfg1": dict(B=1, V=3, H=512, W=640, D=192, train=False,
+                 desc="MVSNet forward, batch 1, 3 views, 640x512, D=192 (BASELINE.json configs[0])"),
+}
+
+
+def _peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json, burst copy)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=lambda: self.rows.extend(self.proc.stdout.readlines()), daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.thread.join(timeout=2)
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def run_reference(args, rank, world):
+    """CPU arm: oracle port, bounded sample, all host threads.  Only rank 0 works."""
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import torch
+    import cpu_path
+    wl = WORKLOADS[args.workload]
+    d_sample = 24
+    torch.set_num_threads(os.cpu_count() or 1)
+    s = cpu_path.make_sample(V=wl["V"], D=d_sample, h=wl["H"] // 4, w=wl["W"] // 4, d_total=wl["D"])
+    for _ in range(args.warmup):
+        cpu_path.hot_path_step(s, backward=wl["train"])
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_path.hot_path_step(s, backward=wl["train"])
+    dt = (time.perf_counter() - t0) / args.steps
+    scale = wl["D"] / d_sample
+    value = 1.0 / (dt * scale)
+    sample = (f"hot path only (warp+variance+regulariser+depth, {'fwd+bwd' if wl['train'] else 'fwd'}), 1 batch item, "
+              f"first {d_sample} of {wl['D']} planes at full 160x128x32; time scaled x{scale:g} linearly in D "
+              f"(favours the CPU: the reference's torch.cat growth is super-linear in D)")
+    line = {"impl": "reference", "metric": "depth maps/sec", "value": value, "unit": "depth maps/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["desc"]},
+            "cpu_baseline": {"value": value, "unit": "depth maps/s", "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": sample},
+            "e2e": {"value": value, "unit": "depth maps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def run_b200(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the mvs_b200 path has no CPU fallback")
+    import mvs_b200
+    from mvs_b200 import ops
+    from mvs_b200.harness import MVSNet, loss_fcn, FlatGradAllReduce
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))      # fixtures (DTU cameras) + the cpu_baseline leg only
+    import plane_sweep as ps
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    wl = WORKLOADS[args.workload]
+    B, V, H, W, D, train = wl["B"], wl["V"], wl["H"], wl["W"], wl["D"], wl["train"]
+    h, w, C = H // 4, W // 4, 32
+    d_scale = 480.0 / D
+    torch.manual_seed(0)
+    model = MVSNet(D, d_scale, precision="bf16").to(dev)
+    model.train()                                          # train-mode BN also at test time (test.py:61)
+    params = [p for p in model.parameters()]
+    opt = torch.optim.Adam(params, lr=0.005)               # train.py:160
+    reducer = FlatGradAllReduce(params) if world > 1 else None
+    if reducer:
+        reducer.broadcast_parameters(list(model.buffers()))
+
+    gen = torch.Generator().manual_seed(1000 + rank)
+    K, R, T = ps.synthetic_cameras(B, V, h, w, seed=rank)
+    d_min, d_int = torch.full((B, 1, 1, 1), 425.0), torch.ones(B, 1, 1, 1)
+    img_host = torch.randn(B * V, 3, H, W, generator=gen).pin_memory()
+    gt_host = (425.0 + 480.0 * torch.rand(B, 1, h, w, generator=gen))
+    gt_host = (gt_host * (torch.rand(B, 1, h, w, generator=gen) > 0.3)).pin_memory()     # 30 % invalid (loss.py:8)
+    img_dev, gt_dev = img_host.to(dev), gt_host.to(dev)
+    loss_host = torch.zeros(1).pin_memory()
+
+    def step(img, gt):
+        if train:
+            opt.zero_grad(set_to_none=True)
+            initial, refined = model(img, K, R, T, d_min, d_int, B, V)
+            loss, _, _ = loss_fcn(gt, initial, refined)
+            loss.backward()
+            if reducer:
+                reducer.reduce()
+            opt.step()
+            return loss.detach()
+        with torch.no_grad():
+            initial, refined = model(img, K, R, T, d_min, d_int, B, V)
+            return loss_fcn(gt, initial, refined)[0]
+
+    def step_resident():
+        return step(img_dev, gt_dev)
+
+    def step_e2e():
+        img = img_host.to(dev, non_blocking=True)
+        gt = gt_host.to(dev, non_blocking=True)
+        loss_host.copy_(step(img, gt).reshape(1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()          # the user reads the loss every step
+        return loss_host
+
+    def timed(fn, n):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ops.EVENTS = {}
+    n0 = mvs_b200.launch_count()
+    ms = timed(step_resident, args.steps)
+    launches = mvs_b200.launch_count() - n0
+    events, ops.EVENTS = ops.EVENTS, None
+    clocks = sampler.stop() if rank == 0 else None
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+
+    maps = B * world * args.steps
+    value, e2e_value = maps / (ms * 1e-3), maps / (ms_e2e * 1e-3)
+
+    # per-kernel live timings -> roofline of the fused warp+variance kernel
+    peak, peak_src = _peaks()
+    vox = B * D * h * w
+    alg = {"warp_variance_fwd": 4 * B * V * C * h * w + 2 * vox * C,            # fp32 features in, bf16 volume out
+           "warp_variance_bwd": 2 * vox * C + 2 * 4 * B * V * C * h * w,        # bf16 gcost + features in, gfeat out
+           "softmax_ranks_fwd": 2 * 4 * vox + 4 * 5 * B * h * w}
+    kern = {}
+    for name, evs in events.items():
+        t = sum(a.elapsed_time(b) for a, b in evs) / len(evs)
+        kern[name] = {"ms": t, "launches": len(evs)}
+        if name in alg:
+            kern[name].update({"alg_bytes": alg[name], "GBps": alg[name] / (t * 1e-3) / 1e9,
+                               "frac_hbm": alg[name] / (t * 1e-3) / 1e9 / peak})
+    k1 = kern.get("warp_variance_fwd", {})
+    roofline = {"kernel": "warp_variance_fwd_kernel<V=3,CPL=8,bf16 out>", "bound": "hbm", "achieved": k1.get("GBps"),
+                "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": k1.get("frac_hbm"), "traffic": None,
+                "alg_bytes_per_launch": alg["warp_variance_fwd"], "ms_per_launch": k1.get("ms"),
+                "voxels_per_s": vox / (k1["ms"] * 1e-3) if k1 else None,
+                "note": "traffic (dram bytes from ncu --set full) is recorded in profiles/ when a capture exists"}
+
+    line = None
+    if rank == 0:
+        line = {"metric": "depth maps/sec", "value": value, "unit": "depth maps/s", "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": wl["desc"], "per_gpu_batch": B, "views": V, "D": D, "features": [C, h, w],
+                           "l2": "inputs_exceed_l2 (cost volume %.0f MB per step > 126 MB L2)" % (2 * vox * C / 1e6),
+                           "parallelism": f"dp{world} (scene/batch sharding, flat-bucket NCCL grad all-reduce)" if world > 1 else "single GPU",
+                           "regulariser_convs": model.cost_volume_reg.conv_backend},
+                "e2e": {"value": e2e_value, "unit": "depth maps/s", "ms_per_step": ms_e2e / args.steps,
+                        "h2d_bytes_per_step": img_host.numel() * 4 + gt_host.numel() * 4, "d2h_bytes_per_step": 4},
+                "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "kernels": kern,
+                "cost_volume_voxels_per_s": roofline["voxels_per_s"]}
+    return line
+
+
+def cpu_baseline(workload):
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import cpu_path
+    wl = WORKLOADS[workload]
+    d_sample = 48
+    torch.set_num_threads(os.cpu_count() or 1)
+    s = cpu_path.make_sample(V=wl["V"], D=d_sample, h=wl["H"] // 4, w=wl["W"] // 4, d_total=wl["D"])
+    dt, _ = cpu_path.hot_path_step(s, backward=wl["train"])
+    scale = wl["D"] / d_sample
+    return {"value": 1.0 / (dt * scale), "unit": "depth maps/s", "cores": torch.get_num_threads(), "kind": "port",
+            "seconds_sample": dt,
+            "sample": (f"oracle port (oracle/cpu_path.py), hot path {'fwd+bwd' if wl['train'] else 'fwd'}, 1 batch item, first "
+                       f"{d_sample} of {wl['D']} planes at 160x128x32, one un-warmed pass; time scaled x{scale:g} linearly in D")}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    line = run_b200(args, rank, world, local_rank)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(args.workload)
+        print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,61 @@
+// Shared host/device helpers for libmvs_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <atomic>
+#include "../../include/mvs_b200.h"
+
+namespace mvsb200 {
+
+extern thread_local char g_err[512];
+extern std::atomic<uint64_t> g_launches;
+
+#define MVS_FAIL(code, ...)                                         \
+    do {                                                            \
+        snprintf(::mvsb200::g_err, sizeof(::mvsb200::g_err), __VA_ARGS__); \
+        return (code);                                              \
+    } while (0)
+
+#define MVS_REQUIRE(cond, ...)                                      \
+    do {                                                            \
+        if (!(cond)) MVS_FAIL(MVSB200_E_BADARG, __VA_ARGS__);       \
+    } while (0)
+
+// call right after a kernel launch
+#define MVS_CHECK_LAUNCH(name)                                      \
+    do {                                                            \
+        ::mvsb200::g_launches.fetch_add(1, std::memory_order_relaxed); \
+        cudaError_t e_ = cudaGetLastError();                        \
+        if (e_ != cudaSuccess)                                      \
+            MVS_FAIL(MVSB200_E_LAUNCH, "%s: %s", name, cudaGetErrorString(e_)); \
+    } while (0)
+
+#define MVS_CUDA(call)                                              \
+    do {                                                            \
+        cudaError_t e_ = (call);                                    \
+        if (e_ != cudaSuccess)                                      \
+            MVS_FAIL(MVSB200_E_LAUNCH, "%s: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// streaming (evict-first) 16-byte store: cost volumes are far larger than L2 and are read once
+__device__ __forceinline__ void st_cs_f4(float4* p, float4 v) {
+    asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void st_cs_u4(uint4* p, uint4 v) {
+    asm volatile("st.global.cs.v4.b32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 ld_cs_f4(const float4* p) {
+    float4 v;
+    asm volatile("ld.global.cs.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
+}  // namespace mvsb200

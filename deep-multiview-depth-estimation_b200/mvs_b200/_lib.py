@@ -1,0 +1,77 @@
+"""ctypes binding of libmvs_b200.so (C ABI declared in include/mvs_b200.h).
+
+There is no CPU or PyTorch fallback: if the shared library is missing, or a call fails, this raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.normpath(os.path.join(_HERE, "..", "csrc", "libmvs_b200.so"))
+ABI_VERSION = 1
+F32, BF16 = 0, 1
+VIEW_PARAM_FLOATS = 16
+
+_c = ctypes
+_P, _I = _c.c_void_p, _c.c_int
+
+_SIGNATURES = {
+    "mvsb200_abi_version": (_I, []),
+    "mvsb200_last_error": (_c.c_char_p, []),
+    "mvsb200_launch_count": (_c.c_uint64, []),
+    "mvsb200_nchw_to_nhwc_f32": (_I, [_P, _P, _I, _I, _I, _I, _P]),
+    "mvsb200_nhwc_to_nchw_f32": (_I, [_P, _P, _I, _I, _I, _I, _P]),
+    "mvsb200_warp_variance_fwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "mvsb200_warp_variance_bwd": (_I, [_P, _P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "mvsb200_warp_materialize": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "mvsb200_softmax_depth_fwd": (_I, [_P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "mvsb200_depth_from_ranks": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "mvsb200_depth_bwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "mvsb200_softmax_bwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
+    "mvsb200_variance_views_fwd": (_I, [_P, _P, _I, _I, _c.c_int64, _P]),
+    "mvsb200_variance_views_bwd": (_I, [_P, _P, _P, _I, _I, _c.c_int64, _P]),
+}
+
+_lib = None
+
+
+class MvsB200Error(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library (once).  Raises MvsB200Error when it is missing or has the wrong ABI."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise MvsB200Error(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            f"or `make -C {os.path.dirname(LIB_PATH)}`.  There is no CPU fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGNATURES.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError as e:
+            raise MvsB200Error(f"{LIB_PATH} does not export {name}; rebuild it") from e
+        fn.restype, fn.argtypes = res, args
+    if lib.mvsb200_abi_version() != ABI_VERSION:
+        raise MvsB200Error(f"ABI mismatch: library {lib.mvsb200_abi_version()}, binding {ABI_VERSION}")
+    _lib = lib
+    return lib
+
+
+def exported_symbols():
+    return sorted(_SIGNATURES)
+
+
+def call(name, *args):
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise MvsB200Error(f"{name} failed ({rc}): {lib.mvsb200_last_error().decode(errors='replace')}")
+
+
+def launch_count() -> int:
+    return int(load().mvsb200_launch_count())

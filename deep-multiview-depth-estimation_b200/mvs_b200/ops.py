@@ -1,0 +1,264 @@
+"""Host-side operators of the plane-sweep path: thin autograd wrappers over the C ABI (include/mvs_b200.h).
+
+PyTorch is used for device memory, streams and autograd bookkeeping only; every computation below is a
+kernel of libmvs_b200.so.  All ops raise on CPU tensors -- there is no fallback.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from . import geometry
+
+_DT = {torch.float32: _lib.F32, torch.bfloat16: _lib.BF16}
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+# bench.py sets EVENTS = {} to have every kernel launch bracketed by CUDA events on its launching stream
+EVENTS = None
+
+
+class _timed:
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if EVENTS is not None:
+            self.start = torch.cuda.Event(enable_timing=True)
+            self.start.record()
+
+    def __exit__(self, *exc):
+        if EVENTS is not None:
+            end = torch.cuda.Event(enable_timing=True)
+            end.record()
+            EVENTS.setdefault(self.name, []).append((self.start, end))
+        return False
+
+
+def _need_cuda(t: torch.Tensor, what: str):
+    if not t.is_cuda:
+        raise _lib.MvsB200Error(f"{what} must live on a CUDA device (got {t.device}); mvs_b200 has no CPU path")
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+# --------------------------------------------------------------------------------------------------
+# feature-map layout
+# --------------------------------------------------------------------------------------------------
+def _features_nhwc(feat: torch.Tensor) -> torch.Tensor:
+    """[N,C,h,w] fp32 (any strides) -> tensor whose memory is N x h x w x C.  Zero-copy when the encoder
+    already emits channels_last."""
+    N, C, h, w = feat.shape
+    if feat.dtype != torch.float32:
+        feat = feat.float()
+    if feat.permute(0, 2, 3, 1).is_contiguous():
+        return feat.permute(0, 2, 3, 1)
+    src = feat.contiguous()
+    dst = torch.empty((N, h, w, C), dtype=torch.float32, device=feat.device)
+    _lib.call("mvsb200_nchw_to_nhwc_f32", src.data_ptr(), dst.data_ptr(), N, C, h, w, _stream())
+    return dst
+
+
+def _grad_nchw(g_nhwc: torch.Tensor) -> torch.Tensor:
+    N, h, w, C = g_nhwc.shape
+    out = torch.empty((N, C, h, w), dtype=torch.float32, device=g_nhwc.device)
+    _lib.call("mvsb200_nhwc_to_nchw_f32", g_nhwc.data_ptr(), out.data_ptr(), N, C, h, w, _stream())
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
+# K1 / K2
+# --------------------------------------------------------------------------------------------------
+class _WarpVariance(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feat, view_params, tinv, B, V, D, out_dtype):
+        _need_cuda(feat, "feature_maps")
+        N, C, h, w = feat.shape
+        if N != B * V:
+            raise ValueError(f"feature_maps has {N} views, expected batch_size*n_views = {B * V}")
+        nhwc = _features_nhwc(feat.detach())
+        cost = torch.empty((B, C, D, h, w), dtype=out_dtype, device=feat.device, memory_format=torch.channels_last_3d)
+        with _timed("warp_variance_fwd"):
+            _lib.call("mvsb200_warp_variance_fwd", nhwc.data_ptr(), view_params.data_ptr(), tinv.data_ptr(),
+                      cost.data_ptr(), _DT[out_dtype], B, V, C, D, h, w, _stream())
+        ctx.save_for_backward(nhwc, view_params, tinv)
+        ctx.dims = (B, V, C, D, h, w)
+        ctx.feat_was_nhwc = feat.permute(0, 2, 3, 1).is_contiguous()
+        return cost
+
+    @staticmethod
+    def backward(ctx, gcost):
+        nhwc, view_params, tinv = ctx.saved_tensors
+        B, V, C, D, h, w = ctx.dims
+        if gcost.dtype not in _DT:
+            gcost = gcost.float()
+        gcost = gcost.contiguous(memory_format=torch.channels_last_3d)
+        g_nhwc = torch.empty((B * V, h, w, C), dtype=torch.float32, device=gcost.device)
+        with _timed("warp_variance_bwd"):
+            _lib.call("mvsb200_warp_variance_bwd", nhwc.data_ptr(), view_params.data_ptr(), tinv.data_ptr(),
+                      gcost.data_ptr(), _DT[gcost.dtype], g_nhwc.data_ptr(), B, V, C, D, h, w, _stream())
+        gfeat = g_nhwc.permute(0, 3, 1, 2) if ctx.feat_was_nhwc else _grad_nchw(g_nhwc)
+        return gfeat, None, None, None, None, None, None
+
+
+class PlaneSweep:
+    """Geometry of one homography_warping call, resident on the device: what the fused kernel needs
+    instead of the N*D 3x3 matrices the reference builds (homography.py:40-75)."""
+
+    def __init__(self, K, R, T, d_min, d_int, batch_size, n_views, d_num, d_scale, h, w, device,
+                 bug_compatible=True):
+        self.B, self.V, self.D, self.h, self.w = batch_size, n_views, d_num, h, w
+        self.d_batch_0 = geometry.depth_table(d_min, d_int, d_num, d_scale)            # CPU [B,D,1,1]
+        params, tinv = geometry.view_tables(K, R, T, self.d_batch_0, batch_size, n_views, h, w, bug_compatible)
+        packed = torch.from_numpy(params).pin_memory() if torch.cuda.is_available() else torch.from_numpy(params)
+        self.view_params = packed.to(device, non_blocking=True)
+        self.tinv = torch.from_numpy(tinv).to(device)
+        self.d_batch_dev = self.d_batch_0.to(device)
+
+
+def warp_variance(feat: torch.Tensor, sweep: PlaneSweep, out_dtype=torch.float32) -> torch.Tensor:
+    """features [B*V,32,h,w] -> variance cost volume [B,32,D,h,w] (channels_last_3d strides)."""
+    return _WarpVariance.apply(feat, sweep.view_params, sweep.tinv, sweep.B, sweep.V, sweep.D, out_dtype)
+
+
+def warp_materialize(feat: torch.Tensor, sweep: PlaneSweep) -> torch.Tensor:
+    """Parity/debug: the [B*V,C,D,h,w] warped volumes the reference's homography_warping returns."""
+    _need_cuda(feat, "feature_maps")
+    N, C, h, w = feat.shape
+    nhwc = _features_nhwc(feat.detach())
+    out = torch.empty((N, C, sweep.D, h, w), dtype=torch.float32, device=feat.device)
+    _lib.call("mvsb200_warp_materialize", nhwc.data_ptr(), sweep.view_params.data_ptr(), sweep.tinv.data_ptr(),
+              out.data_ptr(), sweep.B, sweep.V, C, sweep.D, h, w, _stream())
+    return out
+
+
+class _VarianceViews(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, warped, n_views):
+        _need_cuda(warped, "warped_feature_maps")
+        bn, c, d, h, w = warped.shape
+        x = warped.detach().float().contiguous()
+        B, M = bn // n_views, c * d * h * w
+        out = torch.empty((B, c, d, h, w), dtype=torch.float32, device=warped.device)
+        _lib.call("mvsb200_variance_views_fwd", x.data_ptr(), out.data_ptr(), B, n_views, M, _stream())
+        ctx.save_for_backward(x)
+        ctx.n_views = n_views
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        (x,) = ctx.saved_tensors
+        V = ctx.n_views
+        B, M = x.shape[0] // V, x[0].numel()
+        gx = torch.empty_like(x)
+        g = gout.float().contiguous()
+        _lib.call("mvsb200_variance_views_bwd", x.data_ptr(), g.data_ptr(), gx.data_ptr(), B, V, M, _stream())
+        return gx, None
+
+
+def variance_views(warped: torch.Tensor, n_views: int) -> torch.Tensor:
+    return _VarianceViews.apply(warped, n_views)
+
+
+# --------------------------------------------------------------------------------------------------
+# K4
+# --------------------------------------------------------------------------------------------------
+def _as_bdhw(t: torch.Tensor):
+    B, one, D, h, w = t.shape
+    if one != 1:
+        raise ValueError(f"expected a [B,1,D,h,w] volume, got {tuple(t.shape)}")
+    return t.reshape(B, D, h, w).contiguous(), (B, D, h, w)
+
+
+class _SoftmaxRanks(torch.autograd.Function):
+    """prob = softmax_D(logits); also produces the kept-plane ranks (non-differentiable side output)."""
+
+    @staticmethod
+    def forward(ctx, logits, n_est):
+        _need_cuda(logits, "logits")
+        x, (B, D, h, w) = _as_bdhw(logits.detach().float())
+        prob = torch.empty_like(x)
+        n_keep = min(n_est, D)
+        ranks = torch.empty((B, n_keep, h, w), dtype=torch.int32, device=x.device)
+        with _timed("softmax_ranks_fwd"):
+            _lib.call("mvsb200_softmax_depth_fwd", x.data_ptr(), 1, None, prob.data_ptr(), ranks.data_ptr(), None,
+                      B, D, h, w, n_est, _stream())
+        ctx.save_for_backward(prob)
+        ctx.dims = (B, D, h, w)
+        ctx.mark_non_differentiable(ranks)
+        return prob.view(B, 1, D, h, w), ranks
+
+    @staticmethod
+    def backward(ctx, gprob, _granks):
+        (prob,) = ctx.saved_tensors
+        B, D, h, w = ctx.dims
+        g = gprob.float().reshape(B, D, h, w).contiguous()
+        out = torch.empty_like(prob)
+        _lib.call("mvsb200_softmax_bwd", prob.data_ptr(), g.data_ptr(), out.data_ptr(), B, D, h, w, _stream())
+        return out.view(B, 1, D, h, w), None
+
+
+class _DepthFromProb(torch.autograd.Function):
+    """depth = sum_kept d P / sum_kept P.  `ranks` may be None (computed here from the probabilities)."""
+
+    @staticmethod
+    def forward(ctx, prob, depths, ranks, n_est):
+        _need_cuda(prob, "prob_volume")
+        p, (B, D, h, w) = _as_bdhw(prob.detach().float())
+        depths = depths.detach().to(device=p.device, dtype=torch.float32).reshape(B, D).contiguous()
+        depth = torch.empty((B, h, w), dtype=torch.float32, device=p.device)
+        n_keep = min(n_est, D)
+        if ranks is None:
+            ranks = torch.empty((B, n_keep, h, w), dtype=torch.int32, device=p.device)
+            _lib.call("mvsb200_softmax_depth_fwd", p.data_ptr(), 0, depths.data_ptr(), None, ranks.data_ptr(),
+                      depth.data_ptr(), B, D, h, w, n_est, _stream())
+        else:
+            _lib.call("mvsb200_depth_from_ranks", p.data_ptr(), ranks.data_ptr(), depths.data_ptr(), depth.data_ptr(),
+                      B, D, h, w, n_keep, _stream())
+        ctx.save_for_backward(p, ranks, depths)
+        ctx.dims = (B, D, h, w, n_keep)
+        return depth.view(B, 1, h, w)
+
+    @staticmethod
+    def backward(ctx, gdepth):
+        p, ranks, depths = ctx.saved_tensors
+        B, D, h, w, n_keep = ctx.dims
+        g = gdepth.float().reshape(B, h, w).contiguous()
+        gprob = torch.empty_like(p)
+        _lib.call("mvsb200_depth_bwd", p.data_ptr(), ranks.data_ptr(), depths.data_ptr(), g.data_ptr(),
+                  gprob.data_ptr(), B, D, h, w, n_keep, _stream())
+        return gprob.view(B, 1, D, h, w), None, None, None
+
+
+def softmax_over_depth(logits: torch.Tensor, n_est: int = 5) -> torch.Tensor:
+    """CostVolumeReg.Norm replacement.  The returned prob tensor carries the kept-plane ranks so that
+    extract_depth_map needs no second pass over the volume."""
+    prob, ranks = _SoftmaxRanks.apply(logits, int(n_est))
+    prob._mvs_ranks = (ranks, int(n_est), prob._version)
+    return prob
+
+
+def depth_from_prob(prob: torch.Tensor, d_batch: torch.Tensor, n_est: int = 5) -> torch.Tensor:
+    """extract_depth_map replacement: prob [B,1,D,h,w], d_batch [B,D,1,1] -> [B,1,h,w]."""
+    stash = getattr(prob, "_mvs_ranks", None)
+    ranks = None
+    if stash is not None and stash[1] == int(n_est) and stash[2] == prob._version:
+        ranks = stash[0]
+    return _DepthFromProb.apply(prob, d_batch, ranks, int(n_est))
+
+
+def softmax_depth(logits: torch.Tensor, d_batch: torch.Tensor, n_est: int = 5):
+    """Fully fused forward (one launch): logits -> (prob, depth).  Inference helper; no autograd."""
+    _need_cuda(logits, "logits")
+    x, (B, D, h, w) = _as_bdhw(logits.detach().float())
+    depths = d_batch.detach().to(device=x.device, dtype=torch.float32).reshape(B, D).contiguous()
+    prob = torch.empty_like(x)
+    depth = torch.empty((B, h, w), dtype=torch.float32, device=x.device)
+    _lib.call("mvsb200_softmax_depth_fwd", x.data_ptr(), 1, depths.data_ptr(), prob.data_ptr(), None, depth.data_ptr(),
+              B, D, h, w, int(n_est), _stream())
+    return prob.view(B, 1, D, h, w), depth.view(B, 1, h, w)

@@ -1,0 +1,193 @@
+"""CostVolumeReg drop-in (reference: /root/reference/scripts/model.py:68-126, factories :223-247).
+
+Same constructor, same parameter / buffer names (state_dict compatible: conv_0_0.weight ... BN_3.num_batches_tracked),
+same construction order (so ``torch.manual_seed(s); CostVolumeReg()`` draws the same initial weights), same
+forward contract ``cv[B,32,D,h,w] -> prob[B,1,D,h,w]``.
+
+What is different is HOW MUCH is computed.  The reference's "U-Net" never changes resolution: its stride-2
+convolutions use padding ``dim/2+1`` (scripts/config.py:20), so every tensor is a full D x h x w canvas
+(SURVEY App. A.5).  But on that canvas
+  * a stride-2 conv output is exactly 0 outside a central box C (per axis [ceil((p-2)/2), floor((n-1+p)/2)],
+    ~1/8 of the voxels); after BatchNorm+ReLU the outside is one constant per channel;
+  * a stride-2 transposed conv only READS the box C of its input.
+Hence: conv_{1,2,3}_0 are evaluated on C only; conv_{1,2,3}_1 are evaluated on C dilated by one voxel (the
+part that sees real data), the rest of their canvas is 27 closed-form constants per channel that enter the
+BatchNorm statistics analytically; the transposed convs run from C.  Dense full-canvas work remains only for
+conv_0_0, the three transposed-conv outputs (their batch statistics are over the full canvas) and conv_out.
+Results are those of the reference network (same statistics, same zero regions), with ~7x fewer FLOPs than
+the dense canvases cuDNN executes for the reference.
+
+The convolutions themselves go through ``conv_backend`` (mvs_b200.conv3d): sm_100a implicit-GEMM kernels
+where built, cuDNN otherwise (stated per layer in DESIGN.md).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib, ops
+from . import conv3d as conv_backends
+
+
+def central_region(n: int):
+    """Per-axis geometry of the reference's stride-2 layers on a canvas of size n.
+    Returns (lo, hi, L): output box [lo, hi] that can be non-zero / input box a transposed conv reads,
+    and L = p - 2*lo, the left padding of the equivalent small conv."""
+    p = n // 2 + 1                      # scripts/config.py:20
+    lo = (p - 1) // 2                   # ceil((p-2)/2)
+    hi = min(n - 1, (n - 1 + p) // 2)
+    return lo, hi, p - 2 * lo
+
+
+def _bview(v):
+    return v.view(1, -1, 1, 1, 1)
+
+
+class CostVolumeReg(nn.Module):
+    def __init__(self, in_ch=32, base_filt=8, device=None, precision="fp32", conv_backend="auto", n_depth_est=5):
+        super().__init__()
+        f = base_filt
+        mk = lambda i, o, s: nn.Conv3d(i, o, 3, stride=s, padding=1, bias=False, device=device)
+        mkT = lambda i, o: nn.ConvTranspose3d(i, o, 3, stride=2, padding=1, bias=False, device=device)
+        # construction order == reference (model.py:76-95) so default init consumes the RNG identically
+        self.conv_0_0 = mk(in_ch, f, 1)
+        self.conv_1_0 = mk(in_ch, f * 2, 2)
+        self.conv_2_0 = mk(in_ch, f * 4, 2)
+        self.conv_3_0 = mk(in_ch, f * 8, 2)
+        self.conv_1_1 = mk(f * 2, f * 2, 1)
+        self.conv_2_1 = mk(f * 4, f * 4, 1)
+        self.conv_3_1 = mk(f * 8, f * 8, 1)
+        self.deconv_3_0 = mkT(f * 8, f * 4)
+        self.deconv_2_0 = mkT(f * 4, f * 2)
+        self.deconv_1_0 = mkT(f * 2, f)
+        self.conv_out = mk(f, 1, 1)
+        self.ReLU = nn.ReLU()
+        bn = lambda c: nn.BatchNorm3d(c, eps=1e-5, momentum=0.1, track_running_stats=True, device=device)
+        self.BN_0, self.BN_1, self.BN_2, self.BN_3 = bn(f), bn(f * 2), bn(f * 4), bn(f * 8)
+        self.Norm = nn.Softmax(2)       # kept for state/printing parity; forward uses the fused K4 kernel
+        if precision not in ("fp32", "bf16"):
+            raise ValueError("precision must be 'fp32' or 'bf16'")
+        self.precision = precision
+        self.conv_backend = conv_backend
+        self.n_depth_est = int(n_depth_est)
+
+    # ------------------------------------------------------------------------------------------
+    def forward(self, cv: torch.Tensor) -> torch.Tensor:
+        if not cv.is_cuda:
+            raise _lib.MvsB200Error("CostVolumeReg.forward needs a CUDA tensor; mvs_b200 has no CPU path")
+        logits = self.logits(cv, conv_backends.get(self.conv_backend))
+        return ops.softmax_over_depth(logits, self.n_depth_est)
+
+    # ------------------------------------------------------------------------------------------
+    def _w(self, name, dtype):
+        w = getattr(self, name).weight
+        return w if w.dtype == dtype else w.to(dtype)
+
+    def _bn_dense(self, bn: nn.BatchNorm3d, x):
+        """Plain BatchNorm over a full canvas (+ReLU)."""
+        y = F.batch_norm(x, bn.running_mean, bn.running_var, bn.weight, bn.bias, bn.training, bn.momentum, bn.eps)
+        if bn.training:
+            bn.num_batches_tracked += 1
+        return F.relu(y)
+
+    def _bn_affine(self, bn: nn.BatchNorm3d, mean, var, n_full):
+        """scale/shift of BatchNorm given full-canvas batch statistics (train) or the running ones (eval)."""
+        if bn.training:
+            with torch.no_grad():
+                m = bn.momentum
+                bn.running_mean.mul_(1 - m).add_(mean.detach(), alpha=m)
+                bn.running_var.mul_(1 - m).add_(var.detach() * (n_full / max(n_full - 1, 1)), alpha=m)
+                bn.num_batches_tracked += 1
+        else:
+            mean, var = bn.running_mean, bn.running_var
+        scale = bn.weight * torch.rsqrt(var + bn.eps)
+        return scale, bn.bias - mean * scale
+
+    def logits(self, cv: torch.Tensor, be) -> torch.Tensor:
+        """Everything up to (excluding) the depth softmax.  `be` is a conv backend (mvs_b200.conv3d)."""
+        B, _, D, h, w = cv.shape
+        dims = (D, h, w)
+        if min(dims) < 2:
+            raise ValueError("CostVolumeReg needs D, h, w >= 2")
+        dt = torch.bfloat16 if self.precision == "bf16" else torch.float32
+        x = cv if cv.dtype == dt else cv.to(dt)
+        n_full = B * D * h * w
+        reg = [central_region(n) for n in dims]
+        C = tuple(slice(lo, hi + 1) for lo, hi, _ in reg)                     # central box on the canvas
+        train = self.BN_0.training
+
+        y0 = self._bn_dense(self.BN_0, be.conv3d(x, self._w("conv_0_0", dt), 1, (1, 1, 1)))
+
+        # ---- encoder branches: stride-2 conv on C, then stride-1 conv on C (+1 ring for the statistics)
+        P = tuple(L if L >= 2 else L + 2 for _, _, L in reg)                  # symmetric pad with P == L (mod 2)
+        off = tuple((Pp - L) // 2 for Pp, (_, _, L) in zip(P, reg))
+        cut = tuple(slice(o, o + (hi - lo + 1)) for o, (lo, hi, _) in zip(off, reg))
+        E_lo = [max(0, lo - 1) for lo, _, _ in reg]
+        E_hi = [min(n - 1, hi + 1) for (_, hi, _), n in zip(reg, dims)]
+        F_lo = [max(0, e - 1) for e in E_lo]
+        F_hi = [min(n - 1, e + 1) for e, n in zip(E_hi, dims)]
+        zpad, bgpad, inner = [], [], []
+        for ax in (2, 1, 0):                                                  # F.pad order: w, h, d
+            lo, hi, _ = reg[ax]
+            zpad += [1 if E_lo[ax] == 0 else 0, 1 if E_hi[ax] == dims[ax] - 1 else 0]
+            bgpad += [lo - F_lo[ax], F_hi[ax] - hi]
+        for ax in range(3):
+            lo, hi, _ = reg[ax]
+            inner.append(slice(lo - E_lo[ax], lo - E_lo[ax] + (hi - lo + 1)))  # C inside E
+        enc = {}
+        for k, bn in ((1, self.BN_1), (2, self.BN_2), (3, self.BN_3)):
+            S = be.conv3d(x, self._w(f"conv_{k}_0", dt), 2, P)[(slice(None), slice(None)) + cut]
+            Sf = S.float()
+            if train:
+                mean = Sf.sum((0, 2, 3, 4)) / n_full
+                n_c = Sf.numel() // Sf.shape[1]
+                var = ((Sf - _bview(mean)).pow(2).sum((0, 2, 3, 4)) + (n_full - n_c) * mean.pow(2)) / n_full
+            else:
+                mean = var = None
+            scale, shift = self._bn_affine(bn, mean, var, n_full)
+            a = F.relu(Sf * _bview(scale) + _bview(shift))                    # on C
+            bg = F.relu(shift)                                                # everywhere else on the canvas
+            # conv_k_1 input over F = C dilated by 2 (clipped): background constant + real data on C
+            X = F.pad(a - _bview(bg), bgpad) + _bview(bg)
+            X = F.pad(X, zpad)                                                # canvas border -> zero padding
+            Wk = self._w(f"conv_{k}_1", dt)
+            T = be.conv3d(X.to(dt), Wk, 1, (0, 0, 0))                         # output exactly on E
+            Tf = T.float()
+            if train:
+                mean, var = self._stats_with_constant_outside(Tf, Wk.float(), bg, dims, E_lo, E_hi, B, n_full)
+            scale, shift = self._bn_affine(bn, mean if train else None, var if train else None, n_full)
+            Tc = Tf[(slice(None), slice(None)) + tuple(inner)]
+            enc[k] = F.relu(Tc * _bview(scale) + _bview(shift))               # on C, fp32
+
+        # ---- decoder: transposed convs read only C; their outputs are dense canvases (statistics are dense)
+        Lp = tuple(L for _, _, L in reg)
+
+        def up(z, name, bn):
+            U = be.conv_transpose3d(z.to(dt), self._w(name, dt), 2, Lp, dims)
+            return self._bn_dense(bn, U)
+
+        c3 = up(enc[3], "deconv_3_0", self.BN_2)[(slice(None), slice(None)) + C].float()
+        c2 = up(c3 + enc[2], "deconv_2_0", self.BN_1)[(slice(None), slice(None)) + C].float()
+        y1 = up(c2 + enc[1], "deconv_1_0", self.BN_0)
+        return be.conv3d(y1 + y0, self._w("conv_out", dt), 1, (1, 1, 1)).float()
+
+    @staticmethod
+    def _stats_with_constant_outside(T, Wf, bg, dims, E_lo, E_hi, B, n_full):
+        """Batch mean / biased variance over the FULL canvas of a stride-1, pad-1 conv whose input is the
+        per-channel constant `bg` everywhere outside the computed box E (T holds the output on E).
+        Outside E the output takes one of 27 values per channel (which taps fall off the canvas)."""
+        dev = T.device
+        M = torch.tensor([[0., 1., 1.], [1., 1., 1.], [1., 1., 0.]], device=dev)       # [edge class][tap valid]
+        val = torch.einsum("oidhw,ad,bh,cw,i->oabc", Wf, M, M, M, bg)                   # [Cout,3,3,3]
+        full = [torch.tensor([1., n - 2., 1.], device=dev) for n in dims]
+        inside = []
+        for ax, n in enumerate(dims):
+            lo_edge = 1.0 if E_lo[ax] == 0 else 0.0
+            hi_edge = 1.0 if E_hi[ax] == n - 1 else 0.0
+            inside.append(torch.tensor([lo_edge, (E_hi[ax] - E_lo[ax] + 1) - lo_edge - hi_edge, hi_edge], device=dev))
+        cnt = B * (torch.einsum("a,b,c->abc", *full) - torch.einsum("a,b,c->abc", *inside))
+        mean = (T.sum((0, 2, 3, 4)) + (val * cnt).sum((1, 2, 3))) / n_full
+        dev_out = (val - mean.view(-1, 1, 1, 1)).pow(2) * cnt
+        var = ((T - _bview(mean)).pow(2).sum((0, 2, 3, 4)) + dev_out.sum((1, 2, 3))) / n_full
+        return mean, var

@@ -1,0 +1,119 @@
+/*
+ * mvs_b200.h  --  C ABI of libmvs_b200.so, the sm_100a implementation of MVSNet's plane-sweep
+ * hot path (homography warp -> variance cost volume -> 3D-conv regulariser -> softmax + depth).
+ *
+ * Drop-in boundary.  The reference (bcollico/Deep-Multiview-Depth-Estimation) is pure Python: its
+ * "FFI" for this path is the set of Python callables that scripts/model.py:5-7 imports by name.
+ * Each entry point below cites the reference interface it sits under; INTEGRATION.md shows the
+ * ctypes binding and the 3-line swap a maintainer adds.
+ *
+ * Conventions
+ *   - plain C types only; every pointer is a DEVICE pointer unless the name ends in _host.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *   - return value: 0 on success, <0 on error (MVSB200_E_*); mvsb200_last_error() gives the
+ *     message for the calling thread.  No entry point synchronises the device.
+ *   - the caller owns and allocates every buffer; nothing is retained after return.
+ *   - thread-safe for concurrent calls on distinct streams.
+ *
+ * Volume layout ("plane-major, channel-last"): a volume with logical shape [B, C, D, h, w] is stored
+ * as B x D x h x w x C, i.e. torch's channels_last_3d strides.  A voxel (b,d,y,x) is one contiguous
+ * row of C values (128 B fp32 / 64 B bf16 at C = 32).  Feature maps [N, C, h, w] are stored
+ * N x h x w x C (torch channels_last).
+ */
+#ifndef MVS_B200_H_
+#define MVS_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MVSB200_ABI_VERSION 1
+
+#define MVSB200_OK             0
+#define MVSB200_E_BADARG      -1   /* unsupported shape / null pointer / misaligned pointer */
+#define MVSB200_E_LAUNCH      -2   /* CUDA launch or runtime failure */
+#define MVSB200_E_UNSUPPORTED -3   /* valid request this build does not cover */
+
+#define MVSB200_F32  0
+#define MVSB200_BF16 1
+
+/* Floats per view in the `view_params` table of the warp kernels.
+ *   [0..8]  A'  = S * A^-1, row major          (S = diag(w/(w-1), h/(h-1), 1), kornia's resample)
+ *   [9..11] g'  = S * A^-1 u
+ *   [12..14] r  = w^T A^-1
+ *   [15]    reserved (0)
+ * with H_i(d) = A - u w^T / d the matrix of scripts/homography.py:61-75, so that the sampling
+ * position of destination pixel p = (x,y,1) on plane d is
+ *   q = A' p + g' (r.p) * tinv[i][d],   ix = qx/qz - 0.5,  iy = qy/qz - 0.5,
+ *   tinv[i][d] = 1 / (depth_i[d] - w^T A^-1 u)            (NaN marks a d == 0 plane: output NaN,
+ *                                                          as the reference's division by d does) */
+#define MVSB200_VIEW_PARAM_FLOATS 16
+
+int         mvsb200_abi_version(void);
+const char* mvsb200_last_error(void);
+/* number of kernel launches issued through this library by the calling process (all threads) */
+uint64_t    mvsb200_launch_count(void);
+
+/* ---- layout helpers --------------------------------------------------------------------------
+ * FeatureEncoder output (scripts/model.py:174) is NCHW; the warp kernels read channel-last rows. */
+int mvsb200_nchw_to_nhwc_f32(const float* src, float* dst, int N, int C, int H, int W, void* stream);
+int mvsb200_nhwc_to_nchw_f32(const float* src, float* dst, int N, int C, int H, int W, void* stream);
+
+/* ---- K1: fused homography warp + variance cost volume -------------------------------------------
+ * Replaces homography_warping's plane loop + kornia.warp_perspective (scripts/homography.py:78-90)
+ * AND assemble_cost_volume (scripts/costvolume.py:3-16) in one pass; the N warped volumes are never
+ * written.  feat: [B*V, h, w, C] fp32, view index b*V+v with v = 0 the reference view.
+ * view_params: [B*V, 16] fp32, tinv: [B*V, D] fp32.  cost: [B, D, h, w, C] of cost_dtype.
+ * Supported: C == 32, 2 <= V <= 8. */
+int mvsb200_warp_variance_fwd(const float* feat, const float* view_params, const float* tinv,
+                              void* cost, int cost_dtype,
+                              int B, int V, int C, int D, int h, int w, void* stream);
+
+/* ---- K2: backward of K1 wrt the feature maps -----------------------------------------------------
+ * The gradient the reference obtains by autograd through grid_sample and the variance
+ * (scripts/homography.py:85-90, scripts/costvolume.py:10-14).  gcost: [B, D, h, w, C] of
+ * gcost_dtype.  gfeat: [B*V, h, w, C] fp32, ZEROED BY THIS CALL, then accumulated. */
+int mvsb200_warp_variance_bwd(const float* feat, const float* view_params, const float* tinv,
+                              const void* gcost, int gcost_dtype, float* gfeat,
+                              int B, int V, int C, int D, int h, int w, void* stream);
+
+/* ---- parity/debug: materialise the warped volumes exactly as homography_warping returns them ----
+ * warped: [B*V, C, D, h, w] fp32, plain contiguous NCDHW (scripts/homography.py:92). */
+int mvsb200_warp_materialize(const float* feat, const float* view_params, const float* tinv,
+                             float* warped, int B, int V, int C, int D, int h, int w, void* stream);
+
+/* ---- assemble_cost_volume on a plain, already materialised tensor (scripts/costvolume.py:3-16) ---
+ * x: [B, V, M] fp32 (M = C*D*h*w), out: [B, M].  Backward: gx = (2/V)(x - mean) * gout. */
+int mvsb200_variance_views_fwd(const float* x, float* out, int B, int V, int64_t M, void* stream);
+int mvsb200_variance_views_bwd(const float* x, const float* gout, float* gx, int B, int V, int64_t M, void* stream);
+
+/* ---- K4: depth-axis softmax + "top-N" expected depth ----------------------------------------------
+ * Replaces CostVolumeReg.Norm = Softmax(dim=2) (scripts/model.py:96,123) and extract_depth_map
+ * (scripts/depthmap.py:4-22).  in: [B, D, h, w] fp32 (logits if apply_softmax, else probabilities).
+ * prob (out, may be NULL when !apply_softmax): [B, D, h, w].  depths: [B, D] fp32 or NULL.
+ * ranks (out, may be NULL): [B, n_keep, h, w] int32, n_keep = min(n_est, D): position of plane j in
+ * the stable descending sort over D == the planes the reference keeps.  depth (out, NULL iff depths
+ * is NULL): [B, h, w].  D <= 1024. */
+int mvsb200_softmax_depth_fwd(const float* in, int apply_softmax, const float* depths,
+                              float* prob, int32_t* ranks, float* depth,
+                              int B, int D, int h, int w, int n_est, void* stream);
+
+/* depth from precomputed ranks (the cheap second half when softmax ran earlier, in CostVolumeReg) */
+int mvsb200_depth_from_ranks(const float* prob, const int32_t* ranks, const float* depths, float* depth,
+                             int B, int D, int h, int w, int n_keep, void* stream);
+
+/* d depth / d prob: dense [B, D, h, w] with n_keep non-zeros per pixel (mask is constant, as in autograd
+ * through scripts/depthmap.py:12-19).  gprob is fully written. */
+int mvsb200_depth_bwd(const float* prob, const int32_t* ranks, const float* depths, const float* gdepth,
+                      float* gprob, int B, int D, int h, int w, int n_keep, void* stream);
+
+/* softmax backward over D: glogits = prob * (gprob - sum_D(gprob * prob)) */
+int mvsb200_softmax_bwd(const float* prob, const float* gprob, float* glogits,
+                        int B, int D, int h, int w, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MVS_B200_H_ */
