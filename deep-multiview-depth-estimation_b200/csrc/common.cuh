@@ -41,12 +41,16 @@ extern std::atomic<uint64_t> g_launches;
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-// streaming (evict-first) 16-byte store: cost volumes are far larger than L2 and are read once
+// streaming 16-byte store that does NOT allocate in L1: cost volumes are far larger than L2 and are read once, and an
+// L1-allocating store stream evicts the feature-map lines the tap loads live on (profiles/k1 notes)
 __device__ __forceinline__ void st_cs_f4(float4* p, float4 v) {
-    asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 __device__ __forceinline__ void st_cs_u4(uint4* p, uint4 v) {
-    asm volatile("st.global.cs.v4.b32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+    asm volatile("st.global.L1::no_allocate.v4.b32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void st_cs_u2(void* p, uint32_t a, uint32_t b) {
+    asm volatile("st.global.L1::no_allocate.v2.b32 [%0], {%1,%2};" ::"l"(p), "r"(a), "r"(b) : "memory");
 }
 __device__ __forceinline__ float4 ld_cs_f4(const float4* p) {
     float4 v;

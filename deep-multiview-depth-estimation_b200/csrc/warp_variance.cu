@@ -50,6 +50,15 @@ __device__ __forceinline__ PixelView pixel_view(const ViewParams& p, float x, fl
     return o;
 }
 
+// 1/x to <= 1 ulp (MUFU.RCP): sampling-position error ~2e-5 px, below the 9e-5 px by which the reference's own
+// fp32 matrix chain deviates from exact arithmetic.  Every kernel uses this same reciprocal so
+// that forward, backward and the materialised volumes agree on the footprints.
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 struct Sample {  // bilinear footprint of one sampling position
     int x0, y0;
     float w00, w01, w10, w11;
@@ -60,7 +69,7 @@ struct Sample {  // bilinear footprint of one sampling position
 __device__ __forceinline__ Sample sample_at(const PixelView& pv, float gx, float gy, float gz, float t, int h, int w) {
     const float m = pv.c * t;
     const float qx = fmaf(gx, m, pv.a0), qy = fmaf(gy, m, pv.a1), qz = fmaf(gz, m, pv.a2);
-    const float rz = __frcp_rn(qz);
+    const float rz = rcp_approx(qz);
     float ix = fmaf(qx, rz, -0.5f), iy = fmaf(qy, rz, -0.5f);
     ix = fminf(fmaxf(ix, -2.0f), (float)(w + 1));   // NaN -> -2
     iy = fminf(fmaxf(iy, -2.0f), (float)(h + 1));
@@ -94,6 +103,104 @@ __device__ __forceinline__ float4 blend(const Sample& s, float4 t00, float4 t01,
     o.w = fmaf(s.w11, t11.w, fmaf(s.w10, t10.w, fmaf(s.w01, t01.w, s.w00 * t00.w)));
     return o;
 }
+
+
+// ---- packed-fp32 (FFMA2 / FADD2 / FMUL2, sm_100) forward-path helpers ------------------------------------
+// The forward kernel is issue-bound (profiles/k1_r1a_summary.md), so its per-channel math runs on the packed
+// f32x2 pipe (same IEEE fp32 results, half the instructions) and the footprint reload is branch-light:
+// tap addresses are CLAMPED into the image and an out-of-bounds tap gets weight 0 (grid_sample zero padding).
+struct Sample2 {
+    int key;                       // (y0 << 16) + x0 of the 2x2 footprint (x0,y0 in [-2, 32767])
+    int x0, y0;
+    float w00, w01, w10, w11;      // bilinear weights, already 0 for out-of-bounds taps
+};
+
+__device__ __forceinline__ Sample2 sample_at2(const PixelView& pv, float gx, float gy, float gz, float t, int h, int w) {
+    const float m = pv.c * t;
+    const float qx = fmaf(gx, m, pv.a0), qy = fmaf(gy, m, pv.a1), qz = fmaf(gz, m, pv.a2);
+    const float rz = rcp_approx(qz);
+    float ix = fmaf(qx, rz, -0.5f), iy = fmaf(qy, rz, -0.5f);
+    ix = fminf(fmaxf(ix, -2.0f), (float)(w + 1));   // NaN -> -2: footprint entirely out of bounds
+    iy = fminf(fmaxf(iy, -2.0f), (float)(h + 1));
+    const float fx0 = floorf(ix), fy0 = floorf(iy);
+    Sample2 s;
+    s.x0 = (int)fx0;
+    s.y0 = (int)fy0;
+    s.key = (s.y0 << 16) + s.x0;
+    float wx1 = ix - fx0, wy1 = iy - fy0;
+    float wx0 = 1.0f - wx1, wy0 = 1.0f - wy1;
+    wx0 = ((unsigned)s.x0 < (unsigned)w) ? wx0 : 0.f;
+    wx1 = ((unsigned)(s.x0 + 1) < (unsigned)w) ? wx1 : 0.f;
+    wy0 = ((unsigned)s.y0 < (unsigned)h) ? wy0 : 0.f;
+    wy1 = ((unsigned)(s.y0 + 1) < (unsigned)h) ? wy1 : 0.f;
+    s.w00 = wx0 * wy0; s.w01 = wx1 * wy0; s.w10 = wx0 * wy1; s.w11 = wx1 * wy1;
+    return s;
+}
+
+// taps of a footprint, addresses clamped into the image (the weights carry the zero padding)
+__device__ __forceinline__ void ldg_f4_if(float4& t, const float4* p, int pred) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %5, 0;\n\t@p ld.global.nc.L1::evict_last.v4.f32 {%0,%1,%2,%3}, [%4];\n\t}"
+                 : "+f"(t.x), "+f"(t.y), "+f"(t.z), "+f"(t.w) : "l"(p), "r"(pred));
+}
+
+// branch-free refresh of a cached footprint: predicated loads keep both source views' loads in one basic block
+template <int NV4, int KSTRIDE>
+__device__ __forceinline__ void load_taps_clamped_if(const float4* __restrict__ flane, int x0, int y0, int h, int w,
+                                                     float4 (&t)[4][NV4], int pred) {
+    const int xa = min(max(x0, 0), w - 1), xb = min(max(x0 + 1, 0), w - 1);
+    const int ya = min(max(y0, 0), h - 1) * w, yb = min(max(y0 + 1, 0), h - 1) * w;
+    const int o[4] = {ya + xa, ya + xb, yb + xa, yb + xb};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float4* p = flane + (unsigned)o[j] * (unsigned)kSlots;
+#pragma unroll
+        for (int k = 0; k < NV4; ++k) ldg_f4_if(t[j][k], p + k * KSTRIDE, pred);
+    }
+}
+
+template <int NV4, int KSTRIDE>
+__device__ __forceinline__ void load_taps_clamped(const float4* __restrict__ flane, int x0, int y0, int h, int w,
+                                                  float4 (&t)[4][NV4]) {
+    const int xa = min(max(x0, 0), w - 1), xb = min(max(x0 + 1, 0), w - 1);
+    const int ya = min(max(y0, 0), h - 1) * w, yb = min(max(y0 + 1, 0), h - 1) * w;
+    const int o[4] = {ya + xa, ya + xb, yb + xa, yb + xb};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float4* p = flane + (unsigned)o[j] * (unsigned)kSlots;
+#pragma unroll
+        for (int k = 0; k < NV4; ++k) t[j][k] = __ldg(p + k * KSTRIDE);
+    }
+}
+
+__device__ __forceinline__ float2 lo2(const float4& v) { return make_float2(v.x, v.y); }
+__device__ __forceinline__ float2 hi2(const float4& v) { return make_float2(v.z, v.w); }
+
+// same operation order as blend(): fma(w11,t11, fma(w10,t10, fma(w01,t01, w00*t00)))
+__device__ __forceinline__ void blend2(const Sample2& s, const float4& t00, const float4& t01, const float4& t10,
+                                       const float4& t11, float2& lo, float2& hi) {
+    const float2 a = make_float2(s.w00, s.w00), b = make_float2(s.w01, s.w01), c = make_float2(s.w10, s.w10),
+                 d = make_float2(s.w11, s.w11);
+    lo = __ffma2_rn(d, lo2(t11), __ffma2_rn(c, lo2(t10), __ffma2_rn(b, lo2(t01), __fmul2_rn(a, lo2(t00)))));
+    hi = __ffma2_rn(d, hi2(t11), __ffma2_rn(c, hi2(t10), __ffma2_rn(b, hi2(t01), __fmul2_rn(a, hi2(t00)))));
+}
+
+// population variance over V samples, two-pass as costvolume.py:12-14 (mean, then sum (x-mean)^2, / V)
+template <int V>
+__device__ __forceinline__ float2 variance2(const float2 (&x)[V], float2 ninv, float2 inv_out) {
+    float2 sum = x[0];
+#pragma unroll
+    for (int v = 1; v < V; ++v) sum = __fadd2_rn(sum, x[v]);
+    const float2 nmean = __fmul2_rn(sum, ninv);               // -(sum/V), exact negation of the mean
+    float2 d = __fadd2_rn(x[0], nmean);
+    float2 acc = __fmul2_rn(d, d);
+#pragma unroll
+    for (int v = 1; v < V; ++v) {
+        d = __fadd2_rn(x[v], nmean);
+        acc = __ffma2_rn(d, d, acc);
+    }
+    return __fmul2_rn(acc, inv_out);
+}
+
 
 // Which float4 slots of the 32-channel row a lane owns.  fp32 rows: interleaved so that each store
 // instruction of a pixel's lane group covers a contiguous 16*LPP bytes; bf16 rows: contiguous channels
@@ -139,96 +246,153 @@ __device__ __forceinline__ void stage_tinv(float* s_tinv, const float* __restric
 // ------------------------------------------------------------------------------------------------
 // K1 forward
 // ------------------------------------------------------------------------------------------------
-template <int V, int CPL, bool BF16OUT>
-__global__ void __launch_bounds__(kThreads) warp_variance_fwd_kernel(const float4* __restrict__ feat,
-                                                                     const ViewParams* __restrict__ vp,
-                                                                     const float* __restrict__ tinv,
-                                                                     void* __restrict__ cost, int D, int h, int w,
-                                                                     int dchunk, int tiles_x) {
-    constexpr int NV4 = CPL / 4;
-    extern __shared__ float s_tinv[];
-    const TileCoord tc = tile_coord<NV4>(D, h, w, dchunk, tiles_x);
-    stage_tinv<V>(s_tinv, tinv, tc.b, D, tc.d0, tc.nd, dchunk);
-    if (!tc.active) return;
+// Forward kernel, two phases per run of kRun planes (profiles/k1_r1c_summary.md: the one-phase version was bound by
+// issue slots and L1 data-pipe wavefronts, not by HBM):
+//   phase 1  the CTA computes the bilinear footprint record of every (pixel, plane, source view) of its tile ONCE
+//            (homography in registers, clamped tap offsets, zero-padding folded into the weights) into shared memory;
+//   phase 2  8 lanes own one pixel (4 channels each, so a tap load of a pixel is one full 128-byte line and a warp's
+//            load instruction touches only the lines of pixels whose footprint moved); per plane a lane reads the
+//            record (2 broadcast LDS.128), refreshes its cached 2x2 taps with predicated loads, blends with packed
+//            f32x2 math, takes the two-pass variance over the V samples it holds and streams one 16-byte piece of
+//            the [B,D,h,w,32] row.
+constexpr int kTX = 8, kTY = 4, kPix = kTX * kTY;   // pixel tile of a CTA
+constexpr int kRun = 8;                              // planes per staged run (shared memory spent here is L1 lost)
+constexpr int kLanesPerPixel = 8;                    // 32 channels / 4 per lane
 
-    int slot[NV4];
-    lane_slots<NV4, BF16OUT>(tc.cg, slot);
-    const float xf = (float)tc.x, yf = (float)tc.y;
-    const size_t plane = (size_t)h * w;
-    const ViewParams* vpb = vp + (size_t)tc.b * V;
+struct __align__(16) FootRec {
+    float w00, w01, w10, w11;     // weights (0 for out-of-bounds taps, NaN on a d == 0 plane)
+    int o00, o01, o10, o11;       // pixel offsets y*w + x of the taps, clamped into the image
+};
 
-    // reference view: H = I for every plane => one sample per pixel
-    float4 ref[NV4];
+__device__ __forceinline__ FootRec make_record(const PixelView& pv, float gx, float gy, float gz, float t, int h, int w) {
+    const Sample2 s = sample_at2(pv, gx, gy, gz, t, h, w);
+    const int xa = min(max(s.x0, 0), w - 1), xb = min(max(s.x0 + 1, 0), w - 1);
+    const int ya = min(max(s.y0, 0), h - 1) * w, yb = min(max(s.y0 + 1, 0), h - 1) * w;
+    FootRec r;
+    const bool nan_plane = (t != t);                 // reference divides by d == 0 there: whole plane NaN
+    r.w00 = nan_plane ? NAN : s.w00; r.w01 = nan_plane ? NAN : s.w01;
+    r.w10 = nan_plane ? NAN : s.w10; r.w11 = nan_plane ? NAN : s.w11;
+    r.o00 = ya + xa; r.o01 = ya + xb; r.o10 = yb + xa; r.o11 = yb + xb;
+    return r;
+}
+
+__device__ __forceinline__ void blend2w(float w00, float w01, float w10, float w11, const float4& t00, const float4& t01,
+                                        const float4& t10, const float4& t11, float2& lo, float2& hi) {
+    const float2 a = make_float2(w00, w00), b = make_float2(w01, w01), c = make_float2(w10, w10), d = make_float2(w11, w11);
+    lo = __ffma2_rn(d, lo2(t11), __ffma2_rn(c, lo2(t10), __ffma2_rn(b, lo2(t01), __fmul2_rn(a, lo2(t00)))));
+    hi = __ffma2_rn(d, hi2(t11), __ffma2_rn(c, hi2(t10), __ffma2_rn(b, hi2(t01), __fmul2_rn(a, hi2(t00)))));
+}
+
+template <int V>
+struct FwdCfg {
+    static constexpr int kRunV = V <= 4 ? kRun : kRun / 2;                       // planes per staged run
+    static constexpr int kRecs = (V - 1) * kRunV * kPix;                         // records per buffer
+    static constexpr size_t kSmem = 2 * (size_t)kRecs * 2 * sizeof(float4);      // double-buffered, weights + offsets
+};
+
+template <int V, bool BF16OUT>
+__global__ void __launch_bounds__(kThreads, V <= 3 ? 3 : (V <= 5 ? 2 : 1))
+warp_variance_fwd_kernel(const float4* __restrict__ feat, const ViewParams* __restrict__ vp, const float* __restrict__ tinv,
+                         void* __restrict__ cost, int D, int h, int w, int dchunk, int tiles_x) {
+    constexpr int RUN = FwdCfg<V>::kRunV, RECS = FwdCfg<V>::kRecs;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    // structure-of-arrays records, [buffer][V-1][RUN][kPix]: consecutive pixels are consecutive 16-byte words
+    float4* rec_w = reinterpret_cast<float4*>(smem_raw);
+    int4* rec_o = reinterpret_cast<int4*>(smem_raw) + 2 * RECS;
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.z, d0 = blockIdx.y * dchunk, nd = min(dchunk, D - d0);
+    const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
+    const unsigned plane = (unsigned)h * (unsigned)w;
+    const ViewParams* vpb = vp + (size_t)b * V;
+
+    // ---- phase-1 identity: pixel slot p1, plane lane q
+    const int p1 = threadIdx.x & (kPix - 1), q = threadIdx.x >> 5;
+    PixelView pv1[V];
     {
-        const PixelView pv = pixel_view(vpb[0], xf, yf);
-        const Sample s = sample_at(pv, 0.f, 0.f, 0.f, 0.f, h, w);
-        float4 t[4][NV4];
-        load_taps<NV4>(feat + (size_t)(tc.b * V) * plane * kSlots, s.x0, s.y0, h, w, slot, t);
+        const float x1 = (float)(tx * kTX + (p1 & (kTX - 1))), y1 = (float)(ty * kTY + p1 / kTX);
 #pragma unroll
-        for (int k = 0; k < NV4; ++k) ref[k] = blend(s, t[0][k], t[1][k], t[2][k], t[3][k]);
+        for (int v = 1; v < V; ++v) pv1[v] = pixel_view(vpb[v], x1, y1);
     }
-
-    PixelView pv[V];
-    float gx[V], gy[V], gz[V];
-    int cx[V], cy[V];
-    float4 taps[V][4][NV4];
-#pragma unroll
-    for (int v = 1; v < V; ++v) {
-        pv[v] = pixel_view(vpb[v], xf, yf);
-        gx[v] = vpb[v].g[0]; gy[v] = vpb[v].g[1]; gz[v] = vpb[v].g[2];
-        cx[v] = INT_MIN; cy[v] = INT_MIN;
-    }
-
-    const float invV = 1.0f / (float)V;
-    size_t vox = ((size_t)(tc.b * D + tc.d0) * h + tc.y) * w + tc.x;
-    for (int dd = 0; dd < tc.nd; ++dd, vox += plane) {
-        float4 val[V][NV4];
-#pragma unroll
-        for (int k = 0; k < NV4; ++k) val[0][k] = ref[k];
-        bool nan_plane = false;
+    auto stage_run = [&](int run0, int buf) {        // phase 1: footprint records of planes [run0, run0+RUN)
+        const int nrun = min(RUN, nd - run0);
 #pragma unroll
         for (int v = 1; v < V; ++v) {
-            const float t = s_tinv[(v - 1) * dchunk + dd];
-            nan_plane |= (t != t);
-            const Sample s = sample_at(pv[v], gx[v], gy[v], gz[v], t, h, w);
-            if (s.x0 != cx[v] || s.y0 != cy[v]) {
-                load_taps<NV4>(feat + (size_t)(tc.b * V + v) * plane * kSlots, s.x0, s.y0, h, w, slot, taps[v]);
-                cx[v] = s.x0; cy[v] = s.y0;
+            const float gx = vpb[v].g[0], gy = vpb[v].g[1], gz = vpb[v].g[2];
+            const float* tv = tinv + (size_t)(b * V + v) * D + d0 + run0;
+            for (int dd = q; dd < nrun; dd += kThreads / kPix) {
+                const FootRec r = make_record(pv1[v], gx, gy, gz, __ldg(tv + dd), h, w);
+                const int i = buf * RECS + ((v - 1) * RUN + dd) * kPix + p1;
+                rec_w[i] = make_float4(r.w00, r.w01, r.w10, r.w11);
+                rec_o[i] = make_int4(r.o00, r.o01, r.o10, r.o11);
             }
-#pragma unroll
-            for (int k = 0; k < NV4; ++k) val[v][k] = blend(s, taps[v][0][k], taps[v][1][k], taps[v][2][k], taps[v][3][k]);
         }
-        float4 res[NV4];
+    };
+
+    // ---- phase-2 identity: pixel slot pl, channels 4*cg .. 4*cg+3
+    const int pl = warp * (32 / kLanesPerPixel) + lane / kLanesPerPixel, cg = lane % kLanesPerPixel;
+    const int px = tx * kTX + (pl & (kTX - 1)), py = ty * kTY + pl / kTX;
+    const bool active = px < w && py < h;
+    const float4* fb = feat + (size_t)(b * V) * plane * kSlots + cg;
+
+    stage_run(0, 0);
+
+    float2 ref[2];                                   // reference view: H = I on every plane => one sample per pixel
+    {
+        const PixelView pv = pixel_view(vpb[0], (float)px, (float)py);
+        const FootRec r = make_record(pv, 0.f, 0.f, 0.f, 0.f, h, w);
+        const float4 t00 = __ldg(fb + (unsigned)r.o00 * kSlots), t01 = __ldg(fb + (unsigned)r.o01 * kSlots),
+                     t10 = __ldg(fb + (unsigned)r.o10 * kSlots), t11 = __ldg(fb + (unsigned)r.o11 * kSlots);
+        blend2w(r.w00, r.w01, r.w10, r.w11, t00, t01, t10, t11, ref[0], ref[1]);
+    }
+
+    float4 taps[V][4];
+    int k00[V], k11[V];
 #pragma unroll
-        for (int k = 0; k < NV4; ++k) {
-            float4 sum = val[0][k];
+    for (int v = 1; v < V; ++v) {
+        k00[v] = -1; k11[v] = -1;
 #pragma unroll
-            for (int v = 1; v < V; ++v) { sum.x += val[v][k].x; sum.y += val[v][k].y; sum.z += val[v][k].z; sum.w += val[v][k].w; }
-            const float4 mean = make_float4(sum.x * invV, sum.y * invV, sum.z * invV, sum.w * invV);
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j = 0; j < 4; ++j) taps[v][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const float invV = 1.0f / (float)V;
+    const float2 ninv = make_float2(-invV, -invV), inv_out = make_float2(invV, invV);
+    __syncthreads();
+
+    int buf = 0;
+    for (int run0 = 0; run0 < nd; run0 += RUN, buf ^= 1) {
+        const int nrun = min(RUN, nd - run0);
+        if (run0 + RUN < nd) stage_run(run0 + RUN, buf ^ 1);   // next run's records, other buffer
+        if (active) {
+            // ---- phase 2
+            size_t vox = ((size_t)(b * D + d0 + run0) * h + py) * w + px;
+            const float4* rw = rec_w + buf * RECS + pl;
+            const int4* ro = rec_o + buf * RECS + pl;
+            for (int dd = 0; dd < nrun; ++dd, vox += plane) {
+                float2 val[2][V];
+                val[0][0] = ref[0]; val[1][0] = ref[1];
 #pragma unroll
-            for (int v = 0; v < V; ++v) {
-                const float dx = val[v][k].x - mean.x, dy = val[v][k].y - mean.y, dz = val[v][k].z - mean.z, dw = val[v][k].w - mean.w;
-                acc.x = fmaf(dx, dx, acc.x); acc.y = fmaf(dy, dy, acc.y); acc.z = fmaf(dz, dz, acc.z); acc.w = fmaf(dw, dw, acc.w);
+                for (int v = 1; v < V; ++v) {
+                    const float4 wt = rw[((v - 1) * RUN + dd) * kPix];
+                    const int4 of = ro[((v - 1) * RUN + dd) * kPix];
+                    const int changed = (of.x != k00[v]) | (of.w != k11[v]);
+                    const float4* fv = fb + (size_t)v * plane * kSlots;
+                    ldg_f4_if(taps[v][0], fv + (unsigned)of.x * kSlots, changed);
+                    ldg_f4_if(taps[v][1], fv + (unsigned)of.y * kSlots, changed);
+                    ldg_f4_if(taps[v][2], fv + (unsigned)of.z * kSlots, changed);
+                    ldg_f4_if(taps[v][3], fv + (unsigned)of.w * kSlots, changed);
+                    k00[v] = of.x; k11[v] = of.w;
+                    blend2w(wt.x, wt.y, wt.z, wt.w, taps[v][0], taps[v][1], taps[v][2], taps[v][3], val[0][v], val[1][v]);
+                }
+                const float2 r0 = variance2<V>(val[0], ninv, inv_out), r1 = variance2<V>(val[1], ninv, inv_out);
+                if (BF16OUT) {
+                    __nv_bfloat16* row = reinterpret_cast<__nv_bfloat16*>(cost) + vox * kC + 4 * cg;
+                    st_cs_u2(row, pack_bf16x2(r0.x, r0.y), pack_bf16x2(r1.x, r1.y));
+                } else {
+                    st_cs_f4(reinterpret_cast<float4*>(cost) + vox * kSlots + cg, make_float4(r0.x, r0.y, r1.x, r1.y));
+                }
             }
-            res[k] = make_float4(acc.x * invV, acc.y * invV, acc.z * invV, acc.w * invV);
-            if (nan_plane) res[k] = make_float4(NAN, NAN, NAN, NAN);   // d == 0 plane (reference divides by d)
         }
-        if (BF16OUT) {
-            __nv_bfloat16* row = reinterpret_cast<__nv_bfloat16*>(cost) + vox * kC + tc.cg * CPL;
-            if (NV4 == 1) {
-                uint2 o = make_uint2(pack_bf16x2(res[0].x, res[0].y), pack_bf16x2(res[0].z, res[0].w));
-                asm volatile("st.global.cs.v2.b32 [%0], {%1,%2};" ::"l"(row), "r"(o.x), "r"(o.y) : "memory");
-            } else {
-                uint4 o = make_uint4(pack_bf16x2(res[0].x, res[0].y), pack_bf16x2(res[0].z, res[0].w),
-                                     pack_bf16x2(res[NV4 - 1].x, res[NV4 - 1].y), pack_bf16x2(res[NV4 - 1].z, res[NV4 - 1].w));
-                st_cs_u4(reinterpret_cast<uint4*>(row), o);
-            }
-        } else {
-            float4* row = reinterpret_cast<float4*>(cost) + vox * kSlots;
-#pragma unroll
-            for (int k = 0; k < NV4; ++k) st_cs_f4(row + slot[k], res[k]);
-        }
+        __syncthreads();                             // next buffer staged by everyone, this buffer consumed
     }
 }
 
@@ -462,16 +626,49 @@ Plan make_plan(int B, int V, int D, int h, int w, int cpl) {
     return p;
 }
 
-template <int V, int CPL>
+struct FwdPlan {
+    dim3 grid;
+    int dchunk, tiles_x;
+    size_t smem;
+};
+
+FwdPlan make_fwd_plan(int B, int V, int D, int h, int w) {
+    FwdPlan p;
+    p.tiles_x = (w + kTX - 1) / kTX;
+    const int tiles_y = (h + kTY - 1) / kTY;
+    const long tiles = (long)p.tiles_x * tiles_y * B;
+    // >= 4 waves of 3 CTAs/SM on 148 SMs, in depth runs that are multiples of kRun
+    long nchunks = (4L * 3 * 148 + tiles - 1) / tiles;
+    const long maxchunks = (D + kRun - 1) / kRun;
+    if (nchunks > maxchunks) nchunks = maxchunks;
+    if (nchunks < 1) nchunks = 1;
+    p.dchunk = (int)((D + nchunks - 1) / nchunks);
+    p.dchunk = (p.dchunk + kRun - 1) / kRun * kRun;
+    if (const char* e = getenv("MVSB200_DCHUNK")) {
+        int v = atoi(e);
+        if (v > 0) p.dchunk = v;
+    }
+    p.grid = dim3((unsigned)(p.tiles_x * tiles_y), (unsigned)((D + p.dchunk - 1) / p.dchunk), (unsigned)B);
+    return p;
+}
+
+template <int V>
 int launch_fwd(const float* feat, const float* vp, const float* tinv, void* cost, int dtype, int B, int D, int h, int w,
                cudaStream_t st) {
-    const Plan p = make_plan(B, V, D, h, w, CPL);
-    MVS_REQUIRE(p.smem <= 48 * 1024 && p.grid.y <= 65535, "warp_variance_fwd: depth run too long");
+    FwdPlan p = make_fwd_plan(B, V, D, h, w);
+    p.smem = FwdCfg<V>::kSmem;
+    MVS_REQUIRE(p.grid.y <= 65535 && (long)h * w < (1L << 27), "warp_variance_fwd: volume too large");
+    static bool attr_set = false;                    // per instantiation; benign race (idempotent call)
+    if (!attr_set) {
+        MVS_CUDA(cudaFuncSetAttribute(warp_variance_fwd_kernel<V, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+        MVS_CUDA(cudaFuncSetAttribute(warp_variance_fwd_kernel<V, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+        attr_set = true;
+    }
     if (dtype == MVSB200_BF16)
-        warp_variance_fwd_kernel<V, CPL, true><<<p.grid, kThreads, p.smem, st>>>(
+        warp_variance_fwd_kernel<V, true><<<p.grid, kThreads, p.smem, st>>>(
             (const float4*)feat, (const ViewParams*)vp, tinv, cost, D, h, w, p.dchunk, p.tiles_x);
     else
-        warp_variance_fwd_kernel<V, CPL, false><<<p.grid, kThreads, p.smem, st>>>(
+        warp_variance_fwd_kernel<V, false><<<p.grid, kThreads, p.smem, st>>>(
             (const float4*)feat, (const ViewParams*)vp, tinv, cost, D, h, w, p.dchunk, p.tiles_x);
     MVS_CHECK_LAUNCH("warp_variance_fwd");
     return MVSB200_OK;
@@ -500,13 +697,13 @@ extern "C" int mvsb200_warp_variance_fwd(const float* feat, const float* view_pa
     MVS_REQUIRE(cost_dtype == MVSB200_F32 || cost_dtype == MVSB200_BF16, "warp_variance_fwd: bad cost dtype %d", cost_dtype);
     cudaStream_t st = (cudaStream_t)stream;
     switch (V) {
-        case 2: return launch_fwd<2, 8>(feat, view_params, tinv, cost, cost_dtype, B, D, h, w, st);
-        case 3: return launch_fwd<3, 8>(feat, view_params, tinv, cost, cost_dtype, B, D, h, w, st);
-        case 4: return launch_fwd<4, 4>(feat, view_params, tinv, cost, cost_dtype, B, D, h, w, st);
-        case 5: return launch_fwd<5, 4>(feat, view_params, tinv, cost, cost_dtype, B, D, h, w, st);
-        case 6: return launch_fwd<6, 4>(feat, view_params, tinv, cost, cost_dtype, B, D, h, w, st);
-        case 7: return launch_fwd<7, 4>(feat, view_params, tinv, cost, cost_dtype, B, D, h, w, st);
-        case 8: return launch_fwd<8, 4>(feat, view_params, tinv, cost, cost_dtype, B, D, h, w, st);
+        case 2: return launch_fwd<2>(feat, view_params, tinv, cost, cost_dtype, B, D, h, w, st);
+        case 3: return launch_fwd<3>(feat, view_params, tinv, cost, cost_dtype, B, D, h, w, st);
+        case 4: return launch_fwd<4>(feat, view_params, tinv, cost, cost_dtype, B, D, h, w, st);
+        case 5: return launch_fwd<5>(feat, view_params, tinv, cost, cost_dtype, B, D, h, w, st);
+        case 6: return launch_fwd<6>(feat, view_params, tinv, cost, cost_dtype, B, D, h, w, st);
+        case 7: return launch_fwd<7>(feat, view_params, tinv, cost, cost_dtype, B, D, h, w, st);
+        case 8: return launch_fwd<8>(feat, view_params, tinv, cost, cost_dtype, B, D, h, w, st);
     }
     MVS_FAIL(MVSB200_E_UNSUPPORTED, "warp_variance_fwd: V=%d", V);
 }

@@ -61,7 +61,8 @@ def test_identical_views_give_zero_variance_and_scaling_is_quadratic():
     Ks, Rs, Ts = K[:1].repeat(V, 1, 1), R[:1].repeat(V, 1, 1), T[:1].repeat(V, 1, 1)
     same = feat[:1].repeat(V, 1, 1, 1)
     c0, _, _ = _cost(Ks, Rs, Ts, d_min, d_int, same)
-    assert c0.abs().max().item() == 0.0
+    # not exactly 0: (x+x+x)/3 need not round back to x (the reference's mean has the same rounding)
+    assert c0.abs().max().item() <= 1e-12 * same.abs().max().item() ** 2
     c1, _, _ = _cost(K, R, T, d_min, d_int, feat)
     c4, _, _ = _cost(K, R, T, d_min, d_int, feat * 4.0)      # power of two: exact in fp32
     assert torch.equal(c4, c1 * 16.0)
