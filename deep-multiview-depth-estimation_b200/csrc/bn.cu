@@ -1,0 +1,298 @@
+// K3b: train-mode BatchNorm3d (+ReLU) over channel-last volumes, forward and backward (sm_100a).
+//
+// Reference semantics (citations into /root/reference/scripts):
+//   model.py:241-247   BatchNorm3d(eps=1e-5, momentum=0.1), ReLU
+//   model.py:101-121   y = ReLU(BN(conv(x))) after every convolution of CostVolumeReg except conv_out
+//   train.py:61 / test.py:61   the modules run in train mode => batch statistics over (B, D, h, w)
+//
+// Layout: a [B, C, D, h, w] volume in channels_last_3d strides is M = B*D*h*w rows of C contiguous channels.  Every
+// kernel below is one streaming pass (HBM-bound): a thread owns one 8-channel chunk position (so its channel group is
+// fixed over a grid-stride loop whose stride is a multiple of C/8) and moves 16 bytes (bf16) / 32 bytes (fp32) per row.
+//   bn_stats          sum, sum of squares per channel  -> per-CTA partials -> fixed-order fp64 finalize (deterministic)
+//   bn_relu_fwd       y = max(x*scale + shift, 0)
+//   bn_relu_bwd_reduce   dbeta = sum g, dgamma = sum g*xhat with g = gy * [x*scale+shift > 0]
+//   bn_relu_bwd_apply    dx = gamma*invstd * (g - dbeta/M - xhat*dgamma/M)
+#include "common.cuh"
+
+using namespace mvsb200;
+
+namespace {
+
+constexpr int kBnThreads = 256;
+constexpr int kBnBlocks = 148 * 4;      // persistent grid: 4 CTAs of 256 threads per SM
+constexpr int kMaxC = 64;
+
+template <typename T>
+struct Chunk;                            // 8 consecutive channels of one row
+template <>
+struct Chunk<float> {
+    static __device__ __forceinline__ void load(const float* p, float (&v)[8]) {
+        const float4 a = __ldcs(reinterpret_cast<const float4*>(p)), b = __ldcs(reinterpret_cast<const float4*>(p) + 1);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    }
+    static __device__ __forceinline__ void store(float* p, const float (&v)[8]) {
+        __stcs(reinterpret_cast<float4*>(p), make_float4(v[0], v[1], v[2], v[3]));
+        __stcs(reinterpret_cast<float4*>(p) + 1, make_float4(v[4], v[5], v[6], v[7]));
+    }
+};
+template <>
+struct Chunk<__nv_bfloat16> {
+    static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[8]) {
+        const uint4 u = __ldcs(reinterpret_cast<const uint4*>(p));
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            v[2 * i] = __uint_as_float(w[i] << 16);
+            v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+        }
+    }
+    static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&v)[8]) {
+        __stcs(reinterpret_cast<uint4*>(p), make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
+                                                        pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7])));
+    }
+};
+
+// Sum each thread's 2 x 8 accumulators over the CTA per channel and write the CTA's partial row [2][C].
+// Lanes with equal (lane % CPR) hold the same channel group.
+__device__ __forceinline__ void block_reduce_to_partial(float (&a)[8], float (&b)[8], int cpr, int C, float* partial_row) {
+    __shared__ float s_part[kBnThreads / 32][2][kMaxC];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        for (int o = 16; o >= cpr; o >>= 1) {
+            a[i] += __shfl_xor_sync(0xffffffffu, a[i], o);
+            b[i] += __shfl_xor_sync(0xffffffffu, b[i], o);
+        }
+    }
+    if (lane < cpr) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            s_part[warp][0][lane * 8 + i] = a[i];
+            s_part[warp][1][lane * 8 + i] = b[i];
+        }
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < 2 * C) {
+        const int which = threadIdx.x / C, c = threadIdx.x % C;
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < kBnThreads / 32; ++w) s += s_part[w][which][c];
+        partial_row[which * C + c] = s;
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kBnThreads) bn_stats_kernel(const T* __restrict__ x, long long n_chunks, int C,
+                                                              float* __restrict__ partials) {
+    const int cpr = C / 8;
+    float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const long long stride = (long long)gridDim.x * kBnThreads;
+    for (long long i = (long long)blockIdx.x * kBnThreads + threadIdx.x; i < n_chunks; i += stride) {
+        float v[8];
+        Chunk<T>::load(x + i * 8, v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { s[k] += v[k]; q[k] = fmaf(v[k], v[k], q[k]); }
+    }
+    block_reduce_to_partial(s, q, cpr, C, partials + (size_t)blockIdx.x * 2 * C);
+}
+
+// one CTA: out[0][c] = sum_a / M, out[1][c] = sum_b / M - (sum_a / M)^2   (mode 0: mean, biased variance)
+//          out[0][c] = sum_a,     out[1][c] = sum_b                        (mode 1: raw sums)
+__global__ void bn_finalize_kernel(const float* __restrict__ partials, int nblocks, int C, double inv_m, int mode,
+                                   float* __restrict__ out0, float* __restrict__ out1) {
+    const int c = threadIdx.x;
+    if (c >= C) return;
+    double a = 0.0, b = 0.0;
+    for (int k = 0; k < nblocks; ++k) {
+        a += (double)partials[(size_t)k * 2 * C + c];
+        b += (double)partials[(size_t)k * 2 * C + C + c];
+    }
+    if (mode == 0) {
+        const double mean = a * inv_m;
+        double var = b * inv_m - mean * mean;
+        out0[c] = (float)mean;
+        out1[c] = (float)(var > 0.0 ? var : 0.0);
+    } else {
+        out0[c] = (float)a;
+        out1[c] = (float)b;
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kBnThreads) bn_relu_fwd_kernel(const T* __restrict__ x, const float* __restrict__ scale,
+                                                                 const float* __restrict__ shift, T* __restrict__ y,
+                                                                 long long n_chunks, int C, int relu) {
+    const int cpr = C / 8;
+    const long long i0 = (long long)blockIdx.x * kBnThreads + threadIdx.x;
+    const int cg = (int)(i0 % cpr);
+    float sc[8], sh[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { sc[k] = scale[cg * 8 + k]; sh[k] = shift[cg * 8 + k]; }
+    const long long stride = (long long)gridDim.x * kBnThreads;
+    for (long long i = i0; i < n_chunks; i += stride) {
+        float v[8];
+        Chunk<T>::load(x + i * 8, v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            v[k] = fmaf(v[k], sc[k], sh[k]);
+            if (relu) v[k] = fmaxf(v[k], 0.f);
+        }
+        Chunk<T>::store(y + i * 8, v);
+    }
+}
+
+template <typename TX, typename TG>
+__global__ void __launch_bounds__(kBnThreads) bn_relu_bwd_reduce_kernel(const TX* __restrict__ x, const TG* __restrict__ gy,
+                                                                        const float* __restrict__ scale,
+                                                                        const float* __restrict__ shift,
+                                                                        const float* __restrict__ mean,
+                                                                        const float* __restrict__ invstd, long long n_chunks,
+                                                                        int C, int relu, float* __restrict__ partials) {
+    const int cpr = C / 8;
+    const long long i0 = (long long)blockIdx.x * kBnThreads + threadIdx.x;
+    const int cg = (int)(i0 % cpr);
+    float sc[8], sh[8], mu[8], is[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        sc[k] = scale[cg * 8 + k]; sh[k] = shift[cg * 8 + k]; mu[k] = mean[cg * 8 + k]; is[k] = invstd[cg * 8 + k];
+    }
+    float sg[8] = {0, 0, 0, 0, 0, 0, 0, 0}, sgx[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const long long stride = (long long)gridDim.x * kBnThreads;
+    for (long long i = i0; i < n_chunks; i += stride) {
+        float v[8], g[8];
+        Chunk<TX>::load(x + i * 8, v);
+        Chunk<TG>::load(gy + i * 8, g);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float gk = (!relu || fmaf(v[k], sc[k], sh[k]) > 0.f) ? g[k] : 0.f;
+            sg[k] += gk;
+            sgx[k] = fmaf(gk, (v[k] - mu[k]) * is[k], sgx[k]);
+        }
+    }
+    block_reduce_to_partial(sg, sgx, cpr, C, partials + (size_t)blockIdx.x * 2 * C);
+}
+
+template <typename TX, typename TG>
+__global__ void __launch_bounds__(kBnThreads) bn_relu_bwd_apply_kernel(const TX* __restrict__ x, const TG* __restrict__ gy,
+                                                                       const float* __restrict__ scale,
+                                                                       const float* __restrict__ shift,
+                                                                       const float* __restrict__ mean,
+                                                                       const float* __restrict__ invstd,
+                                                                       const float* __restrict__ gamma,
+                                                                       const float* __restrict__ dbeta,
+                                                                       const float* __restrict__ dgamma, TX* __restrict__ dx,
+                                                                       long long n_chunks, int C, int relu, float inv_m) {
+    const int cpr = C / 8;
+    const long long i0 = (long long)blockIdx.x * kBnThreads + threadIdx.x;
+    const int cg = (int)(i0 % cpr);
+    float sc[8], sh[8], mu[8], is[8], k0[8], k1[8], k2[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int c = cg * 8 + k;
+        sc[k] = scale[c]; sh[k] = shift[c]; mu[k] = mean[c]; is[k] = invstd[c];
+        k0[k] = gamma[c] * is[k];                 // dx = k0 * (g - k1 - xhat * k2)
+        k1[k] = dbeta[c] * inv_m;
+        k2[k] = dgamma[c] * inv_m;
+    }
+    const long long stride = (long long)gridDim.x * kBnThreads;
+    for (long long i = i0; i < n_chunks; i += stride) {
+        float v[8], g[8];
+        Chunk<TX>::load(x + i * 8, v);
+        Chunk<TG>::load(gy + i * 8, g);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float gk = (!relu || fmaf(v[k], sc[k], sh[k]) > 0.f) ? g[k] : 0.f;
+            const float xhat = (v[k] - mu[k]) * is[k];
+            v[k] = k0[k] * (gk - k1[k] - xhat * k2[k]);
+        }
+        Chunk<TX>::store(dx + i * 8, v);
+    }
+}
+
+int check_bn(const void* x, long long M, int C, const char* name) {
+    MVS_REQUIRE(x && aligned16(x), "%s: null or misaligned volume", name);
+    MVS_REQUIRE(C == 8 || C == 16 || C == 32 || C == 64, "%s: C must be 8, 16, 32 or 64 (got %d)", name, C);
+    MVS_REQUIRE(M >= 1, "%s: empty volume", name);
+    return MVSB200_OK;
+}
+
+int grid_for(long long n_chunks) {
+    long long b = (n_chunks + kBnThreads - 1) / kBnThreads;
+    return (int)(b < kBnBlocks ? b : kBnBlocks);
+}
+
+}  // namespace
+
+extern "C" int64_t mvsb200_bn_workspace_floats(void) { return (int64_t)kBnBlocks * 2 * kMaxC; }
+
+extern "C" int mvsb200_bn_stats(const void* x, int dtype, int64_t M, int C, float* workspace, float* mean, float* var,
+                                void* stream) {
+    if (int rc = check_bn(x, M, C, "bn_stats")) return rc;
+    MVS_REQUIRE(workspace && mean && var, "bn_stats: null output");
+    MVS_REQUIRE(dtype == MVSB200_F32 || dtype == MVSB200_BF16, "bn_stats: bad dtype %d", dtype);
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long n_chunks = (long long)M * C / 8;
+    const int grid = grid_for(n_chunks);
+    if (dtype == MVSB200_BF16)
+        bn_stats_kernel<__nv_bfloat16><<<grid, kBnThreads, 0, st>>>((const __nv_bfloat16*)x, n_chunks, C, workspace);
+    else
+        bn_stats_kernel<float><<<grid, kBnThreads, 0, st>>>((const float*)x, n_chunks, C, workspace);
+    MVS_CHECK_LAUNCH("bn_stats");
+    bn_finalize_kernel<<<1, kMaxC, 0, st>>>(workspace, grid, C, 1.0 / (double)M, 0, mean, var);
+    MVS_CHECK_LAUNCH("bn_finalize");
+    return MVSB200_OK;
+}
+
+extern "C" int mvsb200_bn_relu_fwd(const void* x, int dtype, const float* scale, const float* shift, void* y, int relu,
+                                   int64_t M, int C, void* stream) {
+    if (int rc = check_bn(x, M, C, "bn_relu_fwd")) return rc;
+    MVS_REQUIRE(y && aligned16(y) && scale && shift, "bn_relu_fwd: null or misaligned argument");
+    MVS_REQUIRE(dtype == MVSB200_F32 || dtype == MVSB200_BF16, "bn_relu_fwd: bad dtype %d", dtype);
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long n_chunks = (long long)M * C / 8;
+    const int grid = grid_for(n_chunks);
+    if (dtype == MVSB200_BF16)
+        bn_relu_fwd_kernel<__nv_bfloat16><<<grid, kBnThreads, 0, st>>>((const __nv_bfloat16*)x, scale, shift,
+                                                                       (__nv_bfloat16*)y, n_chunks, C, relu);
+    else
+        bn_relu_fwd_kernel<float><<<grid, kBnThreads, 0, st>>>((const float*)x, scale, shift, (float*)y, n_chunks, C, relu);
+    MVS_CHECK_LAUNCH("bn_relu_fwd");
+    return MVSB200_OK;
+}
+
+template <typename TX, typename TG>
+static int bn_bwd_impl(const void* x, const void* gy, const float* scale, const float* shift, const float* mean,
+                       const float* invstd, const float* gamma, float* workspace, float* dbeta, float* dgamma, void* dx,
+                       int relu, int64_t M, int C, cudaStream_t st) {
+    const long long n_chunks = (long long)M * C / 8;
+    const int grid = grid_for(n_chunks);
+    bn_relu_bwd_reduce_kernel<TX, TG><<<grid, kBnThreads, 0, st>>>((const TX*)x, (const TG*)gy, scale, shift, mean, invstd,
+                                                                   n_chunks, C, relu, workspace);
+    MVS_CHECK_LAUNCH("bn_relu_bwd_reduce");
+    bn_finalize_kernel<<<1, kMaxC, 0, st>>>(workspace, grid, C, 1.0, 1, dbeta, dgamma);
+    MVS_CHECK_LAUNCH("bn_finalize");
+    bn_relu_bwd_apply_kernel<TX, TG><<<grid, kBnThreads, 0, st>>>((const TX*)x, (const TG*)gy, scale, shift, mean, invstd,
+                                                                  gamma, dbeta, dgamma, (TX*)dx, n_chunks, C, relu,
+                                                                  (float)(1.0 / (double)M));
+    MVS_CHECK_LAUNCH("bn_relu_bwd_apply");
+    return MVSB200_OK;
+}
+
+extern "C" int mvsb200_bn_relu_bwd(const void* x, int x_dtype, const void* gy, int g_dtype, const float* scale,
+                                   const float* shift, const float* mean, const float* invstd, const float* gamma,
+                                   float* workspace, float* dbeta, float* dgamma, void* dx, int relu, int64_t M, int C,
+                                   void* stream) {
+    if (int rc = check_bn(x, M, C, "bn_relu_bwd")) return rc;
+    MVS_REQUIRE(gy && aligned16(gy) && dx && aligned16(dx), "bn_relu_bwd: null or misaligned volume");
+    MVS_REQUIRE(scale && shift && mean && invstd && gamma && workspace && dbeta && dgamma, "bn_relu_bwd: null vector");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (x_dtype == MVSB200_BF16 && g_dtype == MVSB200_BF16)
+        return bn_bwd_impl<__nv_bfloat16, __nv_bfloat16>(x, gy, scale, shift, mean, invstd, gamma, workspace, dbeta, dgamma, dx, relu, M, C, st);
+    if (x_dtype == MVSB200_BF16 && g_dtype == MVSB200_F32)
+        return bn_bwd_impl<__nv_bfloat16, float>(x, gy, scale, shift, mean, invstd, gamma, workspace, dbeta, dgamma, dx, relu, M, C, st);
+    if (x_dtype == MVSB200_F32 && g_dtype == MVSB200_F32)
+        return bn_bwd_impl<float, float>(x, gy, scale, shift, mean, invstd, gamma, workspace, dbeta, dgamma, dx, relu, M, C, st);
+    if (x_dtype == MVSB200_F32 && g_dtype == MVSB200_BF16)
+        return bn_bwd_impl<float, __nv_bfloat16>(x, gy, scale, shift, mean, invstd, gamma, workspace, dbeta, dgamma, dx, relu, M, C, st);
+    MVS_FAIL(MVSB200_E_BADARG, "bn_relu_bwd: bad dtypes %d / %d", x_dtype, g_dtype);
+}

@@ -262,3 +262,86 @@ def softmax_depth(logits: torch.Tensor, d_batch: torch.Tensor, n_est: int = 5):
     _lib.call("mvsb200_softmax_depth_fwd", x.data_ptr(), 1, depths.data_ptr(), prob.data_ptr(), None, depth.data_ptr(),
               B, D, h, w, int(n_est), _stream())
     return prob.view(B, 1, D, h, w), depth.view(B, 1, h, w)
+
+
+# --------------------------------------------------------------------------------------------------
+# K3b: train-mode BatchNorm3d + ReLU on channel-last volumes
+# --------------------------------------------------------------------------------------------------
+_BN_WS = {}
+
+
+def _bn_workspace(device):
+    ws = _BN_WS.get(device)
+    if ws is None:
+        ws = torch.empty(int(_lib.load().mvsb200_bn_workspace_floats()), dtype=torch.float32, device=device)
+        _BN_WS[device] = ws
+    return ws
+
+
+def _rows(x: torch.Tensor):
+    """[B,C,D,h,w] volume -> (tensor whose memory is M x C rows, M, C)."""
+    if x.dtype not in _DT:
+        x = x.float()
+    x = x.contiguous(memory_format=torch.channels_last_3d)
+    B, C, D, h, w = x.shape
+    return x, B * D * h * w, C
+
+
+class _BatchNormReLU(torch.autograd.Function):
+    """y = ReLU(BatchNorm_train(x)) with batch statistics (model.py:101-121).  Returns (y, mean, biased var)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps, relu):
+        _need_cuda(x, "BatchNorm input")
+        xr, M, C = _rows(x.detach())
+        dev = xr.device
+        mean = torch.empty(C, dtype=torch.float32, device=dev)
+        var = torch.empty(C, dtype=torch.float32, device=dev)
+        ws = _bn_workspace(dev)
+        with _timed("bn_stats"):
+            _lib.call("mvsb200_bn_stats", xr.data_ptr(), _DT[xr.dtype], M, C, ws.data_ptr(), mean.data_ptr(),
+                      var.data_ptr(), _stream())
+        invstd = torch.rsqrt(var + eps)
+        scale = (weight.detach().float() * invstd).contiguous()
+        shift = (bias.detach().float() - mean * scale).contiguous()
+        y = torch.empty_like(xr)
+        with _timed("bn_relu_fwd"):
+            _lib.call("mvsb200_bn_relu_fwd", xr.data_ptr(), _DT[xr.dtype], scale.data_ptr(), shift.data_ptr(),
+                      y.data_ptr(), int(relu), M, C, _stream())
+        ctx.save_for_backward(xr, scale, shift, mean, invstd, weight.detach().float().contiguous())
+        ctx.relu, ctx.dims = bool(relu), (M, C)
+        ctx.mark_non_differentiable(mean, var)
+        return y, mean, var
+
+    @staticmethod
+    def backward(ctx, gy, _gm, _gv):
+        xr, scale, shift, mean, invstd, gamma = ctx.saved_tensors
+        M, C = ctx.dims
+        if gy.dtype not in _DT:
+            gy = gy.float()
+        gy = gy.contiguous(memory_format=torch.channels_last_3d)
+        dev = xr.device
+        dbeta = torch.empty(C, dtype=torch.float32, device=dev)
+        dgamma = torch.empty(C, dtype=torch.float32, device=dev)
+        dx = torch.empty_like(xr)
+        with _timed("bn_relu_bwd"):
+            _lib.call("mvsb200_bn_relu_bwd", xr.data_ptr(), _DT[xr.dtype], gy.data_ptr(), _DT[gy.dtype], scale.data_ptr(),
+                      shift.data_ptr(), mean.data_ptr(), invstd.data_ptr(), gamma.data_ptr(),
+                      _bn_workspace(dev).data_ptr(), dbeta.data_ptr(), dgamma.data_ptr(), dx.data_ptr(), int(ctx.relu),
+                      M, C, _stream())
+        return dx, dgamma, dbeta, None, None
+
+
+def batchnorm_relu_train(x, weight, bias, eps=1e-5, relu=True):
+    """-> (y, batch mean [C], biased batch variance [C]); y has x's dtype (fp32 or bf16), channels_last_3d."""
+    return _BatchNormReLU.apply(x, weight, bias, float(eps), bool(relu))
+
+
+def affine_relu(x, scale, shift, relu=True):
+    """Eval-mode BatchNorm(+ReLU): y = max(x*scale + shift, 0) with given per-channel fp32 vectors (no autograd)."""
+    _need_cuda(x, "BatchNorm input")
+    xr, M, C = _rows(x.detach())
+    y = torch.empty_like(xr)
+    _lib.call("mvsb200_bn_relu_fwd", xr.data_ptr(), _DT[xr.dtype], scale.float().contiguous().data_ptr(),
+              shift.float().contiguous().data_ptr(), y.data_ptr(), int(relu), M, C, _stream())
+    return y

@@ -85,7 +85,21 @@ class CostVolumeReg(nn.Module):
         return w if w.dtype == dtype else w.to(dtype)
 
     def _bn_dense(self, bn: nn.BatchNorm3d, x):
-        """Plain BatchNorm over a full canvas (+ReLU)."""
+        """BatchNorm over a full canvas (+ReLU).  On the GPU this is the fused channel-last kernel pair of
+        libmvs_b200.so (K3b); the torch expression below serves only the CPU unit tests of the canvas algebra."""
+        if x.is_cuda:
+            if bn.training:
+                y, mean, var = ops.batchnorm_relu_train(x, bn.weight, bn.bias, bn.eps, relu=True)
+                n = x.numel() // x.shape[1]
+                with torch.no_grad():
+                    m = bn.momentum
+                    bn.running_mean.mul_(1 - m).add_(mean, alpha=m)
+                    bn.running_var.mul_(1 - m).add_(var * (n / max(n - 1, 1)), alpha=m)
+                    bn.num_batches_tracked += 1
+                return y
+            if not torch.is_grad_enabled() or not (x.requires_grad or bn.weight.requires_grad):
+                scale = bn.weight * torch.rsqrt(bn.running_var + bn.eps)
+                return ops.affine_relu(x, scale, bn.bias - bn.running_mean * scale, relu=True)
         y = F.batch_norm(x, bn.running_mean, bn.running_var, bn.weight, bn.bias, bn.training, bn.momentum, bn.eps)
         if bn.training:
             bn.num_batches_tracked += 1
@@ -136,8 +150,14 @@ class CostVolumeReg(nn.Module):
             lo, hi, _ = reg[ax]
             inner.append(slice(lo - E_lo[ax], lo - E_lo[ax] + (hi - lo + 1)))  # C inside E
         enc = {}
+        # the three stride-2 branches all read cv (model.py:104-110): ONE convolution with the weights stacked along
+        # Cout (16+32+64 = 112) reads the cost volume once instead of three times
+        w_cat = torch.cat([self._w(f"conv_{k}_0", dt) for k in (1, 2, 3)], 0)
+        S_all = be.conv3d(x, w_cat, 2, P)[(slice(None), slice(None)) + cut]
+        S_split = dict(zip((1, 2, 3), torch.split(S_all, [self.conv_1_0.out_channels, self.conv_2_0.out_channels,
+                                                          self.conv_3_0.out_channels], 1)))
         for k, bn in ((1, self.BN_1), (2, self.BN_2), (3, self.BN_3)):
-            S = be.conv3d(x, self._w(f"conv_{k}_0", dt), 2, P)[(slice(None), slice(None)) + cut]
+            S = S_split[k]
             Sf = S.float()
             if train:
                 mean = Sf.sum((0, 2, 3, 4)) / n_full

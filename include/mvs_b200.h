@@ -113,6 +113,26 @@ int mvsb200_depth_bwd(const float* prob, const int32_t* ranks, const float* dept
 int mvsb200_softmax_bwd(const float* prob, const float* gprob, float* glogits,
                         int B, int D, int h, int w, void* stream);
 
+/* ---- K3b: train-mode BatchNorm3d (+ReLU) on channel-last volumes -----------------------------------
+ * Replaces the BatchNorm3d + ReLU pairs of CostVolumeReg.forward (scripts/model.py:101-121; layer
+ * factory :241-247) in train mode (batch statistics over B, D, h, w; scripts/train.py:61, test.py:61).
+ * x, y, gy, dx: [M, C] rows of C contiguous channels (a [B,C,D,h,w] volume in channels_last_3d
+ * strides, M = B*D*h*w), dtype MVSB200_F32 or MVSB200_BF16; C in {8,16,32,64}.  Per-channel vectors
+ * are fp32 [C].  `workspace` is caller-owned scratch of mvsb200_bn_workspace_floats() floats.
+ *   bn_stats     mean[c], biased variance[c] of x (deterministic two-stage reduction, fp64 finalize)
+ *   bn_relu_fwd  y = x*scale + shift, then max(.,0) if relu        (scale = gamma/sqrt(var+eps))
+ *   bn_relu_bwd  dbeta = sum g, dgamma = sum g*xhat, dx = gamma*invstd*(g - dbeta/M - xhat*dgamma/M)
+ *                with g = gy * [x*scale+shift > 0] (or gy when !relu), xhat = (x-mean)*invstd */
+int64_t mvsb200_bn_workspace_floats(void);
+int mvsb200_bn_stats(const void* x, int dtype, int64_t M, int C, float* workspace, float* mean, float* var,
+                     void* stream);
+int mvsb200_bn_relu_fwd(const void* x, int dtype, const float* scale, const float* shift, void* y, int relu,
+                        int64_t M, int C, void* stream);
+int mvsb200_bn_relu_bwd(const void* x, int x_dtype, const void* gy, int g_dtype, const float* scale,
+                        const float* shift, const float* mean, const float* invstd, const float* gamma,
+                        float* workspace, float* dbeta, float* dgamma, void* dx, int relu, int64_t M, int C,
+                        void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,105 @@
+"""K3b parity: fused train-mode BatchNorm3d+ReLU kernels (C ABI: mvsb200_bn_*) against torch's batch_norm on the same
+seeded inputs, forward and backward, fp32 and bf16 storage, every channel count the regulariser uses, ragged row
+counts; plus the whole regulariser's gradients against the goldens produced by the unmodified reference."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import mvs_b200
+from mvs_b200 import ops
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _ref(x, w, b, eps, relu):
+    y = F.batch_norm(x, None, None, w, b, True, 0.1, eps)
+    return F.relu(y) if relu else y
+
+
+@pytest.mark.parametrize("C", [8, 16, 32, 64])
+@pytest.mark.parametrize("shape", [(1, 5, 7, 9), (2, 8, 16, 20), (1, 1, 1, 3)])
+@pytest.mark.parametrize("relu", [True, False])
+def test_bn_relu_fp32_forward_backward(C, shape, relu):
+    B, D, h, w = shape
+    g = torch.Generator().manual_seed(C * 100 + D)
+    x = (torch.randn(B, C, D, h, w, generator=g) * 2 + 0.5).to(DEV).contiguous(memory_format=torch.channels_last_3d)
+    wt = (torch.rand(C, generator=g) + 0.5).to(DEV).requires_grad_(True)
+    bs = torch.randn(C, generator=g).to(DEV).requires_grad_(True)
+    gy = torch.randn(B, C, D, h, w, generator=g).to(DEV)
+    x1 = x.clone().requires_grad_(True)
+    y, mean, var = ops.batchnorm_relu_train(x1, wt, bs, 1e-5, relu)
+    y.backward(gy)
+    x2 = x.clone().requires_grad_(True)
+    w2, b2 = wt.detach().clone().requires_grad_(True), bs.detach().clone().requires_grad_(True)
+    yr = _ref(x2, w2, b2, 1e-5, relu)
+    yr.backward(gy)
+    assert y.shape == yr.shape and y.is_contiguous(memory_format=torch.channels_last_3d)
+    assert torch.allclose(mean, x.mean((0, 2, 3, 4)), rtol=1e-5, atol=1e-6)
+    assert torch.allclose(var, x.var((0, 2, 3, 4), unbiased=False), rtol=1e-4, atol=1e-6)
+    tol = dict(rtol=1e-4, atol=1e-5)
+    assert torch.allclose(y, yr, **tol)
+    scale = max(1.0, float(x2.grad.abs().max()))
+    assert (x1.grad - x2.grad).abs().max().item() < 2e-4 * scale
+    assert torch.allclose(wt.grad, w2.grad, rtol=1e-3, atol=1e-3 * float(w2.grad.abs().max()))
+    assert torch.allclose(bs.grad, b2.grad, rtol=1e-3, atol=1e-3 * float(b2.grad.abs().max()))
+
+
+@pytest.mark.parametrize("C", [8, 32])
+def test_bn_relu_bf16_storage(C):
+    g = torch.Generator().manual_seed(C)
+    x = torch.randn(2, C, 6, 10, 12, generator=g).to(DEV).to(torch.bfloat16).contiguous(memory_format=torch.channels_last_3d)
+    wt, bs = (torch.rand(C, generator=g) + 0.5).to(DEV), torch.randn(C, generator=g).to(DEV)
+    gy = torch.randn(2, C, 6, 10, 12, generator=g).to(DEV).to(torch.bfloat16)
+    x1 = x.clone().requires_grad_(True)
+    y, _, _ = ops.batchnorm_relu_train(x1, wt, bs)
+    y.backward(gy)
+    x2 = x.float().requires_grad_(True)
+    yr = _ref(x2, wt, bs, 1e-5, True)
+    yr.backward(gy.float())
+    assert y.dtype == torch.bfloat16 and x1.grad.dtype == torch.bfloat16
+    assert (y.float() - yr).abs().max().item() < 1e-2 * float(yr.abs().max())
+    assert (x1.grad.float() - x2.grad).abs().max().item() < 1e-2 * float(x2.grad.abs().max())
+
+
+def test_bn_full_canvas_statistics_are_deterministic():
+    x = torch.randn(1, 8, 192, 128, 160, device=DEV).to(torch.bfloat16).contiguous(memory_format=torch.channels_last_3d)
+    wt, bs = torch.ones(8, device=DEV), torch.zeros(8, device=DEV)
+    _, m1, v1 = ops.batchnorm_relu_train(x, wt, bs)
+    _, m2, v2 = ops.batchnorm_relu_train(x, wt, bs)
+    assert torch.equal(m1, m2) and torch.equal(v1, v2)
+    assert torch.allclose(m1, x.float().mean((0, 2, 3, 4)), atol=1e-5)
+    assert torch.allclose(v1, x.float().var((0, 2, 3, 4), unbiased=False), rtol=1e-4)
+
+
+def test_bad_channel_count_raises():
+    x = torch.zeros(1, 12, 2, 2, 2, device=DEV)
+    with pytest.raises(mvs_b200.MvsB200Error, match="C must be"):
+        ops.batchnorm_relu_train(x, torch.ones(12, device=DEV), torch.zeros(12, device=DEV))
+
+
+def test_regulariser_gradients_match_reference(golden_dir):
+    """Whole CostVolumeReg on the GPU (fused BN kernels + convs + K4) against the reference's autograd."""
+    g = dict(np.load(os.path.join(golden_dir, "tiny_b1v3.npz")))
+    reg = mvs_b200.CostVolumeReg(device=DEV)
+    w0 = np.load(os.path.join(golden_dir, "reg_weights.npz"))
+    reg.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in w0.items()})
+    reg.train()
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        cv = torch.from_numpy(g["cost"]).to(DEV).requires_grad_(True)
+        prob = reg(cv)
+        depth = mvs_b200.extract_depth_map(prob, torch.from_numpy(g["d_batch"]).to(DEV))
+        names = [n for n, _ in reg.named_parameters()]
+        grads = torch.autograd.grad((depth * torch.from_numpy(g["gdepth"]).to(DEV)).sum(), [cv] + list(reg.parameters()))
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    ref = g["gcv"]
+    assert np.abs(grads[0].cpu().numpy() - ref).max() < 5e-4 * np.abs(ref).max()
+    for n, gr in zip(names, grads[1:]):
+        ref = g["gparam/" + n]
+        assert np.abs(gr.cpu().numpy() - ref).max() <= 5e-4 * max(np.abs(ref).max(), 1e-3), n

@@ -18,6 +18,7 @@ ap.add_argument("--D", type=int, default=192)
 ap.add_argument("--fwd-only", action="store_true")
 ap.add_argument("--precision", default="bf16")
 ap.add_argument("--rows", type=int, default=45)
+ap.add_argument("--shapes", action="store_true")
 a = ap.parse_args()
 dev = "cuda:0"
 B, V, H, W, D = a.B, 3, 512, 640, a.D
@@ -43,8 +44,8 @@ def step():
 for _ in range(3):
     step()
 torch.cuda.synchronize()
-with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU], record_shapes=a.shapes) as prof:
     step()
     torch.cuda.synchronize()
-print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=a.rows, max_name_column_width=70))
+print(prof.key_averages(group_by_input_shape=a.shapes).table(sort_by="cuda_time_total", row_limit=a.rows, max_name_column_width=60, max_shapes_column_width=110))
 print("peak memory GB:", torch.cuda.max_memory_allocated() / 1e9)
