@@ -1,0 +1,405 @@
+// K3: 3x3x3 stride-1 convolution of channel-last bf16 volumes as an implicit GEMM on tcgen05 tensor cores (sm_100a).
+//
+// Reference semantics (citations into /root/reference/scripts):
+//   model.py:223-234   Conv3d(k=3, stride, padding, bias=False)  -- the stride-1 layers conv_0_0, conv_{1,2,3}_1
+//   model.py:101-113   their use in CostVolumeReg.forward; autograd's dgrad of the same layers is this very
+//                      convolution with the flipped, transposed filter (host side packs it)
+//
+// GEMM view: D[M = voxels, N = Cout] += A[M, K = Cin] * B[K, N] summed over the 27 taps.  The design removes the
+// 27-fold re-read of the activations that a tap-by-tap im2col costs:
+//   * a CTA owns an (x, y) tile of the volume and MARCHES ALONG DEPTH.  Per input plane ONE TMA tile load brings the
+//     (L+2) x BW halo'd slab of voxel rows (Cin bf16 each, hardware-swizzled) into a 4-slot shared-memory ring; every
+//     slab is used by the three output planes around it.
+//   * inside a slab the 9 in-plane taps are NOT separate copies: voxel rows are consecutive in shared memory, so the
+//     A operand of tap (kh, kw) is the same slab read from row offset kh*BW + kw -- only the start address of the
+//     UMMA shared-memory descriptor changes.  Output rows that fall on the halo columns are computed and dropped
+//     (BW-2 useful of BW).
+//   * all 27 x Cout x Cin filter taps stay resident in shared memory (loaded once per CTA by TMA).
+//   * accumulators live in TMEM (MB blocks of 128 rows x NOUT fp32 columns, double buffered), the epilogue warps read
+//     them back with tcgen05.ld, convert to bf16 and store voxel rows while the MMA warp works on the next plane.
+// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane) + TMEM allocator, warps 2..5 = epilogue.
+#include "common.cuh"
+#include <cuda.h>
+#include <stdlib.h>
+
+using namespace mvsb200;
+
+namespace {
+
+constexpr int kTcThreads = 192;
+constexpr int kSlots3 = 4;          // slab ring depth (3 live planes + 1 in flight)
+constexpr int kMaxMB = 4;
+
+struct ConvParams {
+    int B, Do, Ho, Wo;              // output volume
+    int off_d, off_h, off_w;        // input coordinate = output coordinate + tap + off   (-1 = padding 1, 0 = valid)
+    int BW, L, MB;                  // slab: BW voxels per line (incl. 2 halo), L output lines, MB 128-row blocks
+    int tiles_x, tiles_y;
+    int dchunk;                     // output planes per CTA
+    int cout, y_cs, y_coff;         // channels to store, channel stride of an output voxel row, first channel
+    int n_rows;                     // filter rows per tap in the packed weights (multiple of 16)
+    int w_row0;                     // first filter row this launch computes (N split of wide layers)
+    int slab_bytes;                 // per ring slot, multiple of 1024
+    __nv_bfloat16* y;
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3,
+                                            int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc),
+        "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t (&v)[N]);
+template <>
+__device__ __forceinline__ void tmem_ld<16>(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                   "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr));
+}
+template <>
+__device__ __forceinline__ void tmem_ld<32>(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,"
+        "%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptor of a K-major operand whose rows are ROWB bytes (= the swizzle span) apart.
+// Measured on B200 (tools/test_conv_tc.py, round 1): the hardware applies the swizzle XOR to the ABSOLUTE shared-memory
+// address, exactly as TMA does when it writes the tile, so a start address shifted by any number of voxel rows (not
+// only by whole 8-row swizzle atoms) addresses the shifted operand correctly with the base-offset field left 0.
+// (Setting base_offset = (addr >> 7) & 7 for unaligned starts gives wrong results.)
+template <int ROWB>
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+    constexpr uint64_t layout = ROWB == 128 ? 2 : (ROWB == 64 ? 4 : 6);          // SWIZZLE_128B / 64B / 32B
+    uint64_t d = (uint64_t)((saddr >> 4) & 0x3fff);
+    d |= (uint64_t)1 << 16;                                                       // LBO: unused for swizzled K-major
+    d |= (uint64_t)((8 * ROWB) >> 4) << 32;                                       // SBO: 8 rows
+    d |= (uint64_t)1 << 46;                                                       // descriptor version (Blackwell)
+    d |= layout << 61;
+    return d;
+}
+
+template <int CIN, int NOUT>
+__global__ void __launch_bounds__(kTcThreads, 1)
+conv3d_s1_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w, const ConvParams p) {
+    constexpr int ROWB = CIN * 2;                       // bytes per voxel row == swizzle span
+    constexpr int KSTEPS = CIN / 16;                    // UMMA K = 16 bf16 = 32 bytes
+    constexpr int W_TAP_BYTES = NOUT * ROWB;
+    constexpr int W_BYTES = 27 * W_TAP_BYTES;
+    constexpr int W_BYTES_AL = (W_BYTES + 1023) / 1024 * 1024;
+    // instruction descriptor: D fp32, A/B bf16, both K-major, N, M = 128
+    constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NOUT >> 3) << 17) | ((128u >> 4) << 24);
+
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
+    unsigned char* w_smem = smem;
+    unsigned char* slab_smem = smem + W_BYTES_AL;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(slab_smem + (size_t)kSlots3 * p.slab_bytes);
+    uint64_t* full = bars;                  // [kSlots3]  slab landed
+    uint64_t* empty = bars + kSlots3;       // [kSlots3]  slab no longer read by any MMA
+    uint64_t* wfull = bars + 2 * kSlots3;   // [1]        filter resident
+    uint64_t* tfull = wfull + 1;            // [2]        accumulator stage complete
+    uint64_t* tempty = tfull + 2;           // [2]        accumulator stage drained by the epilogue
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tx = blockIdx.x % p.tiles_x, ty = blockIdx.x / p.tiles_x;
+    const int x0 = tx * (p.BW - 2), y0 = ty * p.L;
+    const int d_begin = blockIdx.y * p.dchunk;
+    const int nd = min(p.dchunk, p.Do - d_begin);
+    const int b = blockIdx.z;
+    const int MB = p.MB;
+    uint32_t tmem_cols = 32;
+    while ((int)tmem_cols < 2 * MB * NOUT) tmem_cols <<= 1;
+
+    if (threadIdx.x == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_x) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_w) : "memory");
+        for (int i = 0; i < kSlots3; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
+        mbar_init(wfull, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(tfull + i, 1); mbar_init(tempty + i, 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================================== TMA producer =====================================
+        if (lane == 0) {
+            mbar_expect_tx(wfull, W_BYTES);
+            for (int tap = 0; tap < 27; ++tap)
+                tma_load_2d(w_smem + tap * W_TAP_BYTES, &tm_w, wfull, 0, tap * p.n_rows + p.w_row0);
+            const uint32_t box_bytes = (uint32_t)ROWB * p.BW * (p.L + 2);
+            for (int s = 0; s < nd + 2; ++s) {          // input planes d_begin+off_d+s, s = 0 .. nd+1
+                const int slot = s % kSlots3;
+                if (s >= kSlots3) mbar_wait(empty + slot, ((s / kSlots3) - 1) & 1);
+                mbar_expect_tx(full + slot, box_bytes);
+                tma_load_5d(slab_smem + (size_t)slot * p.slab_bytes, &tm_x, full + slot, 0, x0 + p.off_w, y0 + p.off_h,
+                            d_begin + p.off_d + s, b);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===================================== MMA issuer =======================================
+        if (lane == 0) {
+            mbar_wait(wfull, 0);
+            const uint32_t w_addr = smem_u32(w_smem), slab_addr = smem_u32(slab_smem);
+            int landed = 0;                              // slabs s < landed have been waited for
+            for (int d = 0; d < nd; ++d) {
+                const int stage = d & 1;
+                if (d >= 2) mbar_wait(tempty + stage, ((d >> 1) - 1) & 1);
+                while (landed <= d + 2) { mbar_wait(full + landed % kSlots3, (landed / kSlots3) & 1); ++landed; }
+                tc_fence_after();
+                for (int mb = 0; mb < MB; ++mb) {
+                    const uint32_t d_tmem = tmem_base + (uint32_t)((stage * MB + mb) * NOUT);
+                    uint32_t acc = 0;
+                    for (int kd = 0; kd < 3; ++kd) {
+                        const uint32_t slab = slab_addr + (uint32_t)(((d + kd) % kSlots3) * p.slab_bytes);
+                        for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+                            for (int kw = 0; kw < 3; ++kw) {
+                                const uint32_t a_addr = slab + (uint32_t)((mb * 128 + kh * p.BW + kw) * ROWB);
+                                const uint32_t b_addr = w_addr + (uint32_t)(((kd * 3 + kh) * 3 + kw) * W_TAP_BYTES);
+#pragma unroll
+                                for (int k = 0; k < KSTEPS; ++k) {
+                                    umma_bf16(d_tmem, umma_desc<ROWB>(a_addr + k * 32),
+                                              umma_desc<ROWB>(b_addr + k * 32), IDESC, acc);
+                                    acc = 1;
+                                }
+                            }
+                        }
+                    }
+                }
+                umma_commit(empty + d % kSlots3);        // input plane s = d is not needed after this output plane
+                umma_commit(tfull + stage);
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===================================== epilogue =========================================
+        const int q = warp & 3;                          // TMEM lane quarter this warp may access
+        for (int d = 0; d < nd; ++d) {
+            const int stage = d & 1;
+            mbar_wait(tfull + stage, (d >> 1) & 1);
+            tc_fence_after();
+            for (int mb = 0; mb < MB; ++mb) {
+                const int m = mb * 128 + q * 32 + lane;
+                const int j = m / p.BW, i = m - j * p.BW;
+                const bool valid = i < p.BW - 2 && j < p.L && x0 + i < p.Wo && y0 + j < p.Ho;
+                uint32_t v[NOUT];
+                tmem_ld<NOUT>(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((stage * MB + mb) * NOUT), v);
+                tmem_ld_wait();
+                if (valid) {
+                    __nv_bfloat16* row = p.y + ((((size_t)b * p.Do + d_begin + d) * p.Ho + y0 + j) * p.Wo + x0 + i) * p.y_cs + p.y_coff;
+#pragma unroll
+                    for (int c = 0; c < NOUT; c += 8) {
+                        if (c < p.cout) {
+                            const uint4 o = make_uint4(pack_bf16x2(__uint_as_float(v[c]), __uint_as_float(v[c + 1])),
+                                                       pack_bf16x2(__uint_as_float(v[c + 2]), __uint_as_float(v[c + 3])),
+                                                       pack_bf16x2(__uint_as_float(v[c + 4]), __uint_as_float(v[c + 5])),
+                                                       pack_bf16x2(__uint_as_float(v[c + 6]), __uint_as_float(v[c + 7])));
+                            *reinterpret_cast<uint4*>(row + c) = o;
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty + stage);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+    }
+}
+
+// ---- host side ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+CUtensorMapSwizzle swizzle_for(int rowb) {
+    return rowb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (rowb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
+struct TilePlan {
+    int BW, L, MB, tiles_x, tiles_y, slab_bytes;
+    double score;
+};
+
+// pick the slab geometry: maximise useful rows per MMA row and per loaded row within the shared-memory budget
+TilePlan plan_tiles(int Ho, int Wo, int rowb, size_t w_bytes_al, size_t smem_budget) {
+    TilePlan best{};
+    best.score = -1.0;
+    for (int MB = 1; MB <= kMaxMB; MB *= 2) {
+        for (int BW = 10; BW <= 256; BW += 2) {
+            const int L = (MB * 128) / BW;
+            if (L < 1 || L + 2 > 256) continue;
+            const int rows = MB * 128 + 2 * BW + 2;
+            const int slab = ((rows * rowb) + 1023) / 1024 * 1024;
+            if (w_bytes_al + (size_t)kSlots3 * slab + 256 > smem_budget) continue;
+            const int tiles_x = (Wo + BW - 3) / (BW - 2), tiles_y = (Ho + L - 1) / L;
+            const double mma_eff = (double)Wo * Ho / ((double)tiles_x * tiles_y * MB * 128);
+            const double load_eff = (double)Wo * Ho / ((double)tiles_x * tiles_y * (L + 2) * BW);
+            const double score = mma_eff * (0.5 + 0.5 * load_eff);
+            if (score > best.score) best = TilePlan{BW, L, MB, tiles_x, tiles_y, slab, score};
+        }
+    }
+    return best;
+}
+
+template <int CIN, int NOUT>
+int launch_conv(const void* x, const void* w, void* y, int B, int Di, int Hi, int Wi, int Do, int Ho, int Wo, int cout,
+                int y_cs, int y_coff, int n_rows, int w_row0, int off_d, int off_h, int off_w, cudaStream_t st) {
+    constexpr int ROWB = CIN * 2;
+    constexpr size_t W_BYTES_AL = ((size_t)27 * NOUT * ROWB + 1023) / 1024 * 1024;
+    EncodeTiledFn enc = encode_fn();
+    MVS_REQUIRE(enc != nullptr, "conv3d_s1: cuTensorMapEncodeTiled is not available from the driver");
+    const size_t smem_budget = 227 * 1024 - 1024;       // 1024 for the manual alignment of the dynamic window
+    const TilePlan tp = plan_tiles(Ho, Wo, ROWB, W_BYTES_AL, smem_budget);
+    MVS_REQUIRE(tp.score > 0, "conv3d_s1: no slab geometry fits shared memory (Cin=%d, N=%d)", CIN, NOUT);
+
+    CUtensorMap tm_x, tm_w;
+    {
+        const cuuint64_t dims[5] = {(cuuint64_t)CIN, (cuuint64_t)Wi, (cuuint64_t)Hi, (cuuint64_t)Di, (cuuint64_t)B};
+        const cuuint64_t strides[4] = {(cuuint64_t)ROWB, (cuuint64_t)ROWB * Wi, (cuuint64_t)ROWB * Wi * Hi,
+                                       (cuuint64_t)ROWB * Wi * Hi * Di};
+        const cuuint32_t box[5] = {(cuuint32_t)CIN, (cuuint32_t)tp.BW, (cuuint32_t)(tp.L + 2), 1, 1};
+        const cuuint32_t es[5] = {1, 1, 1, 1, 1};
+        CUresult r = enc(&tm_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), dims, strides, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(ROWB), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        MVS_REQUIRE(r == CUDA_SUCCESS, "conv3d_s1: cuTensorMapEncodeTiled(x) failed (%d)", (int)r);
+    }
+    {
+        const cuuint64_t dims[2] = {(cuuint64_t)CIN, (cuuint64_t)27 * n_rows};
+        const cuuint64_t strides[1] = {(cuuint64_t)ROWB};
+        const cuuint32_t box[2] = {(cuuint32_t)CIN, (cuuint32_t)NOUT};
+        const cuuint32_t es[2] = {1, 1};
+        CUresult r = enc(&tm_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims, strides, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(ROWB), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        MVS_REQUIRE(r == CUDA_SUCCESS, "conv3d_s1: cuTensorMapEncodeTiled(w) failed (%d)", (int)r);
+    }
+
+    ConvParams p;
+    p.B = B; p.Do = Do; p.Ho = Ho; p.Wo = Wo;
+    p.off_d = off_d; p.off_h = off_h; p.off_w = off_w;
+    p.BW = tp.BW; p.L = tp.L; p.MB = tp.MB; p.tiles_x = tp.tiles_x; p.tiles_y = tp.tiles_y;
+    p.cout = cout; p.y_cs = y_cs; p.y_coff = y_coff; p.n_rows = n_rows; p.w_row0 = w_row0;
+    p.slab_bytes = tp.slab_bytes;
+    p.y = reinterpret_cast<__nv_bfloat16*>(y);
+    // depth runs: enough CTAs for ~2 waves of 148 SMs, but long runs (each run re-loads 2 halo planes)
+    const long tiles = (long)tp.tiles_x * tp.tiles_y * B;
+    long nchunks = (2L * 148 + tiles - 1) / tiles;
+    if (nchunks > (Do + 7) / 8) nchunks = (Do + 7) / 8;
+    if (nchunks < 1) nchunks = 1;
+    p.dchunk = (int)((Do + nchunks - 1) / nchunks);
+    if (const char* e = getenv("MVSB200_CONV_DCHUNK")) { int v = atoi(e); if (v > 0) p.dchunk = v; }
+    const dim3 grid((unsigned)(tp.tiles_x * tp.tiles_y), (unsigned)((Do + p.dchunk - 1) / p.dchunk), (unsigned)B);
+    const size_t smem = 1024 + W_BYTES_AL + (size_t)kSlots3 * tp.slab_bytes + 256;
+    MVS_CUDA(cudaFuncSetAttribute(conv3d_s1_tc_kernel<CIN, NOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conv3d_s1_tc_kernel<CIN, NOUT><<<grid, kTcThreads, smem, st>>>(tm_x, tm_w, p);
+    MVS_CHECK_LAUNCH("conv3d_s1_tc");
+    return MVSB200_OK;
+}
+
+}  // namespace
+
+extern "C" int mvsb200_conv3d_s1_fwd(const void* x, const void* w_packed, void* y, int B, int Di, int Hi, int Wi, int Cin,
+                                     int Do, int Ho, int Wo, int cout, int y_cs, int n_rows, int off_d, int off_h, int off_w,
+                                     void* stream) {
+    MVS_REQUIRE(x && w_packed && y, "conv3d_s1_fwd: null pointer");
+    MVS_REQUIRE(aligned16(x) && aligned16(w_packed) && aligned16(y), "conv3d_s1_fwd: pointers must be 16-byte aligned");
+    MVS_REQUIRE(B >= 1 && B <= 65535 && Di >= 1 && Hi >= 1 && Wi >= 1 && Do >= 1 && Ho >= 1 && Wo >= 1, "conv3d_s1_fwd: bad shape");
+    MVS_REQUIRE(cout >= 8 && cout % 8 == 0 && cout <= n_rows && n_rows % 16 == 0 && n_rows <= 64,
+                "conv3d_s1_fwd: cout must be a multiple of 8 and n_rows a multiple of 16 <= 64 (cout=%d n_rows=%d)", cout, n_rows);
+    MVS_REQUIRE(y_cs >= cout && y_cs % 8 == 0, "conv3d_s1_fwd: output channel stride %d", y_cs);
+    cudaStream_t st = (cudaStream_t)stream;
+#define MVS_CONV(CI, NO) return launch_conv<CI, NO>(x, w_packed, y, B, Di, Hi, Wi, Do, Ho, Wo, cout, y_cs, 0, n_rows, 0, off_d, off_h, off_w, st)
+    if (Cin == 16 && n_rows == 16) MVS_CONV(16, 16);
+    if (Cin == 16 && n_rows == 32) MVS_CONV(16, 32);
+    if (Cin == 32 && n_rows == 16) MVS_CONV(32, 16);
+    if (Cin == 32 && n_rows == 32) MVS_CONV(32, 32);
+    if (Cin == 64 && n_rows == 32) MVS_CONV(64, 32);
+    if (Cin == 64 && n_rows == 64) {                     // 64 -> 64: two N = 32 halves (filter does not fit at N = 64)
+        int rc = launch_conv<64, 32>(x, w_packed, y, B, Di, Hi, Wi, Do, Ho, Wo, cout < 32 ? cout : 32, y_cs, 0, n_rows, 0,
+                                     off_d, off_h, off_w, st);
+        if (rc != MVSB200_OK || cout <= 32) return rc;
+        return launch_conv<64, 32>(x, w_packed, y, B, Di, Hi, Wi, Do, Ho, Wo, cout - 32, y_cs, 32, n_rows, 32, off_d, off_h,
+                                   off_w, st);
+    }
+#undef MVS_CONV
+    MVS_FAIL(MVSB200_E_UNSUPPORTED, "conv3d_s1_fwd: unsupported channels Cin=%d n_rows=%d", Cin, n_rows);
+}

@@ -113,6 +113,21 @@ int mvsb200_depth_bwd(const float* prob, const int32_t* ranks, const float* dept
 int mvsb200_softmax_bwd(const float* prob, const float* gprob, float* glogits,
                         int B, int D, int h, int w, void* stream);
 
+/* ---- K3: 3x3x3 stride-1 convolution, implicit GEMM on tcgen05 tensor cores fed by TMA ---------------
+ * Replaces nn.Conv3d(k=3, stride=1, bias=False) of CostVolumeReg (scripts/model.py:223-234; the layers
+ * conv_0_0, conv_1_1, conv_2_1, conv_3_1 at :101-113) and, with the flipped/transposed filter, autograd's
+ * data gradient of the same layers.  bf16 in, fp32 accumulate (TMEM), bf16 out.
+ *   x        [B, Di, Hi, Wi, Cin]  bf16, dense (channels_last_3d of a [B,Cin,Di,Hi,Wi] volume), Cin in {16,32,64}
+ *   w_packed [27, n_rows, Cin]     bf16: tap-major (kd,kh,kw), then output channel (zero rows up to n_rows,
+ *                                  n_rows in {16,32,64}), then input channel
+ *   y        [B, Do, Ho, Wo, y_cs] bf16; channels [0, cout) of every voxel row are written (cout % 8 == 0)
+ *   out(z,y,x) = sum_taps W[tap] . x(z + kd + off_d, y + kh + off_h, x + kw + off_w), zero outside the input:
+ *   off = -1 is padding 1 (Do = Di), off = 0 a valid convolution (Do = Di - 2).
+ */
+int mvsb200_conv3d_s1_fwd(const void* x, const void* w_packed, void* y, int B, int Di, int Hi, int Wi, int Cin,
+                          int Do, int Ho, int Wo, int cout, int y_cs, int n_rows, int off_d, int off_h, int off_w,
+                          void* stream);
+
 /* ---- K3b: train-mode BatchNorm3d (+ReLU) on channel-last volumes -----------------------------------
  * Replaces the BatchNorm3d + ReLU pairs of CostVolumeReg.forward (scripts/model.py:101-121; layer
  * factory :241-247) in train mode (batch statistics over B, D, h, w; scripts/train.py:61, test.py:61).
