@@ -35,7 +35,8 @@ struct ConvParams {
     int off_d, off_h, off_w;        // input coordinate = output coordinate + tap + off   (-1 = padding 1, 0 = valid)
     int BW, L, MB;                  // slab: BW voxels per line (incl. 2 halo), L output lines, MB 128-row blocks
     int tiles_x, tiles_y;
-    int dchunk;                     // output planes per CTA
+    int dchunk, nchunks;            // output planes per item, depth runs per volume
+    int n_items;                    // B * nchunks * tiles_x * tiles_y work items
     int cout, y_cs, y_coff;         // channels to store, channel stride of an output voxel row, first channel
     int n_rows;                     // filter rows per tap in the packed weights (multiple of 16)
     int w_row0;                     // first filter row this launch computes (N split of wide layers)
@@ -76,6 +77,17 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
                  : "memory");
+}
+// one lane of a converged warp (the form the compiler recognises as single-thread issue: no uniformisation loops
+// around the tcgen05 / TMA instructions it guards)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+        "elect.sync rx|px, 0xffffffff;\n\t"
+        "@px mov.s32 %0, 1;\n\t}"
+        : "+r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -127,6 +139,20 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
     return d;
 }
 
+// one tcgen05.mma, descriptors given as (lo, hi) halves so the issue loop only does 32-bit adds on the start address
+__device__ __forceinline__ void umma_bf16_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                               uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi),
+        "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// Persistent kernel: CTA c works on items c, c + gridDim.x, ...; an item is (batch, depth run, xy tile).  The filter is
+// loaded once per CTA; the slab ring, the TMEM stages and all mbarrier phases run on across items (global counters).
 template <int CIN, int NOUT>
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv3d_s1_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w, const ConvParams p) {
@@ -151,12 +177,8 @@ conv3d_s1_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tx = blockIdx.x % p.tiles_x, ty = blockIdx.x / p.tiles_x;
-    const int x0 = tx * (p.BW - 2), y0 = ty * p.L;
-    const int d_begin = blockIdx.y * p.dchunk;
-    const int nd = min(p.dchunk, p.Do - d_begin);
-    const int b = blockIdx.z;
     const int MB = p.MB;
+    const int tiles = p.tiles_x * p.tiles_y;
     uint32_t tmem_cols = 32;
     while ((int)tmem_cols < 2 * MB * NOUT) tmem_cols <<= 1;
 
@@ -178,89 +200,137 @@ conv3d_s1_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // item -> (b, d_begin, nd, x0, y0)
+    auto decode = [&](int item, int& b, int& d_begin, int& nd, int& x0, int& y0) {
+        const int t = item % tiles, r = item / tiles;
+        const int c = r % p.nchunks;
+        b = r / p.nchunks;
+        d_begin = c * p.dchunk;
+        nd = min(p.dchunk, p.Do - d_begin);
+        x0 = (t % p.tiles_x) * (p.BW - 2);
+        y0 = (t / p.tiles_x) * p.L;
+    };
+
     if (warp == 0) {
         // ===================================== TMA producer =====================================
-        if (lane == 0) {
+        if (elect_one()) {
             mbar_expect_tx(wfull, W_BYTES);
             for (int tap = 0; tap < 27; ++tap)
                 tma_load_2d(w_smem + tap * W_TAP_BYTES, &tm_w, wfull, 0, tap * p.n_rows + p.w_row0);
-            const uint32_t box_bytes = (uint32_t)ROWB * p.BW * (p.L + 2);
-            for (int s = 0; s < nd + 2; ++s) {          // input planes d_begin+off_d+s, s = 0 .. nd+1
-                const int slot = s % kSlots3;
-                if (s >= kSlots3) mbar_wait(empty + slot, ((s / kSlots3) - 1) & 1);
-                mbar_expect_tx(full + slot, box_bytes);
-                tma_load_5d(slab_smem + (size_t)slot * p.slab_bytes, &tm_x, full + slot, 0, x0 + p.off_w, y0 + p.off_h,
-                            d_begin + p.off_d + s, b);
-            }
         }
         __syncwarp();
+        const uint32_t box_bytes = (uint32_t)ROWB * p.BW * (p.L + 2);
+        int gs = 0;                                      // slabs loaded so far (all items)
+        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+            int b, d_begin, nd, x0, y0;
+            decode(item, b, d_begin, nd, x0, y0);
+            for (int s = 0; s < nd + 2; ++s, ++gs) {     // input planes d_begin+off_d+s
+                const int slot = gs % kSlots3;
+                if (gs >= kSlots3) mbar_wait(empty + slot, ((gs / kSlots3) - 1) & 1);
+                if (elect_one()) {
+                    mbar_expect_tx(full + slot, box_bytes);
+                    tma_load_5d(slab_smem + (size_t)slot * p.slab_bytes, &tm_x, full + slot, 0, x0 + p.off_w, y0 + p.off_h,
+                                d_begin + p.off_d + s, b);
+                }
+                __syncwarp();
+            }
+        }
     } else if (warp == 1) {
         // ===================================== MMA issuer =======================================
-        if (lane == 0) {
-            mbar_wait(wfull, 0);
-            const uint32_t w_addr = smem_u32(w_smem), slab_addr = smem_u32(slab_smem);
-            int landed = 0;                              // slabs s < landed have been waited for
-            for (int d = 0; d < nd; ++d) {
-                const int stage = d & 1;
-                if (d >= 2) mbar_wait(tempty + stage, ((d >> 1) - 1) & 1);
-                while (landed <= d + 2) { mbar_wait(full + landed % kSlots3, (landed / kSlots3) & 1); ++landed; }
+        mbar_wait(wfull, 0);
+        const uint64_t d0 = umma_desc<ROWB>(0);
+        const uint32_t desc_hi = (uint32_t)(d0 >> 32);
+        const uint32_t w_lo = (uint32_t)d0 | (smem_u32(w_smem) >> 4);
+        const uint32_t slab_lo = (uint32_t)d0 | (smem_u32(slab_smem) >> 4);
+        const uint32_t bw16 = (uint32_t)(p.BW * ROWB) >> 4, slab16 = (uint32_t)p.slab_bytes >> 4;
+        int gs0 = 0, gp = 0, landed = 0;                 // first slab of the item, planes issued, slabs waited for
+        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+            int b, d_begin, nd, x0, y0;
+            decode(item, b, d_begin, nd, x0, y0);
+            for (int d = 0; d < nd; ++d, ++gp) {
+                const int stage = gp & 1;
+                if (gp >= 2) mbar_wait(tempty + stage, ((gp >> 1) - 1) & 1);
+                while (landed <= gs0 + d + 2) { mbar_wait(full + landed % kSlots3, (landed / kSlots3) & 1); ++landed; }
                 tc_fence_after();
-                for (int mb = 0; mb < MB; ++mb) {
-                    const uint32_t d_tmem = tmem_base + (uint32_t)((stage * MB + mb) * NOUT);
-                    uint32_t acc = 0;
-                    for (int kd = 0; kd < 3; ++kd) {
-                        const uint32_t slab = slab_addr + (uint32_t)(((d + kd) % kSlots3) * p.slab_bytes);
-                        for (int kh = 0; kh < 3; ++kh) {
+                if (elect_one()) {
+                    uint32_t slot_lo[3];
 #pragma unroll
-                            for (int kw = 0; kw < 3; ++kw) {
-                                const uint32_t a_addr = slab + (uint32_t)((mb * 128 + kh * p.BW + kw) * ROWB);
-                                const uint32_t b_addr = w_addr + (uint32_t)(((kd * 3 + kh) * 3 + kw) * W_TAP_BYTES);
+                    for (int kd = 0; kd < 3; ++kd) slot_lo[kd] = slab_lo + (uint32_t)((gs0 + d + kd) % kSlots3) * slab16;
+                    for (int mb = 0; mb < MB; ++mb) {
+                        const uint32_t d_tmem = tmem_base + (uint32_t)((stage * MB + mb) * NOUT);
+                        const uint32_t mb16 = (uint32_t)(mb * 128 * ROWB) >> 4;
 #pragma unroll
-                                for (int k = 0; k < KSTEPS; ++k) {
-                                    umma_bf16(d_tmem, umma_desc<ROWB>(a_addr + k * 32),
-                                              umma_desc<ROWB>(b_addr + k * 32), IDESC, acc);
-                                    acc = 1;
+                        for (int kd = 0; kd < 3; ++kd) {
+#pragma unroll
+                            for (int kh = 0; kh < 3; ++kh) {
+                                const uint32_t row_lo = slot_lo[kd] + mb16 + kh * bw16;
+#pragma unroll
+                                for (int kw = 0; kw < 3; ++kw) {
+#pragma unroll
+                                    for (int k = 0; k < KSTEPS; ++k) {
+                                        umma_bf16_lohi(d_tmem, row_lo + (uint32_t)((kw * ROWB + k * 32) >> 4), desc_hi,
+                                                       w_lo + (uint32_t)((((kd * 3 + kh) * 3 + kw) * W_TAP_BYTES + k * 32) >> 4),
+                                                       desc_hi, IDESC, (kd | kh | kw | k) != 0);
+                                    }
+                                }
+                            }
+                        }
+                    }
+                    umma_commit(empty + (gs0 + d) % kSlots3);      // input plane s = d is not read after this output plane
+                    if (d == nd - 1) {                               // end of the run: its two trailing halo planes too
+                        umma_commit(empty + (gs0 + nd) % kSlots3);
+                        umma_commit(empty + (gs0 + nd + 1) % kSlots3);
+                    }
+                    umma_commit(tfull + stage);
+                }
+                __syncwarp();
+            }
+            gs0 += nd + 2;
+        }
+    } else {
+        // ===================================== epilogue =========================================
+        const int q = warp & 3;                          // TMEM lane quarter this warp may access
+        int rel[kMaxMB], ti[kMaxMB], tj[kMaxMB];          // this thread's row of each 128-row block inside the tile
+#pragma unroll
+        for (int mb = 0; mb < kMaxMB; ++mb) {
+            const int m = mb * 128 + q * 32 + lane;
+            tj[mb] = m / p.BW; ti[mb] = m - tj[mb] * p.BW;
+            rel[mb] = (ti[mb] < p.BW - 2 && tj[mb] < p.L) ? (tj[mb] * p.Wo + ti[mb]) * p.y_cs : -1;
+        }
+        int gp = 0;
+        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+            int b, d_begin, nd, x0, y0;
+            decode(item, b, d_begin, nd, x0, y0);
+            for (int d = 0; d < nd; ++d, ++gp) {
+                const int stage = gp & 1;
+                mbar_wait(tfull + stage, (gp >> 1) & 1);
+                tc_fence_after();
+                __nv_bfloat16* plane0 = p.y + ((((size_t)b * p.Do + d_begin + d) * p.Ho + y0) * p.Wo + x0) * p.y_cs + p.y_coff;
+#pragma unroll
+                for (int mb = 0; mb < kMaxMB; ++mb) {
+                    if (mb < MB) {
+                        uint32_t v[NOUT];
+                        tmem_ld<NOUT>(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((stage * MB + mb) * NOUT), v);
+                        tmem_ld_wait();
+                        if (rel[mb] >= 0 && x0 + ti[mb] < p.Wo && y0 + tj[mb] < p.Ho) {
+                            __nv_bfloat16* row = plane0 + rel[mb];
+#pragma unroll
+                            for (int c = 0; c < NOUT; c += 8) {
+                                if (c < p.cout) {
+                                    const uint4 o = make_uint4(pack_bf16x2(__uint_as_float(v[c]), __uint_as_float(v[c + 1])),
+                                                               pack_bf16x2(__uint_as_float(v[c + 2]), __uint_as_float(v[c + 3])),
+                                                               pack_bf16x2(__uint_as_float(v[c + 4]), __uint_as_float(v[c + 5])),
+                                                               pack_bf16x2(__uint_as_float(v[c + 6]), __uint_as_float(v[c + 7])));
+                                    *reinterpret_cast<uint4*>(row + c) = o;
                                 }
                             }
                         }
                     }
                 }
-                umma_commit(empty + d % kSlots3);        // input plane s = d is not needed after this output plane
-                umma_commit(tfull + stage);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty + stage);
             }
-        }
-        __syncwarp();
-    } else {
-        // ===================================== epilogue =========================================
-        const int q = warp & 3;                          // TMEM lane quarter this warp may access
-        for (int d = 0; d < nd; ++d) {
-            const int stage = d & 1;
-            mbar_wait(tfull + stage, (d >> 1) & 1);
-            tc_fence_after();
-            for (int mb = 0; mb < MB; ++mb) {
-                const int m = mb * 128 + q * 32 + lane;
-                const int j = m / p.BW, i = m - j * p.BW;
-                const bool valid = i < p.BW - 2 && j < p.L && x0 + i < p.Wo && y0 + j < p.Ho;
-                uint32_t v[NOUT];
-                tmem_ld<NOUT>(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((stage * MB + mb) * NOUT), v);
-                tmem_ld_wait();
-                if (valid) {
-                    __nv_bfloat16* row = p.y + ((((size_t)b * p.Do + d_begin + d) * p.Ho + y0 + j) * p.Wo + x0 + i) * p.y_cs + p.y_coff;
-#pragma unroll
-                    for (int c = 0; c < NOUT; c += 8) {
-                        if (c < p.cout) {
-                            const uint4 o = make_uint4(pack_bf16x2(__uint_as_float(v[c]), __uint_as_float(v[c + 1])),
-                                                       pack_bf16x2(__uint_as_float(v[c + 2]), __uint_as_float(v[c + 3])),
-                                                       pack_bf16x2(__uint_as_float(v[c + 4]), __uint_as_float(v[c + 5])),
-                                                       pack_bf16x2(__uint_as_float(v[c + 6]), __uint_as_float(v[c + 7])));
-                            *reinterpret_cast<uint4*>(row + c) = o;
-                        }
-                    }
-                }
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tempty + stage);
         }
     }
 
@@ -360,14 +430,31 @@ int launch_conv(const void* x, const void* w, void* y, int B, int Di, int Hi, in
     p.cout = cout; p.y_cs = y_cs; p.y_coff = y_coff; p.n_rows = n_rows; p.w_row0 = w_row0;
     p.slab_bytes = tp.slab_bytes;
     p.y = reinterpret_cast<__nv_bfloat16*>(y);
-    // depth runs: enough CTAs for ~2 waves of 148 SMs, but long runs (each run re-loads 2 halo planes)
-    const long tiles = (long)tp.tiles_x * tp.tiles_y * B;
-    long nchunks = (2L * 148 + tiles - 1) / tiles;
-    if (nchunks > (Do + 7) / 8) nchunks = (Do + 7) / 8;
-    if (nchunks < 1) nchunks = 1;
-    p.dchunk = (int)((Do + nchunks - 1) / nchunks);
-    if (const char* e = getenv("MVSB200_CONV_DCHUNK")) { int v = atoi(e); if (v > 0) p.dchunk = v; }
-    const dim3 grid((unsigned)(tp.tiles_x * tp.tiles_y), (unsigned)((Do + p.dchunk - 1) / p.dchunk), (unsigned)B);
+    // depth runs: an item costs (planes + 2 halo planes + ~2 planes of pipeline fill); CTAs are persistent, one per SM,
+    // so pick the run length that minimises (items per CTA) x (cost per item)
+    const long tiles = (long)tp.tiles_x * tp.tiles_y;
+    int sms = 148;
+    {
+        int dev = 0, n = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) sms = n;
+    }
+    long best_cost = -1;
+    int best_chunks = 1;
+    for (int nc = 1; nc <= Do; ++nc) {
+        const int dc = (Do + nc - 1) / nc;
+        if ((long)(nc - 1) * dc >= Do) continue;           // would leave an empty run
+        const long items = tiles * nc * B;
+        const long cost = ((items + sms - 1) / sms) * (dc + 4);
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_chunks = nc; }
+    }
+    p.nchunks = best_chunks;
+    p.dchunk = (Do + best_chunks - 1) / best_chunks;
+    if (const char* e = getenv("MVSB200_CONV_DCHUNK")) {
+        int v = atoi(e);
+        if (v > 0) { p.dchunk = v < Do ? v : Do; p.nchunks = (Do + p.dchunk - 1) / p.dchunk; }
+    }
+    p.n_items = (int)(tiles * p.nchunks * B);
+    const dim3 grid((unsigned)(p.n_items < sms ? p.n_items : sms), 1, 1);
     const size_t smem = 1024 + W_BYTES_AL + (size_t)kSlots3 * tp.slab_bytes + 256;
     MVS_CUDA(cudaFuncSetAttribute(conv3d_s1_tc_kernel<CIN, NOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     conv3d_s1_tc_kernel<CIN, NOUT><<<grid, kTcThreads, smem, st>>>(tm_x, tm_w, p);
@@ -387,19 +474,23 @@ extern "C" int mvsb200_conv3d_s1_fwd(const void* x, const void* w_packed, void* 
                 "conv3d_s1_fwd: cout must be a multiple of 8 and n_rows a multiple of 16 <= 64 (cout=%d n_rows=%d)", cout, n_rows);
     MVS_REQUIRE(y_cs >= cout && y_cs % 8 == 0, "conv3d_s1_fwd: output channel stride %d", y_cs);
     cudaStream_t st = (cudaStream_t)stream;
-#define MVS_CONV(CI, NO) return launch_conv<CI, NO>(x, w_packed, y, B, Di, Hi, Wi, Do, Ho, Wo, cout, y_cs, 0, n_rows, 0, off_d, off_h, off_w, st)
-    if (Cin == 16 && n_rows == 16) MVS_CONV(16, 16);
-    if (Cin == 16 && n_rows == 32) MVS_CONV(16, 32);
-    if (Cin == 32 && n_rows == 16) MVS_CONV(32, 16);
-    if (Cin == 32 && n_rows == 32) MVS_CONV(32, 32);
-    if (Cin == 64 && n_rows == 32) MVS_CONV(64, 32);
-    if (Cin == 64 && n_rows == 64) {                     // 64 -> 64: two N = 32 halves (filter does not fit at N = 64)
-        int rc = launch_conv<64, 32>(x, w_packed, y, B, Di, Hi, Wi, Do, Ho, Wo, cout < 32 ? cout : 32, y_cs, 0, n_rows, 0,
-                                     off_d, off_h, off_w, st);
-        if (rc != MVSB200_OK || cout <= 32) return rc;
-        return launch_conv<64, 32>(x, w_packed, y, B, Di, Hi, Wi, Do, Ho, Wo, cout - 32, y_cs, 32, n_rows, 32, off_d, off_h,
-                                   off_w, st);
-    }
+    // N (filter rows per launch) is 16 or 32; a 64-row filter runs as two 32-row halves (all 27 taps of a 64 x 64
+    // filter do not fit next to the slab ring; at N = 32 the tensor pipe is fed from shared memory at the same rate)
+    for (int row0 = 0; row0 < n_rows && row0 < cout; row0 += 32) {
+        const int nout = n_rows - row0 < 32 ? n_rows - row0 : 32;
+        const int c_here = cout - row0 < nout ? cout - row0 : nout;
+        int rc = MVSB200_E_UNSUPPORTED;
+#define MVS_CONV(CI, NO) \
+    rc = launch_conv<CI, NO>(x, w_packed, y, B, Di, Hi, Wi, Do, Ho, Wo, c_here, y_cs, row0, n_rows, row0, off_d, off_h, off_w, st)
+        if (Cin == 16 && nout == 16) MVS_CONV(16, 16);
+        else if (Cin == 16 && nout == 32) MVS_CONV(16, 32);
+        else if (Cin == 32 && nout == 16) MVS_CONV(32, 16);
+        else if (Cin == 32 && nout == 32) MVS_CONV(32, 32);
+        else if (Cin == 64 && nout == 16) MVS_CONV(64, 16);
+        else if (Cin == 64 && nout == 32) MVS_CONV(64, 32);
+        else MVS_FAIL(MVSB200_E_UNSUPPORTED, "conv3d_s1_fwd: unsupported channels Cin=%d n_rows=%d", Cin, n_rows);
 #undef MVS_CONV
-    MVS_FAIL(MVSB200_E_UNSUPPORTED, "conv3d_s1_fwd: unsupported channels Cin=%d n_rows=%d", Cin, n_rows);
+        if (rc != MVSB200_OK) return rc;
+    }
+    return MVSB200_OK;
 }
