@@ -56,7 +56,10 @@ class MVSNet(nn.Module):
         self.depthmap_refine = DepthRefinement()
 
     def forward(self, nn_input, K_batch, R_batch, T_batch, d_min, d_int, batch_size, n_views):
-        feats = self.feature_encoder(nn_input)
+        amp = self.precision == "bf16" and nn_input.is_cuda
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):        # out-of-scope 2D net: stock torch AMP
+            feats = self.feature_encoder(nn_input.contiguous(memory_format=torch.channels_last))
+        feats = feats.float()
         warped, d_batch, ref_views = api.homography_warping(K_batch, R_batch, T_batch, d_min, d_int, feats,
                                                             batch_size, n_views, self.d_num, self.d_scale)
         vol_dtype = torch.bfloat16 if self.precision == "bf16" else torch.float32
@@ -69,7 +72,9 @@ class MVSNet(nn.Module):
         norm = (initial - d_trans) / d_span
         h, w = initial.shape[-2:]
         ref_img = F.interpolate(nn_input[ref_views.to(dev)], (h, w), mode="bilinear", align_corners=False)
-        refined = self.depthmap_refine(torch.cat((norm, ref_img), 1)) * d_span + d_trans
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
+            refined = self.depthmap_refine(torch.cat((norm, ref_img), 1))
+        refined = refined.float() * d_span + d_trans
         return initial, refined
 
 

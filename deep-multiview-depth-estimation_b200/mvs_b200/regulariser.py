@@ -172,7 +172,7 @@ class CostVolumeReg(nn.Module):
             X = F.pad(a - _bview(bg), bgpad) + _bview(bg)
             X = F.pad(X, zpad)                                                # canvas border -> zero padding
             Wk = self._w(f"conv_{k}_1", dt)
-            T = be.conv3d(X.to(dt), Wk, 1, (0, 0, 0))                         # output exactly on E
+            T = be.conv3d(X.to(dt).contiguous(memory_format=torch.channels_last_3d), Wk, 1, (0, 0, 0))   # output exactly on E
             Tf = T.float()
             if train:
                 mean, var = self._stats_with_constant_outside(Tf, Wk.float(), bg, dims, E_lo, E_hi, B, n_full)
@@ -184,7 +184,8 @@ class CostVolumeReg(nn.Module):
         Lp = tuple(L for _, _, L in reg)
 
         def up(z, name, bn):
-            U = be.conv_transpose3d(z.to(dt), self._w(name, dt), 2, Lp, dims)
+            # channel-last operands keep the library on its NDHWC kernels (no layout-conversion passes over the canvas)
+            U = be.conv_transpose3d(z.to(dt).contiguous(memory_format=torch.channels_last_3d), self._w(name, dt), 2, Lp, dims)
             return self._bn_dense(bn, U)
 
         c3 = up(enc[3], "deconv_3_0", self.BN_2)[(slice(None), slice(None)) + C].float()

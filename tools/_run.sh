@@ -1,3 +1,3 @@
-python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
-python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bench_for_ncu.json 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/launches_r01.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launches.log 2>&1
-python tools/bench_conv_tc.py 1 dense32x32 > gpurun_out/conv_one.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:conv3d_s1_tc -s 3 -c 1 -o gpurun_out/k3_r1a python tools/bench_conv_tc.py 1 dense32x32 > gpurun_out/ncu_k3.log 2>&1
+python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
+python tools/profile_step.py --B 1 --rows 40 > gpurun_out/prof_step_b1_v4.txt 2>&1
+python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench4.json 2> gpurun_out/bench4.err
