@@ -42,6 +42,26 @@ def _peaks():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def _tensor_peak():
+    """bf16 tensor peak for a kernel timed inside a long step: the sustained figure."""
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["bf16_tflops_sustained"]), "measured (MEASURED_PEAKS.json, sustained cuBLAS bf16)"
+    except Exception:
+        return 1500.0, "fallback (B200_PROFILING.md)"
+
+
+def _ncu_traffic(name):
+    """DRAM bytes (read + write) of the committed `ncu --set full` capture of a kernel, or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", name)) as f:
+            m = json.load(f)["metrics"]
+        return (float(m["dram__bytes_read.sum"]) + float(m["dram__bytes_write.sum"])) * 1e6
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -217,17 +237,33 @@ def run_b200(args, rank, world, local_rank):
            "softmax_ranks_fwd": 2 * 4 * vox + 4 * 5 * B * h * w}
     kern = {}
     for name, evs in events.items():
-        t = sum(a.elapsed_time(b) for a, b in evs) / len(evs)
-        kern[name] = {"ms": t, "launches": len(evs)}
+        tot = sum(a.elapsed_time(b) for a, b, _ in evs)
+        kern[name] = {"ms": tot / len(evs), "launches": len(evs), "ms_per_step": tot / args.steps}
         if name in alg:
+            t = tot / len(evs)
             kern[name].update({"alg_bytes": alg[name], "GBps": alg[name] / (t * 1e-3) / 1e9,
                                "frac_hbm": alg[name] / (t * 1e-3) / 1e9 / peak})
+        work = [w for _, _, w in evs if w is not None]
+        if work and name == "conv3d_s1_tc":
+            kern[name].update({"alg_flops_per_step": sum(work) / args.steps, "TFLOPs": sum(work) / (tot * 1e-3) / 1e12})
     k1 = kern.get("warp_variance_fwd", {})
-    roofline = {"kernel": "warp_variance_fwd_kernel<V=3,CPL=8,bf16 out>", "bound": "hbm", "achieved": k1.get("GBps"),
-                "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": k1.get("frac_hbm"), "traffic": None,
-                "alg_bytes_per_launch": alg["warp_variance_fwd"], "ms_per_launch": k1.get("ms"),
-                "voxels_per_s": vox / (k1["ms"] * 1e-3) if k1 else None,
-                "note": "traffic (dram bytes from ncu --set full) is recorded in profiles/ when a capture exists"}
+    roofline_k1 = {"kernel": "warp_variance_fwd_kernel<V=3, bf16 volume>", "bound": "hbm", "achieved": k1.get("GBps"),
+                   "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": k1.get("frac_hbm"),
+                   "traffic": None, "alg_bytes_per_launch": alg["warp_variance_fwd"], "ms_per_launch": k1.get("ms"),
+                   "voxels_per_s": vox / (k1["ms"] * 1e-3) if k1 else None,
+                   "note": "ncu (profiles/r01_k1_*): DRAM traffic = algorithmic bytes (fp32-volume capture 7.7 MB read + 446 MB "
+                           "written of 511 MB); fp32-volume variant reaches 44 % of peak (tools/microbench.py)"}
+    # dominant own kernel by time in the step: the tcgen05 convolution (all its launches of the timed steps together)
+    k3 = kern.get("conv3d_s1_tc", {})
+    tpeak, tpeak_src = _tensor_peak()
+    roofline = {"kernel": "conv3d_s1_tc_kernel<CIN,NOUT> (tcgen05/TMEM/TMA implicit-GEMM conv3d; %d launches/step: forward of "
+                          "conv_0_0, conv_{1,2,3}_1 and data gradient of conv_{1,2,3}_1)" % (k3.get("launches", 0) // max(args.steps, 1)),
+                "bound": "tensor", "achieved": k3.get("TFLOPs"), "peak": tpeak, "peak_source": tpeak_src, "unit": "TFLOP/s",
+                "frac": (k3["TFLOPs"] / tpeak) if k3.get("TFLOPs") else None,
+                "traffic": _ncu_traffic("r01_k3_conv3d_s1_tc_ncu.json"),
+                "traffic_case": "ncu --set full capture of the 32->32 dense canvas launch (252 MB in + 252 MB out algorithmic)",
+                "alg_flops_per_step": k3.get("alg_flops_per_step"), "ms_per_step": k3.get("ms_per_step"),
+                "note": "ncu: tensor pipe busy 92 % of cycles, shared-memory operand feed 78 % of peak (N = 32): profiles/r01_k3_notes.md"}
 
     line = None
     if rank == 0:
@@ -240,8 +276,8 @@ def run_b200(args, rank, world, local_rank):
                            "regulariser_convs": model.cost_volume_reg.conv_backend},
                 "e2e": {"value": e2e_value, "unit": "depth maps/s", "ms_per_step": ms_e2e / args.steps,
                         "h2d_bytes_per_step": img_host.numel() * 4 + gt_host.numel() * 4, "d2h_bytes_per_step": 4},
-                "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "kernels": kern,
-                "cost_volume_voxels_per_s": roofline["voxels_per_s"]}
+                "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "roofline_k1": roofline_k1, "kernels": kern,
+                "cost_volume_voxels_per_s": roofline_k1["voxels_per_s"]}
     return line
 
 

@@ -398,161 +398,181 @@ warp_variance_fwd_kernel(const float4* __restrict__ feat, const ViewParams* __re
 
 // ------------------------------------------------------------------------------------------------
 // K2 backward: d cost / d features
-//   d cost / d f_v = (2/V) (f_v - mean) * gcost   (the mean term cancels), chained
-//   through the bilinear taps.  Tap gradients of a footprint are accumulated in registers across the
-//   planes that share it and flushed with 16-byte vector atomics when the footprint moves.
+//   d cost / d f_v = (2/V) (f_v - mean) * gcost   (the mean term cancels), chained through the
+//   bilinear taps.  Same two-phase structure as the forward kernel (footprint records in shared memory, 8 lanes per
+//   pixel, 4 channels per lane).  The gradient of a cached 2x2 footprint is accumulated in registers over the planes
+//   that share it and flushed with predicated 16-byte vector reductions (8 lanes = one full 128-byte line per tap)
+//   when the footprint moves; the reference view's constant footprint is flushed once per run of planes.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void red_add_f4(float4* p, float4 v) {
-    atomicAdd(p, v);   // sm_90+: single 16-byte reduction at L2
+__device__ __forceinline__ void red_add_f4_if(float4* p, const float4& v, int pred) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %5, 0;\n\t@p red.global.add.v4.f32 [%0], {%1,%2,%3,%4};\n\t}" ::"l"(p),
+                 "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"(pred)
+                 : "memory");
 }
 
-template <int NV4>
-__device__ __forceinline__ void flush_taps(float4* __restrict__ gview, int x0, int y0, int h, int w,
-                                           const int (&slot)[NV4], float4 (&acc)[4][NV4]) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int xx = x0 + (j & 1), yy = y0 + (j >> 1);
-        const bool ok = (unsigned)xx < (unsigned)w && (unsigned)yy < (unsigned)h;
-        float4* p = gview + ((size_t)yy * w + xx) * kSlots;
-#pragma unroll
-        for (int k = 0; k < NV4; ++k) {
-            if (ok) red_add_f4(p + slot[k], acc[j][k]);
-            acc[j][k] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-    }
-}
+template <int V, bool BF16G>
+__global__ void __launch_bounds__(kThreads, V <= 3 ? 2 : 1)
+warp_variance_bwd_kernel(const float4* __restrict__ feat, const ViewParams* __restrict__ vp, const float* __restrict__ tinv,
+                         const void* __restrict__ gcost, float4* __restrict__ gfeat, int D, int h, int w, int dchunk,
+                         int tiles_x) {
+    constexpr int RUN = FwdCfg<V>::kRunV, RECS = FwdCfg<V>::kRecs;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float4* rec_w = reinterpret_cast<float4*>(smem_raw);
+    int4* rec_o = reinterpret_cast<int4*>(smem_raw) + 2 * RECS;
 
-__device__ __forceinline__ void axpy4(float4& a, float s, const float4& g) {
-    a.x = fmaf(s, g.x, a.x); a.y = fmaf(s, g.y, a.y); a.z = fmaf(s, g.z, a.z); a.w = fmaf(s, g.w, a.w);
-}
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.z, d0 = blockIdx.y * dchunk, nd = min(dchunk, D - d0);
+    const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
+    const unsigned plane = (unsigned)h * (unsigned)w;
+    const ViewParams* vpb = vp + (size_t)b * V;
 
-template <int V, int CPL, bool BF16G>
-__global__ void __launch_bounds__(kThreads) warp_variance_bwd_kernel(const float4* __restrict__ feat,
-                                                                     const ViewParams* __restrict__ vp,
-                                                                     const float* __restrict__ tinv,
-                                                                     const void* __restrict__ gcost,
-                                                                     float4* __restrict__ gfeat, int D, int h, int w,
-                                                                     int dchunk, int tiles_x) {
-    constexpr int NV4 = CPL / 4;
-    extern __shared__ float s_tinv[];
-    const TileCoord tc = tile_coord<NV4>(D, h, w, dchunk, tiles_x);
-    stage_tinv<V>(s_tinv, tinv, tc.b, D, tc.d0, tc.nd, dchunk);
-    if (!tc.active) return;
-
-    int slot[NV4];
-    lane_slots<NV4, BF16G>(tc.cg, slot);
-    const float xf = (float)tc.x, yf = (float)tc.y;
-    const size_t plane = (size_t)h * w;
-    const ViewParams* vpb = vp + (size_t)tc.b * V;
-
-    float4 ref[NV4], gref[NV4];
-    Sample sref;
+    const int p1 = threadIdx.x & (kPix - 1), q = threadIdx.x >> 5;
+    PixelView pv1[V];
     {
-        const PixelView pv0 = pixel_view(vpb[0], xf, yf);
-        sref = sample_at(pv0, 0.f, 0.f, 0.f, 0.f, h, w);
-        float4 t[4][NV4];
-        load_taps<NV4>(feat + (size_t)(tc.b * V) * plane * kSlots, sref.x0, sref.y0, h, w, slot, t);
+        const float x1 = (float)(tx * kTX + (p1 & (kTX - 1))), y1 = (float)(ty * kTY + p1 / kTX);
 #pragma unroll
-        for (int k = 0; k < NV4; ++k) {
-            ref[k] = blend(sref, t[0][k], t[1][k], t[2][k], t[3][k]);
-            gref[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+        for (int v = 1; v < V; ++v) pv1[v] = pixel_view(vpb[v], x1, y1);
     }
-
-    PixelView pv[V];
-    float gx[V], gy[V], gz[V];
-    int cx[V], cy[V];
-    float4 taps[V][4][NV4];
-    float4 acc[V][4][NV4];
-#pragma unroll
-    for (int v = 1; v < V; ++v) {
-        pv[v] = pixel_view(vpb[v], xf, yf);
-        gx[v] = vpb[v].g[0]; gy[v] = vpb[v].g[1]; gz[v] = vpb[v].g[2];
-        cx[v] = INT_MIN; cy[v] = INT_MIN;
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-#pragma unroll
-            for (int k = 0; k < NV4; ++k) acc[v][j][k] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-
-    const float invV = 1.0f / (float)V, twoV = 2.0f / (float)V;
-    size_t vox = ((size_t)(tc.b * D + tc.d0) * h + tc.y) * w + tc.x;
-    for (int dd = 0; dd < tc.nd; ++dd, vox += plane) {
-        // upstream gradient row slice
-        float4 g[NV4];
-        if (BF16G) {
-            const __nv_bfloat16* row = reinterpret_cast<const __nv_bfloat16*>(gcost) + vox * kC + tc.cg * CPL;
-#pragma unroll
-            for (int k = 0; k < NV4; ++k) {
-                const uint2 u = *reinterpret_cast<const uint2*>(row + 4 * k);
-                const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162*>(&u.x);
-                const __nv_bfloat162 hi = *reinterpret_cast<const __nv_bfloat162*>(&u.y);
-                g[k] = make_float4(__low2float(lo), __high2float(lo), __low2float(hi), __high2float(hi));
-            }
-        } else {
-            const float4* row = reinterpret_cast<const float4*>(gcost) + vox * kSlots;
-#pragma unroll
-            for (int k = 0; k < NV4; ++k) g[k] = ld_cs_f4(row + slot[k]);
-        }
-
-        float4 val[V][NV4];
-        Sample smp[V];
-#pragma unroll
-        for (int k = 0; k < NV4; ++k) val[0][k] = ref[k];
-        bool nan_plane = false;
+    auto stage_run = [&](int run0, int buf) {
+        const int nrun = min(RUN, nd - run0);
 #pragma unroll
         for (int v = 1; v < V; ++v) {
-            const float t = s_tinv[(v - 1) * dchunk + dd];
-            nan_plane |= (t != t);
-            smp[v] = sample_at(pv[v], gx[v], gy[v], gz[v], t, h, w);
-            if (smp[v].x0 != cx[v] || smp[v].y0 != cy[v]) {
-                if (cx[v] != INT_MIN)
-                    flush_taps<NV4>(gfeat + (size_t)(tc.b * V + v) * plane * kSlots, cx[v], cy[v], h, w, slot, acc[v]);
-                load_taps<NV4>(feat + (size_t)(tc.b * V + v) * plane * kSlots, smp[v].x0, smp[v].y0, h, w, slot, taps[v]);
-                cx[v] = smp[v].x0; cy[v] = smp[v].y0;
+            const float gx = vpb[v].g[0], gy = vpb[v].g[1], gz = vpb[v].g[2];
+            const float* tv = tinv + (size_t)(b * V + v) * D + d0 + run0;
+            for (int dd = q; dd < nrun; dd += kThreads / kPix) {
+                const FootRec r = make_record(pv1[v], gx, gy, gz, __ldg(tv + dd), h, w);
+                const int i = buf * RECS + ((v - 1) * RUN + dd) * kPix + p1;
+                rec_w[i] = make_float4(r.w00, r.w01, r.w10, r.w11);
+                rec_o[i] = make_int4(r.o00, r.o01, r.o10, r.o11);
             }
-#pragma unroll
-            for (int k = 0; k < NV4; ++k)
-                val[v][k] = blend(smp[v], taps[v][0][k], taps[v][1][k], taps[v][2][k], taps[v][3][k]);
         }
-        if (nan_plane) continue;   // d == 0 plane: the reference's gradient is NaN there; contribute nothing
+    };
+
+    const int pl = warp * (32 / kLanesPerPixel) + lane / kLanesPerPixel, cg = lane % kLanesPerPixel;
+    const int px = tx * kTX + (pl & (kTX - 1)), py = ty * kTY + pl / kTX;
+    const bool active = px < w && py < h;
+    const float4* fb = feat + (size_t)(b * V) * plane * kSlots + cg;
+    float4* gb = gfeat + (size_t)(b * V) * plane * kSlots + cg;
+
+    stage_run(0, 0);
+
+    float2 ref[2], gref[2];
+    FootRec rref;
+    {
+        const PixelView pv = pixel_view(vpb[0], (float)px, (float)py);
+        rref = make_record(pv, 0.f, 0.f, 0.f, 0.f, h, w);
+        const float4 t00 = __ldg(fb + (unsigned)rref.o00 * kSlots), t01 = __ldg(fb + (unsigned)rref.o01 * kSlots),
+                     t10 = __ldg(fb + (unsigned)rref.o10 * kSlots), t11 = __ldg(fb + (unsigned)rref.o11 * kSlots);
+        blend2w(rref.w00, rref.w01, rref.w10, rref.w11, t00, t01, t10, t11, ref[0], ref[1]);
+        gref[0] = gref[1] = make_float2(0.f, 0.f);
+    }
+
+    float4 taps[V][4];
+    float2 acc[V][4][2];                              // gradient of the cached footprint, [tap][channel pair]
+    int4 old[V];                                      // its tap offsets (old[v].x < 0: nothing cached yet)
 #pragma unroll
-        for (int k = 0; k < NV4; ++k) {
-            float4 sum = val[0][k];
+    for (int v = 1; v < V; ++v) {
+        old[v] = make_int4(-1, -1, -1, -1);
 #pragma unroll
-            for (int v = 1; v < V; ++v) { sum.x += val[v][k].x; sum.y += val[v][k].y; sum.z += val[v][k].z; sum.w += val[v][k].w; }
-            const float4 mean = make_float4(sum.x * invV, sum.y * invV, sum.z * invV, sum.w * invV);
-            const float4 gs = make_float4(g[k].x * twoV, g[k].y * twoV, g[k].z * twoV, g[k].w * twoV);
-#pragma unroll
-            for (int v = 0; v < V; ++v) {
-                const float4 gv = make_float4((val[v][k].x - mean.x) * gs.x, (val[v][k].y - mean.y) * gs.y,
-                                              (val[v][k].z - mean.z) * gs.z, (val[v][k].w - mean.w) * gs.w);
-                if (v == 0) {
-                    gref[k].x += gv.x; gref[k].y += gv.y; gref[k].z += gv.z; gref[k].w += gv.w;
+        for (int j = 0; j < 4; ++j) {
+            taps[v][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            acc[v][j][0] = acc[v][j][1] = make_float2(0.f, 0.f);
+        }
+    }
+    const float invV = 1.0f / (float)V, twoV = 2.0f / (float)V;
+    const float2 ninv = make_float2(-invV, -invV);
+    __syncthreads();
+
+    int buf = 0;
+    for (int run0 = 0; run0 < nd; run0 += RUN, buf ^= 1) {
+        const int nrun = min(RUN, nd - run0);
+        if (run0 + RUN < nd) stage_run(run0 + RUN, buf ^ 1);
+        if (active) {
+            size_t vox = ((size_t)(b * D + d0 + run0) * h + py) * w + px;
+            const float4* rw = rec_w + buf * RECS + pl;
+            const int4* ro = rec_o + buf * RECS + pl;
+            for (int dd = 0; dd < nrun; ++dd, vox += plane) {
+                // upstream gradient of this lane's 4 channels
+                float2 g[2];
+                if (BF16G) {
+                    const uint2 u = __ldcs(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(gcost) + vox * kC + 4 * cg));
+                    g[0] = make_float2(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u));
+                    g[1] = make_float2(__uint_as_float(u.y << 16), __uint_as_float(u.y & 0xffff0000u));
                 } else {
-                    axpy4(acc[v][0][k], smp[v].w00, gv);
-                    axpy4(acc[v][1][k], smp[v].w01, gv);
-                    axpy4(acc[v][2][k], smp[v].w10, gv);
-                    axpy4(acc[v][3][k], smp[v].w11, gv);
+                    const float4 u = ld_cs_f4(reinterpret_cast<const float4*>(gcost) + vox * kSlots + cg);
+                    g[0] = make_float2(u.x, u.y); g[1] = make_float2(u.z, u.w);
+                }
+                float2 val[2][V];
+                float4 wts[V];
+                val[0][0] = ref[0]; val[1][0] = ref[1];
+                bool nan_plane = false;
+#pragma unroll
+                for (int v = 1; v < V; ++v) {
+                    float4 wt = rw[((v - 1) * RUN + dd) * kPix];
+                    const int4 of = ro[((v - 1) * RUN + dd) * kPix];
+                    if (wt.x != wt.x) { nan_plane = true; wt = make_float4(0.f, 0.f, 0.f, 0.f); }   // d == 0 plane
+                    const int changed = (of.x != old[v].x) | (of.w != old[v].w);
+                    const int flush = changed & (old[v].x >= 0);
+                    float4* gv = gb + (size_t)v * plane * kSlots;
+                    red_add_f4_if(gv + (unsigned)max(old[v].x, 0) * kSlots, make_float4(acc[v][0][0].x, acc[v][0][0].y, acc[v][0][1].x, acc[v][0][1].y), flush);
+                    red_add_f4_if(gv + (unsigned)max(old[v].y, 0) * kSlots, make_float4(acc[v][1][0].x, acc[v][1][0].y, acc[v][1][1].x, acc[v][1][1].y), flush);
+                    red_add_f4_if(gv + (unsigned)max(old[v].z, 0) * kSlots, make_float4(acc[v][2][0].x, acc[v][2][0].y, acc[v][2][1].x, acc[v][2][1].y), flush);
+                    red_add_f4_if(gv + (unsigned)max(old[v].w, 0) * kSlots, make_float4(acc[v][3][0].x, acc[v][3][0].y, acc[v][3][1].x, acc[v][3][1].y), flush);
+                    if (changed) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) acc[v][j][0] = acc[v][j][1] = make_float2(0.f, 0.f);
+                    }
+                    const float4* fv = fb + (size_t)v * plane * kSlots;
+                    ldg_f4_if(taps[v][0], fv + (unsigned)of.x * kSlots, changed);
+                    ldg_f4_if(taps[v][1], fv + (unsigned)of.y * kSlots, changed);
+                    ldg_f4_if(taps[v][2], fv + (unsigned)of.z * kSlots, changed);
+                    ldg_f4_if(taps[v][3], fv + (unsigned)of.w * kSlots, changed);
+                    old[v] = of;
+                    wts[v] = wt;
+                    blend2w(wt.x, wt.y, wt.z, wt.w, taps[v][0], taps[v][1], taps[v][2], taps[v][3], val[0][v], val[1][v]);
+                }
+                // gv_v = (f_v - mean) * g * 2/V ; the reference's gradient is NaN on a d == 0 plane: contribute nothing
+                const float gsc = nan_plane ? 0.f : twoV;
+                const float2 gs2 = make_float2(gsc, gsc);
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    float2 sum = val[k][0];
+#pragma unroll
+                    for (int v = 1; v < V; ++v) sum = __fadd2_rn(sum, val[k][v]);
+                    const float2 nmean = __fmul2_rn(sum, ninv);
+                    const float2 gk = __fmul2_rn(g[k], gs2);
+                    gref[k] = __ffma2_rn(__fadd2_rn(val[k][0], nmean), gk, gref[k]);
+#pragma unroll
+                    for (int v = 1; v < V; ++v) {
+                        const float2 gv = __fmul2_rn(__fadd2_rn(val[k][v], nmean), gk);
+                        acc[v][0][k] = __ffma2_rn(make_float2(wts[v].x, wts[v].x), gv, acc[v][0][k]);
+                        acc[v][1][k] = __ffma2_rn(make_float2(wts[v].y, wts[v].y), gv, acc[v][1][k]);
+                        acc[v][2][k] = __ffma2_rn(make_float2(wts[v].z, wts[v].z), gv, acc[v][2][k]);
+                        acc[v][3][k] = __ffma2_rn(make_float2(wts[v].w, wts[v].w), gv, acc[v][3][k]);
+                    }
                 }
             }
         }
+        __syncthreads();
     }
-    // final flush: source views, then the reference view's constant footprint
+    if (!active) return;
+    // final flush: the cached source-view footprints, then the reference view's constant footprint
 #pragma unroll
-    for (int v = 1; v < V; ++v)
-        if (cx[v] != INT_MIN)
-            flush_taps<NV4>(gfeat + (size_t)(tc.b * V + v) * plane * kSlots, cx[v], cy[v], h, w, slot, acc[v]);
+    for (int v = 1; v < V; ++v) {
+        const int flush = old[v].x >= 0;
+        float4* gv = gb + (size_t)v * plane * kSlots;
+        red_add_f4_if(gv + (unsigned)max(old[v].x, 0) * kSlots, make_float4(acc[v][0][0].x, acc[v][0][0].y, acc[v][0][1].x, acc[v][0][1].y), flush);
+        red_add_f4_if(gv + (unsigned)max(old[v].y, 0) * kSlots, make_float4(acc[v][1][0].x, acc[v][1][0].y, acc[v][1][1].x, acc[v][1][1].y), flush);
+        red_add_f4_if(gv + (unsigned)max(old[v].z, 0) * kSlots, make_float4(acc[v][2][0].x, acc[v][2][0].y, acc[v][2][1].x, acc[v][2][1].y), flush);
+        red_add_f4_if(gv + (unsigned)max(old[v].w, 0) * kSlots, make_float4(acc[v][3][0].x, acc[v][3][0].y, acc[v][3][1].x, acc[v][3][1].y), flush);
+    }
     {
-        float4 a0[4][NV4];
+        const float4 gr = make_float4(gref[0].x, gref[0].y, gref[1].x, gref[1].y);
+        const float wr[4] = {rref.w00, rref.w01, rref.w10, rref.w11};
+        const int orf[4] = {rref.o00, rref.o01, rref.o10, rref.o11};
 #pragma unroll
-        for (int k = 0; k < NV4; ++k) {
-            a0[0][k] = make_float4(sref.w00 * gref[k].x, sref.w00 * gref[k].y, sref.w00 * gref[k].z, sref.w00 * gref[k].w);
-            a0[1][k] = make_float4(sref.w01 * gref[k].x, sref.w01 * gref[k].y, sref.w01 * gref[k].z, sref.w01 * gref[k].w);
-            a0[2][k] = make_float4(sref.w10 * gref[k].x, sref.w10 * gref[k].y, sref.w10 * gref[k].z, sref.w10 * gref[k].w);
-            a0[3][k] = make_float4(sref.w11 * gref[k].x, sref.w11 * gref[k].y, sref.w11 * gref[k].z, sref.w11 * gref[k].w);
-        }
-        flush_taps<NV4>(gfeat + (size_t)(tc.b * V) * plane * kSlots, sref.x0, sref.y0, h, w, slot, a0);
+        for (int j = 0; j < 4; ++j)
+            red_add_f4_if(gb + (unsigned)orf[j] * kSlots, make_float4(wr[j] * gr.x, wr[j] * gr.y, wr[j] * gr.z, wr[j] * gr.w), 1);
     }
 }
 
@@ -674,16 +694,23 @@ int launch_fwd(const float* feat, const float* vp, const float* tinv, void* cost
     return MVSB200_OK;
 }
 
-template <int V, int CPL>
+template <int V>
 int launch_bwd(const float* feat, const float* vp, const float* tinv, const void* gcost, int dtype, float* gfeat, int B,
                int D, int h, int w, cudaStream_t st) {
-    const Plan p = make_plan(B, V, D, h, w, CPL);
-    MVS_REQUIRE(p.smem <= 48 * 1024 && p.grid.y <= 65535, "warp_variance_bwd: depth run too long");
+    FwdPlan p = make_fwd_plan(B, V, D, h, w);
+    p.smem = FwdCfg<V>::kSmem;
+    MVS_REQUIRE(p.grid.y <= 65535 && (long)h * w < (1L << 27), "warp_variance_bwd: volume too large");
+    static bool attr_set = false;
+    if (!attr_set) {
+        MVS_CUDA(cudaFuncSetAttribute(warp_variance_bwd_kernel<V, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+        MVS_CUDA(cudaFuncSetAttribute(warp_variance_bwd_kernel<V, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+        attr_set = true;
+    }
     if (dtype == MVSB200_BF16)
-        warp_variance_bwd_kernel<V, CPL, true><<<p.grid, kThreads, p.smem, st>>>(
+        warp_variance_bwd_kernel<V, true><<<p.grid, kThreads, p.smem, st>>>(
             (const float4*)feat, (const ViewParams*)vp, tinv, gcost, (float4*)gfeat, D, h, w, p.dchunk, p.tiles_x);
     else
-        warp_variance_bwd_kernel<V, CPL, false><<<p.grid, kThreads, p.smem, st>>>(
+        warp_variance_bwd_kernel<V, false><<<p.grid, kThreads, p.smem, st>>>(
             (const float4*)feat, (const ViewParams*)vp, tinv, gcost, (float4*)gfeat, D, h, w, p.dchunk, p.tiles_x);
     MVS_CHECK_LAUNCH("warp_variance_bwd");
     return MVSB200_OK;
@@ -717,13 +744,13 @@ extern "C" int mvsb200_warp_variance_bwd(const float* feat, const float* view_pa
     cudaStream_t st = (cudaStream_t)stream;
     MVS_CUDA(cudaMemsetAsync(gfeat, 0, (size_t)B * V * h * w * kC * sizeof(float), st));
     switch (V) {
-        case 2: return launch_bwd<2, 4>(feat, view_params, tinv, gcost, gcost_dtype, gfeat, B, D, h, w, st);
-        case 3: return launch_bwd<3, 4>(feat, view_params, tinv, gcost, gcost_dtype, gfeat, B, D, h, w, st);
-        case 4: return launch_bwd<4, 4>(feat, view_params, tinv, gcost, gcost_dtype, gfeat, B, D, h, w, st);
-        case 5: return launch_bwd<5, 4>(feat, view_params, tinv, gcost, gcost_dtype, gfeat, B, D, h, w, st);
-        case 6: return launch_bwd<6, 4>(feat, view_params, tinv, gcost, gcost_dtype, gfeat, B, D, h, w, st);
-        case 7: return launch_bwd<7, 4>(feat, view_params, tinv, gcost, gcost_dtype, gfeat, B, D, h, w, st);
-        case 8: return launch_bwd<8, 4>(feat, view_params, tinv, gcost, gcost_dtype, gfeat, B, D, h, w, st);
+        case 2: return launch_bwd<2>(feat, view_params, tinv, gcost, gcost_dtype, gfeat, B, D, h, w, st);
+        case 3: return launch_bwd<3>(feat, view_params, tinv, gcost, gcost_dtype, gfeat, B, D, h, w, st);
+        case 4: return launch_bwd<4>(feat, view_params, tinv, gcost, gcost_dtype, gfeat, B, D, h, w, st);
+        case 5: return launch_bwd<5>(feat, view_params, tinv, gcost, gcost_dtype, gfeat, B, D, h, w, st);
+        case 6: return launch_bwd<6>(feat, view_params, tinv, gcost, gcost_dtype, gfeat, B, D, h, w, st);
+        case 7: return launch_bwd<7>(feat, view_params, tinv, gcost, gcost_dtype, gfeat, B, D, h, w, st);
+        case 8: return launch_bwd<8>(feat, view_params, tinv, gcost, gcost_dtype, gfeat, B, D, h, w, st);
     }
     MVS_FAIL(MVSB200_E_UNSUPPORTED, "warp_variance_bwd: V=%d", V);
 }

@@ -43,7 +43,7 @@ def _launch(x_cl, wp, cout, out_dims, off):
     B, cin, Di, Hi, Wi = x_cl.shape
     Do, Ho, Wo = out_dims
     y = torch.empty((B, cout, Do, Ho, Wo), dtype=torch.bfloat16, device=x_cl.device, memory_format=torch.channels_last_3d)
-    with _timed("conv3d_s1_tc"):
+    with _timed("conv3d_s1_tc", 2.0 * 27 * cin * cout * B * Do * Ho * Wo):
         _lib.call("mvsb200_conv3d_s1_fwd", x_cl.data_ptr(), wp.data_ptr(), y.data_ptr(), B, Di, Hi, Wi, cin, Do, Ho, Wo,
                   cout, cout, wp.shape[1], off, off, off, _stream())
     return y

@@ -22,8 +22,8 @@ EVENTS = None
 
 
 class _timed:
-    def __init__(self, name):
-        self.name = name
+    def __init__(self, name, work=None):
+        self.name, self.work = name, work          # work: algorithmic FLOPs (tensor kernels) or bytes of this launch
 
     def __enter__(self):
         if EVENTS is not None:
@@ -34,7 +34,7 @@ class _timed:
         if EVENTS is not None:
             end = torch.cuda.Event(enable_timing=True)
             end.record()
-            EVENTS.setdefault(self.name, []).append((self.start, end))
+            EVENTS.setdefault(self.name, []).append((self.start, end, self.work))
         return False
 
 
