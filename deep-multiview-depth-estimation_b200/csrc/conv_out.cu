@@ -1,0 +1,197 @@
+// K3c: the regulariser's output convolution, 8 -> 1 channels, k = 3, stride 1, padding 1 (sm_100a, SIMT).
+//
+// Reference: scripts/model.py:91 `self.conv_out = conv_layer(base_filt, 1, ...)`, used at :123 on (y1 + y0) before the
+// depth softmax.  With 8 input channels and ONE output channel this is not a tensor-core shape (K = 8 per tap, N = 1);
+// it is 216 MACs per voxel over a 16-byte voxel row -- HBM/L1-bound streaming work.  cuDNN spends 7.3 ms on the forward
+// and 13.7 ms on the two gradients at B = 4 (profiles/r01 step profile); these three kernels do the same in ~1 ms.
+//   fwd    logits[v]   = sum_tap sum_c W[tap][c] * z[v + tap - 1][c]            z: bf16 [B,D,h,w,8]  ->  fp32 [B,D,h,w]
+//   dgrad  gz[v][c]    = sum_tap W[tap][c] * glogits[v - tap + 1]               fp32 [B,D,h,w]       ->  bf16 [B,D,h,w,8]
+//   wgrad  gW[tap][c]  = sum_v glogits[v] * z[v + tap - 1][c]                   deterministic two-stage reduction
+#include "common.cuh"
+
+using namespace mvsb200;
+
+namespace {
+
+constexpr int kCi = 8;
+constexpr int kTaps = 27;
+constexpr int kWn = kTaps * kCi;                 // 216 filter values
+
+__device__ __forceinline__ void bf16x8_to_f32(const uint4& u, float (&v)[8]) {
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        v[2 * i] = __uint_as_float(w[i] << 16);
+        v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+}
+
+// ---- forward: one thread per voxel, 32 x 8 (x, y) tiles, one plane per blockIdx.z -------------------------------
+__global__ void __launch_bounds__(256) conv_out_fwd_kernel(const uint4* __restrict__ z, const float* __restrict__ wt,
+                                                           float* __restrict__ out, int D, int h, int w) {
+    __shared__ __align__(16) float s_w[kWn];
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    if (tid < kWn) s_w[tid] = wt[tid];
+    __syncthreads();
+    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+    const int b = blockIdx.z / D, d = blockIdx.z % D;
+    if (x >= w || y >= h) return;
+    float acc = 0.f;
+#pragma unroll
+    for (int kd = 0; kd < 3; ++kd) {
+        const int dz = d + kd - 1;
+        if ((unsigned)dz >= (unsigned)D) continue;
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+            const int yy = y + kh - 1;
+            if ((unsigned)yy >= (unsigned)h) continue;
+            const uint4* line = z + ((size_t)(b * D + dz) * h + yy) * w;
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+                const int xx = x + kw - 1;
+                if ((unsigned)xx >= (unsigned)w) continue;
+                float v[8];
+                bf16x8_to_f32(__ldg(line + xx), v);
+                const float4 w0 = *reinterpret_cast<const float4*>(s_w + ((kd * 3 + kh) * 3 + kw) * kCi);
+                const float4 w1 = *reinterpret_cast<const float4*>(s_w + ((kd * 3 + kh) * 3 + kw) * kCi + 4);
+                acc = fmaf(v[0], w0.x, acc); acc = fmaf(v[1], w0.y, acc); acc = fmaf(v[2], w0.z, acc); acc = fmaf(v[3], w0.w, acc);
+                acc = fmaf(v[4], w1.x, acc); acc = fmaf(v[5], w1.y, acc); acc = fmaf(v[6], w1.z, acc); acc = fmaf(v[7], w1.w, acc);
+            }
+        }
+    }
+    out[((size_t)(b * D + d) * h + y) * w + x] = acc;
+}
+
+// ---- data gradient: one thread per voxel ----------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) conv_out_dgrad_kernel(const float* __restrict__ g, const float* __restrict__ wt,
+                                                             uint4* __restrict__ gz, int D, int h, int w) {
+    __shared__ __align__(16) float s_w[kWn];
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    if (tid < kWn) s_w[tid] = wt[tid];
+    __syncthreads();
+    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+    const int b = blockIdx.z / D, d = blockIdx.z % D;
+    if (x >= w || y >= h) return;
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int kd = 0; kd < 3; ++kd) {
+        const int dz = d - kd + 1;                       // output voxel v - tap + 1 used input voxel v with this tap
+        if ((unsigned)dz >= (unsigned)D) continue;
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+            const int yy = y - kh + 1;
+            if ((unsigned)yy >= (unsigned)h) continue;
+            const float* line = g + ((size_t)(b * D + dz) * h + yy) * w;
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+                const int xx = x - kw + 1;
+                if ((unsigned)xx >= (unsigned)w) continue;
+                const float gv = __ldg(line + xx);
+                const float4 w0 = *reinterpret_cast<const float4*>(s_w + ((kd * 3 + kh) * 3 + kw) * kCi);
+                const float4 w1 = *reinterpret_cast<const float4*>(s_w + ((kd * 3 + kh) * 3 + kw) * kCi + 4);
+                acc[0] = fmaf(gv, w0.x, acc[0]); acc[1] = fmaf(gv, w0.y, acc[1]); acc[2] = fmaf(gv, w0.z, acc[2]); acc[3] = fmaf(gv, w0.w, acc[3]);
+                acc[4] = fmaf(gv, w1.x, acc[4]); acc[5] = fmaf(gv, w1.y, acc[5]); acc[6] = fmaf(gv, w1.z, acc[6]); acc[7] = fmaf(gv, w1.w, acc[7]);
+            }
+        }
+    }
+    gz[((size_t)(b * D + d) * h + y) * w + x] = make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]),
+                                                            pack_bf16x2(acc[4], acc[5]), pack_bf16x2(acc[6], acc[7]));
+}
+
+// ---- weight gradient -------------------------------------------------------------------------------------------------
+// A warp walks one (b, d, y) line.  Lane = (kw, c) for 24 lanes: it owns the 9 (kd, kh) taps of its (kw, c) and reads, per
+// voxel, 9 bf16 values (the 24 lanes of a tap read 48 contiguous bytes) and the broadcast upstream gradient.
+constexpr int kWgBlocks = 148 * 4;
+__global__ void __launch_bounds__(256) conv_out_wgrad_kernel(const __nv_bfloat16* __restrict__ z, const float* __restrict__ g,
+                                                             float* __restrict__ partials, int B, int D, int h, int w) {
+    __shared__ float s_acc[8][kWn];                 // one slot per warp: fixed summation order (deterministic)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int kw = lane >> 3, c = lane & 7;
+    const bool owner = lane < 24;
+    float acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    const long lines = (long)B * D * h;
+    for (long line = (long)blockIdx.x * 8 + warp; line < lines; line += (long)gridDim.x * 8) {
+        const int y = (int)(line % h);
+        const int d = (int)((line / h) % D);
+        const int b = (int)(line / ((long)h * D));
+        const float* gl = g + line * w;
+        const __nv_bfloat16* rows[9];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+            const int dz = d + t / 3 - 1, yy = y + t % 3 - 1;
+            rows[t] = ((unsigned)dz < (unsigned)D && (unsigned)yy < (unsigned)h)
+                          ? z + (((size_t)(b * D + dz) * h + yy) * w) * kCi + c : nullptr;
+        }
+        for (int x = 0; x < w; ++x) {
+            const float gv = __ldg(gl + x);
+            const int xx = x + kw - 1;
+            const bool ok = owner && (unsigned)xx < (unsigned)w;
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+                if (ok && rows[t] != nullptr) {
+                    const float zv = __bfloat162float(rows[t][(size_t)xx * kCi]);
+                    acc[t] = fmaf(gv, zv, acc[t]);
+                }
+            }
+        }
+    }
+    if (owner) {
+#pragma unroll
+        for (int t = 0; t < 9; ++t) s_acc[warp][(t * 3 + kw) * kCi + c] = acc[t];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kWn; i += 256) {
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s += s_acc[k][i];
+        partials[(size_t)blockIdx.x * kWn + i] = s;
+    }
+}
+
+__global__ void conv_out_wgrad_finalize_kernel(const float* __restrict__ partials, int nblocks, float* __restrict__ gw) {
+    const int i = threadIdx.x;
+    if (i >= kWn) return;
+    double s = 0.0;
+    for (int k = 0; k < nblocks; ++k) s += (double)partials[(size_t)k * kWn + i];
+    gw[i] = (float)s;
+}
+
+int check_shape(int B, int D, int h, int w, const char* name) {
+    MVS_REQUIRE(B >= 1 && D >= 1 && h >= 1 && w >= 1 && (long)B * D <= 65535 && (h + 7) / 8 <= 65535, "%s: bad shape", name);
+    return MVSB200_OK;
+}
+
+}  // namespace
+
+extern "C" int64_t mvsb200_conv_out_workspace_floats(void) { return (int64_t)kWgBlocks * kWn; }
+
+extern "C" int mvsb200_conv_out_fwd(const void* z, const float* w27x8, float* logits, int B, int D, int h, int w, void* stream) {
+    MVS_REQUIRE(z && w27x8 && logits && aligned16(z), "conv_out_fwd: null or misaligned pointer");
+    if (int rc = check_shape(B, D, h, w, "conv_out_fwd")) return rc;
+    const dim3 grid((w + 31) / 32, (h + 7) / 8, B * D);
+    conv_out_fwd_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>((const uint4*)z, w27x8, logits, D, h, w);
+    MVS_CHECK_LAUNCH("conv_out_fwd");
+    return MVSB200_OK;
+}
+
+extern "C" int mvsb200_conv_out_dgrad(const float* glogits, const float* w27x8, void* gz, int B, int D, int h, int w, void* stream) {
+    MVS_REQUIRE(glogits && w27x8 && gz && aligned16(gz), "conv_out_dgrad: null or misaligned pointer");
+    if (int rc = check_shape(B, D, h, w, "conv_out_dgrad")) return rc;
+    const dim3 grid((w + 31) / 32, (h + 7) / 8, B * D);
+    conv_out_dgrad_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(glogits, w27x8, (uint4*)gz, D, h, w);
+    MVS_CHECK_LAUNCH("conv_out_dgrad");
+    return MVSB200_OK;
+}
+
+extern "C" int mvsb200_conv_out_wgrad(const void* z, const float* glogits, float* workspace, float* gw27x8, int B, int D, int h,
+                                      int w, void* stream) {
+    MVS_REQUIRE(z && glogits && workspace && gw27x8, "conv_out_wgrad: null pointer");
+    if (int rc = check_shape(B, D, h, w, "conv_out_wgrad")) return rc;
+    const long lines = (long)B * D * h;
+    const int blocks = (int)((lines + 7) / 8 < kWgBlocks ? (lines + 7) / 8 : kWgBlocks);
+    conv_out_wgrad_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)z, glogits, workspace, B, D, h, w);
+    MVS_CHECK_LAUNCH("conv_out_wgrad");
+    conv_out_wgrad_finalize_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(workspace, blocks, gw27x8);
+    MVS_CHECK_LAUNCH("conv_out_wgrad_finalize");
+    return MVSB200_OK;
+}

@@ -32,6 +32,10 @@ _SIGNATURES = {
     "mvsb200_variance_views_fwd": (_I, [_P, _P, _I, _I, _c.c_int64, _P]),
     "mvsb200_variance_views_bwd": (_I, [_P, _P, _P, _I, _I, _c.c_int64, _P]),
     "mvsb200_conv3d_s1_fwd": (_I, [_P, _P, _P] + [_I] * 14 + [_P]),
+    "mvsb200_conv_out_workspace_floats": (_c.c_int64, []),
+    "mvsb200_conv_out_fwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
+    "mvsb200_conv_out_dgrad": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
+    "mvsb200_conv_out_wgrad": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "mvsb200_bn_workspace_floats": (_c.c_int64, []),
     "mvsb200_bn_stats": (_I, [_P, _I, _c.c_int64, _I, _P, _P, _P, _P]),
     "mvsb200_bn_relu_fwd": (_I, [_P, _I, _P, _P, _P, _I, _c.c_int64, _I, _P]),

@@ -345,3 +345,58 @@ def affine_relu(x, scale, shift, relu=True):
     _lib.call("mvsb200_bn_relu_fwd", xr.data_ptr(), _DT[xr.dtype], scale.float().contiguous().data_ptr(),
               shift.float().contiguous().data_ptr(), y.data_ptr(), int(relu), M, C, _stream())
     return y
+
+
+# --------------------------------------------------------------------------------------------------
+# K3c: the output convolution 8 -> 1 (model.py:91,123)
+# --------------------------------------------------------------------------------------------------
+_CO_WS = {}
+
+
+def _conv_out_workspace(device):
+    ws = _CO_WS.get(device)
+    if ws is None:
+        ws = torch.empty(int(_lib.load().mvsb200_conv_out_workspace_floats()), dtype=torch.float32, device=device)
+        _CO_WS[device] = ws
+    return ws
+
+
+class _ConvOut(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, z, weight):
+        _need_cuda(z, "conv_out input")
+        B, C, D, h, w = z.shape
+        zc = z.detach().to(torch.bfloat16).contiguous(memory_format=torch.channels_last_3d)
+        w27 = weight.detach().float()[0].permute(1, 2, 3, 0).reshape(27, 8).contiguous()
+        out = torch.empty((B, 1, D, h, w), dtype=torch.float32, device=z.device)
+        with _timed("conv_out_fwd"):
+            _lib.call("mvsb200_conv_out_fwd", zc.data_ptr(), w27.data_ptr(), out.data_ptr(), B, D, h, w, _stream())
+        ctx.save_for_backward(zc, w27)
+        ctx.wdtype, ctx.zdtype = weight.dtype, z.dtype
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        zc, w27 = ctx.saved_tensors
+        B, _, D, h, w = zc.shape
+        g = gout.float().contiguous()
+        gz = gw = None
+        if ctx.needs_input_grad[0]:
+            gz = torch.empty_like(zc)
+            with _timed("conv_out_dgrad"):
+                _lib.call("mvsb200_conv_out_dgrad", g.data_ptr(), w27.data_ptr(), gz.data_ptr(), B, D, h, w, _stream())
+            gz = gz.to(ctx.zdtype)
+        if ctx.needs_input_grad[1]:
+            gw27 = torch.empty_like(w27)
+            with _timed("conv_out_wgrad"):
+                _lib.call("mvsb200_conv_out_wgrad", zc.data_ptr(), g.data_ptr(), _conv_out_workspace(zc.device).data_ptr(),
+                          gw27.data_ptr(), B, D, h, w, _stream())
+            gw = gw27.reshape(3, 3, 3, 8).permute(3, 0, 1, 2).unsqueeze(0).to(ctx.wdtype)
+        return gz, gw
+
+
+def conv_out(z: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
+    """Conv3d(8, 1, 3, padding=1, bias=False) on a [B,8,D,h,w] volume -> fp32 logits [B,1,D,h,w]."""
+    if z.shape[1] != 8 or tuple(weight.shape) != (1, 8, 3, 3, 3):
+        raise ValueError(f"conv_out expects 8 -> 1 channels, got input {tuple(z.shape)} and weight {tuple(weight.shape)}")
+    return _ConvOut.apply(z, weight)

@@ -191,7 +191,10 @@ class CostVolumeReg(nn.Module):
         c3 = up(enc[3], "deconv_3_0", self.BN_2)[(slice(None), slice(None)) + C].float()
         c2 = up(c3 + enc[2], "deconv_2_0", self.BN_1)[(slice(None), slice(None)) + C].float()
         y1 = up(c2 + enc[1], "deconv_1_0", self.BN_0)
-        return be.conv3d(y1 + y0, self._w("conv_out", dt), 1, (1, 1, 1)).float()
+        z = y1 + y0
+        if z.is_cuda and dt == torch.bfloat16 and z.shape[1] == 8 and self.conv_out.out_channels == 1:
+            return ops.conv_out(z, self.conv_out.weight)              # K3c: 8 -> 1 is streaming work, not a GEMM
+        return be.conv3d(z, self._w("conv_out", dt), 1, (1, 1, 1)).float()
 
     @staticmethod
     def _stats_with_constant_outside(T, Wf, bg, dims, E_lo, E_hi, B, n_full):

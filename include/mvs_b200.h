@@ -128,6 +128,17 @@ int mvsb200_conv3d_s1_fwd(const void* x, const void* w_packed, void* y, int B, i
                           int Do, int Ho, int Wo, int cout, int y_cs, int n_rows, int off_d, int off_h, int off_w,
                           void* stream);
 
+/* ---- K3c: the output convolution 8 -> 1 channels (k = 3, stride 1, padding 1) -----------------------
+ * Replaces conv_out = Conv3d(8, 1, 3, padding=1, bias=False) (scripts/model.py:91, used at :123) and its two
+ * gradients.  z: [B, D, h, w, 8] bf16 (the sum y1 + y0, channels_last_3d); w27x8: [27, 8] fp32, tap-major
+ * (kd, kh, kw) then input channel; logits / glogits: [B, D, h, w] fp32; gz: [B, D, h, w, 8] bf16;
+ * gw27x8: [27, 8] fp32 (deterministic reduction); workspace: mvsb200_conv_out_workspace_floats() floats. */
+int64_t mvsb200_conv_out_workspace_floats(void);
+int mvsb200_conv_out_fwd(const void* z, const float* w27x8, float* logits, int B, int D, int h, int w, void* stream);
+int mvsb200_conv_out_dgrad(const float* glogits, const float* w27x8, void* gz, int B, int D, int h, int w, void* stream);
+int mvsb200_conv_out_wgrad(const void* z, const float* glogits, float* workspace, float* gw27x8, int B, int D, int h,
+                           int w, void* stream);
+
 /* ---- K3b: train-mode BatchNorm3d (+ReLU) on channel-last volumes -----------------------------------
  * Replaces the BatchNorm3d + ReLU pairs of CostVolumeReg.forward (scripts/model.py:101-121; layer
  * factory :241-247) in train mode (batch statistics over B, D, h, w; scripts/train.py:61, test.py:61).

@@ -90,3 +90,26 @@ def test_unsupported_operands_fall_back_to_library_conv():
     y = conv_backends.get("tcgen05").conv3d(x, wt, 1, (1, 1, 1))          # 8 -> 1 channels: not a tensor-core shape
     assert mvs_b200.launch_count() == n0 and y.shape == (1, 1, 4, 6, 8)
     assert conv3d_sm100.available()
+
+
+@pytest.mark.parametrize("shape", [(1, 6, 9, 14), (2, 5, 33, 47), (1, 1, 1, 1), (1, 3, 8, 160)])
+def test_conv_out_forward_and_gradients(shape):
+    """K3c: Conv3d(8, 1, 3, padding=1) (model.py:91,123) -- forward, data and weight gradient vs torch fp32."""
+    from mvs_b200 import ops
+    B, D, h, w = shape
+    g = torch.Generator().manual_seed(D * 100 + w)
+    z = torch.randn(B, 8, D, h, w, generator=g).to(DEV).to(torch.bfloat16).contiguous(memory_format=torch.channels_last_3d)
+    wt = (torch.randn(1, 8, 3, 3, 3, generator=g) / 216 ** 0.5).to(DEV)
+    gy = torch.randn(B, 1, D, h, w, generator=g).to(DEV)
+    z1, w1 = z.clone().requires_grad_(True), wt.clone().requires_grad_(True)
+    y = ops.conv_out(z1, w1)
+    y.backward(gy)
+    z2, w2 = z.float().requires_grad_(True), wt.clone().requires_grad_(True)
+    yr = F.conv3d(z2, w2, padding=1)
+    yr.backward(gy)
+    assert y.dtype == torch.float32 and y.shape == yr.shape
+    assert _rel(y, yr) < 1e-5                                   # fp32 accumulation of exact bf16 inputs
+    assert _rel(z1.grad, z2.grad) < TOL                         # stored as bf16
+    assert _rel(w1.grad, w2.grad) < 1e-4
+    y2 = ops.conv_out(z1.detach(), w1.detach())
+    assert torch.equal(y, y2)
