@@ -209,6 +209,130 @@ __global__ void __launch_bounds__(kBnThreads) bn_relu_bwd_apply_kernel(const TX*
     }
 }
 
+
+// ---- crop-aware variants -------------------------------------------------------------------------------------------
+// The transposed convolutions of the regulariser produce dense canvases whose BatchNorm statistics are over the full
+// canvas, but only the central box of the normalised result is ever read (regulariser.py).  These variants normalise
+// the full canvas' statistics-wise while writing / reading gradients only on the box [d0,d0+dc) x [h0,h0+hc) x [w0,w0+wc).
+struct CropBox {
+    int D, h, w;            // canvas
+    int d0, h0, w0;         // box origin
+    int dc, hc, wc;         // box size
+};
+
+// chunk index inside the box volume -> chunk index inside the canvas volume
+__device__ __forceinline__ long long box_to_canvas(long long i, int cpr, const CropBox& c) {
+    const int cg = (int)(i % cpr);
+    long long r = i / cpr;
+    const int x = (int)(r % c.wc); r /= c.wc;
+    const int y = (int)(r % c.hc); r /= c.hc;
+    const int d = (int)(r % c.dc);
+    const long long b = r / c.dc;
+    return ((((b * c.D + d + c.d0) * c.h + y + c.h0) * c.w + x + c.w0)) * cpr + cg;
+}
+// chunk index inside the canvas -> chunk index inside the box, or -1 outside
+__device__ __forceinline__ long long canvas_to_box(long long i, int cpr, const CropBox& c) {
+    const int cg = (int)(i % cpr);
+    long long r = i / cpr;
+    const int x = (int)(r % c.w) - c.w0; r /= c.w;
+    const int y = (int)(r % c.h) - c.h0; r /= c.h;
+    const int d = (int)(r % c.D) - c.d0;
+    const long long b = r / c.D;
+    if ((unsigned)x >= (unsigned)c.wc || (unsigned)y >= (unsigned)c.hc || (unsigned)d >= (unsigned)c.dc) return -1;
+    return ((((b * c.dc + d) * c.hc + y) * c.wc + x)) * cpr + cg;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kBnThreads) bn_relu_fwd_crop_kernel(const T* __restrict__ x, const float* __restrict__ scale,
+                                                                      const float* __restrict__ shift, T* __restrict__ y,
+                                                                      long long n_box_chunks, int C, int relu, CropBox cb) {
+    const int cpr = C / 8;
+    const long long i0 = (long long)blockIdx.x * kBnThreads + threadIdx.x;
+    const int cg = (int)(i0 % cpr);
+    float sc[8], sh[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { sc[k] = scale[cg * 8 + k]; sh[k] = shift[cg * 8 + k]; }
+    const long long stride = (long long)gridDim.x * kBnThreads;
+    for (long long i = i0; i < n_box_chunks; i += stride) {
+        float v[8];
+        Chunk<T>::load(x + box_to_canvas(i, cpr, cb) * 8, v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            v[k] = fmaf(v[k], sc[k], sh[k]);
+            if (relu) v[k] = fmaxf(v[k], 0.f);
+        }
+        Chunk<T>::store(y + i * 8, v);
+    }
+}
+
+template <typename TX, typename TG>
+__global__ void __launch_bounds__(kBnThreads) bn_relu_bwd_reduce_crop_kernel(
+    const TX* __restrict__ x, const TG* __restrict__ gy, const float* __restrict__ scale, const float* __restrict__ shift,
+    const float* __restrict__ mean, const float* __restrict__ invstd, long long n_box_chunks, int C, int relu,
+    float* __restrict__ partials, CropBox cb) {
+    const int cpr = C / 8;
+    const long long i0 = (long long)blockIdx.x * kBnThreads + threadIdx.x;
+    const int cg = (int)(i0 % cpr);
+    float sc[8], sh[8], mu[8], is[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        sc[k] = scale[cg * 8 + k]; sh[k] = shift[cg * 8 + k]; mu[k] = mean[cg * 8 + k]; is[k] = invstd[cg * 8 + k];
+    }
+    float sg[8] = {0, 0, 0, 0, 0, 0, 0, 0}, sgx[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const long long stride = (long long)gridDim.x * kBnThreads;
+    for (long long i = i0; i < n_box_chunks; i += stride) {      // the gradient is zero outside the box
+        float v[8], g[8];
+        Chunk<TX>::load(x + box_to_canvas(i, cpr, cb) * 8, v);
+        Chunk<TG>::load(gy + i * 8, g);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float gk = (!relu || fmaf(v[k], sc[k], sh[k]) > 0.f) ? g[k] : 0.f;
+            sg[k] += gk;
+            sgx[k] = fmaf(gk, (v[k] - mu[k]) * is[k], sgx[k]);
+        }
+    }
+    block_reduce_to_partial(sg, sgx, cpr, C, partials + (size_t)blockIdx.x * 2 * C);
+}
+
+template <typename TX, typename TG>
+__global__ void __launch_bounds__(kBnThreads) bn_relu_bwd_apply_crop_kernel(
+    const TX* __restrict__ x, const TG* __restrict__ gy, const float* __restrict__ scale, const float* __restrict__ shift,
+    const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
+    const float* __restrict__ dbeta, const float* __restrict__ dgamma, TX* __restrict__ dx, long long n_chunks, int C, int relu,
+    float inv_m, CropBox cb) {
+    const int cpr = C / 8;
+    const long long i0 = (long long)blockIdx.x * kBnThreads + threadIdx.x;
+    const int cg = (int)(i0 % cpr);
+    float sc[8], sh[8], mu[8], is[8], k0[8], k1[8], k2[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int c = cg * 8 + k;
+        sc[k] = scale[c]; sh[k] = shift[c]; mu[k] = mean[c]; is[k] = invstd[c];
+        k0[k] = gamma[c] * is[k];
+        k1[k] = dbeta[c] * inv_m;
+        k2[k] = dgamma[c] * inv_m;
+    }
+    const long long stride = (long long)gridDim.x * kBnThreads;
+    for (long long i = i0; i < n_chunks; i += stride) {          // dx is dense: the statistics couple every voxel
+        float v[8], g[8];
+        Chunk<TX>::load(x + i * 8, v);
+        const long long j = canvas_to_box(i, cpr, cb);
+        if (j >= 0) {
+            Chunk<TG>::load(gy + j * 8, g);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) g[k] = 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float gk = (!relu || fmaf(v[k], sc[k], sh[k]) > 0.f) ? g[k] : 0.f;
+            const float xhat = (v[k] - mu[k]) * is[k];
+            v[k] = k0[k] * (gk - k1[k] - xhat * k2[k]);
+        }
+        Chunk<TX>::store(dx + i * 8, v);
+    }
+}
+
 int check_bn(const void* x, long long M, int C, const char* name) {
     MVS_REQUIRE(x && aligned16(x), "%s: null or misaligned volume", name);
     MVS_REQUIRE(C == 8 || C == 16 || C == 32 || C == 64, "%s: C must be 8, 16, 32 or 64 (got %d)", name, C);
@@ -295,4 +419,76 @@ extern "C" int mvsb200_bn_relu_bwd(const void* x, int x_dtype, const void* gy, i
     if (x_dtype == MVSB200_F32 && g_dtype == MVSB200_BF16)
         return bn_bwd_impl<float, __nv_bfloat16>(x, gy, scale, shift, mean, invstd, gamma, workspace, dbeta, dgamma, dx, relu, M, C, st);
     MVS_FAIL(MVSB200_E_BADARG, "bn_relu_bwd: bad dtypes %d / %d", x_dtype, g_dtype);
+}
+
+// ---- crop-aware entry points: box = {D, h, w, d0, h0, w0, dc, hc, wc} (host ints) ------------------------------------
+static int make_box(const int* box9, int64_t M, int64_t* Bout, CropBox* cb) {
+    MVS_REQUIRE(box9 != nullptr, "bn crop: null box");
+    cb->D = box9[0]; cb->h = box9[1]; cb->w = box9[2]; cb->d0 = box9[3]; cb->h0 = box9[4]; cb->w0 = box9[5];
+    cb->dc = box9[6]; cb->hc = box9[7]; cb->wc = box9[8];
+    const int64_t per = (int64_t)cb->D * cb->h * cb->w;
+    MVS_REQUIRE(per > 0 && M % per == 0, "bn crop: canvas %dx%dx%d does not divide M", cb->D, cb->h, cb->w);
+    MVS_REQUIRE(cb->d0 >= 0 && cb->h0 >= 0 && cb->w0 >= 0 && cb->dc >= 1 && cb->hc >= 1 && cb->wc >= 1 &&
+                cb->d0 + cb->dc <= cb->D && cb->h0 + cb->hc <= cb->h && cb->w0 + cb->wc <= cb->w, "bn crop: box outside the canvas");
+    *Bout = M / per;
+    return MVSB200_OK;
+}
+
+extern "C" int mvsb200_bn_relu_fwd_crop(const void* x, int dtype, const float* scale, const float* shift, void* y, int relu,
+                                        int64_t M, int C, const int* box9, void* stream) {
+    if (int rc = check_bn(x, M, C, "bn_relu_fwd_crop")) return rc;
+    MVS_REQUIRE(y && aligned16(y) && scale && shift, "bn_relu_fwd_crop: null or misaligned argument");
+    MVS_REQUIRE(dtype == MVSB200_F32 || dtype == MVSB200_BF16, "bn_relu_fwd_crop: bad dtype %d", dtype);
+    CropBox cb; int64_t B;
+    if (int rc = make_box(box9, M, &B, &cb)) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long n_box = (long long)B * cb.dc * cb.hc * cb.wc * C / 8;
+    const int grid = grid_for(n_box);
+    if (dtype == MVSB200_BF16)
+        bn_relu_fwd_crop_kernel<__nv_bfloat16><<<grid, kBnThreads, 0, st>>>((const __nv_bfloat16*)x, scale, shift,
+                                                                            (__nv_bfloat16*)y, n_box, C, relu, cb);
+    else
+        bn_relu_fwd_crop_kernel<float><<<grid, kBnThreads, 0, st>>>((const float*)x, scale, shift, (float*)y, n_box, C, relu, cb);
+    MVS_CHECK_LAUNCH("bn_relu_fwd_crop");
+    return MVSB200_OK;
+}
+
+template <typename TX, typename TG>
+static int bn_bwd_crop_impl(const void* x, const void* gy, const float* scale, const float* shift, const float* mean,
+                            const float* invstd, const float* gamma, float* workspace, float* dbeta, float* dgamma, void* dx,
+                            int relu, int64_t M, int C, int64_t B, const CropBox& cb, cudaStream_t st) {
+    const long long n_chunks = (long long)M * C / 8;
+    const long long n_box = (long long)B * cb.dc * cb.hc * cb.wc * C / 8;
+    const int grid_box = grid_for(n_box), grid = grid_for(n_chunks);
+    bn_relu_bwd_reduce_crop_kernel<TX, TG><<<grid_box, kBnThreads, 0, st>>>((const TX*)x, (const TG*)gy, scale, shift, mean,
+                                                                            invstd, n_box, C, relu, workspace, cb);
+    MVS_CHECK_LAUNCH("bn_relu_bwd_reduce_crop");
+    bn_finalize_kernel<<<1, kMaxC, 0, st>>>(workspace, grid_box, C, 1.0, 1, dbeta, dgamma);
+    MVS_CHECK_LAUNCH("bn_finalize");
+    bn_relu_bwd_apply_crop_kernel<TX, TG><<<grid, kBnThreads, 0, st>>>((const TX*)x, (const TG*)gy, scale, shift, mean, invstd,
+                                                                       gamma, dbeta, dgamma, (TX*)dx, n_chunks, C, relu,
+                                                                       (float)(1.0 / (double)M), cb);
+    MVS_CHECK_LAUNCH("bn_relu_bwd_apply_crop");
+    return MVSB200_OK;
+}
+
+extern "C" int mvsb200_bn_relu_bwd_crop(const void* x, int x_dtype, const void* gy, int g_dtype, const float* scale,
+                                        const float* shift, const float* mean, const float* invstd, const float* gamma,
+                                        float* workspace, float* dbeta, float* dgamma, void* dx, int relu, int64_t M, int C,
+                                        const int* box9, void* stream) {
+    if (int rc = check_bn(x, M, C, "bn_relu_bwd_crop")) return rc;
+    MVS_REQUIRE(gy && aligned16(gy) && dx && aligned16(dx), "bn_relu_bwd_crop: null or misaligned volume");
+    MVS_REQUIRE(scale && shift && mean && invstd && gamma && workspace && dbeta && dgamma, "bn_relu_bwd_crop: null vector");
+    CropBox cb; int64_t B;
+    if (int rc = make_box(box9, M, &B, &cb)) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (x_dtype == MVSB200_BF16 && g_dtype == MVSB200_BF16)
+        return bn_bwd_crop_impl<__nv_bfloat16, __nv_bfloat16>(x, gy, scale, shift, mean, invstd, gamma, workspace, dbeta, dgamma, dx, relu, M, C, B, cb, st);
+    if (x_dtype == MVSB200_BF16 && g_dtype == MVSB200_F32)
+        return bn_bwd_crop_impl<__nv_bfloat16, float>(x, gy, scale, shift, mean, invstd, gamma, workspace, dbeta, dgamma, dx, relu, M, C, B, cb, st);
+    if (x_dtype == MVSB200_F32 && g_dtype == MVSB200_F32)
+        return bn_bwd_crop_impl<float, float>(x, gy, scale, shift, mean, invstd, gamma, workspace, dbeta, dgamma, dx, relu, M, C, B, cb, st);
+    if (x_dtype == MVSB200_F32 && g_dtype == MVSB200_BF16)
+        return bn_bwd_crop_impl<float, __nv_bfloat16>(x, gy, scale, shift, mean, invstd, gamma, workspace, dbeta, dgamma, dx, relu, M, C, B, cb, st);
+    MVS_FAIL(MVSB200_E_BADARG, "bn_relu_bwd_crop: bad dtypes %d / %d", x_dtype, g_dtype);
 }

@@ -287,11 +287,20 @@ def _rows(x: torch.Tensor):
     return x, B * D * h * w, C
 
 
+def _box9(dims, crop):
+    import ctypes
+    D, h, w = dims
+    (d0, d1), (h0, h1), (w0, w1) = crop
+    return (ctypes.c_int * 9)(D, h, w, d0, h0, w0, d1 - d0, h1 - h0, w1 - w0)
+
+
 class _BatchNormReLU(torch.autograd.Function):
-    """y = ReLU(BatchNorm_train(x)) with batch statistics (model.py:101-121).  Returns (y, mean, biased var)."""
+    """y = ReLU(BatchNorm_train(x)) with batch statistics (model.py:101-121).  Returns (y, mean, biased var).
+    With `crop` = ((d0,d1),(h0,h1),(w0,w1)) the statistics are still those of the full volume but y (and the incoming
+    gradient) exist only on that box."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, eps, relu):
+    def forward(ctx, x, weight, bias, eps, relu, crop):
         _need_cuda(x, "BatchNorm input")
         xr, M, C = _rows(x.detach())
         dev = xr.device
@@ -304,12 +313,21 @@ class _BatchNormReLU(torch.autograd.Function):
         invstd = torch.rsqrt(var + eps)
         scale = (weight.detach().float() * invstd).contiguous()
         shift = (bias.detach().float() - mean * scale).contiguous()
-        y = torch.empty_like(xr)
-        with _timed("bn_relu_fwd"):
-            _lib.call("mvsb200_bn_relu_fwd", xr.data_ptr(), _DT[xr.dtype], scale.data_ptr(), shift.data_ptr(),
-                      y.data_ptr(), int(relu), M, C, _stream())
+        if crop is None:
+            y = torch.empty_like(xr)
+            with _timed("bn_relu_fwd"):
+                _lib.call("mvsb200_bn_relu_fwd", xr.data_ptr(), _DT[xr.dtype], scale.data_ptr(), shift.data_ptr(),
+                          y.data_ptr(), int(relu), M, C, _stream())
+        else:
+            B = xr.shape[0]
+            (d0, d1), (h0, h1), (w0, w1) = crop
+            y = torch.empty((B, C, d1 - d0, h1 - h0, w1 - w0), dtype=xr.dtype, device=dev,
+                            memory_format=torch.channels_last_3d)
+            with _timed("bn_relu_fwd"):
+                _lib.call("mvsb200_bn_relu_fwd_crop", xr.data_ptr(), _DT[xr.dtype], scale.data_ptr(), shift.data_ptr(),
+                          y.data_ptr(), int(relu), M, C, _box9(xr.shape[2:], crop), _stream())
         ctx.save_for_backward(xr, scale, shift, mean, invstd, weight.detach().float().contiguous())
-        ctx.relu, ctx.dims = bool(relu), (M, C)
+        ctx.relu, ctx.dims, ctx.crop = bool(relu), (M, C), crop
         ctx.mark_non_differentiable(mean, var)
         return y, mean, var
 
@@ -325,16 +343,25 @@ class _BatchNormReLU(torch.autograd.Function):
         dgamma = torch.empty(C, dtype=torch.float32, device=dev)
         dx = torch.empty_like(xr)
         with _timed("bn_relu_bwd"):
-            _lib.call("mvsb200_bn_relu_bwd", xr.data_ptr(), _DT[xr.dtype], gy.data_ptr(), _DT[gy.dtype], scale.data_ptr(),
-                      shift.data_ptr(), mean.data_ptr(), invstd.data_ptr(), gamma.data_ptr(),
-                      _bn_workspace(dev).data_ptr(), dbeta.data_ptr(), dgamma.data_ptr(), dx.data_ptr(), int(ctx.relu),
-                      M, C, _stream())
-        return dx, dgamma, dbeta, None, None
+            if ctx.crop is None:
+                _lib.call("mvsb200_bn_relu_bwd", xr.data_ptr(), _DT[xr.dtype], gy.data_ptr(), _DT[gy.dtype],
+                          scale.data_ptr(), shift.data_ptr(), mean.data_ptr(), invstd.data_ptr(), gamma.data_ptr(),
+                          _bn_workspace(dev).data_ptr(), dbeta.data_ptr(), dgamma.data_ptr(), dx.data_ptr(),
+                          int(ctx.relu), M, C, _stream())
+            else:
+                _lib.call("mvsb200_bn_relu_bwd_crop", xr.data_ptr(), _DT[xr.dtype], gy.data_ptr(), _DT[gy.dtype],
+                          scale.data_ptr(), shift.data_ptr(), mean.data_ptr(), invstd.data_ptr(), gamma.data_ptr(),
+                          _bn_workspace(dev).data_ptr(), dbeta.data_ptr(), dgamma.data_ptr(), dx.data_ptr(),
+                          int(ctx.relu), M, C, _box9(xr.shape[2:], ctx.crop), _stream())
+        return dx, dgamma, dbeta, None, None, None
 
 
-def batchnorm_relu_train(x, weight, bias, eps=1e-5, relu=True):
-    """-> (y, batch mean [C], biased batch variance [C]); y has x's dtype (fp32 or bf16), channels_last_3d."""
-    return _BatchNormReLU.apply(x, weight, bias, float(eps), bool(relu))
+def batchnorm_relu_train(x, weight, bias, eps=1e-5, relu=True, crop=None):
+    """-> (y, batch mean [C], biased batch variance [C]); y has x's dtype (fp32 or bf16), channels_last_3d.
+    crop = ((d0,d1),(h0,h1),(w0,w1)): full-volume statistics, y only on that box."""
+    if crop is not None:
+        crop = tuple((int(a), int(b)) for a, b in crop)
+    return _BatchNormReLU.apply(x, weight, bias, float(eps), bool(relu), crop)
 
 
 def affine_relu(x, scale, shift, relu=True):

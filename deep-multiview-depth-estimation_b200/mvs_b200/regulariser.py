@@ -84,12 +84,13 @@ class CostVolumeReg(nn.Module):
         w = getattr(self, name).weight
         return w if w.dtype == dtype else w.to(dtype)
 
-    def _bn_dense(self, bn: nn.BatchNorm3d, x):
-        """BatchNorm over a full canvas (+ReLU).  On the GPU this is the fused channel-last kernel pair of
+    def _bn_dense(self, bn: nn.BatchNorm3d, x, crop=None):
+        """BatchNorm over a full canvas (+ReLU); with `crop` (three slices) only that box of the result is produced.  On the GPU this is the fused channel-last kernel pair of
         libmvs_b200.so (K3b); the torch expression below serves only the CPU unit tests of the canvas algebra."""
         if x.is_cuda:
             if bn.training:
-                y, mean, var = ops.batchnorm_relu_train(x, bn.weight, bn.bias, bn.eps, relu=True)
+                box = None if crop is None else tuple((c.start, c.stop) for c in crop)
+                y, mean, var = ops.batchnorm_relu_train(x, bn.weight, bn.bias, bn.eps, relu=True, crop=box)
                 n = x.numel() // x.shape[1]
                 with torch.no_grad():
                     m = bn.momentum
@@ -99,11 +100,13 @@ class CostVolumeReg(nn.Module):
                 return y
             if not torch.is_grad_enabled() or not (x.requires_grad or bn.weight.requires_grad):
                 scale = bn.weight * torch.rsqrt(bn.running_var + bn.eps)
-                return ops.affine_relu(x, scale, bn.bias - bn.running_mean * scale, relu=True)
+                y = ops.affine_relu(x, scale, bn.bias - bn.running_mean * scale, relu=True)
+                return y if crop is None else y[(slice(None), slice(None)) + tuple(crop)]
         y = F.batch_norm(x, bn.running_mean, bn.running_var, bn.weight, bn.bias, bn.training, bn.momentum, bn.eps)
         if bn.training:
             bn.num_batches_tracked += 1
-        return F.relu(y)
+        y = F.relu(y)
+        return y if crop is None else y[(slice(None), slice(None)) + tuple(crop)]
 
     def _bn_affine(self, bn: nn.BatchNorm3d, mean, var, n_full):
         """scale/shift of BatchNorm given full-canvas batch statistics (train) or the running ones (eval)."""
@@ -183,13 +186,14 @@ class CostVolumeReg(nn.Module):
         # ---- decoder: transposed convs read only C; their outputs are dense canvases (statistics are dense)
         Lp = tuple(L for _, _, L in reg)
 
-        def up(z, name, bn):
+        def up(z, name, bn, crop=None):
             # channel-last operands keep the library on its NDHWC kernels (no layout-conversion passes over the canvas)
             U = be.conv_transpose3d(z.to(dt).contiguous(memory_format=torch.channels_last_3d), self._w(name, dt), 2, Lp, dims)
-            return self._bn_dense(bn, U)
+            return self._bn_dense(bn, U, crop)
 
-        c3 = up(enc[3], "deconv_3_0", self.BN_2)[(slice(None), slice(None)) + C].float()
-        c2 = up(c3 + enc[2], "deconv_2_0", self.BN_1)[(slice(None), slice(None)) + C].float()
+        # the transposed convs' canvases are normalised with full-canvas statistics but only their box C is read
+        c3 = up(enc[3], "deconv_3_0", self.BN_2, C).float()
+        c2 = up(c3 + enc[2], "deconv_2_0", self.BN_1, C).float()
         y1 = up(c2 + enc[1], "deconv_1_0", self.BN_0)
         z = y1 + y0
         if z.is_cuda and dt == torch.bfloat16 and z.shape[1] == 8 and self.conv_out.out_channels == 1:

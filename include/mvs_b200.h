@@ -159,6 +159,16 @@ int mvsb200_bn_relu_bwd(const void* x, int x_dtype, const void* gy, int g_dtype,
                         float* workspace, float* dbeta, float* dgamma, void* dx, int relu, int64_t M, int C,
                         void* stream);
 
+/* Crop-aware variants: statistics over the full canvas, but y / gy live only on a box of it (the transposed
+ * convolutions' outputs are normalised densely and read only on the central box, regulariser.py).
+ * box9 (HOST ints) = {D, h, w, d0, h0, w0, dc, hc, wc}; y, gy: [B, dc, hc, wc, C]; x, dx: [B, D, h, w, C]. */
+int mvsb200_bn_relu_fwd_crop(const void* x, int dtype, const float* scale, const float* shift, void* y, int relu,
+                             int64_t M, int C, const int* box9_host, void* stream);
+int mvsb200_bn_relu_bwd_crop(const void* x, int x_dtype, const void* gy, int g_dtype, const float* scale,
+                             const float* shift, const float* mean, const float* invstd, const float* gamma,
+                             float* workspace, float* dbeta, float* dgamma, void* dx, int relu, int64_t M, int C,
+                             const int* box9_host, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -103,3 +103,27 @@ def test_regulariser_gradients_match_reference(golden_dir):
     for n, gr in zip(names, grads[1:]):
         ref = g["gparam/" + n]
         assert np.abs(gr.cpu().numpy() - ref).max() <= 5e-4 * max(np.abs(ref).max(), 1e-3), n
+
+
+@pytest.mark.parametrize("C,dtype", [(16, torch.float32), (32, torch.bfloat16)])
+def test_cropped_output_equals_dense_then_slice(C, dtype):
+    """Crop-aware BN: full-volume statistics, result and incoming gradient only on a box."""
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(2, C, 9, 11, 13, generator=g).to(DEV).to(dtype).contiguous(memory_format=torch.channels_last_3d)
+    wt, bs = (torch.rand(C, generator=g) + 0.5).to(DEV).requires_grad_(True), torch.randn(C, generator=g).to(DEV).requires_grad_(True)
+    crop = ((2, 7), (1, 9), (3, 12))
+    sl = (slice(None), slice(None), slice(2, 7), slice(1, 9), slice(3, 12))
+    gy = torch.randn(2, C, 5, 8, 9, generator=g).to(DEV).to(dtype)
+    x1 = x.clone().requires_grad_(True)
+    y1, m1, v1 = ops.batchnorm_relu_train(x1, wt, bs, crop=crop)
+    y1.backward(gy)
+    gw1, gb1 = wt.grad.clone(), bs.grad.clone()
+    wt.grad = bs.grad = None
+    x2 = x.clone().requires_grad_(True)
+    y2, m2, v2 = ops.batchnorm_relu_train(x2, wt, bs)
+    y2[sl].backward(gy)
+    assert torch.equal(m1, m2) and torch.equal(v1, v2)
+    assert torch.equal(y1, y2[sl])
+    tol = 1e-5 if dtype == torch.float32 else 1e-2
+    assert (x1.grad.float() - x2.grad.float()).abs().max().item() <= tol * max(1.0, float(x2.grad.float().abs().max()))
+    assert torch.allclose(gw1, wt.grad, rtol=1e-4, atol=1e-4) and torch.allclose(gb1, bs.grad, rtol=1e-4, atol=1e-4)
