@@ -215,7 +215,9 @@ __global__ void __launch_bounds__(kBnThreads) bn_relu_bwd_apply_kernel(const TX*
 // canvas, but only the central box of the normalised result is ever read (regulariser.py).  These variants normalise
 // the full canvas' statistics-wise while writing / reading gradients only on the box [d0,d0+dc) x [h0,h0+hc) x [w0,w0+wc).
 struct CropBox {
-    int D, h, w;            // canvas
+    int Da, ha, wa;         // allocation that holds the canvas at its origin (the library's transposed conv returns one
+                            // extra plane/line/column that the reference crops away)
+    int D, h, w;            // canvas: the volume the statistics are taken over
     int d0, h0, w0;         // box origin
     int dc, hc, wc;         // box size
 };
@@ -228,18 +230,46 @@ __device__ __forceinline__ long long box_to_canvas(long long i, int cpr, const C
     const int y = (int)(r % c.hc); r /= c.hc;
     const int d = (int)(r % c.dc);
     const long long b = r / c.dc;
-    return ((((b * c.D + d + c.d0) * c.h + y + c.h0) * c.w + x + c.w0)) * cpr + cg;
+    return ((((b * c.Da + d + c.d0) * c.ha + y + c.h0) * c.wa + x + c.w0)) * cpr + cg;
 }
-// chunk index inside the canvas -> chunk index inside the box, or -1 outside
-__device__ __forceinline__ long long canvas_to_box(long long i, int cpr, const CropBox& c) {
+// chunk index inside the canvas -> chunk index inside the allocation
+__device__ __forceinline__ long long canvas_to_alloc(long long i, int cpr, const CropBox& c) {
     const int cg = (int)(i % cpr);
     long long r = i / cpr;
-    const int x = (int)(r % c.w) - c.w0; r /= c.w;
-    const int y = (int)(r % c.h) - c.h0; r /= c.h;
-    const int d = (int)(r % c.D) - c.d0;
+    const int x = (int)(r % c.w); r /= c.w;
+    const int y = (int)(r % c.h); r /= c.h;
+    const int d = (int)(r % c.D);
     const long long b = r / c.D;
+    return ((((b * c.Da + d) * c.ha + y) * c.wa + x)) * cpr + cg;
+}
+// chunk index inside the allocation -> chunk index inside the box (>= 0), -1 inside the canvas but outside the box,
+// -2 outside the canvas
+__device__ __forceinline__ long long alloc_to_box(long long i, int cpr, const CropBox& c) {
+    const int cg = (int)(i % cpr);
+    long long r = i / cpr;
+    const int xa = (int)(r % c.wa); r /= c.wa;
+    const int ya = (int)(r % c.ha); r /= c.ha;
+    const int da = (int)(r % c.Da);
+    const long long b = r / c.Da;
+    if (xa >= c.w || ya >= c.h || da >= c.D) return -2;
+    const int x = xa - c.w0, y = ya - c.h0, d = da - c.d0;
     if ((unsigned)x >= (unsigned)c.wc || (unsigned)y >= (unsigned)c.hc || (unsigned)d >= (unsigned)c.dc) return -1;
     return ((((b * c.dc + d) * c.hc + y) * c.wc + x)) * cpr + cg;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kBnThreads) bn_stats_geo_kernel(const T* __restrict__ x, long long n_canvas_chunks, int C,
+                                                                  float* __restrict__ partials, CropBox cb) {
+    const int cpr = C / 8;
+    float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const long long stride = (long long)gridDim.x * kBnThreads;
+    for (long long i = (long long)blockIdx.x * kBnThreads + threadIdx.x; i < n_canvas_chunks; i += stride) {
+        float v[8];
+        Chunk<T>::load(x + canvas_to_alloc(i, cpr, cb) * 8, v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { s[k] += v[k]; q[k] = fmaf(v[k], v[k], q[k]); }
+    }
+    block_reduce_to_partial(s, q, cpr, C, partials + (size_t)blockIdx.x * 2 * C);
 }
 
 template <typename T>
@@ -313,10 +343,16 @@ __global__ void __launch_bounds__(kBnThreads) bn_relu_bwd_apply_crop_kernel(
         k2[k] = dgamma[c] * inv_m;
     }
     const long long stride = (long long)gridDim.x * kBnThreads;
-    for (long long i = i0; i < n_chunks; i += stride) {          // dx is dense: the statistics couple every voxel
+    for (long long i = i0; i < n_chunks; i += stride) {          // dx is dense on the canvas: the statistics couple every voxel
         float v[8], g[8];
+        const long long j = alloc_to_box(i, cpr, cb);
+        if (j == -2) {                                            // allocation slack outside the canvas: no gradient
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = 0.f;
+            Chunk<TX>::store(dx + i * 8, v);
+            continue;
+        }
         Chunk<TX>::load(x + i * 8, v);
-        const long long j = canvas_to_box(i, cpr, cb);
         if (j >= 0) {
             Chunk<TG>::load(gy + j * 8, g);
         } else {
@@ -421,26 +457,47 @@ extern "C" int mvsb200_bn_relu_bwd(const void* x, int x_dtype, const void* gy, i
     MVS_FAIL(MVSB200_E_BADARG, "bn_relu_bwd: bad dtypes %d / %d", x_dtype, g_dtype);
 }
 
-// ---- crop-aware entry points: box = {D, h, w, d0, h0, w0, dc, hc, wc} (host ints) ------------------------------------
-static int make_box(const int* box9, int64_t M, int64_t* Bout, CropBox* cb) {
-    MVS_REQUIRE(box9 != nullptr, "bn crop: null box");
-    cb->D = box9[0]; cb->h = box9[1]; cb->w = box9[2]; cb->d0 = box9[3]; cb->h0 = box9[4]; cb->w0 = box9[5];
-    cb->dc = box9[6]; cb->hc = box9[7]; cb->wc = box9[8];
+// ---- crop-aware entry points: geo = {Da, ha, wa, D, h, w, d0, h0, w0, dc, hc, wc} (host ints) --------------------------
+static int make_box(const int* g, int64_t M, int64_t* Bout, CropBox* cb) {
+    MVS_REQUIRE(g != nullptr, "bn crop: null geometry");
+    cb->Da = g[0]; cb->ha = g[1]; cb->wa = g[2]; cb->D = g[3]; cb->h = g[4]; cb->w = g[5];
+    cb->d0 = g[6]; cb->h0 = g[7]; cb->w0 = g[8]; cb->dc = g[9]; cb->hc = g[10]; cb->wc = g[11];
     const int64_t per = (int64_t)cb->D * cb->h * cb->w;
     MVS_REQUIRE(per > 0 && M % per == 0, "bn crop: canvas %dx%dx%d does not divide M", cb->D, cb->h, cb->w);
+    MVS_REQUIRE(cb->Da >= cb->D && cb->ha >= cb->h && cb->wa >= cb->w, "bn crop: canvas larger than its allocation");
     MVS_REQUIRE(cb->d0 >= 0 && cb->h0 >= 0 && cb->w0 >= 0 && cb->dc >= 1 && cb->hc >= 1 && cb->wc >= 1 &&
                 cb->d0 + cb->dc <= cb->D && cb->h0 + cb->hc <= cb->h && cb->w0 + cb->wc <= cb->w, "bn crop: box outside the canvas");
     *Bout = M / per;
     return MVSB200_OK;
 }
 
+extern "C" int mvsb200_bn_stats_geo(const void* x, int dtype, int64_t M, int C, float* workspace, float* mean, float* var,
+                                    const int* geo12, void* stream) {
+    if (int rc = check_bn(x, M, C, "bn_stats_geo")) return rc;
+    MVS_REQUIRE(workspace && mean && var, "bn_stats_geo: null output");
+    MVS_REQUIRE(dtype == MVSB200_F32 || dtype == MVSB200_BF16, "bn_stats_geo: bad dtype %d", dtype);
+    CropBox cb; int64_t B;
+    if (int rc = make_box(geo12, M, &B, &cb)) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long n_chunks = (long long)M * C / 8;
+    const int grid = grid_for(n_chunks);
+    if (dtype == MVSB200_BF16)
+        bn_stats_geo_kernel<__nv_bfloat16><<<grid, kBnThreads, 0, st>>>((const __nv_bfloat16*)x, n_chunks, C, workspace, cb);
+    else
+        bn_stats_geo_kernel<float><<<grid, kBnThreads, 0, st>>>((const float*)x, n_chunks, C, workspace, cb);
+    MVS_CHECK_LAUNCH("bn_stats_geo");
+    bn_finalize_kernel<<<1, kMaxC, 0, st>>>(workspace, grid, C, 1.0 / (double)M, 0, mean, var);
+    MVS_CHECK_LAUNCH("bn_finalize");
+    return MVSB200_OK;
+}
+
 extern "C" int mvsb200_bn_relu_fwd_crop(const void* x, int dtype, const float* scale, const float* shift, void* y, int relu,
-                                        int64_t M, int C, const int* box9, void* stream) {
+                                        int64_t M, int C, const int* geo12, void* stream) {
     if (int rc = check_bn(x, M, C, "bn_relu_fwd_crop")) return rc;
     MVS_REQUIRE(y && aligned16(y) && scale && shift, "bn_relu_fwd_crop: null or misaligned argument");
     MVS_REQUIRE(dtype == MVSB200_F32 || dtype == MVSB200_BF16, "bn_relu_fwd_crop: bad dtype %d", dtype);
     CropBox cb; int64_t B;
-    if (int rc = make_box(box9, M, &B, &cb)) return rc;
+    if (int rc = make_box(geo12, M, &B, &cb)) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     const long long n_box = (long long)B * cb.dc * cb.hc * cb.wc * C / 8;
     const int grid = grid_for(n_box);
@@ -457,7 +514,7 @@ template <typename TX, typename TG>
 static int bn_bwd_crop_impl(const void* x, const void* gy, const float* scale, const float* shift, const float* mean,
                             const float* invstd, const float* gamma, float* workspace, float* dbeta, float* dgamma, void* dx,
                             int relu, int64_t M, int C, int64_t B, const CropBox& cb, cudaStream_t st) {
-    const long long n_chunks = (long long)M * C / 8;
+    const long long n_chunks = (long long)B * cb.Da * cb.ha * cb.wa * C / 8;       // dx covers the whole allocation
     const long long n_box = (long long)B * cb.dc * cb.hc * cb.wc * C / 8;
     const int grid_box = grid_for(n_box), grid = grid_for(n_chunks);
     bn_relu_bwd_reduce_crop_kernel<TX, TG><<<grid_box, kBnThreads, 0, st>>>((const TX*)x, (const TG*)gy, scale, shift, mean,
@@ -475,12 +532,12 @@ static int bn_bwd_crop_impl(const void* x, const void* gy, const float* scale, c
 extern "C" int mvsb200_bn_relu_bwd_crop(const void* x, int x_dtype, const void* gy, int g_dtype, const float* scale,
                                         const float* shift, const float* mean, const float* invstd, const float* gamma,
                                         float* workspace, float* dbeta, float* dgamma, void* dx, int relu, int64_t M, int C,
-                                        const int* box9, void* stream) {
+                                        const int* geo12, void* stream) {
     if (int rc = check_bn(x, M, C, "bn_relu_bwd_crop")) return rc;
     MVS_REQUIRE(gy && aligned16(gy) && dx && aligned16(dx), "bn_relu_bwd_crop: null or misaligned volume");
     MVS_REQUIRE(scale && shift && mean && invstd && gamma && workspace && dbeta && dgamma, "bn_relu_bwd_crop: null vector");
     CropBox cb; int64_t B;
-    if (int rc = make_box(box9, M, &B, &cb)) return rc;
+    if (int rc = make_box(geo12, M, &B, &cb)) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     if (x_dtype == MVSB200_BF16 && g_dtype == MVSB200_BF16)
         return bn_bwd_crop_impl<__nv_bfloat16, __nv_bfloat16>(x, gy, scale, shift, mean, invstd, gamma, workspace, dbeta, dgamma, dx, relu, M, C, B, cb, st);

@@ -19,13 +19,18 @@ class TorchConvBackend:
         return F.conv3d(x, w, None, stride, padding)
 
     @staticmethod
-    def conv_transpose3d(x, w, stride, padding, out_dims):
-        """Stride-2 transposed conv from the central box to the full canvas `out_dims` (cropped to it)."""
+    def conv_transpose3d_alloc(x, w, stride, padding, out_dims):
+        """Stride-2 transposed conv from the central box; the result holds the canvas `out_dims` at its origin and may be
+        up to one plane/line/column larger (callers that can address the canvas inside it avoid a crop copy)."""
         size = [stride * (m - 1) - 2 * p + 3 for m, p in zip(x.shape[-3:], padding)]
         opad = tuple(max(0, n - s) for n, s in zip(out_dims, size))
-        y = F.conv_transpose3d(x, w, None, stride, tuple(padding), opad)
+        return F.conv_transpose3d(x, w, None, stride, tuple(padding), opad)
+
+    @classmethod
+    def conv_transpose3d(cls, x, w, stride, padding, out_dims):
+        """Stride-2 transposed conv from the central box to the full canvas `out_dims` (cropped to it)."""
         D, h, w_ = out_dims
-        return y[..., :D, :h, :w_]
+        return cls.conv_transpose3d_alloc(x, w, stride, padding, out_dims)[..., :D, :h, :w_]
 
 
 _BACKENDS = {"cudnn": TorchConvBackend}

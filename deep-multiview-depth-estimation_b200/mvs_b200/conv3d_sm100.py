@@ -88,7 +88,8 @@ class Tcgen05ConvBackend:
             return _Conv3dS1.apply(x, w, pad[0])
         return conv_backends.TorchConvBackend.conv3d(x, w, stride, padding)
 
-    conv_transpose3d = staticmethod(conv_backends.TorchConvBackend.conv_transpose3d)
+    conv_transpose3d = conv_backends.TorchConvBackend.conv_transpose3d
+    conv_transpose3d_alloc = conv_backends.TorchConvBackend.conv_transpose3d_alloc
 
 
 def available() -> bool:

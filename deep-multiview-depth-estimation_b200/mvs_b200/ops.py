@@ -287,47 +287,56 @@ def _rows(x: torch.Tensor):
     return x, B * D * h * w, C
 
 
-def _box9(dims, crop):
+def _geo12(alloc, canvas, crop):
     import ctypes
-    D, h, w = dims
     (d0, d1), (h0, h1), (w0, w1) = crop
-    return (ctypes.c_int * 9)(D, h, w, d0, h0, w0, d1 - d0, h1 - h0, w1 - w0)
+    return (ctypes.c_int * 12)(*alloc, *canvas, d0, h0, w0, d1 - d0, h1 - h0, w1 - w0)
 
 
 class _BatchNormReLU(torch.autograd.Function):
     """y = ReLU(BatchNorm_train(x)) with batch statistics (model.py:101-121).  Returns (y, mean, biased var).
-    With `crop` = ((d0,d1),(h0,h1),(w0,w1)) the statistics are still those of the full volume but y (and the incoming
-    gradient) exist only on that box."""
+    `canvas` = (D,h,w): the statistics volume, sitting at the origin of x's (possibly larger) allocation.
+    `crop` = ((d0,d1),(h0,h1),(w0,w1)): y (and the incoming gradient) exist only on that box of the canvas."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, eps, relu, crop):
+    def forward(ctx, x, weight, bias, eps, relu, crop, canvas):
         _need_cuda(x, "BatchNorm input")
-        xr, M, C = _rows(x.detach())
+        xr, _, C = _rows(x.detach())
         dev = xr.device
+        B = xr.shape[0]
+        alloc = tuple(xr.shape[2:])
+        canvas = alloc if canvas is None else tuple(canvas)
+        plain = crop is None and canvas == alloc
+        M = B * canvas[0] * canvas[1] * canvas[2]
+        box = crop if crop is not None else tuple((0, n) for n in canvas)
+        geo = None if plain else _geo12(alloc, canvas, box)
         mean = torch.empty(C, dtype=torch.float32, device=dev)
         var = torch.empty(C, dtype=torch.float32, device=dev)
         ws = _bn_workspace(dev)
         with _timed("bn_stats"):
-            _lib.call("mvsb200_bn_stats", xr.data_ptr(), _DT[xr.dtype], M, C, ws.data_ptr(), mean.data_ptr(),
-                      var.data_ptr(), _stream())
+            if canvas == alloc:
+                _lib.call("mvsb200_bn_stats", xr.data_ptr(), _DT[xr.dtype], M, C, ws.data_ptr(), mean.data_ptr(),
+                          var.data_ptr(), _stream())
+            else:
+                _lib.call("mvsb200_bn_stats_geo", xr.data_ptr(), _DT[xr.dtype], M, C, ws.data_ptr(), mean.data_ptr(),
+                          var.data_ptr(), geo, _stream())
         invstd = torch.rsqrt(var + eps)
         scale = (weight.detach().float() * invstd).contiguous()
         shift = (bias.detach().float() - mean * scale).contiguous()
-        if crop is None:
+        if plain:
             y = torch.empty_like(xr)
             with _timed("bn_relu_fwd"):
                 _lib.call("mvsb200_bn_relu_fwd", xr.data_ptr(), _DT[xr.dtype], scale.data_ptr(), shift.data_ptr(),
                           y.data_ptr(), int(relu), M, C, _stream())
         else:
-            B = xr.shape[0]
-            (d0, d1), (h0, h1), (w0, w1) = crop
+            (d0, d1), (h0, h1), (w0, w1) = box
             y = torch.empty((B, C, d1 - d0, h1 - h0, w1 - w0), dtype=xr.dtype, device=dev,
                             memory_format=torch.channels_last_3d)
             with _timed("bn_relu_fwd"):
                 _lib.call("mvsb200_bn_relu_fwd_crop", xr.data_ptr(), _DT[xr.dtype], scale.data_ptr(), shift.data_ptr(),
-                          y.data_ptr(), int(relu), M, C, _box9(xr.shape[2:], crop), _stream())
+                          y.data_ptr(), int(relu), M, C, geo, _stream())
         ctx.save_for_backward(xr, scale, shift, mean, invstd, weight.detach().float().contiguous())
-        ctx.relu, ctx.dims, ctx.crop = bool(relu), (M, C), crop
+        ctx.relu, ctx.dims, ctx.geo = bool(relu), (M, C), (None if plain else (alloc, canvas, box))
         ctx.mark_non_differentiable(mean, var)
         return y, mean, var
 
@@ -343,7 +352,7 @@ class _BatchNormReLU(torch.autograd.Function):
         dgamma = torch.empty(C, dtype=torch.float32, device=dev)
         dx = torch.empty_like(xr)
         with _timed("bn_relu_bwd"):
-            if ctx.crop is None:
+            if ctx.geo is None:
                 _lib.call("mvsb200_bn_relu_bwd", xr.data_ptr(), _DT[xr.dtype], gy.data_ptr(), _DT[gy.dtype],
                           scale.data_ptr(), shift.data_ptr(), mean.data_ptr(), invstd.data_ptr(), gamma.data_ptr(),
                           _bn_workspace(dev).data_ptr(), dbeta.data_ptr(), dgamma.data_ptr(), dx.data_ptr(),
@@ -352,16 +361,19 @@ class _BatchNormReLU(torch.autograd.Function):
                 _lib.call("mvsb200_bn_relu_bwd_crop", xr.data_ptr(), _DT[xr.dtype], gy.data_ptr(), _DT[gy.dtype],
                           scale.data_ptr(), shift.data_ptr(), mean.data_ptr(), invstd.data_ptr(), gamma.data_ptr(),
                           _bn_workspace(dev).data_ptr(), dbeta.data_ptr(), dgamma.data_ptr(), dx.data_ptr(),
-                          int(ctx.relu), M, C, _box9(xr.shape[2:], ctx.crop), _stream())
-        return dx, dgamma, dbeta, None, None, None
+                          int(ctx.relu), M, C, _geo12(*ctx.geo), _stream())
+        return dx, dgamma, dbeta, None, None, None, None
 
 
-def batchnorm_relu_train(x, weight, bias, eps=1e-5, relu=True, crop=None):
+def batchnorm_relu_train(x, weight, bias, eps=1e-5, relu=True, crop=None, canvas=None):
     """-> (y, batch mean [C], biased batch variance [C]); y has x's dtype (fp32 or bf16), channels_last_3d.
-    crop = ((d0,d1),(h0,h1),(w0,w1)): full-volume statistics, y only on that box."""
+    canvas = (D,h,w) <= x's spatial dims: the statistics volume (x may carry allocation slack beyond it);
+    crop = ((d0,d1),(h0,h1),(w0,w1)): full-canvas statistics, y only on that box."""
     if crop is not None:
         crop = tuple((int(a), int(b)) for a, b in crop)
-    return _BatchNormReLU.apply(x, weight, bias, float(eps), bool(relu), crop)
+    if canvas is not None:
+        canvas = tuple(int(n) for n in canvas)
+    return _BatchNormReLU.apply(x, weight, bias, float(eps), bool(relu), crop, canvas)
 
 
 def affine_relu(x, scale, shift, relu=True):

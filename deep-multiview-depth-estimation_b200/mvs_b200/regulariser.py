@@ -84,20 +84,25 @@ class CostVolumeReg(nn.Module):
         w = getattr(self, name).weight
         return w if w.dtype == dtype else w.to(dtype)
 
-    def _bn_dense(self, bn: nn.BatchNorm3d, x, crop=None):
-        """BatchNorm over a full canvas (+ReLU); with `crop` (three slices) only that box of the result is produced.  On the GPU this is the fused channel-last kernel pair of
-        libmvs_b200.so (K3b); the torch expression below serves only the CPU unit tests of the canvas algebra."""
+    def _bn_dense(self, bn: nn.BatchNorm3d, x, crop=None, canvas=None):
+        """BatchNorm (+ReLU) over a full canvas.  `canvas` = (D,h,w): the canvas sits at the origin of x, which may be one
+        plane/line/column larger (un-cropped transposed conv); `crop` (three slices): only that box of the result is
+        produced.  On the GPU in train mode this is the fused channel-last kernel family of libmvs_b200.so (K3b); the
+        torch expressions below serve eval mode and the CPU unit tests of the canvas algebra."""
+        if x.is_cuda and bn.training:
+            box = None if crop is None else tuple((c.start, c.stop) for c in crop)
+            y, mean, var = ops.batchnorm_relu_train(x, bn.weight, bn.bias, bn.eps, relu=True, crop=box, canvas=canvas)
+            dims_ = tuple(x.shape[2:]) if canvas is None else tuple(canvas)
+            n = x.shape[0] * dims_[0] * dims_[1] * dims_[2]
+            with torch.no_grad():
+                m = bn.momentum
+                bn.running_mean.mul_(1 - m).add_(mean, alpha=m)
+                bn.running_var.mul_(1 - m).add_(var * (n / max(n - 1, 1)), alpha=m)
+                bn.num_batches_tracked += 1
+            return y
+        if canvas is not None:
+            x = x[..., :canvas[0], :canvas[1], :canvas[2]]
         if x.is_cuda:
-            if bn.training:
-                box = None if crop is None else tuple((c.start, c.stop) for c in crop)
-                y, mean, var = ops.batchnorm_relu_train(x, bn.weight, bn.bias, bn.eps, relu=True, crop=box)
-                n = x.numel() // x.shape[1]
-                with torch.no_grad():
-                    m = bn.momentum
-                    bn.running_mean.mul_(1 - m).add_(mean, alpha=m)
-                    bn.running_var.mul_(1 - m).add_(var * (n / max(n - 1, 1)), alpha=m)
-                    bn.num_batches_tracked += 1
-                return y
             if not torch.is_grad_enabled() or not (x.requires_grad or bn.weight.requires_grad):
                 scale = bn.weight * torch.rsqrt(bn.running_var + bn.eps)
                 y = ops.affine_relu(x, scale, bn.bias - bn.running_mean * scale, relu=True)
@@ -188,8 +193,8 @@ class CostVolumeReg(nn.Module):
 
         def up(z, name, bn, crop=None):
             # channel-last operands keep the library on its NDHWC kernels (no layout-conversion passes over the canvas)
-            U = be.conv_transpose3d(z.to(dt).contiguous(memory_format=torch.channels_last_3d), self._w(name, dt), 2, Lp, dims)
-            return self._bn_dense(bn, U, crop)
+            U = be.conv_transpose3d_alloc(z.to(dt).contiguous(memory_format=torch.channels_last_3d), self._w(name, dt), 2, Lp, dims)
+            return self._bn_dense(bn, U, crop, dims)      # U holds the canvas at its origin (+ up to one slack plane/line/column)
 
         # the transposed convs' canvases are normalised with full-canvas statistics but only their box C is read
         c3 = up(enc[3], "deconv_3_0", self.BN_2, C).float()

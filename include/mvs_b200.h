@@ -159,15 +159,20 @@ int mvsb200_bn_relu_bwd(const void* x, int x_dtype, const void* gy, int g_dtype,
                         float* workspace, float* dbeta, float* dgamma, void* dx, int relu, int64_t M, int C,
                         void* stream);
 
-/* Crop-aware variants: statistics over the full canvas, but y / gy live only on a box of it (the transposed
- * convolutions' outputs are normalised densely and read only on the central box, regulariser.py).
- * box9 (HOST ints) = {D, h, w, d0, h0, w0, dc, hc, wc}; y, gy: [B, dc, hc, wc, C]; x, dx: [B, D, h, w, C]. */
+/* Geometry-aware variants.  The canvas [D,h,w] (what the statistics are taken over; M = B*D*h*w) sits at the origin
+ * of a possibly larger allocation [Da,ha,wa] (the library's stride-2 transposed convolution returns one extra
+ * plane/line/column that the reference crops away, scripts/config.py:21 OUTPAD), and y / gy live only on a box of the
+ * canvas (the normalised result is read only on the central box, regulariser.py).
+ * geo12 (HOST ints) = {Da, ha, wa, D, h, w, d0, h0, w0, dc, hc, wc};
+ * x, dx: [B, Da, ha, wa, C] (dx is 0 outside the canvas); y, gy: [B, dc, hc, wc, C]. */
+int mvsb200_bn_stats_geo(const void* x, int dtype, int64_t M, int C, float* workspace, float* mean, float* var,
+                         const int* geo12_host, void* stream);
 int mvsb200_bn_relu_fwd_crop(const void* x, int dtype, const float* scale, const float* shift, void* y, int relu,
-                             int64_t M, int C, const int* box9_host, void* stream);
+                             int64_t M, int C, const int* geo12_host, void* stream);
 int mvsb200_bn_relu_bwd_crop(const void* x, int x_dtype, const void* gy, int g_dtype, const float* scale,
                              const float* shift, const float* mean, const float* invstd, const float* gamma,
                              float* workspace, float* dbeta, float* dgamma, void* dx, int relu, int64_t M, int C,
-                             const int* box9_host, void* stream);
+                             const int* geo12_host, void* stream);
 
 #ifdef __cplusplus
 }

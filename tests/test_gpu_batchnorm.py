@@ -127,3 +127,27 @@ def test_cropped_output_equals_dense_then_slice(C, dtype):
     tol = 1e-5 if dtype == torch.float32 else 1e-2
     assert (x1.grad.float() - x2.grad.float()).abs().max().item() <= tol * max(1.0, float(x2.grad.float().abs().max()))
     assert torch.allclose(gw1, wt.grad, rtol=1e-4, atol=1e-4) and torch.allclose(gb1, bs.grad, rtol=1e-4, atol=1e-4)
+
+
+def test_canvas_inside_larger_allocation():
+    """The un-cropped transposed conv returns the canvas plus one slack plane/line/column: statistics and results must be
+    those of the canvas alone, and the gradient into the slack must be zero."""
+    g = torch.Generator().manual_seed(11)
+    C = 16
+    xa = torch.randn(2, C, 9, 7, 11, generator=g).to(DEV).contiguous(memory_format=torch.channels_last_3d)
+    canvas = (8, 6, 10)
+    wt, bs = (torch.rand(C, generator=g) + 0.5).to(DEV), torch.randn(C, generator=g).to(DEV)
+    for crop in (None, ((1, 7), (2, 5), (0, 9))):
+        sl = (slice(None), slice(None)) + tuple(slice(a, b) for a, b in (crop or tuple((0, n) for n in canvas)))
+        x1 = xa.clone().requires_grad_(True)
+        y1, m1, v1 = ops.batchnorm_relu_train(x1, wt, bs, crop=crop, canvas=canvas)
+        gy = torch.randn(y1.shape, generator=torch.Generator().manual_seed(3)).to(DEV)
+        y1.backward(gy)
+        x2 = xa.clone().requires_grad_(True)
+        xc = x2[..., :8, :6, :10].contiguous(memory_format=torch.channels_last_3d)
+        y2, m2, v2 = ops.batchnorm_relu_train(xc, wt, bs)
+        y2[sl].backward(gy)
+        assert torch.allclose(m1, m2, atol=1e-6) and torch.allclose(v1, v2, rtol=1e-5)
+        assert torch.allclose(y1, y2[sl], atol=1e-5)
+        assert torch.allclose(x1.grad, x2.grad, atol=1e-5)
+        assert x1.grad[..., 8:, :, :].abs().max() == 0 and x1.grad[..., :, 6:, :].abs().max() == 0
