@@ -68,8 +68,19 @@ class _Conv3dS1(torch.autograd.Function):
         gy = gy.to(torch.bfloat16).contiguous(memory_format=torch.channels_last_3d)
         if ctx.needs_input_grad[0]:
             cout, cin = w.shape[:2]
+            off = -1 if pad == 1 else -2
             if _supported(cout, cin):          # roles swap: the gradient volume has Cout channels, the result Cin
-                gx = _launch(gy, pack_filter_dgrad(w), cin, tuple(x_cl.shape[2:]), -1 if pad == 1 else -2)
+                gx = _launch(gy, pack_filter_dgrad(w), cin, tuple(x_cl.shape[2:]), off)
+            elif cout == 8 and _supported(16, cin):
+                # 8-channel gradient rows (K = 8 < UMMA K): widen to 16 channels with zeros, zero filter rows to match
+                B, _, Do, Ho, Wo = gy.shape
+                gy16 = torch.empty((B, 16, Do, Ho, Wo), dtype=torch.bfloat16, device=gy.device,
+                                   memory_format=torch.channels_last_3d)
+                gy16[:, :8] = gy
+                gy16[:, 8:] = 0
+                w16 = torch.zeros((16,) + tuple(w.shape[1:]), dtype=w.dtype, device=w.device)
+                w16[:8] = w.detach()
+                gx = _launch(gy16, pack_filter_dgrad(w16), cin, tuple(x_cl.shape[2:]), off)
             else:
                 gx = torch.nn.grad.conv3d_input(x_cl.shape, w.to(gy.dtype), gy, padding=pad)
         if ctx.needs_input_grad[1]:
