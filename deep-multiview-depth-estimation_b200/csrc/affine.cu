@@ -1,0 +1,341 @@
+// K3d: per-channel sums and affine+ReLU over BOXES of channel-last volumes, with their gradients (sm_100a).
+//
+// Why: the reference's stride-2 branches (scripts/model.py:104-113, padding dim/2+1 from scripts/config.py:20) only carry
+// information on a central box of the canvas; outside it their BatchNorm+ReLU output is one constant per channel.
+// regulariser.py therefore evaluates those layers on boxes and folds the remainder into the batch statistics
+// analytically.  What is left per branch is streaming work on box-shaped tensors:
+//   channel_sums      s1[c] = sum x, s2[c] = sum x^2 over a (strided) box            -> statistics
+//   affine_relu_geo   y(p) = max(xv(p)*scale[c] + shift[c], 0) for p in an OUTPUT box, with xv(p) = x(p) inside the INPUT
+//                     box and 0 outside it (both boxes given in one coordinate frame).  Output box larger than the input
+//                     box = "data on the box, BatchNorm'd zero around it" (the next convolution's operand); output box
+//                     inside the input box = crop.
+// Each is one pass; gradients: d/dx of the sums, and (dx, dscale, dshift) of the affine map.  x may be any view with
+// unit channel stride (e.g. a channel slice of the stacked branch convolution); outputs are dense channel-last.
+#include "common.cuh"
+
+using namespace mvsb200;
+
+namespace {
+
+constexpr int kThreadsA = 256;
+constexpr int kBlocksA = 148 * 4;
+constexpr int kMaxCA = 64;
+
+struct View {                 // a [B, C, D, h, w] view with unit channel stride; strides in elements
+    long long sb, sd, sh, sw;
+    int B, D, h, w;
+};
+struct Geo {
+    View in;                  // x
+    int io[3];                // origin of the input box in the common frame
+    int oo[3];                // origin of the output box
+    int od[3];                // size of the output box (D, h, w)
+};
+
+__device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&v)[8]) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(w[i] << 16); v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+}
+__device__ __forceinline__ void store8(float* p, const float (&v)[8]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&v)[8]) {
+    *reinterpret_cast<uint4*>(p) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                                               pack_bf16x2(v[6], v[7]));
+}
+
+// dense row index -> coordinates (32-bit arithmetic: rows < 2^31 is checked on the host)
+__device__ __forceinline__ void decode_row(unsigned r, int D, int h, int w, int& b, int& d, int& y, int& x) {
+    x = (int)(r % (unsigned)w); r /= (unsigned)w;
+    y = (int)(r % (unsigned)h); r /= (unsigned)h;
+    d = (int)(r % (unsigned)D);
+    b = (int)(r / (unsigned)D);
+}
+
+__device__ __forceinline__ void reduce_to_partial(float (&a)[8], float (&b)[8], int cpr, int C, float* partial_row) {
+    __shared__ float s_part[kThreadsA / 32][2][kMaxCA];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        for (int o = 16; o >= cpr; o >>= 1) {
+            a[i] += __shfl_xor_sync(0xffffffffu, a[i], o);
+            b[i] += __shfl_xor_sync(0xffffffffu, b[i], o);
+        }
+    }
+    if (lane < cpr) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { s_part[warp][0][lane * 8 + i] = a[i]; s_part[warp][1][lane * 8 + i] = b[i]; }
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < 2 * C) {
+        const int which = threadIdx.x / C, c = threadIdx.x % C;
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < kThreadsA / 32; ++w) s += s_part[w][which][c];
+        partial_row[which * C + c] = s;
+    }
+}
+
+__global__ void finalize_sums_kernel(const float* __restrict__ partials, int nblocks, int C, float* __restrict__ o0,
+                                     float* __restrict__ o1) {
+    const int c = threadIdx.x;
+    if (c >= C) return;
+    double a = 0.0, b = 0.0;
+    for (int k = 0; k < nblocks; ++k) { a += (double)partials[(size_t)k * 2 * C + c]; b += (double)partials[(size_t)k * 2 * C + C + c]; }
+    o0[c] = (float)a;
+    o1[c] = (float)b;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreadsA) channel_sums_kernel(const T* __restrict__ x, View v, unsigned n_chunks, int C,
+                                                                 float* __restrict__ partials) {
+    const int cpr = C / 8;
+    const unsigned i0 = blockIdx.x * kThreadsA + threadIdx.x;
+    const int cg = (int)(i0 % (unsigned)cpr);
+    float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (unsigned i = i0; i < n_chunks; i += gridDim.x * kThreadsA) {
+        int b, d, y, xx;
+        decode_row(i / (unsigned)cpr, v.D, v.h, v.w, b, d, y, xx);
+        float val[8];
+        load8(x + b * v.sb + d * v.sd + y * v.sh + xx * v.sw + cg * 8, val);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { s[k] += val[k]; q[k] = fmaf(val[k], val[k], q[k]); }
+    }
+    reduce_to_partial(s, q, cpr, C, partials + (size_t)blockIdx.x * 2 * C);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreadsA) channel_sums_bwd_kernel(const T* __restrict__ x, View v, unsigned n_chunks, int C,
+                                                                     const float* __restrict__ g1, const float* __restrict__ g2,
+                                                                     T* __restrict__ gx) {
+    const int cpr = C / 8;
+    const unsigned i0 = blockIdx.x * kThreadsA + threadIdx.x;
+    const int cg = (int)(i0 % (unsigned)cpr);
+    float a[8], b2[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { a[k] = g1[cg * 8 + k]; b2[k] = 2.f * g2[cg * 8 + k]; }
+    for (unsigned i = i0; i < n_chunks; i += gridDim.x * kThreadsA) {
+        int b, d, y, xx;
+        decode_row(i / (unsigned)cpr, v.D, v.h, v.w, b, d, y, xx);
+        float val[8];
+        load8(x + b * v.sb + d * v.sd + y * v.sh + xx * v.sw + cg * 8, val);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) val[k] = fmaf(val[k], b2[k], a[k]);
+        store8(gx + (size_t)i * 8, val);
+    }
+}
+
+// value of x at output row (b, od, oy, ox) of the output box, 0 outside the input box
+template <typename T>
+__device__ __forceinline__ bool load_in(const T* __restrict__ x, const Geo& g, int b, int od, int oy, int ox, int cg, float (&val)[8]) {
+    const int id = od + g.oo[0] - g.io[0], iy = oy + g.oo[1] - g.io[1], ix = ox + g.oo[2] - g.io[2];
+    if ((unsigned)id < (unsigned)g.in.D && (unsigned)iy < (unsigned)g.in.h && (unsigned)ix < (unsigned)g.in.w) {
+        load8(x + b * g.in.sb + id * g.in.sd + iy * g.in.sh + ix * g.in.sw + cg * 8, val);
+        return true;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) val[k] = 0.f;
+    return false;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreadsA) affine_relu_geo_fwd_kernel(const T* __restrict__ x, Geo g, unsigned n_out_chunks, int C,
+                                                                        const float* __restrict__ scale,
+                                                                        const float* __restrict__ shift, T* __restrict__ y, int relu) {
+    const int cpr = C / 8;
+    const unsigned i0 = blockIdx.x * kThreadsA + threadIdx.x;
+    const int cg = (int)(i0 % (unsigned)cpr);
+    float sc[8], sh[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { sc[k] = scale[cg * 8 + k]; sh[k] = shift[cg * 8 + k]; }
+    for (unsigned i = i0; i < n_out_chunks; i += gridDim.x * kThreadsA) {
+        int b, d, yy, xx;
+        decode_row(i / (unsigned)cpr, g.od[0], g.od[1], g.od[2], b, d, yy, xx);
+        float val[8];
+        load_in(x, g, b, d, yy, xx, cg, val);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            val[k] = fmaf(val[k], sc[k], sh[k]);
+            if (relu) val[k] = fmaxf(val[k], 0.f);
+        }
+        store8(y + (size_t)i * 8, val);
+    }
+}
+
+// dshift[c] = sum_O g, dscale[c] = sum_O g * xv   with g = gy * [xv*scale+shift > 0]
+template <typename T, typename TG>
+__global__ void __launch_bounds__(kThreadsA) affine_relu_geo_bwd_reduce_kernel(const T* __restrict__ x, const TG* __restrict__ gy,
+                                                                               Geo g, unsigned n_out_chunks, int C,
+                                                                               const float* __restrict__ scale,
+                                                                               const float* __restrict__ shift, int relu,
+                                                                               float* __restrict__ partials) {
+    const int cpr = C / 8;
+    const unsigned i0 = blockIdx.x * kThreadsA + threadIdx.x;
+    const int cg = (int)(i0 % (unsigned)cpr);
+    float sc[8], sh[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { sc[k] = scale[cg * 8 + k]; sh[k] = shift[cg * 8 + k]; }
+    float sg[8] = {0, 0, 0, 0, 0, 0, 0, 0}, sgx[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (unsigned i = i0; i < n_out_chunks; i += gridDim.x * kThreadsA) {
+        int b, d, yy, xx;
+        decode_row(i / (unsigned)cpr, g.od[0], g.od[1], g.od[2], b, d, yy, xx);
+        float val[8], gv[8];
+        load_in(x, g, b, d, yy, xx, cg, val);
+        load8(gy + (size_t)i * 8, gv);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float gk = (!relu || fmaf(val[k], sc[k], sh[k]) > 0.f) ? gv[k] : 0.f;
+            sg[k] += gk;
+            sgx[k] = fmaf(gk, val[k], sgx[k]);
+        }
+    }
+    reduce_to_partial(sg, sgx, cpr, C, partials + (size_t)blockIdx.x * 2 * C);
+}
+
+// gx over the input box (dense): g * scale where the voxel is inside the output box, else 0
+template <typename T, typename TG>
+__global__ void __launch_bounds__(kThreadsA) affine_relu_geo_bwd_dx_kernel(const T* __restrict__ x, const TG* __restrict__ gy, Geo g,
+                                                                           unsigned n_in_chunks, int C,
+                                                                           const float* __restrict__ scale,
+                                                                           const float* __restrict__ shift, int relu,
+                                                                           T* __restrict__ gx) {
+    const int cpr = C / 8;
+    const unsigned i0 = blockIdx.x * kThreadsA + threadIdx.x;
+    const int cg = (int)(i0 % (unsigned)cpr);
+    float sc[8], sh[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { sc[k] = scale[cg * 8 + k]; sh[k] = shift[cg * 8 + k]; }
+    for (unsigned i = i0; i < n_in_chunks; i += gridDim.x * kThreadsA) {
+        int b, d, yy, xx;
+        decode_row(i / (unsigned)cpr, g.in.D, g.in.h, g.in.w, b, d, yy, xx);
+        const int od = d + g.io[0] - g.oo[0], oy = yy + g.io[1] - g.oo[1], ox = xx + g.io[2] - g.oo[2];
+        float out[8];
+        if ((unsigned)od < (unsigned)g.od[0] && (unsigned)oy < (unsigned)g.od[1] && (unsigned)ox < (unsigned)g.od[2]) {
+            float val[8], gv[8];
+            load8(x + b * g.in.sb + d * g.in.sd + yy * g.in.sh + xx * g.in.sw + cg * 8, val);
+            const size_t orow = (((size_t)b * g.od[0] + od) * g.od[1] + oy) * g.od[2] + ox;
+            load8(gy + (orow * cpr + cg) * 8, gv);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) out[k] = (!relu || fmaf(val[k], sc[k], sh[k]) > 0.f) ? gv[k] * sc[k] : 0.f;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) out[k] = 0.f;
+        }
+        store8(gx + (size_t)i * 8, out);
+    }
+}
+
+int make_view(const int64_t* strides4, const int* dims4, int C, View* v, const char* name) {
+    MVS_REQUIRE(strides4 && dims4, "%s: null geometry", name);
+    MVS_REQUIRE(C == 8 || C == 16 || C == 32 || C == 64, "%s: C must be 8, 16, 32 or 64 (got %d)", name, C);
+    v->sb = strides4[0]; v->sd = strides4[1]; v->sh = strides4[2]; v->sw = strides4[3];
+    v->B = dims4[0]; v->D = dims4[1]; v->h = dims4[2]; v->w = dims4[3];
+    MVS_REQUIRE(v->B >= 1 && v->D >= 1 && v->h >= 1 && v->w >= 1, "%s: empty box", name);
+    MVS_REQUIRE(v->sb % 8 == 0 && v->sd % 8 == 0 && v->sh % 8 == 0 && v->sw % 8 == 0, "%s: strides must be multiples of 8 elements", name);
+    MVS_REQUIRE((long long)v->B * v->D * v->h * v->w * (C / 8) < (1LL << 31), "%s: box too large", name);
+    return MVSB200_OK;
+}
+
+int grid_of(unsigned n_chunks) {
+    const unsigned b = (n_chunks + kThreadsA - 1) / kThreadsA;
+    return (int)(b < (unsigned)kBlocksA ? (b ? b : 1) : kBlocksA);
+}
+
+int make_geo(const int64_t* strides4, const int* geo13, int C, Geo* g, const char* name) {
+    MVS_REQUIRE(geo13 != nullptr, "%s: null geometry", name);
+    if (int rc = make_view(strides4, geo13, C, &g->in, name)) return rc;
+    for (int i = 0; i < 3; ++i) { g->io[i] = geo13[4 + i]; g->oo[i] = geo13[7 + i]; g->od[i] = geo13[10 + i]; }
+    MVS_REQUIRE(g->od[0] >= 1 && g->od[1] >= 1 && g->od[2] >= 1, "%s: empty output box", name);
+    MVS_REQUIRE((long long)g->in.B * g->od[0] * g->od[1] * g->od[2] * (C / 8) < (1LL << 31), "%s: output box too large", name);
+    return MVSB200_OK;
+}
+
+}  // namespace
+
+extern "C" int64_t mvsb200_affine_workspace_floats(void) { return (int64_t)kBlocksA * 2 * kMaxCA; }
+
+extern "C" int mvsb200_channel_sums(const void* x, int dtype, const int64_t* strides4, const int* dims4, int C, float* workspace,
+                                    float* s1, float* s2, void* stream) {
+    MVS_REQUIRE(x && aligned16(x) && workspace && s1 && s2, "channel_sums: null or misaligned pointer");
+    View v;
+    if (int rc = make_view(strides4, dims4, C, &v, "channel_sums")) return rc;
+    const unsigned n = (unsigned)((long long)v.B * v.D * v.h * v.w * (C / 8));
+    const int grid = grid_of(n);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == MVSB200_BF16) channel_sums_kernel<__nv_bfloat16><<<grid, kThreadsA, 0, st>>>((const __nv_bfloat16*)x, v, n, C, workspace);
+    else if (dtype == MVSB200_F32) channel_sums_kernel<float><<<grid, kThreadsA, 0, st>>>((const float*)x, v, n, C, workspace);
+    else MVS_FAIL(MVSB200_E_BADARG, "channel_sums: bad dtype %d", dtype);
+    MVS_CHECK_LAUNCH("channel_sums");
+    finalize_sums_kernel<<<1, kMaxCA, 0, st>>>(workspace, grid, C, s1, s2);
+    MVS_CHECK_LAUNCH("channel_sums_finalize");
+    return MVSB200_OK;
+}
+
+extern "C" int mvsb200_channel_sums_bwd(const void* x, int dtype, const int64_t* strides4, const int* dims4, int C, const float* g1,
+                                        const float* g2, void* gx, void* stream) {
+    MVS_REQUIRE(x && aligned16(x) && g1 && g2 && gx && aligned16(gx), "channel_sums_bwd: null or misaligned pointer");
+    View v;
+    if (int rc = make_view(strides4, dims4, C, &v, "channel_sums_bwd")) return rc;
+    const unsigned n = (unsigned)((long long)v.B * v.D * v.h * v.w * (C / 8));
+    const int grid = grid_of(n);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == MVSB200_BF16) channel_sums_bwd_kernel<__nv_bfloat16><<<grid, kThreadsA, 0, st>>>((const __nv_bfloat16*)x, v, n, C, g1, g2, (__nv_bfloat16*)gx);
+    else if (dtype == MVSB200_F32) channel_sums_bwd_kernel<float><<<grid, kThreadsA, 0, st>>>((const float*)x, v, n, C, g1, g2, (float*)gx);
+    else MVS_FAIL(MVSB200_E_BADARG, "channel_sums_bwd: bad dtype %d", dtype);
+    MVS_CHECK_LAUNCH("channel_sums_bwd");
+    return MVSB200_OK;
+}
+
+extern "C" int mvsb200_affine_relu_geo_fwd(const void* x, int dtype, const int64_t* strides4, const int* geo13, int C,
+                                           const float* scale, const float* shift, void* y, int relu, void* stream) {
+    MVS_REQUIRE(x && aligned16(x) && y && aligned16(y) && scale && shift, "affine_relu_geo_fwd: null or misaligned pointer");
+    Geo g;
+    if (int rc = make_geo(strides4, geo13, C, &g, "affine_relu_geo_fwd")) return rc;
+    const unsigned n = (unsigned)((long long)g.in.B * g.od[0] * g.od[1] * g.od[2] * (C / 8));
+    const int grid = grid_of(n);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == MVSB200_BF16)
+        affine_relu_geo_fwd_kernel<__nv_bfloat16><<<grid, kThreadsA, 0, st>>>((const __nv_bfloat16*)x, g, n, C, scale, shift, (__nv_bfloat16*)y, relu);
+    else if (dtype == MVSB200_F32)
+        affine_relu_geo_fwd_kernel<float><<<grid, kThreadsA, 0, st>>>((const float*)x, g, n, C, scale, shift, (float*)y, relu);
+    else MVS_FAIL(MVSB200_E_BADARG, "affine_relu_geo_fwd: bad dtype %d", dtype);
+    MVS_CHECK_LAUNCH("affine_relu_geo_fwd");
+    return MVSB200_OK;
+}
+
+template <typename T, typename TG>
+static int affine_bwd_impl(const void* x, const void* gy, const Geo& g, int C, const float* scale, const float* shift, int relu,
+                           float* workspace, float* gscale, float* gshift, void* gx, cudaStream_t st) {
+    const unsigned n_out = (unsigned)((long long)g.in.B * g.od[0] * g.od[1] * g.od[2] * (C / 8));
+    const unsigned n_in = (unsigned)((long long)g.in.B * g.in.D * g.in.h * g.in.w * (C / 8));
+    const int grid_out = grid_of(n_out), grid_in = grid_of(n_in);
+    affine_relu_geo_bwd_reduce_kernel<T, TG><<<grid_out, kThreadsA, 0, st>>>((const T*)x, (const TG*)gy, g, n_out, C, scale, shift, relu, workspace);
+    MVS_CHECK_LAUNCH("affine_relu_geo_bwd_reduce");
+    finalize_sums_kernel<<<1, kMaxCA, 0, st>>>(workspace, grid_out, C, gshift, gscale);
+    MVS_CHECK_LAUNCH("affine_relu_geo_bwd_finalize");
+    affine_relu_geo_bwd_dx_kernel<T, TG><<<grid_in, kThreadsA, 0, st>>>((const T*)x, (const TG*)gy, g, n_in, C, scale, shift, relu, (T*)gx);
+    MVS_CHECK_LAUNCH("affine_relu_geo_bwd_dx");
+    return MVSB200_OK;
+}
+
+extern "C" int mvsb200_affine_relu_geo_bwd(const void* x, int x_dtype, const int64_t* strides4, const int* geo13, int C,
+                                           const float* scale, const float* shift, const void* gy, int g_dtype, float* workspace,
+                                           float* gscale, float* gshift, void* gx, int relu, void* stream) {
+    MVS_REQUIRE(x && aligned16(x) && gy && aligned16(gy) && gx && aligned16(gx), "affine_relu_geo_bwd: null or misaligned volume");
+    MVS_REQUIRE(scale && shift && workspace && gscale && gshift, "affine_relu_geo_bwd: null vector");
+    Geo g;
+    if (int rc = make_geo(strides4, geo13, C, &g, "affine_relu_geo_bwd")) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (x_dtype == MVSB200_BF16 && g_dtype == MVSB200_BF16) return affine_bwd_impl<__nv_bfloat16, __nv_bfloat16>(x, gy, g, C, scale, shift, relu, workspace, gscale, gshift, gx, st);
+    if (x_dtype == MVSB200_BF16 && g_dtype == MVSB200_F32) return affine_bwd_impl<__nv_bfloat16, float>(x, gy, g, C, scale, shift, relu, workspace, gscale, gshift, gx, st);
+    if (x_dtype == MVSB200_F32 && g_dtype == MVSB200_F32) return affine_bwd_impl<float, float>(x, gy, g, C, scale, shift, relu, workspace, gscale, gshift, gx, st);
+    if (x_dtype == MVSB200_F32 && g_dtype == MVSB200_BF16) return affine_bwd_impl<float, __nv_bfloat16>(x, gy, g, C, scale, shift, relu, workspace, gscale, gshift, gx, st);
+    MVS_FAIL(MVSB200_E_BADARG, "affine_relu_geo_bwd: bad dtypes %d / %d", x_dtype, g_dtype);
+}

@@ -439,3 +439,106 @@ def conv_out(z: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
     if z.shape[1] != 8 or tuple(weight.shape) != (1, 8, 3, 3, 3):
         raise ValueError(f"conv_out expects 8 -> 1 channels, got input {tuple(z.shape)} and weight {tuple(weight.shape)}")
     return _ConvOut.apply(z, weight)
+
+
+# --------------------------------------------------------------------------------------------------
+# K3d: per-channel sums and affine+ReLU over boxes (the stride-2 branches' BatchNorm on their central box)
+# --------------------------------------------------------------------------------------------------
+_AF_WS = {}
+
+
+def _affine_workspace(device):
+    ws = _AF_WS.get(device)
+    if ws is None:
+        ws = torch.empty(int(_lib.load().mvsb200_affine_workspace_floats()), dtype=torch.float32, device=device)
+        _AF_WS[device] = ws
+    return ws
+
+
+def _box_view(x: torch.Tensor):
+    """A [B,C,D,h,w] view with unit channel stride (made so if needed) -> (tensor, strides4, dims4 ctypes arrays)."""
+    import ctypes
+    if x.dtype not in _DT:
+        x = x.float()
+    if x.stride(1) != 1 or any(s % 8 for s in (x.stride(0), x.stride(2), x.stride(3), x.stride(4))) or x.data_ptr() % 16:
+        x = x.contiguous(memory_format=torch.channels_last_3d)
+    B, C, D, h, w = x.shape
+    strides = (ctypes.c_int64 * 4)(x.stride(0), x.stride(2), x.stride(3), x.stride(4))
+    dims = (ctypes.c_int * 4)(B, D, h, w)
+    return x, strides, dims
+
+
+class _ChannelSums(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        _need_cuda(x, "channel_sums input")
+        xv, strides, dims = _box_view(x.detach())
+        C = xv.shape[1]
+        s1 = torch.empty(C, dtype=torch.float32, device=xv.device)
+        s2 = torch.empty(C, dtype=torch.float32, device=xv.device)
+        with _timed("channel_sums"):
+            _lib.call("mvsb200_channel_sums", xv.data_ptr(), _DT[xv.dtype], strides, dims, C,
+                      _affine_workspace(xv.device).data_ptr(), s1.data_ptr(), s2.data_ptr(), _stream())
+        ctx.save_for_backward(xv)
+        return s1, s2
+
+    @staticmethod
+    def backward(ctx, g1, g2):
+        (xv,) = ctx.saved_tensors
+        _, strides, dims = _box_view(xv)
+        gx = torch.empty(xv.shape, dtype=xv.dtype, device=xv.device, memory_format=torch.channels_last_3d)
+        with _timed("channel_sums_bwd"):
+            _lib.call("mvsb200_channel_sums_bwd", xv.data_ptr(), _DT[xv.dtype], strides, dims, xv.shape[1],
+                      g1.float().contiguous().data_ptr(), g2.float().contiguous().data_ptr(), gx.data_ptr(), _stream())
+        return gx
+
+
+def channel_sums(x: torch.Tensor):
+    """(sum x, sum x^2) per channel over a [B,C,D,h,w] box (any view with unit channel stride); differentiable."""
+    return _ChannelSums.apply(x)
+
+
+def _geo13(xv, in_origin, out_origin, out_dims):
+    import ctypes
+    B, _, D, h, w = xv.shape
+    return (ctypes.c_int * 13)(B, D, h, w, *in_origin, *out_origin, *out_dims)
+
+
+class _AffineReLUGeo(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, scale, shift, in_origin, out_origin, out_dims, relu):
+        _need_cuda(x, "affine_relu_geo input")
+        xv, strides, _ = _box_view(x.detach())
+        B, C = xv.shape[:2]
+        sc, sh = scale.detach().float().contiguous(), shift.detach().float().contiguous()
+        y = torch.empty((B, C) + tuple(out_dims), dtype=xv.dtype, device=xv.device, memory_format=torch.channels_last_3d)
+        with _timed("affine_relu_geo_fwd"):
+            _lib.call("mvsb200_affine_relu_geo_fwd", xv.data_ptr(), _DT[xv.dtype], strides, _geo13(xv, in_origin, out_origin, out_dims),
+                      C, sc.data_ptr(), sh.data_ptr(), y.data_ptr(), int(relu), _stream())
+        ctx.save_for_backward(xv, sc, sh)
+        ctx.geo, ctx.relu = (tuple(in_origin), tuple(out_origin), tuple(out_dims)), bool(relu)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        xv, sc, sh = ctx.saved_tensors
+        _, strides, _ = _box_view(xv)
+        C = xv.shape[1]
+        if gy.dtype not in _DT:
+            gy = gy.float()
+        gy = gy.contiguous(memory_format=torch.channels_last_3d)
+        gx = torch.empty(xv.shape, dtype=xv.dtype, device=xv.device, memory_format=torch.channels_last_3d)
+        gscale = torch.empty(C, dtype=torch.float32, device=xv.device)
+        gshift = torch.empty(C, dtype=torch.float32, device=xv.device)
+        with _timed("affine_relu_geo_bwd"):
+            _lib.call("mvsb200_affine_relu_geo_bwd", xv.data_ptr(), _DT[xv.dtype], strides, _geo13(xv, *ctx.geo), C,
+                      sc.data_ptr(), sh.data_ptr(), gy.data_ptr(), _DT[gy.dtype], _affine_workspace(xv.device).data_ptr(),
+                      gscale.data_ptr(), gshift.data_ptr(), gx.data_ptr(), int(ctx.relu), _stream())
+        return gx, gscale, gshift, None, None, None, None
+
+
+def affine_relu_geo(x, scale, shift, in_origin, out_origin, out_dims, relu=True):
+    """y(p) = max(xv(p)*scale + shift, 0) on the output box; xv = x inside the input box, 0 outside (one frame).
+    Differentiable w.r.t. x, scale and shift."""
+    return _AffineReLUGeo.apply(x, scale, shift, tuple(int(v) for v in in_origin), tuple(int(v) for v in out_origin),
+                                tuple(int(v) for v in out_dims), bool(relu))

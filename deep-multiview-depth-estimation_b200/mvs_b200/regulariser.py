@@ -164,8 +164,34 @@ class CostVolumeReg(nn.Module):
         S_all = be.conv3d(x, w_cat, 2, P)[(slice(None), slice(None)) + cut]
         S_split = dict(zip((1, 2, 3), torch.split(S_all, [self.conv_1_0.out_channels, self.conv_2_0.out_channels,
                                                           self.conv_3_0.out_channels], 1)))
+        C_lo = [lo for lo, _, _ in reg]
+        C_dims = [hi - lo + 1 for lo, hi, _ in reg]
+        F_dims = [F_hi[ax] - F_lo[ax] + 1 for ax in range(3)]
+        E_dims = [E_hi[ax] - E_lo[ax] + 1 for ax in range(3)]
         for k, bn in ((1, self.BN_1), (2, self.BN_2), (3, self.BN_3)):
             S = S_split[k]
+            Wk = self._w(f"conv_{k}_1", dt)
+            if x.is_cuda:
+                # GPU: statistics and normalisation of the box tensors in libmvs_b200.so (K3d), per-channel algebra here
+                if train:
+                    s1, s2 = ops.channel_sums(S)
+                    mean64 = s1.double() / n_full
+                    mean, var = mean64.float(), (s2.double() / n_full - mean64 * mean64).clamp_min(0).float()
+                else:
+                    mean = var = None
+                scale, shift = self._bn_affine(bn, mean, var, n_full)
+                bg = F.relu(shift)                                            # everywhere else on the canvas
+                # conv_k_1 input over F = C dilated by 2 (clipped): data on C, BatchNorm'd zero (= bg) around it
+                X = ops.affine_relu_geo(S, scale, shift, C_lo, F_lo, F_dims)
+                if any(zpad):
+                    X = F.pad(X, zpad)                                        # canvas border -> zero padding
+                T = be.conv3d(X if X.dtype == dt else X.to(dt), Wk, 1, (0, 0, 0))      # output exactly on E
+                if train:
+                    t1, t2 = ops.channel_sums(T)
+                    mean, var = self._stats_from_sums_with_constant_outside(t1, t2, Wk.float(), bg, dims, E_lo, E_hi, B, n_full)
+                scale, shift = self._bn_affine(bn, mean if train else None, var if train else None, n_full)
+                enc[k] = ops.affine_relu_geo(T, scale, shift, E_lo, C_lo, C_dims).float()      # on C
+                continue
             Sf = S.float()
             if train:
                 mean = Sf.sum((0, 2, 3, 4)) / n_full
@@ -179,7 +205,6 @@ class CostVolumeReg(nn.Module):
             # conv_k_1 input over F = C dilated by 2 (clipped): background constant + real data on C
             X = F.pad(a - _bview(bg), bgpad) + _bview(bg)
             X = F.pad(X, zpad)                                                # canvas border -> zero padding
-            Wk = self._w(f"conv_{k}_1", dt)
             T = be.conv3d(X.to(dt).contiguous(memory_format=torch.channels_last_3d), Wk, 1, (0, 0, 0))   # output exactly on E
             Tf = T.float()
             if train:
@@ -204,6 +229,36 @@ class CostVolumeReg(nn.Module):
         if z.is_cuda and dt == torch.bfloat16 and z.shape[1] == 8 and self.conv_out.out_channels == 1:
             return ops.conv_out(z, self.conv_out.weight)              # K3c: 8 -> 1 is streaming work, not a GEMM
         return be.conv3d(z, self._w("conv_out", dt), 1, (1, 1, 1)).float()
+
+    @staticmethod
+    def _outside_classes(Wf, bg, dims, E_lo, E_hi, B):
+        """Values and voxel counts of the 27 border classes of a stride-1, pad-1 conv output outside the box E when its
+        input is the per-channel constant `bg` there: ([Cout,3,3,3] values, [3,3,3] counts)."""
+        dev = Wf.device
+        M = torch.tensor([[0., 1., 1.], [1., 1., 1.], [1., 1., 0.]], device=dev)       # [edge class][tap valid]
+        val = torch.einsum("oidhw,ad,bh,cw,i->oabc", Wf, M, M, M, bg)                   # [Cout,3,3,3]
+        full = [torch.tensor([1., n - 2., 1.], device=dev) for n in dims]
+        inside = []
+        for ax, n in enumerate(dims):
+            lo_edge = 1.0 if E_lo[ax] == 0 else 0.0
+            hi_edge = 1.0 if E_hi[ax] == n - 1 else 0.0
+            inside.append(torch.tensor([lo_edge, (E_hi[ax] - E_lo[ax] + 1) - lo_edge - hi_edge, hi_edge], device=dev))
+        cnt = B * (torch.einsum("a,b,c->abc", *full) - torch.einsum("a,b,c->abc", *inside))
+        return val, cnt
+
+    @classmethod
+    def _stats_from_sums_with_constant_outside(cls, t1, t2, Wf, bg, dims, E_lo, E_hi, B, n_full):
+        """Same statistics as _stats_with_constant_outside, from the per-channel sums (sum T, sum T^2) over E."""
+        val, cnt = cls._outside_classes(Wf, bg, dims, E_lo, E_hi, B)
+        val, cnt = val.double(), cnt.double()
+        n_e = float(B)
+        for ax in range(3):
+            n_e *= (E_hi[ax] - E_lo[ax] + 1)
+        mean = (t1.double() + (val * cnt).sum((1, 2, 3))) / n_full
+        inside = t2.double() - 2.0 * mean * t1.double() + n_e * mean * mean
+        outside = ((val - mean.view(-1, 1, 1, 1)).pow(2) * cnt).sum((1, 2, 3))
+        var = ((inside + outside) / n_full).clamp_min(0)
+        return mean.float(), var.float()
 
     @staticmethod
     def _stats_with_constant_outside(T, Wf, bg, dims, E_lo, E_hi, B, n_full):

@@ -174,6 +174,27 @@ int mvsb200_bn_relu_bwd_crop(const void* x, int x_dtype, const void* gy, int g_d
                              float* workspace, float* dbeta, float* dgamma, void* dx, int relu, int64_t M, int C,
                              const int* geo12_host, void* stream);
 
+/* ---- K3d: per-channel sums and affine+ReLU over boxes of channel-last volumes -------------------------
+ * The BatchNorm3d + ReLU pairs of the stride-2 branches (scripts/model.py:104-113) evaluated on the central box
+ * where those layers carry data (padding dim/2+1, scripts/config.py:20); the constant remainder of the canvas enters
+ * the statistics analytically on the host (mvs_b200/regulariser.py).
+ * x: a [B, C, D, h, w] view with unit channel stride; strides4 (HOST int64, elements) = {b, d, h, w}; dims4 (HOST)
+ * = {B, D, h, w}; C in {8,16,32,64}; dtype f32/bf16.  workspace: mvsb200_affine_workspace_floats() floats.
+ *   channel_sums        s1[c] = sum x, s2[c] = sum x^2 (deterministic);  _bwd: gx = g1[c] + 2 x g2[c]  (dense)
+ *   affine_relu_geo     geo13 (HOST) = {B, Id, Ih, Iw, in_origin[3], out_origin[3], out_dims[3]} in one frame:
+ *                       y(p) = max(xv(p) scale[c] + shift[c], 0) on the output box, xv = x inside the input box, 0 outside.
+ *                       y, gy: dense [B, od, oh, ow, C]; gx: dense over the input box; gscale/gshift: [C]. */
+int64_t mvsb200_affine_workspace_floats(void);
+int mvsb200_channel_sums(const void* x, int dtype, const int64_t* strides4_host, const int* dims4_host, int C,
+                         float* workspace, float* s1, float* s2, void* stream);
+int mvsb200_channel_sums_bwd(const void* x, int dtype, const int64_t* strides4_host, const int* dims4_host, int C,
+                             const float* g1, const float* g2, void* gx, void* stream);
+int mvsb200_affine_relu_geo_fwd(const void* x, int dtype, const int64_t* strides4_host, const int* geo13_host, int C,
+                                const float* scale, const float* shift, void* y, int relu, void* stream);
+int mvsb200_affine_relu_geo_bwd(const void* x, int x_dtype, const int64_t* strides4_host, const int* geo13_host, int C,
+                                const float* scale, const float* shift, const void* gy, int g_dtype, float* workspace,
+                                float* gscale, float* gshift, void* gx, int relu, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
