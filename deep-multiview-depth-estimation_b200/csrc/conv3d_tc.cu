@@ -462,6 +462,330 @@ int launch_conv(const void* x, const void* w, void* y, int B, int Di, int Hi, in
     return MVSB200_OK;
 }
 
+// =================================================================================================================
+// Weight gradient of the same convolution on tcgen05:  gW[tap][ci][co] = sum_v x(v + tap + off)[ci] * gy(v)[co].
+// Per tap this is a GEMM whose REDUCTION runs over voxels: D[M = ci, N = co] += A[M, K = 16 voxels] * B[K, N].  In shared
+// memory both operands have the voxel (K) as the row and the channels contiguous, i.e. they are MN-major UMMA operands:
+//   A = the same halo'd, TMA-written x slab as in the forward kernel, read from row (k0 + kh*BW + kw) for tap (kh, kw);
+//       its Cin channels are one swizzle atom along M; M = 128 is presented by repeating that atom (leading byte offset 0),
+//       rows >= Cin of D are copies and are never read back;
+//   B = the gy tile of the plane, written by TMA line by line at the slab's pitch BW (the two halo columns of every line
+//       and everything past the tile stay zero, so halo rows contribute nothing).
+// The accumulators of all taps of the launch stay in TMEM over the CTA's whole run (taps x co <= 512 columns: wide
+// layers are launched per kd / per 32-channel half) and are added to gW with fp32 reductions at the end.
+struct WgradParams {
+    int B, Do, Ho, Wo;              // gy volume
+    int off_d, off_h, off_w;
+    int BW, L, MB;
+    int tiles_x, tiles_y;
+    int dchunk, nchunks, n_items;
+    int kd0, nkd;                   // depth taps handled by this launch
+    int co0;                        // first gy channel handled by this launch
+    int cout;                       // real output channels of the layer (row length of gW)
+    int slab_bytes, gy_bytes;       // per ring slot / per gy stage, multiples of 1024
+    int ksteps;                     // ceil(L*BW / 16)
+    float* gw;                      // [27][CIN][cout] fp32, accumulated into
+};
+
+// MN-major operand descriptor: rows (K) are ROWB bytes apart, one swizzle atom of ROWB bytes along MN
+template <int ROWB>
+__device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr) {
+    constexpr uint64_t layout = ROWB == 128 ? 2 : (ROWB == 64 ? 4 : (ROWB == 32 ? 6 : 0));
+    uint64_t d = (uint64_t)((saddr >> 4) & 0x3fff);
+    if (ROWB == 16) {
+        d |= (uint64_t)(128 >> 4) << 16;              // no swizzle: LBO = stride between 8-row K groups
+        d |= (uint64_t)0 << 32;                       //             SBO = stride between 8-channel MN atoms: 0 => repeats
+    } else {
+        d |= (uint64_t)0 << 16;                       // LBO = stride between MN atoms: 0 => the atom repeats along M
+        d |= (uint64_t)((8 * ROWB) >> 4) << 32;       // SBO = stride between 8-row K groups
+    }
+    d |= (uint64_t)1 << 46;
+    d |= layout << 61;
+    return d;
+}
+
+__device__ __forceinline__ void tma_load_5d_box(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3, int c4) {
+    tma_load_5d(dst, map, bar, c0, c1, c2, c3, c4);
+}
+
+template <int CIN, int NCO>
+__global__ void __launch_bounds__(kTcThreads, 1)
+conv3d_s1_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_g, const WgradParams p) {
+    constexpr int ROWX = CIN * 2, ROWG = NCO * 2;
+    constexpr int UN = NCO < 16 ? 16 : NCO;             // UMMA N (M = 128 needs N % 16 == 0): 8 channels are presented twice
+    // D fp32, A/B bf16, A and B MN-major, N = UN, M = 128
+    constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(UN >> 3) << 17) | ((128u >> 4) << 24);
+
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
+    unsigned char* slab_smem = smem;
+    unsigned char* gy_smem = smem + (size_t)kSlots3 * p.slab_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(gy_smem + (size_t)2 * p.gy_bytes);
+    uint64_t* full = bars;                  // [kSlots3] x slab landed
+    uint64_t* empty = bars + kSlots3;       // [kSlots3] x slab free
+    uint64_t* gfull = bars + 2 * kSlots3;   // [2] gy tile landed
+    uint64_t* gempty = gfull + 2;           // [2] gy tile free
+    uint64_t* done = gempty + 2;            // [1] all MMAs complete
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles = p.tiles_x * p.tiles_y;
+    const int ntaps = p.nkd * 9;
+    uint32_t tmem_cols = 32;
+    while ((int)tmem_cols < ntaps * UN) tmem_cols <<= 1;
+
+    // zero what TMA never writes: the slab tails (read by the last K step) and the whole gy stages (halo columns, tail)
+    {
+        const int box_rows = (p.L + 2) * p.BW;
+        for (int s = 0; s < kSlots3; ++s) {
+            uint4* tail = reinterpret_cast<uint4*>(slab_smem + (size_t)s * p.slab_bytes + (size_t)box_rows * ROWX);
+            const int n = (p.slab_bytes - box_rows * ROWX) / 16;
+            for (int i = threadIdx.x; i < n; i += kTcThreads) tail[i] = make_uint4(0, 0, 0, 0);
+        }
+        uint4* g = reinterpret_cast<uint4*>(gy_smem);
+        for (int i = threadIdx.x; i < 2 * p.gy_bytes / 16; i += kTcThreads) g[i] = make_uint4(0, 0, 0, 0);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (threadIdx.x == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_x) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_g) : "memory");
+        for (int i = 0; i < kSlots3; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(gfull + i, 1); mbar_init(gempty + i, 1); }
+        mbar_init(done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    auto decode = [&](int item, int& b, int& d_begin, int& nd, int& x0, int& y0) {
+        const int t = item % tiles, r = item / tiles;
+        const int c = r % p.nchunks;
+        b = r / p.nchunks;
+        d_begin = c * p.dchunk;
+        nd = min(p.dchunk, p.Do - d_begin);
+        x0 = (t % p.tiles_x) * (p.BW - 2);
+        y0 = (t / p.tiles_x) * p.L;
+    };
+    const int nslab_extra = p.nkd - 1;      // input planes per run = nd + nkd - 1
+
+    if (warp == 0) {
+        // ===================================== TMA producer: x slabs and gy tiles ================
+        const uint32_t box_bytes = (uint32_t)ROWX * p.BW * (p.L + 2);
+        const uint32_t line_bytes = (uint32_t)ROWG * (p.BW - 2);
+        int gs = 0, gp = 0;
+        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+            int b, d_begin, nd, x0, y0;
+            decode(item, b, d_begin, nd, x0, y0);
+            const int nslab = nd + nslab_extra;
+            int s = 0;
+            for (int d = 0; d < nd; ++d, ++gp) {
+                // slabs needed by gy plane d: s <= d + nkd - 1
+                for (; s < nslab && s <= d + nslab_extra; ++s, ++gs) {
+                    const int slot = gs % kSlots3;
+                    if (gs >= kSlots3) mbar_wait(empty + slot, ((gs / kSlots3) - 1) & 1);
+                    if (elect_one()) {
+                        mbar_expect_tx(full + slot, box_bytes);
+                        tma_load_5d(slab_smem + (size_t)slot * p.slab_bytes, &tm_x, full + slot, 0, x0 + p.off_w, y0 + p.off_h,
+                                    d_begin + p.off_d + p.kd0 + s, b);
+                    }
+                    __syncwarp();
+                }
+                const int st = gp & 1;
+                if (gp >= 2) mbar_wait(gempty + st, ((gp >> 1) - 1) & 1);
+                if (elect_one()) {
+                    mbar_expect_tx(gfull + st, line_bytes * p.L);
+                    for (int j = 0; j < p.L; ++j)      // line j of the tile -> rows j*BW .. j*BW + BW-3 (out of range => zeros)
+                        tma_load_5d(gy_smem + (size_t)st * p.gy_bytes + (size_t)j * p.BW * ROWG, &tm_g, gfull + st, p.co0, x0, y0 + j,
+                                    d_begin + d, b);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================== MMA issuer =======================================
+        const uint64_t da0 = umma_desc_mn<ROWX>(0), db0 = umma_desc_mn<ROWG>(0);
+        const uint32_t a_hi = (uint32_t)(da0 >> 32), b_hi = (uint32_t)(db0 >> 32);
+        const uint32_t slab_lo = (uint32_t)da0 | (smem_u32(slab_smem) >> 4);
+        const uint32_t gy_lo = (uint32_t)db0 | (smem_u32(gy_smem) >> 4);
+        const uint32_t bw16 = (uint32_t)(p.BW * ROWX) >> 4, slab16 = (uint32_t)p.slab_bytes >> 4, gy16 = (uint32_t)p.gy_bytes >> 4;
+        int gs0 = 0, gp = 0, landed = 0;
+        uint32_t first = 1;                              // the CTA's first gy plane initialises the accumulators
+        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+            int b, d_begin, nd, x0, y0;
+            decode(item, b, d_begin, nd, x0, y0);
+            for (int d = 0; d < nd; ++d, ++gp) {
+                const int st = gp & 1;
+                while (landed <= gs0 + d + nslab_extra) { mbar_wait(full + landed % kSlots3, (landed / kSlots3) & 1); ++landed; }
+                mbar_wait(gfull + st, (gp >> 1) & 1);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t g_lo = gy_lo + (uint32_t)st * gy16;
+                    for (int kd = 0; kd < p.nkd; ++kd) {
+                        const uint32_t s_lo = slab_lo + (uint32_t)((gs0 + d + kd) % kSlots3) * slab16;
+#pragma unroll
+                        for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+                            for (int kw = 0; kw < 3; ++kw) {
+                                const uint32_t d_tmem = tmem_base + (uint32_t)(((kd * 3 + kh) * 3 + kw) * UN);
+                                uint32_t a_lo = s_lo + kh * bw16 + (uint32_t)((kw * ROWX) >> 4);
+                                uint32_t b_lo = g_lo;
+                                for (int ks = 0; ks < p.ksteps; ++ks) {
+                                    umma_bf16_lohi(d_tmem, a_lo, a_hi, b_lo, b_hi, IDESC, (first ^ 1u) | (uint32_t)(ks != 0));
+                                    a_lo += (uint32_t)(16 * ROWX) >> 4;
+                                    b_lo += (uint32_t)(16 * ROWG) >> 4;
+                                }
+                            }
+                        }
+                    }
+                    umma_commit(empty + (gs0 + d) % kSlots3);
+                    if (d == nd - 1)
+                        for (int e = 1; e <= nslab_extra; ++e) umma_commit(empty + (gs0 + d + e) % kSlots3);
+                    umma_commit(gempty + st);
+                }
+                __syncwarp();
+                first = 0;
+            }
+            gs0 += nd + nslab_extra;
+        }
+        if (elect_one()) umma_commit(done);
+        __syncwarp();
+    } else {
+        // ===================================== epilogue: TMEM -> gW ==============================
+        mbar_wait(done, 0);
+        tc_fence_after();
+        const int q = warp & 3;
+        const int ci = q * 32 + lane;                    // D row = input channel
+        const bool has_work = blockIdx.x < p.n_items;
+        for (int t = 0; t < ntaps; ++t) {
+            if (q * 32 < CIN) {                          // warp-uniform: this lane quarter holds real rows
+                uint32_t v[NCO >= 16 ? NCO : 16];
+                if (NCO >= 32) {
+#pragma unroll
+                    for (int c = 0; c < NCO; c += 32) {
+                        uint32_t w[32];
+                        tmem_ld<32>(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * UN + c), w);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int k = 0; k < 32; ++k) v[(c + k) % (NCO >= 16 ? NCO : 16)] = w[k];
+                    }
+                } else {
+                    uint32_t w[16];
+                    tmem_ld<16>(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * UN), w);    // NCO = 8: columns 8..15 are copies
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) v[k] = w[k];
+                }
+                if (has_work && ci < CIN) {
+                    float* row = p.gw + ((size_t)(p.kd0 * 9 + t) * CIN + ci) * p.cout + p.co0;
+#pragma unroll
+                    for (int c = 0; c < NCO; ++c)
+                        if (p.co0 + c < p.cout) atomicAdd(row + c, __uint_as_float(v[c]));
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+    }
+}
+
+TilePlan plan_tiles_wgrad(int Ho, int Wo, int rowx, int rowg, size_t smem_budget) {
+    TilePlan best{};
+    best.score = -1.0;
+    for (int MB = 1; MB <= kMaxMB; MB *= 2) {
+        for (int BW = 16; BW <= 256; BW += 8) {                // BW*rowg must be a multiple of 128 (TMA destination of a gy line)
+            if ((BW * rowg) % 128) continue;
+            const int L = (MB * 128) / BW;
+            if (L < 1 || L + 2 > 256) continue;
+            const int rows = MB * 128 + 2 * BW + 2 + 16;
+            const int slab = ((rows * rowx) + 1023) / 1024 * 1024;
+            const int gyb = ((MB * 128 + 16) * rowg + 1023) / 1024 * 1024;
+            if ((size_t)kSlots3 * slab + 2 * (size_t)gyb + 256 > smem_budget) continue;
+            const int tiles_x = (Wo + BW - 3) / (BW - 2), tiles_y = (Ho + L - 1) / L;
+            const double eff = (double)Wo * Ho / ((double)tiles_x * tiles_y * MB * 128);
+            const double load_eff = (double)Wo * Ho / ((double)tiles_x * tiles_y * (L + 2) * BW);
+            const double score = eff * (0.5 + 0.5 * load_eff);
+            if (score > best.score) best = TilePlan{BW, L, MB, tiles_x, tiles_y, slab, score};
+        }
+    }
+    return best;
+}
+
+template <int CIN, int NCO>
+int launch_wgrad(const void* x, const void* gy, float* gw, int B, int Di, int Hi, int Wi, int Do, int Ho, int Wo, int cout, int co0,
+                 int kd0, int nkd, int off_d, int off_h, int off_w, cudaStream_t st) {
+    constexpr int ROWX = CIN * 2, ROWG = NCO * 2;
+    EncodeTiledFn enc = encode_fn();
+    MVS_REQUIRE(enc != nullptr, "conv3d_s1_wgrad: cuTensorMapEncodeTiled is not available from the driver");
+    const size_t smem_budget = 227 * 1024 - 1024;
+    const TilePlan tp = plan_tiles_wgrad(Ho, Wo, ROWX, ROWG, smem_budget);
+    MVS_REQUIRE(tp.score > 0, "conv3d_s1_wgrad: no slab geometry fits shared memory (Cin=%d, N=%d)", CIN, NCO);
+    const int gy_bytes = ((tp.MB * 128 + 16) * ROWG + 1023) / 1024 * 1024;
+
+    CUtensorMap tm_x, tm_g;
+    {
+        const cuuint64_t dims[5] = {(cuuint64_t)CIN, (cuuint64_t)Wi, (cuuint64_t)Hi, (cuuint64_t)Di, (cuuint64_t)B};
+        const cuuint64_t strides[4] = {(cuuint64_t)ROWX, (cuuint64_t)ROWX * Wi, (cuuint64_t)ROWX * Wi * Hi, (cuuint64_t)ROWX * Wi * Hi * Di};
+        const cuuint32_t box[5] = {(cuuint32_t)CIN, (cuuint32_t)tp.BW, (cuuint32_t)(tp.L + 2), 1, 1};
+        const cuuint32_t es[5] = {1, 1, 1, 1, 1};
+        CUresult r = enc(&tm_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), dims, strides, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(ROWX), CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        MVS_REQUIRE(r == CUDA_SUCCESS, "conv3d_s1_wgrad: cuTensorMapEncodeTiled(x) failed (%d)", (int)r);
+    }
+    {
+        const cuuint64_t rowb = (cuuint64_t)cout * 2;
+        const cuuint64_t dims[5] = {(cuuint64_t)cout, (cuuint64_t)Wo, (cuuint64_t)Ho, (cuuint64_t)Do, (cuuint64_t)B};
+        const cuuint64_t strides[4] = {rowb, rowb * Wo, rowb * Wo * Ho, rowb * Wo * Ho * Do};
+        const cuuint32_t box[5] = {(cuuint32_t)NCO, (cuuint32_t)(tp.BW - 2), 1, 1, 1};
+        const cuuint32_t es[5] = {1, 1, 1, 1, 1};
+        const CUtensorMapSwizzle sw = ROWG == 16 ? CU_TENSOR_MAP_SWIZZLE_NONE : swizzle_for(ROWG);
+        CUresult r = enc(&tm_g, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(gy), dims, strides, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        MVS_REQUIRE(r == CUDA_SUCCESS, "conv3d_s1_wgrad: cuTensorMapEncodeTiled(gy) failed (%d)", (int)r);
+    }
+    WgradParams p;
+    p.B = B; p.Do = Do; p.Ho = Ho; p.Wo = Wo; p.off_d = off_d; p.off_h = off_h; p.off_w = off_w;
+    p.BW = tp.BW; p.L = tp.L; p.MB = tp.MB; p.tiles_x = tp.tiles_x; p.tiles_y = tp.tiles_y;
+    p.kd0 = kd0; p.nkd = nkd; p.co0 = co0; p.cout = cout; p.slab_bytes = tp.slab_bytes; p.gy_bytes = gy_bytes;
+    p.ksteps = (tp.L * tp.BW + 15) / 16;
+    p.gw = gw;
+    const long tiles = (long)tp.tiles_x * tp.tiles_y;
+    int sms = 148;
+    {
+        int dev = 0, n = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) sms = n;
+    }
+    long best_cost = -1;
+    int best_chunks = 1;
+    for (int nc = 1; nc <= Do; ++nc) {
+        const int dc = (Do + nc - 1) / nc;
+        if ((long)(nc - 1) * dc >= Do) continue;
+        const long items = tiles * nc * B;
+        const long cost = ((items + sms - 1) / sms) * (dc + nkd + 1);
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_chunks = nc; }
+    }
+    p.nchunks = best_chunks;
+    p.dchunk = (Do + best_chunks - 1) / best_chunks;
+    p.n_items = (int)(tiles * p.nchunks * B);
+    const dim3 grid((unsigned)(p.n_items < sms ? p.n_items : sms), 1, 1);
+    const size_t smem = 1024 + (size_t)kSlots3 * tp.slab_bytes + 2 * (size_t)gy_bytes + 256;
+    MVS_CUDA(cudaFuncSetAttribute(conv3d_s1_wgrad_tc_kernel<CIN, NCO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conv3d_s1_wgrad_tc_kernel<CIN, NCO><<<grid, kTcThreads, smem, st>>>(tm_x, tm_g, p);
+    MVS_CHECK_LAUNCH("conv3d_s1_wgrad_tc");
+    return MVSB200_OK;
+}
+
 }  // namespace
 
 extern "C" int mvsb200_conv3d_s1_fwd(const void* x, const void* w_packed, void* y, int B, int Di, int Hi, int Wi, int Cin,
@@ -491,6 +815,39 @@ extern "C" int mvsb200_conv3d_s1_fwd(const void* x, const void* w_packed, void* 
         else MVS_FAIL(MVSB200_E_UNSUPPORTED, "conv3d_s1_fwd: unsupported channels Cin=%d n_rows=%d", Cin, n_rows);
 #undef MVS_CONV
         if (rc != MVSB200_OK) return rc;
+    }
+    return MVSB200_OK;
+}
+
+extern "C" int mvsb200_conv3d_s1_wgrad(const void* x, const void* gy, float* gw, int B, int Di, int Hi, int Wi, int Cin, int Do,
+                                       int Ho, int Wo, int cout, int off_d, int off_h, int off_w, void* stream) {
+    MVS_REQUIRE(x && gy && gw, "conv3d_s1_wgrad: null pointer");
+    MVS_REQUIRE(aligned16(x) && aligned16(gy) && aligned16(gw), "conv3d_s1_wgrad: pointers must be 16-byte aligned");
+    MVS_REQUIRE(B >= 1 && Di >= 1 && Hi >= 1 && Wi >= 1 && Do >= 1 && Ho >= 1 && Wo >= 1, "conv3d_s1_wgrad: bad shape");
+    MVS_REQUIRE(cout == 8 || cout == 16 || cout == 32 || cout == 64, "conv3d_s1_wgrad: cout must be 8, 16, 32 or 64 (got %d)", cout);
+    cudaStream_t st = (cudaStream_t)stream;
+    MVS_CUDA(cudaMemsetAsync(gw, 0, (size_t)27 * Cin * cout * sizeof(float), st));
+    // taps x channels per launch <= 512 TMEM columns: all 27 taps for co <= 16, one depth tap (9 taps) per launch above;
+    // 64 output channels additionally in two 32-channel halves
+    const int nco = cout < 32 ? cout : 32;
+    const int nkd = cout <= 16 ? 3 : 1;
+    for (int co0 = 0; co0 < cout; co0 += nco) {
+        for (int kd0 = 0; kd0 < 3; kd0 += nkd) {
+            int rc = MVSB200_E_UNSUPPORTED;
+#define MVS_WG(CI, NC) rc = launch_wgrad<CI, NC>(x, gy, gw, B, Di, Hi, Wi, Do, Ho, Wo, cout, co0, kd0, nkd, off_d, off_h, off_w, st)
+            if (Cin == 16 && nco == 8) MVS_WG(16, 8);
+            else if (Cin == 16 && nco == 16) MVS_WG(16, 16);
+            else if (Cin == 16 && nco == 32) MVS_WG(16, 32);
+            else if (Cin == 32 && nco == 8) MVS_WG(32, 8);
+            else if (Cin == 32 && nco == 16) MVS_WG(32, 16);
+            else if (Cin == 32 && nco == 32) MVS_WG(32, 32);
+            else if (Cin == 64 && nco == 8) MVS_WG(64, 8);
+            else if (Cin == 64 && nco == 16) MVS_WG(64, 16);
+            else if (Cin == 64 && nco == 32) MVS_WG(64, 32);
+            else MVS_FAIL(MVSB200_E_UNSUPPORTED, "conv3d_s1_wgrad: unsupported channels Cin=%d cout=%d", Cin, cout);
+#undef MVS_WG
+            if (rc != MVSB200_OK) return rc;
+        }
     }
     return MVSB200_OK;
 }

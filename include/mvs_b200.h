@@ -128,6 +128,13 @@ int mvsb200_conv3d_s1_fwd(const void* x, const void* w_packed, void* y, int B, i
                           int Do, int Ho, int Wo, int cout, int y_cs, int n_rows, int off_d, int off_h, int off_w,
                           void* stream);
 
+/* Weight gradient of the same convolution on tcgen05 (autograd of scripts/model.py:101-113 w.r.t. the filters):
+ *   gW[tap][ci][co] = sum_v x(v + tap + off)[ci] * gy(v)[co]
+ * x: [B, Di, Hi, Wi, Cin] bf16; gy: [B, Do, Ho, Wo, cout] bf16 (cout in {8,16,32,64}); gw: [27, Cin, cout] fp32,
+ * ZEROED BY THIS CALL, then accumulated with fp32 reductions (summation order across CTAs is not fixed). */
+int mvsb200_conv3d_s1_wgrad(const void* x, const void* gy, float* gw, int B, int Di, int Hi, int Wi, int Cin,
+                            int Do, int Ho, int Wo, int cout, int off_d, int off_h, int off_w, void* stream);
+
 /* ---- K3c: the output convolution 8 -> 1 channels (k = 3, stride 1, padding 1) -----------------------
  * Replaces conv_out = Conv3d(8, 1, 3, padding=1, bias=False) (scripts/model.py:91, used at :123) and its two
  * gradients.  z: [B, D, h, w, 8] bf16 (the sum y1 + y0, channels_last_3d); w27x8: [27, 8] fp32, tap-major
