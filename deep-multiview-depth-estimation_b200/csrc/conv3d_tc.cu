@@ -464,55 +464,55 @@ int launch_conv(const void* x, const void* w, void* y, int B, int Di, int Hi, in
 
 // =================================================================================================================
 // Weight gradient of the same convolution on tcgen05:  gW[tap][ci][co] = sum_v x(v + tap + off)[ci] * gy(v)[co].
-// Per tap this is a GEMM whose REDUCTION runs over voxels: D[M = ci, N = co] += A[M, K = 16 voxels] * B[K, N].  In shared
-// memory both operands have the voxel (K) as the row and the channels contiguous, i.e. they are MN-major UMMA operands:
-//   A = the same halo'd, TMA-written x slab as in the forward kernel, read from row (k0 + kh*BW + kw) for tap (kh, kw);
-//       its Cin channels are one swizzle atom along M; M = 128 is presented by repeating that atom (leading byte offset 0),
-//       rows >= Cin of D are copies and are never read back;
-//   B = the gy tile of the plane, written by TMA line by line at the slab's pitch BW (the two halo columns of every line
-//       and everything past the tile stay zero, so halo rows contribute nothing).
-// The accumulators of all taps of the launch stay in TMEM over the CTA's whole run (taps x co <= 512 columns: wide
-// layers are launched per kd / per 32-channel half) and are added to gW with fp32 reductions at the end.
+// The REDUCTION runs over voxels: D[M, N] += A[M, K = 16 voxels] * B[K, N].  In shared memory both operands have the voxel
+// (K) as the row and the channels contiguous, i.e. they are MN-major UMMA operands, and a swizzle atom of an MN-major
+// operand may start at ANY row -- which lets one MMA cover 9 taps of a depth slice:
+//   A = the halo'd, TMA-written x slab of the forward kernel.  Its M extent is built from atoms of Cin channels whose
+//       stride (the descriptor's leading byte offset) is ONE VOXEL ROW: atom kw is the slab shifted by kw voxels, so
+//       D rows are (kw, ci).
+//   B = the gy tile of the plane, written by TMA line by line at the slab's pitch BW behind 2*BW rows of zeros (halo
+//       columns and everything outside the tile stay zero).  Its N extent is built from atoms of co channels whose
+//       stride is ONE LINE (BW rows): atom n is the tile shifted by n lines, so D columns are (kh = 2 - n, co):
+//       sum_v x[v + kw] * gy[v - kh*BW] = sum_r x[r + kh*BW + kw] * gy[r].
+// One accumulator block per depth tap kd stays in TMEM over the CTA's whole run (<= 512 columns; 64-channel gy in
+// 32-channel halves, 64-channel x with its third kw tap in a second block) and is added to gW with fp32 reductions.
 struct WgradParams {
     int B, Do, Ho, Wo;              // gy volume
     int off_d, off_h, off_w;
-    int BW, L, MB;
+    int BW, L;                      // slab pitch (voxels per line incl. 2 halo), gy lines per tile
     int tiles_x, tiles_y;
     int dchunk, nchunks, n_items;
-    int kd0, nkd;                   // depth taps handled by this launch
     int co0;                        // first gy channel handled by this launch
     int cout;                       // real output channels of the layer (row length of gW)
     int slab_bytes, gy_bytes;       // per ring slot / per gy stage, multiples of 1024
-    int ksteps;                     // ceil(L*BW / 16)
+    int ksteps;                     // ceil((L+2)*BW / 16)
     float* gw;                      // [27][CIN][cout] fp32, accumulated into
 };
 
-// MN-major operand descriptor: rows (K) are ROWB bytes apart, one swizzle atom of ROWB bytes along MN
+// MN-major operand descriptor: rows (K) are ROWB bytes apart (= one swizzle atom of channels), MN atoms `atom_stride`
+// bytes apart
 template <int ROWB>
-__device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr) {
+__device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr, uint32_t atom_stride) {
     constexpr uint64_t layout = ROWB == 128 ? 2 : (ROWB == 64 ? 4 : (ROWB == 32 ? 6 : 0));
     uint64_t d = (uint64_t)((saddr >> 4) & 0x3fff);
     if (ROWB == 16) {
-        d |= (uint64_t)(128 >> 4) << 16;              // no swizzle: LBO = stride between 8-row K groups
-        d |= (uint64_t)0 << 32;                       //             SBO = stride between 8-channel MN atoms: 0 => repeats
+        d |= (uint64_t)(128 >> 4) << 16;                      // no swizzle: LBO = stride between 8-row K groups
+        d |= (uint64_t)((atom_stride >> 4) & 0x3fff) << 32;   //             SBO = stride between 8-channel MN atoms
     } else {
-        d |= (uint64_t)0 << 16;                       // LBO = stride between MN atoms: 0 => the atom repeats along M
-        d |= (uint64_t)((8 * ROWB) >> 4) << 32;       // SBO = stride between 8-row K groups
+        d |= (uint64_t)((atom_stride >> 4) & 0x3fff) << 16;   // LBO = stride between MN atoms
+        d |= (uint64_t)((8 * ROWB) >> 4) << 32;               // SBO = stride between 8-row K groups
     }
     d |= (uint64_t)1 << 46;
     d |= layout << 61;
     return d;
 }
 
-__device__ __forceinline__ void tma_load_5d_box(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3, int c4) {
-    tma_load_5d(dst, map, bar, c0, c1, c2, c3, c4);
-}
-
 template <int CIN, int NCO>
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv3d_s1_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_g, const WgradParams p) {
     constexpr int ROWX = CIN * 2, ROWG = NCO * 2;
-    constexpr int UN = NCO < 16 ? 16 : NCO;             // UMMA N (M = 128 needs N % 16 == 0): 8 channels are presented twice
+    constexpr int UN = (3 * NCO + 15) / 16 * 16;        // UMMA N: atoms kh = 2,1,0 (+ a junk atom when 3*NCO % 16 != 0)
+    constexpr int KWB = CIN == 64 ? 2 : 1;              // A blocks per depth tap: 64-channel atoms fit twice into M = 128
     // D fp32, A/B bf16, A and B MN-major, N = UN, M = 128
     constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(UN >> 3) << 17) | ((128u >> 4) << 24);
 
@@ -530,11 +530,10 @@ conv3d_s1_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles = p.tiles_x * p.tiles_y;
-    const int ntaps = p.nkd * 9;
     uint32_t tmem_cols = 32;
-    while ((int)tmem_cols < ntaps * UN) tmem_cols <<= 1;
+    while ((int)tmem_cols < 3 * KWB * UN) tmem_cols <<= 1;
 
-    // zero what TMA never writes: the slab tails (read by the last K step) and the whole gy stages (halo columns, tail)
+    // zero what TMA never writes: the slab tails (read by the last K step) and the whole gy stages (padding, halo columns)
     {
         const int box_rows = (p.L + 2) * p.BW;
         for (int s = 0; s < kSlots3; ++s) {
@@ -573,7 +572,6 @@ conv3d_s1_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid
         x0 = (t % p.tiles_x) * (p.BW - 2);
         y0 = (t / p.tiles_x) * p.L;
     };
-    const int nslab_extra = p.nkd - 1;      // input planes per run = nd + nkd - 1
 
     if (warp == 0) {
         // ===================================== TMA producer: x slabs and gy tiles ================
@@ -583,17 +581,15 @@ conv3d_s1_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
             int b, d_begin, nd, x0, y0;
             decode(item, b, d_begin, nd, x0, y0);
-            const int nslab = nd + nslab_extra;
             int s = 0;
             for (int d = 0; d < nd; ++d, ++gp) {
-                // slabs needed by gy plane d: s <= d + nkd - 1
-                for (; s < nslab && s <= d + nslab_extra; ++s, ++gs) {
+                for (; s < nd + 2 && s <= d + 2; ++s, ++gs) {      // input planes needed by gy plane d: s <= d + 2
                     const int slot = gs % kSlots3;
                     if (gs >= kSlots3) mbar_wait(empty + slot, ((gs / kSlots3) - 1) & 1);
                     if (elect_one()) {
                         mbar_expect_tx(full + slot, box_bytes);
                         tma_load_5d(slab_smem + (size_t)slot * p.slab_bytes, &tm_x, full + slot, 0, x0 + p.off_w, y0 + p.off_h,
-                                    d_begin + p.off_d + p.kd0 + s, b);
+                                    d_begin + p.off_d + s, b);
                     }
                     __syncwarp();
                 }
@@ -601,20 +597,21 @@ conv3d_s1_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid
                 if (gp >= 2) mbar_wait(gempty + st, ((gp >> 1) - 1) & 1);
                 if (elect_one()) {
                     mbar_expect_tx(gfull + st, line_bytes * p.L);
-                    for (int j = 0; j < p.L; ++j)      // line j of the tile -> rows j*BW .. j*BW + BW-3 (out of range => zeros)
-                        tma_load_5d(gy_smem + (size_t)st * p.gy_bytes + (size_t)j * p.BW * ROWG, &tm_g, gfull + st, p.co0, x0, y0 + j,
-                                    d_begin + d, b);
+                    for (int j = 0; j < p.L; ++j)      // line j -> rows (2+j)*BW .. (2+j)*BW + BW-3 (out of range => zeros)
+                        tma_load_5d(gy_smem + (size_t)st * p.gy_bytes + (size_t)(2 + j) * p.BW * ROWG, &tm_g, gfull + st, p.co0, x0,
+                                    y0 + j, d_begin + d, b);
                 }
                 __syncwarp();
             }
         }
     } else if (warp == 1) {
         // ===================================== MMA issuer =======================================
-        const uint64_t da0 = umma_desc_mn<ROWX>(0), db0 = umma_desc_mn<ROWG>(0);
+        const uint64_t da0 = umma_desc_mn<ROWX>(0, ROWX);                        // A atoms: one voxel row apart (kw)
+        const uint64_t db0 = umma_desc_mn<ROWG>(0, (uint32_t)(p.BW * ROWG));     // B atoms: one line apart (kh = 2 - n)
         const uint32_t a_hi = (uint32_t)(da0 >> 32), b_hi = (uint32_t)(db0 >> 32);
         const uint32_t slab_lo = (uint32_t)da0 | (smem_u32(slab_smem) >> 4);
         const uint32_t gy_lo = (uint32_t)db0 | (smem_u32(gy_smem) >> 4);
-        const uint32_t bw16 = (uint32_t)(p.BW * ROWX) >> 4, slab16 = (uint32_t)p.slab_bytes >> 4, gy16 = (uint32_t)p.gy_bytes >> 4;
+        const uint32_t slab16 = (uint32_t)p.slab_bytes >> 4, gy16 = (uint32_t)p.gy_bytes >> 4;
         int gs0 = 0, gp = 0, landed = 0;
         uint32_t first = 1;                              // the CTA's first gy plane initialises the accumulators
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
@@ -622,37 +619,37 @@ conv3d_s1_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid
             decode(item, b, d_begin, nd, x0, y0);
             for (int d = 0; d < nd; ++d, ++gp) {
                 const int st = gp & 1;
-                while (landed <= gs0 + d + nslab_extra) { mbar_wait(full + landed % kSlots3, (landed / kSlots3) & 1); ++landed; }
+                while (landed <= gs0 + d + 2) { mbar_wait(full + landed % kSlots3, (landed / kSlots3) & 1); ++landed; }
                 mbar_wait(gfull + st, (gp >> 1) & 1);
                 tc_fence_after();
                 if (elect_one()) {
                     const uint32_t g_lo = gy_lo + (uint32_t)st * gy16;
-                    for (int kd = 0; kd < p.nkd; ++kd) {
+#pragma unroll
+                    for (int kd = 0; kd < 3; ++kd) {
                         const uint32_t s_lo = slab_lo + (uint32_t)((gs0 + d + kd) % kSlots3) * slab16;
 #pragma unroll
-                        for (int kh = 0; kh < 3; ++kh) {
-#pragma unroll
-                            for (int kw = 0; kw < 3; ++kw) {
-                                const uint32_t d_tmem = tmem_base + (uint32_t)(((kd * 3 + kh) * 3 + kw) * UN);
-                                uint32_t a_lo = s_lo + kh * bw16 + (uint32_t)((kw * ROWX) >> 4);
-                                uint32_t b_lo = g_lo;
-                                for (int ks = 0; ks < p.ksteps; ++ks) {
-                                    umma_bf16_lohi(d_tmem, a_lo, a_hi, b_lo, b_hi, IDESC, (first ^ 1u) | (uint32_t)(ks != 0));
-                                    a_lo += (uint32_t)(16 * ROWX) >> 4;
-                                    b_lo += (uint32_t)(16 * ROWG) >> 4;
-                                }
+                        for (int blk = 0; blk < KWB; ++blk) {
+                            const uint32_t d_tmem = tmem_base + (uint32_t)((kd * KWB + blk) * UN);
+                            uint32_t a_lo = s_lo + (uint32_t)((blk * 2 * ROWX) >> 4);      // second block: atoms kw = 2, 3(junk)
+                            uint32_t b_lo = g_lo;
+                            for (int ks = 0; ks < p.ksteps; ++ks) {
+                                umma_bf16_lohi(d_tmem, a_lo, a_hi, b_lo, b_hi, IDESC, (first ^ 1u) | (uint32_t)(ks != 0));
+                                a_lo += (uint32_t)(16 * ROWX) >> 4;
+                                b_lo += (uint32_t)(16 * ROWG) >> 4;
                             }
                         }
                     }
                     umma_commit(empty + (gs0 + d) % kSlots3);
-                    if (d == nd - 1)
-                        for (int e = 1; e <= nslab_extra; ++e) umma_commit(empty + (gs0 + d + e) % kSlots3);
+                    if (d == nd - 1) {
+                        umma_commit(empty + (gs0 + nd) % kSlots3);
+                        umma_commit(empty + (gs0 + nd + 1) % kSlots3);
+                    }
                     umma_commit(gempty + st);
                 }
                 __syncwarp();
                 first = 0;
             }
-            gs0 += nd + nslab_extra;
+            gs0 += nd + 2;
         }
         if (elect_one()) umma_commit(done);
         __syncwarp();
@@ -661,32 +658,28 @@ conv3d_s1_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid
         mbar_wait(done, 0);
         tc_fence_after();
         const int q = warp & 3;
-        const int ci = q * 32 + lane;                    // D row = input channel
-        const bool has_work = blockIdx.x < p.n_items;
-        for (int t = 0; t < ntaps; ++t) {
-            if (q * 32 < CIN) {                          // warp-uniform: this lane quarter holds real rows
-                uint32_t v[NCO >= 16 ? NCO : 16];
-                if (NCO >= 32) {
+        const int row = q * 32 + lane;                   // D row = (kw atom, ci)
+        constexpr int ATOMS = 128 / CIN;                 // kw atoms per block
+        const int kw_in_blk = row / CIN, ci = row % CIN;
+        for (int kd = 0; kd < 3; ++kd) {
 #pragma unroll
-                    for (int c = 0; c < NCO; c += 32) {
-                        uint32_t w[32];
-                        tmem_ld<32>(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * UN + c), w);
-                        tmem_ld_wait();
+            for (int blk = 0; blk < KWB; ++blk) {
+                const int kw = blk * 2 + kw_in_blk;
+                const bool real = kw < 3 && kw_in_blk < ATOMS;
 #pragma unroll
-                        for (int k = 0; k < 32; ++k) v[(c + k) % (NCO >= 16 ? NCO : 16)] = w[k];
-                    }
-                } else {
-                    uint32_t w[16];
-                    tmem_ld<16>(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * UN), w);    // NCO = 8: columns 8..15 are copies
+                for (int c0 = 0; c0 < UN; c0 += 16) {
+                    uint32_t v[16];
+                    tmem_ld<16>(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((kd * KWB + blk) * UN + c0), v);
                     tmem_ld_wait();
+                    if (real) {
 #pragma unroll
-                    for (int k = 0; k < 16; ++k) v[k] = w[k];
-                }
-                if (has_work && ci < CIN) {
-                    float* row = p.gw + ((size_t)(p.kd0 * 9 + t) * CIN + ci) * p.cout + p.co0;
-#pragma unroll
-                    for (int c = 0; c < NCO; ++c)
-                        if (p.co0 + c < p.cout) atomicAdd(row + c, __uint_as_float(v[c]));
+                        for (int k = 0; k < 16; ++k) {
+                            const int col = c0 + k, n = col / NCO, co = col % NCO;     // atom n <-> kh = 2 - n
+                            if (n < 3 && p.co0 + co < p.cout)
+                                atomicAdd(p.gw + ((size_t)((kd * 3 + (2 - n)) * 3 + kw) * CIN + ci) * p.cout + p.co0 + co,
+                                          __uint_as_float(v[k]));
+                        }
+                    }
                 }
             }
         }
@@ -700,23 +693,25 @@ conv3d_s1_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid
     }
 }
 
-TilePlan plan_tiles_wgrad(int Ho, int Wo, int rowx, int rowg, size_t smem_budget) {
-    TilePlan best{};
+struct WgPlan {
+    int BW, L, tiles_x, tiles_y, slab_bytes, gy_bytes;
+    double score;
+};
+
+WgPlan plan_tiles_wgrad(int Ho, int Wo, int rowx, int rowg, size_t smem_budget) {
+    WgPlan best{};
     best.score = -1.0;
-    for (int MB = 1; MB <= kMaxMB; MB *= 2) {
+    for (int L = 1; L <= 64; ++L) {
         for (int BW = 16; BW <= 256; BW += 8) {                // BW*rowg must be a multiple of 128 (TMA destination of a gy line)
             if ((BW * rowg) % 128) continue;
-            const int L = (MB * 128) / BW;
-            if (L < 1 || L + 2 > 256) continue;
-            const int rows = MB * 128 + 2 * BW + 2 + 16;
-            const int slab = ((rows * rowx) + 1023) / 1024 * 1024;
-            const int gyb = ((MB * 128 + 16) * rowg + 1023) / 1024 * 1024;
+            const int rows_x = (L + 2) * BW + 32;               // + last K step + junk kw atom
+            const int rows_g = (L + 5) * BW + 32;               // 2 zero lines before, the tile, the junk atom's reach after
+            const int slab = ((rows_x * rowx) + 1023) / 1024 * 1024;
+            const int gyb = ((rows_g * rowg) + 1023) / 1024 * 1024;
             if ((size_t)kSlots3 * slab + 2 * (size_t)gyb + 256 > smem_budget) continue;
             const int tiles_x = (Wo + BW - 3) / (BW - 2), tiles_y = (Ho + L - 1) / L;
-            const double eff = (double)Wo * Ho / ((double)tiles_x * tiles_y * MB * 128);
-            const double load_eff = (double)Wo * Ho / ((double)tiles_x * tiles_y * (L + 2) * BW);
-            const double score = eff * (0.5 + 0.5 * load_eff);
-            if (score > best.score) best = TilePlan{BW, L, MB, tiles_x, tiles_y, slab, score};
+            const double eff = (double)Wo * Ho / ((double)tiles_x * tiles_y * (L + 2) * BW);   // useful / reduced rows
+            if (eff > best.score) best = WgPlan{BW, L, tiles_x, tiles_y, slab, gyb, eff};
         }
     }
     return best;
@@ -724,14 +719,13 @@ TilePlan plan_tiles_wgrad(int Ho, int Wo, int rowx, int rowg, size_t smem_budget
 
 template <int CIN, int NCO>
 int launch_wgrad(const void* x, const void* gy, float* gw, int B, int Di, int Hi, int Wi, int Do, int Ho, int Wo, int cout, int co0,
-                 int kd0, int nkd, int off_d, int off_h, int off_w, cudaStream_t st) {
+                 int off_d, int off_h, int off_w, cudaStream_t st) {
     constexpr int ROWX = CIN * 2, ROWG = NCO * 2;
     EncodeTiledFn enc = encode_fn();
     MVS_REQUIRE(enc != nullptr, "conv3d_s1_wgrad: cuTensorMapEncodeTiled is not available from the driver");
     const size_t smem_budget = 227 * 1024 - 1024;
-    const TilePlan tp = plan_tiles_wgrad(Ho, Wo, ROWX, ROWG, smem_budget);
+    const WgPlan tp = plan_tiles_wgrad(Ho, Wo, ROWX, ROWG, smem_budget);
     MVS_REQUIRE(tp.score > 0, "conv3d_s1_wgrad: no slab geometry fits shared memory (Cin=%d, N=%d)", CIN, NCO);
-    const int gy_bytes = ((tp.MB * 128 + 16) * ROWG + 1023) / 1024 * 1024;
 
     CUtensorMap tm_x, tm_g;
     {
@@ -756,9 +750,9 @@ int launch_wgrad(const void* x, const void* gy, float* gw, int B, int Di, int Hi
     }
     WgradParams p;
     p.B = B; p.Do = Do; p.Ho = Ho; p.Wo = Wo; p.off_d = off_d; p.off_h = off_h; p.off_w = off_w;
-    p.BW = tp.BW; p.L = tp.L; p.MB = tp.MB; p.tiles_x = tp.tiles_x; p.tiles_y = tp.tiles_y;
-    p.kd0 = kd0; p.nkd = nkd; p.co0 = co0; p.cout = cout; p.slab_bytes = tp.slab_bytes; p.gy_bytes = gy_bytes;
-    p.ksteps = (tp.L * tp.BW + 15) / 16;
+    p.BW = tp.BW; p.L = tp.L; p.tiles_x = tp.tiles_x; p.tiles_y = tp.tiles_y;
+    p.co0 = co0; p.cout = cout; p.slab_bytes = tp.slab_bytes; p.gy_bytes = tp.gy_bytes;
+    p.ksteps = ((tp.L + 2) * tp.BW + 15) / 16;
     p.gw = gw;
     const long tiles = (long)tp.tiles_x * tp.tiles_y;
     int sms = 148;
@@ -772,14 +766,14 @@ int launch_wgrad(const void* x, const void* gy, float* gw, int B, int Di, int Hi
         const int dc = (Do + nc - 1) / nc;
         if ((long)(nc - 1) * dc >= Do) continue;
         const long items = tiles * nc * B;
-        const long cost = ((items + sms - 1) / sms) * (dc + nkd + 1);
+        const long cost = ((items + sms - 1) / sms) * (dc + 4);
         if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_chunks = nc; }
     }
     p.nchunks = best_chunks;
     p.dchunk = (Do + best_chunks - 1) / best_chunks;
     p.n_items = (int)(tiles * p.nchunks * B);
     const dim3 grid((unsigned)(p.n_items < sms ? p.n_items : sms), 1, 1);
-    const size_t smem = 1024 + (size_t)kSlots3 * tp.slab_bytes + 2 * (size_t)gy_bytes + 256;
+    const size_t smem = 1024 + (size_t)kSlots3 * tp.slab_bytes + 2 * (size_t)tp.gy_bytes + 256;
     MVS_CUDA(cudaFuncSetAttribute(conv3d_s1_wgrad_tc_kernel<CIN, NCO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     conv3d_s1_wgrad_tc_kernel<CIN, NCO><<<grid, kTcThreads, smem, st>>>(tm_x, tm_g, p);
     MVS_CHECK_LAUNCH("conv3d_s1_wgrad_tc");
@@ -827,27 +821,24 @@ extern "C" int mvsb200_conv3d_s1_wgrad(const void* x, const void* gy, float* gw,
     MVS_REQUIRE(cout == 8 || cout == 16 || cout == 32 || cout == 64, "conv3d_s1_wgrad: cout must be 8, 16, 32 or 64 (got %d)", cout);
     cudaStream_t st = (cudaStream_t)stream;
     MVS_CUDA(cudaMemsetAsync(gw, 0, (size_t)27 * Cin * cout * sizeof(float), st));
-    // taps x channels per launch <= 512 TMEM columns: all 27 taps for co <= 16, one depth tap (9 taps) per launch above;
-    // 64 output channels additionally in two 32-channel halves
-    const int nco = cout < 32 ? cout : 32;
-    const int nkd = cout <= 16 ? 3 : 1;
+    // gy channels per launch: 3 depth taps x (1 or 2 kw blocks) x (kh, co) columns must fit the 512 TMEM columns
+    const int nco_max = Cin == 64 ? 16 : 32;
+    const int nco = cout < nco_max ? cout : nco_max;
     for (int co0 = 0; co0 < cout; co0 += nco) {
-        for (int kd0 = 0; kd0 < 3; kd0 += nkd) {
-            int rc = MVSB200_E_UNSUPPORTED;
-#define MVS_WG(CI, NC) rc = launch_wgrad<CI, NC>(x, gy, gw, B, Di, Hi, Wi, Do, Ho, Wo, cout, co0, kd0, nkd, off_d, off_h, off_w, st)
-            if (Cin == 16 && nco == 8) MVS_WG(16, 8);
-            else if (Cin == 16 && nco == 16) MVS_WG(16, 16);
-            else if (Cin == 16 && nco == 32) MVS_WG(16, 32);
-            else if (Cin == 32 && nco == 8) MVS_WG(32, 8);
-            else if (Cin == 32 && nco == 16) MVS_WG(32, 16);
-            else if (Cin == 32 && nco == 32) MVS_WG(32, 32);
-            else if (Cin == 64 && nco == 8) MVS_WG(64, 8);
-            else if (Cin == 64 && nco == 16) MVS_WG(64, 16);
-            else if (Cin == 64 && nco == 32) MVS_WG(64, 32);
-            else MVS_FAIL(MVSB200_E_UNSUPPORTED, "conv3d_s1_wgrad: unsupported channels Cin=%d cout=%d", Cin, cout);
+        int rc = MVSB200_E_UNSUPPORTED;
+#define MVS_WG(CI, NC) rc = launch_wgrad<CI, NC>(x, gy, gw, B, Di, Hi, Wi, Do, Ho, Wo, cout, co0, off_d, off_h, off_w, st)
+        if (Cin == 16 && nco == 8) MVS_WG(16, 8);
+        else if (Cin == 16 && nco == 16) MVS_WG(16, 16);
+        else if (Cin == 16 && nco == 32) MVS_WG(16, 32);
+        else if (Cin == 32 && nco == 8) MVS_WG(32, 8);
+        else if (Cin == 32 && nco == 16) MVS_WG(32, 16);
+        else if (Cin == 32 && nco == 32) MVS_WG(32, 32);
+        else if (Cin == 64 && nco == 8) MVS_WG(64, 8);
+        else if (Cin == 64 && nco == 16) MVS_WG(64, 16);
+        else if (Cin == 64 && nco == 32) MVS_WG(64, 32);
+        else MVS_FAIL(MVSB200_E_UNSUPPORTED, "conv3d_s1_wgrad: unsupported channels Cin=%d cout=%d", Cin, cout);
 #undef MVS_WG
-            if (rc != MVSB200_OK) return rc;
-        }
+        if (rc != MVSB200_OK) return rc;
     }
     return MVSB200_OK;
 }

@@ -84,7 +84,17 @@ class _Conv3dS1(torch.autograd.Function):
             else:
                 gx = torch.nn.grad.conv3d_input(x_cl.shape, w.to(gy.dtype), gy, padding=pad)
         if ctx.needs_input_grad[1]:
-            gw = torch.nn.grad.conv3d_weight(x_cl, w.shape, gy, padding=pad).to(w.dtype)
+            cout, cin = w.shape[:2]
+            if cin in _CIN_OK and cout in (8, 16, 32, 64):
+                B, _, Di, Hi, Wi = x_cl.shape
+                Do, Ho, Wo = gy.shape[2:]
+                gw27 = torch.empty((27, cin, cout), dtype=torch.float32, device=gy.device)
+                with _timed("conv3d_s1_wgrad_tc", 2.0 * 27 * cin * cout * B * Do * Ho * Wo):
+                    _lib.call("mvsb200_conv3d_s1_wgrad", x_cl.data_ptr(), gy.data_ptr(), gw27.data_ptr(), B, Di, Hi, Wi, cin,
+                              Do, Ho, Wo, cout, -pad, -pad, -pad, _stream())
+                gw = gw27.reshape(3, 3, 3, cin, cout).permute(4, 3, 0, 1, 2).to(w.dtype)
+            else:
+                gw = torch.nn.grad.conv3d_weight(x_cl, w.shape, gy, padding=pad).to(w.dtype)
         return gx, gw, None
 
 

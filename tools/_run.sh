@@ -1,3 +1,2 @@
-python tools/microbench.py --cases sweep --kernels fwd,bwd --reps 5 > gpurun_out/sweep_cfg5.jsonl 2> gpurun_out/sweep.err
-python bench.py --workload cfg1 --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_cfg1.json 2> gpurun_out/bench_cfg1.err
-python tools/microbench.py --cases cfg --kernels fwd,bwd,k4 > gpurun_out/micro_cfg7.jsonl 2>> gpurun_out/sweep.err
+python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
+python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench7.json 2> gpurun_out/bench7.err

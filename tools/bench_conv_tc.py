@@ -55,7 +55,14 @@ def layer(name, B, Cin, Cout, D, h, w, pad):
     err = (y.float() - ref.float()).abs().max().item() / ref.float().abs().max().item()
     flops = 2.0 * 27 * Cin * Cout * B * Do * Ho * Wo
     byts = 2.0 * B * (Cin * D * h * w + Cout * Do * Ho * Wo)
-    print(json.dumps(dict(layer=name, Cin=Cin, Cout=Cout, out=[B, Do, Ho, Wo], ms=t_ours, ms_cudnn=t_cudnn, rel_err_vs_cudnn=err,
+    # weight gradient
+    gy = torch.randn_like(y)
+    gw = torch.empty(27, Cin, Cout, device=DEV)
+    wg = lambda: _lib.call("mvsb200_conv3d_s1_wgrad", x.data_ptr(), gy.data_ptr(), gw.data_ptr(), B, D, h, w, Cin, Do, Ho, Wo, Cout,
+                           off, off, off, st)
+    wg_cudnn = lambda: torch.nn.grad.conv3d_weight(x, wt.shape, gy, padding=1 if pad else 0)
+    t_wg, t_wg_cudnn = (timeit(wg), timeit(wg_cudnn)) if Cout in (8, 16, 32, 64) else (None, None)
+    print(json.dumps(dict(layer=name, wgrad_ms=t_wg, wgrad_ms_cudnn=t_wg_cudnn, wgrad_TFLOPs=(flops / t_wg / 1e9) if t_wg else None, Cin=Cin, Cout=Cout, out=[B, Do, Ho, Wo], ms=t_ours, ms_cudnn=t_cudnn, rel_err_vs_cudnn=err,
                           TFLOPs=flops / t_ours / 1e9, frac_tensor_peak=flops / t_ours / 1e9 / PEAK_TF,
                           act_GBps=byts / t_ours / 1e6, frac_hbm=byts / t_ours / 1e6 / PEAK_GB)), flush=True)
 
