@@ -41,6 +41,8 @@ struct ConvParams {
     int n_rows;                     // filter rows per tap in the packed weights (multiple of 16)
     int w_row0;                     // first filter row this launch computes (N split of wide layers)
     int slab_bytes;                 // per ring slot, multiple of 1024
+    unsigned tap_mask;              // bit (kd*3+kh)*3+kw: tap present (absent taps are neither loaded nor multiplied)
+    long long y_sb, y_sd, y_sh, y_sw;   // output voxel-row strides in elements (a parity sub-lattice of a canvas, or dense)
     __nv_bfloat16* y;
 };
 
@@ -214,9 +216,9 @@ conv3d_s1_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
     if (warp == 0) {
         // ===================================== TMA producer =====================================
         if (elect_one()) {
-            mbar_expect_tx(wfull, W_BYTES);
+            mbar_expect_tx(wfull, (uint32_t)__popc(p.tap_mask) * W_TAP_BYTES);
             for (int tap = 0; tap < 27; ++tap)
-                tma_load_2d(w_smem + tap * W_TAP_BYTES, &tm_w, wfull, 0, tap * p.n_rows + p.w_row0);
+                if (p.tap_mask >> tap & 1u) tma_load_2d(w_smem + tap * W_TAP_BYTES, &tm_w, wfull, 0, tap * p.n_rows + p.w_row0);
         }
         __syncwarp();
         const uint32_t box_bytes = (uint32_t)ROWB * p.BW * (p.L + 2);
@@ -259,6 +261,7 @@ conv3d_s1_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
                     for (int mb = 0; mb < MB; ++mb) {
                         const uint32_t d_tmem = tmem_base + (uint32_t)((stage * MB + mb) * NOUT);
                         const uint32_t mb16 = (uint32_t)(mb * 128 * ROWB) >> 4;
+                        uint32_t acc = 0;
 #pragma unroll
                         for (int kd = 0; kd < 3; ++kd) {
 #pragma unroll
@@ -266,11 +269,14 @@ conv3d_s1_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
                                 const uint32_t row_lo = slot_lo[kd] + mb16 + kh * bw16;
 #pragma unroll
                                 for (int kw = 0; kw < 3; ++kw) {
+                                    if (p.tap_mask >> ((kd * 3 + kh) * 3 + kw) & 1u) {
 #pragma unroll
-                                    for (int k = 0; k < KSTEPS; ++k) {
-                                        umma_bf16_lohi(d_tmem, row_lo + (uint32_t)((kw * ROWB + k * 32) >> 4), desc_hi,
-                                                       w_lo + (uint32_t)((((kd * 3 + kh) * 3 + kw) * W_TAP_BYTES + k * 32) >> 4),
-                                                       desc_hi, IDESC, (kd | kh | kw | k) != 0);
+                                        for (int k = 0; k < KSTEPS; ++k) {
+                                            umma_bf16_lohi(d_tmem, row_lo + (uint32_t)((kw * ROWB + k * 32) >> 4), desc_hi,
+                                                           w_lo + (uint32_t)((((kd * 3 + kh) * 3 + kw) * W_TAP_BYTES + k * 32) >> 4),
+                                                           desc_hi, IDESC, acc);
+                                            acc = 1;
+                                        }
                                     }
                                 }
                             }
@@ -295,7 +301,7 @@ conv3d_s1_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
         for (int mb = 0; mb < kMaxMB; ++mb) {
             const int m = mb * 128 + q * 32 + lane;
             tj[mb] = m / p.BW; ti[mb] = m - tj[mb] * p.BW;
-            rel[mb] = (ti[mb] < p.BW - 2 && tj[mb] < p.L) ? (tj[mb] * p.Wo + ti[mb]) * p.y_cs : -1;
+            rel[mb] = (ti[mb] < p.BW - 2 && tj[mb] < p.L) ? 1 : -1;
         }
         int gp = 0;
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
@@ -305,7 +311,7 @@ conv3d_s1_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
                 const int stage = gp & 1;
                 mbar_wait(tfull + stage, (gp >> 1) & 1);
                 tc_fence_after();
-                __nv_bfloat16* plane0 = p.y + ((((size_t)b * p.Do + d_begin + d) * p.Ho + y0) * p.Wo + x0) * p.y_cs + p.y_coff;
+                __nv_bfloat16* plane0 = p.y + (long long)b * p.y_sb + (long long)(d_begin + d) * p.y_sd + (long long)y0 * p.y_sh + (long long)x0 * p.y_sw + p.y_coff;
 #pragma unroll
                 for (int mb = 0; mb < kMaxMB; ++mb) {
                     if (mb < MB) {
@@ -313,7 +319,7 @@ conv3d_s1_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
                         tmem_ld<NOUT>(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((stage * MB + mb) * NOUT), v);
                         tmem_ld_wait();
                         if (rel[mb] >= 0 && x0 + ti[mb] < p.Wo && y0 + tj[mb] < p.Ho) {
-                            __nv_bfloat16* row = plane0 + rel[mb];
+                            __nv_bfloat16* row = plane0 + (long long)tj[mb] * p.y_sh + (long long)ti[mb] * p.y_sw;
 #pragma unroll
                             for (int c = 0; c < NOUT; c += 8) {
                                 if (c < p.cout) {
@@ -391,7 +397,8 @@ TilePlan plan_tiles(int Ho, int Wo, int rowb, size_t w_bytes_al, size_t smem_bud
 
 template <int CIN, int NOUT>
 int launch_conv(const void* x, const void* w, void* y, int B, int Di, int Hi, int Wi, int Do, int Ho, int Wo, int cout,
-                int y_cs, int y_coff, int n_rows, int w_row0, int off_d, int off_h, int off_w, cudaStream_t st) {
+                int y_cs, int y_coff, int n_rows, int w_row0, int off_d, int off_h, int off_w, unsigned tap_mask,
+                const long long* y_strides4, cudaStream_t st) {
     constexpr int ROWB = CIN * 2;
     constexpr size_t W_BYTES_AL = ((size_t)27 * NOUT * ROWB + 1023) / 1024 * 1024;
     EncodeTiledFn enc = encode_fn();
@@ -429,6 +436,12 @@ int launch_conv(const void* x, const void* w, void* y, int B, int Di, int Hi, in
     p.BW = tp.BW; p.L = tp.L; p.MB = tp.MB; p.tiles_x = tp.tiles_x; p.tiles_y = tp.tiles_y;
     p.cout = cout; p.y_cs = y_cs; p.y_coff = y_coff; p.n_rows = n_rows; p.w_row0 = w_row0;
     p.slab_bytes = tp.slab_bytes;
+    p.tap_mask = tap_mask & 0x7ffffffu;
+    if (y_strides4) {
+        p.y_sb = y_strides4[0]; p.y_sd = y_strides4[1]; p.y_sh = y_strides4[2]; p.y_sw = y_strides4[3];
+    } else {
+        p.y_sw = y_cs; p.y_sh = (long long)Wo * y_cs; p.y_sd = (long long)Ho * Wo * y_cs; p.y_sb = (long long)Do * Ho * Wo * y_cs;
+    }
     p.y = reinterpret_cast<__nv_bfloat16*>(y);
     // depth runs: an item costs (planes + 2 halo planes + ~2 planes of pipeline fill); CTAs are persistent, one per SM,
     // so pick the run length that minimises (items per CTA) x (cost per item)
@@ -782,16 +795,16 @@ int launch_wgrad(const void* x, const void* gy, float* gw, int B, int Di, int Hi
 
 }  // namespace
 
-extern "C" int mvsb200_conv3d_s1_fwd(const void* x, const void* w_packed, void* y, int B, int Di, int Hi, int Wi, int Cin,
-                                     int Do, int Ho, int Wo, int cout, int y_cs, int n_rows, int off_d, int off_h, int off_w,
-                                     void* stream) {
-    MVS_REQUIRE(x && w_packed && y, "conv3d_s1_fwd: null pointer");
-    MVS_REQUIRE(aligned16(x) && aligned16(w_packed) && aligned16(y), "conv3d_s1_fwd: pointers must be 16-byte aligned");
-    MVS_REQUIRE(B >= 1 && B <= 65535 && Di >= 1 && Hi >= 1 && Wi >= 1 && Do >= 1 && Ho >= 1 && Wo >= 1, "conv3d_s1_fwd: bad shape");
+static int conv3d_s1_dispatch(const void* x, const void* w_packed, void* y, int B, int Di, int Hi, int Wi, int Cin, int Do, int Ho,
+                              int Wo, int cout, int y_cs, int n_rows, int off_d, int off_h, int off_w, unsigned tap_mask,
+                              const long long* y_strides4, cudaStream_t st, const char* name) {
+    MVS_REQUIRE(x && w_packed && y, "%s: null pointer", name);
+    MVS_REQUIRE(aligned16(x) && aligned16(w_packed) && aligned16(y), "%s: pointers must be 16-byte aligned", name);
+    MVS_REQUIRE(B >= 1 && B <= 65535 && Di >= 1 && Hi >= 1 && Wi >= 1 && Do >= 1 && Ho >= 1 && Wo >= 1, "%s: bad shape", name);
     MVS_REQUIRE(cout >= 8 && cout % 8 == 0 && cout <= n_rows && n_rows % 16 == 0 && n_rows <= 64,
-                "conv3d_s1_fwd: cout must be a multiple of 8 and n_rows a multiple of 16 <= 64 (cout=%d n_rows=%d)", cout, n_rows);
-    MVS_REQUIRE(y_cs >= cout && y_cs % 8 == 0, "conv3d_s1_fwd: output channel stride %d", y_cs);
-    cudaStream_t st = (cudaStream_t)stream;
+                "%s: cout must be a multiple of 8 and n_rows a multiple of 16 <= 64 (cout=%d n_rows=%d)", name, cout, n_rows);
+    MVS_REQUIRE(y_cs >= cout && y_cs % 8 == 0, "%s: output channel stride %d", name, y_cs);
+    MVS_REQUIRE((tap_mask & 0x7ffffffu) != 0, "%s: empty tap mask", name);
     // N (filter rows per launch) is 16 or 32; a 64-row filter runs as two 32-row halves (all 27 taps of a 64 x 64
     // filter do not fit next to the slab ring; at N = 32 the tensor pipe is fed from shared memory at the same rate)
     for (int row0 = 0; row0 < n_rows && row0 < cout; row0 += 32) {
@@ -799,18 +812,35 @@ extern "C" int mvsb200_conv3d_s1_fwd(const void* x, const void* w_packed, void* 
         const int c_here = cout - row0 < nout ? cout - row0 : nout;
         int rc = MVSB200_E_UNSUPPORTED;
 #define MVS_CONV(CI, NO) \
-    rc = launch_conv<CI, NO>(x, w_packed, y, B, Di, Hi, Wi, Do, Ho, Wo, c_here, y_cs, row0, n_rows, row0, off_d, off_h, off_w, st)
+    rc = launch_conv<CI, NO>(x, w_packed, y, B, Di, Hi, Wi, Do, Ho, Wo, c_here, y_cs, row0, n_rows, row0, off_d, off_h, off_w, tap_mask, y_strides4, st)
         if (Cin == 16 && nout == 16) MVS_CONV(16, 16);
         else if (Cin == 16 && nout == 32) MVS_CONV(16, 32);
         else if (Cin == 32 && nout == 16) MVS_CONV(32, 16);
         else if (Cin == 32 && nout == 32) MVS_CONV(32, 32);
         else if (Cin == 64 && nout == 16) MVS_CONV(64, 16);
         else if (Cin == 64 && nout == 32) MVS_CONV(64, 32);
-        else MVS_FAIL(MVSB200_E_UNSUPPORTED, "conv3d_s1_fwd: unsupported channels Cin=%d n_rows=%d", Cin, n_rows);
+        else MVS_FAIL(MVSB200_E_UNSUPPORTED, "%s: unsupported channels Cin=%d n_rows=%d", name, Cin, n_rows);
 #undef MVS_CONV
         if (rc != MVSB200_OK) return rc;
     }
     return MVSB200_OK;
+}
+
+extern "C" int mvsb200_conv3d_s1_fwd(const void* x, const void* w_packed, void* y, int B, int Di, int Hi, int Wi, int Cin,
+                                     int Do, int Ho, int Wo, int cout, int y_cs, int n_rows, int off_d, int off_h, int off_w,
+                                     void* stream) {
+    return conv3d_s1_dispatch(x, w_packed, y, B, Di, Hi, Wi, Cin, Do, Ho, Wo, cout, y_cs, n_rows, off_d, off_h, off_w, 0x7ffffffu,
+                              nullptr, (cudaStream_t)stream, "conv3d_s1_fwd");
+}
+
+extern "C" int mvsb200_conv3d_s1_fwd_ex(const void* x, const void* w_packed, void* y, int B, int Di, int Hi, int Wi, int Cin,
+                                        int Do, int Ho, int Wo, int cout, int n_rows, int off_d, int off_h, int off_w,
+                                        unsigned tap_mask, const int64_t* y_strides4, void* stream) {
+    MVS_REQUIRE(y_strides4 != nullptr, "conv3d_s1_fwd_ex: null output strides");
+    const long long ys[4] = {(long long)y_strides4[0], (long long)y_strides4[1], (long long)y_strides4[2], (long long)y_strides4[3]};
+    for (int i = 0; i < 4; ++i) MVS_REQUIRE(ys[i] % 8 == 0, "conv3d_s1_fwd_ex: output strides must be multiples of 8 elements");
+    return conv3d_s1_dispatch(x, w_packed, y, B, Di, Hi, Wi, Cin, Do, Ho, Wo, cout, cout, n_rows, off_d, off_h, off_w, tap_mask, ys,
+                              (cudaStream_t)stream, "conv3d_s1_fwd_ex");
 }
 
 extern "C" int mvsb200_conv3d_s1_wgrad(const void* x, const void* gy, float* gw, int B, int Di, int Hi, int Wi, int Cin, int Do,

@@ -98,6 +98,114 @@ class _Conv3dS1(torch.autograd.Function):
         return gx, gw, None
 
 
+# ---- stride-2 transposed convolution as 8 output-parity classes of the stride-1 kernel -------------------------------
+_CLASS_IDX = {}
+
+
+def _deconv_class_tables(pads, device):
+    """For ConvTranspose3d(k=3, stride=2, padding=pads): per output-parity class (pd,ph,pw) the tap mask of the
+    stride-1 kernel and, per kernel tap t, the index of the original filter tap k it carries (27 = none).
+    out[2j + par] = sum_{k: (par+p-k) even} W[k] . in[j + (par+p-k)/2]; with the kernel's off = -1 the tap is
+    t = (par+p-k)/2 + 1 per axis."""
+    key = (tuple(pads), str(device))
+    hit = _CLASS_IDX.get(key)
+    if hit is not None:
+        return hit
+    per_axis = []
+    for p in pads:
+        per_axis.append({par: [(k, (par + p - k) // 2 + 1) for k in range(3) if (par + p - k) % 2 == 0] for par in (0, 1)})
+    idx = torch.full((8, 27), 27, dtype=torch.long)
+    masks = []
+    for c in range(8):
+        par = (c >> 2 & 1, c >> 1 & 1, c & 1)
+        mask = 0
+        for kd, td in per_axis[0][par[0]]:
+            for kh, th in per_axis[1][par[1]]:
+                for kw, tw in per_axis[2][par[2]]:
+                    if not (0 <= td < 3 and 0 <= th < 3 and 0 <= tw < 3):
+                        raise ValueError(f"transposed-conv padding {pads} is outside the 3-tap window of the kernel")
+                    t = (td * 3 + th) * 3 + tw
+                    idx[c, t] = (kd * 3 + kh) * 3 + kw
+                    mask |= 1 << t
+        masks.append(mask)
+    hit = (idx.to(device), masks)
+    _CLASS_IDX[key] = hit
+    return hit
+
+
+def conv_transpose3d_s2(x, w, pads, out_dims):
+    """ConvTranspose3d(k=3, stride=2, padding=pads, bias=False) from the box volume x [B,Cin,md,mh,mw] to the first
+    `out_dims` voxels per axis of its output, on the tcgen05 kernel: one launch per output-parity class, each writing its
+    stride-2 sub-lattice of the canvas.  w: [Cin, Cout, 3, 3, 3] (model.py:229-234)."""
+    import ctypes
+    x_cl = x.detach().contiguous(memory_format=torch.channels_last_3d)
+    B, cin, md, mh, mw = x_cl.shape
+    cout = w.shape[1]
+    D, h, wd = out_dims
+    n_rows = _n_rows(cout)
+    idx, masks = _deconv_class_tables(pads, x.device)
+    wk = w.detach().permute(2, 3, 4, 1, 0).reshape(27, cout, cin)                 # [k][co][ci]
+    wz = torch.cat([wk, wk.new_zeros(1, cout, cin)], 0)
+    wp = torch.zeros(8, 27, n_rows, cin, dtype=torch.bfloat16, device=x.device)
+    wp[:, :, :cout] = wz[idx].to(torch.bfloat16)
+    y = torch.empty((B, cout, D, h, wd), dtype=torch.bfloat16, device=x.device, memory_format=torch.channels_last_3d)
+    sB, sD, sH, sW = y.stride(0), y.stride(2), y.stride(3), y.stride(4)
+    ys = (ctypes.c_int64 * 4)(sB, 2 * sD, 2 * sH, 2 * sW)
+    work = 0.0
+    for c in range(8):
+        pd_, ph_, pw_ = c >> 2 & 1, c >> 1 & 1, c & 1
+        Jd, Jh, Jw = (D - pd_ + 1) // 2, (h - ph_ + 1) // 2, (wd - pw_ + 1) // 2
+        if min(Jd, Jh, Jw) <= 0:
+            continue
+        work += 2.0 * bin(masks[c]).count("1") * cin * cout * B * Jd * Jh * Jw
+    with _timed("conv3d_s1_tc", work):
+        for c in range(8):
+            pd_, ph_, pw_ = c >> 2 & 1, c >> 1 & 1, c & 1
+            Jd, Jh, Jw = (D - pd_ + 1) // 2, (h - ph_ + 1) // 2, (wd - pw_ + 1) // 2
+            if min(Jd, Jh, Jw) <= 0:
+                continue
+            base = y.data_ptr() + 2 * (pd_ * sD + ph_ * sH + pw_ * sW)
+            _lib.call("mvsb200_conv3d_s1_fwd_ex", x_cl.data_ptr(), wp[c].data_ptr(), base, B, md, mh, mw, cin, Jd, Jh, Jw, cout,
+                      n_rows, -1, -1, -1, masks[c], ys, _stream())
+    return y
+
+
+class _ConvTranspose3dS2(torch.autograd.Function):
+    """Forward on the tcgen05 kernel; the two gradients are a stride-2 convolution of the output gradient and its
+    weight gradient (library kernels until the stride-2 tcgen05 kernels exist)."""
+
+    @staticmethod
+    def forward(ctx, x, w, pads, out_dims):
+        y = conv_transpose3d_s2(x, w, pads, out_dims)
+        ctx.save_for_backward(x.detach().contiguous(memory_format=torch.channels_last_3d), w)
+        ctx.pads = tuple(pads)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x_cl, w = ctx.saved_tensors
+        pads = ctx.pads
+        gy = gy.to(torch.bfloat16).contiguous(memory_format=torch.channels_last_3d)
+        gx = gw = None
+        # As a convolution gy -> x: x[i] = sum_k W[k]^T gy[2i - p + k].  With padding p + 2 the library's output index is
+        # i + 1 and its range covers every box row (the plain padding p stops one row short of the box).
+        P2 = tuple(p + 2 for p in pads)
+        m = list(x_cl.shape[2:])
+        n_o = [(n + 2 * q - 3) // 2 + 1 for n, q in zip(gy.shape[2:], P2)]
+        if any(1 + a > b for a, b in zip(m, n_o)):
+            raise _lib.MvsB200Error(f"transposed-conv gradient: box {m} does not fit the strided window {n_o}")
+        inner = (slice(None), slice(None)) + tuple(slice(1, 1 + a) for a in m)
+        wb = w.detach().to(torch.bfloat16)
+        if ctx.needs_input_grad[0]:
+            gx = F.conv3d(gy, wb, None, 2, P2)[inner]                 # weight [Cin, Cout, ...] read as out = Cin, in = Cout
+        if ctx.needs_input_grad[1]:
+            xs = torch.zeros((x_cl.shape[0], x_cl.shape[1]) + tuple(n_o), dtype=x_cl.dtype, device=x_cl.device,
+                             ).contiguous(memory_format=torch.channels_last_3d)
+            xs[inner] = x_cl
+            gw = torch.nn.grad.conv3d_weight(gy, w.shape, xs, stride=2, padding=P2).to(w.dtype)
+        return gx, gw, None, None
+
+
 class Tcgen05ConvBackend:
     name = "tcgen05"
 
@@ -109,8 +217,17 @@ class Tcgen05ConvBackend:
             return _Conv3dS1.apply(x, w, pad[0])
         return conv_backends.TorchConvBackend.conv3d(x, w, stride, padding)
 
-    conv_transpose3d = conv_backends.TorchConvBackend.conv_transpose3d
-    conv_transpose3d_alloc = conv_backends.TorchConvBackend.conv_transpose3d_alloc
+    @staticmethod
+    def conv_transpose3d_alloc(x, w, stride, padding, out_dims):
+        if (stride == 2 and x.is_cuda and x.dtype == torch.bfloat16 and x.shape[1] in _CIN_OK and w.shape[1] % 8 == 0
+                and 8 <= w.shape[1] <= 64 and all(p in (1, 2) for p in padding)):
+            return _ConvTranspose3dS2.apply(x, w, tuple(int(p) for p in padding), tuple(int(n) for n in out_dims))
+        return conv_backends.TorchConvBackend.conv_transpose3d_alloc(x, w, stride, padding, out_dims)
+
+    @classmethod
+    def conv_transpose3d(cls, x, w, stride, padding, out_dims):
+        D, h, w_ = out_dims
+        return cls.conv_transpose3d_alloc(x, w, stride, padding, out_dims)[..., :D, :h, :w_]
 
 
 def available() -> bool:

@@ -128,6 +128,14 @@ int mvsb200_conv3d_s1_fwd(const void* x, const void* w_packed, void* y, int B, i
                           int Do, int Ho, int Wo, int cout, int y_cs, int n_rows, int off_d, int off_h, int off_w,
                           void* stream);
 
+/* Same kernel with a subset of the 27 taps (bit (kd*3+kh)*3+kw of tap_mask) and a strided output: the voxel row of
+ * output (b,z,y,x) starts at y + b*ys[0] + z*ys[1] + y*ys[2] + x*ys[3] elements (y_strides4: HOST int64).  This is one
+ * output-parity class of a stride-2 TRANSPOSED convolution (ConvTranspose3d, scripts/model.py:229-234, used at :115-121):
+ * out[2j + par] = sum over the taps k with (par + p - k) even of W[k] . in[j + (par + p - k)/2]. */
+int mvsb200_conv3d_s1_fwd_ex(const void* x, const void* w_packed, void* y, int B, int Di, int Hi, int Wi, int Cin,
+                             int Do, int Ho, int Wo, int cout, int n_rows, int off_d, int off_h, int off_w,
+                             unsigned tap_mask, const int64_t* y_strides4_host, void* stream);
+
 /* Weight gradient of the same convolution on tcgen05 (autograd of scripts/model.py:101-113 w.r.t. the filters):
  *   gW[tap][ci][co] = sum_v x(v + tap + off)[ci] * gy(v)[co]
  * x: [B, Di, Hi, Wi, Cin] bf16; gy: [B, Do, Ho, Wo, cout] bf16 (cout in {8,16,32,64}); gw: [27, Cin, cout] fp32,

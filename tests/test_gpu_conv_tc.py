@@ -113,3 +113,31 @@ def test_conv_out_forward_and_gradients(shape):
     assert _rel(w1.grad, w2.grad) < 1e-4
     y2 = ops.conv_out(z1.detach(), w1.detach())
     assert torch.equal(y, y2)
+
+
+@pytest.mark.parametrize("cin,cout", [(64, 32), (32, 16), (16, 8)])
+@pytest.mark.parametrize("dims", [(12, 10, 14), (11, 9, 15), (8, 7, 12), (6, 33, 47)])
+def test_transposed_conv_by_parity_classes(cin, cout, dims):
+    """Stride-2 ConvTranspose3d (model.py:229-234) from the central box to the canvas: 8 parity-class launches of the
+    tcgen05 kernel vs torch's conv_transpose3d (fp32) on the same bf16 operands, forward and both gradients."""
+    from mvs_b200.regulariser import central_region
+    reg = [central_region(n) for n in dims]
+    m = [hi - lo + 1 for lo, hi, _ in reg]
+    pads = tuple(L for _, _, L in reg)                     # left padding of the equivalent small transposed conv
+    g = torch.Generator().manual_seed(cin + cout + dims[0])
+    x = torch.randn(2, cin, *m, generator=g).to(DEV).to(torch.bfloat16).contiguous(memory_format=torch.channels_last_3d)
+    wt = (torch.randn(cin, cout, 3, 3, 3, generator=g) / (8 * cin) ** 0.5).to(DEV).to(torch.bfloat16)
+    be = conv_backends.get("tcgen05")
+    x1, w1 = x.clone().requires_grad_(True), wt.clone().requires_grad_(True)
+    n0 = mvs_b200.launch_count()
+    y = be.conv_transpose3d(x1, w1, 2, pads, dims)
+    assert mvs_b200.launch_count() >= n0 + 8
+    x2, w2 = x.float().requires_grad_(True), wt.float().requires_grad_(True)
+    ref = conv_backends.TorchConvBackend.conv_transpose3d(x2, w2, 2, pads, dims)
+    assert y.shape == ref.shape
+    assert _rel(y, ref) < TOL
+    gy = torch.randn(ref.shape, generator=g).to(DEV).to(torch.bfloat16)
+    y.backward(gy)
+    ref.backward(gy.float())
+    assert _rel(x1.grad, x2.grad) < TOL
+    assert _rel(w1.grad, w2.grad) < 2 * TOL
