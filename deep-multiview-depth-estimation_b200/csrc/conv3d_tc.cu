@@ -793,6 +793,326 @@ int launch_wgrad(const void* x, const void* gy, float* gw, int B, int Di, int Hi
     return MVSB200_OK;
 }
 
+// =================================================================================================================
+// Stride-2 convolution forward on tcgen05:  out(o) = sum_k W[k] . x(2o - pad + k)   (per axis, k = 0..2, x zero outside).
+// The three stride-2 branches conv_{1,2,3}_0 of the regulariser (scripts/model.py:104-110, stacked along Cout) and, with the
+// transposed filter, the data gradient of the transposed convolutions.
+// A UMMA operand needs voxel rows at a constant pitch, so the stride-2 reads are turned into stride-1 reads of the four
+// in-plane PARITY sub-lattices of x: tap k of an axis reads sub-lattice q = (k - pad) & 1 at index o + s,
+// s = (k - pad - q) / 2 in {-1, 0}.  Each sub-lattice is just another 5-D TMA tensor map over the same memory (doubled
+// h/w strides, shifted base), so TMA lands parity-pure slabs with a 1-voxel halo; the depth axis needs no
+// de-interleaving (plane 2*od - pad + kd is addressed directly).  The slabs form a linear stream -- per output plane:
+// 4 parity classes x 3 depth taps -- each consumed once by the 1, 2 or 4 taps that live on it, all accumulating into
+// the plane's TMEM accumulator.
+constexpr int kS2Slots = 4;
+
+struct ConvS2Params {
+    int B, Do, Ho, Wo;              // output volume
+    int pad_d, pad_h, pad_w;        // out(o) reads x(2o - pad + k)
+    int Dx;                         // input planes (depth is not de-interleaved: out-of-range planes are zero)
+    int BW, L, MB;                  // sub-slab: BW voxels per line (incl. 1 halo), L output lines, MB 128-row blocks
+    int tiles_x, tiles_y;
+    int dchunk, nchunks, n_items;
+    int cout, y_cs, y_coff, n_rows, w_row0;
+    int slab_bytes;
+    __nv_bfloat16* y;
+};
+
+template <int CIN, int NOUT>
+__global__ void __launch_bounds__(kTcThreads, 1)
+conv3d_s2_tc_kernel(const __grid_constant__ CUtensorMap tm_x00, const __grid_constant__ CUtensorMap tm_x01,
+                    const __grid_constant__ CUtensorMap tm_x10, const __grid_constant__ CUtensorMap tm_x11,
+                    const __grid_constant__ CUtensorMap tm_w, const ConvS2Params p) {
+    constexpr int ROWB = CIN * 2;
+    constexpr int KSTEPS = CIN / 16;
+    constexpr int W_TAP_BYTES = NOUT * ROWB;
+    constexpr int W_BYTES = 27 * W_TAP_BYTES;
+    constexpr int W_BYTES_AL = (W_BYTES + 1023) / 1024 * 1024;
+    constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NOUT >> 3) << 17) | ((128u >> 4) << 24);
+
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
+    unsigned char* w_smem = smem;
+    unsigned char* slab_smem = smem + W_BYTES_AL;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(slab_smem + (size_t)kS2Slots * p.slab_bytes);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + kS2Slots;
+    uint64_t* wfull = bars + 2 * kS2Slots;
+    uint64_t* tfull = wfull + 1;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int MB = p.MB;
+    const int tiles = p.tiles_x * p.tiles_y;
+    uint32_t tmem_cols = 32;
+    while ((int)tmem_cols < 2 * MB * NOUT) tmem_cols <<= 1;
+
+    if (threadIdx.x == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_x00) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_x01) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_x10) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_x11) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_w) : "memory");
+        for (int i = 0; i < kS2Slots; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
+        mbar_init(wfull, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(tfull + i, 1); mbar_init(tempty + i, 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    auto decode = [&](int item, int& b, int& d_begin, int& nd, int& x0, int& y0) {
+        const int t = item % tiles, r = item / tiles;
+        const int c = r % p.nchunks;
+        b = r / p.nchunks;
+        d_begin = c * p.dchunk;
+        nd = min(p.dchunk, p.Do - d_begin);
+        x0 = (t % p.tiles_x) * (p.BW - 1);
+        y0 = (t / p.tiles_x) * p.L;
+    };
+
+    if (warp == 0) {
+        // ===================================== TMA producer =====================================
+        if (elect_one()) {
+            mbar_expect_tx(wfull, W_BYTES);
+            for (int tap = 0; tap < 27; ++tap)
+                tma_load_2d(w_smem + tap * W_TAP_BYTES, &tm_w, wfull, 0, tap * p.n_rows + p.w_row0);
+        }
+        __syncwarp();
+        const uint32_t box_bytes = (uint32_t)ROWB * p.BW * (p.L + 1);
+        int gs = 0;
+        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+            int b, d_begin, nd, x0, y0;
+            decode(item, b, d_begin, nd, x0, y0);
+            for (int d = 0; d < nd; ++d) {
+                for (int c = 0; c < 4; ++c) {
+                    const CUtensorMap* tm = c == 0 ? &tm_x00 : (c == 1 ? &tm_x01 : (c == 2 ? &tm_x10 : &tm_x11));
+                    for (int kd = 0; kd < 3; ++kd, ++gs) {
+                        const int slot = gs % kS2Slots;
+                        if (gs >= kS2Slots) mbar_wait(empty + slot, ((gs / kS2Slots) - 1) & 1);
+                        if (elect_one()) {
+                            mbar_expect_tx(full + slot, box_bytes);
+                            tma_load_5d(slab_smem + (size_t)slot * p.slab_bytes, tm, full + slot, 0, x0 - 1, y0 - 1,
+                                        2 * (d_begin + d) - p.pad_d + kd, b);
+                        }
+                        __syncwarp();
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================== MMA issuer =======================================
+        mbar_wait(wfull, 0);
+        const uint64_t d0 = umma_desc<ROWB>(0);
+        const uint32_t desc_hi = (uint32_t)(d0 >> 32);
+        const uint32_t w_lo = (uint32_t)d0 | (smem_u32(w_smem) >> 4);
+        const uint32_t slab_lo = (uint32_t)d0 | (smem_u32(slab_smem) >> 4);
+        const uint32_t bw16 = (uint32_t)(p.BW * ROWB) >> 4, slab16 = (uint32_t)p.slab_bytes >> 4;
+        int gs = 0, gp = 0;
+        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+            int b, d_begin, nd, x0, y0;
+            decode(item, b, d_begin, nd, x0, y0);
+            for (int d = 0; d < nd; ++d, ++gp) {
+                const int stage = gp & 1;
+                if (gp >= 2) mbar_wait(tempty + stage, ((gp >> 1) - 1) & 1);
+                uint32_t acc = 0;                        // uniform over the 128-row blocks: the plane's first MMA initialises
+                for (int c = 0; c < 4; ++c) {
+                    const int qy = c >> 1, qx = c & 1;
+                    for (int kd = 0; kd < 3; ++kd, ++gs) {
+                        const int slot = gs % kS2Slots;
+                        mbar_wait(full + slot, (gs / kS2Slots) & 1);
+                        tc_fence_after();
+                        if (elect_one()) {
+                            const uint32_t s_lo = slab_lo + (uint32_t)slot * slab16;
+#pragma unroll
+                            for (int kh = 0; kh < 3; ++kh) {
+                                if (((kh - p.pad_h) & 1) != qy) continue;
+                                const int sy = (kh - p.pad_h - qy) >> 1;           // -1 or 0
+#pragma unroll
+                                for (int kw = 0; kw < 3; ++kw) {
+                                    if (((kw - p.pad_w) & 1) != qx) continue;
+                                    const int sx = (kw - p.pad_w - qx) >> 1;
+                                    const uint32_t row_lo = s_lo + (uint32_t)(sy + 1) * bw16 + (uint32_t)(((sx + 1) * ROWB) >> 4);
+                                    const uint32_t wt_lo = w_lo + (uint32_t)((((kd * 3 + kh) * 3 + kw) * W_TAP_BYTES) >> 4);
+                                    for (int mb = 0; mb < MB; ++mb) {
+                                        const uint32_t d_tmem = tmem_base + (uint32_t)((stage * MB + mb) * NOUT);
+#pragma unroll
+                                        for (int k = 0; k < KSTEPS; ++k)
+                                            umma_bf16_lohi(d_tmem, row_lo + (uint32_t)((mb * 128 * ROWB + k * 32) >> 4), desc_hi,
+                                                           wt_lo + (uint32_t)((k * 32) >> 4), desc_hi, IDESC, acc | (uint32_t)(k != 0));
+                                    }
+                                    acc = 1;
+                                }
+                            }
+                            umma_commit(empty + slot);
+                        }
+                        __syncwarp();
+                        acc = 1;                         // every (class, kd) slab carries at least one tap
+                    }
+                }
+                if (elect_one()) umma_commit(tfull + stage);
+                __syncwarp();
+            }
+        }
+    } else {
+        // ===================================== epilogue =========================================
+        const int q = warp & 3;
+        int ti[kMaxMB], tj[kMaxMB];
+        bool ok[kMaxMB];
+#pragma unroll
+        for (int mb = 0; mb < kMaxMB; ++mb) {
+            const int m = mb * 128 + q * 32 + lane;
+            tj[mb] = m / p.BW; ti[mb] = m - tj[mb] * p.BW;
+            ok[mb] = ti[mb] < p.BW - 1 && tj[mb] < p.L;
+        }
+        int gp = 0;
+        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+            int b, d_begin, nd, x0, y0;
+            decode(item, b, d_begin, nd, x0, y0);
+            for (int d = 0; d < nd; ++d, ++gp) {
+                const int stage = gp & 1;
+                mbar_wait(tfull + stage, (gp >> 1) & 1);
+                tc_fence_after();
+                __nv_bfloat16* plane0 = p.y + ((((size_t)b * p.Do + d_begin + d) * p.Ho + y0) * p.Wo + x0) * p.y_cs + p.y_coff;
+#pragma unroll
+                for (int mb = 0; mb < kMaxMB; ++mb) {
+                    if (mb < MB) {
+#pragma unroll
+                        for (int c0 = 0; c0 < NOUT; c0 += 16) {
+                            uint32_t v[16];
+                            tmem_ld<16>(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((stage * MB + mb) * NOUT + c0), v);
+                            tmem_ld_wait();
+                            if (ok[mb] && x0 + ti[mb] < p.Wo && y0 + tj[mb] < p.Ho) {
+                                __nv_bfloat16* row = plane0 + ((size_t)tj[mb] * p.Wo + ti[mb]) * p.y_cs;
+#pragma unroll
+                                for (int c = 0; c < 16; c += 8) {
+                                    if (c0 + c < p.cout) {
+                                        const uint4 o = make_uint4(pack_bf16x2(__uint_as_float(v[c]), __uint_as_float(v[c + 1])),
+                                                                   pack_bf16x2(__uint_as_float(v[c + 2]), __uint_as_float(v[c + 3])),
+                                                                   pack_bf16x2(__uint_as_float(v[c + 4]), __uint_as_float(v[c + 5])),
+                                                                   pack_bf16x2(__uint_as_float(v[c + 6]), __uint_as_float(v[c + 7])));
+                                        *reinterpret_cast<uint4*>(row + c0 + c) = o;
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty + stage);
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+    }
+}
+
+TilePlan plan_tiles_s2(int Ho, int Wo, int rowb, size_t w_bytes_al, size_t smem_budget) {
+    TilePlan best{};
+    best.score = -1.0;
+    for (int MB = 1; MB <= kMaxMB; MB *= 2) {
+        for (int BW = 9; BW <= 256; ++BW) {
+            const int L = (MB * 128) / BW;
+            if (L < 1 || L + 1 > 256) continue;
+            const int rows = MB * 128 + BW + 2;
+            const int slab = ((rows * rowb) + 1023) / 1024 * 1024;
+            if (w_bytes_al + (size_t)kS2Slots * slab + 256 > smem_budget) continue;
+            const int tiles_x = (Wo + BW - 2) / (BW - 1), tiles_y = (Ho + L - 1) / L;
+            const double mma_eff = (double)Wo * Ho / ((double)tiles_x * tiles_y * MB * 128);
+            const double load_eff = (double)Wo * Ho / ((double)tiles_x * tiles_y * (L + 1) * BW);
+            const double score = mma_eff * (0.5 + 0.5 * load_eff);
+            if (score > best.score) best = TilePlan{BW, L, MB, tiles_x, tiles_y, slab, score};
+        }
+    }
+    return best;
+}
+
+template <int CIN, int NOUT>
+int launch_conv_s2(const void* x, const void* w, void* y, int B, int Dx, int Hx, int Wx, int Do, int Ho, int Wo, int cout, int y_cs,
+                   int y_coff, int n_rows, int w_row0, int pad_d, int pad_h, int pad_w, cudaStream_t st) {
+    constexpr int ROWB = CIN * 2;
+    constexpr size_t W_BYTES_AL = ((size_t)27 * NOUT * ROWB + 1023) / 1024 * 1024;
+    EncodeTiledFn enc = encode_fn();
+    MVS_REQUIRE(enc != nullptr, "conv3d_s2: cuTensorMapEncodeTiled is not available from the driver");
+    const size_t smem_budget = 227 * 1024 - 1024;
+    const TilePlan tp = plan_tiles_s2(Ho, Wo, ROWB, W_BYTES_AL, smem_budget);
+    MVS_REQUIRE(tp.score > 0, "conv3d_s2: no slab geometry fits shared memory (Cin=%d, N=%d)", CIN, NOUT);
+
+    CUtensorMap tm_x[4], tm_w;
+    for (int c = 0; c < 4; ++c) {
+        const int qy = c >> 1, qx = c & 1;
+        const int Ws = (Wx - qx + 1) / 2, Hs = (Hx - qy + 1) / 2;      // sub-lattice extents
+        const char* base = reinterpret_cast<const char*>(x) + ((size_t)qy * Wx + qx) * ROWB;
+        if (Ws < 1 || Hs < 1) {                                        // degenerate (1-voxel axis): alias class 0, taps read zeros? never used
+            tm_x[c] = tm_x[0];
+            continue;
+        }
+        const cuuint64_t dims[5] = {(cuuint64_t)CIN, (cuuint64_t)Ws, (cuuint64_t)Hs, (cuuint64_t)Dx, (cuuint64_t)B};
+        const cuuint64_t strides[4] = {(cuuint64_t)2 * ROWB, (cuuint64_t)2 * ROWB * Wx, (cuuint64_t)ROWB * Wx * Hx,
+                                       (cuuint64_t)ROWB * Wx * Hx * Dx};
+        const cuuint32_t box[5] = {(cuuint32_t)CIN, (cuuint32_t)tp.BW, (cuuint32_t)(tp.L + 1), 1, 1};
+        const cuuint32_t es[5] = {1, 1, 1, 1, 1};
+        CUresult r = enc(&tm_x[c], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<char*>(base), dims, strides, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(ROWB), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        MVS_REQUIRE(r == CUDA_SUCCESS, "conv3d_s2: cuTensorMapEncodeTiled(x, class %d) failed (%d)", c, (int)r);
+    }
+    {
+        const cuuint64_t dims[2] = {(cuuint64_t)CIN, (cuuint64_t)27 * n_rows};
+        const cuuint64_t strides[1] = {(cuuint64_t)ROWB};
+        const cuuint32_t box[2] = {(cuuint32_t)CIN, (cuuint32_t)NOUT};
+        const cuuint32_t es[2] = {1, 1};
+        CUresult r = enc(&tm_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims, strides, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(ROWB), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        MVS_REQUIRE(r == CUDA_SUCCESS, "conv3d_s2: cuTensorMapEncodeTiled(w) failed (%d)", (int)r);
+    }
+    ConvS2Params p;
+    p.B = B; p.Do = Do; p.Ho = Ho; p.Wo = Wo; p.pad_d = pad_d; p.pad_h = pad_h; p.pad_w = pad_w; p.Dx = Dx;
+    p.BW = tp.BW; p.L = tp.L; p.MB = tp.MB; p.tiles_x = tp.tiles_x; p.tiles_y = tp.tiles_y;
+    p.cout = cout; p.y_cs = y_cs; p.y_coff = y_coff; p.n_rows = n_rows; p.w_row0 = w_row0;
+    p.slab_bytes = tp.slab_bytes;
+    p.y = reinterpret_cast<__nv_bfloat16*>(y);
+    const long tiles = (long)tp.tiles_x * tp.tiles_y;
+    int sms = 148;
+    {
+        int dev = 0, n = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) sms = n;
+    }
+    long best_cost = -1;
+    int best_chunks = 1;
+    for (int nc = 1; nc <= Do; ++nc) {
+        const int dc = (Do + nc - 1) / nc;
+        if ((long)(nc - 1) * dc >= Do) continue;
+        const long items = tiles * nc * B;
+        const long cost = ((items + sms - 1) / sms) * (dc + 1);
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_chunks = nc; }
+    }
+    p.nchunks = best_chunks;
+    p.dchunk = (Do + best_chunks - 1) / best_chunks;
+    p.n_items = (int)(tiles * p.nchunks * B);
+    const dim3 grid((unsigned)(p.n_items < sms ? p.n_items : sms), 1, 1);
+    const size_t smem = 1024 + W_BYTES_AL + (size_t)kS2Slots * tp.slab_bytes + 256;
+    MVS_CUDA(cudaFuncSetAttribute(conv3d_s2_tc_kernel<CIN, NOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conv3d_s2_tc_kernel<CIN, NOUT><<<grid, kTcThreads, smem, st>>>(tm_x[0], tm_x[1], tm_x[2], tm_x[3], tm_w, p);
+    MVS_CHECK_LAUNCH("conv3d_s2_tc");
+    return MVSB200_OK;
+}
+
 }  // namespace
 
 static int conv3d_s1_dispatch(const void* x, const void* w_packed, void* y, int B, int Di, int Hi, int Wi, int Cin, int Do, int Ho,
@@ -869,6 +1189,41 @@ extern "C" int mvsb200_conv3d_s1_wgrad(const void* x, const void* gy, float* gw,
         else MVS_FAIL(MVSB200_E_UNSUPPORTED, "conv3d_s1_wgrad: unsupported channels Cin=%d cout=%d", Cin, cout);
 #undef MVS_WG
         if (rc != MVSB200_OK) return rc;
+    }
+    return MVSB200_OK;
+}
+
+extern "C" int mvsb200_conv3d_s2_fwd(const void* x, const void* w_packed, void* y, int B, int Dx, int Hx, int Wx, int Cin, int Do,
+                                     int Ho, int Wo, int cout, int y_cs, int n_rows, int pad_d, int pad_h, int pad_w, void* stream) {
+    MVS_REQUIRE(x && w_packed && y, "conv3d_s2_fwd: null pointer");
+    MVS_REQUIRE(aligned16(x) && aligned16(w_packed) && aligned16(y), "conv3d_s2_fwd: pointers must be 16-byte aligned");
+    MVS_REQUIRE(B >= 1 && Dx >= 1 && Hx >= 2 && Wx >= 2 && Do >= 1 && Ho >= 1 && Wo >= 1, "conv3d_s2_fwd: bad shape");
+    MVS_REQUIRE(cout >= 8 && cout % 8 == 0 && cout <= n_rows && n_rows % 16 == 0 && n_rows <= 128, "conv3d_s2_fwd: cout %d / n_rows %d", cout, n_rows);
+    MVS_REQUIRE(y_cs >= cout && y_cs % 8 == 0, "conv3d_s2_fwd: output channel stride %d", y_cs);
+    MVS_REQUIRE(pad_d >= 1 && pad_d <= 2 && pad_h >= 1 && pad_h <= 2 && pad_w >= 1 && pad_w <= 2, "conv3d_s2_fwd: pad must be 1 or 2 per axis");
+    cudaStream_t st = (cudaStream_t)stream;
+    // filter rows per launch: up to 64 (27 x 64 x Cin taps resident in shared memory), then 48 / 32 / 16
+    for (int row0 = 0; row0 < n_rows && row0 < cout;) {
+        const int left = n_rows - row0;
+        const int nmax = Cin == 64 ? 32 : 64;
+        const int nout = left >= nmax ? nmax : left;
+        const int c_here = cout - row0 < nout ? cout - row0 : nout;
+        int rc = MVSB200_E_UNSUPPORTED;
+#define MVS_S2(CI, NO) rc = launch_conv_s2<CI, NO>(x, w_packed, y, B, Dx, Hx, Wx, Do, Ho, Wo, c_here, y_cs, row0, n_rows, row0, pad_d, pad_h, pad_w, st)
+        if (Cin == 16 && nout == 16) MVS_S2(16, 16);
+        else if (Cin == 16 && nout == 32) MVS_S2(16, 32);
+        else if (Cin == 16 && nout == 48) MVS_S2(16, 48);
+        else if (Cin == 16 && nout == 64) MVS_S2(16, 64);
+        else if (Cin == 32 && nout == 16) MVS_S2(32, 16);
+        else if (Cin == 32 && nout == 32) MVS_S2(32, 32);
+        else if (Cin == 32 && nout == 48) MVS_S2(32, 48);
+        else if (Cin == 32 && nout == 64) MVS_S2(32, 64);
+        else if (Cin == 64 && nout == 16) MVS_S2(64, 16);
+        else if (Cin == 64 && nout == 32) MVS_S2(64, 32);
+        else MVS_FAIL(MVSB200_E_UNSUPPORTED, "conv3d_s2_fwd: unsupported channels Cin=%d rows=%d", Cin, nout);
+#undef MVS_S2
+        if (rc != MVSB200_OK) return rc;
+        row0 += nout;
     }
     return MVSB200_OK;
 }

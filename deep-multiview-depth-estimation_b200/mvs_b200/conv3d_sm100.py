@@ -206,8 +206,63 @@ class _ConvTranspose3dS2(torch.autograd.Function):
         return gx, gw, None, None
 
 
+# ---- stride-2 convolution on the central box (the stacked branches conv_{1,2,3}_0) ----------------------------------
+def pack_filter_rows(w: torch.Tensor, n_rows: int) -> torch.Tensor:
+    co, ci = w.shape[:2]
+    wp = torch.zeros(27, n_rows, ci, dtype=torch.bfloat16, device=w.device)
+    wp[:, :co] = w.detach().permute(2, 3, 4, 0, 1).reshape(27, co, ci).to(torch.bfloat16)
+    return wp
+
+
+class _Conv3dS2Box(torch.autograd.Function):
+    """out(o) = sum_k W[k] x(2o - pad + k) for o in a box of `out_dims` voxels (zero outside x).  Forward on the tcgen05
+    stride-2 kernel; the gradients go through the library's strided convolution backward (until the stride-2 wgrad /
+    transposed dgrad kernels take Cout = 112 operands)."""
+
+    @staticmethod
+    def forward(ctx, x, w, pads, out_dims):
+        x_cl = x.detach().contiguous(memory_format=torch.channels_last_3d)
+        B, cin, Dx, Hx, Wx = x_cl.shape
+        cout = w.shape[0]
+        n_rows = (cout + 15) // 16 * 16
+        Do, Ho, Wo = out_dims
+        y = torch.empty((B, cout, Do, Ho, Wo), dtype=torch.bfloat16, device=x.device, memory_format=torch.channels_last_3d)
+        with _timed("conv3d_s2_tc", 2.0 * 27 * cin * cout * B * Do * Ho * Wo):
+            _lib.call("mvsb200_conv3d_s2_fwd", x_cl.data_ptr(), pack_filter_rows(w, n_rows).data_ptr(), y.data_ptr(), B, Dx, Hx, Wx,
+                      cin, Do, Ho, Wo, cout, cout, n_rows, pads[0], pads[1], pads[2], _stream())
+        ctx.save_for_backward(x_cl, w)
+        ctx.pads, ctx.out_dims = tuple(pads), tuple(out_dims)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x_cl, w = ctx.saved_tensors
+        # the same convolution as the library sees it: symmetric padding P = pad (+2 if pad < 2 ... keeps parity), output
+        # cropped at offset (P - pad)/2
+        P = tuple(q if q >= 2 else q + 2 for q in ctx.pads)
+        off = tuple((a - b) // 2 for a, b in zip(P, ctx.pads))
+        nat = tuple((n + 2 * a - 3) // 2 + 1 for n, a in zip(x_cl.shape[2:], P))
+        gy = gy.to(torch.bfloat16)
+        padding = []
+        for ax in (2, 1, 0):
+            padding += [off[ax], nat[ax] - off[ax] - ctx.out_dims[ax]]
+        g_full = F.pad(gy, padding).contiguous(memory_format=torch.channels_last_3d)
+        mask = [bool(ctx.needs_input_grad[0]), bool(ctx.needs_input_grad[1]), False]
+        gx, gw, _ = torch.ops.aten.convolution_backward(g_full, x_cl, w.detach().to(torch.bfloat16), None, [2, 2, 2], list(P),
+                                                        [1, 1, 1], False, [0, 0, 0], 1, mask)
+        return gx, (gw.to(w.dtype) if gw is not None else None), None, None
+
+
 class Tcgen05ConvBackend:
     name = "tcgen05"
+
+    @staticmethod
+    def conv3d_s2_box(x, w, pads, out_dims):
+        """Stride-2 convolution evaluated on a box: out(o) = sum_k W[k] x(2o - pad + k), o in [0, out_dims)."""
+        if (x.is_cuda and x.dtype == torch.bfloat16 and x.shape[1] in _CIN_OK and w.shape[0] % 8 == 0 and w.shape[0] <= 128
+                and all(q in (1, 2) for q in pads) and min(x.shape[3:]) >= 2):
+            return _Conv3dS2Box.apply(x, w, tuple(int(q) for q in pads), tuple(int(n) for n in out_dims))
+        return None
 
     @staticmethod
     def conv3d(x, w, stride, padding):

@@ -136,6 +136,15 @@ int mvsb200_conv3d_s1_fwd_ex(const void* x, const void* w_packed, void* y, int B
                              int Do, int Ho, int Wo, int cout, int n_rows, int off_d, int off_h, int off_w,
                              unsigned tap_mask, const int64_t* y_strides4_host, void* stream);
 
+/* Stride-2 convolution forward on tcgen05 (parity-deinterleaved sub-lattice slabs through TMA): the three stride-2
+ * branches conv_{1,2,3}_0 (scripts/model.py:104-110; padding dim/2+1 of scripts/config.py:20 reduces on the central
+ * box to pad 1 or 2) stacked along Cout, and the data gradient of the transposed convolutions.
+ *   out(z,y,x) = sum_k W[k] . x(2z - pad_d + kd, 2y - pad_h + kh, 2x - pad_w + kw), zero outside x; pad in {1,2}.
+ * x: [B, Dx, Hx, Wx, Cin] bf16; w_packed: [27, n_rows, Cin] bf16 (n_rows % 16 == 0, <= 128); y: [B, Do, Ho, Wo, y_cs] bf16. */
+int mvsb200_conv3d_s2_fwd(const void* x, const void* w_packed, void* y, int B, int Dx, int Hx, int Wx, int Cin,
+                          int Do, int Ho, int Wo, int cout, int y_cs, int n_rows, int pad_d, int pad_h, int pad_w,
+                          void* stream);
+
 /* Weight gradient of the same convolution on tcgen05 (autograd of scripts/model.py:101-113 w.r.t. the filters):
  *   gW[tap][ci][co] = sum_v x(v + tap + off)[ci] * gy(v)[co]
  * x: [B, Di, Hi, Wi, Cin] bf16; gy: [B, Do, Ho, Wo, cout] bf16 (cout in {8,16,32,64}); gw: [27, Cin, cout] fp32,

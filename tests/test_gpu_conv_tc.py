@@ -141,3 +141,32 @@ def test_transposed_conv_by_parity_classes(cin, cout, dims):
     ref.backward(gy.float())
     assert _rel(x1.grad, x2.grad) < TOL
     assert _rel(w1.grad, w2.grad) < 2 * TOL
+
+
+@pytest.mark.parametrize("cin,cout", [(32, 112), (32, 16), (16, 32), (64, 32)])
+@pytest.mark.parametrize("dims", [(12, 10, 14), (11, 9, 15), (8, 7, 12), (6, 33, 47)])
+def test_stride2_conv_on_the_central_box(cin, cout, dims):
+    """The stride-2 branches (model.py:104-110, padding dim/2+1) evaluated on the central box by the tcgen05 stride-2
+    kernel (parity sub-lattice slabs) vs the reference formulation conv3d(stride 2, padding dim/2+1) cropped to the box."""
+    from mvs_b200.regulariser import central_region
+    reg = [central_region(n) for n in dims]
+    box = tuple(slice(lo, hi + 1) for lo, hi, _ in reg)
+    g = torch.Generator().manual_seed(cin + cout + dims[1])
+    x = torch.randn(2, cin, *dims, generator=g).to(DEV).to(torch.bfloat16).contiguous(memory_format=torch.channels_last_3d)
+    wt = (torch.randn(cout, cin, 3, 3, 3, generator=g) / (27 * cin) ** 0.5).to(DEV).to(torch.bfloat16)
+    x1, w1 = x.clone().requires_grad_(True), wt.clone().requires_grad_(True)
+    y = conv_backends.get("tcgen05").conv3d_s2_box(x1, w1, tuple(L for _, _, L in reg), tuple(hi - lo + 1 for lo, hi, _ in reg))
+    assert y is not None
+    x2, w2 = x.float().requires_grad_(True), wt.float().requires_grad_(True)
+    full = F.conv3d(x2, w2, None, 2, tuple(n // 2 + 1 for n in dims))        # the reference's layer on the full canvas
+    ref = full[(slice(None), slice(None)) + box]
+    assert y.shape == ref.shape
+    assert _rel(y, ref) < TOL
+    outside = full.clone()
+    outside[(slice(None), slice(None)) + box] = 0
+    assert outside.abs().max() == 0                                            # ... which is zero outside the box
+    gy = torch.randn(ref.shape, generator=g).to(DEV).to(torch.bfloat16)
+    y.backward(gy)
+    ref.backward(gy.float())
+    assert _rel(x1.grad, x2.grad) < TOL
+    assert _rel(w1.grad, w2.grad) < 2 * TOL
