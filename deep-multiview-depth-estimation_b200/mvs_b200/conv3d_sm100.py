@@ -197,7 +197,18 @@ class _ConvTranspose3dS2(torch.autograd.Function):
         inner = (slice(None), slice(None)) + tuple(slice(1, 1 + a) for a in m)
         wb = w.detach().to(torch.bfloat16)
         if ctx.needs_input_grad[0]:
-            gx = F.conv3d(gy, wb, None, 2, P2)[inner]                 # weight [Cin, Cout, ...] read as out = Cin, in = Cout
+            cin_t, cout_t = w.shape[:2]
+            if cout_t in _CIN_OK and cin_t % 8 == 0:
+                # x[i] = sum_k W[k]^T gy[2i - p + k]: the tcgen05 stride-2 kernel with the filter read as out = Cin, in = Cout
+                B = gy.shape[0]
+                n_rows = (cin_t + 15) // 16 * 16
+                gx = torch.empty(x_cl.shape, dtype=torch.bfloat16, device=gy.device, memory_format=torch.channels_last_3d)
+                with _timed("conv3d_s2_tc", 2.0 * 27 * cin_t * cout_t * x_cl.numel() / cin_t):
+                    _lib.call("mvsb200_conv3d_s2_fwd", gy.data_ptr(), pack_filter_rows(wb, n_rows).data_ptr(), gx.data_ptr(), B,
+                              gy.shape[2], gy.shape[3], gy.shape[4], cout_t, m[0], m[1], m[2], cin_t, cin_t, n_rows,
+                              pads[0], pads[1], pads[2], _stream())
+            else:
+                gx = F.conv3d(gy, wb, None, 2, P2)[inner]             # weight [Cin, Cout, ...] read as out = Cin, in = Cout
         if ctx.needs_input_grad[1]:
             xs = torch.zeros((x_cl.shape[0], x_cl.shape[1]) + tuple(n_o), dtype=x_cl.dtype, device=x_cl.device,
                              ).contiguous(memory_format=torch.channels_last_3d)
