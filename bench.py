@@ -30,6 +30,8 @@ WORKLOADS = {
                  desc="MVSNet train step bf16, batch 4/GPU, 3 views, 640x512, D=192 (BASELINE.json configs[1])"),
     "cfg1": dict(B=1, V=3, H=512, W=640, D=192, train=False,
                  desc="MVSNet forward, batch 1, 3 views, 640x512, D=192 (BASELINE.json configs[0])"),
+    "cfg4": dict(B=1, V=5, H=1184, W=1600, D=256, train=False,
+                 desc="MVSNet inference, 5 views, 1600x1184, D=256 on ONE GPU (BASELINE.json configs[3] without the depth-slab split)"),
 }
 
 
@@ -244,7 +246,7 @@ def run_b200(args, rank, world, local_rank):
             kern[name].update({"alg_bytes": alg[name], "GBps": alg[name] / (t * 1e-3) / 1e9,
                                "frac_hbm": alg[name] / (t * 1e-3) / 1e9 / peak})
         work = [w for _, _, w in evs if w is not None]
-        if work and name == "conv3d_s1_tc":
+        if work and name in ("conv3d_s1_tc", "conv3d_s2_tc", "conv3d_s1_wgrad_tc"):
             kern[name].update({"alg_flops_per_step": sum(work) / args.steps, "TFLOPs": sum(work) / (tot * 1e-3) / 1e12})
     k1 = kern.get("warp_variance_fwd", {})
     roofline_k1 = {"kernel": "warp_variance_fwd_kernel<V=3, bf16 volume>", "bound": "hbm", "achieved": k1.get("GBps"),
@@ -256,8 +258,9 @@ def run_b200(args, rank, world, local_rank):
     # dominant own kernel by time in the step: the tcgen05 convolution (all its launches of the timed steps together)
     k3 = kern.get("conv3d_s1_tc", {})
     tpeak, tpeak_src = _tensor_peak()
-    roofline = {"kernel": "conv3d_s1_tc_kernel<CIN,NOUT> (tcgen05/TMEM/TMA implicit-GEMM conv3d; %d launches/step: forward of "
-                          "conv_0_0, conv_{1,2,3}_1 and data gradient of conv_{1,2,3}_1)" % (k3.get("launches", 0) // max(args.steps, 1)),
+    roofline = {"kernel": "conv3d_s1_tc_kernel<CIN,NOUT> (tcgen05/TMEM/TMA implicit-GEMM conv3d; %d calls/step: forward and data "
+                          "gradient of conv_0_0, conv_{1,2,3}_1, and the transposed convs' forward as 8 parity-class launches each)"
+                          % (k3.get("launches", 0) // max(args.steps, 1)),
                 "bound": "tensor", "achieved": k3.get("TFLOPs"), "peak": tpeak, "peak_source": tpeak_src, "unit": "TFLOP/s",
                 "frac": (k3["TFLOPs"] / tpeak) if k3.get("TFLOPs") else None,
                 "traffic": _ncu_traffic("r01_k3_conv3d_s1_tc_ncu.json"),

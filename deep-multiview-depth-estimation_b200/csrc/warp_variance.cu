@@ -184,6 +184,25 @@ __device__ __forceinline__ void blend2(const Sample2& s, const float4& t00, cons
     hi = __ffma2_rn(d, hi2(t11), __ffma2_rn(c, hi2(t10), __ffma2_rn(b, hi2(t01), __fmul2_rn(a, hi2(t00)))));
 }
 
+// scalar twin of variance2: plain FADD/FFMA can issue on either FMA sub-pipe, the packed f32x2 forms only on the heavy one
+// (profiles/r01_k1_notes.md) -- the forward kernel blends with packed math and takes the variance with scalar math so
+// that both sub-pipes work
+template <int V>
+__device__ __forceinline__ float variance1(const float (&x)[V], float ninv, float inv_out) {
+    float sum = x[0];
+#pragma unroll
+    for (int v = 1; v < V; ++v) sum += x[v];
+    const float nmean = sum * ninv;
+    float d = x[0] + nmean;
+    float acc = d * d;
+#pragma unroll
+    for (int v = 1; v < V; ++v) {
+        d = x[v] + nmean;
+        acc = fmaf(d, d, acc);
+    }
+    return acc * inv_out;
+}
+
 // population variance over V samples, two-pass as costvolume.py:12-14 (mean, then sum (x-mean)^2, / V)
 template <int V>
 __device__ __forceinline__ float2 variance2(const float2 (&x)[V], float2 ninv, float2 inv_out) {
@@ -383,7 +402,11 @@ warp_variance_fwd_kernel(const float4* __restrict__ feat, const ViewParams* __re
                     k00[v] = of.x; k11[v] = of.w;
                     blend2w(wt.x, wt.y, wt.z, wt.w, taps[v][0], taps[v][1], taps[v][2], taps[v][3], val[0][v], val[1][v]);
                 }
-                const float2 r0 = variance2<V>(val[0], ninv, inv_out), r1 = variance2<V>(val[1], ninv, inv_out);
+                float xs[4][V];
+#pragma unroll
+                for (int v = 0; v < V; ++v) { xs[0][v] = val[0][v].x; xs[1][v] = val[0][v].y; xs[2][v] = val[1][v].x; xs[3][v] = val[1][v].y; }
+                const float2 r0 = make_float2(variance1<V>(xs[0], -invV, invV), variance1<V>(xs[1], -invV, invV));
+                const float2 r1 = make_float2(variance1<V>(xs[2], -invV, invV), variance1<V>(xs[3], -invV, invV));
                 if (BF16OUT) {
                     __nv_bfloat16* row = reinterpret_cast<__nv_bfloat16*>(cost) + vox * kC + 4 * cg;
                     st_cs_u2(row, pack_bf16x2(r0.x, r0.y), pack_bf16x2(r1.x, r1.y));

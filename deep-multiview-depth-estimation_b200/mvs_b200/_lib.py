@@ -8,7 +8,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.normpath(os.path.join(_HERE, "..", "csrc", "libmvs_b200.so"))
+LIB_PATH = os.environ.get("MVSB200_LIB") or os.path.normpath(os.path.join(_HERE, "..", "csrc", "libmvs_b200.so"))   # env: A/B builds
 ABI_VERSION = 1
 F32, BF16 = 0, 1
 VIEW_PARAM_FLOATS = 16
