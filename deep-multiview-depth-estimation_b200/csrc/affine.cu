@@ -83,12 +83,23 @@ __device__ __forceinline__ void reduce_to_partial(float (&a)[8], float (&b)[8], 
     }
 }
 
-__global__ void finalize_sums_kernel(const float* __restrict__ partials, int nblocks, int C, float* __restrict__ o0,
-                                     float* __restrict__ o1) {
+// one CTA of 8 x 2C threads; slice s adds the partial rows k = s, s+8, ... in fp64, slices combined in fixed order
+constexpr int kFinSlicesA = 8;
+__global__ void __launch_bounds__(kFinSlicesA * 2 * kMaxCA) finalize_sums_kernel(const float* __restrict__ partials, int nblocks, int C,
+                                                                                float* __restrict__ o0, float* __restrict__ o1) {
+    __shared__ double s_acc[kFinSlicesA][2 * kMaxCA];
+    const int col = threadIdx.x % (2 * kMaxCA), slice = threadIdx.x / (2 * kMaxCA);
+    if (col < 2 * C) {
+        double a = 0.0;
+        for (int k = slice; k < nblocks; k += kFinSlicesA) a += (double)partials[(size_t)k * 2 * C + col];
+        s_acc[slice][col] = a;
+    }
+    __syncthreads();
     const int c = threadIdx.x;
     if (c >= C) return;
     double a = 0.0, b = 0.0;
-    for (int k = 0; k < nblocks; ++k) { a += (double)partials[(size_t)k * 2 * C + c]; b += (double)partials[(size_t)k * 2 * C + C + c]; }
+#pragma unroll
+    for (int s = 0; s < kFinSlicesA; ++s) { a += s_acc[s][c]; b += s_acc[s][C + c]; }
     o0[c] = (float)a;
     o1[c] = (float)b;
 }
@@ -273,7 +284,7 @@ extern "C" int mvsb200_channel_sums(const void* x, int dtype, const int64_t* str
     else if (dtype == MVSB200_F32) channel_sums_kernel<float><<<grid, kThreadsA, 0, st>>>((const float*)x, v, n, C, workspace);
     else MVS_FAIL(MVSB200_E_BADARG, "channel_sums: bad dtype %d", dtype);
     MVS_CHECK_LAUNCH("channel_sums");
-    finalize_sums_kernel<<<1, kMaxCA, 0, st>>>(workspace, grid, C, s1, s2);
+    finalize_sums_kernel<<<1, kFinSlicesA * 2 * kMaxCA, 0, st>>>(workspace, grid, C, s1, s2);
     MVS_CHECK_LAUNCH("channel_sums_finalize");
     return MVSB200_OK;
 }
@@ -318,7 +329,7 @@ static int affine_bwd_impl(const void* x, const void* gy, const Geo& g, int C, c
     const int grid_out = grid_of(n_out), grid_in = grid_of(n_in);
     affine_relu_geo_bwd_reduce_kernel<T, TG><<<grid_out, kThreadsA, 0, st>>>((const T*)x, (const TG*)gy, g, n_out, C, scale, shift, relu, workspace);
     MVS_CHECK_LAUNCH("affine_relu_geo_bwd_reduce");
-    finalize_sums_kernel<<<1, kMaxCA, 0, st>>>(workspace, grid_out, C, gshift, gscale);
+    finalize_sums_kernel<<<1, kFinSlicesA * 2 * kMaxCA, 0, st>>>(workspace, grid_out, C, gshift, gscale);
     MVS_CHECK_LAUNCH("affine_relu_geo_bwd_finalize");
     affine_relu_geo_bwd_dx_kernel<T, TG><<<grid_in, kThreadsA, 0, st>>>((const T*)x, (const TG*)gy, g, n_in, C, scale, shift, relu, (T*)gx);
     MVS_CHECK_LAUNCH("affine_relu_geo_bwd_dx");

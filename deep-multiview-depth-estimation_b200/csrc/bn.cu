@@ -96,17 +96,26 @@ __global__ void __launch_bounds__(kBnThreads) bn_stats_kernel(const T* __restric
     block_reduce_to_partial(s, q, cpr, C, partials + (size_t)blockIdx.x * 2 * C);
 }
 
-// one CTA: out[0][c] = sum_a / M, out[1][c] = sum_b / M - (sum_a / M)^2   (mode 0: mean, biased variance)
-//          out[0][c] = sum_a,     out[1][c] = sum_b                        (mode 1: raw sums)
-__global__ void bn_finalize_kernel(const float* __restrict__ partials, int nblocks, int C, double inv_m, int mode,
-                                   float* __restrict__ out0, float* __restrict__ out1) {
+// one CTA of 8 x 2C threads: out[0][c] = sum_a / M, out[1][c] = sum_b / M - (sum_a / M)^2   (mode 0: mean, biased variance)
+//                            out[0][c] = sum_a,     out[1][c] = sum_b                        (mode 1: raw sums)
+// slice s of 8 adds the partial rows k = s, s+8, ... in fp64; the 8 slices are combined in fixed order (deterministic)
+constexpr int kFinSlices = 8;
+__global__ void __launch_bounds__(kFinSlices * 2 * kMaxC) bn_finalize_kernel(const float* __restrict__ partials, int nblocks, int C,
+                                                                            double inv_m, int mode, float* __restrict__ out0,
+                                                                            float* __restrict__ out1) {
+    __shared__ double s_acc[kFinSlices][2 * kMaxC];
+    const int col = threadIdx.x % (2 * kMaxC), slice = threadIdx.x / (2 * kMaxC);
+    if (col < 2 * C) {
+        double a = 0.0;
+        for (int k = slice; k < nblocks; k += kFinSlices) a += (double)partials[(size_t)k * 2 * C + col];
+        s_acc[slice][col] = a;
+    }
+    __syncthreads();
     const int c = threadIdx.x;
     if (c >= C) return;
     double a = 0.0, b = 0.0;
-    for (int k = 0; k < nblocks; ++k) {
-        a += (double)partials[(size_t)k * 2 * C + c];
-        b += (double)partials[(size_t)k * 2 * C + C + c];
-    }
+#pragma unroll
+    for (int s = 0; s < kFinSlices; ++s) { a += s_acc[s][c]; b += s_acc[s][C + c]; }
     if (mode == 0) {
         const double mean = a * inv_m;
         double var = b * inv_m - mean * mean;
@@ -223,34 +232,38 @@ struct CropBox {
 };
 
 // chunk index inside the box volume -> chunk index inside the canvas volume
+// (32-bit index arithmetic: the host checks that every chunk count is below 2^31)
 __device__ __forceinline__ long long box_to_canvas(long long i, int cpr, const CropBox& c) {
-    const int cg = (int)(i % cpr);
-    long long r = i / cpr;
-    const int x = (int)(r % c.wc); r /= c.wc;
-    const int y = (int)(r % c.hc); r /= c.hc;
-    const int d = (int)(r % c.dc);
-    const long long b = r / c.dc;
+    const unsigned iu = (unsigned)i;
+    const int cg = (int)(iu % (unsigned)cpr);
+    unsigned r = iu / (unsigned)cpr;
+    const int x = (int)(r % (unsigned)c.wc); r /= (unsigned)c.wc;
+    const int y = (int)(r % (unsigned)c.hc); r /= (unsigned)c.hc;
+    const int d = (int)(r % (unsigned)c.dc);
+    const long long b = r / (unsigned)c.dc;
     return ((((b * c.Da + d + c.d0) * c.ha + y + c.h0) * c.wa + x + c.w0)) * cpr + cg;
 }
 // chunk index inside the canvas -> chunk index inside the allocation
 __device__ __forceinline__ long long canvas_to_alloc(long long i, int cpr, const CropBox& c) {
-    const int cg = (int)(i % cpr);
-    long long r = i / cpr;
-    const int x = (int)(r % c.w); r /= c.w;
-    const int y = (int)(r % c.h); r /= c.h;
-    const int d = (int)(r % c.D);
-    const long long b = r / c.D;
+    const unsigned iu = (unsigned)i;
+    const int cg = (int)(iu % (unsigned)cpr);
+    unsigned r = iu / (unsigned)cpr;
+    const int x = (int)(r % (unsigned)c.w); r /= (unsigned)c.w;
+    const int y = (int)(r % (unsigned)c.h); r /= (unsigned)c.h;
+    const int d = (int)(r % (unsigned)c.D);
+    const long long b = r / (unsigned)c.D;
     return ((((b * c.Da + d) * c.ha + y) * c.wa + x)) * cpr + cg;
 }
 // chunk index inside the allocation -> chunk index inside the box (>= 0), -1 inside the canvas but outside the box,
 // -2 outside the canvas
 __device__ __forceinline__ long long alloc_to_box(long long i, int cpr, const CropBox& c) {
-    const int cg = (int)(i % cpr);
-    long long r = i / cpr;
-    const int xa = (int)(r % c.wa); r /= c.wa;
-    const int ya = (int)(r % c.ha); r /= c.ha;
-    const int da = (int)(r % c.Da);
-    const long long b = r / c.Da;
+    const unsigned iu = (unsigned)i;
+    const int cg = (int)(iu % (unsigned)cpr);
+    unsigned r = iu / (unsigned)cpr;
+    const int xa = (int)(r % (unsigned)c.wa); r /= (unsigned)c.wa;
+    const int ya = (int)(r % (unsigned)c.ha); r /= (unsigned)c.ha;
+    const int da = (int)(r % (unsigned)c.Da);
+    const long long b = r / (unsigned)c.Da;
     if (xa >= c.w || ya >= c.h || da >= c.D) return -2;
     const int x = xa - c.w0, y = ya - c.h0, d = da - c.d0;
     if ((unsigned)x >= (unsigned)c.wc || (unsigned)y >= (unsigned)c.hc || (unsigned)d >= (unsigned)c.dc) return -1;
@@ -398,7 +411,7 @@ extern "C" int mvsb200_bn_stats(const void* x, int dtype, int64_t M, int C, floa
     else
         bn_stats_kernel<float><<<grid, kBnThreads, 0, st>>>((const float*)x, n_chunks, C, workspace);
     MVS_CHECK_LAUNCH("bn_stats");
-    bn_finalize_kernel<<<1, kMaxC, 0, st>>>(workspace, grid, C, 1.0 / (double)M, 0, mean, var);
+    bn_finalize_kernel<<<1, kFinSlices * 2 * kMaxC, 0, st>>>(workspace, grid, C, 1.0 / (double)M, 0, mean, var);
     MVS_CHECK_LAUNCH("bn_finalize");
     return MVSB200_OK;
 }
@@ -429,7 +442,7 @@ static int bn_bwd_impl(const void* x, const void* gy, const float* scale, const 
     bn_relu_bwd_reduce_kernel<TX, TG><<<grid, kBnThreads, 0, st>>>((const TX*)x, (const TG*)gy, scale, shift, mean, invstd,
                                                                    n_chunks, C, relu, workspace);
     MVS_CHECK_LAUNCH("bn_relu_bwd_reduce");
-    bn_finalize_kernel<<<1, kMaxC, 0, st>>>(workspace, grid, C, 1.0, 1, dbeta, dgamma);
+    bn_finalize_kernel<<<1, kFinSlices * 2 * kMaxC, 0, st>>>(workspace, grid, C, 1.0, 1, dbeta, dgamma);
     MVS_CHECK_LAUNCH("bn_finalize");
     bn_relu_bwd_apply_kernel<TX, TG><<<grid, kBnThreads, 0, st>>>((const TX*)x, (const TG*)gy, scale, shift, mean, invstd,
                                                                   gamma, dbeta, dgamma, (TX*)dx, n_chunks, C, relu,
@@ -465,6 +478,7 @@ static int make_box(const int* g, int64_t M, int64_t* Bout, CropBox* cb) {
     const int64_t per = (int64_t)cb->D * cb->h * cb->w;
     MVS_REQUIRE(per > 0 && M % per == 0, "bn crop: canvas %dx%dx%d does not divide M", cb->D, cb->h, cb->w);
     MVS_REQUIRE(cb->Da >= cb->D && cb->ha >= cb->h && cb->wa >= cb->w, "bn crop: canvas larger than its allocation");
+    MVS_REQUIRE((M / per) * (int64_t)cb->Da * cb->ha * cb->wa * 8 < (1LL << 31), "bn crop: volume too large for 32-bit chunk indices");
     MVS_REQUIRE(cb->d0 >= 0 && cb->h0 >= 0 && cb->w0 >= 0 && cb->dc >= 1 && cb->hc >= 1 && cb->wc >= 1 &&
                 cb->d0 + cb->dc <= cb->D && cb->h0 + cb->hc <= cb->h && cb->w0 + cb->wc <= cb->w, "bn crop: box outside the canvas");
     *Bout = M / per;
@@ -486,7 +500,7 @@ extern "C" int mvsb200_bn_stats_geo(const void* x, int dtype, int64_t M, int C, 
     else
         bn_stats_geo_kernel<float><<<grid, kBnThreads, 0, st>>>((const float*)x, n_chunks, C, workspace, cb);
     MVS_CHECK_LAUNCH("bn_stats_geo");
-    bn_finalize_kernel<<<1, kMaxC, 0, st>>>(workspace, grid, C, 1.0 / (double)M, 0, mean, var);
+    bn_finalize_kernel<<<1, kFinSlices * 2 * kMaxC, 0, st>>>(workspace, grid, C, 1.0 / (double)M, 0, mean, var);
     MVS_CHECK_LAUNCH("bn_finalize");
     return MVSB200_OK;
 }
@@ -520,7 +534,7 @@ static int bn_bwd_crop_impl(const void* x, const void* gy, const float* scale, c
     bn_relu_bwd_reduce_crop_kernel<TX, TG><<<grid_box, kBnThreads, 0, st>>>((const TX*)x, (const TG*)gy, scale, shift, mean,
                                                                             invstd, n_box, C, relu, workspace, cb);
     MVS_CHECK_LAUNCH("bn_relu_bwd_reduce_crop");
-    bn_finalize_kernel<<<1, kMaxC, 0, st>>>(workspace, grid_box, C, 1.0, 1, dbeta, dgamma);
+    bn_finalize_kernel<<<1, kFinSlices * 2 * kMaxC, 0, st>>>(workspace, grid_box, C, 1.0, 1, dbeta, dgamma);
     MVS_CHECK_LAUNCH("bn_finalize");
     bn_relu_bwd_apply_crop_kernel<TX, TG><<<grid, kBnThreads, 0, st>>>((const TX*)x, (const TG*)gy, scale, shift, mean, invstd,
                                                                        gamma, dbeta, dgamma, (TX*)dx, n_chunks, C, relu,

@@ -1,3 +1,2 @@
-C=deep-multiview-depth-estimation_b200/csrc
-echo "8-lane minb3" > gpurun_out/micro_k1b.jsonl; MVSB200_K1_LANES=8 python tools/microbench.py --cases one --kernels fwd >> gpurun_out/micro_k1b.jsonl 2>> gpurun_out/micro.err
-echo "8-lane minb2 (110 regs)" >> gpurun_out/micro_k1b.jsonl; MVSB200_LIB=$PWD/$C/libmvs_b200_minb2.so MVSB200_K1_LANES=8 python tools/microbench.py --cases one --kernels fwd >> gpurun_out/micro_k1b.jsonl 2>> gpurun_out/micro.err
+timeout 600 python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
+timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench9.json 2> gpurun_out/bench9.err
