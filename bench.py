@@ -172,7 +172,20 @@ def run_b200(args, rank, world, local_rank):
     img_dev, gt_dev = img_host.to(dev), gt_host.to(dev)
     loss_host = torch.zeros(1).pin_memory()
 
+    slab = None
+    if args.workload == "cfg4" and world > 1:              # ONE sample across the ranks: depth-slab split
+        from mvs_b200.harness import DepthSlabMVSNet
+        K, R, T = ps.synthetic_cameras(B, V, h, w, seed=0)  # every rank works on the same scene
+        g0 = torch.Generator().manual_seed(1000)
+        img_host = torch.randn(B * V, 3, H, W, generator=g0).pin_memory()
+        gt_host = (425.0 + 480.0 * torch.rand(B, 1, h, w, generator=g0)).pin_memory()
+        img_dev, gt_dev = img_host.to(dev), gt_host.to(dev)
+        slab = DepthSlabMVSNet(model)
+
     def step(img, gt):
+        if slab is not None:
+            initial, refined = slab.forward(img, K, R, T, d_min, d_int, V)
+            return loss_fcn(gt, initial, refined)[0]
         if train:
             opt.zero_grad(set_to_none=True)
             initial, refined = model(img, K, R, T, d_min, d_int, B, V)
@@ -228,12 +241,15 @@ def run_b200(args, rank, world, local_rank):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
 
-    maps = B * world * args.steps
+    maps = B * (1 if slab is not None else world) * args.steps
     value, e2e_value = maps / (ms * 1e-3), maps / (ms_e2e * 1e-3)
 
     # per-kernel live timings -> roofline of the fused warp+variance kernel
     peak, peak_src = _peaks()
     vox = B * D * h * w
+    if slab is not None:                                   # K1 of this rank: its own planes + halo
+        k0, k1_ = slab.reg.plan(D).cost_planes(rank)
+        vox = B * (k1_ - k0) * h * w
     alg = {"warp_variance_fwd": 4 * B * V * C * h * w + 2 * vox * C,            # fp32 features in, bf16 volume out
            "warp_variance_bwd": 2 * vox * C + 2 * 4 * B * V * C * h * w,        # bf16 gcost + features in, gfeat out
            "softmax_ranks_fwd": 2 * 4 * vox + 4 * 5 * B * h * w}
@@ -271,11 +287,14 @@ def run_b200(args, rank, world, local_rank):
     line = None
     if rank == 0:
         line = {"metric": "depth maps/sec", "value": value, "unit": "depth maps/s", "n_gpus": world, "steps": args.steps,
-                "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "strong" if slab is not None else "weak",
                 "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                 "config": {"workload": wl["desc"], "per_gpu_batch": B, "views": V, "D": D, "features": [C, h, w],
                            "l2": "inputs_exceed_l2 (cost volume %.0f MB per step > 126 MB L2)" % (2 * vox * C / 1e6),
-                           "parallelism": f"dp{world} (scene/batch sharding, flat-bucket NCCL grad all-reduce)" if world > 1 else "single GPU",
+                           "parallelism": (f"depth-slab x{world} (one sample; K1 on own planes + halo, halo/box exchanges and BatchNorm-sum "
+                                           f"all-reduces over NCCL, logits re-sharded to rows for K4)" if slab is not None else
+                                           f"dp{world} (scene/batch sharding, flat-bucket NCCL grad all-reduce)" if world > 1 else "single GPU"),
                            "regulariser_convs": model.cost_volume_reg.conv_backend},
                 "e2e": {"value": e2e_value, "unit": "depth maps/s", "ms_per_step": ms_e2e / args.steps,
                         "h2d_bytes_per_step": img_host.numel() * 4 + gt_host.numel() * 4, "d2h_bytes_per_step": 4},

@@ -78,6 +78,61 @@ class MVSNet(nn.Module):
         return initial, refined
 
 
+class DepthSlabMVSNet:
+    """Inference of ONE multi-view sample across the ranks of a box (BASELINE.json configs[3]): the hot path runs on depth
+    slabs (mvs_b200.depth_slab), the out-of-scope 2D nets are replicated.  Each view is encoded by ONE rank
+    (view v on rank v mod R) and broadcast -- every rank needs all V feature maps (75.8 MB at 5 x 400x296x32) for the sweep
+    of its planes.  Wraps an MVSNet whose parameters are identical on every rank."""
+
+    def __init__(self, model: "MVSNet", comm=None):
+        from .depth_slab import DepthSlabCostVolumeReg, TorchDistComm
+        self.model = model
+        self.comm = TorchDistComm() if comm is None else comm
+        self.reg = DepthSlabCostVolumeReg(model.cost_volume_reg, self.comm)
+
+    @torch.no_grad()
+    def encode(self, nn_input, by_view=None):
+        """Feature maps of all views on every rank, [N,32,h,w] with channel-last memory.  by_view: view v is encoded on rank
+        v mod R and broadcast; exact only when the encoder's BatchNorm uses running statistics (eval mode) -- in train mode
+        (test.py:61) its batch statistics span all views, so the default then is to encode all views on every rank."""
+        m, R, r = self.model, self.comm.world, self.comm.rank
+        N, _, H, W = nn_input.shape
+        amp = m.precision == "bf16" and nn_input.is_cuda
+        if by_view is None:
+            by_view = not m.feature_encoder.training
+        if not by_view or R == 1:
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
+                return m.feature_encoder(nn_input.contiguous(memory_format=torch.channels_last)).float()
+        nhwc = torch.empty((N, H // 4, W // 4, 32), dtype=torch.float32, device=nn_input.device)
+        mine = [v for v in range(N) if v % R == r]
+        if mine:
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
+                f = m.feature_encoder(nn_input[mine].contiguous(memory_format=torch.channels_last))
+            nhwc[mine] = f.float().permute(0, 2, 3, 1)
+        for v in range(N):
+            self.comm.broadcast(nhwc[v], v % R)
+        return nhwc.permute(0, 3, 1, 2)
+
+    @torch.no_grad()
+    def forward(self, nn_input, K_batch, R_batch, T_batch, d_min, d_int, n_views):
+        from . import ops
+        from .depth_slab import slab_cost_fn
+        m = self.model
+        feats = self.encode(nn_input)
+        h, w = feats.shape[-2:]
+        sweep = ops.PlaneSweep(K_batch, R_batch, T_batch, d_min, d_int, 1, n_views, m.d_num, m.d_scale, h, w, feats.device)
+        vol_dtype = torch.bfloat16 if m.precision == "bf16" else torch.float32
+        initial, prob_rows, rows = self.reg.forward(slab_cost_fn(feats, sweep, vol_dtype), sweep.d_batch_dev, 1, m.d_num, h, w)
+        dev = initial.device
+        d_trans, d_span = d_min.to(dev), d_int.to(dev) * m.d_num * m.d_scale
+        norm = (initial - d_trans) / d_span
+        ref_img = F.interpolate(nn_input[:1], (h, w), mode="bilinear", align_corners=False)
+        amp = m.precision == "bf16" and nn_input.is_cuda
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):          # replicated: 4-channel 400x296 maps
+            refined = m.depthmap_refine(torch.cat((norm, ref_img), 1))
+        return initial, refined.float() * d_span + d_trans
+
+
 def loss_fcn(gt, initial, refined):
     """Masked L1 on both depth maps (scripts/loss.py:4-41): returns (loss, initial MAE, refined MAE)."""
     mask = (gt != 0).float()
