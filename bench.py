@@ -182,7 +182,18 @@ def run_b200(args, rank, world, local_rank):
         img_dev, gt_dev = img_host.to(dev), gt_host.to(dev)
         slab = DepthSlabMVSNet(model)
 
+    gstep = None
+    if train and not args.no_graph:
+        from mvs_b200.harness import GraphedTrainStep
+        gstep = GraphedTrainStep(model, B, V, H, W, dev)
+
     def step(img, gt):
+        if gstep is not None:                              # forward + loss + backward as one CUDA graph
+            loss = gstep.run(img, gt, K, R, T, d_min, d_int)
+            if reducer:
+                reducer.reduce()
+            opt.step()
+            return loss
         if slab is not None:
             initial, refined = slab.forward(img, K, R, T, d_min, d_int, V)
             return loss_fcn(gt, initial, refined)[0]
@@ -203,8 +214,11 @@ def run_b200(args, rank, world, local_rank):
         return step(img_dev, gt_dev)
 
     def step_e2e():
-        img = img_host.to(dev, non_blocking=True)
-        gt = gt_host.to(dev, non_blocking=True)
+        if gstep is not None:                              # pinned host -> the graph's static input buffers, one copy
+            img, gt = img_host, gt_host
+        else:
+            img = img_host.to(dev, non_blocking=True)
+            gt = gt_host.to(dev, non_blocking=True)
         loss_host.copy_(step(img, gt).reshape(1), non_blocking=True)
         torch.cuda.current_stream().synchronize()          # the user reads the loss every step
         return loss_host
@@ -226,20 +240,44 @@ def run_b200(args, rank, world, local_rank):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
+    graph_note = None
+    if gstep is not None:
+        try:
+            step_resident()
+            torch.cuda.synchronize()
+        except Exception as e:                             # capture refused: say so and measure the eager step
+            graph_note = f"capture failed, eager step measured: {type(e).__name__}: {str(e)[:200]}"
+            sys.stderr.write("bench.py: " + graph_note + "\n")
+            gstep = None
+            opt.zero_grad(set_to_none=True)
     for _ in range(max(args.warmup, 3)):
         step_resident()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ops.EVENTS = {}
+    if gstep is None:
+        ops.EVENTS = {}
     n0 = mvs_b200.launch_count()
     ms = timed(step_resident, args.steps)
-    launches = mvs_b200.launch_count() - n0
+    launches = (gstep.launches * args.steps) if gstep is not None else mvs_b200.launch_count() - n0
     events, ops.EVENTS = ops.EVENTS, None
     clocks = sampler.stop() if rank == 0 else None
     for _ in range(2):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
+    if gstep is not None:
+        # per-kernel durations cannot be bracketed inside a graph replay: the same step, issued eagerly right after the
+        # timed region with every libmvs_b200.so launch between two CUDA events on its launching stream
+        graphed, gstep = gstep, None
+        for p_ in params:
+            p_.grad = None
+        step_resident()
+        ops.EVENTS = {}
+        for _ in range(args.steps):
+            step_resident()
+        torch.cuda.synchronize()
+        events, ops.EVENTS = ops.EVENTS, None
+        gstep = graphed                                    # (reporting only from here on)
 
     maps = B * (1 if slab is not None else world) * args.steps
     value, e2e_value = maps / (ms * 1e-3), maps / (ms_e2e * 1e-3)
@@ -295,7 +333,10 @@ def run_b200(args, rank, world, local_rank):
                            "parallelism": (f"depth-slab x{world} (one sample; K1 on own planes + halo, halo/box exchanges and BatchNorm-sum "
                                            f"all-reduces over NCCL, logits re-sharded to rows for K4)" if slab is not None else
                                            f"dp{world} (scene/batch sharding, flat-bucket NCCL grad all-reduce)" if world > 1 else "single GPU"),
-                           "regulariser_convs": model.cost_volume_reg.conv_backend},
+                           "regulariser_convs": model.cost_volume_reg.conv_backend,
+                           "cuda_graph": (f"forward+loss+backward replayed as one CUDA graph ({gstep.launches} libmvs_b200.so "
+                                          f"launches per replay); per-kernel timings from {args.steps} eager steps run right "
+                                          f"after the timed region") if gstep is not None else (graph_note or "off")},
                 "e2e": {"value": e2e_value, "unit": "depth maps/s", "ms_per_step": ms_e2e / args.steps,
                         "h2d_bytes_per_step": img_host.numel() * 4 + gt_host.numel() * 4, "d2h_bytes_per_step": 4},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "roofline_k1": roofline_k1, "kernels": kern,
@@ -327,6 +368,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="issue the train step eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))

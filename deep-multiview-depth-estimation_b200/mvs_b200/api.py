@@ -12,7 +12,7 @@ from .handle import WarpedFeatureVolumes
 
 
 def homography_warping(K_batch, R_batch, T_batch, d_min, d_int, feature_maps, batch_size, n_views, d_num,
-                       d_scale, bug_compatible=True):
+                       d_scale, bug_compatible=True, sweep=None):
     """scripts/homography.py:6-92.  Returns (warped handle, d_batch_0 [B,D,1,1] on the feature device,
     ref_idx_0 [B] CPU int64)."""
     if feature_maps.dim() != 4:
@@ -20,8 +20,9 @@ def homography_warping(K_batch, R_batch, T_batch, d_min, d_int, feature_maps, ba
     n, _, h, w = feature_maps.shape
     if n != batch_size * n_views:
         raise ValueError(f"feature_maps has {n} maps, expected batch_size*n_views = {batch_size * n_views}")
-    sweep = ops.PlaneSweep(K_batch, R_batch, T_batch, d_min, d_int, batch_size, n_views, int(d_num), d_scale,
-                           h, w, feature_maps.device, bug_compatible)
+    if sweep is None:                                      # else: geometry already resident (ops.PlaneSweep.update)
+        sweep = ops.PlaneSweep(K_batch, R_batch, T_batch, d_min, d_int, batch_size, n_views, int(d_num), d_scale,
+                               h, w, feature_maps.device, bug_compatible)
     return WarpedFeatureVolumes(feature_maps, sweep), sweep.d_batch_dev, torch.arange(0, n, n_views)
 
 

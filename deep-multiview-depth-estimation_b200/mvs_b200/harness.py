@@ -55,13 +55,15 @@ class MVSNet(nn.Module):
         self.cost_volume_reg = CostVolumeReg(precision=precision, conv_backend=conv_backend, n_depth_est=n_depth_est)
         self.depthmap_refine = DepthRefinement()
 
-    def forward(self, nn_input, K_batch, R_batch, T_batch, d_min, d_int, batch_size, n_views):
+    def forward(self, nn_input, K_batch, R_batch, T_batch, d_min, d_int, batch_size, n_views, sweep=None):
+        """sweep: an ops.PlaneSweep already holding this batch's geometry on the device (PlaneSweep.update); the cameras are
+        then not touched here and d_min / d_int should be device tensors -- the form a captured CUDA graph replays."""
         amp = self.precision == "bf16" and nn_input.is_cuda
         with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):        # out-of-scope 2D net: stock torch AMP
             feats = self.feature_encoder(nn_input.contiguous(memory_format=torch.channels_last))
         feats = feats.float()
         warped, d_batch, ref_views = api.homography_warping(K_batch, R_batch, T_batch, d_min, d_int, feats,
-                                                            batch_size, n_views, self.d_num, self.d_scale)
+                                                            batch_size, n_views, self.d_num, self.d_scale, sweep=sweep)
         vol_dtype = torch.bfloat16 if self.precision == "bf16" else torch.float32
         cost = api.assemble_cost_volume(warped, n_views, vol_dtype)
         prob = self.cost_volume_reg(cost)
@@ -71,11 +73,75 @@ class MVSNet(nn.Module):
         d_span = d_int.to(dev) * self.d_num * self.d_scale
         norm = (initial - d_trans) / d_span
         h, w = initial.shape[-2:]
-        ref_img = F.interpolate(nn_input[ref_views.to(dev)], (h, w), mode="bilinear", align_corners=False)
+        ref_img = F.interpolate(nn_input[::n_views], (h, w), mode="bilinear", align_corners=False)   # == nn_input[ref_views]
         with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
             refined = self.depthmap_refine(torch.cat((norm, ref_img), 1))
         refined = refined.float() * d_span + d_trans
         return initial, refined
+
+
+class GraphedTrainStep:
+    """One MVSNet training step (train.py:93-108: forward, loss, backward) captured as ONE CUDA graph: the step is ~800
+    kernel launches of a few microseconds to a few hundred, which eager PyTorch cannot issue fast enough to keep a B200
+    busy.  Static device buffers hold the step's inputs (images, ground truth, sweep geometry); `run` copies the new
+    batch into them (asynchronously, from pinned host memory or device tensors), replays the graph and leaves the
+    gradients in the parameters' .grad; the gradient all-reduce (N > 1) and the optimiser step stay outside the graph.
+    Shapes are fixed per instance, as in the reference's loaders (fixed resolution, batch and view count)."""
+
+    def __init__(self, model: "MVSNet", batch_size, n_views, H, W, device, warmup=3):
+        from . import ops, _lib
+        self.model, self.B, self.V = model, batch_size, n_views
+        h, w = H // 4, W // 4
+        self.img = torch.zeros(batch_size * n_views, 3, H, W, device=device)
+        self.gt = torch.ones(batch_size, 1, h, w, device=device)
+        self.d_min = torch.zeros(batch_size, 1, 1, 1, device=device)
+        self.d_int = torch.ones(batch_size, 1, 1, 1, device=device)
+        self.sweep = None
+        self.dims = (h, w)
+        self.graph, self.loss, self.launches = None, None, 0
+        self.warmup, self._lib = warmup, _lib
+        self.params = [p for p in model.parameters() if p.requires_grad]
+
+    def _load(self, img, gt, K, R, T, d_min, d_int):
+        from . import ops
+        if self.sweep is None:
+            self.sweep = ops.PlaneSweep(K, R, T, d_min, d_int, self.B, self.V, self.model.d_num, self.model.d_scale,
+                                        self.dims[0], self.dims[1], self.img.device)
+        else:
+            self.sweep.update(K, R, T, d_min, d_int)
+        self.img.copy_(img, non_blocking=True)
+        self.gt.copy_(gt, non_blocking=True)
+        self.d_min.copy_(d_min, non_blocking=True)
+        self.d_int.copy_(d_int, non_blocking=True)
+
+    def _fwd_bwd(self):
+        initial, refined = self.model(self.img, None, None, None, self.d_min, self.d_int, self.B, self.V, sweep=self.sweep)
+        loss, _, _ = loss_fcn(self.gt, initial, refined)
+        loss.backward()
+        return loss.detach()
+
+    def run(self, img, gt, K, R, T, d_min, d_int):
+        """-> loss (device scalar, valid after the current stream reaches this point); gradients in .grad."""
+        self._load(img, gt, K, R, T, d_min, d_int)
+        if self.graph is None:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):                  # warm-up off the capture: lazy workspaces, cuDNN plans, autotune
+                for _ in range(self.warmup):
+                    for p in self.params:
+                        p.grad = None
+                    self._fwd_bwd()
+            torch.cuda.current_stream().wait_stream(side)
+            for p in self.params:
+                p.grad = None
+            n0 = self._lib.launch_count()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.loss = self._fwd_bwd()
+            self.launches = self._lib.launch_count() - n0   # libmvs_b200.so launches recorded in the graph
+            self.graph = g
+        self.graph.replay()
+        return self.loss
 
 
 class DepthSlabMVSNet:

@@ -113,12 +113,35 @@ class PlaneSweep:
     def __init__(self, K, R, T, d_min, d_int, batch_size, n_views, d_num, d_scale, h, w, device,
                  bug_compatible=True):
         self.B, self.V, self.D, self.h, self.w = batch_size, n_views, d_num, h, w
+        self.d_scale, self.bug_compatible = d_scale, bug_compatible
         self.d_batch_0 = geometry.depth_table(d_min, d_int, d_num, d_scale)            # CPU [B,D,1,1]
         params, tinv = geometry.view_tables(K, R, T, self.d_batch_0, batch_size, n_views, h, w, bug_compatible)
         packed = torch.from_numpy(params).pin_memory() if torch.cuda.is_available() else torch.from_numpy(params)
         self.view_params = packed.to(device, non_blocking=True)
         self.tinv = torch.from_numpy(tinv).to(device)
         self.d_batch_dev = self.d_batch_0.to(device)
+        self._stage = None
+
+    def update(self, K, R, T, d_min, d_int):
+        """New cameras / depth range into the SAME device buffers (static addresses: the sweep of a captured CUDA graph is
+        re-targeted by this call; one pinned staging buffer, three asynchronous copies on the current stream)."""
+        self.d_batch_0 = geometry.depth_table(d_min, d_int, self.D, self.d_scale)
+        params, tinv = geometry.view_tables(K, R, T, self.d_batch_0, self.B, self.V, self.h, self.w, self.bug_compatible)
+        n1, n2, n3 = params.size, tinv.size, self.d_batch_0.numel()
+        if self._stage is None:
+            self._stage = torch.empty(n1 + n2 + n3, dtype=torch.float32).pin_memory()
+            self._stage_free = torch.cuda.Event()
+        else:
+            self._stage_free.synchronize()                 # the previous update's copies have left the staging buffer
+        st = self._stage
+        st[:n1].copy_(torch.from_numpy(params).reshape(-1))
+        st[n1:n1 + n2].copy_(torch.from_numpy(tinv).reshape(-1))
+        st[n1 + n2:].copy_(self.d_batch_0.reshape(-1))
+        self.view_params.view(-1).copy_(st[:n1], non_blocking=True)
+        self.tinv.view(-1).copy_(st[n1:n1 + n2], non_blocking=True)
+        self.d_batch_dev.view(-1).copy_(st[n1 + n2:], non_blocking=True)
+        self._stage_free.record()
+        return self
 
 
 def warp_variance(feat: torch.Tensor, sweep: PlaneSweep, out_dtype=torch.float32) -> torch.Tensor:

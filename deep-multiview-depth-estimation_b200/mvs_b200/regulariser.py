@@ -234,20 +234,32 @@ class CostVolumeReg(nn.Module):
             return ops.conv_out(z, self.conv_out.weight)              # K3c: 8 -> 1 is streaming work, not a GEMM
         return be.conv3d(z, self._w("conv_out", dt), 1, (1, 1, 1)).float()
 
-    @staticmethod
-    def _outside_classes(Wf, bg, dims, E_lo, E_hi, B):
+    _GEO = {}
+
+    @classmethod
+    def _outside_geometry(cls, dims, E_lo, E_hi, B, dev):
+        """([3,3] tap-valid mask per edge class, [3,3,3] voxel counts of the 27 border classes outside the box E), built once
+        per geometry and device: forward then performs no host-to-device copy (CUDA-graph capturable)."""
+        key = (tuple(dims), tuple(E_lo), tuple(E_hi), int(B), str(dev))
+        hit = cls._GEO.get(key)
+        if hit is None:
+            M = torch.tensor([[0., 1., 1.], [1., 1., 1.], [1., 1., 0.]], device=dev)   # [edge class][tap valid]
+            full = [torch.tensor([1., n - 2., 1.], device=dev) for n in dims]
+            inside = []
+            for ax, n in enumerate(dims):
+                lo_edge = 1.0 if E_lo[ax] == 0 else 0.0
+                hi_edge = 1.0 if E_hi[ax] == n - 1 else 0.0
+                inside.append(torch.tensor([lo_edge, (E_hi[ax] - E_lo[ax] + 1) - lo_edge - hi_edge, hi_edge], device=dev))
+            cnt = B * (torch.einsum("a,b,c->abc", *full) - torch.einsum("a,b,c->abc", *inside))
+            hit = cls._GEO[key] = (M, cnt)
+        return hit
+
+    @classmethod
+    def _outside_classes(cls, Wf, bg, dims, E_lo, E_hi, B):
         """Values and voxel counts of the 27 border classes of a stride-1, pad-1 conv output outside the box E when its
         input is the per-channel constant `bg` there: ([Cout,3,3,3] values, [3,3,3] counts)."""
-        dev = Wf.device
-        M = torch.tensor([[0., 1., 1.], [1., 1., 1.], [1., 1., 0.]], device=dev)       # [edge class][tap valid]
+        M, cnt = cls._outside_geometry(dims, E_lo, E_hi, B, Wf.device)
         val = torch.einsum("oidhw,ad,bh,cw,i->oabc", Wf, M, M, M, bg)                   # [Cout,3,3,3]
-        full = [torch.tensor([1., n - 2., 1.], device=dev) for n in dims]
-        inside = []
-        for ax, n in enumerate(dims):
-            lo_edge = 1.0 if E_lo[ax] == 0 else 0.0
-            hi_edge = 1.0 if E_hi[ax] == n - 1 else 0.0
-            inside.append(torch.tensor([lo_edge, (E_hi[ax] - E_lo[ax] + 1) - lo_edge - hi_edge, hi_edge], device=dev))
-        cnt = B * (torch.einsum("a,b,c->abc", *full) - torch.einsum("a,b,c->abc", *inside))
         return val, cnt
 
     @classmethod
