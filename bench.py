@@ -25,6 +25,8 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "deep-multiview-depth-estimation_b200"))
 
+TC_KERNELS = ("conv3d_s1_tc", "deconv3d_s2_tc", "conv3d_s2_tc", "conv3d_s1_wgrad_tc")     # tcgen05 convolution kernels
+
 WORKLOADS = {
     "cfg2": dict(B=4, V=3, H=512, W=640, D=192, train=True,
                  desc="MVSNet train step bf16, batch 4/GPU, 3 views, 640x512, D=192 (BASELINE.json configs[1])"),
@@ -284,6 +286,7 @@ def run_b200(args, rank, world, local_rank):
 
     # per-kernel live timings -> roofline of the fused warp+variance kernel
     peak, peak_src = _peaks()
+    tpeak, tpeak_src = _tensor_peak()
     vox = B * D * h * w
     if slab is not None:                                   # K1 of this rank: its own planes + halo
         k0, k1_ = slab.reg.plan(D).cost_planes(rank)
@@ -300,7 +303,7 @@ def run_b200(args, rank, world, local_rank):
             kern[name].update({"alg_bytes": alg[name], "GBps": alg[name] / (t * 1e-3) / 1e9,
                                "frac_hbm": alg[name] / (t * 1e-3) / 1e9 / peak})
         work = [w for _, _, w in evs if w is not None]
-        if work and name in ("conv3d_s1_tc", "conv3d_s2_tc", "conv3d_s1_wgrad_tc"):
+        if work and name in TC_KERNELS:
             kern[name].update({"alg_flops_per_step": sum(work) / args.steps, "TFLOPs": sum(work) / (tot * 1e-3) / 1e12})
     k1 = kern.get("warp_variance_fwd", {})
     roofline_k1 = {"kernel": "warp_variance_fwd_kernel<V=3, bf16 volume>", "bound": "hbm", "achieved": k1.get("GBps"),
@@ -311,10 +314,13 @@ def run_b200(args, rank, world, local_rank):
                            "written of 511 MB); fp32-volume variant reaches 44 % of peak (tools/microbench.py)"}
     # dominant own kernel by time in the step: the tcgen05 convolution (all its launches of the timed steps together)
     k3 = kern.get("conv3d_s1_tc", {})
-    tpeak, tpeak_src = _tensor_peak()
+    tc_ms = sum(kern[n]["ms_per_step"] for n in TC_KERNELS if n in kern and "alg_flops_per_step" in kern[n])
+    tc_fl = sum(kern[n]["alg_flops_per_step"] for n in TC_KERNELS if n in kern and "alg_flops_per_step" in kern[n])
     roofline = {"kernel": "conv3d_s1_tc_kernel<CIN,NOUT> (tcgen05/TMEM/TMA implicit-GEMM conv3d; %d calls/step: forward and data "
-                          "gradient of conv_0_0, conv_{1,2,3}_1, and the transposed convs' forward as 8 parity-class launches each)"
-                          % (k3.get("launches", 0) // max(args.steps, 1)),
+                          "gradient of conv_0_0 and conv_{1,2,3}_1)" % (k3.get("launches", 0) // max(args.steps, 1)),
+                "all_tcgen05_convs": {"kernels": [n for n in TC_KERNELS if n in kern], "ms_per_step": tc_ms,
+                                      "alg_flops_per_step": tc_fl, "TFLOPs": tc_fl / (tc_ms * 1e-3) / 1e12 if tc_ms else None,
+                                      "frac": tc_fl / (tc_ms * 1e-3) / 1e12 / tpeak if tc_ms else None},
                 "bound": "tensor", "achieved": k3.get("TFLOPs"), "peak": tpeak, "peak_source": tpeak_src, "unit": "TFLOP/s",
                 "frac": (k3["TFLOPs"] / tpeak) if k3.get("TFLOPs") else None,
                 "traffic": _ncu_traffic("r01_k3_conv3d_s1_tc_ncu.json"),

@@ -1113,6 +1113,656 @@ int launch_conv_s2(const void* x, const void* w, void* y, int B, int Dx, int Hx,
     return MVSB200_OK;
 }
 
+
+// =================================================================================================================
+// Stride-1 convolution with the DEPTH TAP FOLDED INTO N ("kdn" form).  conv3d_s1_tc_kernel above issues 27 MMAs of N = Cout
+// per 128 voxel rows and K step; at N = 16..32 each of them re-reads its 128-row A operand from shared memory for very few
+// columns, and the kernel sits on the shared-memory operand-feed roof (profiles/r01_k3_notes.md).  Here the three depth
+// taps of a filter become three column blocks of ONE MMA: for an input plane s,
+//     Q_s[v, (kd, co)] = sum_{kh,kw,ci} x_s[v + (kh,kw)][ci] * W[kd,kh,kw][ci][co]          (9 MMAs of N = 3 Cout per K step)
+// and an output plane is the sum of three such partial planes, out_d = Q_d[kd=0] + Q_{d+1}[kd=1] + Q_{d+2}[kd=2], which the
+// epilogue thread that owns the voxel row keeps as two running partial sums in registers while the CTA marches along depth
+// (the row of a voxel is the same TMEM lane in every plane: no cross-lane traffic).  A operand reads drop 3x, every slab is
+// consumed by exactly one MMA batch (the ring only has to cover the TMA latency), the flops per shared-memory byte of an MMA
+// rise 2.1x at Cin = Cout = 32.
+struct KdnParams {
+    ConvParams c;
+    int slots;                      // slab ring depth (2 or 3)
+};
+
+template <int CIN, int NOUT, int MB>
+__global__ void __launch_bounds__(kTcThreads, 1)
+conv3d_s1_kdn_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
+                     const __grid_constant__ KdnParams kp) {
+    const ConvParams& p = kp.c;
+    constexpr int ROWB = CIN * 2;
+    constexpr int KSTEPS = CIN / 16;
+    constexpr int N3 = 3 * NOUT;
+    constexpr int W_TAP_BYTES = NOUT * ROWB;
+    constexpr int W_BYTES = 27 * W_TAP_BYTES;
+    constexpr int W_BYTES_AL = (W_BYTES + 1023) / 1024 * 1024;
+    constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N3 >> 3) << 17) | ((128u >> 4) << 24);
+    constexpr uint32_t TMEM_COLS = 2 * MB * N3 <= 256 ? 256 : 512;
+    static_assert(2 * MB * N3 <= 512 && N3 % 16 == 0 && N3 <= 256, "accumulator columns");
+    constexpr int kMaxSlots = 3;
+
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
+    unsigned char* w_smem = smem;
+    unsigned char* slab_smem = smem + W_BYTES_AL;
+    const int slots = kp.slots;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(slab_smem + (size_t)slots * p.slab_bytes);
+    uint64_t* full = bars;                  // [kMaxSlots]
+    uint64_t* empty = bars + kMaxSlots;     // [kMaxSlots]
+    uint64_t* wfull = bars + 2 * kMaxSlots;
+    uint64_t* tfull = wfull + 1;            // [2]
+    uint64_t* tempty = tfull + 2;           // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles = p.tiles_x * p.tiles_y;
+
+    if (threadIdx.x == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_x) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_w) : "memory");
+        for (int i = 0; i < kMaxSlots; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
+        mbar_init(wfull, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(tfull + i, 1); mbar_init(tempty + i, 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    auto decode = [&](int item, int& b, int& d_begin, int& nd, int& x0, int& y0) {
+        const int t = item % tiles, r = item / tiles;
+        const int c = r % p.nchunks;
+        b = r / p.nchunks;
+        d_begin = c * p.dchunk;
+        nd = min(p.dchunk, p.Do - d_begin);
+        x0 = (t % p.tiles_x) * (p.BW - 2);
+        y0 = (t / p.tiles_x) * p.L;
+    };
+
+    if (warp == 0) {
+        // ===================================== TMA producer =====================================
+        if (elect_one()) {
+            mbar_expect_tx(wfull, 27u * W_TAP_BYTES);
+            // packed as [(kh,kw)][kd][n_rows][Cin]: the three depth taps of an in-plane tap are consecutive row blocks
+            for (int t = 0; t < 27; ++t) tma_load_2d(w_smem + t * W_TAP_BYTES, &tm_w, wfull, 0, t * p.n_rows + p.w_row0);
+        }
+        __syncwarp();
+        const uint32_t box_bytes = (uint32_t)ROWB * p.BW * (p.L + 2);
+        int gs = 0;
+        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+            int b, d_begin, nd, x0, y0;
+            decode(item, b, d_begin, nd, x0, y0);
+            for (int s = 0; s < nd + 2; ++s, ++gs) {
+                const int slot = gs % slots;
+                if (gs >= slots) mbar_wait(empty + slot, ((gs / slots) - 1) & 1);
+                if (elect_one()) {
+                    mbar_expect_tx(full + slot, box_bytes);
+                    tma_load_5d(slab_smem + (size_t)slot * p.slab_bytes, &tm_x, full + slot, 0, x0 + p.off_w, y0 + p.off_h,
+                                d_begin + p.off_d + s, b);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================== MMA issuer =======================================
+        mbar_wait(wfull, 0);
+        const uint64_t d0 = umma_desc<ROWB>(0);
+        const uint32_t desc_hi = (uint32_t)(d0 >> 32);
+        const uint32_t w_lo = (uint32_t)d0 | (smem_u32(w_smem) >> 4);
+        const uint32_t slab_lo = (uint32_t)d0 | (smem_u32(slab_smem) >> 4);
+        const uint32_t bw16 = (uint32_t)(p.BW * ROWB) >> 4, slab16 = (uint32_t)p.slab_bytes >> 4;
+        int gs = 0;                                      // slabs processed (all items): ring slot, TMEM stage and phases
+        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+            int b, d_begin, nd, x0, y0;
+            decode(item, b, d_begin, nd, x0, y0);
+            for (int s = 0; s < nd + 2; ++s, ++gs) {
+                const int stage = gs & 1, slot = gs % slots;
+                if (gs >= 2) mbar_wait(tempty + stage, ((gs >> 1) - 1) & 1);
+                mbar_wait(full + slot, (gs / slots) & 1);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t slot_lo = slab_lo + (uint32_t)slot * slab16;
+#pragma unroll
+                    for (int mb = 0; mb < MB; ++mb) {
+                        const uint32_t d_tmem = tmem_base + (uint32_t)((stage * MB + mb) * N3);
+                        const uint32_t mb16 = (uint32_t)(mb * 128 * ROWB) >> 4;
+                        uint32_t acc = 0;
+#pragma unroll
+                        for (int kh = 0; kh < 3; ++kh) {
+                            const uint32_t row_lo = slot_lo + mb16 + kh * bw16;
+#pragma unroll
+                            for (int kw = 0; kw < 3; ++kw) {
+#pragma unroll
+                                for (int k = 0; k < KSTEPS; ++k) {
+                                    umma_bf16_lohi(d_tmem, row_lo + (uint32_t)((kw * ROWB + k * 32) >> 4), desc_hi,
+                                                   w_lo + (uint32_t)(((kh * 3 + kw) * 3 * W_TAP_BYTES + k * 32) >> 4), desc_hi, IDESC, acc);
+                                    acc = 1;
+                                }
+                            }
+                        }
+                    }
+                    umma_commit(empty + slot);           // this slab is read by this batch only
+                    umma_commit(tfull + stage);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ===================================== epilogue =========================================
+        const int q = warp & 3;
+        int ti[MB], tj[MB];
+        bool in_tile[MB];
+#pragma unroll
+        for (int mb = 0; mb < MB; ++mb) {
+            const int m = mb * 128 + q * 32 + lane;
+            tj[mb] = m / p.BW; ti[mb] = m - tj[mb] * p.BW;
+            in_tile[mb] = ti[mb] < p.BW - 2 && tj[mb] < p.L;
+        }
+        float P1[MB][NOUT], P2[MB][NOUT];                // partial sums of output planes s and s-1 (this thread's voxel rows)
+        int gs = 0;
+        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+            int b, d_begin, nd, x0, y0;
+            decode(item, b, d_begin, nd, x0, y0);
+            for (int s = 0; s < nd + 2; ++s, ++gs) {
+                const int stage = gs & 1;
+                mbar_wait(tfull + stage, (gs >> 1) & 1);
+                tc_fence_after();
+                const bool store = s >= 2;               // output plane s - 2 is complete with this slab's kd = 2 block
+                __nv_bfloat16* plane0 = p.y + (long long)b * p.y_sb + (long long)(d_begin + s - 2) * p.y_sd + (long long)y0 * p.y_sh +
+                                        (long long)x0 * p.y_sw + p.y_coff;
+#pragma unroll
+                for (int mb = 0; mb < MB; ++mb) {
+                    const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((stage * MB + mb) * N3);
+                    const bool ok = store && in_tile[mb] && x0 + ti[mb] < p.Wo && y0 + tj[mb] < p.Ho;
+                    __nv_bfloat16* row = plane0 + (long long)tj[mb] * p.y_sh + (long long)ti[mb] * p.y_sw;
+#pragma unroll
+                    for (int c0 = 0; c0 < NOUT; c0 += 16) {
+                        uint32_t v2[16], v1[16], v0[16];
+                        tmem_ld<16>(t0 + (uint32_t)(2 * NOUT + c0), v2);
+                        tmem_ld<16>(t0 + (uint32_t)(NOUT + c0), v1);
+                        tmem_ld<16>(t0 + (uint32_t)c0, v0);
+                        tmem_ld_wait();
+                        float o[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            o[i] = P2[mb][c0 + i] + __uint_as_float(v2[i]);
+                            P2[mb][c0 + i] = P1[mb][c0 + i] + __uint_as_float(v1[i]);
+                            P1[mb][c0 + i] = __uint_as_float(v0[i]);
+                        }
+                        if (ok) {
+#pragma unroll
+                            for (int i = 0; i < 16; i += 8) {
+                                if (c0 + i < p.cout) {
+                                    const uint4 u = make_uint4(pack_bf16x2(o[i], o[i + 1]), pack_bf16x2(o[i + 2], o[i + 3]),
+                                                               pack_bf16x2(o[i + 4], o[i + 5]), pack_bf16x2(o[i + 6], o[i + 7]));
+                                    *reinterpret_cast<uint4*>(row + c0 + i) = u;
+                                }
+                            }
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty + stage);
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+TilePlan plan_tiles_mb(int Ho, int Wo, int rowb, size_t w_bytes_al, size_t smem_budget, int MB);
+
+template <int CIN, int NOUT, int MB>
+int launch_conv_kdn_mb(const void* x, const void* w, void* y, int B, int Di, int Hi, int Wi, int Do, int Ho, int Wo, int cout,
+                       int y_cs, int y_coff, int n_rows, int w_row0, int off_d, int off_h, int off_w, const TilePlan& tp, int slots,
+                       cudaStream_t st) {
+    constexpr int ROWB = CIN * 2;
+    constexpr size_t W_BYTES_AL = ((size_t)27 * NOUT * ROWB + 1023) / 1024 * 1024;
+    EncodeTiledFn enc = encode_fn();
+    MVS_REQUIRE(enc != nullptr, "conv3d_s1_kdn: cuTensorMapEncodeTiled is not available from the driver");
+    CUtensorMap tm_x, tm_w;
+    {
+        const cuuint64_t dims[5] = {(cuuint64_t)CIN, (cuuint64_t)Wi, (cuuint64_t)Hi, (cuuint64_t)Di, (cuuint64_t)B};
+        const cuuint64_t strides[4] = {(cuuint64_t)ROWB, (cuuint64_t)ROWB * Wi, (cuuint64_t)ROWB * Wi * Hi,
+                                       (cuuint64_t)ROWB * Wi * Hi * Di};
+        const cuuint32_t box[5] = {(cuuint32_t)CIN, (cuuint32_t)tp.BW, (cuuint32_t)(tp.L + 2), 1, 1};
+        const cuuint32_t es[5] = {1, 1, 1, 1, 1};
+        CUresult r = enc(&tm_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), dims, strides, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(ROWB), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        MVS_REQUIRE(r == CUDA_SUCCESS, "conv3d_s1_kdn: cuTensorMapEncodeTiled(x) failed (%d)", (int)r);
+    }
+    {
+        const cuuint64_t dims[2] = {(cuuint64_t)CIN, (cuuint64_t)27 * n_rows};
+        const cuuint64_t strides[1] = {(cuuint64_t)ROWB};
+        const cuuint32_t box[2] = {(cuuint32_t)CIN, (cuuint32_t)NOUT};
+        const cuuint32_t es[2] = {1, 1};
+        CUresult r = enc(&tm_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims, strides, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(ROWB), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        MVS_REQUIRE(r == CUDA_SUCCESS, "conv3d_s1_kdn: cuTensorMapEncodeTiled(w) failed (%d)", (int)r);
+    }
+    KdnParams kp;
+    ConvParams& p = kp.c;
+    p.B = B; p.Do = Do; p.Ho = Ho; p.Wo = Wo;
+    p.off_d = off_d; p.off_h = off_h; p.off_w = off_w;
+    p.BW = tp.BW; p.L = tp.L; p.MB = MB; p.tiles_x = tp.tiles_x; p.tiles_y = tp.tiles_y;
+    p.cout = cout; p.y_cs = y_cs; p.y_coff = y_coff; p.n_rows = n_rows; p.w_row0 = w_row0;
+    p.slab_bytes = tp.slab_bytes;
+    p.tap_mask = 0x7ffffffu;
+    p.y_sw = y_cs; p.y_sh = (long long)Wo * y_cs; p.y_sd = (long long)Ho * Wo * y_cs; p.y_sb = (long long)Do * Ho * Wo * y_cs;
+    p.y = reinterpret_cast<__nv_bfloat16*>(y);
+    kp.slots = slots;
+    const long tiles = (long)tp.tiles_x * tp.tiles_y;
+    int sms = 148;
+    {
+        int dev = 0, n = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) sms = n;
+    }
+    long best_cost = -1;
+    int best_chunks = 1;
+    for (int nc = 1; nc <= Do; ++nc) {
+        const int dc = (Do + nc - 1) / nc;
+        if ((long)(nc - 1) * dc >= Do) continue;
+        const long items = tiles * nc * B;
+        const long cost = ((items + sms - 1) / sms) * (dc + 3);      // nd + 2 slabs per run + pipeline fill
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_chunks = nc; }
+    }
+    p.nchunks = best_chunks;
+    p.dchunk = (Do + best_chunks - 1) / best_chunks;
+    p.n_items = (int)(tiles * p.nchunks * B);
+    const dim3 grid((unsigned)(p.n_items < sms ? p.n_items : sms), 1, 1);
+    const size_t smem = 1024 + W_BYTES_AL + (size_t)slots * tp.slab_bytes + 256;
+    MVS_CUDA(cudaFuncSetAttribute(conv3d_s1_kdn_kernel<CIN, NOUT, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conv3d_s1_kdn_kernel<CIN, NOUT, MB><<<grid, kTcThreads, smem, st>>>(tm_x, tm_w, kp);
+    MVS_CHECK_LAUNCH("conv3d_s1_kdn");
+    return MVSB200_OK;
+}
+
+template <int CIN, int NOUT>
+int launch_conv_kdn(const void* x, const void* w, void* y, int B, int Di, int Hi, int Wi, int Do, int Ho, int Wo, int cout,
+                    int y_cs, int y_coff, int n_rows, int w_row0, int off_d, int off_h, int off_w, cudaStream_t st) {
+    constexpr int ROWB = CIN * 2;
+    constexpr size_t W_BYTES_AL = ((size_t)27 * NOUT * ROWB + 1023) / 1024 * 1024;
+    constexpr int MBMAX = 512 / (2 * 3 * NOUT) >= 4 ? 4 : (512 / (2 * 3 * NOUT) >= 2 ? 2 : 1);
+    const size_t smem_budget = 227 * 1024 - 1024;
+    // slab geometry: the largest block count that fits, with a 3-deep ring if shared memory allows, else 2-deep
+    TilePlan best{};
+    best.score = -1.0;
+    int best_slots = 0;
+    for (int MB = MBMAX; MB >= 1; MB /= 2) {
+        for (int slots = 3; slots >= 2; --slots) {
+            // plan_tiles_mb budgets kSlots3 slabs: hand it the budget scaled to `slots`
+            TilePlan tp{};
+            tp.score = -1.0;
+            for (int BW = 6; BW <= 256; BW += 2) {
+                const int L = (MB * 128) / BW;
+                if (L < 1 || L + 2 > 256) continue;
+                const int rows = MB * 128 + 2 * BW + 2;
+                const int slab = ((rows * ROWB) + 1023) / 1024 * 1024;
+                if (W_BYTES_AL + (size_t)slots * slab + 256 > smem_budget) continue;
+                const int tiles_x = (Wo + BW - 3) / (BW - 2), tiles_y = (Ho + L - 1) / L;
+                const double mma_eff = (double)Wo * Ho / ((double)tiles_x * tiles_y * MB * 128);
+                const double load_eff = (double)Wo * Ho / ((double)tiles_x * tiles_y * (L + 2) * BW);
+                const double score = mma_eff * (0.5 + 0.5 * load_eff);
+                if (score > tp.score) tp = TilePlan{BW, L, MB, tiles_x, tiles_y, slab, score};
+            }
+            if (tp.score > best.score * 1.02 || (best_slots == 0 && tp.score > 0)) { best = tp; best_slots = slots; }
+            if (tp.score > 0) break;                      // a 3-deep ring fits for this MB: do not consider 2
+        }
+    }
+    MVS_REQUIRE(best.score > 0, "conv3d_s1_kdn: no slab geometry fits shared memory (Cin=%d, N=%d)", CIN, NOUT);
+#define MVS_KDN(M) return launch_conv_kdn_mb<CIN, NOUT, M>(x, w, y, B, Di, Hi, Wi, Do, Ho, Wo, cout, y_cs, y_coff, n_rows, w_row0, off_d, off_h, off_w, best, best_slots, st)
+    if (best.MB == 1) MVS_KDN(1);
+    if constexpr (MBMAX >= 2) { if (best.MB == 2) MVS_KDN(2); }
+    if constexpr (MBMAX >= 4) { if (best.MB == 4) MVS_KDN(4); }
+#undef MVS_KDN
+    MVS_FAIL(MVSB200_E_UNSUPPORTED, "conv3d_s1_kdn: block count %d", best.MB);
+}
+
+// =================================================================================================================
+// Stride-2 TRANSPOSED convolution (ConvTranspose3d k=3, scripts/model.py:229-234, used at :115-121) in ONE launch.
+//   out[2J + par] = sum over the filter taps k with (par + pad - k) even of W[k] . in[J + (par + pad - k)/2]   (per axis)
+// i.e. each of the 8 output-parity classes is a stride-1 convolution of the INPUT lattice with a sub-set of the taps, and
+// the 8 sub-sets together are exactly the 27 taps.  The forward kernel above, launched once per class, writes every class
+// as a stride-2 sub-lattice of the canvas (64-byte pieces 128 bytes apart, each line visited by 8 launches).  Here a CTA
+// marches along the input depth once, keeps EIGHT accumulator blocks (one per class) per stage in TMEM, issues each of
+// the 27 taps into the block of its class, and the epilogue interleaves the classes so that a thread writes the two
+// w-parities of a voxel pair back to back: full, contiguous lines of the canvas, each written once.
+struct DeconvParams {
+    int B, Do, Ho, Wo;              // extent of the canvas that is written (voxels beyond it are dropped)
+    int Jd, Jh, Jw;                 // output lattice (voxel octets): ceil(extent / 2)
+    int BW, L, MB;
+    int tiles_x, tiles_y;
+    int dchunk, nchunks, n_items;
+    int cout, n_rows;
+    int slab_bytes;
+    int n_taps;                     // 27
+    int tap_class[27], tap_td[27], tap_th[27], tap_tw[27], tap_k[27];   // ordered by class
+    long long y_sb, y_sd, y_sh, y_sw;   // canvas voxel-row strides in elements
+    __nv_bfloat16* y;
+};
+
+template <int CIN, int NOUT>
+__global__ void __launch_bounds__(kTcThreads, 1)
+deconv3d_s2_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
+                      const __grid_constant__ DeconvParams p) {
+    constexpr int ROWB = CIN * 2;
+    constexpr int KSTEPS = CIN / 16;
+    constexpr int W_TAP_BYTES = NOUT * ROWB;
+    constexpr int W_BYTES = 27 * W_TAP_BYTES;
+    constexpr int W_BYTES_AL = (W_BYTES + 1023) / 1024 * 1024;
+    constexpr int MB = 512 / (16 * NOUT);               // 2 stages x 8 classes x MB x NOUT columns == 512
+    constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NOUT >> 3) << 17) | ((128u >> 4) << 24);
+    static_assert(MB >= 1 && MB <= 2, "accumulator blocks per class");
+
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
+    unsigned char* w_smem = smem;
+    unsigned char* slab_smem = smem + W_BYTES_AL;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(slab_smem + (size_t)kSlots3 * p.slab_bytes);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + kSlots3;
+    uint64_t* wfull = bars + 2 * kSlots3;
+    uint64_t* tfull = wfull + 1;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles = p.tiles_x * p.tiles_y;
+    constexpr uint32_t tmem_cols = 512;
+
+    if (threadIdx.x == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_x) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_w) : "memory");
+        for (int i = 0; i < kSlots3; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
+        mbar_init(wfull, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(tfull + i, 1); mbar_init(tempty + i, 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    auto decode = [&](int item, int& b, int& d_begin, int& nd, int& x0, int& y0) {
+        const int t = item % tiles, r = item / tiles;
+        const int c = r % p.nchunks;
+        b = r / p.nchunks;
+        d_begin = c * p.dchunk;
+        nd = min(p.dchunk, p.Jd - d_begin);
+        x0 = (t % p.tiles_x) * (p.BW - 2);
+        y0 = (t / p.tiles_x) * p.L;
+    };
+
+    if (warp == 0) {
+        // ===================================== TMA producer =====================================
+        if (elect_one()) {
+            mbar_expect_tx(wfull, 27u * W_TAP_BYTES);
+            for (int tap = 0; tap < 27; ++tap) tma_load_2d(w_smem + tap * W_TAP_BYTES, &tm_w, wfull, 0, tap * p.n_rows);
+        }
+        __syncwarp();
+        const uint32_t box_bytes = (uint32_t)ROWB * p.BW * (p.L + 2);
+        int gs = 0;
+        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+            int b, d_begin, nd, x0, y0;
+            decode(item, b, d_begin, nd, x0, y0);
+            for (int s = 0; s < nd + 2; ++s, ++gs) {     // input planes d_begin - 1 + s
+                const int slot = gs % kSlots3;
+                if (gs >= kSlots3) mbar_wait(empty + slot, ((gs / kSlots3) - 1) & 1);
+                if (elect_one()) {
+                    mbar_expect_tx(full + slot, box_bytes);
+                    tma_load_5d(slab_smem + (size_t)slot * p.slab_bytes, &tm_x, full + slot, 0, x0 - 1, y0 - 1, d_begin - 1 + s, b);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================== MMA issuer =======================================
+        mbar_wait(wfull, 0);
+        const uint64_t d0 = umma_desc<ROWB>(0);
+        const uint32_t desc_hi = (uint32_t)(d0 >> 32);
+        const uint32_t w_lo = (uint32_t)d0 | (smem_u32(w_smem) >> 4);
+        const uint32_t slab_lo = (uint32_t)d0 | (smem_u32(slab_smem) >> 4);
+        const uint32_t bw16 = (uint32_t)(p.BW * ROWB) >> 4, slab16 = (uint32_t)p.slab_bytes >> 4;
+        int gs0 = 0, gp = 0, landed = 0;
+        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+            int b, d_begin, nd, x0, y0;
+            decode(item, b, d_begin, nd, x0, y0);
+            for (int d = 0; d < nd; ++d, ++gp) {
+                const int stage = gp & 1;
+                if (gp >= 2) mbar_wait(tempty + stage, ((gp >> 1) - 1) & 1);
+                while (landed <= gs0 + d + 2) { mbar_wait(full + landed % kSlots3, (landed / kSlots3) & 1); ++landed; }
+                tc_fence_after();
+                if (elect_one()) {
+                    uint32_t slot_lo[3];
+#pragma unroll
+                    for (int kd = 0; kd < 3; ++kd) slot_lo[kd] = slab_lo + (uint32_t)((gs0 + d + kd) % kSlots3) * slab16;
+#pragma unroll
+                    for (int mb = 0; mb < MB; ++mb) {
+                        const uint32_t mb16 = (uint32_t)(mb * 128 * ROWB) >> 4;
+                        int prev_class = -1;
+                        for (int e = 0; e < 27; ++e) {
+                            const int c = p.tap_class[e], td = p.tap_td[e];
+                            const uint32_t a_lo = (td == 0 ? slot_lo[0] : (td == 1 ? slot_lo[1] : slot_lo[2])) + mb16 +
+                                                  (uint32_t)p.tap_th[e] * bw16 + (uint32_t)((p.tap_tw[e] * ROWB) >> 4);
+                            const uint32_t b_lo = w_lo + (uint32_t)((p.tap_k[e] * W_TAP_BYTES) >> 4);
+                            const uint32_t d_tmem = tmem_base + (uint32_t)(((stage * 8 + c) * MB + mb) * NOUT);
+                            uint32_t acc = c == prev_class ? 1u : 0u;
+                            prev_class = c;
+#pragma unroll
+                            for (int k = 0; k < KSTEPS; ++k) {
+                                umma_bf16_lohi(d_tmem, a_lo + (uint32_t)((k * 32) >> 4), desc_hi, b_lo + (uint32_t)((k * 32) >> 4), desc_hi,
+                                               IDESC, acc);
+                                acc = 1;
+                            }
+                        }
+                    }
+                    umma_commit(empty + (gs0 + d) % kSlots3);
+                    if (d == nd - 1) {
+                        umma_commit(empty + (gs0 + nd) % kSlots3);
+                        umma_commit(empty + (gs0 + nd + 1) % kSlots3);
+                    }
+                    umma_commit(tfull + stage);
+                }
+                __syncwarp();
+            }
+            gs0 += nd + 2;
+        }
+    } else {
+        // ===================================== epilogue =========================================
+        const int q = warp & 3;
+        int ti[MB], tj[MB];
+        bool in_tile[MB];
+#pragma unroll
+        for (int mb = 0; mb < MB; ++mb) {
+            const int m = mb * 128 + q * 32 + lane;
+            tj[mb] = m / p.BW; ti[mb] = m - tj[mb] * p.BW;
+            in_tile[mb] = ti[mb] < p.BW - 2 && tj[mb] < p.L;
+        }
+        int gp = 0;
+        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+            int b, d_begin, nd, x0, y0;
+            decode(item, b, d_begin, nd, x0, y0);
+            for (int d = 0; d < nd; ++d, ++gp) {
+                const int stage = gp & 1;
+                mbar_wait(tfull + stage, (gp >> 1) & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int mb = 0; mb < MB; ++mb) {
+                    const int ox = 2 * (x0 + ti[mb]), oy = 2 * (y0 + tj[mb]), oz = 2 * (d_begin + d);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        uint32_t v[NOUT];
+                        tmem_ld<NOUT>(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(((stage * 8 + c) * MB + mb) * NOUT), v);
+                        tmem_ld_wait();
+                        const int z = oz + (c >> 2), yy = oy + (c >> 1 & 1), xx = ox + (c & 1);
+                        if (in_tile[mb] && z < p.Do && yy < p.Ho && xx < p.Wo) {
+                            __nv_bfloat16* row = p.y + (long long)b * p.y_sb + (long long)z * p.y_sd + (long long)yy * p.y_sh + (long long)xx * p.y_sw;
+#pragma unroll
+                            for (int ch = 0; ch < NOUT; ch += 8) {
+                                if (ch < p.cout) {
+                                    const uint4 o = make_uint4(pack_bf16x2(__uint_as_float(v[ch]), __uint_as_float(v[ch + 1])),
+                                                               pack_bf16x2(__uint_as_float(v[ch + 2]), __uint_as_float(v[ch + 3])),
+                                                               pack_bf16x2(__uint_as_float(v[ch + 4]), __uint_as_float(v[ch + 5])),
+                                                               pack_bf16x2(__uint_as_float(v[ch + 6]), __uint_as_float(v[ch + 7])));
+                                    *reinterpret_cast<uint4*>(row + ch) = o;
+                                }
+                            }
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty + stage);
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+    }
+}
+
+// slab geometry for a fixed number of 128-row blocks
+TilePlan plan_tiles_mb(int Ho, int Wo, int rowb, size_t w_bytes_al, size_t smem_budget, int MB) {
+    TilePlan best{};
+    best.score = -1.0;
+    for (int BW = 6; BW <= 256; BW += 2) {
+        const int L = (MB * 128) / BW;
+        if (L < 1 || L + 2 > 256) continue;
+        const int rows = MB * 128 + 2 * BW + 2;
+        const int slab = ((rows * rowb) + 1023) / 1024 * 1024;
+        if (w_bytes_al + (size_t)kSlots3 * slab + 256 > smem_budget) continue;
+        const int tiles_x = (Wo + BW - 3) / (BW - 2), tiles_y = (Ho + L - 1) / L;
+        const double mma_eff = (double)Wo * Ho / ((double)tiles_x * tiles_y * MB * 128);
+        const double load_eff = (double)Wo * Ho / ((double)tiles_x * tiles_y * (L + 2) * BW);
+        const double score = mma_eff * (0.5 + 0.5 * load_eff);
+        if (score > best.score) best = TilePlan{BW, L, MB, tiles_x, tiles_y, slab, score};
+    }
+    return best;
+}
+
+template <int CIN, int NOUT>
+int launch_deconv_s2(const void* x, const void* w, void* y, int B, int Di, int Hi, int Wi, int Do, int Ho, int Wo, int cout,
+                     int n_rows, int pad_d, int pad_h, int pad_w, const long long* y_strides4, cudaStream_t st) {
+    constexpr int ROWB = CIN * 2;
+    constexpr int MB = 512 / (16 * NOUT);
+    constexpr size_t W_BYTES_AL = ((size_t)27 * NOUT * ROWB + 1023) / 1024 * 1024;
+    EncodeTiledFn enc = encode_fn();
+    MVS_REQUIRE(enc != nullptr, "deconv3d_s2: cuTensorMapEncodeTiled is not available from the driver");
+    const size_t smem_budget = 227 * 1024 - 1024;
+    const int Jd = (Do + 1) / 2, Jh = (Ho + 1) / 2, Jw = (Wo + 1) / 2;
+    const TilePlan tp = plan_tiles_mb(Jh, Jw, ROWB, W_BYTES_AL, smem_budget, MB);
+    MVS_REQUIRE(tp.score > 0, "deconv3d_s2: no slab geometry fits shared memory (Cin=%d, N=%d)", CIN, NOUT);
+
+    CUtensorMap tm_x, tm_w;
+    {
+        const cuuint64_t dims[5] = {(cuuint64_t)CIN, (cuuint64_t)Wi, (cuuint64_t)Hi, (cuuint64_t)Di, (cuuint64_t)B};
+        const cuuint64_t strides[4] = {(cuuint64_t)ROWB, (cuuint64_t)ROWB * Wi, (cuuint64_t)ROWB * Wi * Hi,
+                                       (cuuint64_t)ROWB * Wi * Hi * Di};
+        const cuuint32_t box[5] = {(cuuint32_t)CIN, (cuuint32_t)tp.BW, (cuuint32_t)(tp.L + 2), 1, 1};
+        const cuuint32_t es[5] = {1, 1, 1, 1, 1};
+        CUresult r = enc(&tm_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), dims, strides, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(ROWB), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        MVS_REQUIRE(r == CUDA_SUCCESS, "deconv3d_s2: cuTensorMapEncodeTiled(x) failed (%d)", (int)r);
+    }
+    {
+        const cuuint64_t dims[2] = {(cuuint64_t)CIN, (cuuint64_t)27 * n_rows};
+        const cuuint64_t strides[1] = {(cuuint64_t)ROWB};
+        const cuuint32_t box[2] = {(cuuint32_t)CIN, (cuuint32_t)NOUT};
+        const cuuint32_t es[2] = {1, 1};
+        CUresult r = enc(&tm_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims, strides, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(ROWB), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        MVS_REQUIRE(r == CUDA_SUCCESS, "deconv3d_s2: cuTensorMapEncodeTiled(w) failed (%d)", (int)r);
+    }
+
+    DeconvParams p;
+    p.B = B; p.Do = Do; p.Ho = Ho; p.Wo = Wo; p.Jd = Jd; p.Jh = Jh; p.Jw = Jw;
+    p.BW = tp.BW; p.L = tp.L; p.MB = MB; p.tiles_x = tp.tiles_x; p.tiles_y = tp.tiles_y;
+    p.cout = cout; p.n_rows = n_rows; p.slab_bytes = tp.slab_bytes;
+    // taps ordered by output-parity class; slab tap t = (par + pad - k)/2 + 1 per axis (input index J + t - 1)
+    const int pads[3] = {pad_d, pad_h, pad_w};
+    int n = 0;
+    for (int c = 0; c < 8; ++c) {
+        const int par[3] = {c >> 2 & 1, c >> 1 & 1, c & 1};
+        for (int kd = 0; kd < 3; ++kd)
+            for (int kh = 0; kh < 3; ++kh)
+                for (int kw = 0; kw < 3; ++kw) {
+                    const int k[3] = {kd, kh, kw};
+                    int t[3];
+                    bool ok = true;
+                    for (int ax = 0; ax < 3; ++ax) {
+                        const int v = par[ax] + pads[ax] - k[ax];
+                        if (v & 1) { ok = false; break; }
+                        t[ax] = v / 2 + 1;
+                        if (t[ax] < 0 || t[ax] > 2) { ok = false; break; }
+                    }
+                    if (!ok) continue;
+                    MVS_REQUIRE(n < 27, "deconv3d_s2: tap table overflow");
+                    p.tap_class[n] = c; p.tap_td[n] = t[0]; p.tap_th[n] = t[1]; p.tap_tw[n] = t[2];
+                    p.tap_k[n] = (kd * 3 + kh) * 3 + kw;
+                    ++n;
+                }
+    }
+    MVS_REQUIRE(n == 27, "deconv3d_s2: padding (%d,%d,%d) does not map all 27 taps into the 3-tap window", pad_d, pad_h, pad_w);
+    p.n_taps = n;
+    p.y_sb = y_strides4[0]; p.y_sd = y_strides4[1]; p.y_sh = y_strides4[2]; p.y_sw = y_strides4[3];
+    p.y = reinterpret_cast<__nv_bfloat16*>(y);
+
+    const long tiles = (long)tp.tiles_x * tp.tiles_y;
+    int sms = 148;
+    {
+        int dev = 0, nsm = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && nsm > 0) sms = nsm;
+    }
+    long best_cost = -1;
+    int best_chunks = 1;
+    for (int nc = 1; nc <= Jd; ++nc) {
+        const int dc = (Jd + nc - 1) / nc;
+        if ((long)(nc - 1) * dc >= Jd) continue;
+        const long items = tiles * nc * B;
+        const long cost = ((items + sms - 1) / sms) * (dc + 4);
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_chunks = nc; }
+    }
+    p.nchunks = best_chunks;
+    p.dchunk = (Jd + best_chunks - 1) / best_chunks;
+    p.n_items = (int)(tiles * p.nchunks * B);
+    const dim3 grid((unsigned)(p.n_items < sms ? p.n_items : sms), 1, 1);
+    const size_t smem = 1024 + W_BYTES_AL + (size_t)kSlots3 * tp.slab_bytes + 256;
+    MVS_CUDA(cudaFuncSetAttribute(deconv3d_s2_tc_kernel<CIN, NOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    deconv3d_s2_tc_kernel<CIN, NOUT><<<grid, kTcThreads, smem, st>>>(tm_x, tm_w, p);
+    MVS_CHECK_LAUNCH("deconv3d_s2_tc");
+    return MVSB200_OK;
+}
+
 }  // namespace
 
 static int conv3d_s1_dispatch(const void* x, const void* w_packed, void* y, int B, int Di, int Hi, int Wi, int Cin, int Do, int Ho,
@@ -1224,6 +1874,62 @@ extern "C" int mvsb200_conv3d_s2_fwd(const void* x, const void* w_packed, void* 
 #undef MVS_S2
         if (rc != MVSB200_OK) return rc;
         row0 += nout;
+    }
+    return MVSB200_OK;
+}
+
+extern "C" int mvsb200_deconv3d_s2_fwd(const void* x, const void* w_packed, void* y, int B, int Di, int Hi, int Wi, int Cin,
+                                       int Do, int Ho, int Wo, int cout, int n_rows, int pad_d, int pad_h, int pad_w,
+                                       const int64_t* y_strides4, void* stream) {
+    MVS_REQUIRE(x && w_packed && y && y_strides4, "deconv3d_s2_fwd: null pointer");
+    MVS_REQUIRE(aligned16(x) && aligned16(w_packed) && aligned16(y), "deconv3d_s2_fwd: pointers must be 16-byte aligned");
+    MVS_REQUIRE(B >= 1 && B <= 65535 && Di >= 1 && Hi >= 1 && Wi >= 1 && Do >= 1 && Ho >= 1 && Wo >= 1, "deconv3d_s2_fwd: bad shape");
+    MVS_REQUIRE(cout >= 8 && cout % 8 == 0 && cout <= n_rows && (n_rows == 16 || n_rows == 32),
+                "deconv3d_s2_fwd: cout must be a multiple of 8 and n_rows 16 or 32 (cout=%d n_rows=%d)", cout, n_rows);
+    MVS_REQUIRE(pad_d >= 1 && pad_d <= 2 && pad_h >= 1 && pad_h <= 2 && pad_w >= 1 && pad_w <= 2, "deconv3d_s2_fwd: pad must be 1 or 2 per axis");
+    const long long ys[4] = {(long long)y_strides4[0], (long long)y_strides4[1], (long long)y_strides4[2], (long long)y_strides4[3]};
+    for (int i = 0; i < 4; ++i) MVS_REQUIRE(ys[i] % 8 == 0, "deconv3d_s2_fwd: output strides must be multiples of 8 elements");
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = MVSB200_E_UNSUPPORTED;
+#define MVS_DC(CI, NO) rc = launch_deconv_s2<CI, NO>(x, w_packed, y, B, Di, Hi, Wi, Do, Ho, Wo, cout, n_rows, pad_d, pad_h, pad_w, ys, st)
+    if (Cin == 16 && n_rows == 16) MVS_DC(16, 16);
+    else if (Cin == 16 && n_rows == 32) MVS_DC(16, 32);
+    else if (Cin == 32 && n_rows == 16) MVS_DC(32, 16);
+    else if (Cin == 32 && n_rows == 32) MVS_DC(32, 32);
+    else if (Cin == 64 && n_rows == 16) MVS_DC(64, 16);
+    else if (Cin == 64 && n_rows == 32) MVS_DC(64, 32);
+    else MVS_FAIL(MVSB200_E_UNSUPPORTED, "deconv3d_s2_fwd: unsupported channels Cin=%d n_rows=%d", Cin, n_rows);
+#undef MVS_DC
+    return rc;
+}
+
+/* Same convolution as mvsb200_conv3d_s1_fwd with the depth tap folded into the MMA N extent (conv3d_s1_kdn_kernel).
+ * w_packed: [9 (kh,kw)][3 (kd)][n_rows][Cin] bf16. */
+extern "C" int mvsb200_conv3d_s1_fwd_kdn(const void* x, const void* w_packed, void* y, int B, int Di, int Hi, int Wi, int Cin,
+                                         int Do, int Ho, int Wo, int cout, int y_cs, int n_rows, int off_d, int off_h, int off_w,
+                                         void* stream) {
+    const char* name = "conv3d_s1_fwd_kdn";
+    MVS_REQUIRE(x && w_packed && y, "%s: null pointer", name);
+    MVS_REQUIRE(aligned16(x) && aligned16(w_packed) && aligned16(y), "%s: pointers must be 16-byte aligned", name);
+    MVS_REQUIRE(B >= 1 && B <= 65535 && Di >= 1 && Hi >= 1 && Wi >= 1 && Do >= 1 && Ho >= 1 && Wo >= 1, "%s: bad shape", name);
+    MVS_REQUIRE(cout >= 8 && cout % 8 == 0 && cout <= n_rows && n_rows % 16 == 0 && n_rows <= 64,
+                "%s: cout must be a multiple of 8 and n_rows a multiple of 16 <= 64 (cout=%d n_rows=%d)", name, cout, n_rows);
+    MVS_REQUIRE(y_cs >= cout && y_cs % 8 == 0, "%s: output channel stride %d", name, y_cs);
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int row0 = 0; row0 < n_rows && row0 < cout; row0 += 32) {
+        const int nout = n_rows - row0 < 32 ? n_rows - row0 : 32;
+        const int c_here = cout - row0 < nout ? cout - row0 : nout;
+        int rc = MVSB200_E_UNSUPPORTED;
+#define MVS_CONV(CI, NO) rc = launch_conv_kdn<CI, NO>(x, w_packed, y, B, Di, Hi, Wi, Do, Ho, Wo, c_here, y_cs, row0, n_rows, row0, off_d, off_h, off_w, st)
+        if (Cin == 16 && nout == 16) MVS_CONV(16, 16);
+        else if (Cin == 16 && nout == 32) MVS_CONV(16, 32);
+        else if (Cin == 32 && nout == 16) MVS_CONV(32, 16);
+        else if (Cin == 32 && nout == 32) MVS_CONV(32, 32);
+        else if (Cin == 64 && nout == 16) MVS_CONV(64, 16);
+        else if (Cin == 64 && nout == 32) MVS_CONV(64, 32);
+        else MVS_FAIL(MVSB200_E_UNSUPPORTED, "%s: unsupported channels Cin=%d n_rows=%d", name, Cin, n_rows);
+#undef MVS_CONV
+        if (rc != MVSB200_OK) return rc;
     }
     return MVSB200_OK;
 }

@@ -32,8 +32,10 @@ _SIGNATURES = {
     "mvsb200_variance_views_fwd": (_I, [_P, _P, _I, _I, _c.c_int64, _P]),
     "mvsb200_variance_views_bwd": (_I, [_P, _P, _P, _I, _I, _c.c_int64, _P]),
     "mvsb200_conv3d_s1_fwd": (_I, [_P, _P, _P] + [_I] * 14 + [_P]),
+    "mvsb200_conv3d_s1_fwd_kdn": (_I, [_P, _P, _P] + [_I] * 14 + [_P]),
     "mvsb200_conv3d_s1_fwd_ex": (_I, [_P, _P, _P] + [_I] * 13 + [_c.c_uint, _P, _P]),
     "mvsb200_conv3d_s2_fwd": (_I, [_P, _P, _P] + [_I] * 14 + [_P]),
+    "mvsb200_deconv3d_s2_fwd": (_I, [_P, _P, _P] + [_I] * 13 + [_P, _P]),
     "mvsb200_conv3d_s1_wgrad": (_I, [_P, _P, _P] + [_I] * 12 + [_P]),
     "mvsb200_conv_out_workspace_floats": (_c.c_int64, []),
     "mvsb200_conv_out_fwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),

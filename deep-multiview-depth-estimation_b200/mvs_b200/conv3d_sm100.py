@@ -39,10 +39,26 @@ def _supported(cin, cout):
     return cin in _CIN_OK and cout % 8 == 0 and 8 <= cout <= 64
 
 
+def _S1_FORM():
+    """"kdn" (default): conv3d_s1_kdn_kernel, depth tap folded into N; "taps": conv3d_s1_tc_kernel, one MMA per tap
+    (MVSB200_CONV_S1 selects; kept for A/B measurements and as the form the parity-class kernels derive from)."""
+    import os
+    form = os.environ.get("MVSB200_CONV_S1", "kdn")
+    return form if form == "taps" or hasattr(_lib.load(), "mvsb200_conv3d_s1_fwd_kdn") else "taps"
+
+
 def _launch(x_cl, wp, cout, out_dims, off):
     B, cin, Di, Hi, Wi = x_cl.shape
     Do, Ho, Wo = out_dims
     y = torch.empty((B, cout, Do, Ho, Wo), dtype=torch.bfloat16, device=x_cl.device, memory_format=torch.channels_last_3d)
+    if _S1_FORM() == "kdn":
+        # depth tap folded into the MMA N extent: filter as [(kh,kw)][kd][rows][Cin]
+        n_rows = wp.shape[1]
+        wk = wp.view(3, 3, 3, n_rows, cin).permute(1, 2, 0, 3, 4).contiguous()
+        with _timed("conv3d_s1_tc", 2.0 * 27 * cin * cout * B * Do * Ho * Wo):
+            _lib.call("mvsb200_conv3d_s1_fwd_kdn", x_cl.data_ptr(), wk.data_ptr(), y.data_ptr(), B, Di, Hi, Wi, cin, Do, Ho, Wo,
+                      cout, cout, n_rows, off, off, off, _stream())
+        return y
     with _timed("conv3d_s1_tc", 2.0 * 27 * cin * cout * B * Do * Ho * Wo):
         _lib.call("mvsb200_conv3d_s1_fwd", x_cl.data_ptr(), wp.data_ptr(), y.data_ptr(), B, Di, Hi, Wi, cin, Do, Ho, Wo,
                   cout, cout, wp.shape[1], off, off, off, _stream())
@@ -135,29 +151,39 @@ def _deconv_class_tables(pads, device):
 
 def conv_transpose3d_s2(x, w, pads, out_dims):
     """ConvTranspose3d(k=3, stride=2, padding=pads, bias=False) from the box volume x [B,Cin,md,mh,mw] to the first
-    `out_dims` voxels per axis of its output, on the tcgen05 kernel: one launch per output-parity class, each writing its
-    stride-2 sub-lattice of the canvas.  w: [Cin, Cout, 3, 3, 3] (model.py:229-234)."""
+    `out_dims` voxels per axis of its output, on the tcgen05 kernels.  One launch (deconv3d_s2_tc_kernel: the 8
+    output-parity classes side by side in TMEM, every canvas line written once); MVSB200_DECONV=classes selects the
+    earlier form, one launch of the stride-1 kernel per class.  w: [Cin, Cout, 3, 3, 3] (model.py:229-234)."""
     import ctypes
+    import os
     x_cl = x.detach().contiguous(memory_format=torch.channels_last_3d)
     B, cin, md, mh, mw = x_cl.shape
     cout = w.shape[1]
     D, h, wd = out_dims
     n_rows = _n_rows(cout)
-    idx, masks = _deconv_class_tables(pads, x.device)
     wk = w.detach().permute(2, 3, 4, 1, 0).reshape(27, cout, cin)                 # [k][co][ci]
-    wz = torch.cat([wk, wk.new_zeros(1, cout, cin)], 0)
-    wp = torch.zeros(8, 27, n_rows, cin, dtype=torch.bfloat16, device=x.device)
-    wp[:, :, :cout] = wz[idx].to(torch.bfloat16)
     y = torch.empty((B, cout, D, h, wd), dtype=torch.bfloat16, device=x.device, memory_format=torch.channels_last_3d)
     sB, sD, sH, sW = y.stride(0), y.stride(2), y.stride(3), y.stride(4)
-    ys = (ctypes.c_int64 * 4)(sB, 2 * sD, 2 * sH, 2 * sW)
+    _, masks = _deconv_class_tables(pads, x.device)
     work = 0.0
     for c in range(8):
         pd_, ph_, pw_ = c >> 2 & 1, c >> 1 & 1, c & 1
         Jd, Jh, Jw = (D - pd_ + 1) // 2, (h - ph_ + 1) // 2, (wd - pw_ + 1) // 2
-        if min(Jd, Jh, Jw) <= 0:
-            continue
-        work += 2.0 * bin(masks[c]).count("1") * cin * cout * B * Jd * Jh * Jw
+        if min(Jd, Jh, Jw) > 0:
+            work += 2.0 * bin(masks[c]).count("1") * cin * cout * B * Jd * Jh * Jw
+    if n_rows <= 32 and os.environ.get("MVSB200_DECONV", "fused") != "classes" and hasattr(_lib.load(), "mvsb200_deconv3d_s2_fwd"):
+        wp = torch.zeros(27, n_rows, cin, dtype=torch.bfloat16, device=x.device)
+        wp[:, :cout] = wk.to(torch.bfloat16)
+        ys = (ctypes.c_int64 * 4)(sB, sD, sH, sW)
+        with _timed("deconv3d_s2_tc", work):
+            _lib.call("mvsb200_deconv3d_s2_fwd", x_cl.data_ptr(), wp.data_ptr(), y.data_ptr(), B, md, mh, mw, cin, D, h, wd, cout,
+                      n_rows, int(pads[0]), int(pads[1]), int(pads[2]), ys, _stream())
+        return y
+    idx, masks = _deconv_class_tables(pads, x.device)
+    wz = torch.cat([wk, wk.new_zeros(1, cout, cin)], 0)
+    wp = torch.zeros(8, 27, n_rows, cin, dtype=torch.bfloat16, device=x.device)
+    wp[:, :, :cout] = wz[idx].to(torch.bfloat16)
+    ys = (ctypes.c_int64 * 4)(sB, 2 * sD, 2 * sH, 2 * sW)
     with _timed("conv3d_s1_tc", work):
         for c in range(8):
             pd_, ph_, pw_ = c >> 2 & 1, c >> 1 & 1, c & 1

@@ -128,6 +128,13 @@ int mvsb200_conv3d_s1_fwd(const void* x, const void* w_packed, void* y, int B, i
                           int Do, int Ho, int Wo, int cout, int y_cs, int n_rows, int off_d, int off_h, int off_w,
                           void* stream);
 
+/* The same convolution with the depth tap folded into the MMA N extent (one MMA of N = 3*Cout per in-plane tap and K step,
+ * running partial sums of the three contributing input planes in the epilogue's registers): 3x fewer A-operand reads from
+ * shared memory.  w_packed: [9 (kh,kw)][3 (kd)][n_rows][Cin] bf16; everything else as mvsb200_conv3d_s1_fwd. */
+int mvsb200_conv3d_s1_fwd_kdn(const void* x, const void* w_packed, void* y, int B, int Di, int Hi, int Wi, int Cin,
+                              int Do, int Ho, int Wo, int cout, int y_cs, int n_rows, int off_d, int off_h, int off_w,
+                              void* stream);
+
 /* Same kernel with a subset of the 27 taps (bit (kd*3+kh)*3+kw of tap_mask) and a strided output: the voxel row of
  * output (b,z,y,x) starts at y + b*ys[0] + z*ys[1] + y*ys[2] + x*ys[3] elements (y_strides4: HOST int64).  This is one
  * output-parity class of a stride-2 TRANSPOSED convolution (ConvTranspose3d, scripts/model.py:229-234, used at :115-121):
@@ -135,6 +142,16 @@ int mvsb200_conv3d_s1_fwd(const void* x, const void* w_packed, void* y, int B, i
 int mvsb200_conv3d_s1_fwd_ex(const void* x, const void* w_packed, void* y, int B, int Di, int Hi, int Wi, int Cin,
                              int Do, int Ho, int Wo, int cout, int n_rows, int off_d, int off_h, int off_w,
                              unsigned tap_mask, const int64_t* y_strides4_host, void* stream);
+
+/* Stride-2 TRANSPOSED convolution forward in ONE launch (ConvTranspose3d k=3, scripts/model.py:229-234, used at :115-121):
+ *   out[2J + par] = sum over the taps k with (par + pad - k) even of W[k] . in[J + (par + pad - k)/2] per axis.
+ * All 8 output-parity classes are accumulated side by side in TMEM and written interleaved, so every line of the canvas is
+ * written once, contiguously.  x: [B, Di, Hi, Wi, Cin] bf16 (the central box); w_packed: [27, n_rows, Cin] bf16 with tap k
+ * = (kd,kh,kw) of the transposed-conv weight, rows = output channels (n_rows 16 or 32); y: voxel row of output (b,z,y,x) at
+ * y + b*ys[0] + z*ys[1] + y*ys[2] + x*ys[3] elements (HOST int64), written for z < Do, y < Ho, x < Wo; pad in {1,2}. */
+int mvsb200_deconv3d_s2_fwd(const void* x, const void* w_packed, void* y, int B, int Di, int Hi, int Wi, int Cin,
+                            int Do, int Ho, int Wo, int cout, int n_rows, int pad_d, int pad_h, int pad_w,
+                            const int64_t* y_strides4_host, void* stream);
 
 /* Stride-2 convolution forward on tcgen05 (parity-deinterleaved sub-lattice slabs through TMA): the three stride-2
  * branches conv_{1,2,3}_0 (scripts/model.py:104-110; padding dim/2+1 of scripts/config.py:20 reduces on the central

@@ -27,8 +27,11 @@ def _rel(a, b):
     return float((a.float() - b.float()).abs().max() / b.float().abs().max())
 
 
-@pytest.fixture(autouse=True)
-def _no_tf32():
+@pytest.fixture(autouse=True, params=["kdn", "taps"])
+def _no_tf32_both_s1_forms(request, monkeypatch):
+    """Every test runs with both forms of the stride-1 kernel: "kdn" (depth tap folded into the MMA N extent, the default)
+    and "taps" (one MMA per tap)."""
+    monkeypatch.setenv("MVSB200_CONV_S1", request.param)
     old = torch.backends.cudnn.allow_tf32
     torch.backends.cudnn.allow_tf32 = False
     yield
@@ -115,12 +118,15 @@ def test_conv_out_forward_and_gradients(shape):
     assert torch.equal(y, y2)
 
 
+@pytest.mark.parametrize("form", ["fused", "classes"])
 @pytest.mark.parametrize("cin,cout", [(64, 32), (32, 16), (16, 8)])
-@pytest.mark.parametrize("dims", [(12, 10, 14), (11, 9, 15), (8, 7, 12), (6, 33, 47)])
-def test_transposed_conv_by_parity_classes(cin, cout, dims):
-    """Stride-2 ConvTranspose3d (model.py:229-234) from the central box to the canvas: 8 parity-class launches of the
-    tcgen05 kernel vs torch's conv_transpose3d (fp32) on the same bf16 operands, forward and both gradients."""
+@pytest.mark.parametrize("dims", [(12, 10, 14), (11, 9, 15), (8, 7, 12), (6, 33, 47), (20, 70, 38)])
+def test_transposed_conv_by_parity_classes(cin, cout, dims, form, monkeypatch):
+    """Stride-2 ConvTranspose3d (model.py:229-234) from the central box to the canvas on the tcgen05 kernels -- "fused": one
+    launch with the 8 output-parity classes side by side in TMEM, "classes": 8 launches of the stride-1 kernel -- vs torch's
+    conv_transpose3d (fp32) on the same bf16 operands, forward and both gradients; the two forms agree to one bf16 rounding."""
     from mvs_b200.regulariser import central_region
+    monkeypatch.setenv("MVSB200_DECONV", form)
     reg = [central_region(n) for n in dims]
     m = [hi - lo + 1 for lo, hi, _ in reg]
     pads = tuple(L for _, _, L in reg)                     # left padding of the equivalent small transposed conv
@@ -131,7 +137,11 @@ def test_transposed_conv_by_parity_classes(cin, cout, dims):
     x1, w1 = x.clone().requires_grad_(True), wt.clone().requires_grad_(True)
     n0 = mvs_b200.launch_count()
     y = be.conv_transpose3d(x1, w1, 2, pads, dims)
-    assert mvs_b200.launch_count() >= n0 + 8
+    assert mvs_b200.launch_count() >= n0 + (8 if form == "classes" else 1)
+    if form == "fused":
+        monkeypatch.setenv("MVSB200_DECONV", "classes")
+        # same products, another summation order of the taps in the fp32 accumulator: equal up to one bf16 rounding
+        assert _rel(y, be.conv_transpose3d(x1.detach(), w1.detach(), 2, pads, dims)) < 4e-3
     x2, w2 = x.float().requires_grad_(True), wt.float().requires_grad_(True)
     ref = conv_backends.TorchConvBackend.conv_transpose3d(x2, w2, 2, pads, dims)
     assert y.shape == ref.shape

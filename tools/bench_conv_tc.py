@@ -48,6 +48,11 @@ def layer(name, B, Cin, Cout, D, h, w, pad):
     st = torch.cuda.current_stream().cuda_stream
     ours = lambda: _lib.call("mvsb200_conv3d_s1_fwd", x.data_ptr(), wp.data_ptr(), y.data_ptr(), B, D, h, w, Cin, Do, Ho, Wo,
                              Cout, Cout, n_rows, off, off, off, st)
+    wk = wp.view(3, 3, 3, n_rows, Cin).permute(1, 2, 0, 3, 4).contiguous()
+    y2 = torch.empty_like(y)
+    kdn = lambda: _lib.call("mvsb200_conv3d_s1_fwd_kdn", x.data_ptr(), wk.data_ptr(), y2.data_ptr(), B, D, h, w, Cin, Do, Ho, Wo,
+                            Cout, Cout, n_rows, off, off, off, st)
+    t_kdn = timeit(kdn)
     wt_cl = wt.contiguous(memory_format=torch.channels_last_3d)
     cudnn = lambda: F.conv3d(x, wt_cl, padding=1 if pad else 0)
     t_ours, t_cudnn = timeit(ours), timeit(cudnn)
@@ -62,7 +67,9 @@ def layer(name, B, Cin, Cout, D, h, w, pad):
                            off, off, off, st)
     wg_cudnn = lambda: torch.nn.grad.conv3d_weight(x, wt.shape, gy, padding=1 if pad else 0)
     t_wg, t_wg_cudnn = (timeit(wg), timeit(wg_cudnn)) if Cout in (8, 16, 32, 64) else (None, None)
-    print(json.dumps(dict(layer=name, wgrad_ms=t_wg, wgrad_ms_cudnn=t_wg_cudnn, wgrad_TFLOPs=(flops / t_wg / 1e9) if t_wg else None, Cin=Cin, Cout=Cout, out=[B, Do, Ho, Wo], ms=t_ours, ms_cudnn=t_cudnn, rel_err_vs_cudnn=err,
+    err_kdn = (y2.float() - ref.float()).abs().max().item() / ref.float().abs().max().item()
+    print(json.dumps(dict(layer=name, ms_kdn=t_kdn, TFLOPs_kdn=flops / t_kdn / 1e9, frac_tensor_peak_kdn=flops / t_kdn / 1e9 / PEAK_TF,
+                          frac_hbm_kdn=byts / t_kdn / 1e6 / PEAK_GB, rel_err_kdn=err_kdn, wgrad_ms=t_wg, wgrad_ms_cudnn=t_wg_cudnn, wgrad_TFLOPs=(flops / t_wg / 1e9) if t_wg else None, Cin=Cin, Cout=Cout, out=[B, Do, Ho, Wo], ms=t_ours, ms_cudnn=t_cudnn, rel_err_vs_cudnn=err,
                           TFLOPs=flops / t_ours / 1e9, frac_tensor_peak=flops / t_ours / 1e9 / PEAK_TF,
                           act_GBps=byts / t_ours / 1e6, frac_hbm=byts / t_ours / 1e6 / PEAK_GB)), flush=True)
 
