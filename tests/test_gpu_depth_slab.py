@@ -18,32 +18,39 @@ class ThreadComm:
         def __init__(self, world):
             self.world = world
             self.barrier = threading.Barrier(world)
-            self.box = {}
+            self.turn = threading.Lock()       # held by the one rank that is computing (ranks share the process-wide
+            self.box = {}                      # library workspaces, allocator pools and module caches: they take turns)
             self.slots = [None] * world
             self.lock = threading.Lock()
 
     def __init__(self, shared, rank):
         self.sh, self.rank, self.world = shared, rank, shared.world
 
+    def _wait(self):
+        self.sh.turn.release()
+        try:
+            self.sh.barrier.wait()
+        finally:
+            self.sh.turn.acquire()
+
     def exchange(self, sends, recvs):
         with self.sh.lock:
             for d, t in sends:
                 assert (self.rank, d) not in self.sh.box
                 self.sh.box[(self.rank, d)] = t
-        self.sh.barrier.wait()
+        self._wait()
         for s, buf in recvs:
             with self.sh.lock:
                 t = self.sh.box.pop((s, self.rank))
             assert t.shape == buf.shape and t.dtype == buf.dtype
             buf.copy_(t)
-        self.sh.barrier.wait()
-        assert not self.sh.box
+        self._wait()
 
     def all_gather(self, t):
         self.sh.slots[self.rank] = t
-        self.sh.barrier.wait()
+        self._wait()
         parts = [p.clone() for p in self.sh.slots]
-        self.sh.barrier.wait()
+        self._wait()
         return parts
 
     def all_reduce_sum(self, t):
@@ -59,16 +66,22 @@ class ThreadComm:
 
 
 def _run_ranks(world, fn):
+    """R virtual ranks as R threads of this process.  Ranks share what real ranks (separate processes) do not -- the library's
+    per-device workspaces, the allocator, module-level caches -- so they take turns: a rank computes while it holds the turn
+    and hands it over only while it waits for the others inside an exchange."""
     shared = ThreadComm.Shared(world)
     out, err = [None] * world, []
 
     def work(r):
+        shared.turn.acquire()
         try:
             torch.cuda.set_device(0)
             out[r] = fn(ThreadComm(shared, r))
         except BaseException as e:      # noqa: BLE001 -- re-raised below; a dead rank must not leave the others at a barrier
             err.append(e)
             shared.barrier.abort()
+        finally:
+            shared.turn.release()
 
     ts = [threading.Thread(target=work, args=(r,)) for r in range(world)]
     for t in ts:
