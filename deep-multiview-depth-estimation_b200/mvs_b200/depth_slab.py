@@ -388,7 +388,7 @@ class DepthSlabCostVolumeReg:
                 mean, var = reg._stats_from_sums_with_constant_outside(t[0], t[1], Wk.float(), bg, dims, E_lo, E_hi, B, n_full)
             scale, shift = reg._bn_affine(bn, mean if train else None, var if train else None, n_full)
             enc[k] = _affine_geo(T, scale, shift, (plan.lo + ta, E_lo[1], E_lo[2]), (plan.lo + ja, C_lo[1], C_lo[2]),
-                                 (jb - ja, C_dims[1], C_dims[2])).float()
+                                 (jb - ja, C_dims[1], C_dims[2]))
 
         # ---- decoder: transposed convolutions from box planes to canvas planes
         Lhw = (rg[1][2], rg[2][2])
@@ -406,11 +406,11 @@ class DepthSlabCostVolumeReg:
             pa, pb = pieces[r]
             Uc = U[:, :, :b - a, :h, :w]
             piece = _affine_geo(Uc, scale, shift, (a, 0, 0), (plan.lo + pa, C_lo[1], C_lo[2]), (pb - pa, C_dims[1], C_dims[2]))
-            return reslab(piece, pieces, plan.box, self.comm).float()
+            return reslab(piece, pieces, plan.box, self.comm)
 
         c3 = up(enc[3], "deconv_3_0", reg.BN_2, True)
-        c2 = up(c3 + enc[2], "deconv_2_0", reg.BN_1, True)
-        y1 = up(c2 + enc[1], "deconv_1_0", reg.BN_0, False)
+        c2 = up(c3 + enc[2].to(c3.dtype), "deconv_2_0", reg.BN_1, True)
+        y1 = up(c2 + enc[1].to(c2.dtype), "deconv_1_0", reg.BN_0, False)
         z = (y1 + y0).contiguous(memory_format=_CL)
 
         # ---- conv_out on the slab + one halo plane per side

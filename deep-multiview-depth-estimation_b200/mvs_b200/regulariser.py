@@ -194,7 +194,7 @@ class CostVolumeReg(nn.Module):
                     t1, t2 = ops.channel_sums(T)
                     mean, var = self._stats_from_sums_with_constant_outside(t1, t2, Wk.float(), bg, dims, E_lo, E_hi, B, n_full)
                 scale, shift = self._bn_affine(bn, mean if train else None, var if train else None, n_full)
-                enc[k] = ops.affine_relu_geo(T, scale, shift, E_lo, C_lo, C_dims).float()      # on C
+                enc[k] = ops.affine_relu_geo(T, scale, shift, E_lo, C_lo, C_dims)      # on C, storage dtype of the path
                 continue
             Sf = S.float()
             if train:
@@ -226,9 +226,11 @@ class CostVolumeReg(nn.Module):
             return self._bn_dense(bn, U, crop, dims)      # U holds the canvas at its origin (+ up to one slack plane/line/column)
 
         # the transposed convs' canvases are normalised with full-canvas statistics but only their box C is read
-        c3 = up(enc[3], "deconv_3_0", self.BN_2, C).float()
-        c2 = up(c3 + enc[2], "deconv_2_0", self.BN_1, C).float()
-        y1 = up(c2 + enc[1], "deconv_1_0", self.BN_0)
+        # skip additions in the storage dtype of the path (bf16 path: one more bf16 rounding instead of two fp32 round trips
+        # of the box tensors per addition, forward and backward)
+        c3 = up(enc[3], "deconv_3_0", self.BN_2, C)
+        c2 = up(c3 + enc[2].to(c3.dtype), "deconv_2_0", self.BN_1, C)
+        y1 = up(c2 + enc[1].to(c2.dtype), "deconv_1_0", self.BN_0)
         z = y1 + y0
         if z.is_cuda and dt == torch.bfloat16 and z.shape[1] == 8 and self.conv_out.out_channels == 1:
             return ops.conv_out(z, self.conv_out.weight)              # K3c: 8 -> 1 is streaming work, not a GEMM

@@ -1,1 +1,2 @@
-for i in 1 2 3 4 5 6 7 8; do timeout 600 python -m pytest tests/test_gpu_depth_slab.py -m gpu -q 2>&1 | grep -E "^FAILED|passed|failed" >> gpurun_out/pytest_flaky3.log; done
+timeout 600 python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
+timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench13.json 2> gpurun_out/bench13.err; echo "rc=$?" >> gpurun_out/bench13.err
