@@ -323,10 +323,11 @@ def run_b200(args, rank, world, local_rank):
                                       "frac": tc_fl / (tc_ms * 1e-3) / 1e12 / tpeak if tc_ms else None},
                 "bound": "tensor", "achieved": k3.get("TFLOPs"), "peak": tpeak, "peak_source": tpeak_src, "unit": "TFLOP/s",
                 "frac": (k3["TFLOPs"] / tpeak) if k3.get("TFLOPs") else None,
-                "traffic": _ncu_traffic("r01_k3_conv3d_s1_tc_ncu.json"),
+                "traffic": _ncu_traffic("r01_k3_kdn_ncu.json"),
                 "traffic_case": "ncu --set full capture of the 32->32 dense canvas launch (252 MB in + 252 MB out algorithmic)",
                 "alg_flops_per_step": k3.get("alg_flops_per_step"), "ms_per_step": k3.get("ms_per_step"),
-                "note": "ncu: tensor pipe busy 92 % of cycles, shared-memory operand feed 78 % of peak (N = 32): profiles/r01_k3_notes.md"}
+                "note": "conv3d_s1_kdn_kernel (depth tap folded into the MMA N extent); ncu of the 32->32 dense launch: MAC array busy 67 % of "
+                        "cycles, 1154 TFLOP/s in isolation = 70 % of the burst bf16 peak: profiles/r01_k3_notes.md"}
 
     line = None
     if rank == 0:
