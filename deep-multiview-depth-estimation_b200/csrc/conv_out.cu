@@ -8,6 +8,7 @@
 //   dgrad  gz[v][c]    = sum_tap W[tap][c] * glogits[v - tap + 1]               fp32 [B,D,h,w]       ->  bf16 [B,D,h,w,8]
 //   wgrad  gW[tap][c]  = sum_v glogits[v] * z[v + tap - 1][c]                   deterministic two-stage reduction
 #include "common.cuh"
+#include <stdlib.h>
 
 using namespace mvsb200;
 
@@ -156,8 +157,163 @@ __global__ void conv_out_wgrad_finalize_kernel(const float* __restrict__ partial
     gw[i] = (float)s;
 }
 
+// =====================================================================================================================
+// Depth-marching forms (the shipped ones).  The one-thread-per-voxel kernels above fetch 27 taps per voxel through L1 and
+// read the filter from shared memory (54 LDS.128 per voxel); here a thread owns an (x, y) column and walks a run of planes:
+// per INPUT plane it loads the 9 in-plane taps once, forms the three depth-tap partial sums with the filter as
+// constant-bank FFMA operands (no load instruction for the weights) and keeps two running sums in registers -- the
+// register-level twin of the kdn tensor-core kernel.  The filter lives in one of 4 __constant__ slots (copied device to
+// device on the launching stream; round-robin so that up to 4 calls with different filters may be in flight).
+__constant__ float c_w[4][kWn];
+constexpr int kDch = 24;                         // planes per run: (kDch + 2) input planes are visited per kDch outputs
+
+__global__ void __launch_bounds__(256) conv_out_fwd_march_kernel(const uint4* __restrict__ z, float* __restrict__ out, int D, int h,
+                                                                 int w, int nch, int slot) {
+    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+    const int b = blockIdx.z / nch, d0 = (blockIdx.z % nch) * kDch, d1 = min(D, d0 + kDch);
+    if (x >= w || y >= h) return;
+    const float* cw = c_w[slot];
+    bool okx[3], oky[3];
+    int offs[9];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { okx[k] = (unsigned)(x + k - 1) < (unsigned)w; oky[k] = (unsigned)(y + k - 1) < (unsigned)h; }
+#pragma unroll
+    for (int t = 0; t < 9; ++t) offs[t] = (min(max(y + t / 3 - 1, 0), h - 1)) * w + min(max(x + t % 3 - 1, 0), w - 1);
+    const size_t plane = (size_t)h * w;
+    float R1 = 0.f, R2 = 0.f;
+    for (int s = d0 - 1; s <= d1; ++s) {
+        float p0 = 0.f, p1 = 0.f, p2 = 0.f;
+        if ((unsigned)s < (unsigned)D) {
+            const uint4* zp = z + (size_t)(b * D + s) * plane;
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+                const bool ok = okx[t % 3] && oky[t / 3];
+                uint4 u = __ldg(zp + offs[t]);
+                if (!ok) u = make_uint4(0u, 0u, 0u, 0u);
+                float v[8];
+                bf16x8_to_f32(u, v);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    p0 = fmaf(v[c], cw[(0 * 9 + t) * kCi + c], p0);
+                    p1 = fmaf(v[c], cw[(1 * 9 + t) * kCi + c], p1);
+                    p2 = fmaf(v[c], cw[(2 * 9 + t) * kCi + c], p2);
+                }
+            }
+        }
+        const float o = R2 + p2;                         // output plane s - 1: taps kd = 0, 1, 2 from input planes s-2, s-1, s
+        R2 = R1 + p1;
+        R1 = p0;
+        if (s - 1 >= d0) out[(size_t)(b * D + s - 1) * plane + (size_t)y * w + x] = o;
+    }
+}
+
+__global__ void __launch_bounds__(256) conv_out_dgrad_march_kernel(const float* __restrict__ g, uint4* __restrict__ gz, int D, int h,
+                                                                   int w, int nch, int slot) {
+    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+    const int b = blockIdx.z / nch, d0 = (blockIdx.z % nch) * kDch, d1 = min(D, d0 + kDch);
+    if (x >= w || y >= h) return;
+    const float* cw = c_w[slot];
+    bool okx[3], oky[3];
+    int offs[9];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { okx[k] = (unsigned)(x - k + 1) < (unsigned)w; oky[k] = (unsigned)(y - k + 1) < (unsigned)h; }
+#pragma unroll
+    for (int t = 0; t < 9; ++t) offs[t] = (min(max(y - t / 3 + 1, 0), h - 1)) * w + min(max(x - t % 3 + 1, 0), w - 1);
+    const size_t plane = (size_t)h * w;
+    float R1[8], R2[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) { R1[c] = 0.f; R2[c] = 0.f; }
+    for (int s = d0 - 1; s <= d1; ++s) {                 // planes of the upstream gradient
+        float q0[8], q1[8], q2[8];                       // its contribution to output planes s-1 (kd=0), s (kd=1), s+1 (kd=2)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) { q0[c] = 0.f; q1[c] = 0.f; q2[c] = 0.f; }
+        if ((unsigned)s < (unsigned)D) {
+            const float* gp = g + (size_t)(b * D + s) * plane;
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+                const bool ok = okx[t % 3] && oky[t / 3];
+                float gv = __ldg(gp + offs[t]);
+                if (!ok) gv = 0.f;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    q0[c] = fmaf(gv, cw[(0 * 9 + t) * kCi + c], q0[c]);
+                    q1[c] = fmaf(gv, cw[(1 * 9 + t) * kCi + c], q1[c]);
+                    q2[c] = fmaf(gv, cw[(2 * 9 + t) * kCi + c], q2[c]);
+                }
+            }
+        }
+        float o[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) { o[c] = R2[c] + q0[c]; R2[c] = R1[c] + q1[c]; R1[c] = q2[c]; }
+        if (s - 1 >= d0)
+            gz[(size_t)(b * D + s - 1) * plane + (size_t)y * w + x] =
+                make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+    }
+}
+
+// weight gradient: a warp walks one (b, d, y) line; lane = tap (27 of 32 lanes) with the 8 channel sums of its tap in
+// registers; per voxel a lane reads ONE 16-byte voxel row (the three kw lanes of a (kd,kh) read 48 contiguous bytes) and
+// the broadcast upstream gradient.  Same two-stage deterministic reduction as before.
+__global__ void __launch_bounds__(256) conv_out_wgrad_tap_kernel(const uint4* __restrict__ z, const float* __restrict__ g,
+                                                                 float* __restrict__ partials, int B, int D, int h, int w) {
+    __shared__ float s_acc[8][kWn];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tap = lane < kTaps ? lane : 0;
+    const int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
+    const bool owner = lane < kTaps;
+    float acc[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[c] = 0.f;
+    const long lines = (long)B * D * h;
+    for (long line = (long)blockIdx.x * 8 + warp; line < lines; line += (long)gridDim.x * 8) {
+        const int y = (int)(line % h);
+        const int d = (int)((line / h) % D);
+        const int b = (int)(line / ((long)h * D));
+        const int dz = d + kd - 1, yy = y + kh - 1;
+        const bool row_ok = owner && (unsigned)dz < (unsigned)D && (unsigned)yy < (unsigned)h;
+        const float* gl = g + line * w;
+        const uint4* zr = z + ((size_t)(b * D + (row_ok ? dz : d)) * h + (row_ok ? yy : y)) * w;
+        const int x_lo = max(0, 1 - kw), x_hi = min(w, w + 1 - kw);       // x with 0 <= x + kw - 1 < w
+#pragma unroll 4
+        for (int x = 0; x < w; ++x) {
+            const float gv = __ldg(gl + x);
+            if (row_ok && x >= x_lo && x < x_hi) {
+                float v[8];
+                bf16x8_to_f32(__ldg(zr + x + kw - 1), v);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) acc[c] = fmaf(gv, v[c], acc[c]);
+            }
+        }
+    }
+    if (owner) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) s_acc[warp][tap * kCi + c] = acc[c];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kWn; i += 256) {
+        float sum = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) sum += s_acc[k][i];
+        partials[(size_t)blockIdx.x * kWn + i] = sum;
+    }
+}
+
+int stage_filter(const float* w27x8, cudaStream_t st, int* slot_out) {
+    static unsigned counter = 0;
+    const int slot = (int)(__atomic_fetch_add(&counter, 1u, __ATOMIC_RELAXED) & 3u);
+    MVS_CUDA(cudaMemcpyToSymbolAsync(c_w, w27x8, sizeof(float) * kWn, sizeof(float) * kWn * slot, cudaMemcpyDeviceToDevice, st));
+    *slot_out = slot;
+    return MVSB200_OK;
+}
+
+bool use_march() {
+    const char* e = getenv("MVSB200_CONV_OUT");
+    return !(e && e[0] == 'v');                          // MVSB200_CONV_OUT=voxel selects the one-thread-per-voxel kernels
+}
+
 int check_shape(int B, int D, int h, int w, const char* name) {
-    MVS_REQUIRE(B >= 1 && D >= 1 && h >= 1 && w >= 1 && (long)B * D <= 65535 && (h + 7) / 8 <= 65535, "%s: bad shape", name);
+    MVS_REQUIRE(B >= 1 && D >= 1 && h >= 1 && w >= 1 && (long)B * D <= 65535 && (h + 7) / 8 <= 65535 && (long)h * w < (1L << 30),
+                "%s: bad shape", name);
     return MVSB200_OK;
 }
 
@@ -168,6 +324,15 @@ extern "C" int64_t mvsb200_conv_out_workspace_floats(void) { return (int64_t)kWg
 extern "C" int mvsb200_conv_out_fwd(const void* z, const float* w27x8, float* logits, int B, int D, int h, int w, void* stream) {
     MVS_REQUIRE(z && w27x8 && logits && aligned16(z), "conv_out_fwd: null or misaligned pointer");
     if (int rc = check_shape(B, D, h, w, "conv_out_fwd")) return rc;
+    if (use_march()) {
+        int slot = 0;
+        if (int rc = stage_filter(w27x8, (cudaStream_t)stream, &slot)) return rc;
+        const int nch = (D + kDch - 1) / kDch;
+        const dim3 grid((w + 31) / 32, (h + 7) / 8, B * nch);
+        conv_out_fwd_march_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>((const uint4*)z, logits, D, h, w, nch, slot);
+        MVS_CHECK_LAUNCH("conv_out_fwd_march");
+        return MVSB200_OK;
+    }
     const dim3 grid((w + 31) / 32, (h + 7) / 8, B * D);
     conv_out_fwd_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>((const uint4*)z, w27x8, logits, D, h, w);
     MVS_CHECK_LAUNCH("conv_out_fwd");
@@ -177,6 +342,15 @@ extern "C" int mvsb200_conv_out_fwd(const void* z, const float* w27x8, float* lo
 extern "C" int mvsb200_conv_out_dgrad(const float* glogits, const float* w27x8, void* gz, int B, int D, int h, int w, void* stream) {
     MVS_REQUIRE(glogits && w27x8 && gz && aligned16(gz), "conv_out_dgrad: null or misaligned pointer");
     if (int rc = check_shape(B, D, h, w, "conv_out_dgrad")) return rc;
+    if (use_march()) {
+        int slot = 0;
+        if (int rc = stage_filter(w27x8, (cudaStream_t)stream, &slot)) return rc;
+        const int nch = (D + kDch - 1) / kDch;
+        const dim3 grid((w + 31) / 32, (h + 7) / 8, B * nch);
+        conv_out_dgrad_march_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(glogits, (uint4*)gz, D, h, w, nch, slot);
+        MVS_CHECK_LAUNCH("conv_out_dgrad_march");
+        return MVSB200_OK;
+    }
     const dim3 grid((w + 31) / 32, (h + 7) / 8, B * D);
     conv_out_dgrad_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(glogits, w27x8, (uint4*)gz, D, h, w);
     MVS_CHECK_LAUNCH("conv_out_dgrad");
@@ -189,8 +363,14 @@ extern "C" int mvsb200_conv_out_wgrad(const void* z, const float* glogits, float
     if (int rc = check_shape(B, D, h, w, "conv_out_wgrad")) return rc;
     const long lines = (long)B * D * h;
     const int blocks = (int)((lines + 7) / 8 < kWgBlocks ? (lines + 7) / 8 : kWgBlocks);
-    conv_out_wgrad_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)z, glogits, workspace, B, D, h, w);
-    MVS_CHECK_LAUNCH("conv_out_wgrad");
+    if (use_march()) {
+        MVS_REQUIRE(aligned16(z), "conv_out_wgrad: misaligned volume");
+        conv_out_wgrad_tap_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const uint4*)z, glogits, workspace, B, D, h, w);
+        MVS_CHECK_LAUNCH("conv_out_wgrad_tap");
+    } else {
+        conv_out_wgrad_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)z, glogits, workspace, B, D, h, w);
+        MVS_CHECK_LAUNCH("conv_out_wgrad");
+    }
     conv_out_wgrad_finalize_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(workspace, blocks, gw27x8);
     MVS_CHECK_LAUNCH("conv_out_wgrad_finalize");
     return MVSB200_OK;
