@@ -499,6 +499,8 @@ struct WgradParams {
     int cout;                       // real output channels of the layer (row length of gW)
     int slab_bytes, gy_bytes;       // per ring slot / per gy stage, multiples of 1024
     int ksteps;                     // ceil((L+2)*BW / 16)
+    unsigned kd_mask;               // depth taps to compute (bit kd); the others' MMAs are not issued
+    int tap_map[27];                // kernel tap (kd*3+kh)*3+kw -> row block of gw it is added to, -1 = dropped
     float* gw;                      // [27][CIN][cout] fp32, accumulated into
 };
 
@@ -639,6 +641,7 @@ conv3d_s1_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid
                     const uint32_t g_lo = gy_lo + (uint32_t)st * gy16;
 #pragma unroll
                     for (int kd = 0; kd < 3; ++kd) {
+                        if (!(p.kd_mask >> kd & 1u)) continue;
                         const uint32_t s_lo = slab_lo + (uint32_t)((gs0 + d + kd) % kSlots3) * slab16;
 #pragma unroll
                         for (int blk = 0; blk < KWB; ++blk) {
@@ -675,6 +678,7 @@ conv3d_s1_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid
         constexpr int ATOMS = 128 / CIN;                 // kw atoms per block
         const int kw_in_blk = row / CIN, ci = row % CIN;
         for (int kd = 0; kd < 3; ++kd) {
+            if (!(p.kd_mask >> kd & 1u)) continue;
 #pragma unroll
             for (int blk = 0; blk < KWB; ++blk) {
                 const int kw = blk * 2 + kw_in_blk;
@@ -688,9 +692,11 @@ conv3d_s1_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid
 #pragma unroll
                         for (int k = 0; k < 16; ++k) {
                             const int col = c0 + k, n = col / NCO, co = col % NCO;     // atom n <-> kh = 2 - n
-                            if (n < 3 && p.co0 + co < p.cout)
-                                atomicAdd(p.gw + ((size_t)((kd * 3 + (2 - n)) * 3 + kw) * CIN + ci) * p.cout + p.co0 + co,
-                                          __uint_as_float(v[k]));
+                            if (n < 3 && p.co0 + co < p.cout) {
+                                const int slot = p.tap_map[(kd * 3 + (2 - n)) * 3 + kw];
+                                if (slot >= 0)
+                                    atomicAdd(p.gw + ((size_t)slot * CIN + ci) * p.cout + p.co0 + co, __uint_as_float(v[k]));
+                            }
                         }
                     }
                 }
@@ -730,9 +736,13 @@ WgPlan plan_tiles_wgrad(int Ho, int Wo, int rowx, int rowg, size_t smem_budget) 
     return best;
 }
 
+// x_es: element stride of the x sub-lattice per spatial axis (1 = dense, 2 = a parity class of a stride-2 layer); x points at
+// the class's first voxel, (Di, Hi, Wi) are the sub-lattice extents and (Dx, Hx, Wx) those of the allocation it lives in.
 template <int CIN, int NCO>
 int launch_wgrad(const void* x, const void* gy, float* gw, int B, int Di, int Hi, int Wi, int Do, int Ho, int Wo, int cout, int co0,
-                 int off_d, int off_h, int off_w, cudaStream_t st) {
+                 int off_d, int off_h, int off_w, cudaStream_t st, int x_es = 1, int Dx = 0, int Hx = 0, int Wx = 0,
+                 unsigned kd_mask = 7u, const int* tap_map = nullptr) {
+    if (x_es == 1) { Dx = Di; Hx = Hi; Wx = Wi; }
     constexpr int ROWX = CIN * 2, ROWG = NCO * 2;
     EncodeTiledFn enc = encode_fn();
     MVS_REQUIRE(enc != nullptr, "conv3d_s1_wgrad: cuTensorMapEncodeTiled is not available from the driver");
@@ -743,7 +753,8 @@ int launch_wgrad(const void* x, const void* gy, float* gw, int B, int Di, int Hi
     CUtensorMap tm_x, tm_g;
     {
         const cuuint64_t dims[5] = {(cuuint64_t)CIN, (cuuint64_t)Wi, (cuuint64_t)Hi, (cuuint64_t)Di, (cuuint64_t)B};
-        const cuuint64_t strides[4] = {(cuuint64_t)ROWX, (cuuint64_t)ROWX * Wi, (cuuint64_t)ROWX * Wi * Hi, (cuuint64_t)ROWX * Wi * Hi * Di};
+        const cuuint64_t strides[4] = {(cuuint64_t)x_es * ROWX, (cuuint64_t)x_es * ROWX * Wx, (cuuint64_t)x_es * ROWX * Wx * Hx,
+                                       (cuuint64_t)ROWX * Wx * Hx * Dx};
         const cuuint32_t box[5] = {(cuuint32_t)CIN, (cuuint32_t)tp.BW, (cuuint32_t)(tp.L + 2), 1, 1};
         const cuuint32_t es[5] = {1, 1, 1, 1, 1};
         CUresult r = enc(&tm_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), dims, strides, box, es,
@@ -766,6 +777,8 @@ int launch_wgrad(const void* x, const void* gy, float* gw, int B, int Di, int Hi
     p.BW = tp.BW; p.L = tp.L; p.tiles_x = tp.tiles_x; p.tiles_y = tp.tiles_y;
     p.co0 = co0; p.cout = cout; p.slab_bytes = tp.slab_bytes; p.gy_bytes = tp.gy_bytes;
     p.ksteps = ((tp.L + 2) * tp.BW + 15) / 16;
+    p.kd_mask = kd_mask & 7u;
+    for (int t = 0; t < 27; ++t) p.tap_map[t] = tap_map ? tap_map[t] : t;
     p.gw = gw;
     const long tiles = (long)tp.tiles_x * tp.tiles_y;
     int sms = 148;
@@ -1930,6 +1943,78 @@ extern "C" int mvsb200_conv3d_s1_fwd_kdn(const void* x, const void* w_packed, vo
         else MVS_FAIL(MVSB200_E_UNSUPPORTED, "%s: unsupported channels Cin=%d n_rows=%d", name, Cin, n_rows);
 #undef MVS_CONV
         if (rc != MVSB200_OK) return rc;
+    }
+    return MVSB200_OK;
+}
+
+/* Weight gradient of the STRIDE-2 layers on the same kernel:  gw[k][cb][cs] = sum_o big(2o - pad + k)[cb] * small(o)[cs]
+ * (per axis, k = 0..2, big zero outside its volume).  For a stride-2 convolution (model.py:104-110) big = its input, small =
+ * the output gradient; for a stride-2 transposed convolution (model.py:115-121) big = the output gradient, small = its input
+ * (gw then holds [k][Cout][Cin]).  Per output-parity class pi of (k - pad) the sum is a stride-1 correlation of the class's
+ * sub-lattice of `big` (a TMA map with doubled strides) with `small`; each class launch issues only the depth taps it needs
+ * and drops the in-plane taps of other classes. */
+extern "C" int mvsb200_conv3d_s2_wgrad(const void* big, const void* small, float* gw, int B, int Db, int Hb, int Wb, int Cb,
+                                       int Ds, int Hs, int Ws, int Cs, int pad_d, int pad_h, int pad_w, void* stream) {
+    const char* name = "conv3d_s2_wgrad";
+    MVS_REQUIRE(big && small && gw, "%s: null pointer", name);
+    MVS_REQUIRE(aligned16(big) && aligned16(small) && aligned16(gw), "%s: pointers must be 16-byte aligned", name);
+    MVS_REQUIRE(B >= 1 && Db >= 1 && Hb >= 1 && Wb >= 1 && Ds >= 1 && Hs >= 1 && Ws >= 1, "%s: bad shape", name);
+    MVS_REQUIRE(Cb == 16 || Cb == 32 || Cb == 64, "%s: the strided operand must have 16, 32 or 64 channels (got %d)", name, Cb);
+    MVS_REQUIRE(Cs >= 8 && Cs % 8 == 0, "%s: the dense operand needs a multiple of 8 channels (got %d)", name, Cs);
+    MVS_REQUIRE(pad_d >= 1 && pad_d <= 2 && pad_h >= 1 && pad_h <= 2 && pad_w >= 1 && pad_w <= 2, "%s: pad must be 1 or 2 per axis", name);
+    cudaStream_t st = (cudaStream_t)stream;
+    MVS_CUDA(cudaMemsetAsync(gw, 0, (size_t)27 * Cb * Cs * sizeof(float), st));
+    const int pads[3] = {pad_d, pad_h, pad_w};
+    const int nb[3] = {Db, Hb, Wb};
+    const int nco_max = Cb == 64 ? 16 : 32;
+    for (int c = 0; c < 8; ++c) {
+        const int par[3] = {c >> 2 & 1, c >> 1 & 1, c & 1};
+        int sub[3];
+        bool empty = false;
+        for (int ax = 0; ax < 3; ++ax) { sub[ax] = (nb[ax] - par[ax] + 1) / 2; if (sub[ax] < 1) empty = true; }
+        if (empty) continue;
+        // filter taps of this class per axis: k with (k - pad - par) even; shift s = (k - pad - par)/2 in {-1, 0}; kernel tap t = s + 1
+        int tap_map[27];
+        for (int t = 0; t < 27; ++t) tap_map[t] = -1;
+        unsigned kd_mask = 0;
+        int n_taps = 0;
+        for (int kd = 0; kd < 3; ++kd)
+            for (int kh = 0; kh < 3; ++kh)
+                for (int kw = 0; kw < 3; ++kw) {
+                    const int k[3] = {kd, kh, kw};
+                    int t[3];
+                    bool ok = true;
+                    for (int ax = 0; ax < 3; ++ax) {
+                        const int v = k[ax] - pads[ax] - par[ax];
+                        if (v & 1) { ok = false; break; }
+                        t[ax] = v / 2 + 1;                   // v is even and <= 0: exact
+                        if (t[ax] < 0 || t[ax] > 2) { ok = false; break; }
+                    }
+                    if (!ok) continue;
+                    tap_map[(t[0] * 3 + t[1]) * 3 + t[2]] = (kd * 3 + kh) * 3 + kw;
+                    kd_mask |= 1u << t[0];
+                    ++n_taps;
+                }
+        if (n_taps == 0) continue;
+        const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(big) + (((size_t)par[0] * Hb + par[1]) * Wb + par[2]) * Cb;
+        for (int co0 = 0; co0 < Cs;) {
+            const int left = Cs - co0;
+            const int nco = left >= nco_max ? nco_max : (left >= 16 ? 16 : 8);
+            int rc = MVSB200_E_UNSUPPORTED;
+#define MVS_WG(CI, NC) rc = launch_wgrad<CI, NC>(base, small, gw, B, sub[0], sub[1], sub[2], Ds, Hs, Ws, Cs, co0, -1, -1, -1, st, 2, Db, Hb, Wb, kd_mask, tap_map)
+            if (Cb == 16 && nco == 8) MVS_WG(16, 8);
+            else if (Cb == 16 && nco == 16) MVS_WG(16, 16);
+            else if (Cb == 16 && nco == 32) MVS_WG(16, 32);
+            else if (Cb == 32 && nco == 8) MVS_WG(32, 8);
+            else if (Cb == 32 && nco == 16) MVS_WG(32, 16);
+            else if (Cb == 32 && nco == 32) MVS_WG(32, 32);
+            else if (Cb == 64 && nco == 8) MVS_WG(64, 8);
+            else if (Cb == 64 && nco == 16) MVS_WG(64, 16);
+            else MVS_FAIL(MVSB200_E_UNSUPPORTED, "%s: unsupported channels %d / %d", name, Cb, nco);
+#undef MVS_WG
+            if (rc != MVSB200_OK) return rc;
+            co0 += nco;
+        }
     }
     return MVSB200_OK;
 }

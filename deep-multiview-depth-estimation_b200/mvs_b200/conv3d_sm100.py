@@ -196,6 +196,28 @@ def conv_transpose3d_s2(x, w, pads, out_dims):
     return y
 
 
+def _s2_wgrad_ok(c_big, c_small):
+    """The tcgen05 strided weight gradient is correct but, launched once per parity class and channel chunk with an atomic
+    epilogue, still behind the library at the regulariser's shapes (tools/bench_s2_wgrad.py, B = 4: 3.21 vs 2.27 ms for the
+    stacked branches, 1.61 vs 0.94 and 0.71 vs 0.66 ms for the transposed layers): opt-in with MVSB200_S2_WGRAD=tcgen05."""
+    import os
+    return (c_big in _CIN_OK and c_small % 8 == 0 and os.environ.get("MVSB200_S2_WGRAD", "cudnn") == "tcgen05"
+            and hasattr(_lib.load(), "mvsb200_conv3d_s2_wgrad"))
+
+
+def s2_wgrad(big, small, pads):
+    """gw[k][cb][cs] = sum_o big(2o - pad + k)[cb] * small(o)[cs] on the tcgen05 weight-gradient kernel (parity sub-lattices of
+    `big` through doubled-stride TMA maps) -> fp32 [27, Cb, Cs].  big, small: bf16 channels_last_3d [B,C,D,h,w]."""
+    B, cb, Db, Hb, Wb = big.shape
+    _, cs, Ds, Hs, Ws = small.shape
+    gw = torch.empty((27, cb, cs), dtype=torch.float32, device=big.device)
+    # algorithmic work: every tap once over the small volume
+    with _timed("conv3d_s2_wgrad_tc", 2.0 * 27 * cb * cs * B * Ds * Hs * Ws):
+        _lib.call("mvsb200_conv3d_s2_wgrad", big.data_ptr(), small.data_ptr(), gw.data_ptr(), B, Db, Hb, Wb, cb, Ds, Hs, Ws, cs,
+                  int(pads[0]), int(pads[1]), int(pads[2]), _stream())
+    return gw
+
+
 class _ConvTranspose3dS2(torch.autograd.Function):
     """Forward on the tcgen05 kernel; the two gradients are a stride-2 convolution of the output gradient and its
     weight gradient (library kernels until the stride-2 tcgen05 kernels exist)."""
@@ -236,10 +258,16 @@ class _ConvTranspose3dS2(torch.autograd.Function):
             else:
                 gx = F.conv3d(gy, wb, None, 2, P2)[inner]             # weight [Cin, Cout, ...] read as out = Cin, in = Cout
         if ctx.needs_input_grad[1]:
-            xs = torch.zeros((x_cl.shape[0], x_cl.shape[1]) + tuple(n_o), dtype=x_cl.dtype, device=x_cl.device,
-                             ).contiguous(memory_format=torch.channels_last_3d)
-            xs[inner] = x_cl
-            gw = torch.nn.grad.conv3d_weight(gy, w.shape, xs, stride=2, padding=P2).to(w.dtype)
+            cin_t, cout_t = w.shape[:2]
+            if _s2_wgrad_ok(cout_t, cin_t):
+                # gW[ci][co][k] = sum_j x[j][ci] gy[2j - p + k][co]: the strided operand is the output gradient
+                g27 = s2_wgrad(gy, x_cl, pads)                                           # [27, Cout, Cin]
+                gw = g27.reshape(3, 3, 3, cout_t, cin_t).permute(4, 3, 0, 1, 2).to(w.dtype)
+            else:
+                xs = torch.zeros((x_cl.shape[0], x_cl.shape[1]) + tuple(n_o), dtype=x_cl.dtype, device=x_cl.device,
+                                 ).contiguous(memory_format=torch.channels_last_3d)
+                xs[inner] = x_cl
+                gw = torch.nn.grad.conv3d_weight(gy, w.shape, xs, stride=2, padding=P2).to(w.dtype)
         return gx, gw, None, None
 
 
@@ -283,10 +311,17 @@ class _Conv3dS2Box(torch.autograd.Function):
         padding = []
         for ax in (2, 1, 0):
             padding += [off[ax], nat[ax] - off[ax] - ctx.out_dims[ax]]
-        g_full = F.pad(gy, padding).contiguous(memory_format=torch.channels_last_3d)
-        mask = [bool(ctx.needs_input_grad[0]), bool(ctx.needs_input_grad[1]), False]
-        gx, gw, _ = torch.ops.aten.convolution_backward(g_full, x_cl, w.detach().to(torch.bfloat16), None, [2, 2, 2], list(P),
-                                                        [1, 1, 1], False, [0, 0, 0], 1, mask)
+        own_wgrad = bool(ctx.needs_input_grad[1]) and _s2_wgrad_ok(x_cl.shape[1], w.shape[0])
+        mask = [bool(ctx.needs_input_grad[0]), bool(ctx.needs_input_grad[1]) and not own_wgrad, False]
+        gx = gw = None
+        if mask[0] or mask[1]:
+            g_full = F.pad(gy, padding).contiguous(memory_format=torch.channels_last_3d)
+            gx, gw, _ = torch.ops.aten.convolution_backward(g_full, x_cl, w.detach().to(torch.bfloat16), None, [2, 2, 2], list(P),
+                                                            [1, 1, 1], False, [0, 0, 0], 1, mask)
+        if own_wgrad:
+            # gW[co][ci][k] = sum_o x[2o - pad + k][ci] gy[o][co]: the strided operand is the layer's input
+            g27 = s2_wgrad(x_cl, gy.contiguous(memory_format=torch.channels_last_3d), ctx.pads)       # [27, Cin, Cout]
+            gw = g27.reshape(3, 3, 3, x_cl.shape[1], w.shape[0]).permute(4, 3, 0, 1, 2)
         return gx, (gw.to(w.dtype) if gw is not None else None), None, None
 
 

@@ -143,6 +143,14 @@ int mvsb200_conv3d_s1_fwd_ex(const void* x, const void* w_packed, void* y, int B
                              int Do, int Ho, int Wo, int cout, int n_rows, int off_d, int off_h, int off_w,
                              unsigned tap_mask, const int64_t* y_strides4_host, void* stream);
 
+/* Weight gradient of the stride-2 layers (tcgen05, the stride-1 weight-gradient kernel on parity sub-lattices of the strided
+ * operand):  gw[k][cb][cs] = sum_o big(2o - pad + k)[cb] * small(o)[cs], k = (kd,kh,kw), big zero outside its volume.
+ *   stride-2 convolution (scripts/model.py:104-110):            big = input x [B,Db,Hb,Wb,Cb], small = output gradient
+ *   stride-2 transposed convolution (scripts/model.py:115-121): big = output gradient, small = input (gw is [k][Cout][Cin])
+ * big: bf16, Cb in {16,32,64}; small: bf16 [B,Ds,Hs,Ws,Cs], Cs % 8 == 0; gw: fp32 [27,Cb,Cs], zeroed by the call; pad in {1,2}. */
+int mvsb200_conv3d_s2_wgrad(const void* big, const void* small, float* gw, int B, int Db, int Hb, int Wb, int Cb,
+                            int Ds, int Hs, int Ws, int Cs, int pad_d, int pad_h, int pad_w, void* stream);
+
 /* Stride-2 TRANSPOSED convolution forward in ONE launch (ConvTranspose3d k=3, scripts/model.py:229-234, used at :115-121):
  *   out[2J + par] = sum over the taps k with (par + pad - k) even of W[k] . in[J + (par + pad - k)/2] per axis.
  * All 8 output-parity classes are accumulated side by side in TMEM and written interleaved, so every line of the canvas is
