@@ -14,8 +14,29 @@ from . import api
 from .regulariser import CostVolumeReg
 
 
+class BatchNormReLU2d(nn.BatchNorm2d):
+    """BatchNorm2d followed by ReLU (model.py:236-247 pairs).  Train mode on the GPU: the fused channel-last statistics /
+    apply / backward kernels of libmvs_b200.so (K3b) on the [N*H*W, C] rows of the map (ATen's channels-last bf16 BatchNorm
+    takes ~2x as long per pass and a separate ReLU pass); otherwise stock torch.  Same parameters and buffers as
+    nn.BatchNorm2d (state_dict-compatible with the BatchNorm2d + ReLU pair of the reference)."""
+
+    def forward(self, x):
+        if x.is_cuda and self.training and self.num_features in (8, 16, 32, 64) and x.dtype in (torch.float32, torch.bfloat16):
+            from . import ops
+            y, mean, var = ops.batchnorm_relu_train(x.unsqueeze(2), self.weight, self.bias, self.eps, relu=True)
+            n = x.numel() // x.shape[1]
+            with torch.no_grad():
+                m = self.momentum
+                self.running_mean.mul_(1 - m).add_(mean, alpha=m)
+                self.running_var.mul_(1 - m).add_(var * (n / max(n - 1, 1)), alpha=m)
+                self.num_batches_tracked += 1
+            return y.squeeze(2)
+        return F.relu(super().forward(x))
+
+
 def _conv_bn_relu(i, o, k, s):
-    return [nn.Conv2d(i, o, k, stride=s, padding=k // 2, bias=False), nn.BatchNorm2d(o), nn.ReLU()]
+    # Identity keeps the module indices (state_dict keys) of the reference's Conv2d / BatchNorm2d / ReLU triples
+    return [nn.Conv2d(i, o, k, stride=s, padding=k // 2, bias=False), BatchNormReLU2d(o), nn.Identity()]
 
 
 class FeatureEncoder(nn.Module):
