@@ -281,11 +281,13 @@ def pack_filter_rows(w: torch.Tensor, n_rows: int) -> torch.Tensor:
 
 class _Conv3dS2Box(torch.autograd.Function):
     """out(o) = sum_k W[k] x(2o - pad + k) for o in a box of `out_dims` voxels (zero outside x).  Forward on the tcgen05
-    stride-2 kernel; the gradients go through the library's strided convolution backward (until the stride-2 wgrad /
-    transposed dgrad kernels take Cout = 112 operands)."""
+    stride-2 kernel.  `splits`: the output channels are returned as that many separate tensors (the stacked branches
+    conv_{1,2,3}_0); their gradients are then written straight into the padded channel-last buffer the library's strided
+    convolution backward wants -- no concatenation, padding and layout copies of the 112-channel box gradient.  The
+    gradients go through the library (a tcgen05 strided weight gradient exists, opt-in: _s2_wgrad_ok)."""
 
     @staticmethod
-    def forward(ctx, x, w, pads, out_dims):
+    def forward(ctx, x, w, pads, out_dims, splits):
         x_cl = x.detach().contiguous(memory_format=torch.channels_last_3d)
         B, cin, Dx, Hx, Wx = x_cl.shape
         cout = w.shape[0]
@@ -296,44 +298,58 @@ class _Conv3dS2Box(torch.autograd.Function):
             _lib.call("mvsb200_conv3d_s2_fwd", x_cl.data_ptr(), pack_filter_rows(w, n_rows).data_ptr(), y.data_ptr(), B, Dx, Hx, Wx,
                       cin, Do, Ho, Wo, cout, cout, n_rows, pads[0], pads[1], pads[2], _stream())
         ctx.save_for_backward(x_cl, w)
-        ctx.pads, ctx.out_dims = tuple(pads), tuple(out_dims)
-        return y
+        ctx.pads, ctx.out_dims, ctx.splits = tuple(pads), tuple(out_dims), splits
+        if splits is None:
+            return y
+        return tuple(torch.split(y, list(splits), 1))
 
     @staticmethod
-    def backward(ctx, gy):
+    def backward(ctx, *gys):
         x_cl, w = ctx.saved_tensors
         # the same convolution as the library sees it: symmetric padding P = pad (+2 if pad < 2 ... keeps parity), output
         # cropped at offset (P - pad)/2
         P = tuple(q if q >= 2 else q + 2 for q in ctx.pads)
         off = tuple((a - b) // 2 for a, b in zip(P, ctx.pads))
         nat = tuple((n + 2 * a - 3) // 2 + 1 for n, a in zip(x_cl.shape[2:], P))
-        gy = gy.to(torch.bfloat16)
-        padding = []
-        for ax in (2, 1, 0):
-            padding += [off[ax], nat[ax] - off[ax] - ctx.out_dims[ax]]
-        own_wgrad = bool(ctx.needs_input_grad[1]) and _s2_wgrad_ok(x_cl.shape[1], w.shape[0])
+        B, cout = x_cl.shape[0], w.shape[0]
+        box = tuple(slice(o, o + n) for o, n in zip(off, ctx.out_dims))
+        own_wgrad = bool(ctx.needs_input_grad[1]) and _s2_wgrad_ok(x_cl.shape[1], cout)
         mask = [bool(ctx.needs_input_grad[0]), bool(ctx.needs_input_grad[1]) and not own_wgrad, False]
         gx = gw = None
+        gy_box = None
         if mask[0] or mask[1]:
-            g_full = F.pad(gy, padding).contiguous(memory_format=torch.channels_last_3d)
+            # gradient of the natural (padded) output, channel-last, filled in place: zeros + one strided copy per branch
+            g_full = torch.empty((B, cout) + nat, dtype=torch.bfloat16, device=x_cl.device, memory_format=torch.channels_last_3d)
+            g_full.zero_()
+            c0 = 0
+            for g, n in zip(gys, ctx.splits if ctx.splits is not None else (cout,)):
+                if g is not None:
+                    g_full[(slice(None), slice(c0, c0 + n)) + box] = g
+                c0 += n
             gx, gw, _ = torch.ops.aten.convolution_backward(g_full, x_cl, w.detach().to(torch.bfloat16), None, [2, 2, 2], list(P),
                                                             [1, 1, 1], False, [0, 0, 0], 1, mask)
+            gy_box = g_full[(slice(None), slice(None)) + box]
         if own_wgrad:
+            if gy_box is None:
+                gy_box = torch.cat([g if g is not None else torch.zeros((B, n) + ctx.out_dims, dtype=torch.bfloat16, device=x_cl.device)
+                                    for g, n in zip(gys, ctx.splits if ctx.splits is not None else (cout,))], 1)
             # gW[co][ci][k] = sum_o x[2o - pad + k][ci] gy[o][co]: the strided operand is the layer's input
-            g27 = s2_wgrad(x_cl, gy.contiguous(memory_format=torch.channels_last_3d), ctx.pads)       # [27, Cin, Cout]
-            gw = g27.reshape(3, 3, 3, x_cl.shape[1], w.shape[0]).permute(4, 3, 0, 1, 2)
-        return gx, (gw.to(w.dtype) if gw is not None else None), None, None
+            g27 = s2_wgrad(x_cl, gy_box.to(torch.bfloat16).contiguous(memory_format=torch.channels_last_3d), ctx.pads)   # [27, Cin, Cout]
+            gw = g27.reshape(3, 3, 3, x_cl.shape[1], cout).permute(4, 3, 0, 1, 2)
+        return gx, (gw.to(w.dtype) if gw is not None else None), None, None, None
 
 
 class Tcgen05ConvBackend:
     name = "tcgen05"
 
     @staticmethod
-    def conv3d_s2_box(x, w, pads, out_dims):
-        """Stride-2 convolution evaluated on a box: out(o) = sum_k W[k] x(2o - pad + k), o in [0, out_dims)."""
+    def conv3d_s2_box(x, w, pads, out_dims, splits=None):
+        """Stride-2 convolution evaluated on a box: out(o) = sum_k W[k] x(2o - pad + k), o in [0, out_dims).  With `splits`
+        (channel counts) the result is a tuple of tensors, one per group of output channels."""
         if (x.is_cuda and x.dtype == torch.bfloat16 and x.shape[1] in _CIN_OK and w.shape[0] % 8 == 0 and w.shape[0] <= 128
                 and all(q in (1, 2) for q in pads) and min(x.shape[3:]) >= 2):
-            return _Conv3dS2Box.apply(x, w, tuple(int(q) for q in pads), tuple(int(n) for n in out_dims))
+            return _Conv3dS2Box.apply(x, w, tuple(int(q) for q in pads), tuple(int(n) for n in out_dims),
+                                      None if splits is None else tuple(int(n) for n in splits))
         return None
 
     @staticmethod

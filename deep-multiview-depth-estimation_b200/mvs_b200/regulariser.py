@@ -161,13 +161,13 @@ class CostVolumeReg(nn.Module):
         # the three stride-2 branches all read cv (model.py:104-110): ONE convolution with the weights stacked along
         # Cout (16+32+64 = 112) reads the cost volume once instead of three times
         w_cat = torch.cat([self._w(f"conv_{k}_0", dt) for k in (1, 2, 3)], 0)
-        S_all = None
+        widths = [self.conv_1_0.out_channels, self.conv_2_0.out_channels, self.conv_3_0.out_channels]
+        S_parts = None
         if hasattr(be, "conv3d_s2_box"):                                      # tcgen05 stride-2 kernel, straight onto the box
-            S_all = be.conv3d_s2_box(x, w_cat, tuple(L for _, _, L in reg), tuple(hi - lo + 1 for lo, hi, _ in reg))
-        if S_all is None:
-            S_all = be.conv3d(x, w_cat, 2, P)[(slice(None), slice(None)) + cut]
-        S_split = dict(zip((1, 2, 3), torch.split(S_all, [self.conv_1_0.out_channels, self.conv_2_0.out_channels,
-                                                          self.conv_3_0.out_channels], 1)))
+            S_parts = be.conv3d_s2_box(x, w_cat, tuple(L for _, _, L in reg), tuple(hi - lo + 1 for lo, hi, _ in reg), widths)
+        if S_parts is None:
+            S_parts = torch.split(be.conv3d(x, w_cat, 2, P)[(slice(None), slice(None)) + cut], widths, 1)
+        S_split = dict(zip((1, 2, 3), S_parts))
         C_lo = [lo for lo, _, _ in reg]
         C_dims = [hi - lo + 1 for lo, hi, _ in reg]
         F_dims = [F_hi[ax] - F_lo[ax] + 1 for ax in range(3)]
