@@ -306,12 +306,40 @@ def run_b200(args, rank, world, local_rank):
         if work and name in TC_KERNELS:
             kern[name].update({"alg_flops_per_step": sum(work) / args.steps, "TFLOPs": sum(work) / (tot * 1e-3) / 1e12})
     k1 = kern.get("warp_variance_fwd", {})
-    roofline_k1 = {"kernel": "warp_variance_fwd_kernel<V=3, bf16 volume>", "bound": "hbm", "achieved": k1.get("GBps"),
+    roofline_k1 = {"kernel": "warp_variance_fwd2_kernel<V=%d, bf16 volume> (as used by the bf16 regulariser)" % V, "bound": "hbm", "achieved": k1.get("GBps"),
                    "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": k1.get("frac_hbm"),
                    "traffic": None, "alg_bytes_per_launch": alg["warp_variance_fwd"], "ms_per_launch": k1.get("ms"),
                    "voxels_per_s": vox / (k1["ms"] * 1e-3) if k1 else None,
                    "note": "ncu (profiles/r01_k1_*): DRAM traffic = algorithmic bytes (fp32-volume capture 7.7 MB read + 446 MB "
                            "written of 511 MB); fp32-volume variant reaches 44 % of peak (tools/microbench.py)"}
+    # the same kernel with the fp32 volume the reference produces (SURVEY §8d quotes the HBM roofline on these bytes:
+    # 4*V*C*h*w in + 4*C*D*h*w out per sample), timed live on this batch's geometry: L2 flushed between launches, CUDA events
+    roofline_k1_fp32 = None
+    if slab is None:
+        with torch.no_grad():
+            sweep = ops.PlaneSweep(K, R, T, d_min, d_int, B, V, D, d_scale, h, w, dev)
+            feat = torch.randn(B * V, h, w, C, device=dev).permute(0, 3, 1, 2)
+            flush = torch.empty(160 * 1024 * 1024, dtype=torch.float32, device=dev)       # 640 MB > L2
+            ts = []
+            for i in range(3 + 5):
+                flush.zero_()
+                a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                cv32 = ops.warp_variance(feat, sweep, torch.float32)
+                b_.record()
+                torch.cuda.synchronize()
+                if i >= 3:
+                    ts.append(a.elapsed_time(b_))
+                del cv32
+            del flush
+        t32 = sorted(ts)[len(ts) // 2]
+        bytes32 = 4 * B * V * C * h * w + 4 * B * D * h * w * C
+        roofline_k1_fp32 = {"kernel": "warp_variance_fwd2_kernel<V=%d, fp32 volume>" % V, "bound": "hbm",
+                            "achieved": bytes32 / (t32 * 1e-3) / 1e9, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                            "frac": bytes32 / (t32 * 1e-3) / 1e9 / peak, "alg_bytes_per_launch": bytes32, "ms_per_launch": t32,
+                            "voxels_per_s": B * D * h * w / (t32 * 1e-3),
+                            "traffic": _ncu_traffic("r01_k1_fwd2_ncu.json"),
+                            "note": "isolated launches on the step's shapes (B=%d), median of 5, L2 flushed" % B}
     # dominant own kernel by time in the step: the tcgen05 convolution (all its launches of the timed steps together)
     k3 = kern.get("conv3d_s1_tc", {})
     tc_ms = sum(kern[n]["ms_per_step"] for n in TC_KERNELS if n in kern and "alg_flops_per_step" in kern[n])
@@ -346,7 +374,7 @@ def run_b200(args, rank, world, local_rank):
                                           f"after the timed region") if gstep is not None else (graph_note or "off")},
                 "e2e": {"value": e2e_value, "unit": "depth maps/s", "ms_per_step": ms_e2e / args.steps,
                         "h2d_bytes_per_step": img_host.numel() * 4 + gt_host.numel() * 4, "d2h_bytes_per_step": 4},
-                "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "roofline_k1": roofline_k1, "kernels": kern,
+                "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "roofline_k1": roofline_k1, "roofline_k1_fp32": roofline_k1_fp32, "kernels": kern,
                 "cost_volume_voxels_per_s": roofline_k1["voxels_per_s"]}
     return line
 

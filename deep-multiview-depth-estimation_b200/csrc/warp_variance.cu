@@ -420,6 +420,197 @@ warp_variance_fwd_kernel(const float4* __restrict__ feat, const ViewParams* __re
 }
 
 // ------------------------------------------------------------------------------------------------
+// K1 forward, second form ("one offset"): same two phases, fewer instructions per plane and no CTA barrier.
+//   * the 2x2 footprint is addressed from ONE clamped base (xc, yc) in [0, w-2] x [0, h-2]: the taps are base, base + one
+//     voxel row (an immediate), base + one line, base + line + row.  Zero padding and the clamping are folded into the four
+//     weights when the record is made (a footprint hanging over the left/top edge hands its in-bounds weight to the first
+//     tap, over the right/bottom edge to the second), so phase 2 needs one 32-bit byte offset, one compare and two 64-bit
+//     address additions per view instead of four offsets, two compares, eight shifts and eight wide multiply-adds;
+//   * a warp stages the records of ITS four pixels itself (2 records per lane and run at V = 3): __syncwarp instead of
+//     __syncthreads, warps drift apart instead of convoying through phase 1 together;
+//   * V = 3: population variance from the three pairwise differences, ((a-b)^2 + (a-c)^2 + (b-c)^2) / 9 -- algebraically
+//     the two-pass value, no cancellation, 7 packed operations per channel pair instead of 10.
+struct __align__(16) FootRec1 {
+    float w00, w01, w10, w11;     // weights of the taps at base, base+1, base+line, base+line+1
+    int off;                      // byte offset of the base tap inside the view's feature map
+};
+
+__device__ __forceinline__ FootRec1 make_record1(const PixelView& pv, float gx, float gy, float gz, float t, int h, int w) {
+    const float m = pv.c * t;
+    const float qx = fmaf(gx, m, pv.a0), qy = fmaf(gy, m, pv.a1), qz = fmaf(gz, m, pv.a2);
+    const float rz = rcp_approx(qz);
+    float ix = fmaf(qx, rz, -0.5f), iy = fmaf(qy, rz, -0.5f);
+    ix = fminf(fmaxf(ix, -2.0f), (float)(w + 1));   // NaN -> -2: footprint entirely out of bounds
+    iy = fminf(fmaxf(iy, -2.0f), (float)(h + 1));
+    const float fx0 = floorf(ix), fy0 = floorf(iy);
+    const int x0 = (int)fx0, y0 = (int)fy0;
+    const float wx1 = ix - fx0, wy1 = iy - fy0;
+    float ax = ((unsigned)x0 < (unsigned)w) ? 1.0f - wx1 : 0.f, bx = ((unsigned)(x0 + 1) < (unsigned)w) ? wx1 : 0.f;
+    float ay = ((unsigned)y0 < (unsigned)h) ? 1.0f - wy1 : 0.f, by = ((unsigned)(y0 + 1) < (unsigned)h) ? wy1 : 0.f;
+    if (x0 < 0) { ax = bx; bx = 0.f; } else if (x0 > w - 2) { bx = ax; ax = 0.f; }
+    if (y0 < 0) { ay = by; by = 0.f; } else if (y0 > h - 2) { by = ay; ay = 0.f; }
+    const int xc = min(max(x0, 0), w - 2), yc = min(max(y0, 0), h - 2);
+    FootRec1 r;
+    r.w00 = ax * ay; r.w01 = bx * ay; r.w10 = ax * by; r.w11 = bx * by;
+    if (t != t) { r.w00 = NAN; r.w01 = NAN; r.w10 = NAN; r.w11 = NAN; }      // d == 0 plane: the reference's whole plane is NaN
+    r.off = (yc * w + xc) * (kC * 4);
+    return r;
+}
+
+__device__ __forceinline__ void ldg_f4_if_b(float4& t, const char* p, int pred) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %5, 0;\n\t@p ld.global.nc.L1::evict_last.v4.f32 {%0,%1,%2,%3}, [%4];\n\t}"
+                 : "+f"(t.x), "+f"(t.y), "+f"(t.z), "+f"(t.w) : "l"(p), "r"(pred));
+}
+
+// population variance of three samples from their pairwise differences (packed fp32)
+__device__ __forceinline__ float2 variance3_pairwise(float2 a, float2 b, float2 c, float2 ninth) {
+    const float2 nb = make_float2(-b.x, -b.y), nc = make_float2(-c.x, -c.y);
+    const float2 d01 = __fadd2_rn(a, nb), d02 = __fadd2_rn(a, nc), d12 = __fadd2_rn(b, nc);
+    return __fmul2_rn(__ffma2_rn(d12, d12, __ffma2_rn(d02, d02, __fmul2_rn(d01, d01))), ninth);
+}
+
+template <int V>
+struct Fwd2Cfg {
+    static constexpr int kRunV = V <= 4 ? kRun : kRun / 2;
+    static constexpr int kWRec = (V - 1) * kRunV * 4;                                    // records per warp and buffer
+    static constexpr size_t kSmem = (size_t)(kThreads / 32) * 2 * kWRec * (sizeof(float4) + sizeof(int));
+};
+
+template <int V, bool BF16OUT>
+__global__ void __launch_bounds__(kThreads, V <= 3 ? 3 : (V <= 5 ? 2 : 1))
+warp_variance_fwd2_kernel(const float4* __restrict__ feat, const ViewParams* __restrict__ vp, const float* __restrict__ tinv,
+                          void* __restrict__ cost, int D, int h, int w, int dchunk, int tiles_x) {
+    constexpr int RUN = Fwd2Cfg<V>::kRunV, WREC = Fwd2Cfg<V>::kWRec, NW = kThreads / 32;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float4* rec_w = reinterpret_cast<float4*>(smem_raw) + warp * 2 * WREC;              // [buffer][V-1][RUN][4 pixels]
+    int* rec_o = reinterpret_cast<int*>(reinterpret_cast<float4*>(smem_raw) + NW * 2 * WREC) + warp * 2 * WREC;
+
+    const int b = blockIdx.z, d0 = blockIdx.y * dchunk, nd = min(dchunk, D - d0);
+    const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
+    const unsigned plane = (unsigned)h * (unsigned)w;
+    const ViewParams* vpb = vp + (size_t)b * V;
+
+    // ---- phase-1 identity: pixel p4 of this warp's four (fixed per lane: 32 is a multiple of 4)
+    const int slot1 = warp * 4 + (lane & 3);
+    PixelView pv1[V];
+    {
+        const float x1 = (float)(tx * kTX + (slot1 & (kTX - 1))), y1 = (float)(ty * kTY + slot1 / kTX);
+#pragma unroll
+        for (int v = 1; v < V; ++v) pv1[v] = pixel_view(vpb[v], x1, y1);
+    }
+    auto stage_run = [&](int run0, int buf) {
+        const int nrun = min(RUN, nd - run0);
+#pragma unroll
+        for (int i0 = 0; i0 < WREC; i0 += 32) {
+            const int i = i0 + lane;                     // record (v, dd, p4): p4 = i & 3 == lane & 3
+            const int v = i / (RUN * 4) + 1, dd = (i >> 2) % RUN;
+            if (i < WREC && dd < nrun) {
+                PixelView pv = pv1[1];
+#pragma unroll
+                for (int u = 2; u < V; ++u) if (u == v) pv = pv1[u];
+                const ViewParams& q = vpb[v];
+                const FootRec1 r = make_record1(pv, q.g[0], q.g[1], q.g[2], __ldg(tinv + (size_t)(b * V + v) * D + d0 + run0 + dd), h, w);
+                rec_w[buf * WREC + i] = make_float4(r.w00, r.w01, r.w10, r.w11);
+                rec_o[buf * WREC + i] = r.off;
+            }
+        }
+    };
+
+    // ---- phase-2 identity: pixel lane/8 of the warp's four, channels 4*cg .. 4*cg+3
+    const int p4 = lane >> 3, cg = lane & 7;
+    const int pl = warp * 4 + p4;
+    const int px = tx * kTX + (pl & (kTX - 1)), py = ty * kTY + pl / kTX;
+    const bool active = px < w && py < h;
+    const char* fb = reinterpret_cast<const char*>(feat + (size_t)(b * V) * plane * kSlots + cg);
+    const size_t view_bytes = (size_t)plane * kC * 4, line_bytes = (size_t)w * kC * 4;
+
+    stage_run(0, 0);
+
+    float2 ref[2];                                   // reference view: H = I on every plane => one sample per pixel
+    {
+        const PixelView pv = pixel_view(vpb[0], (float)px, (float)py);
+        const FootRec1 r = make_record1(pv, 0.f, 0.f, 0.f, 0.f, h, w);
+        const char* pa = fb + (unsigned)r.off;
+        const float4 t00 = __ldg(reinterpret_cast<const float4*>(pa)), t01 = __ldg(reinterpret_cast<const float4*>(pa + kC * 4)),
+                     t10 = __ldg(reinterpret_cast<const float4*>(pa + line_bytes)),
+                     t11 = __ldg(reinterpret_cast<const float4*>(pa + line_bytes + kC * 4));
+        blend2w(r.w00, r.w01, r.w10, r.w11, t00, t01, t10, t11, ref[0], ref[1]);
+    }
+
+    float4 taps[V][4];
+    int key[V];
+    const char* fv[V];                               // this lane's 16 bytes of every voxel row of view v
+#pragma unroll
+    for (int v = 1; v < V; ++v) {
+        key[v] = -1;
+        fv[v] = fb + (size_t)v * view_bytes;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) taps[v][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const float invV = 1.0f / (float)V;
+    const float2 ninth = make_float2(1.0f / 9.0f, 1.0f / 9.0f);
+    __syncwarp();
+
+    int buf = 0;
+    for (int run0 = 0; run0 < nd; run0 += RUN, buf ^= 1) {
+        const int nrun = min(RUN, nd - run0);
+        if (run0 + RUN < nd) stage_run(run0 + RUN, buf ^ 1);
+        if (active) {
+            size_t vox = ((size_t)(b * D + d0 + run0) * h + py) * w + px;
+            const float4* rw = rec_w + buf * WREC + p4;
+            const int* ro = rec_o + buf * WREC + p4;
+            // (Requesting the taps of plane dd+1 before the variance of plane dd -- a software pipeline -- needs the next
+            // plane's weights live across the blend: 120 registers => 2 CTAs/SM => 217 us instead of 160; with 80 registers
+            // it spills => 390 us.  64 registers / 4 CTAs per SM: 166 us.  Measured, profiles/r01_k1_notes.md.)
+            float4 wt[V];
+            auto fetch = [&](int dd) {
+#pragma unroll
+                for (int v = 1; v < V; ++v) {
+                    wt[v] = rw[((v - 1) * RUN + dd) * 4];
+                    const int of = ro[((v - 1) * RUN + dd) * 4];
+                    const int changed = of != key[v];
+                    key[v] = of;
+                    const char* pa = fv[v] + (unsigned)of;
+                    const char* pb = pa + line_bytes;
+                    ldg_f4_if_b(taps[v][0], pa, changed);
+                    ldg_f4_if_b(taps[v][1], pa + kC * 4, changed);
+                    ldg_f4_if_b(taps[v][2], pb, changed);
+                    ldg_f4_if_b(taps[v][3], pb + kC * 4, changed);
+                }
+            };
+            for (int dd = 0; dd < nrun; ++dd, vox += plane) {
+                float2 val[2][V];
+                val[0][0] = ref[0]; val[1][0] = ref[1];
+                fetch(dd);
+#pragma unroll
+                for (int v = 1; v < V; ++v)
+                    blend2w(wt[v].x, wt[v].y, wt[v].z, wt[v].w, taps[v][0], taps[v][1], taps[v][2], taps[v][3], val[0][v], val[1][v]);
+                float2 r0, r1;
+                if (V == 3) {
+                    const float2 lo = variance3_pairwise(val[0][0], val[0][1], val[0][2], ninth);
+                    const float2 hi = variance3_pairwise(val[1][0], val[1][1], val[1][2], ninth);
+                    r0 = lo; r1 = hi;
+                } else {
+                    float xs[4][V];
+#pragma unroll
+                    for (int v = 0; v < V; ++v) { xs[0][v] = val[0][v].x; xs[1][v] = val[0][v].y; xs[2][v] = val[1][v].x; xs[3][v] = val[1][v].y; }
+                    r0 = make_float2(variance1<V>(xs[0], -invV, invV), variance1<V>(xs[1], -invV, invV));
+                    r1 = make_float2(variance1<V>(xs[2], -invV, invV), variance1<V>(xs[3], -invV, invV));
+                }
+                if (BF16OUT) {
+                    __nv_bfloat16* row = reinterpret_cast<__nv_bfloat16*>(cost) + vox * kC + 4 * cg;
+                    st_cs_u2(row, pack_bf16x2(r0.x, r0.y), pack_bf16x2(r1.x, r1.y));
+                } else {
+                    st_cs_f4(reinterpret_cast<float4*>(cost) + vox * kSlots + cg, make_float4(r0.x, r0.y, r1.x, r1.y));
+                }
+            }
+        }
+        __syncwarp();                                // next buffer staged by every lane, this buffer consumed
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // K2 backward: d cost / d features
 //   d cost / d f_v = (2/V) (f_v - mean) * gcost   (the mean term cancels), chained through the
 //   bilinear taps.  Same two-phase structure as the forward kernel (footprint records in shared memory, 8 lanes per
@@ -695,9 +886,31 @@ FwdPlan make_fwd_plan(int B, int V, int D, int h, int w) {
     return p;
 }
 
+int fwd_form() {                                     // MVSB200_K1=1 selects the first form (four offsets, CTA-staged records)
+    const char* e = getenv("MVSB200_K1");
+    return (e && e[0] == '1') ? 1 : 2;
+}
+
+template <int V>
+int launch_fwd2(const float* feat, const float* vp, const float* tinv, void* cost, int dtype, int B, int D, int h, int w,
+                cudaStream_t st) {
+    FwdPlan p = make_fwd_plan(B, V, D, h, w);
+    p.smem = Fwd2Cfg<V>::kSmem;
+    MVS_REQUIRE(p.grid.y <= 65535 && (long)h * w < (1L << 24), "warp_variance_fwd: volume too large");
+    if (dtype == MVSB200_BF16)
+        warp_variance_fwd2_kernel<V, true><<<p.grid, kThreads, p.smem, st>>>(
+            (const float4*)feat, (const ViewParams*)vp, tinv, cost, D, h, w, p.dchunk, p.tiles_x);
+    else
+        warp_variance_fwd2_kernel<V, false><<<p.grid, kThreads, p.smem, st>>>(
+            (const float4*)feat, (const ViewParams*)vp, tinv, cost, D, h, w, p.dchunk, p.tiles_x);
+    MVS_CHECK_LAUNCH("warp_variance_fwd2");
+    return MVSB200_OK;
+}
+
 template <int V>
 int launch_fwd(const float* feat, const float* vp, const float* tinv, void* cost, int dtype, int B, int D, int h, int w,
                cudaStream_t st) {
+    if (fwd_form() != 1 && h >= 2 && w >= 2 && (long)h * w < (1L << 24)) return launch_fwd2<V>(feat, vp, tinv, cost, dtype, B, D, h, w, st);
     FwdPlan p = make_fwd_plan(B, V, D, h, w);
     p.smem = FwdCfg<V>::kSmem;
     MVS_REQUIRE(p.grid.y <= 65535 && (long)h * w < (1L << 27), "warp_variance_fwd: volume too large");
