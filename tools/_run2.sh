@@ -1,9 +1,3 @@
 export NCCL_DEBUG=WARN
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/run_depth_slab.py --D 64 --H 512 --W 640 --V 3 --reps 3 > gpurun_out/slab2_small.json 2> gpurun_out/slab2_small.err
-echo "rc=$?" >> gpurun_out/slab2_small.err
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 tools/run_depth_slab.py --reps 5 > gpurun_out/slab2_cfg4.json 2> gpurun_out/slab2_cfg4.err
-echo "rc=$?" >> gpurun_out/slab2_cfg4.err
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 2 --workload cfg4 --steps 5 --warmup 3 > gpurun_out/bench_cfg4_slab2.json 2> gpurun_out/bench_cfg4_slab2.err
-echo "rc=$?" >> gpurun_out/bench_cfg4_slab2.err
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29514 bench.py --gpus 2 --steps 5 --warmup 3 > gpurun_out/bench_cfg2_dp2.json 2> gpurun_out/bench_cfg2_dp2.err
-echo "rc=$?" >> gpurun_out/bench_cfg2_dp2.err
+timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29531 tools/run_depth_slab.py --reps 5 --graph > gpurun_out/slab2_graph.json 2> gpurun_out/slab2_graph.err; echo "rc=$?" >> gpurun_out/slab2_graph.err
+timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29532 tools/run_depth_slab.py --reps 5 > gpurun_out/slab2_eager.json 2> gpurun_out/slab2_eager.err; echo "rc=$?" >> gpurun_out/slab2_eager.err

@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--W", type=int, default=1600)
     ap.add_argument("--V", type=int, default=5)
     ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--graph", action="store_true", help="replay the rank's whole forward (kernels + NCCL exchanges) as one CUDA graph")
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -54,6 +55,22 @@ def main():
     for _ in range(2):
         depth, prob_rows, rows = run()
     dist.barrier(); torch.cuda.synchronize()
+    if args.graph:
+        eager = run
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            eager()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize(); dist.barrier()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            captured = eager()
+
+        def run():
+            g.replay()
+            return captured
+        run(); torch.cuda.synchronize(); dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.reps):
@@ -63,7 +80,7 @@ def main():
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     logits_all = [torch.empty((1, 1, b - a, h, w), device=dev) for a, b in SlabPlan(D, world).canvas]
     dist.all_gather(logits_all, sharded.last_logits.contiguous())      # equal slabs when D % (2 world) == 0
-    out = {"world": world, "D": D, "V": V, "h": h, "w": w, "ms_sharded": float(ms.item())}
+    out = {"world": world, "D": D, "V": V, "h": h, "w": w, "ms_sharded": float(ms.item()), "cuda_graph": bool(args.graph)}
     if rank == 0:
         import copy
         reg1 = copy.deepcopy(reg)
