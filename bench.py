@@ -182,7 +182,7 @@ def run_b200(args, rank, world, local_rank):
         img_host = torch.randn(B * V, 3, H, W, generator=g0).pin_memory()
         gt_host = (425.0 + 480.0 * torch.rand(B, 1, h, w, generator=g0)).pin_memory()
         img_dev, gt_dev = img_host.to(dev), gt_host.to(dev)
-        slab = DepthSlabMVSNet(model)
+        slab = DepthSlabMVSNet(model, graph=not args.no_graph)
 
     gstep = None
     if train and not args.no_graph:
@@ -366,7 +366,9 @@ def run_b200(args, rank, world, local_rank):
                 "config": {"workload": wl["desc"], "per_gpu_batch": B, "views": V, "D": D, "features": [C, h, w],
                            "l2": "inputs_exceed_l2 (cost volume %.0f MB per step > 126 MB L2)" % (2 * vox * C / 1e6),
                            "parallelism": (f"depth-slab x{world} (one sample; K1 on own planes + halo, halo/box exchanges and BatchNorm-sum "
-                                           f"all-reduces over NCCL, logits re-sharded to rows for K4)" if slab is not None else
+                                           f"all-reduces over NCCL, logits re-sharded to rows for K4; hot path "
+                                           f"{'replayed as one CUDA graph per rank' if not args.no_graph else 'issued eagerly'})"
+                                           if slab is not None else
                                            f"dp{world} (scene/batch sharding, flat-bucket NCCL grad all-reduce)" if world > 1 else "single GPU"),
                            "regulariser_convs": model.cost_volume_reg.conv_backend,
                            "cuda_graph": (f"forward+loss+backward replayed as one CUDA graph ({gstep.launches} libmvs_b200.so "
@@ -419,13 +421,18 @@ def main():
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     line = run_b200(args, rank, world, local_rank)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args.workload)
         print(json.dumps(line), flush=True)
+    if world > 1:
+        if args.workload == "cfg4" and not args.no_graph:
+            # a replayed graph that holds NCCL work: drain and leave without the collective teardown (it does not return)
+            torch.cuda.synchronize()
+            sys.stdout.flush(); sys.stderr.flush()
+            os._exit(0)
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -433,6 +433,46 @@ class DepthSlabCostVolumeReg:
         return gather_rows(depth_rows, rows, self.comm), prob_rows, rows[self.rank]
 
 
+class GraphedSlabForward:
+    """A rank's whole sharded forward -- K1 on its planes, the regulariser slabs, every NCCL exchange, K4, the depth
+    all-gather -- captured once and replayed as ONE CUDA graph.  At 4-8 ranks a slab's ~250 kernels last tens of
+    microseconds each; issued eagerly the pass is bound by the host (8 GPUs at cfg4: 14.2 ms eager, 4.15 ms replayed; 1 GPU
+    unsharded: 12.2 ms -- profiles/r01_scaling.md).  Inputs live in static buffers: `features` is copied into the graph's own
+    feature tensor, cameras / depth range are re-targeted with `sweep.update(...)`.  Call `release()` before tearing the
+    process group down (a live graph that holds NCCL work blocks the communicator's destruction)."""
+
+    def __init__(self, sharded: "DepthSlabCostVolumeReg", sweep, feature_shape, device, out_dtype=torch.bfloat16, warmup=2):
+        self.sharded, self.sweep, self.out_dtype, self.warmup = sharded, sweep, out_dtype, warmup
+        N, C, h, w = feature_shape
+        self.features = torch.zeros((N, h, w, C), dtype=torch.float32, device=device).permute(0, 3, 1, 2)   # channel-last
+        self.graph, self.out = None, None
+
+    def _run(self):
+        sw = self.sweep
+        return self.sharded.forward(slab_cost_fn(self.features, sw, self.out_dtype), sw.d_batch_dev, sw.B, sw.D, sw.h, sw.w)
+
+    def __call__(self, features):
+        self.features.copy_(features)
+        if self.graph is None:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(self.warmup):           # lazy workspaces, NCCL connections, tile plans -- outside the capture
+                    self._run()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.out = self._run()
+            self.graph = g
+        self.graph.replay()
+        return self.out
+
+    def release(self):
+        self.graph, self.out = None, None
+        torch.cuda.synchronize()
+
+
 def slab_cost_fn(feature_maps: torch.Tensor, sweep: "ops.PlaneSweep", out_dtype=torch.bfloat16):
     """cost_fn for DepthSlabCostVolumeReg: K1 on a plane range of a full sweep (every rank holds all V feature maps and
     the whole 1/(d - s) table; it launches the fused kernel on the planes it needs)."""

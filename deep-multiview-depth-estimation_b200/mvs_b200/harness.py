@@ -171,11 +171,19 @@ class DepthSlabMVSNet:
     (view v on rank v mod R) and broadcast -- every rank needs all V feature maps (75.8 MB at 5 x 400x296x32) for the sweep
     of its planes.  Wraps an MVSNet whose parameters are identical on every rank."""
 
-    def __init__(self, model: "MVSNet", comm=None):
+    def __init__(self, model: "MVSNet", comm=None, graph=False):
+        """graph: replay the sharded hot path (kernels + NCCL exchanges) as one CUDA graph per rank (fixed shapes); call
+        release() before destroying the process group."""
         from .depth_slab import DepthSlabCostVolumeReg, TorchDistComm
         self.model = model
         self.comm = TorchDistComm() if comm is None else comm
         self.reg = DepthSlabCostVolumeReg(model.cost_volume_reg, self.comm)
+        self.use_graph, self._graphed, self._sweep = bool(graph), None, None
+
+    def release(self):
+        if self._graphed is not None:
+            self._graphed.release()
+            self._graphed = None
 
     @torch.no_grad()
     def encode(self, nn_input, by_view=None):
@@ -207,9 +215,19 @@ class DepthSlabMVSNet:
         m = self.model
         feats = self.encode(nn_input)
         h, w = feats.shape[-2:]
-        sweep = ops.PlaneSweep(K_batch, R_batch, T_batch, d_min, d_int, 1, n_views, m.d_num, m.d_scale, h, w, feats.device)
         vol_dtype = torch.bfloat16 if m.precision == "bf16" else torch.float32
-        initial, prob_rows, rows = self.reg.forward(slab_cost_fn(feats, sweep, vol_dtype), sweep.d_batch_dev, 1, m.d_num, h, w)
+        if self.use_graph:
+            from .depth_slab import GraphedSlabForward
+            if self._sweep is None:
+                self._sweep = ops.PlaneSweep(K_batch, R_batch, T_batch, d_min, d_int, 1, n_views, m.d_num, m.d_scale, h, w, feats.device)
+                self._graphed = GraphedSlabForward(self.reg, self._sweep, tuple(feats.shape), feats.device, vol_dtype)
+            else:
+                self._sweep.update(K_batch, R_batch, T_batch, d_min, d_int)
+            sweep = self._sweep
+            initial, prob_rows, rows = self._graphed(feats)
+        else:
+            sweep = ops.PlaneSweep(K_batch, R_batch, T_batch, d_min, d_int, 1, n_views, m.d_num, m.d_scale, h, w, feats.device)
+            initial, prob_rows, rows = self.reg.forward(slab_cost_fn(feats, sweep, vol_dtype), sweep.d_batch_dev, 1, m.d_num, h, w)
         dev = initial.device
         d_trans, d_span = d_min.to(dev), d_int.to(dev) * m.d_num * m.d_scale
         norm = (initial - d_trans) / d_span

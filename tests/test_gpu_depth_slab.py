@@ -235,3 +235,41 @@ def test_depth_slab_mvsnet_wrapper(monkeypatch):
         assert initial.shape == (1, 1, H // 4, W // 4) and refined.shape == initial.shape
         assert torch.equal(initial, outs[0][1][0]) and torch.isfinite(refined).all()
         assert float(initial.min()) >= 425.0 - 1e-3 and float(initial.max()) <= 425.0 + 480.0
+
+
+def test_graphed_slab_forward_replays():
+    """depth_slab.GraphedSlabForward: the rank's forward captured as one CUDA graph gives the eager result, also after the
+    features and the cameras change between replays (one rank here; the NCCL capture is exercised by tools/run_depth_slab.py
+    --graph and bench.py --workload cfg4 --gpus N)."""
+    import copy
+    import mvs_b200
+    import plane_sweep as ps
+    from mvs_b200.depth_slab import DepthSlabCostVolumeReg, GraphedSlabForward, slab_cost_fn
+    B, V, D, h, w = 1, 3, 32, 24, 40
+    reg, feat, sweep = _setup(B, V, D, h, w, "bf16", True)
+    twin = copy.deepcopy(reg)
+
+    def rank_fn(comm):
+        sharded = DepthSlabCostVolumeReg(reg, comm)
+        eager = DepthSlabCostVolumeReg(twin, comm)
+        graphed = GraphedSlabForward(sharded, sweep, tuple(feat.shape), feat.device, torch.bfloat16, warmup=1)
+        outs = []
+        for it in range(3):
+            torch.manual_seed(10 + it)
+            f = torch.randn_like(feat)
+            K, R, T = ps.synthetic_cameras(B, V, h, w, seed=it)
+            sweep.update(K, R, T, torch.full((B, 1, 1, 1), 425.0 + 10 * it), torch.ones(B, 1, 1, 1))
+            n0 = mvs_b200.launch_count()
+            depth, prob_rows, rows = graphed(f)
+            torch.cuda.synchronize()
+            if it > 0:
+                assert mvs_b200.launch_count() == n0                 # a replay issues no C-ABI call
+            d2, p2, _ = eager.forward(slab_cost_fn(f, sweep, torch.bfloat16), sweep.d_batch_dev, B, D, h, w)
+            outs.append((depth.clone(), prob_rows.clone(), d2, p2))
+        graphed.release()
+        return outs
+
+    (outs,) = _run_ranks(1, rank_fn)
+    for depth, prob, d2, p2 in outs:
+        assert float((prob - p2).abs().max()) < 2e-2 * float(p2.abs().max())
+        assert float(((depth - d2).abs() < 0.05 * 480.0 / D).float().mean()) > 0.97

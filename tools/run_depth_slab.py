@@ -103,6 +103,13 @@ def main():
                     "depth_within_5pct_step": float(((depth - ref_depth).abs() < 0.05 * step).float().mean()),
                     "depth_median_abs_err_steps": float((depth - ref_depth).abs().median() / step)})
         print(json.dumps(out), flush=True)
+    if args.graph:
+        # a live graph that holds NCCL work keeps the communicator busy in its teardown: drop it, drain the device, and leave
+        # without the collective destroy (observed: destroy_process_group() after a captured forward does not return)
+        del run, captured, g
+        torch.cuda.synchronize()
+        sys.stdout.flush(); sys.stderr.flush()
+        os._exit(0)
     dist.barrier()
     dist.destroy_process_group()
 
