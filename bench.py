@@ -115,7 +115,7 @@ def run_reference(args, rank, world):
     import torch
     import cpu_path
     wl = WORKLOADS[args.workload]
-    d_sample = 24
+    d_sample = 48
     torch.set_num_threads(os.cpu_count() or 1)
     s = cpu_path.make_sample(V=wl["V"], D=d_sample, h=wl["H"] // 4, w=wl["W"] // 4, d_total=wl["D"])
     for _ in range(args.warmup):
@@ -386,7 +386,7 @@ def cpu_baseline(workload):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import cpu_path
     wl = WORKLOADS[workload]
-    d_sample = 48
+    d_sample = min(wl["D"], 96)                      # ~10-20 s of CPU work on 16 cores (48 planes: 3.1 s)
     torch.set_num_threads(os.cpu_count() or 1)
     s = cpu_path.make_sample(V=wl["V"], D=d_sample, h=wl["H"] // 4, w=wl["W"] // 4, d_total=wl["D"])
     dt, _ = cpu_path.hot_path_step(s, backward=wl["train"])

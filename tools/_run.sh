@@ -1,3 +1,4 @@
-python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bench_for_ncu2.json 2> gpurun_out/bench_for_ncu2.err && \
-ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/launches_r01c.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launches2.log 2>&1
-echo "rc=$?" >> gpurun_out/ncu_launches2.log
+( time python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err ) 2> gpurun_out/bench_default.time; echo "rc=$?" >> gpurun_out/bench_default.err
+( time python bench.py --impl reference > gpurun_out/bench_default_ref.json 2> gpurun_out/bench_default_ref.err ) 2> gpurun_out/bench_default_ref.time; echo "rc=$?" >> gpurun_out/bench_default_ref.err
+( time python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1 ) 2> gpurun_out/smoke.time
+nproc > gpurun_out/nproc.txt
