@@ -386,7 +386,9 @@ def cpu_baseline(workload):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import cpu_path
     wl = WORKLOADS[workload]
-    d_sample = min(wl["D"], 96)                      # ~10-20 s of CPU work on 16 cores (48 planes: 3.1 s)
+    # cfg1/cfg2: the whole D = 192 sweep of one batch item (~13 s on 16 cores, nothing extrapolated); cfg4: 24 of 256 planes
+    # (the reference materialises 19 GB of warped volumes at cfg4)
+    d_sample = wl["D"] if wl["H"] * wl["W"] <= 512 * 640 else 24
     torch.set_num_threads(os.cpu_count() or 1)
     s = cpu_path.make_sample(V=wl["V"], D=d_sample, h=wl["H"] // 4, w=wl["W"] // 4, d_total=wl["D"])
     dt, _ = cpu_path.hot_path_step(s, backward=wl["train"])

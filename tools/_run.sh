@@ -1,4 +1,2 @@
-( time python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err ) 2> gpurun_out/bench_default.time; echo "rc=$?" >> gpurun_out/bench_default.err
-( time python bench.py --impl reference > gpurun_out/bench_default_ref.json 2> gpurun_out/bench_default_ref.err ) 2> gpurun_out/bench_default_ref.time; echo "rc=$?" >> gpurun_out/bench_default_ref.err
-( time python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1 ) 2> gpurun_out/smoke.time
-nproc > gpurun_out/nproc.txt
+for i in 1 2 3; do timeout 600 python -m pytest tests -m gpu -q -x 2>&1 | tail -1 >> gpurun_out/pytest_gpu_rep.log; done
+timeout 300 python bench.py --steps 5 --warmup 3 > gpurun_out/bench18.json 2> gpurun_out/bench18.err; echo "rc=$?" >> gpurun_out/bench18.err
