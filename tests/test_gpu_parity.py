@@ -250,6 +250,39 @@ def test_cost_volume_against_live_oracle(B, V, D, h, w):
     assert _relmax(cost.cpu().numpy(), ref.numpy()) < 1e-4
 
 
+@pytest.mark.parametrize("form", ["2", "1"])
+@pytest.mark.parametrize("V,D,h,w,d0,shift", [(3, 12, 13, 21, 150.0, 0.0), (4, 10, 9, 7, 120.0, 30.0), (2, 16, 2, 2, 425.0, 0.0),
+                                              (5, 6, 31, 17, 80.0, -25.0)])
+def test_cost_volume_with_footprints_hanging_over_every_edge(V, D, h, w, d0, shift, form, monkeypatch):
+    """Both forms of the forward kernel (MVSB200_K1=2: one clamped base offset per footprint with the padding and clamping
+    folded into the weights; =1: four clamped offsets) on sweeps whose sampling positions leave the image on every side:
+    near planes (large disparity) and a shifted principal point; tiny and odd-sized maps.  Also the backward of the same
+    sweep against the oracle's autograd."""
+    monkeypatch.setenv("MVSB200_K1", form)
+    gen = torch.Generator().manual_seed(V * 100 + D + h)
+    K, R, T = ps.synthetic_cameras(1, V, h, w, seed=V)
+    K = K.clone()
+    K[1:, 0, 2] += shift * w / 160.0                                   # source principal points off-centre
+    K[1:, 1, 2] -= shift * h / 128.0
+    d_min, d_int = torch.full((1, 1, 1, 1), d0), torch.ones(1, 1, 1, 1)
+    feat = torch.randn(V, 32, h, w, generator=gen)
+    d_scale = 40.0
+    fo = feat.clone().requires_grad_(True)
+    ref, _, _ = ps.plane_sweep_cost(fo, K, R, T, d_min, d_int, 1, V, D, d_scale, sampler="torch")
+    g = torch.randn(ref.shape, generator=gen)
+    (ref * g).sum().backward()
+    fg = feat.to(DEV).requires_grad_(True)
+    warped, _, _ = mvs_b200.homography_warping(K, R, T, d_min, d_int, fg, 1, V, D, d_scale)
+    cost = mvs_b200.assemble_cost_volume(warped, V)
+    (cost * g.to(DEV)).sum().backward()
+    refn = ref.detach().numpy()
+    vols = warped.materialize()                                         # [V,32,D,h,w]: zero rows = samples outside the image
+    outside = float((vols[1:].abs().amax(1) == 0).float().mean())
+    assert outside > 0.02 or h * w <= 4, outside                        # the case really has out-of-image samples
+    assert _relmax(cost.detach().cpu().numpy(), refn) < 1e-4
+    assert _relmax(fg.grad.cpu().numpy(), fo.grad.numpy()) < 1e-4
+
+
 def test_bad_arguments_raise():
     K, R, T = ps.synthetic_cameras(1, 3, 8, 8)
     d_min, d_int = torch.full((1, 1, 1, 1), 425.0), torch.ones(1, 1, 1, 1)

@@ -1,2 +1,1 @@
-for i in 1 2 3; do timeout 600 python -m pytest tests -m gpu -q -x 2>&1 | tail -1 >> gpurun_out/pytest_gpu_rep.log; done
-timeout 300 python bench.py --steps 5 --warmup 3 > gpurun_out/bench18.json 2> gpurun_out/bench18.err; echo "rc=$?" >> gpurun_out/bench18.err
+timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "hanging" > gpurun_out/pytest_edges.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_edges.log
