@@ -92,8 +92,7 @@ class _Conv3dS1(torch.autograd.Function):
                 B, _, Do, Ho, Wo = gy.shape
                 gy16 = torch.empty((B, 16, Do, Ho, Wo), dtype=torch.bfloat16, device=gy.device,
                                    memory_format=torch.channels_last_3d)
-                gy16[:, :8] = gy
-                gy16[:, 8:] = 0
+                _lib.call("mvsb200_widen_rows_8to16_bf16", gy.data_ptr(), gy16.data_ptr(), B * Do * Ho * Wo, _stream())
                 w16 = torch.zeros((16,) + tuple(w.shape[1:]), dtype=w.dtype, device=w.device)
                 w16[:8] = w.detach()
                 gx = _launch(gy16, pack_filter_dgrad(w16), cin, tuple(x_cl.shape[2:]), off)
