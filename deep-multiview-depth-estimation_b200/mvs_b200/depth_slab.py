@@ -342,22 +342,25 @@ class DepthSlabCostVolumeReg:
         cv = cv if cv.dtype == dt else cv.to(dt)
         cv = cv.contiguous(memory_format=_CL)
 
-        # ---- conv_0_0 + BN_0 on the canvas slab
+        # ---- conv_0_0 on the canvas slab and the three stride-2 branches on box planes [ja, jb), both from the cost volume
         d0, d1 = plan.conv0_input(r)
         y0_raw = be.conv3d(cv[:, :, d0 - k0:d1 - k0], W_("conv_0_0"), 1, (1, 1, 1))
         own = y0_raw[:, :, a - d0:b - d0]
-        mean, var = self._moments(self._allsum(_sums(own)), n_full) if train else (None, None)
-        scale, shift = reg._bn_affine(reg.BN_0, mean, var, n_full)
-        y0 = _affine_geo(y0_raw, scale, shift, (d0, 0, 0), (a, 0, 0), (b - a, h, w))
-
-        # ---- the three stride-2 branches from the cost volume, on box planes [ja, jb)
         c0, c1, g, n_out = plan.s2_input(r)
         w_cat = torch.cat([W_(f"conv_{k}_0") for k in (1, 2, 3)], 0)
+        widths = [reg.conv_1_0.out_channels, reg.conv_2_0.out_channels, reg.conv_3_0.out_channels]
         S_all = _s2_box(be, cv[:, :, c0 - k0:c1 - k0], w_cat, tuple(L for _, _, L in rg),
                         (n_out,) + tuple(hi - lo + 1 for lo, hi, _ in rg[1:]))[:, :, g:]
         del cv
-        S_split = dict(zip((1, 2, 3), torch.split(S_all, [reg.conv_1_0.out_channels, reg.conv_2_0.out_channels,
-                                                          reg.conv_3_0.out_channels], 1)))
+        S_parts = torch.split(S_all, widths, 1)
+        # ONE all-reduce for the statistics of BN_0(conv_0_0) and of the three branch outputs (they are independent)
+        if train:
+            st = self._allsum(torch.cat([_sums(own)] + [_sums(S) for S in S_parts], 1))
+            st = torch.split(st, [own.shape[1]] + widths, 1)
+        mean, var = self._moments(st[0], n_full) if train else (None, None)
+        scale, shift = reg._bn_affine(reg.BN_0, mean, var, n_full)
+        y0 = _affine_geo(y0_raw, scale, shift, (d0, 0, 0), (a, 0, 0), (b - a, h, w))
+
         # in-plane geometry exactly as regulariser.py: C (box), E = C+1 ring, F = C+2 ring, clipped to the canvas
         C_lo = [lo for lo, _, _ in rg]
         C_dims = [hi - lo + 1 for lo, hi, _ in rg]
@@ -369,26 +372,32 @@ class DepthSlabCostVolumeReg:
         xa, xb, zlo, zhi = plan.x_range(r)
         zpad = [1 if E_lo[2] == 0 else 0, 1 if E_hi[2] == w - 1 else 0,
                 1 if E_lo[1] == 0 else 0, 1 if E_hi[1] == h - 1 else 0, zlo, zhi]
-        enc = {}
-        for k, bn in ((1, reg.BN_1), (2, reg.BN_2), (3, reg.BN_3)):
-            S = S_split[k]
-            Wk = W_(f"conv_{k}_1")
-            mean, var = self._moments(self._allsum(_sums(S)), n_full) if train else (None, None)
+        # ONE halo exchange for the three branches (they are channel groups of one tensor)
+        S_ext_parts = torch.split(reslab(S_all, plan.box, [plan.s_halo(q) for q in range(R)], self.comm), widths, 1)
+        bns = (reg.BN_1, reg.BN_2, reg.BN_3)
+        Ts, bgs = [], []
+        for idx, (k, bn) in enumerate(zip((1, 2, 3), bns)):
+            mean, var = self._moments(st[1 + idx], n_full) if train else (None, None)
             scale, shift = reg._bn_affine(bn, mean, var, n_full)
-            bg = F.relu(shift)
-            S_ext = reslab(S, plan.box, [plan.s_halo(q) for q in range(R)], self.comm)
-            X = _affine_geo(S_ext, scale, shift, (plan.lo + sa, C_lo[1], C_lo[2]), (plan.lo + xa, F_lo[1], F_lo[2]),
+            bgs.append(F.relu(shift))
+            X = _affine_geo(S_ext_parts[idx], scale, shift, (plan.lo + sa, C_lo[1], C_lo[2]), (plan.lo + xa, F_lo[1], F_lo[2]),
                             (xb - xa, F_hi[1] - F_lo[1] + 1, F_hi[2] - F_lo[2] + 1))
             if any(zpad):
                 X = F.pad(X, zpad)
             X = (X if X.dtype == dt else X.to(dt)).contiguous(memory_format=_CL)
-            T = be.conv3d(X, Wk, 1, (0, 0, 0))                                        # planes [ta, tb) x E_h x E_w
+            Ts.append(be.conv3d(X, W_(f"conv_{k}_1"), 1, (0, 0, 0)))                   # planes [ta, tb) x E_h x E_w
+        if train:                                                                     # ONE all-reduce for the three conv_k_1 outputs
+            tt = torch.split(self._allsum(torch.cat([_sums(T) for T in Ts], 1)), widths, 1)
+        enc = {}
+        for idx, (k, bn) in enumerate(zip((1, 2, 3), bns)):
+            mean = var = None
             if train:
-                t = self._allsum(_sums(T))
-                mean, var = reg._stats_from_sums_with_constant_outside(t[0], t[1], Wk.float(), bg, dims, E_lo, E_hi, B, n_full)
-            scale, shift = reg._bn_affine(bn, mean if train else None, var if train else None, n_full)
-            enc[k] = _affine_geo(T, scale, shift, (plan.lo + ta, E_lo[1], E_lo[2]), (plan.lo + ja, C_lo[1], C_lo[2]),
+                mean, var = reg._stats_from_sums_with_constant_outside(tt[idx][0], tt[idx][1], W_(f"conv_{k}_1").float(), bgs[idx],
+                                                                       dims, E_lo, E_hi, B, n_full)
+            scale, shift = reg._bn_affine(bn, mean, var, n_full)
+            enc[k] = _affine_geo(Ts[idx], scale, shift, (plan.lo + ta, E_lo[1], E_lo[2]), (plan.lo + ja, C_lo[1], C_lo[2]),
                                  (jb - ja, C_dims[1], C_dims[2]))
+        del Ts
 
         # ---- decoder: transposed convolutions from box planes to canvas planes
         Lhw = (rg[1][2], rg[2][2])

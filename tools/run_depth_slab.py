@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--W", type=int, default=1600)
     ap.add_argument("--V", type=int, default=5)
     ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--profile", action="store_true", help="torch.profiler table of one eager pass on rank 0 (to stderr)")
     ap.add_argument("--graph", action="store_true", help="replay the rank's whole forward (kernels + NCCL exchanges) as one CUDA graph")
     args = ap.parse_args()
     import torch
@@ -55,6 +56,13 @@ def main():
     for _ in range(2):
         depth, prob_rows, rows = run()
     dist.barrier(); torch.cuda.synchronize()
+    if args.profile:
+        from torch.profiler import profile, ProfilerActivity
+        with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+            run(); torch.cuda.synchronize()
+        if rank == 0:
+            sys.stderr.write(prof.key_averages().table(sort_by="cuda_time_total", row_limit=45, max_name_column_width=70) + "\n")
+        dist.barrier()
     if args.graph:
         eager = run
         side = torch.cuda.Stream()
@@ -84,17 +92,26 @@ def main():
     if rank == 0:
         import copy
         reg1 = copy.deepcopy(reg)
+        def single():
+            cost = ops.warp_variance(feat, sweep, torch.bfloat16)
+            lg = reg1.logits(cost, mvs_b200.conv3d.get(reg1.conv_backend))
+            return (lg,) + tuple(ops.softmax_depth(lg, sweep.d_batch_dev, 5))
+
         with torch.no_grad():
             for _ in range(2):
-                cost = ops.warp_variance(feat, sweep, torch.bfloat16)
-                ref_logits = reg1.logits(cost, mvs_b200.conv3d.get(reg1.conv_backend))
-                ref_prob, ref_depth = ops.softmax_depth(ref_logits, sweep.d_batch_dev, 5)
+                ref_logits, ref_prob, ref_depth = single()
             torch.cuda.synchronize()
+            run1 = single
+            if args.graph:                              # the unsharded pass replayed as a graph too: like for like
+                g1 = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g1):
+                    held = single()
+                ref_logits, ref_prob, ref_depth = held
+                run1 = g1.replay
+                run1(); torch.cuda.synchronize()
             e0.record()
             for _ in range(args.reps):
-                cost = ops.warp_variance(feat, sweep, torch.bfloat16)
-                ref_logits = reg1.logits(cost, mvs_b200.conv3d.get(reg1.conv_backend))
-                ref_prob, ref_depth = ops.softmax_depth(ref_logits, sweep.d_batch_dev, 5)
+                run1()
             e1.record(); torch.cuda.synchronize()
         logits = torch.cat(logits_all, 2)
         step = 480.0 / D
