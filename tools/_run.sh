@@ -1,1 +1,1 @@
-timeout 600 python -m pytest tests/test_gpu_depth_slab.py -m gpu -q -x > gpurun_out/pytest_slab.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_slab.log
+timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench20.json 2> gpurun_out/bench20.err; echo "rc=$?" >> gpurun_out/bench20.err
