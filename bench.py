@@ -152,6 +152,8 @@ def run_b200(args, rank, world, local_rank):
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    if os.environ.get("MVSB200_CUDNN_BENCHMARK", "1") == "1":
+        torch.backends.cudnn.benchmark = True              # library convolutions (2D nets, strided 3D backward): autotuned plans
     wl = WORKLOADS[args.workload]
     B, V, H, W, D, train = wl["B"], wl["V"], wl["H"], wl["W"], wl["D"], wl["train"]
     h, w, C = H // 4, W // 4, 32
@@ -391,6 +393,7 @@ def run_b200(args, rank, world, local_rank):
                                            if slab is not None else
                                            f"dp{world} (scene/batch sharding, flat-bucket NCCL grad all-reduce)" if world > 1 else "single GPU"),
                            "regulariser_convs": model.cost_volume_reg.conv_backend,
+                           "cudnn_benchmark": bool(torch.backends.cudnn.benchmark),
                            "cuda_graph": (f"forward+loss+backward replayed as one CUDA graph ({gstep.launches} libmvs_b200.so "
                                           f"launches per replay); per-kernel timings from {args.steps} eager steps run right "
                                           f"after the timed region") if gstep is not None else (graph_note or "off")},

@@ -1,1 +1,1 @@
-timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench20.json 2> gpurun_out/bench20.err; echo "rc=$?" >> gpurun_out/bench20.err
+timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench21.json 2> gpurun_out/bench21.err; echo "rc=$?" >> gpurun_out/bench21.err
