@@ -1,10 +1,17 @@
-"""tcgen05 convolution backend of the regulariser (K3): stride-1 3x3x3 convolutions of bf16 channel-last volumes run in
-libmvs_b200.so's implicit-GEMM kernel (csrc/conv3d_tc.cu) -- forward AND the data gradient, which for a stride-1
-convolution is the same convolution with the flipped, transposed filter.  Everything the kernel does not cover yet
-(stride-2 branches, transposed convolutions, 8- and 1-channel operands, the weight gradient, fp32 volumes) goes to
-the cuDNN backend; DESIGN.md §K3 lists which layer runs where.
+"""tcgen05 convolution backend of the regulariser (K3): 3x3x3 convolutions of bf16 channel-last volumes on the implicit-GEMM
+kernels of libmvs_b200.so (csrc/conv3d_tc.cu).
 
-Reference layers: scripts/model.py:223-234 (Conv3d factory), :101-113 (their use).
+  stride 1 (conv_0_0, conv_{1,2,3}_1)      forward and data gradient: conv3d_s1_kdn_kernel (depth tap folded into the MMA N
+                                           extent; MVSB200_CONV_S1=taps selects the one-MMA-per-tap kernel); weight gradient:
+                                           conv3d_s1_wgrad_tc_kernel
+  stride 2 (conv_{1,2,3}_0, stacked)       forward: conv3d_s2_tc_kernel; gradients: library (a tcgen05 strided weight gradient is
+                                           opt-in, MVSB200_S2_WGRAD=tcgen05)
+  stride-2 transposed (deconv_{3,2,1}_0)   forward: deconv3d_s2_tc_kernel (one launch; MVSB200_DECONV=classes selects one launch
+                                           per output-parity class); data gradient: conv3d_s2_tc_kernel; weight gradient: library
+Operands the kernels do not take (8- and 1-channel rows, fp32 volumes) go to the cuDNN backend; DESIGN.md §4 lists which
+layer runs where.
+
+Reference layers: scripts/model.py:223-234 (Conv3d / ConvTranspose3d factories), :101-121 (their use).
 """
 from __future__ import annotations
 
@@ -218,8 +225,8 @@ def s2_wgrad(big, small, pads):
 
 
 class _ConvTranspose3dS2(torch.autograd.Function):
-    """Forward on the tcgen05 kernel; the two gradients are a stride-2 convolution of the output gradient and its
-    weight gradient (library kernels until the stride-2 tcgen05 kernels exist)."""
+    """Forward on the one-launch tcgen05 kernel; the data gradient is a stride-2 convolution of the output gradient
+    (conv3d_s2_tc_kernel), the weight gradient goes to the library (or, opt-in, to the tcgen05 strided kernel)."""
 
     @staticmethod
     def forward(ctx, x, w, pads, out_dims):

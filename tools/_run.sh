@@ -1,1 +1,1 @@
-timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench21.json 2> gpurun_out/bench21.err; echo "rc=$?" >> gpurun_out/bench21.err
+timeout 300 python tools/profile_step.py --rows 70 > gpurun_out/prof_step_b4_r4.txt 2>&1

@@ -21,6 +21,7 @@ ap.add_argument("--rows", type=int, default=45)
 ap.add_argument("--shapes", action="store_true")
 a = ap.parse_args()
 dev = "cuda:0"
+torch.backends.cudnn.benchmark = True
 B, V, H, W, D = a.B, 3, 512, 640, a.D
 torch.manual_seed(0)
 model = MVSNet(D, 480.0 / D, precision=a.precision).to(dev).train()
