@@ -24,12 +24,14 @@ constexpr int kMaxCA = 64;
 struct View {                 // a [B, C, D, h, w] view with unit channel stride; strides in elements
     long long sb, sd, sh, sw;
     int B, D, h, w;
+    FastDiv fD, fh, fw;       // the extents as division constants (common.cuh)
 };
 struct Geo {
     View in;                  // x
     int io[3];                // origin of the input box in the common frame
     int oo[3];                // origin of the output box
     int od[3];                // size of the output box (D, h, w)
+    FastDiv fod[3];
 };
 
 __device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
@@ -52,11 +54,13 @@ __device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&v)[8]) {
 }
 
 // dense row index -> coordinates (32-bit arithmetic: rows < 2^31 is checked on the host)
-__device__ __forceinline__ void decode_row(unsigned r, int D, int h, int w, int& b, int& d, int& y, int& x) {
-    x = (int)(r % (unsigned)w); r /= (unsigned)w;
-    y = (int)(r % (unsigned)h); r /= (unsigned)h;
-    d = (int)(r % (unsigned)D);
-    b = (int)(r / (unsigned)D);
+__device__ __forceinline__ void decode_row(unsigned r, const FastDiv& fD, const FastDiv& fh, const FastDiv& fw, int& b, int& d,
+                                           int& y, int& x) {
+    unsigned ux, uy, ud;
+    r = fd_divmod(r, fw, ux);
+    r = fd_divmod(r, fh, uy);
+    b = (int)fd_divmod(r, fD, ud);
+    x = (int)ux; y = (int)uy; d = (int)ud;
 }
 
 __device__ __forceinline__ void reduce_to_partial(float (&a)[8], float (&b)[8], int cpr, int C, float* partial_row) {
@@ -109,11 +113,12 @@ __global__ void __launch_bounds__(kThreadsA) channel_sums_kernel(const T* __rest
                                                                  float* __restrict__ partials) {
     const int cpr = C / 8;
     const unsigned i0 = blockIdx.x * kThreadsA + threadIdx.x;
-    const int cg = (int)(i0 % (unsigned)cpr);
+    const int cshift = cpr == 1 ? 0 : (cpr == 2 ? 1 : (cpr == 4 ? 2 : 3));
+    const int cg = (int)(i0 & (unsigned)(cpr - 1));
     float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (unsigned i = i0; i < n_chunks; i += gridDim.x * kThreadsA) {
         int b, d, y, xx;
-        decode_row(i / (unsigned)cpr, v.D, v.h, v.w, b, d, y, xx);
+        decode_row(i >> cshift, v.fD, v.fh, v.fw, b, d, y, xx);
         float val[8];
         load8(x + b * v.sb + d * v.sd + y * v.sh + xx * v.sw + cg * 8, val);
 #pragma unroll
@@ -128,13 +133,14 @@ __global__ void __launch_bounds__(kThreadsA) channel_sums_bwd_kernel(const T* __
                                                                      T* __restrict__ gx) {
     const int cpr = C / 8;
     const unsigned i0 = blockIdx.x * kThreadsA + threadIdx.x;
-    const int cg = (int)(i0 % (unsigned)cpr);
+    const int cshift = cpr == 1 ? 0 : (cpr == 2 ? 1 : (cpr == 4 ? 2 : 3));
+    const int cg = (int)(i0 & (unsigned)(cpr - 1));
     float a[8], b2[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) { a[k] = g1[cg * 8 + k]; b2[k] = 2.f * g2[cg * 8 + k]; }
     for (unsigned i = i0; i < n_chunks; i += gridDim.x * kThreadsA) {
         int b, d, y, xx;
-        decode_row(i / (unsigned)cpr, v.D, v.h, v.w, b, d, y, xx);
+        decode_row(i >> cshift, v.fD, v.fh, v.fw, b, d, y, xx);
         float val[8];
         load8(x + b * v.sb + d * v.sd + y * v.sh + xx * v.sw + cg * 8, val);
 #pragma unroll
@@ -162,13 +168,14 @@ __global__ void __launch_bounds__(kThreadsA) affine_relu_geo_fwd_kernel(const T*
                                                                         const float* __restrict__ shift, T* __restrict__ y, int relu) {
     const int cpr = C / 8;
     const unsigned i0 = blockIdx.x * kThreadsA + threadIdx.x;
-    const int cg = (int)(i0 % (unsigned)cpr);
+    const int cshift = cpr == 1 ? 0 : (cpr == 2 ? 1 : (cpr == 4 ? 2 : 3));
+    const int cg = (int)(i0 & (unsigned)(cpr - 1));
     float sc[8], sh[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) { sc[k] = scale[cg * 8 + k]; sh[k] = shift[cg * 8 + k]; }
     for (unsigned i = i0; i < n_out_chunks; i += gridDim.x * kThreadsA) {
         int b, d, yy, xx;
-        decode_row(i / (unsigned)cpr, g.od[0], g.od[1], g.od[2], b, d, yy, xx);
+        decode_row(i >> cshift, g.fod[0], g.fod[1], g.fod[2], b, d, yy, xx);
         float val[8];
         load_in(x, g, b, d, yy, xx, cg, val);
 #pragma unroll
@@ -189,14 +196,15 @@ __global__ void __launch_bounds__(kThreadsA) affine_relu_geo_bwd_reduce_kernel(c
                                                                                float* __restrict__ partials) {
     const int cpr = C / 8;
     const unsigned i0 = blockIdx.x * kThreadsA + threadIdx.x;
-    const int cg = (int)(i0 % (unsigned)cpr);
+    const int cshift = cpr == 1 ? 0 : (cpr == 2 ? 1 : (cpr == 4 ? 2 : 3));
+    const int cg = (int)(i0 & (unsigned)(cpr - 1));
     float sc[8], sh[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) { sc[k] = scale[cg * 8 + k]; sh[k] = shift[cg * 8 + k]; }
     float sg[8] = {0, 0, 0, 0, 0, 0, 0, 0}, sgx[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (unsigned i = i0; i < n_out_chunks; i += gridDim.x * kThreadsA) {
         int b, d, yy, xx;
-        decode_row(i / (unsigned)cpr, g.od[0], g.od[1], g.od[2], b, d, yy, xx);
+        decode_row(i >> cshift, g.fod[0], g.fod[1], g.fod[2], b, d, yy, xx);
         float val[8], gv[8];
         load_in(x, g, b, d, yy, xx, cg, val);
         load8(gy + (size_t)i * 8, gv);
@@ -219,13 +227,14 @@ __global__ void __launch_bounds__(kThreadsA) affine_relu_geo_bwd_dx_kernel(const
                                                                            T* __restrict__ gx) {
     const int cpr = C / 8;
     const unsigned i0 = blockIdx.x * kThreadsA + threadIdx.x;
-    const int cg = (int)(i0 % (unsigned)cpr);
+    const int cshift = cpr == 1 ? 0 : (cpr == 2 ? 1 : (cpr == 4 ? 2 : 3));
+    const int cg = (int)(i0 & (unsigned)(cpr - 1));
     float sc[8], sh[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) { sc[k] = scale[cg * 8 + k]; sh[k] = shift[cg * 8 + k]; }
     for (unsigned i = i0; i < n_in_chunks; i += gridDim.x * kThreadsA) {
         int b, d, yy, xx;
-        decode_row(i / (unsigned)cpr, g.in.D, g.in.h, g.in.w, b, d, yy, xx);
+        decode_row(i >> cshift, g.in.fD, g.in.fh, g.in.fw, b, d, yy, xx);
         const int od = d + g.io[0] - g.oo[0], oy = yy + g.io[1] - g.oo[1], ox = xx + g.io[2] - g.oo[2];
         float out[8];
         if ((unsigned)od < (unsigned)g.od[0] && (unsigned)oy < (unsigned)g.od[1] && (unsigned)ox < (unsigned)g.od[2]) {
@@ -251,6 +260,7 @@ int make_view(const int64_t* strides4, const int* dims4, int C, View* v, const c
     MVS_REQUIRE(v->B >= 1 && v->D >= 1 && v->h >= 1 && v->w >= 1, "%s: empty box", name);
     MVS_REQUIRE(v->sb % 8 == 0 && v->sd % 8 == 0 && v->sh % 8 == 0 && v->sw % 8 == 0, "%s: strides must be multiples of 8 elements", name);
     MVS_REQUIRE((long long)v->B * v->D * v->h * v->w * (C / 8) < (1LL << 31), "%s: box too large", name);
+    v->fD = make_fastdiv((unsigned)v->D); v->fh = make_fastdiv((unsigned)v->h); v->fw = make_fastdiv((unsigned)v->w);
     return MVSB200_OK;
 }
 
@@ -265,6 +275,7 @@ int make_geo(const int64_t* strides4, const int* geo13, int C, Geo* g, const cha
     for (int i = 0; i < 3; ++i) { g->io[i] = geo13[4 + i]; g->oo[i] = geo13[7 + i]; g->od[i] = geo13[10 + i]; }
     MVS_REQUIRE(g->od[0] >= 1 && g->od[1] >= 1 && g->od[2] >= 1, "%s: empty output box", name);
     MVS_REQUIRE((long long)g->in.B * g->od[0] * g->od[1] * g->od[2] * (C / 8) < (1LL << 31), "%s: output box too large", name);
+    for (int i = 0; i < 3; ++i) g->fod[i] = make_fastdiv((unsigned)g->od[i]);
     return MVSB200_OK;
 }
 

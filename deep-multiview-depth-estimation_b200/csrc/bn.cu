@@ -229,41 +229,43 @@ struct CropBox {
     int D, h, w;            // canvas: the volume the statistics are taken over
     int d0, h0, w0;         // box origin
     int dc, hc, wc;         // box size
+    FastDiv f_wa, f_ha, f_Da, f_w, f_h, f_D, f_wc, f_hc, f_dc;   // the same extents as division constants
+    int cshift;             // log2(channel groups per row): C/8 is 1, 2, 4 or 8
 };
 
 // chunk index inside the box volume -> chunk index inside the canvas volume
 // (32-bit index arithmetic: the host checks that every chunk count is below 2^31)
 __device__ __forceinline__ long long box_to_canvas(long long i, int cpr, const CropBox& c) {
     const unsigned iu = (unsigned)i;
-    const int cg = (int)(iu % (unsigned)cpr);
-    unsigned r = iu / (unsigned)cpr;
-    const int x = (int)(r % (unsigned)c.wc); r /= (unsigned)c.wc;
-    const int y = (int)(r % (unsigned)c.hc); r /= (unsigned)c.hc;
-    const int d = (int)(r % (unsigned)c.dc);
-    const long long b = r / (unsigned)c.dc;
+    const int cg = (int)(iu & (unsigned)(cpr - 1));
+    unsigned r = iu >> c.cshift, ux, uy, ud;
+    r = fd_divmod(r, c.f_wc, ux);
+    r = fd_divmod(r, c.f_hc, uy);
+    const long long b = fd_divmod(r, c.f_dc, ud);
+    const int x = (int)ux, y = (int)uy, d = (int)ud;
     return ((((b * c.Da + d + c.d0) * c.ha + y + c.h0) * c.wa + x + c.w0)) * cpr + cg;
 }
 // chunk index inside the canvas -> chunk index inside the allocation
 __device__ __forceinline__ long long canvas_to_alloc(long long i, int cpr, const CropBox& c) {
     const unsigned iu = (unsigned)i;
-    const int cg = (int)(iu % (unsigned)cpr);
-    unsigned r = iu / (unsigned)cpr;
-    const int x = (int)(r % (unsigned)c.w); r /= (unsigned)c.w;
-    const int y = (int)(r % (unsigned)c.h); r /= (unsigned)c.h;
-    const int d = (int)(r % (unsigned)c.D);
-    const long long b = r / (unsigned)c.D;
+    const int cg = (int)(iu & (unsigned)(cpr - 1));
+    unsigned r = iu >> c.cshift, ux, uy, ud;
+    r = fd_divmod(r, c.f_w, ux);
+    r = fd_divmod(r, c.f_h, uy);
+    const long long b = fd_divmod(r, c.f_D, ud);
+    const int x = (int)ux, y = (int)uy, d = (int)ud;
     return ((((b * c.Da + d) * c.ha + y) * c.wa + x)) * cpr + cg;
 }
 // chunk index inside the allocation -> chunk index inside the box (>= 0), -1 inside the canvas but outside the box,
 // -2 outside the canvas
 __device__ __forceinline__ long long alloc_to_box(long long i, int cpr, const CropBox& c) {
     const unsigned iu = (unsigned)i;
-    const int cg = (int)(iu % (unsigned)cpr);
-    unsigned r = iu / (unsigned)cpr;
-    const int xa = (int)(r % (unsigned)c.wa); r /= (unsigned)c.wa;
-    const int ya = (int)(r % (unsigned)c.ha); r /= (unsigned)c.ha;
-    const int da = (int)(r % (unsigned)c.Da);
-    const long long b = r / (unsigned)c.Da;
+    const int cg = (int)(iu & (unsigned)(cpr - 1));
+    unsigned r = iu >> c.cshift, ux, uy, ud;
+    r = fd_divmod(r, c.f_wa, ux);
+    r = fd_divmod(r, c.f_ha, uy);
+    const long long b = fd_divmod(r, c.f_Da, ud);
+    const int xa = (int)ux, ya = (int)uy, da = (int)ud;
     if (xa >= c.w || ya >= c.h || da >= c.D) return -2;
     const int x = xa - c.w0, y = ya - c.h0, d = da - c.d0;
     if ((unsigned)x >= (unsigned)c.wc || (unsigned)y >= (unsigned)c.hc || (unsigned)d >= (unsigned)c.dc) return -1;
@@ -482,8 +484,14 @@ static int make_box(const int* g, int64_t M, int64_t* Bout, CropBox* cb) {
     MVS_REQUIRE(cb->d0 >= 0 && cb->h0 >= 0 && cb->w0 >= 0 && cb->dc >= 1 && cb->hc >= 1 && cb->wc >= 1 &&
                 cb->d0 + cb->dc <= cb->D && cb->h0 + cb->hc <= cb->h && cb->w0 + cb->wc <= cb->w, "bn crop: box outside the canvas");
     *Bout = M / per;
+    cb->f_wa = make_fastdiv((unsigned)cb->wa); cb->f_ha = make_fastdiv((unsigned)cb->ha); cb->f_Da = make_fastdiv((unsigned)cb->Da);
+    cb->f_w = make_fastdiv((unsigned)cb->w); cb->f_h = make_fastdiv((unsigned)cb->h); cb->f_D = make_fastdiv((unsigned)cb->D);
+    cb->f_wc = make_fastdiv((unsigned)cb->wc); cb->f_hc = make_fastdiv((unsigned)cb->hc); cb->f_dc = make_fastdiv((unsigned)cb->dc);
+    cb->cshift = 0;                                   // set per call from C (set_cshift)
     return MVSB200_OK;
 }
+
+static void set_cshift(CropBox* cb, int C) { cb->cshift = C == 8 ? 0 : (C == 16 ? 1 : (C == 32 ? 2 : 3)); }
 
 extern "C" int mvsb200_bn_stats_geo(const void* x, int dtype, int64_t M, int C, float* workspace, float* mean, float* var,
                                     const int* geo12, void* stream) {
@@ -492,6 +500,7 @@ extern "C" int mvsb200_bn_stats_geo(const void* x, int dtype, int64_t M, int C, 
     MVS_REQUIRE(dtype == MVSB200_F32 || dtype == MVSB200_BF16, "bn_stats_geo: bad dtype %d", dtype);
     CropBox cb; int64_t B;
     if (int rc = make_box(geo12, M, &B, &cb)) return rc;
+    set_cshift(&cb, C);
     cudaStream_t st = (cudaStream_t)stream;
     const long long n_chunks = (long long)M * C / 8;
     const int grid = grid_for(n_chunks);
@@ -512,6 +521,7 @@ extern "C" int mvsb200_bn_relu_fwd_crop(const void* x, int dtype, const float* s
     MVS_REQUIRE(dtype == MVSB200_F32 || dtype == MVSB200_BF16, "bn_relu_fwd_crop: bad dtype %d", dtype);
     CropBox cb; int64_t B;
     if (int rc = make_box(geo12, M, &B, &cb)) return rc;
+    set_cshift(&cb, C);
     cudaStream_t st = (cudaStream_t)stream;
     const long long n_box = (long long)B * cb.dc * cb.hc * cb.wc * C / 8;
     const int grid = grid_for(n_box);
@@ -552,6 +562,7 @@ extern "C" int mvsb200_bn_relu_bwd_crop(const void* x, int x_dtype, const void* 
     MVS_REQUIRE(scale && shift && mean && invstd && gamma && workspace && dbeta && dgamma, "bn_relu_bwd_crop: null vector");
     CropBox cb; int64_t B;
     if (int rc = make_box(geo12, M, &B, &cb)) return rc;
+    set_cshift(&cb, C);
     cudaStream_t st = (cudaStream_t)stream;
     if (x_dtype == MVSB200_BF16 && g_dtype == MVSB200_BF16)
         return bn_bwd_crop_impl<__nv_bfloat16, __nv_bfloat16>(x, gy, scale, shift, mean, invstd, gamma, workspace, dbeta, dgamma, dx, relu, M, C, B, cb, st);

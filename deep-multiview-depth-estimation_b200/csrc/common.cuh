@@ -41,6 +41,40 @@ extern std::atomic<uint64_t> g_launches;
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+// Unsigned 32-bit division by a run-time constant without a divide instruction (multiply-high + shift; the branch-free
+// scheme of Granlund & Montgomery as used by libdivide; exact for every 32-bit numerator, checked by brute force on the host).
+// The streaming kernels decode a flat chunk index into (b, d, y, x, channel group) per 16 bytes moved: with `/` and `%` on
+// run-time extents that decode cost more instructions than the arithmetic on the data.
+struct FastDiv {
+    unsigned d, magic, shift;
+};
+inline FastDiv make_fastdiv(unsigned d) {
+    FastDiv f;
+    f.d = d; f.magic = 0; f.shift = 0;
+    if (d <= 1) return f;
+    const unsigned l = 31 - (unsigned)__builtin_clz(d);
+    if ((d & (d - 1)) == 0) { f.shift = l - 1; return f; }
+    const uint64_t num = (uint64_t)1 << (32 + l);
+    uint32_t m = (uint32_t)(num / d);
+    const uint32_t rem = (uint32_t)(num % d);
+    m += m;
+    const uint32_t twice = rem + rem;
+    if (twice >= d || twice < rem) m += 1;
+    f.magic = m + 1; f.shift = l;
+    return f;
+}
+__device__ __forceinline__ unsigned fd_div(unsigned n, const FastDiv& f) {
+    const unsigned q = __umulhi(n, f.magic);
+    const unsigned t = ((n - q) >> 1) + q;
+    return f.d == 1 ? n : (t >> f.shift);
+}
+// n -> (n / d, n % d)
+__device__ __forceinline__ unsigned fd_divmod(unsigned n, const FastDiv& f, unsigned& rem) {
+    const unsigned q = fd_div(n, f);
+    rem = n - q * f.d;
+    return q;
+}
+
 // streaming 16-byte store that does NOT allocate in L1: cost volumes are far larger than L2 and are read once, and an
 // L1-allocating store stream evicts the feature-map lines the tap loads live on (profiles/k1 notes)
 __device__ __forceinline__ void st_cs_f4(float4* p, float4 v) {
