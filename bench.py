@@ -186,10 +186,13 @@ def run_b200(args, rank, world, local_rank):
         img_dev, gt_dev = img_host.to(dev), gt_host.to(dev)
         slab = DepthSlabMVSNet(model, graph=not args.no_graph)
 
-    gstep = None
+    gstep = ginf = None
     if train and not args.no_graph:
         from mvs_b200.harness import GraphedTrainStep
         gstep = GraphedTrainStep(model, B, V, H, W, dev)
+    elif not train and slab is None and not args.no_graph:
+        from mvs_b200.harness import GraphedInference
+        ginf = GraphedInference(model, B, V, H, W, dev)
 
     def step(img, gt):
         if gstep is not None:                              # forward + loss + backward as one CUDA graph
@@ -211,7 +214,10 @@ def run_b200(args, rank, world, local_rank):
             opt.step()
             return loss.detach()
         with torch.no_grad():
-            initial, refined = model(img, K, R, T, d_min, d_int, B, V)
+            if ginf is not None:                           # inference forward replayed as one CUDA graph
+                initial, refined = ginf.run(img, K, R, T, d_min, d_int)
+            else:
+                initial, refined = model(img, K, R, T, d_min, d_int, B, V)
             return loss_fcn(gt, initial, refined)[0]
 
     def step_resident():
@@ -279,20 +285,21 @@ def run_b200(args, rank, world, local_rank):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    if gstep is None:
+    if gstep is None and ginf is None:
         ops.EVENTS = {}
     n0 = mvs_b200.launch_count()
     ms = timed(step_resident, args.steps)
-    launches = (gstep.launches * args.steps) if gstep is not None else mvs_b200.launch_count() - n0
+    launches = ((gstep.launches * args.steps) if gstep is not None else
+                (ginf.launches * args.steps) if ginf is not None else mvs_b200.launch_count() - n0)
     events, ops.EVENTS = ops.EVENTS, None
     clocks = sampler.stop() if rank == 0 else None
     for _ in range(2):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
-    if gstep is not None:
+    if gstep is not None or ginf is not None:
         # per-kernel durations cannot be bracketed inside a graph replay: the same step, issued eagerly right after the
         # timed region with every libmvs_b200.so launch between two CUDA events on its launching stream
-        graphed, gstep = gstep, None
+        graphed, gstep, graphed_inf, ginf = gstep, None, ginf, None
         for p_ in params:
             p_.grad = None
         step_resident()
@@ -301,7 +308,7 @@ def run_b200(args, rank, world, local_rank):
             step_resident()
         torch.cuda.synchronize()
         events, ops.EVENTS = ops.EVENTS, None
-        gstep = graphed                                    # (reporting only from here on)
+        gstep, ginf = graphed, graphed_inf                 # (reporting only from here on)
 
     maps = B * (1 if slab is not None else world) * args.steps
     value, e2e_value = maps / (ms * 1e-3), maps / (ms_e2e * 1e-3)
@@ -396,7 +403,9 @@ def run_b200(args, rank, world, local_rank):
                            "cudnn_benchmark": bool(torch.backends.cudnn.benchmark),
                            "cuda_graph": (f"forward+loss+backward replayed as one CUDA graph ({gstep.launches} libmvs_b200.so "
                                           f"launches per replay); per-kernel timings from {args.steps} eager steps run right "
-                                          f"after the timed region") if gstep is not None else (graph_note or "off")},
+                                          f"after the timed region") if gstep is not None else
+                                         (f"inference forward replayed as one CUDA graph ({ginf.launches} libmvs_b200.so launches per "
+                                          f"replay)" if ginf is not None else (graph_note or "off"))},
                 "e2e": {"value": e2e_value, "unit": "depth maps/s", "ms_per_step": ms_e2e / args.steps,
                         "h2d_bytes_per_step": img_host.numel() * 4 + gt_host.numel() * 4, "d2h_bytes_per_step": 4,
                         "input_pipeline": "pinned host buffers, double-buffered device staging: the H2D copy of step i+1 runs on a "

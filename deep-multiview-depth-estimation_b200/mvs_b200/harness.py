@@ -165,6 +165,51 @@ class GraphedTrainStep:
         return self.loss
 
 
+class GraphedInference:
+    """MVSNet.forward under torch.no_grad() (test.py:86-92) replayed as ONE CUDA graph for a fixed input shape: static image /
+    geometry buffers re-filled per call (`PlaneSweep.update`), ~250 kernel launches per depth map issued by one graph launch."""
+
+    def __init__(self, model: "MVSNet", batch_size, n_views, H, W, device, warmup=2):
+        self.model, self.B, self.V, self.warmup = model, batch_size, n_views, warmup
+        self.img = torch.zeros(batch_size * n_views, 3, H, W, device=device)
+        self.d_min = torch.zeros(batch_size, 1, 1, 1, device=device)
+        self.d_int = torch.ones(batch_size, 1, 1, 1, device=device)
+        self.dims = (H // 4, W // 4)
+        self.sweep, self.graph, self.out, self.launches = None, None, None, 0
+
+    @torch.no_grad()
+    def _fwd(self):
+        return self.model(self.img, None, None, None, self.d_min, self.d_int, self.B, self.V, sweep=self.sweep)
+
+    @torch.no_grad()
+    def run(self, img, K, R, T, d_min, d_int):
+        from . import ops
+        if self.sweep is None:
+            self.sweep = ops.PlaneSweep(K, R, T, d_min, d_int, self.B, self.V, self.model.d_num, self.model.d_scale,
+                                        self.dims[0], self.dims[1], self.img.device)
+        else:
+            self.sweep.update(K, R, T, d_min, d_int)
+        self.img.copy_(img, non_blocking=True)
+        self.d_min.copy_(d_min, non_blocking=True)
+        self.d_int.copy_(d_int, non_blocking=True)
+        if self.graph is None:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(self.warmup):
+                    self._fwd()
+            torch.cuda.current_stream().wait_stream(side)
+            from . import _lib
+            n0 = _lib.launch_count()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.out = self._fwd()
+            self.launches = _lib.launch_count() - n0       # libmvs_b200.so launches recorded in the graph
+            self.graph = g
+        self.graph.replay()
+        return self.out
+
+
 class DepthSlabMVSNet:
     """Inference of ONE multi-view sample across the ranks of a box (BASELINE.json configs[3]): the hot path runs on depth
     slabs (mvs_b200.depth_slab), the out-of-scope 2D nets are replicated.  Each view is encoded by ONE rank
