@@ -52,3 +52,28 @@ def test_graphed_step_equals_eager_step(precision):
             if p.grad is not None:
                 worst = max(worst, float((p.grad - q.grad).abs().max() / (q.grad.abs().max() + 1e-12)))
         assert worst < (0.15 if precision == "bf16" else 2e-2), worst
+
+
+def test_graphed_inference_equals_eager_forward():
+    """harness.GraphedInference: the no-grad forward replayed as one CUDA graph returns the eager forward's depth maps, also
+    after images and cameras change between replays."""
+    import mvs_b200
+    from mvs_b200.harness import MVSNet, GraphedInference
+    B, V, H, W, D = 1, 3, 96, 128, 16
+    dev = torch.device("cuda:0")
+    torch.manual_seed(0)
+    model = MVSNet(D, 480.0 / D, precision="bf16").to(dev).train()      # train-mode BatchNorm also at test time (test.py:61)
+    twin = copy.deepcopy(model)
+    ginf = GraphedInference(model, B, V, H, W, dev, warmup=1)
+    for it, (seed, d0) in enumerate([(1, 425.0), (2, 500.0), (3, 425.0)]):
+        img, _, K, R, T, d_min, d_int = _batch(B, V, H, W, seed, d0)
+        n0 = mvs_b200.launch_count()
+        initial, refined = ginf.run(img, K, R, T, d_min, d_int)
+        torch.cuda.synchronize()
+        if it > 0:
+            assert mvs_b200.launch_count() == n0
+        with torch.no_grad():
+            ref_i, ref_r = twin(img.to(dev), K, R, T, d_min, d_int, B, V)
+        step = 480.0 / D
+        assert float(((initial - ref_i).abs() < 0.05 * step).float().mean()) > 0.97
+        assert torch.isfinite(refined).all() and refined.shape == ref_r.shape
