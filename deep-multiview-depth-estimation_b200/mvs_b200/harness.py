@@ -217,18 +217,18 @@ class DepthSlabMVSNet:
     of its planes.  Wraps an MVSNet whose parameters are identical on every rank."""
 
     def __init__(self, model: "MVSNet", comm=None, graph=False):
-        """graph: replay the sharded hot path (kernels + NCCL exchanges) as one CUDA graph per rank (fixed shapes); call
-        release() before destroying the process group."""
+        """graph: replay the rank's whole forward (2D nets, sharded hot path, NCCL exchanges) as one CUDA graph (fixed shapes);
+        call release() before destroying the process group."""
         from .depth_slab import DepthSlabCostVolumeReg, TorchDistComm
         self.model = model
         self.comm = TorchDistComm() if comm is None else comm
         self.reg = DepthSlabCostVolumeReg(model.cost_volume_reg, self.comm)
-        self.use_graph, self._graphed, self._sweep = bool(graph), None, None
+        self.use_graph, self._graphed, self._sweep, self._out = bool(graph), None, None, None
 
     def release(self):
-        if self._graphed is not None:
-            self._graphed.release()
-            self._graphed = None
+        """Drop the captured graph (it holds NCCL work: do this before destroy_process_group())."""
+        self._graphed, self._out = None, None
+        torch.cuda.synchronize()
 
     @torch.no_grad()
     def encode(self, nn_input, by_view=None):
@@ -253,34 +253,56 @@ class DepthSlabMVSNet:
             self.comm.broadcast(nhwc[v], v % R)
         return nhwc.permute(0, 3, 1, 2)
 
-    @torch.no_grad()
-    def forward(self, nn_input, K_batch, R_batch, T_batch, d_min, d_int, n_views):
-        from . import ops
+    def _pipeline(self, nn_input, sweep, d_trans, d_span):
+        """encode -> slab sweep + slab regulariser + depth -> refinement, on geometry already resident on the device."""
         from .depth_slab import slab_cost_fn
         m = self.model
         feats = self.encode(nn_input)
         h, w = feats.shape[-2:]
         vol_dtype = torch.bfloat16 if m.precision == "bf16" else torch.float32
-        if self.use_graph:
-            from .depth_slab import GraphedSlabForward
-            if self._sweep is None:
-                self._sweep = ops.PlaneSweep(K_batch, R_batch, T_batch, d_min, d_int, 1, n_views, m.d_num, m.d_scale, h, w, feats.device)
-                self._graphed = GraphedSlabForward(self.reg, self._sweep, tuple(feats.shape), feats.device, vol_dtype)
-            else:
-                self._sweep.update(K_batch, R_batch, T_batch, d_min, d_int)
-            sweep = self._sweep
-            initial, prob_rows, rows = self._graphed(feats)
-        else:
-            sweep = ops.PlaneSweep(K_batch, R_batch, T_batch, d_min, d_int, 1, n_views, m.d_num, m.d_scale, h, w, feats.device)
-            initial, prob_rows, rows = self.reg.forward(slab_cost_fn(feats, sweep, vol_dtype), sweep.d_batch_dev, 1, m.d_num, h, w)
-        dev = initial.device
-        d_trans, d_span = d_min.to(dev), d_int.to(dev) * m.d_num * m.d_scale
+        initial, prob_rows, rows = self.reg.forward(slab_cost_fn(feats, sweep, vol_dtype), sweep.d_batch_dev, 1, m.d_num, h, w)
         norm = (initial - d_trans) / d_span
         ref_img = F.interpolate(nn_input[:1], (h, w), mode="bilinear", align_corners=False)
         amp = m.precision == "bf16" and nn_input.is_cuda
         with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):          # replicated: 4-channel 400x296 maps
             refined = m.depthmap_refine(torch.cat((norm, ref_img), 1))
         return initial, refined.float() * d_span + d_trans
+
+    @torch.no_grad()
+    def forward(self, nn_input, K_batch, R_batch, T_batch, d_min, d_int, n_views):
+        from . import ops
+        m = self.model
+        N, _, H, W = nn_input.shape
+        h, w = H // 4, W // 4
+        dev = nn_input.device
+        if not self.use_graph:
+            sweep = ops.PlaneSweep(K_batch, R_batch, T_batch, d_min, d_int, 1, n_views, m.d_num, m.d_scale, h, w, dev)
+            return self._pipeline(nn_input, sweep, d_min.to(dev), d_int.to(dev) * m.d_num * m.d_scale)
+        # the rank's WHOLE forward -- 2D nets, K1, slab regulariser, every NCCL exchange, K4 -- as one CUDA graph
+        if self._sweep is None:
+            self._sweep = ops.PlaneSweep(K_batch, R_batch, T_batch, d_min, d_int, 1, n_views, m.d_num, m.d_scale, h, w, dev)
+            self._img = torch.zeros_like(nn_input)
+            self._d_trans = torch.zeros(1, 1, 1, 1, device=dev)
+            self._d_span = torch.ones(1, 1, 1, 1, device=dev)
+        else:
+            self._sweep.update(K_batch, R_batch, T_batch, d_min, d_int)
+        self._img.copy_(nn_input, non_blocking=True)
+        self._d_trans.copy_(d_min, non_blocking=True)
+        self._d_span.copy_(d_int * (m.d_num * m.d_scale), non_blocking=True)
+        if self._graphed is None:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):                       # lazy workspaces, NCCL connections, cuDNN plans -- outside the capture
+                    self._pipeline(self._img, self._sweep, self._d_trans, self._d_span)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._out = self._pipeline(self._img, self._sweep, self._d_trans, self._d_span)
+            self._graphed = g
+        self._graphed.replay()
+        return self._out
 
 
 def loss_fcn(gt, initial, refined):
