@@ -1,13 +1,16 @@
 #!/usr/bin/env python
-"""bench.py -- headline measurement of the plane-sweep hot path (contract: see the task brief / DESIGN.md §Measurement).
+"""bench.py -- headline measurement of the plane-sweep hot path (contract: see the task brief / DESIGN.md §5).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload cfg2|cfg1]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload cfg2|cfg1|cfg4] [--no-graph]
 
-Own arm: one "step" = one MVSNet train step (forward + backward + Adam) on one synthetic DTU-shaped batch
-(BASELINE.json configs[1]: bf16, batch 4, 3 views, 640x512 input => 160x128x32 features, D = 192).  `value` is
-depth maps/s with the batch already resident in HBM; `e2e` is the same step fed from pinned HOST buffers with the
-H2D copy of the images and the D2H read of the loss inside the timed region.  `roofline` is for the fused
-warp+variance kernel (K1), timed live with CUDA events on its launching stream inside the timed steps.
+Own arm: one "step" = one MVSNet train step (forward + loss + backward + Adam) on one synthetic DTU-shaped batch
+(BASELINE.json configs[1]: bf16, batch 4, 3 views, 640x512 input => 160x128x32 features, D = 192), replayed as one CUDA graph
+(harness.GraphedTrainStep; --no-graph issues it eagerly).  `value` is depth maps/s with the batch already resident in HBM;
+`e2e` is the same step fed from pinned HOST buffers (H2D of the images, ground truth and sweep geometry, D2H read of the loss
+inside the timed region).  `roofline` is the dominant own kernel (the stride-1 tcgen05 convolution, tensor bound),
+`roofline_k1` / `roofline_k1_fp32` the fused warp+variance kernel (HBM bound), all timed live with CUDA events on the
+launching stream.  Under torchrun (--gpus N): cfg2 shards by scene/batch with a flat-bucket NCCL gradient all-reduce (weak
+scaling); cfg4 splits ONE sample into depth slabs across the ranks (strong scaling, mvs_b200.depth_slab).
 
 Reference arm (--impl reference): the oracle port of the reference's CPU algorithm (oracle/cpu_path.py) on the
 host cores, each step a bounded sample of the same workload (stated in `cpu_baseline.sample`).
