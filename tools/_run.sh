@@ -1,1 +1,1 @@
-timeout 600 python -m pytest tests/test_dropin_boundary.py -m gpu -q -x > gpurun_out/pytest_dropin.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_dropin.log
+timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench24.json 2> gpurun_out/bench24.err; echo "rc=$?" >> gpurun_out/bench24.err
