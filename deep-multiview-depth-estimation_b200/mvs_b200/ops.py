@@ -128,10 +128,13 @@ class PlaneSweep:
         self.d_batch_0 = geometry.depth_table(d_min, d_int, self.D, self.d_scale)
         params, tinv = geometry.view_tables(K, R, T, self.d_batch_0, self.B, self.V, self.h, self.w, self.bug_compatible)
         n1, n2, n3 = params.size, tinv.size, self.d_batch_0.numel()
+        on_gpu = self.view_params.is_cuda
         if self._stage is None:
-            self._stage = torch.empty(n1 + n2 + n3, dtype=torch.float32).pin_memory()
-            self._stage_free = torch.cuda.Event()
-        else:
+            self._stage = torch.empty(n1 + n2 + n3, dtype=torch.float32)
+            if on_gpu:
+                self._stage = self._stage.pin_memory()
+                self._stage_free = torch.cuda.Event()
+        elif on_gpu:
             self._stage_free.synchronize()                 # the previous update's copies have left the staging buffer
         st = self._stage
         st[:n1].copy_(torch.from_numpy(params).reshape(-1))
@@ -140,7 +143,8 @@ class PlaneSweep:
         self.view_params.view(-1).copy_(st[:n1], non_blocking=True)
         self.tinv.view(-1).copy_(st[n1:n1 + n2], non_blocking=True)
         self.d_batch_dev.view(-1).copy_(st[n1 + n2:], non_blocking=True)
-        self._stage_free.record()
+        if on_gpu:
+            self._stage_free.record()
         return self
 
 

@@ -64,3 +64,26 @@ def test_zero_depth_plane_is_flagged_nan():
     d0 = geometry.depth_table(torch.zeros(1, 1, 1, 1), torch.ones(1, 1, 1, 1), 4, 10)
     _, tinv = geometry.view_tables(K, R, T, d0, 1, 3, 16, 20)
     assert np.isnan(tinv[:, 0]).all() and np.isfinite(tinv[:, 1:]).all()
+
+
+def test_plane_sweep_update_rewrites_the_same_buffers():
+    """ops.PlaneSweep.update (what a captured CUDA graph relies on): new cameras / depth range land in the SAME tensors and
+    equal the tables of a freshly built sweep."""
+    import torch
+    import plane_sweep as ps
+    from mvs_b200 import ops
+    B, V, D, h, w = 2, 3, 12, 16, 20
+    K0, R0, T0 = ps.synthetic_cameras(B, V, h, w, seed=1)
+    K1, R1, T1 = ps.synthetic_cameras(B, V, h, w, seed=2)
+    d0, i0 = torch.full((B, 1, 1, 1), 425.0), torch.ones(B, 1, 1, 1)
+    d1, i1 = torch.full((B, 1, 1, 1), 500.0), torch.full((B, 1, 1, 1), 1.5)
+    sweep = ops.PlaneSweep(K0, R0, T0, d0, i0, B, V, D, 40.0, h, w, torch.device("cpu"))
+    ptrs = (sweep.view_params.data_ptr(), sweep.tinv.data_ptr(), sweep.d_batch_dev.data_ptr())
+    sweep.update(K1, R1, T1, d1, i1)
+    fresh = ops.PlaneSweep(K1, R1, T1, d1, i1, B, V, D, 40.0, h, w, torch.device("cpu"))
+    assert ptrs == (sweep.view_params.data_ptr(), sweep.tinv.data_ptr(), sweep.d_batch_dev.data_ptr())
+    assert torch.equal(sweep.view_params, fresh.view_params) and torch.equal(sweep.tinv, fresh.tinv)
+    assert torch.equal(sweep.d_batch_dev, fresh.d_batch_dev) and torch.equal(sweep.d_batch_0, fresh.d_batch_0)
+    sweep.update(K0, R0, T0, d0, i0)                                    # and back
+    first = ops.PlaneSweep(K0, R0, T0, d0, i0, B, V, D, 40.0, h, w, torch.device("cpu"))
+    assert torch.equal(sweep.tinv, first.tinv)
