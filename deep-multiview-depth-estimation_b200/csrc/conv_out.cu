@@ -162,9 +162,10 @@ __global__ void conv_out_wgrad_finalize_kernel(const float* __restrict__ partial
 // read the filter from shared memory (54 LDS.128 per voxel); here a thread owns an (x, y) column and walks a run of planes:
 // per INPUT plane it loads the 9 in-plane taps once, forms the three depth-tap partial sums with the filter as
 // constant-bank FFMA operands (no load instruction for the weights) and keeps two running sums in registers -- the
-// register-level twin of the kdn tensor-core kernel.  The filter lives in one of 4 __constant__ slots (copied device to
-// device on the launching stream; round-robin so that up to 4 calls with different filters may be in flight).
-__constant__ float c_w[4][kWn];
+// register-level twin of the kdn tensor-core kernel.  The filter lives in one of 8 __constant__ slots, one per launching
+// stream (copied device to device on that stream before the kernel: stage_filter).
+constexpr int kSlotsW = 8;
+__constant__ float c_w[kSlotsW][kWn];
 constexpr int kDch = 24;                         // planes per run: (kDch + 2) input planes are visited per kDch outputs
 
 __global__ void __launch_bounds__(256) conv_out_fwd_march_kernel(const uint4* __restrict__ z, float* __restrict__ out, int D, int h,
@@ -298,9 +299,18 @@ __global__ void __launch_bounds__(256) conv_out_wgrad_tap_kernel(const uint4* __
     }
 }
 
+// One filter slot per launching stream (first come, first served): a stream's staging copy and its kernels are ordered, and
+// two streams -- or a replaying graph captured on its own stream beside eager launches -- never overwrite a slot under each
+// other's live kernel.  More than kSlotsW distinct streams share the last slot (single-stream ordering still holds there).
 int stage_filter(const float* w27x8, cudaStream_t st, int* slot_out) {
-    static unsigned counter = 0;
-    const int slot = (int)(__atomic_fetch_add(&counter, 1u, __ATOMIC_RELAXED) & 3u);
+    static std::atomic<uintptr_t> owner[kSlotsW];
+    const uintptr_t id = reinterpret_cast<uintptr_t>(st) + 1;          // +1: the default stream (0) is an owner too
+    int slot = kSlotsW - 1;
+    for (int i = 0; i < kSlotsW; ++i) {
+        uintptr_t cur = owner[i].load(std::memory_order_acquire);
+        if (cur == 0 && owner[i].compare_exchange_strong(cur, id)) cur = id;
+        if (cur == id) { slot = i; break; }
+    }
     MVS_CUDA(cudaMemcpyToSymbolAsync(c_w, w27x8, sizeof(float) * kWn, sizeof(float) * kWn * slot, cudaMemcpyDeviceToDevice, st));
     *slot_out = slot;
     return MVSB200_OK;

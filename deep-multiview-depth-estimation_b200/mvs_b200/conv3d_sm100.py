@@ -54,19 +54,22 @@ def _S1_FORM():
     return form if form == "taps" or hasattr(_lib.load(), "mvsb200_conv3d_s1_fwd_kdn") else "taps"
 
 
-def _launch(x_cl, wp, cout, out_dims, off):
+def _launch(x_cl, wp, cout, out_dims, off, k_alg=None):
+    """k_alg: the contraction channels that carry data (algorithmic FLOPs are counted on them; a volume widened with zero
+    channels to reach the UMMA K of 16 is launched with cin = 16 but does the work of k_alg = 8)."""
     B, cin, Di, Hi, Wi = x_cl.shape
     Do, Ho, Wo = out_dims
+    k_alg = cin if k_alg is None else k_alg
     y = torch.empty((B, cout, Do, Ho, Wo), dtype=torch.bfloat16, device=x_cl.device, memory_format=torch.channels_last_3d)
     if _S1_FORM() == "kdn":
         # depth tap folded into the MMA N extent: filter as [(kh,kw)][kd][rows][Cin]
         n_rows = wp.shape[1]
         wk = wp.view(3, 3, 3, n_rows, cin).permute(1, 2, 0, 3, 4).contiguous()
-        with _timed("conv3d_s1_tc", 2.0 * 27 * cin * cout * B * Do * Ho * Wo):
+        with _timed("conv3d_s1_tc", 2.0 * 27 * k_alg * cout * B * Do * Ho * Wo):
             _lib.call("mvsb200_conv3d_s1_fwd_kdn", x_cl.data_ptr(), wk.data_ptr(), y.data_ptr(), B, Di, Hi, Wi, cin, Do, Ho, Wo,
                       cout, cout, n_rows, off, off, off, _stream())
         return y
-    with _timed("conv3d_s1_tc", 2.0 * 27 * cin * cout * B * Do * Ho * Wo):
+    with _timed("conv3d_s1_tc", 2.0 * 27 * k_alg * cout * B * Do * Ho * Wo):
         _lib.call("mvsb200_conv3d_s1_fwd", x_cl.data_ptr(), wp.data_ptr(), y.data_ptr(), B, Di, Hi, Wi, cin, Do, Ho, Wo,
                   cout, cout, wp.shape[1], off, off, off, _stream())
     return y
@@ -102,7 +105,7 @@ class _Conv3dS1(torch.autograd.Function):
                 _lib.call("mvsb200_widen_rows_8to16_bf16", gy.data_ptr(), gy16.data_ptr(), B * Do * Ho * Wo, _stream())
                 w16 = torch.zeros((16,) + tuple(w.shape[1:]), dtype=w.dtype, device=w.device)
                 w16[:8] = w.detach()
-                gx = _launch(gy16, pack_filter_dgrad(w16), cin, tuple(x_cl.shape[2:]), off)
+                gx = _launch(gy16, pack_filter_dgrad(w16), cin, tuple(x_cl.shape[2:]), off, k_alg=8)
             else:
                 gx = torch.nn.grad.conv3d_input(x_cl.shape, w.to(gy.dtype), gy, padding=pad)
         if ctx.needs_input_grad[1]:
@@ -361,6 +364,8 @@ class Tcgen05ConvBackend:
     @staticmethod
     def conv3d(x, w, stride, padding):
         pad = tuple(padding) if isinstance(padding, (tuple, list)) else (padding,) * 3
+        if x.is_cuda and not w.is_cuda:
+            raise _lib.MvsB200Error("convolution weights live on the CPU while the volume is on the GPU; mvs_b200 has no CPU path")
         if (stride == 1 and x.is_cuda and x.dtype == torch.bfloat16 and pad in ((0, 0, 0), (1, 1, 1))
                 and _supported(x.shape[1], w.shape[0]) and min(x.shape[2:]) >= 3):
             return _Conv3dS1.apply(x, w, pad[0])

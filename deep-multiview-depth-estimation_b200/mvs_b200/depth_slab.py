@@ -324,7 +324,8 @@ class DepthSlabCostVolumeReg:
     @torch.no_grad()
     def slab_logits(self, cost_fn, B, D, h, w, be=None):
         reg, r, R = self.reg, self.rank, self.world
-        be = conv_backends.get(reg.conv_backend) if be is None else be
+        if be is None:        # as CostVolumeReg.forward: precision="fp32" owns its precision (TF32 off inside the calls)
+            be = conv_backends.ExactTorchConvBackend if reg.precision == "fp32" else conv_backends.get(reg.conv_backend)
         plan = SlabPlan(D, R)
         dt = torch.bfloat16 if reg.precision == "bf16" else torch.float32
         train = reg.BN_0.training

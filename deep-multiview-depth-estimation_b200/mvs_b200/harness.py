@@ -101,15 +101,34 @@ class MVSNet(nn.Module):
         return initial, refined
 
 
+def _snapshot(tensors):
+    return [t.detach().clone() for t in tensors]
+
+
+def _restore(tensors, saved):
+    with torch.no_grad():
+        for t, s in zip(tensors, saved):
+            t.copy_(s)
+
+
 class GraphedTrainStep:
-    """One MVSNet training step (train.py:93-108: forward, loss, backward) captured as ONE CUDA graph: the step is ~800
-    kernel launches of a few microseconds to a few hundred, which eager PyTorch cannot issue fast enough to keep a B200
-    busy.  Static device buffers hold the step's inputs (images, ground truth, sweep geometry); `run` copies the new
-    batch into them (asynchronously, from pinned host memory or device tensors), replays the graph and leaves the
-    gradients in the parameters' .grad; the gradient all-reduce (N > 1) and the optimiser step stay outside the graph.
+    """One MVSNet training step (train.py:93-108: forward, loss, backward -- and, when given, the data-parallel gradient
+    all-reduce and the optimiser step) captured as ONE CUDA graph: the step is ~800 kernel launches of a few microseconds to a
+    few hundred, which eager PyTorch cannot issue fast enough to keep a B200 busy.  Static device buffers hold the step's inputs
+    (images, ground truth, sweep geometry); `run` copies the new batch into them (asynchronously, from pinned host memory or
+    device tensors) and replays the graph.
+
+    reducer (FlatGradAllReduce) and optimizer are optional.  With a reducer every parameter's .grad is a VIEW into the reducer's
+    flat bucket (no pack / unpack copies): the graph zeroes the bucket, backward accumulates into the views, ONE all-reduce
+    (NCCL work is capturable) and one scale average it, all inside the replay.  With an optimizer (torch.optim.Adam(fused=True,
+    capturable=True)) its step is the last node of the graph; otherwise the caller steps after run().
+
+    The warm-up passes that precede the capture (lazy workspaces, library plans) run on real data; BatchNorm buffers,
+    parameters and optimiser state are restored afterwards, so the first replay starts from the state the caller handed in --
+    an eager step and the graphed step see the same running statistics.
     Shapes are fixed per instance, as in the reference's loaders (fixed resolution, batch and view count)."""
 
-    def __init__(self, model: "MVSNet", batch_size, n_views, H, W, device, warmup=3):
+    def __init__(self, model: "MVSNet", batch_size, n_views, H, W, device, warmup=3, reducer=None, optimizer=None):
         from . import ops, _lib
         self.model, self.B, self.V = model, batch_size, n_views
         h, w = H // 4, W // 4
@@ -122,6 +141,9 @@ class GraphedTrainStep:
         self.graph, self.loss, self.launches = None, None, 0
         self.warmup, self._lib = warmup, _lib
         self.params = [p for p in model.parameters() if p.requires_grad]
+        self.reducer, self.optimizer = reducer, optimizer
+        if reducer is not None:
+            reducer.attach_grads()                         # .grad of every parameter := view into the flat bucket
 
     def _load(self, img, gt, K, R, T, d_min, d_int):
         from . import ops
@@ -135,26 +157,58 @@ class GraphedTrainStep:
         self.d_min.copy_(d_min, non_blocking=True)
         self.d_int.copy_(d_int, non_blocking=True)
 
+    def _zero_grads(self):
+        if self.reducer is not None:
+            self.reducer.bucket.zero_()                    # one memset; the .grad views stay attached
+        else:
+            for p in self.params:
+                p.grad = None
+
     def _fwd_bwd(self):
+        if self.reducer is not None:
+            self.reducer.bucket.zero_()
         initial, refined = self.model(self.img, None, None, None, self.d_min, self.d_int, self.B, self.V, sweep=self.sweep)
         loss, _, _ = loss_fcn(self.gt, initial, refined)
         loss.backward()
+        if self.reducer is not None:
+            self.reducer.reduce_attached()                 # all-reduce + average of the flat bucket, in place
+        if self.optimizer is not None:
+            self.optimizer.step()
         return loss.detach()
+
+    def _optimizer_state_tensors(self):
+        out = []
+        if self.optimizer is not None:
+            for st in self.optimizer.state.values():
+                out += [v for v in st.values() if torch.is_tensor(v)]
+        return out
 
     def run(self, img, gt, K, R, T, d_min, d_int):
         """-> loss (device scalar, valid after the current stream reaches this point); gradients in .grad."""
         self._load(img, gt, K, R, T, d_min, d_int)
         if self.graph is None:
+            buffers = list(self.model.buffers())
+            keep = _snapshot(buffers + (self.params if self.optimizer is not None else []))
+            opt_fresh = self.optimizer is not None and len(self.optimizer.state) == 0
+            opt_keep = _snapshot(self._optimizer_state_tensors())
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):                  # warm-up off the capture: lazy workspaces, cuDNN plans, autotune
                 for _ in range(self.warmup):
-                    for p in self.params:
-                        p.grad = None
+                    if self.reducer is None:
+                        self._zero_grads()
                     self._fwd_bwd()
+                # undo what the warm-up passes did to the training state (BatchNorm running statistics, weights, moments)
+                _restore(buffers + (self.params if self.optimizer is not None else []), keep)
+                if opt_fresh:
+                    with torch.no_grad():
+                        for t in self._optimizer_state_tensors():
+                            t.zero_()                      # state tensors were created by the warm-up: back to step 0, in place
+                else:
+                    _restore(self._optimizer_state_tensors(), opt_keep)
             torch.cuda.current_stream().wait_stream(side)
-            for p in self.params:
-                p.grad = None
+            if self.reducer is None:
+                self._zero_grads()
             n0 = self._lib.launch_count()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
@@ -163,6 +217,11 @@ class GraphedTrainStep:
             self.graph = g
         self.graph.replay()
         return self.loss
+
+    def release(self):
+        """Drop the captured graph (with a reducer it holds NCCL work: do this before destroy_process_group())."""
+        self.graph, self.loss = None, None
+        torch.cuda.synchronize()
 
 
 class GraphedInference:
@@ -305,6 +364,43 @@ class DepthSlabMVSNet:
         return self._out
 
 
+# DTU cameras of SURVEY App. C (views = cams 0, 10, 1 of scripts/test_dataloader, K at the 160x128 feature resolution):
+# the synthetic DTU-shaped geometry bench.py and the tools feed the path with.
+_DTU_K = [[361.54126, 0.0, 82.90063], [0.0, 360.3975, 66.38387], [0.0, 0.0, 1.0]]
+_DTU_R = [
+    [[0.970263, 0.00748, 0.241939], [-0.014743, 0.999493, 0.028223], [-0.241605, -0.030951, 0.969881]],
+    [[0.885052, -0.307962, 0.34906], [0.220575, 0.937798, 0.268109], [-0.409915, -0.160296, 0.897928]],
+    [[0.802256, -0.439347, 0.404178], [0.427993, 0.895282, 0.123659], [-0.416183, 0.073779, 0.906283]],
+]
+_DTU_T = [[-191.02, 3.28832, 22.5401], [-258.497, -156.493, 71.838], [-291.419, -77.0495, 71.2762]]
+
+
+def synthetic_cameras(batch_size, n_views, h=128, w=160, seed=0):
+    """DTU-shaped cameras for synthetic batches: views 0..2 of a sample are the three DTU cameras above, further views and
+    further batch items are small seeded perturbations of them (rotation of a few degrees about a random axis, a few
+    millimetres of translation); K scaled from the 160x128 feature grid to (w, h).
+    -> CPU fp32 K [N,3,3], R [N,3,3], T [N,3,1], N = batch_size * n_views, ordered b*V + v (data.py:272-274)."""
+    import numpy as np
+    rng = np.random.RandomState(seed)
+    K = np.array(_DTU_K)
+    K[0] *= w / 160.0
+    K[1] *= h / 128.0
+    Ks, Rs, Ts = [], [], []
+    for b in range(batch_size):
+        for v in range(n_views):
+            R, T = np.array(_DTU_R[v % 3]), np.array(_DTU_T[v % 3])
+            if v >= 3 or b > 0:
+                axis = rng.randn(3)
+                axis /= np.linalg.norm(axis)
+                ang = 0.04 * rng.randn()
+                X = np.array([[0, -axis[2], axis[1]], [axis[2], 0, -axis[0]], [-axis[1], axis[0], 0]])
+                R = (np.eye(3) + np.sin(ang) * X + (1 - np.cos(ang)) * X @ X) @ R
+                T = T + rng.randn(3) * 8.0
+            Ks.append(K); Rs.append(R); Ts.append(T.reshape(3, 1))
+    f = lambda a: torch.tensor(np.stack(a), dtype=torch.float32)
+    return f(Ks), f(Rs), f(Ts)
+
+
 def loss_fcn(gt, initial, refined):
     """Masked L1 on both depth maps (scripts/loss.py:4-41): returns (loss, initial MAE, refined MAE)."""
     mask = (gt != 0).float()
@@ -328,6 +424,7 @@ class FlatGradAllReduce:
         n = sum(p.numel() for p in self.params)
         dev = self.params[0].device
         self.bucket = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.attached = False
         self.views, o = [], 0
         for p in self.params:
             self.views.append(self.bucket[o:o + p.numel()].view_as(p))
@@ -339,10 +436,27 @@ class FlatGradAllReduce:
         for t in list(self.params) + list(buffers):
             self.dist.broadcast(t.data if isinstance(t, nn.Parameter) else t, 0, group=self.group)
 
+    def attach_grads(self):
+        """.grad of every parameter becomes a view into the flat bucket: backward accumulates straight into it, the
+        all-reduce needs no pack / unpack copies, and the whole reduction is capturable in a CUDA graph (static addresses)."""
+        self.bucket.zero_()
+        for p, v in zip(self.params, self.views):
+            p.grad = v
+        self.attached = True
+
+    def reduce_attached(self):
+        """After backward() with attached gradients: bucket <- mean over ranks, in place (one collective, one scale)."""
+        if self.world == 1:
+            return
+        self.dist.all_reduce(self.bucket, group=self.group)
+        self.bucket.mul_(1.0 / self.world)
+
     def reduce(self):
         """Call after backward(): grads <- mean over ranks."""
         if self.world == 1:
             return
+        if self.attached and all(p.grad is v for p, v in zip(self.params, self.views)):
+            return self.reduce_attached()
         for p, v in zip(self.params, self.views):
             if p.grad is None:
                 v.zero_()

@@ -297,11 +297,18 @@ def softmax_depth(logits: torch.Tensor, d_batch: torch.Tensor, n_est: int = 5):
 _BN_WS = {}
 
 
+def _ws_key(device):
+    """Scratch buffers are per (device, launching stream): kernels of one stream are ordered, two streams (or a replaying graph
+    captured on its own stream and eager launches) never share scratch memory."""
+    return (device, torch.cuda.current_stream(device).cuda_stream)
+
+
 def _bn_workspace(device):
-    ws = _BN_WS.get(device)
+    key = _ws_key(device)
+    ws = _BN_WS.get(key)
     if ws is None:
         ws = torch.empty(int(_lib.load().mvsb200_bn_workspace_floats()), dtype=torch.float32, device=device)
-        _BN_WS[device] = ws
+        _BN_WS[key] = ws
     return ws
 
 
@@ -328,6 +335,7 @@ class _BatchNormReLU(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, eps, relu, crop, canvas):
         _need_cuda(x, "BatchNorm input")
+        _need_cuda(weight, "BatchNorm weight")
         xr, _, C = _rows(x.detach())
         dev = xr.device
         B = xr.shape[0]
@@ -420,10 +428,11 @@ _CO_WS = {}
 
 
 def _conv_out_workspace(device):
-    ws = _CO_WS.get(device)
+    key = _ws_key(device)
+    ws = _CO_WS.get(key)
     if ws is None:
         ws = torch.empty(int(_lib.load().mvsb200_conv_out_workspace_floats()), dtype=torch.float32, device=device)
-        _CO_WS[device] = ws
+        _CO_WS[key] = ws
     return ws
 
 
@@ -431,6 +440,7 @@ class _ConvOut(torch.autograd.Function):
     @staticmethod
     def forward(ctx, z, weight):
         _need_cuda(z, "conv_out input")
+        _need_cuda(weight, "conv_out weight")
         B, C, D, h, w = z.shape
         zc = z.detach().to(torch.bfloat16).contiguous(memory_format=torch.channels_last_3d)
         w27 = weight.detach().float()[0].permute(1, 2, 3, 0).reshape(27, 8).contiguous()
@@ -475,10 +485,11 @@ _AF_WS = {}
 
 
 def _affine_workspace(device):
-    ws = _AF_WS.get(device)
+    key = _ws_key(device)
+    ws = _AF_WS.get(key)
     if ws is None:
         ws = torch.empty(int(_lib.load().mvsb200_affine_workspace_floats()), dtype=torch.float32, device=device)
-        _AF_WS[device] = ws
+        _AF_WS[key] = ws
     return ws
 
 

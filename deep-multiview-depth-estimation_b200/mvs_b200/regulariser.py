@@ -17,10 +17,19 @@ conv_0_0, the three transposed-conv outputs (their batch statistics are over the
 Results are those of the reference network (same statistics, same zero regions), with ~7x fewer FLOPs than
 the dense canvases cuDNN executes for the reference.
 
-The convolutions themselves go through ``conv_backend`` (mvs_b200.conv3d): sm_100a implicit-GEMM kernels
-where built, cuDNN otherwise (stated per layer in DESIGN.md).
+The convolutions themselves go through ``conv_backend`` (mvs_b200.conv3d).
+
+Precision (``precision=``), i.e. what ``CostVolumeReg()`` -- the call of scripts/model.py:161 -- computes in:
+  "bf16" (default)  the native path: bf16 operands, fp32 accumulation on the tcgen05 kernels of libmvs_b200.so (BASELINE
+                    north_star "bf16/tf32 in, fp32 accumulate"); fp32 volumes in and out, parameters stay fp32.  Tolerance
+                    against the reference's fp32 network: probability volume 1e-2 relative (max-norm), the north_star figure
+                    for the bf16 convolution path; tests/test_gpu_parity.py, tests/test_gpu_fullsize.py.
+  "fp32"            explicit opt-in for parity diagnostics at 1e-4: fp32 volumes through the library convolutions with TF32
+                    switched off INSIDE the module (it does not depend on torch.backends.cudnn.allow_tf32).
 """
 from __future__ import annotations
+
+import sys
 
 import torch
 import torch.nn as nn
@@ -28,6 +37,19 @@ import torch.nn.functional as F
 
 from . import _lib, ops
 from . import conv3d as conv_backends
+
+
+def default_device():
+    """The reference's constructor default is ``device=DEVICE`` (scripts/model.py:70, scripts/config.py:24): the host
+    application's ``config.DEVICE`` when that module is loaded, else the current CUDA device, else the CPU (parameters can be
+    built there; forward needs CUDA)."""
+    cfg = sys.modules.get("config")
+    dev = getattr(cfg, "DEVICE", None)
+    if isinstance(dev, (torch.device, str)):
+        return torch.device(dev)
+    if torch.cuda.is_available():
+        return torch.device("cuda", torch.cuda.current_device())
+    return torch.device("cpu")
 
 
 def central_region(n: int):
@@ -45,8 +67,10 @@ def _bview(v):
 
 
 class CostVolumeReg(nn.Module):
-    def __init__(self, in_ch=32, base_filt=8, device=None, precision="fp32", conv_backend="auto", n_depth_est=5):
+    def __init__(self, in_ch=32, base_filt=8, device=None, precision="bf16", conv_backend="auto", n_depth_est=5):
         super().__init__()
+        if device is None:
+            device = default_device()
         f = base_filt
         mk = lambda i, o, s: nn.Conv3d(i, o, 3, stride=s, padding=1, bias=False, device=device)
         mkT = lambda i, o: nn.ConvTranspose3d(i, o, 3, stride=2, padding=1, bias=False, device=device)
@@ -76,7 +100,13 @@ class CostVolumeReg(nn.Module):
     def forward(self, cv: torch.Tensor) -> torch.Tensor:
         if not cv.is_cuda:
             raise _lib.MvsB200Error("CostVolumeReg.forward needs a CUDA tensor; mvs_b200 has no CPU path")
-        logits = self.logits(cv, conv_backends.get(self.conv_backend))
+        if not self.conv_out.weight.is_cuda:
+            raise _lib.MvsB200Error("CostVolumeReg parameters live on the CPU; build the module with device=cuda or move it "
+                                    "with .to(device) -- mvs_b200 has no CPU path")
+        # precision="fp32" means fp32: that mode's library convolutions run with TF32 off in forward AND backward, whatever
+        # the process-wide torch.backends flags say (conv3d.ExactTorchConvBackend); the bf16 mode runs on this library's kernels
+        be = conv_backends.ExactTorchConvBackend if self.precision == "fp32" else conv_backends.get(self.conv_backend)
+        logits = self.logits(cv, be)
         return ops.softmax_over_depth(logits, self.n_depth_est)
 
     # ------------------------------------------------------------------------------------------

@@ -6,7 +6,8 @@ provided by oracle/kornia_shim, see its docstring), patches ``config`` *before* 
 modules bind its constants, pushes seeded inputs through the reference's own
 functions on CPU and stores inputs + outputs as ``tests/golden/*.npz``.
 
-    python oracle/make_golden.py            # rewrites tests/golden/
+    python oracle/make_golden.py            # rewrites tests/golden/ (small cases, seconds)
+    python oracle/make_golden.py --fullsize # tests/golden/cfg1_digest.npz: the reference at BASELINE size (~1-2 min CPU)
 
 Nothing under tests/ or the product reads /root/reference at run time; the committed vectors are
 what travels to the GPU box.
@@ -55,11 +56,15 @@ def smooth_features(n, c, h, w, gen):
     return torch.nn.functional.conv2d(x, k, groups=c) * 3.0
 
 
-def run_case(name, B, V, D, h, w, d_scale, seed, keep_warped=False, with_reg=True, d_min_val=425.0):
+def run_case(name, B, V, D, h, w, d_scale, seed, keep_warped=False, with_reg=True, d_min_val=425.0, keep_gparam=None):
     ref = load_reference(D, d_scale, h * 4, w * 4)
     gen = torch.Generator().manual_seed(seed)
     K, R, T = ps.synthetic_cameras(B, V, h, w, seed=seed)
-    d_min = torch.full((B, 1, 1, 1), d_min_val)
+    keep_gparam = keep_warped if keep_gparam is None else keep_gparam
+    if isinstance(d_min_val, (list, tuple)):                          # unequal d_min per batch item (homography.py:26 quirk)
+        d_min = torch.tensor(d_min_val, dtype=torch.float32).reshape(B, 1, 1, 1)
+    else:
+        d_min = torch.full((B, 1, 1, 1), d_min_val)
     d_int = torch.ones(B, 1, 1, 1)
     feat = smooth_features(B * V, 32, h, w, gen).requires_grad_(True)
 
@@ -96,7 +101,7 @@ def run_case(name, B, V, D, h, w, d_scale, seed, keep_warped=False, with_reg=Tru
         out.update(prob=prob.detach(), logits=logit_box[0], depth=depth.detach(), gdepth=gd, gcv=grads[0])
         sd = {k: v.detach().clone() for k, v in reg.state_dict().items()}       # after 1 train fwd
         out.update({"bn_after/" + k: v for k, v in sd.items() if "running" in k or "tracked" in k})
-        if keep_warped:   # parameter gradients only in the tiny case (1.3 MB per copy)
+        if keep_gparam:   # parameter gradients only in the tiny case (1.3 MB per copy)
             out.update({"gparam/" + n: g for (n, _), g in zip(reg.named_parameters(), grads[1:])})
         # initial weights (identical for every case thanks to the fixed seed) are stored once
         wpath = os.path.join(OUT, "reg_weights.npz")
@@ -126,7 +131,67 @@ def run_depth_ties(name, seed=7):
     print(f"{name}: depth [{float(depth.min()):.2f}, {float(depth.max()):.2f}]")
 
 
+DIGEST_PLANES = [0, 1, 47, 96, 143, 191]
+DIGEST_COST_CH = [0, 13, 31]
+
+
+def run_fullsize_digest(name="cfg1_digest", seed=11):
+    """BASELINE.json configs[0]/[1] size (B=1, V=3, D=192, 128x160x32): the unmodified reference's whole hot path on CPU
+    (~1 min), stored as a DIGEST -- the depth map, the kept-plane ranks and their stability margin, sampled planes of the cost /
+    logit / probability volumes, BatchNorm running statistics -- because the full tensors (503 MB cost volume) cannot be
+    committed.  Inputs are rebuilt from the seed on the GPU box (ps.smooth_features_exact, checksum stored)."""
+    B, V, D, h, w = 1, 3, 192, 128, 160
+    d_scale = 480.0 / D
+    ref = load_reference(D, d_scale, h * 4, w * 4)
+    K, R, T = ps.synthetic_cameras(B, V, h, w, seed=seed)
+    d_min, d_int = torch.full((B, 1, 1, 1), 425.0), torch.ones(B, 1, 1, 1)
+    feat = ps.smooth_features_exact(B * V, 32, h, w, seed)
+    with torch.no_grad():
+        warped, d_batch, ref_idx = ref["homography"].homography_warping(K, R, T, d_min, d_int, feat, B, V)
+        cost = ref["costvolume"].assemble_cost_volume(warped, V)
+        del warped
+        torch.manual_seed(1234)
+        reg = ref["model"].CostVolumeReg()
+        reg.train()
+        box = []
+        reg.conv_out.register_forward_hook(lambda m, i, o: box.append(o.detach()))
+        prob = reg(cost)
+        depth = ref["depthmap"].extract_depth_map(prob, d_batch)
+    logits = box[0]
+    pn = prob.numpy()
+    odepth, ranks = ps.extract_depth(pn, d_batch.numpy())
+    ties = ps.tie_pixels(pn)
+    margin = ps.rank_margin(pn)
+    err = np.abs(odepth[:, 0] - depth.numpy()[:, 0])[~ties].max()
+    oprob = ps.reg_forward(_fresh_reg_state(ref), cost, train_bn=True)
+    perr = float((oprob - prob).abs().max() / prob.abs().max())
+    print(f"{name}: oracle-vs-reference at full size: depth (ties excluded) {err:.3e}, prob rel {perr:.3e}; ties {int(ties.sum())} px")
+    sd = reg.state_dict()
+    out = dict(B=B, V=V, D=D, h=h, w=w, d_scale=d_scale, seed=seed, K=K, R=R, T=T, d_min=d_min, d_int=d_int,
+               d_batch=d_batch, planes=np.array(DIGEST_PLANES), cost_ch=np.array(DIGEST_COST_CH),
+               feat_sum=np.float64(feat.double().sum().item()), feat_abs_sum=np.float64(feat.double().abs().sum().item()),
+               feat_probe=feat[:, ::11, ::37, ::41].numpy(),
+               cost=cost[:, DIGEST_COST_CH][:, :, DIGEST_PLANES].numpy(), cost_absmax=np.float32(cost.abs().max().item()),
+               logits=logits[:, :, DIGEST_PLANES].numpy(), logits_absmax=np.float32(logits.abs().max().item()),
+               prob=prob[:, :, DIGEST_PLANES].numpy(), prob_absmax=np.float32(prob.abs().max().item()),
+               depth=depth.numpy(), ranks=ranks.astype(np.int16), ties=ties, margin=margin.astype(np.float32),
+               oracle_prob_relerr=np.float64(perr), oracle_depth_abserr=np.float64(err))
+    out.update({"bn_after/" + k: v.numpy() for k, v in sd.items() if "running" in k or "tracked" in k})
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(f"{name}: depth [{float(depth.min()):.2f}, {float(depth.max()):.2f}], median rank margin {float(np.median(margin)):.2e}")
+
+
+def _fresh_reg_state(ref):
+    torch.manual_seed(1234)
+    return {k: v.detach().clone() for k, v in ref["model"].CostVolumeReg().state_dict().items()}
+
+
 def main():
+    if "--fullsize" in sys.argv:                   # ~1-2 min of CPU: kept out of the default regeneration
+        os.makedirs(OUT, exist_ok=True)
+        torch.set_num_threads(max(1, os.cpu_count() or 1))
+        run_fullsize_digest()
+        return
     os.makedirs(OUT, exist_ok=True)
     wpath = os.path.join(OUT, "reg_weights.npz")
     if os.path.exists(wpath):
@@ -138,6 +203,9 @@ def main():
     run_case("v7_odd", B=1, V=7, D=7, h=15, w=19, d_scale=70, seed=3)
     run_case("val_dmin0", B=1, V=3, D=8, h=16, w=20, d_scale=60, seed=4, with_reg=False, d_min_val=0.0)
     run_depth_ties("depth_ties")
+    # batch quirk (homography.py:26) with UNEQUAL d_min: flat view i reads depth row i mod B
+    run_case("bquirk_b2v3", B=2, V=3, D=8, h=16, w=20, d_scale=60, seed=5, keep_warped=True, keep_gparam=False,
+             d_min_val=[425.0, 520.0])
 
 
 if __name__ == "__main__":

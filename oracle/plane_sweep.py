@@ -376,6 +376,34 @@ def _rot(axis, ang):
     return np.eye(3) + np.sin(ang) * Kx + (1 - np.cos(ang)) * Kx @ Kx
 
 
+def smooth_features_exact(n, c, h, w, seed):
+    """Seeded conv-like (smooth) feature maps that regenerate BIT-IDENTICALLY on any host: CPU-generator white noise through a
+    3x3 box blur written as nine shifted adds in a fixed order (elementwise IEEE fp32 -- no library convolution whose summation
+    order could differ between CPUs).  Full-size fixtures (tests/golden/cfg1_digest.npz) store only digests of the reference's
+    outputs; the inputs are rebuilt from the seed by this function and verified against a stored checksum."""
+    gen = torch.Generator().manual_seed(int(seed))
+    x = torch.randn(n, c, h + 2, w + 2, generator=gen)
+    acc = torch.zeros(n, c, h, w)
+    for dy in range(3):
+        for dx in range(3):
+            acc = acc + x[:, :, dy:dy + h, dx:dx + w]
+    return acc * (1.0 / 3.0)
+
+
+def rank_margin(prob: np.ndarray, n_est: int = N_DEPTH_EST) -> np.ndarray:
+    """[B,h,w]: smallest relative gap between the probability of any plane j < n_est and any OTHER plane of the pixel.  The kept
+    set of scripts/depthmap.py:11-15 is {rank(j)}: a perturbation of every probability by less than margin/2 (relative) cannot
+    change it.  Parity tests of reduced-precision paths compare depth only where the reference's kept set is that stable."""
+    P = np.asarray(prob, dtype=np.float64)[:, 0]
+    B, D, h, w = P.shape
+    m = np.full((B, h, w), np.inf)
+    for j in range(min(n_est, D)):
+        gap = np.abs(P - P[:, j:j + 1])
+        gap[:, j] = np.inf
+        m = np.minimum(m, gap.min(1) / np.maximum(P[:, j], 1e-300))
+    return m
+
+
 def synthetic_cameras(batch_size, n_views, h=128, w=160, seed=0):
     """DTU-shaped cameras: views 0..2 are the real DTU cams of SURVEY App. C; further views are small
     seeded perturbations of them (the 49-camera table lives in a pickle that does not travel).

@@ -127,7 +127,7 @@ def test_reslab_and_row_reshard(world):
 
 def _reg(golden_dir, train=True):
     import mvs_b200
-    reg = mvs_b200.CostVolumeReg(device="cpu")
+    reg = mvs_b200.CostVolumeReg(device="cpu", precision="fp32")
     w0 = np.load(os.path.join(golden_dir, "reg_weights.npz"))
     reg.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in w0.items()})
     return reg.train(train)

@@ -11,7 +11,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, attached=False):
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     sys.path.insert(0, os.path.join(root, "deep-multiview-depth-estimation_b200"))
@@ -27,16 +27,27 @@ def _worker(rank, world, port, out):
     torch.manual_seed(7)
     x_all = torch.randn(8, 6); y_all = torch.randn(8, 1)
     x, y = x_all[rank::world], y_all[rank::world]       # shard the batch by rank
+    if attached:                                        # .grad of every parameter is a view into the flat bucket
+        red.attach_grads()
+        assert all(p.grad.untyped_storage().data_ptr() == red.bucket.untyped_storage().data_ptr() for p in params)
+        ((net(x) - y) ** 2).mean().backward()           # a first pass that the next step's bucket.zero_() must wipe
+        red.bucket.zero_()
     ((net(x) - y) ** 2).mean().backward()
     red.reduce()
+    if attached:
+        assert all(p.grad is v for p, v in zip(params, red.views))       # still the views: nothing was re-allocated
     out[rank] = [p.grad.clone() for p in params] + [p.detach().clone() for p in params]
     dist.destroy_process_group()
 
 
-def test_flat_bucket_allreduce_equals_full_batch_gradient():
+import pytest
+
+
+@pytest.mark.parametrize("attached", [False, True])
+def test_flat_bucket_allreduce_equals_full_batch_gradient(attached):
     world, port = 2, _free_port()
     mgr = mp.Manager(); out = mgr.dict()
-    mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, out, attached), nprocs=world, join=True)
     g0, g1 = out[0], out[1]
     for a, b in zip(g0, g1):
         assert torch.equal(a, b)                         # identical grads AND identical (broadcast) params

@@ -70,7 +70,6 @@ def test_cpu_tensors_are_refused_not_computed_on_a_fallback():
 def test_mvsnet_forward_sequence_through_the_dropins(golden_dir, name, monkeypatch):
     import mvs_b200
     import plane_sweep as ps
-    monkeypatch.setattr(torch.backends.cudnn, "allow_tf32", False)
     g = dict(np.load(os.path.join(golden_dir, name + ".npz")))
     t = lambda a: torch.from_numpy(np.asarray(a))
     B, V, D = int(g["B"]), int(g["V"]), int(g["D"])
@@ -83,7 +82,7 @@ def test_mvsnet_forward_sequence_through_the_dropins(golden_dir, name, monkeypat
     assert ref_idx.dtype == torch.int64 and not ref_idx.is_cuda and ref_idx.tolist() == list(range(0, B * V, V))
     cost = mods["costvolume"].assemble_cost_volume(warped, V)
     assert float((cost.detach().cpu() - t(g["cost"])).abs().max() / t(g["cost"]).abs().max()) < 1e-4
-    reg = mvs_b200.CostVolumeReg(device="cuda:0").train()
+    reg = mvs_b200.CostVolumeReg(device="cuda:0", precision="fp32").train()
     w0 = np.load(os.path.join(golden_dir, "reg_weights.npz"))
     reg.load_state_dict({k: t(v).to("cuda:0") for k, v in w0.items()})
     prob = reg(cost)
@@ -93,3 +92,54 @@ def test_mvsnet_forward_sequence_through_the_dropins(golden_dir, name, monkeypat
     assert np.abs(depth.detach().cpu().numpy()[:, 0] - g["depth"][:, 0])[ok].max() < 0.005 * step
     depth.sum().backward()
     assert feat.grad is not None and bool(torch.isfinite(feat.grad).all())
+
+
+_REAL_MODEL_SCRIPT = r"""
+import sys, os
+ROOT, REF = sys.argv[1], sys.argv[2]
+PKG = os.path.join(ROOT, "deep-multiview-depth-estimation_b200")
+sys.path.insert(0, REF)                                   # the reference's scripts/ (config, utils, model, ...)
+# ---- the swap of INTEGRATION.md section 2: drop-in modules shadow homography / costvolume / depthmap
+sys.path.insert(0, os.path.join(PKG, "dropin"))
+sys.path.insert(0, PKG)
+import torch
+import model                                             # the reference's UNMODIFIED scripts/model.py
+import mvs_b200
+model.CostVolumeReg = mvs_b200.CostVolumeReg             # the one rebinding (model.py:161 then builds the native regulariser)
+dropin = os.path.join(PKG, "dropin")
+for fn in (model.homography_warping, model.assemble_cost_volume, model.extract_depth_map):
+    assert os.path.dirname(os.path.abspath(sys.modules[fn.__module__].__file__)) == dropin, fn
+assert "kornia" not in sys.modules                       # the reference's own homography.py was never imported
+torch.manual_seed(0)
+net = model.MVSNet()                                     # exactly as train.py:159 / test.py:199 build it
+assert type(net.cost_volume_reg) is mvs_b200.CostVolumeReg
+assert net.cost_volume_reg.conv_0_0.weight.device.type == model.DEVICE.type     # reference default device=DEVICE (model.py:70)
+assert sum(p.numel() for p in net.parameters) == 382016  # MVSNet.parameters is a LIST (model.py:164-166); report Table 1
+B, V = 1, 3
+img = torch.randn(B * V, 3, 512, 640)
+K = torch.eye(3).repeat(B * V, 1, 1); R = torch.eye(3).repeat(B * V, 1, 1); T = torch.zeros(B * V, 3, 1)
+d_min, d_int = torch.full((B, 1, 1, 1), 425.0), torch.ones(B, 1, 1, 1)
+try:
+    with torch.no_grad():
+        net(img.to(model.DEVICE), K, R, T, d_min, d_int, B, V)
+except mvs_b200.MvsB200Error as e:
+    print("REACHED_NATIVE_PATH_NO_CUDA:", str(e)[:80])
+else:
+    print("FORWARD_RAN_ON", model.DEVICE)
+"""
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/scripts"), reason="the reference tree is only mounted in the authoring container")
+def test_real_reference_model_binds_the_dropins():
+    """The reference's UNMODIFIED scripts/model.py, imported with dropin/ ahead of scripts/ on sys.path and the one
+    CostVolumeReg rebinding of INTEGRATION.md: `model.homography_warping` & co. are the drop-ins, `MVSNet()` builds the native
+    regulariser with the reference's default device, and `MVSNet.forward` reaches the native path (here, without a GPU, its
+    refusal to compute on the CPU; on a CUDA machine the forward runs)."""
+    import subprocess
+    r = subprocess.run([sys.executable, "-c", _REAL_MODEL_SCRIPT, ROOT, "/root/reference/scripts"], capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    if torch.cuda.is_available():
+        assert "FORWARD_RAN_ON" in r.stdout, r.stdout
+    else:
+        assert "REACHED_NATIVE_PATH_NO_CUDA" in r.stdout, r.stdout

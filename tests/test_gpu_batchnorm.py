@@ -84,20 +84,15 @@ def test_bad_channel_count_raises():
 def test_regulariser_gradients_match_reference(golden_dir):
     """Whole CostVolumeReg on the GPU (fused BN kernels + convs + K4) against the reference's autograd."""
     g = dict(np.load(os.path.join(golden_dir, "tiny_b1v3.npz")))
-    reg = mvs_b200.CostVolumeReg(device=DEV)
+    reg = mvs_b200.CostVolumeReg(device=DEV, precision="fp32")       # owns its precision: no TF32 flag flip needed
     w0 = np.load(os.path.join(golden_dir, "reg_weights.npz"))
     reg.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in w0.items()})
     reg.train()
-    old = torch.backends.cudnn.allow_tf32
-    torch.backends.cudnn.allow_tf32 = False
-    try:
-        cv = torch.from_numpy(g["cost"]).to(DEV).requires_grad_(True)
-        prob = reg(cv)
-        depth = mvs_b200.extract_depth_map(prob, torch.from_numpy(g["d_batch"]).to(DEV))
-        names = [n for n, _ in reg.named_parameters()]
-        grads = torch.autograd.grad((depth * torch.from_numpy(g["gdepth"]).to(DEV)).sum(), [cv] + list(reg.parameters()))
-    finally:
-        torch.backends.cudnn.allow_tf32 = old
+    cv = torch.from_numpy(g["cost"]).to(DEV).requires_grad_(True)
+    prob = reg(cv)
+    depth = mvs_b200.extract_depth_map(prob, torch.from_numpy(g["d_batch"]).to(DEV))
+    names = [n for n, _ in reg.named_parameters()]
+    grads = torch.autograd.grad((depth * torch.from_numpy(g["gdepth"]).to(DEV)).sum(), [cv] + list(reg.parameters()))
     ref = g["gcv"]
     assert np.abs(grads[0].cpu().numpy() - ref).max() < 5e-4 * np.abs(ref).max()
     for n, gr in zip(names, grads[1:]):

@@ -178,7 +178,7 @@ def test_depth_slab_fp32_matches_reference_golden(golden_dir, name, monkeypatch)
     B, V, D, world = int(g["B"]), int(g["V"]), int(g["D"]), 2
     feat = t(g["feat"]).to("cuda:0")
     h, w = feat.shape[-2:]
-    reg = mvs_b200.CostVolumeReg(device="cuda:0").train()
+    reg = mvs_b200.CostVolumeReg(device="cuda:0", precision="fp32").train()
     w0 = np.load(os.path.join(golden_dir, "reg_weights.npz"))
     reg.load_state_dict({k: t(v).to("cuda:0") for k, v in w0.items()})
     regs = [copy.deepcopy(reg) for _ in range(world)]

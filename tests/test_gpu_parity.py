@@ -180,23 +180,48 @@ def test_few_planes_keep_everything():
 
 
 # ------------------------------------------------------------------------------------ regulariser
-def _reg(golden_dir, precision="fp32"):
-    reg = mvs_b200.CostVolumeReg(device=DEV, precision=precision)
+def _reg(golden_dir, **kw):
+    reg = mvs_b200.CostVolumeReg(**kw)
     w0 = np.load(os.path.join(golden_dir, "reg_weights.npz"))
     reg.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in w0.items()})
     return reg.train()
 
 
-@pytest.mark.parametrize("name", ["tiny_b1v3", "b2v3", "v7_odd"])
-def test_regulariser_fp32_matches_reference(golden_dir, name):
-    g = _load(golden_dir, name)
-    old = torch.backends.cudnn.allow_tf32
-    torch.backends.cudnn.allow_tf32 = False
+def test_default_constructor_is_the_native_path(golden_dir):
+    """`CostVolumeReg()` exactly as scripts/model.py:161 calls it: parameters on the CUDA device (reference default
+    device=DEVICE, model.py:70), convolutions on this library's tcgen05 kernels -- not the library fallback -- and the
+    probability volume inside the tolerance BASELINE.json states for that mode (1e-2, bf16 operands / fp32 accumulate),
+    with torch's TF32 switches left alone."""
+    from mvs_b200 import ops
+    g = _load(golden_dir, "tiny_b1v3")
+    torch.manual_seed(1234)
+    reg = mvs_b200.CostVolumeReg()
+    assert reg.precision == "bf16" and all(p.is_cuda for p in reg.parameters())
+    w0 = np.load(os.path.join(golden_dir, "reg_weights.npz"))
+    for k, v in reg.state_dict().items():                      # seed 1234 on the CUDA generator: same shapes and keys
+        assert tuple(v.shape) == w0[k].shape, k
+    reg.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in w0.items()})
+    reg.train()
+    ops.EVENTS = {}
     try:
-        reg = _reg(golden_dir)
-        prob = reg(_t(g["cost"], DEV))
+        prob = reg(_t(g["cost"], DEV))                          # fp32 volume in, as assemble_cost_volume returns it
+        torch.cuda.synchronize()
+        ran = set(ops.EVENTS)
     finally:
-        torch.backends.cudnn.allow_tf32 = old
+        ops.EVENTS = None
+    assert {"conv3d_s1_tc", "conv3d_s2_tc", "deconv3d_s2_tc", "conv_out_fwd", "bn_stats"} <= ran, ran
+    assert prob.dtype == torch.float32 and tuple(prob.shape) == g["prob"].shape
+    assert _relmax(prob.detach().cpu().numpy(), g["prob"]) < 1e-2
+
+
+@pytest.mark.parametrize("allow_tf32", [True, False])
+@pytest.mark.parametrize("name", ["tiny_b1v3", "b2v3", "v7_odd"])
+def test_regulariser_fp32_matches_reference(golden_dir, name, allow_tf32, monkeypatch):
+    """precision="fp32" owns its precision: 1e-4 whatever torch.backends.cudnn.allow_tf32 says."""
+    monkeypatch.setattr(torch.backends.cudnn, "allow_tf32", allow_tf32)
+    g = _load(golden_dir, name)
+    reg = _reg(golden_dir, device=DEV, precision="fp32")
+    prob = reg(_t(g["cost"], DEV))
     assert _relmax(prob.detach().cpu().numpy(), g["prob"]) < 1e-4
     sd = reg.state_dict()
     for k, v in g.items():
@@ -204,35 +229,57 @@ def test_regulariser_fp32_matches_reference(golden_dir, name):
             assert np.allclose(sd[k[len("bn_after/"):]].cpu().numpy(), v, rtol=1e-4, atol=1e-6), k
 
 
-@pytest.mark.parametrize("name", ["tiny_b1v3", "v7_odd"])
+@pytest.mark.parametrize("name", ["tiny_b1v3", "b2v3", "v7_odd", "bquirk_b2v3"])
 def test_regulariser_bf16(golden_dir, name):
     g = _load(golden_dir, name)
-    reg = _reg(golden_dir, "bf16")
+    reg = _reg(golden_dir, device=DEV)                          # default precision: bf16 operands on tcgen05
     prob = reg(_t(g["cost"], DEV).to(torch.bfloat16))
     assert _relmax(prob.detach().cpu().numpy(), g["prob"]) < 1e-2
+    prob32 = _reg(golden_dir, device=DEV)(_t(g["cost"], DEV))  # fp32 volume in: converted inside
+    assert _relmax(prob32.detach().cpu().numpy(), g["prob"]) < 1e-2
+
+
+def test_cpu_parameters_are_refused(golden_dir):
+    g = _load(golden_dir, "tiny_b1v3")
+    reg = mvs_b200.CostVolumeReg(device="cpu")
+    with pytest.raises(mvs_b200.MvsB200Error, match="CPU"):
+        reg(_t(g["cost"], DEV))
 
 
 def test_hot_path_end_to_end_like_mvsnet_forward(golden_dir):
-    """The call sequence of MVSNet.forward (model.py:177-187) on the drop-in functions, incl. backward."""
+    """The call sequence of MVSNet.forward (model.py:177-187) on the drop-in functions, incl. backward (fp32 mode, 1e-4 class)."""
     g = _load(golden_dir, "tiny_b1v3")
-    old = torch.backends.cudnn.allow_tf32
-    torch.backends.cudnn.allow_tf32 = False
-    try:
-        reg = _reg(golden_dir)
-        feat = _t(g["feat"], DEV).requires_grad_(True)
-        warped, d_batch, ref_views = mvs_b200.homography_warping(*_sweep_inputs(g), feat, 1, 3, 8, 60)
-        cost = mvs_b200.assemble_cost_volume(warped, 3)
-        prob = reg(cost)
-        depth = mvs_b200.extract_depth_map(prob, d_batch)
-        (depth * _t(g["gdepth"], DEV)).sum().backward()
-    finally:
-        torch.backends.cudnn.allow_tf32 = old
+    reg = _reg(golden_dir, device=DEV, precision="fp32")
+    feat = _t(g["feat"], DEV).requires_grad_(True)
+    warped, d_batch, ref_views = mvs_b200.homography_warping(*_sweep_inputs(g), feat, 1, 3, 8, 60)
+    cost = mvs_b200.assemble_cost_volume(warped, 3)
+    prob = reg(cost)
+    depth = mvs_b200.extract_depth_map(prob, d_batch)
+    (depth * _t(g["gdepth"], DEV)).sum().backward()
     ok = ~ps.tie_pixels(g["prob"])
     assert np.abs(depth.detach().cpu().numpy()[:, 0] - g["depth"][:, 0])[ok].max() < 0.005 * 60
     assert feat.grad is not None and torch.isfinite(feat.grad).all()
     gw = dict(reg.named_parameters())["conv_out.weight"].grad.cpu().numpy()
     ref = g["gparam/conv_out.weight"]
     assert np.abs(gw - ref).max() < 1e-3 * np.abs(ref).max()
+
+
+def test_batch_quirk_with_unequal_d_min(golden_dir):
+    """scripts/homography.py:26 tiles the depth table V times along dim 0 while the matrices are ordered b*V+v: flat view i reads
+    depth row i mod B.  Golden from the unmodified reference with d_min = (425, 520): the CUDA path reproduces the quirk."""
+    g = _load(golden_dir, "bquirk_b2v3")
+    assert float(g["d_min"].ravel()[0]) != float(g["d_min"].ravel()[1])
+    feat = _t(g["feat"], DEV).requires_grad_(True)
+    cost, warped, d_batch, _ = _cost_from_golden_inputs(g, feat)
+    assert np.array_equal(d_batch.cpu().numpy(), g["d_batch"])
+    assert _relmax(warped.materialize().cpu().numpy(), g["warped"]) < 1e-4
+    assert _relmax(cost.detach().cpu().numpy(), g["cost"]) < 1e-4
+    (gf,) = torch.autograd.grad((cost * _t(g["gcost"], DEV)).sum(), feat)
+    assert _relmax(gf.cpu().numpy(), g["gfeat"]) < 1e-4
+    # and the geometrically intended table gives something else (the quirk is really exercised)
+    w2, _, _ = mvs_b200.api.homography_warping(*_sweep_inputs(g), feat.detach(), 2, 3, int(g["D"]), int(g["d_scale"]), bug_compatible=False)
+    c2 = mvs_b200.assemble_cost_volume(w2, 3)
+    assert _relmax(c2.cpu().numpy(), g["cost"]) > 1e-2
 
 
 # ------------------------------------------------------------------- oracle on seeded inputs, errors

@@ -128,3 +128,41 @@ def test_depth_ties(golden_dir):
     assert (err[ties] < 0.005 * 40).mean() > 0.5
     lit = ps.extract_depth_torch(_t(g["prob"]), _t(g["d_batch"])).numpy()
     assert np.abs(lit - depth)[~np.isnan(lit)].max() < 1e-3
+
+
+def test_batch_quirk_golden_with_unequal_d_min(golden_dir):
+    """scripts/homography.py:26: the depth table is tiled V times along dim 0 while views are ordered b*V+v, so flat view i reads
+    depth row i mod B.  Golden with d_min = (425, 520) from the unmodified reference: the oracle reproduces it in bug-compatible
+    mode and does NOT with the geometrically intended rows."""
+    g = _load(golden_dir, "bquirk_b2v3")
+    assert float(g["d_min"].ravel()[0]) != float(g["d_min"].ravel()[1])
+    args = (_t(g["feat"]), g["K"], g["R"], g["T"], _t(g["d_min"]), _t(g["d_int"]), 2, 3, int(g["D"]), int(g["d_scale"]))
+    cost, warped, _ = ps.plane_sweep_cost(*args)
+    assert _relmax(warped, g["warped"]) < 1e-4 and _relmax(cost, g["cost"]) < 1e-4
+    cost_fixed, _, _ = ps.plane_sweep_cost(*args, bug_compatible=False)
+    assert _relmax(cost_fixed, g["cost"]) > 1e-2
+    w0 = {k: _t(v).clone() for k, v in np.load(os.path.join(golden_dir, "reg_weights.npz")).items()}
+    prob = ps.reg_forward(w0, _t(g["cost"]), train_bn=True)
+    assert _relmax(prob.numpy(), g["prob"]) < 1e-4
+
+
+def test_fullsize_digest_inputs_regenerate_and_oracle_was_pinned_there(golden_dir):
+    """tests/golden/cfg1_digest.npz (the reference at BASELINE size, oracle/make_golden.py --fullsize): its seeded inputs
+    regenerate bit-identically, the kept ranks stored are consistent with the stored depth map, and the oracle's restatement
+    agreed with the reference at that size when the digest was made."""
+    g = _load(golden_dir, "cfg1_digest")
+    feat = ps.smooth_features_exact(3, 32, 128, 160, int(g["seed"]))
+    assert np.array_equal(feat[:, ::11, ::37, ::41].numpy(), g["feat_probe"])
+    assert abs(feat.double().sum().item() - float(g["feat_sum"])) <= 1e-9 * float(g["feat_abs_sum"])
+    K, R, T = ps.synthetic_cameras(1, 3, 128, 160, seed=int(g["seed"]))
+    assert np.array_equal(K.numpy(), g["K"]) and np.array_equal(R.numpy(), g["R"]) and np.array_equal(T.numpy(), g["T"])
+    assert float(g["oracle_prob_relerr"]) < 1e-6 and float(g["oracle_depth_abserr"]) < 0.005 * float(g["d_scale"])
+    assert g["ranks"].shape == (1, 5, 128, 160) and int(g["ties"].sum()) < 20
+    lo, hi = float(g["d_batch"].min()), float(g["d_batch"].max())
+    assert lo <= float(g["depth"].min()) and float(g["depth"].max()) <= hi
+    # cost samples against the oracle's sampler on the same planes (the CPU oracle at full size, sampled)
+    planes = g["planes"].tolist()
+    prm = ps.view_params_closed64(g["K"], g["R"], g["T"], 1, 3, 128, 160)
+    ix, iy = ps.sample_positions_closed64(prm, g["d_batch"].reshape(1, -1)[[0, 0, 0]][:, planes], 128, 160)
+    ref = ps.variance_cost(ps.bilinear_grid_sample(feat, _t(ix), _t(iy)), 3).numpy()
+    assert np.abs(ref[:, g["cost_ch"].tolist()] - g["cost"]).max() / float(g["cost_absmax"]) < 1e-4

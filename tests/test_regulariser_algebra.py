@@ -16,7 +16,7 @@ def _load(golden_dir, name):
 
 
 def _reg(golden_dir):
-    reg = mvs_b200.CostVolumeReg(device="cpu")
+    reg = mvs_b200.CostVolumeReg(device="cpu", precision="fp32")
     w0 = np.load(os.path.join(golden_dir, "reg_weights.npz"))
     reg.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in w0.items()})     # reference key names
     return reg
@@ -29,7 +29,7 @@ def _relmax(a, b):
 def test_state_dict_keys_and_init_match_reference(golden_dir):
     w0 = np.load(os.path.join(golden_dir, "reg_weights.npz"))
     torch.manual_seed(1234)                                   # seed used by oracle/make_golden.py
-    reg = mvs_b200.CostVolumeReg(device="cpu")
+    reg = mvs_b200.CostVolumeReg(device="cpu", precision="fp32")
     sd = reg.state_dict()
     assert sorted(sd.keys()) == sorted(w0.keys())
     for k in w0:
