@@ -1,4 +1,5 @@
-# gpurun payload, one B200:  gpurun --timeout 1500 -- 'bash tools/_run.sh'
+# gpurun payload, one B200:  gpurun --timeout 1200 -- 'bash tools/_run.sh'
 timeout 600 python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
 timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "rc=$?" >> gpurun_out/smoke.log
-timeout 400 python bench.py > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err; echo "rc=$?" >> gpurun_out/bench_final.err
+timeout 500 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "rc=$?" >> gpurun_out/bench.err
+tail -3 gpurun_out/pytest_gpu.log; cat gpurun_out/smoke.log | tail -3; tail -2 gpurun_out/bench.err; head -c 600 gpurun_out/bench.json
