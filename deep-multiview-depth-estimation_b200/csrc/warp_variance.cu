@@ -16,48 +16,24 @@
 //   * all V samples of a voxel are in registers => mean, then sum (f - mean)^2, exactly the reference's
 //     two-pass variance (the sum f / sum f^2 moment form loses the 1e-4 target).
 //   * the [B,D,h,w,C] volume is written once with streaming 16 B stores; warped volumes never exist.
-#include "common.cuh"
+#include "warp_common.cuh"
 #include <limits.h>
 #include <stdlib.h>
 
 using namespace mvsb200;
+using namespace mvsb200::warp;
+
+namespace mvsb200 {
+namespace warp {
+int warp_variance_fwd3(const float* feat, const float* vp, const float* tinv, void* cost, int dtype, int B, int V, int D, int h,
+                       int w, cudaStream_t st);
+}  // namespace warp
+}  // namespace mvsb200
 
 namespace {
 
-struct __align__(16) ViewParams {
-    float A[9];
-    float g[3];
-    float r[3];
-    float pad;
-};
-static_assert(sizeof(ViewParams) == MVSB200_VIEW_PARAM_FLOATS * 4, "view param size");
-
-constexpr int kC = 32;          // channels (CostVolumeReg in_ch, scripts/model.py:70)
-constexpr int kSlots = kC / 4;  // float4 slots per voxel row
 constexpr int kWX = 2, kWY = 4; // warps per CTA along x / y
 constexpr int kThreads = 32 * kWX * kWY;
-
-struct PixelView {  // per (pixel, view) constants of the rank-one form
-    float a0, a1, a2, c;
-};
-
-__device__ __forceinline__ PixelView pixel_view(const ViewParams& p, float x, float y) {
-    PixelView o;
-    o.a0 = fmaf(p.A[0], x, fmaf(p.A[1], y, p.A[2]));
-    o.a1 = fmaf(p.A[3], x, fmaf(p.A[4], y, p.A[5]));
-    o.a2 = fmaf(p.A[6], x, fmaf(p.A[7], y, p.A[8]));
-    o.c = fmaf(p.r[0], x, fmaf(p.r[1], y, p.r[2]));
-    return o;
-}
-
-// 1/x to <= 1 ulp (MUFU.RCP): sampling-position error ~2e-5 px, below the 9e-5 px by which the reference's own
-// fp32 matrix chain deviates from exact arithmetic.  Every kernel uses this same reciprocal so
-// that forward, backward and the materialised volumes agree on the footprints.
-__device__ __forceinline__ float rcp_approx(float x) {
-    float r;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
 
 struct Sample {  // bilinear footprint of one sampling position
     int x0, y0;
@@ -143,50 +119,8 @@ __device__ __forceinline__ void ldg_f4_if(float4& t, const float4* p, int pred) 
                  : "+f"(t.x), "+f"(t.y), "+f"(t.z), "+f"(t.w) : "l"(p), "r"(pred));
 }
 
-// branch-free refresh of a cached footprint: predicated loads keep both source views' loads in one basic block
-template <int NV4, int KSTRIDE>
-__device__ __forceinline__ void load_taps_clamped_if(const float4* __restrict__ flane, int x0, int y0, int h, int w,
-                                                     float4 (&t)[4][NV4], int pred) {
-    const int xa = min(max(x0, 0), w - 1), xb = min(max(x0 + 1, 0), w - 1);
-    const int ya = min(max(y0, 0), h - 1) * w, yb = min(max(y0 + 1, 0), h - 1) * w;
-    const int o[4] = {ya + xa, ya + xb, yb + xa, yb + xb};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const float4* p = flane + (unsigned)o[j] * (unsigned)kSlots;
-#pragma unroll
-        for (int k = 0; k < NV4; ++k) ldg_f4_if(t[j][k], p + k * KSTRIDE, pred);
-    }
-}
-
-template <int NV4, int KSTRIDE>
-__device__ __forceinline__ void load_taps_clamped(const float4* __restrict__ flane, int x0, int y0, int h, int w,
-                                                  float4 (&t)[4][NV4]) {
-    const int xa = min(max(x0, 0), w - 1), xb = min(max(x0 + 1, 0), w - 1);
-    const int ya = min(max(y0, 0), h - 1) * w, yb = min(max(y0 + 1, 0), h - 1) * w;
-    const int o[4] = {ya + xa, ya + xb, yb + xa, yb + xb};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const float4* p = flane + (unsigned)o[j] * (unsigned)kSlots;
-#pragma unroll
-        for (int k = 0; k < NV4; ++k) t[j][k] = __ldg(p + k * KSTRIDE);
-    }
-}
-
-__device__ __forceinline__ float2 lo2(const float4& v) { return make_float2(v.x, v.y); }
-__device__ __forceinline__ float2 hi2(const float4& v) { return make_float2(v.z, v.w); }
-
-// same operation order as blend(): fma(w11,t11, fma(w10,t10, fma(w01,t01, w00*t00)))
-__device__ __forceinline__ void blend2(const Sample2& s, const float4& t00, const float4& t01, const float4& t10,
-                                       const float4& t11, float2& lo, float2& hi) {
-    const float2 a = make_float2(s.w00, s.w00), b = make_float2(s.w01, s.w01), c = make_float2(s.w10, s.w10),
-                 d = make_float2(s.w11, s.w11);
-    lo = __ffma2_rn(d, lo2(t11), __ffma2_rn(c, lo2(t10), __ffma2_rn(b, lo2(t01), __fmul2_rn(a, lo2(t00)))));
-    hi = __ffma2_rn(d, hi2(t11), __ffma2_rn(c, hi2(t10), __ffma2_rn(b, hi2(t01), __fmul2_rn(a, hi2(t00)))));
-}
-
-// scalar twin of variance2: plain FADD/FFMA can issue on either FMA sub-pipe, the packed f32x2 forms only on the heavy one
-// (profiles/r01_k1_notes.md) -- the forward kernel blends with packed math and takes the variance with scalar math so
-// that both sub-pipes work
+// population variance over V samples, two-pass as costvolume.py:12-14 (mean, then sum (x-mean)^2, / V).  Scalar math: plain
+// FADD/FFMA can issue on either FMA sub-pipe, the packed f32x2 forms only on the heavy one (profiles/r01_k1_notes.md)
 template <int V>
 __device__ __forceinline__ float variance1(const float (&x)[V], float ninv, float inv_out) {
     float sum = x[0];
@@ -201,65 +135,6 @@ __device__ __forceinline__ float variance1(const float (&x)[V], float ninv, floa
         acc = fmaf(d, d, acc);
     }
     return acc * inv_out;
-}
-
-// population variance over V samples, two-pass as costvolume.py:12-14 (mean, then sum (x-mean)^2, / V)
-template <int V>
-__device__ __forceinline__ float2 variance2(const float2 (&x)[V], float2 ninv, float2 inv_out) {
-    float2 sum = x[0];
-#pragma unroll
-    for (int v = 1; v < V; ++v) sum = __fadd2_rn(sum, x[v]);
-    const float2 nmean = __fmul2_rn(sum, ninv);               // -(sum/V), exact negation of the mean
-    float2 d = __fadd2_rn(x[0], nmean);
-    float2 acc = __fmul2_rn(d, d);
-#pragma unroll
-    for (int v = 1; v < V; ++v) {
-        d = __fadd2_rn(x[v], nmean);
-        acc = __ffma2_rn(d, d, acc);
-    }
-    return __fmul2_rn(acc, inv_out);
-}
-
-
-// Which float4 slots of the 32-channel row a lane owns.  fp32 rows: interleaved so that each store
-// instruction of a pixel's lane group covers a contiguous 16*LPP bytes; bf16 rows: contiguous channels
-// per lane so that one lane emits one 8/16-byte store.
-template <int NV4, bool CONTIG>
-__device__ __forceinline__ void lane_slots(int cg, int (&slot)[NV4]) {
-    constexpr int LPP = kSlots / NV4;
-#pragma unroll
-    for (int k = 0; k < NV4; ++k) slot[k] = CONTIG ? cg * NV4 + k : cg + k * LPP;
-}
-
-struct TileCoord {
-    int b, d0, nd, x, y, cg;
-    bool active;
-};
-
-template <int NV4>
-__device__ __forceinline__ TileCoord tile_coord(int D, int h, int w, int dchunk, int tiles_x) {
-    constexpr int LPP = kSlots / NV4, PPW = 32 / LPP;
-    TileCoord t;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    t.b = blockIdx.z;
-    t.d0 = blockIdx.y * dchunk;
-    t.nd = min(dchunk, D - t.d0);
-    const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
-    t.x = (tx * kWX + (warp % kWX)) * PPW + lane / LPP;
-    t.y = ty * kWY + warp / kWX;
-    t.cg = lane % LPP;
-    t.active = t.x < w && t.y < h;
-    return t;
-}
-
-template <int V>
-__device__ __forceinline__ void stage_tinv(float* s_tinv, const float* __restrict__ tinv, int b, int D, int d0, int nd,
-                                           int dchunk) {
-    for (int i = threadIdx.x; i < (V - 1) * nd; i += kThreads) {
-        const int v = i / nd, dd = i - v * nd;
-        s_tinv[v * dchunk + dd] = tinv[(size_t)(b * V + v + 1) * D + d0 + dd];
-    }
-    __syncthreads();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -309,116 +184,6 @@ struct FwdCfg {
     static constexpr size_t kSmem = 2 * (size_t)kRecs * 2 * sizeof(float4);      // double-buffered, weights + offsets
 };
 
-template <int V, bool BF16OUT>
-__global__ void __launch_bounds__(kThreads, V <= 3 ? 3 : (V <= 5 ? 2 : 1))
-warp_variance_fwd_kernel(const float4* __restrict__ feat, const ViewParams* __restrict__ vp, const float* __restrict__ tinv,
-                         void* __restrict__ cost, int D, int h, int w, int dchunk, int tiles_x) {
-    constexpr int RUN = FwdCfg<V>::kRunV, RECS = FwdCfg<V>::kRecs;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    // structure-of-arrays records, [buffer][V-1][RUN][kPix]: consecutive pixels are consecutive 16-byte words
-    float4* rec_w = reinterpret_cast<float4*>(smem_raw);
-    int4* rec_o = reinterpret_cast<int4*>(smem_raw) + 2 * RECS;
-
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int b = blockIdx.z, d0 = blockIdx.y * dchunk, nd = min(dchunk, D - d0);
-    const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
-    const unsigned plane = (unsigned)h * (unsigned)w;
-    const ViewParams* vpb = vp + (size_t)b * V;
-
-    // ---- phase-1 identity: pixel slot p1, plane lane q
-    const int p1 = threadIdx.x & (kPix - 1), q = threadIdx.x >> 5;
-    PixelView pv1[V];
-    {
-        const float x1 = (float)(tx * kTX + (p1 & (kTX - 1))), y1 = (float)(ty * kTY + p1 / kTX);
-#pragma unroll
-        for (int v = 1; v < V; ++v) pv1[v] = pixel_view(vpb[v], x1, y1);
-    }
-    auto stage_run = [&](int run0, int buf) {        // phase 1: footprint records of planes [run0, run0+RUN)
-        const int nrun = min(RUN, nd - run0);
-#pragma unroll
-        for (int v = 1; v < V; ++v) {
-            const float gx = vpb[v].g[0], gy = vpb[v].g[1], gz = vpb[v].g[2];
-            const float* tv = tinv + (size_t)(b * V + v) * D + d0 + run0;
-            for (int dd = q; dd < nrun; dd += kThreads / kPix) {
-                const FootRec r = make_record(pv1[v], gx, gy, gz, __ldg(tv + dd), h, w);
-                const int i = buf * RECS + ((v - 1) * RUN + dd) * kPix + p1;
-                rec_w[i] = make_float4(r.w00, r.w01, r.w10, r.w11);
-                rec_o[i] = make_int4(r.o00, r.o01, r.o10, r.o11);
-            }
-        }
-    };
-
-    // ---- phase-2 identity: pixel slot pl, channels 4*cg .. 4*cg+3
-    const int pl = warp * (32 / kLanesPerPixel) + lane / kLanesPerPixel, cg = lane % kLanesPerPixel;
-    const int px = tx * kTX + (pl & (kTX - 1)), py = ty * kTY + pl / kTX;
-    const bool active = px < w && py < h;
-    const float4* fb = feat + (size_t)(b * V) * plane * kSlots + cg;
-
-    stage_run(0, 0);
-
-    float2 ref[2];                                   // reference view: H = I on every plane => one sample per pixel
-    {
-        const PixelView pv = pixel_view(vpb[0], (float)px, (float)py);
-        const FootRec r = make_record(pv, 0.f, 0.f, 0.f, 0.f, h, w);
-        const float4 t00 = __ldg(fb + (unsigned)r.o00 * kSlots), t01 = __ldg(fb + (unsigned)r.o01 * kSlots),
-                     t10 = __ldg(fb + (unsigned)r.o10 * kSlots), t11 = __ldg(fb + (unsigned)r.o11 * kSlots);
-        blend2w(r.w00, r.w01, r.w10, r.w11, t00, t01, t10, t11, ref[0], ref[1]);
-    }
-
-    float4 taps[V][4];
-    int k00[V], k11[V];
-#pragma unroll
-    for (int v = 1; v < V; ++v) {
-        k00[v] = -1; k11[v] = -1;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) taps[v][j] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    const float invV = 1.0f / (float)V;
-    const float2 ninv = make_float2(-invV, -invV), inv_out = make_float2(invV, invV);
-    __syncthreads();
-
-    int buf = 0;
-    for (int run0 = 0; run0 < nd; run0 += RUN, buf ^= 1) {
-        const int nrun = min(RUN, nd - run0);
-        if (run0 + RUN < nd) stage_run(run0 + RUN, buf ^ 1);   // next run's records, other buffer
-        if (active) {
-            // ---- phase 2
-            size_t vox = ((size_t)(b * D + d0 + run0) * h + py) * w + px;
-            const float4* rw = rec_w + buf * RECS + pl;
-            const int4* ro = rec_o + buf * RECS + pl;
-            for (int dd = 0; dd < nrun; ++dd, vox += plane) {
-                float2 val[2][V];
-                val[0][0] = ref[0]; val[1][0] = ref[1];
-#pragma unroll
-                for (int v = 1; v < V; ++v) {
-                    const float4 wt = rw[((v - 1) * RUN + dd) * kPix];
-                    const int4 of = ro[((v - 1) * RUN + dd) * kPix];
-                    const int changed = (of.x != k00[v]) | (of.w != k11[v]);
-                    const float4* fv = fb + (size_t)v * plane * kSlots;
-                    ldg_f4_if(taps[v][0], fv + (unsigned)of.x * kSlots, changed);
-                    ldg_f4_if(taps[v][1], fv + (unsigned)of.y * kSlots, changed);
-                    ldg_f4_if(taps[v][2], fv + (unsigned)of.z * kSlots, changed);
-                    ldg_f4_if(taps[v][3], fv + (unsigned)of.w * kSlots, changed);
-                    k00[v] = of.x; k11[v] = of.w;
-                    blend2w(wt.x, wt.y, wt.z, wt.w, taps[v][0], taps[v][1], taps[v][2], taps[v][3], val[0][v], val[1][v]);
-                }
-                float xs[4][V];
-#pragma unroll
-                for (int v = 0; v < V; ++v) { xs[0][v] = val[0][v].x; xs[1][v] = val[0][v].y; xs[2][v] = val[1][v].x; xs[3][v] = val[1][v].y; }
-                const float2 r0 = make_float2(variance1<V>(xs[0], -invV, invV), variance1<V>(xs[1], -invV, invV));
-                const float2 r1 = make_float2(variance1<V>(xs[2], -invV, invV), variance1<V>(xs[3], -invV, invV));
-                if (BF16OUT) {
-                    __nv_bfloat16* row = reinterpret_cast<__nv_bfloat16*>(cost) + vox * kC + 4 * cg;
-                    st_cs_u2(row, pack_bf16x2(r0.x, r0.y), pack_bf16x2(r1.x, r1.y));
-                } else {
-                    st_cs_f4(reinterpret_cast<float4*>(cost) + vox * kSlots + cg, make_float4(r0.x, r0.y, r1.x, r1.y));
-                }
-            }
-        }
-        __syncthreads();                             // next buffer staged by everyone, this buffer consumed
-    }
-}
-
 // ------------------------------------------------------------------------------------------------
 // K1 forward, second form ("one offset"): same two phases, fewer instructions per plane and no CTA barrier.
 //   * the 2x2 footprint is addressed from ONE clamped base (xc, yc) in [0, w-2] x [0, h-2]: the taps are base, base + one
@@ -430,38 +195,6 @@ warp_variance_fwd_kernel(const float4* __restrict__ feat, const ViewParams* __re
 //     __syncthreads, warps drift apart instead of convoying through phase 1 together;
 //   * V = 3: population variance from the three pairwise differences, ((a-b)^2 + (a-c)^2 + (b-c)^2) / 9 -- algebraically
 //     the two-pass value, no cancellation, 7 packed operations per channel pair instead of 10.
-struct __align__(16) FootRec1 {
-    float w00, w01, w10, w11;     // weights of the taps at base, base+1, base+line, base+line+1
-    int off;                      // byte offset of the base tap inside the view's feature map
-};
-
-__device__ __forceinline__ FootRec1 make_record1(const PixelView& pv, float gx, float gy, float gz, float t, int h, int w) {
-    const float m = pv.c * t;
-    const float qx = fmaf(gx, m, pv.a0), qy = fmaf(gy, m, pv.a1), qz = fmaf(gz, m, pv.a2);
-    const float rz = rcp_approx(qz);
-    float ix = fmaf(qx, rz, -0.5f), iy = fmaf(qy, rz, -0.5f);
-    ix = fminf(fmaxf(ix, -2.0f), (float)(w + 1));   // NaN -> -2: footprint entirely out of bounds
-    iy = fminf(fmaxf(iy, -2.0f), (float)(h + 1));
-    const float fx0 = floorf(ix), fy0 = floorf(iy);
-    const int x0 = (int)fx0, y0 = (int)fy0;
-    const float wx1 = ix - fx0, wy1 = iy - fy0;
-    float ax = ((unsigned)x0 < (unsigned)w) ? 1.0f - wx1 : 0.f, bx = ((unsigned)(x0 + 1) < (unsigned)w) ? wx1 : 0.f;
-    float ay = ((unsigned)y0 < (unsigned)h) ? 1.0f - wy1 : 0.f, by = ((unsigned)(y0 + 1) < (unsigned)h) ? wy1 : 0.f;
-    if (x0 < 0) { ax = bx; bx = 0.f; } else if (x0 > w - 2) { bx = ax; ax = 0.f; }
-    if (y0 < 0) { ay = by; by = 0.f; } else if (y0 > h - 2) { by = ay; ay = 0.f; }
-    const int xc = min(max(x0, 0), w - 2), yc = min(max(y0, 0), h - 2);
-    FootRec1 r;
-    r.w00 = ax * ay; r.w01 = bx * ay; r.w10 = ax * by; r.w11 = bx * by;
-    if (t != t) { r.w00 = NAN; r.w01 = NAN; r.w10 = NAN; r.w11 = NAN; }      // d == 0 plane: the reference's whole plane is NaN
-    r.off = (yc * w + xc) * (kC * 4);
-    return r;
-}
-
-__device__ __forceinline__ void ldg_f4_if_b(float4& t, const char* p, int pred) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %5, 0;\n\t@p ld.global.nc.L1::evict_last.v4.f32 {%0,%1,%2,%3}, [%4];\n\t}"
-                 : "+f"(t.x), "+f"(t.y), "+f"(t.z), "+f"(t.w) : "l"(p), "r"(pred));
-}
-
 // population variance of three samples from their pairwise differences (packed fp32)
 __device__ __forceinline__ float2 variance3_pairwise(float2 a, float2 b, float2 c, float2 ninth) {
     const float2 nb = make_float2(-b.x, -b.y), nc = make_float2(-c.x, -c.y);
@@ -476,7 +209,29 @@ struct Fwd2Cfg {
     static constexpr size_t kSmem = (size_t)(kThreads / 32) * 2 * kWRec * (sizeof(float4) + sizeof(int));
 };
 
-template <int V, bool BF16OUT>
+// two-difference form of the same variance: d1 = b - a, d2 = c - a, var = (2/9)(d1 (d1 - d2) + d2^2)  (6 operations)
+__device__ __forceinline__ float2 variance3_two_diff(float2 a, float2 b, float2 c) {
+    const float2 m1 = make_float2(-1.f, -1.f);
+    const float2 d1 = __ffma2_rn(a, m1, b), d2 = __ffma2_rn(a, m1, c);
+    const float2 t = __ffma2_rn(d1, __ffma2_rn(d2, m1, d1), __fmul2_rn(d2, d2));
+    return __fmul2_rn(t, make_float2(2.0f / 9.0f, 2.0f / 9.0f));
+}
+__device__ __forceinline__ float variance3_two_diff1(float a, float b, float c) {
+    const float d1 = b - a, d2 = c - a;
+    return fmaf(d1, d1 - d2, d2 * d2) * (2.0f / 9.0f);
+}
+__device__ __forceinline__ void blend1w(const float4& wt, const float4& t00, const float4& t01, const float4& t10, const float4& t11,
+                                        float2& lo, float2& hi) {
+    lo.x = fmaf(wt.w, t11.x, fmaf(wt.z, t10.x, fmaf(wt.y, t01.x, wt.x * t00.x)));
+    lo.y = fmaf(wt.w, t11.y, fmaf(wt.z, t10.y, fmaf(wt.y, t01.y, wt.x * t00.y)));
+    hi.x = fmaf(wt.w, t11.z, fmaf(wt.z, t10.z, fmaf(wt.y, t01.z, wt.x * t00.z)));
+    hi.y = fmaf(wt.w, t11.w, fmaf(wt.z, t10.w, fmaf(wt.y, t01.w, wt.x * t00.w)));
+}
+
+// MIX (V == 3 only; MVSB200_K1_MIX): which FP instructions are packed f32x2 (fmaheavy sub-pipe only, half the issue slots) and
+// which scalar (either sub-pipe).  0: all packed, pairwise variance (round 1); 1: all packed, two-difference variance;
+// 2: packed blend, scalar variance; 3: second source view's blend scalar, rest packed; 4: all scalar
+template <int V, bool BF16OUT, int MIX = 0>
 __global__ void __launch_bounds__(kThreads, V <= 3 ? 3 : (V <= 5 ? 2 : 1))
 warp_variance_fwd2_kernel(const float4* __restrict__ feat, const ViewParams* __restrict__ vp, const float* __restrict__ tinv,
                           void* __restrict__ cost, int D, int h, int w, int dchunk, int tiles_x) {
@@ -584,13 +339,23 @@ warp_variance_fwd2_kernel(const float4* __restrict__ feat, const ViewParams* __r
                 val[0][0] = ref[0]; val[1][0] = ref[1];
                 fetch(dd);
 #pragma unroll
-                for (int v = 1; v < V; ++v)
-                    blend2w(wt[v].x, wt[v].y, wt[v].z, wt[v].w, taps[v][0], taps[v][1], taps[v][2], taps[v][3], val[0][v], val[1][v]);
+                for (int v = 1; v < V; ++v) {
+                    if (V == 3 && (MIX == 4 || (MIX == 3 && v == 2)))
+                        blend1w(wt[v], taps[v][0], taps[v][1], taps[v][2], taps[v][3], val[0][v], val[1][v]);
+                    else
+                        blend2w(wt[v].x, wt[v].y, wt[v].z, wt[v].w, taps[v][0], taps[v][1], taps[v][2], taps[v][3], val[0][v], val[1][v]);
+                }
                 float2 r0, r1;
-                if (V == 3) {
+                if (V == 3 && MIX == 0) {
                     const float2 lo = variance3_pairwise(val[0][0], val[0][1], val[0][2], ninth);
                     const float2 hi = variance3_pairwise(val[1][0], val[1][1], val[1][2], ninth);
                     r0 = lo; r1 = hi;
+                } else if (V == 3 && (MIX == 1 || MIX == 3)) {
+                    r0 = variance3_two_diff(val[0][0], val[0][1], val[0][2]);
+                    r1 = variance3_two_diff(val[1][0], val[1][1], val[1][2]);
+                } else if (V == 3) {
+                    r0 = make_float2(variance3_two_diff1(val[0][0].x, val[0][1].x, val[0][2].x), variance3_two_diff1(val[0][0].y, val[0][1].y, val[0][2].y));
+                    r1 = make_float2(variance3_two_diff1(val[1][0].x, val[1][1].x, val[1][2].x), variance3_two_diff1(val[1][0].y, val[1][1].y, val[1][2].y));
                 } else {
                     float xs[4][V];
 #pragma unroll
@@ -628,7 +393,7 @@ template <int V, bool BF16G>
 __global__ void __launch_bounds__(kThreads, V <= 3 ? 2 : 1)
 warp_variance_bwd_kernel(const float4* __restrict__ feat, const ViewParams* __restrict__ vp, const float* __restrict__ tinv,
                          const void* __restrict__ gcost, float4* __restrict__ gfeat, int D, int h, int w, int dchunk,
-                         int tiles_x) {
+                         int tiles_x, int diag) {
     constexpr int RUN = FwdCfg<V>::kRunV, RECS = FwdCfg<V>::kRecs;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4* rec_w = reinterpret_cast<float4*>(smem_raw);
@@ -726,7 +491,7 @@ warp_variance_bwd_kernel(const float4* __restrict__ feat, const ViewParams* __re
                     const int4 of = ro[((v - 1) * RUN + dd) * kPix];
                     if (wt.x != wt.x) { nan_plane = true; wt = make_float4(0.f, 0.f, 0.f, 0.f); }   // d == 0 plane
                     const int changed = (of.x != old[v].x) | (of.w != old[v].w);
-                    const int flush = changed & (old[v].x >= 0);
+                    const int flush = changed & (old[v].x >= 0) & !(diag & 1);        // diag bit 0: timing without the reductions
                     float4* gv = gb + (size_t)v * plane * kSlots;
                     red_add_f4_if(gv + (unsigned)max(old[v].x, 0) * kSlots, make_float4(acc[v][0][0].x, acc[v][0][0].y, acc[v][0][1].x, acc[v][0][1].y), flush);
                     red_add_f4_if(gv + (unsigned)max(old[v].y, 0) * kSlots, make_float4(acc[v][1][0].x, acc[v][1][0].y, acc[v][1][1].x, acc[v][1][1].y), flush);
@@ -737,10 +502,11 @@ warp_variance_bwd_kernel(const float4* __restrict__ feat, const ViewParams* __re
                         for (int j = 0; j < 4; ++j) acc[v][j][0] = acc[v][j][1] = make_float2(0.f, 0.f);
                     }
                     const float4* fv = fb + (size_t)v * plane * kSlots;
-                    ldg_f4_if(taps[v][0], fv + (unsigned)of.x * kSlots, changed);
-                    ldg_f4_if(taps[v][1], fv + (unsigned)of.y * kSlots, changed);
-                    ldg_f4_if(taps[v][2], fv + (unsigned)of.z * kSlots, changed);
-                    ldg_f4_if(taps[v][3], fv + (unsigned)of.w * kSlots, changed);
+                    const int reload = changed & !(diag & 2);                           // diag bit 1: timing without the tap loads
+                    ldg_f4_if(taps[v][0], fv + (unsigned)of.x * kSlots, reload);
+                    ldg_f4_if(taps[v][1], fv + (unsigned)of.y * kSlots, reload);
+                    ldg_f4_if(taps[v][2], fv + (unsigned)of.z * kSlots, reload);
+                    ldg_f4_if(taps[v][3], fv + (unsigned)of.w * kSlots, reload);
                     old[v] = of;
                     wts[v] = wt;
                     blend2w(wt.x, wt.y, wt.z, wt.w, taps[v][0], taps[v][1], taps[v][2], taps[v][3], val[0][v], val[1][v]);
@@ -833,33 +599,6 @@ int check_common(const void* feat, const void* vp, const void* tinv, const void*
     return MVSB200_OK;
 }
 
-struct Plan {
-    dim3 grid;
-    int dchunk, tiles_x;
-    size_t smem;
-};
-
-Plan make_plan(int B, int V, int D, int h, int w, int cpl) {
-    const int ppw = 32 / (kSlots / (cpl / 4));
-    Plan p;
-    p.tiles_x = (w + kWX * ppw - 1) / (kWX * ppw);
-    const int tiles_y = (h + kWY - 1) / kWY;
-    const long tiles = (long)p.tiles_x * tiles_y * B;
-    // enough CTAs for >= 4 waves of 2 CTAs/SM on 148 SMs, but keep depth runs long (tap reuse across planes)
-    long nchunks = (4L * 2 * 148 + tiles - 1) / tiles;
-    long maxchunks = D >= 32 ? D / 16 : 1;
-    if (nchunks > maxchunks) nchunks = maxchunks;
-    if (nchunks < 1) nchunks = 1;
-    p.dchunk = (int)((D + nchunks - 1) / nchunks);
-    if (const char* e = getenv("MVSB200_DCHUNK")) {
-        int v = atoi(e);
-        if (v > 0) p.dchunk = v < D ? v : D;
-    }
-    p.grid = dim3((unsigned)(p.tiles_x * tiles_y), (unsigned)((D + p.dchunk - 1) / p.dchunk), (unsigned)B);
-    p.smem = (size_t)(V - 1) * p.dchunk * sizeof(float);
-    return p;
-}
-
 struct FwdPlan {
     dim3 grid;
     int dchunk, tiles_x;
@@ -880,15 +619,15 @@ FwdPlan make_fwd_plan(int B, int V, int D, int h, int w) {
     p.dchunk = (p.dchunk + kRun - 1) / kRun * kRun;
     if (const char* e = getenv("MVSB200_DCHUNK")) {
         int v = atoi(e);
-        if (v > 0) p.dchunk = v;
+        if (v > 0) p.dchunk = v < D ? v : D;         // clamped to [1, D]
     }
     p.grid = dim3((unsigned)(p.tiles_x * tiles_y), (unsigned)((D + p.dchunk - 1) / p.dchunk), (unsigned)B);
     return p;
 }
 
-int fwd_form() {                                     // MVSB200_K1=1 selects the first form (four offsets, CTA-staged records)
-    const char* e = getenv("MVSB200_K1");
-    return (e && e[0] == '1') ? 1 : 2;
+int kernel_form(const char* var, int dflt) {          // MVSB200_K1 / MVSB200_K2 = 2 select the second-form kernels (A/B measurements)
+    const char* e = getenv(var);
+    return (e && e[0] >= '0' && e[0] <= '9') ? e[0] - '0' : dflt;
 }
 
 template <int V>
@@ -897,36 +636,18 @@ int launch_fwd2(const float* feat, const float* vp, const float* tinv, void* cos
     FwdPlan p = make_fwd_plan(B, V, D, h, w);
     p.smem = Fwd2Cfg<V>::kSmem;
     MVS_REQUIRE(p.grid.y <= 65535 && (long)h * w < (1L << 24), "warp_variance_fwd: volume too large");
-    if (dtype == MVSB200_BF16)
-        warp_variance_fwd2_kernel<V, true><<<p.grid, kThreads, p.smem, st>>>(
-            (const float4*)feat, (const ViewParams*)vp, tinv, cost, D, h, w, p.dchunk, p.tiles_x);
-    else
-        warp_variance_fwd2_kernel<V, false><<<p.grid, kThreads, p.smem, st>>>(
-            (const float4*)feat, (const ViewParams*)vp, tinv, cost, D, h, w, p.dchunk, p.tiles_x);
+    const int mix = V == 3 ? kernel_form("MVSB200_K1_MIX", 0) : 0;
+#define MVS_LAUNCH_FWD2(BF, MIXV)                                                                      \
+    warp_variance_fwd2_kernel<V, BF, MIXV><<<p.grid, kThreads, p.smem, st>>>((const float4*)feat, (const ViewParams*)vp, tinv, \
+                                                                             cost, D, h, w, p.dchunk, p.tiles_x)
+    const bool bf = dtype == MVSB200_BF16;
+    if (V != 3 || mix == 0) { if (bf) MVS_LAUNCH_FWD2(true, 0); else MVS_LAUNCH_FWD2(false, 0); }
+    else if (mix == 1) { if (bf) MVS_LAUNCH_FWD2(true, 1); else MVS_LAUNCH_FWD2(false, 1); }
+    else if (mix == 2) { if (bf) MVS_LAUNCH_FWD2(true, 2); else MVS_LAUNCH_FWD2(false, 2); }
+    else if (mix == 3) { if (bf) MVS_LAUNCH_FWD2(true, 3); else MVS_LAUNCH_FWD2(false, 3); }
+    else { if (bf) MVS_LAUNCH_FWD2(true, 4); else MVS_LAUNCH_FWD2(false, 4); }
+#undef MVS_LAUNCH_FWD2
     MVS_CHECK_LAUNCH("warp_variance_fwd2");
-    return MVSB200_OK;
-}
-
-template <int V>
-int launch_fwd(const float* feat, const float* vp, const float* tinv, void* cost, int dtype, int B, int D, int h, int w,
-               cudaStream_t st) {
-    if (fwd_form() != 1 && h >= 2 && w >= 2 && (long)h * w < (1L << 24)) return launch_fwd2<V>(feat, vp, tinv, cost, dtype, B, D, h, w, st);
-    FwdPlan p = make_fwd_plan(B, V, D, h, w);
-    p.smem = FwdCfg<V>::kSmem;
-    MVS_REQUIRE(p.grid.y <= 65535 && (long)h * w < (1L << 27), "warp_variance_fwd: volume too large");
-    static bool attr_set = false;                    // per instantiation; benign race (idempotent call)
-    if (!attr_set) {
-        MVS_CUDA(cudaFuncSetAttribute(warp_variance_fwd_kernel<V, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
-        MVS_CUDA(cudaFuncSetAttribute(warp_variance_fwd_kernel<V, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
-        attr_set = true;
-    }
-    if (dtype == MVSB200_BF16)
-        warp_variance_fwd_kernel<V, true><<<p.grid, kThreads, p.smem, st>>>(
-            (const float4*)feat, (const ViewParams*)vp, tinv, cost, D, h, w, p.dchunk, p.tiles_x);
-    else
-        warp_variance_fwd_kernel<V, false><<<p.grid, kThreads, p.smem, st>>>(
-            (const float4*)feat, (const ViewParams*)vp, tinv, cost, D, h, w, p.dchunk, p.tiles_x);
-    MVS_CHECK_LAUNCH("warp_variance_fwd");
     return MVSB200_OK;
 }
 
@@ -936,18 +657,17 @@ int launch_bwd(const float* feat, const float* vp, const float* tinv, const void
     FwdPlan p = make_fwd_plan(B, V, D, h, w);
     p.smem = FwdCfg<V>::kSmem;
     MVS_REQUIRE(p.grid.y <= 65535 && (long)h * w < (1L << 27), "warp_variance_bwd: volume too large");
-    static bool attr_set = false;
-    if (!attr_set) {
-        MVS_CUDA(cudaFuncSetAttribute(warp_variance_bwd_kernel<V, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
-        MVS_CUDA(cudaFuncSetAttribute(warp_variance_bwd_kernel<V, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
-        attr_set = true;
-    }
+    // the attribute is per device / context: set on every launch (cheap), not once per process
+    MVS_CUDA(cudaFuncSetAttribute(warp_variance_bwd_kernel<V, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+    MVS_CUDA(cudaFuncSetAttribute(warp_variance_bwd_kernel<V, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+    int diag = 0;
+    if (const char* e = getenv("MVSB200_K2_DIAG")) diag = atoi(e);      // timing experiments only (results are wrong with diag != 0)
     if (dtype == MVSB200_BF16)
         warp_variance_bwd_kernel<V, true><<<p.grid, kThreads, p.smem, st>>>(
-            (const float4*)feat, (const ViewParams*)vp, tinv, gcost, (float4*)gfeat, D, h, w, p.dchunk, p.tiles_x);
+            (const float4*)feat, (const ViewParams*)vp, tinv, gcost, (float4*)gfeat, D, h, w, p.dchunk, p.tiles_x, diag);
     else
         warp_variance_bwd_kernel<V, false><<<p.grid, kThreads, p.smem, st>>>(
-            (const float4*)feat, (const ViewParams*)vp, tinv, gcost, (float4*)gfeat, D, h, w, p.dchunk, p.tiles_x);
+            (const float4*)feat, (const ViewParams*)vp, tinv, gcost, (float4*)gfeat, D, h, w, p.dchunk, p.tiles_x, diag);
     MVS_CHECK_LAUNCH("warp_variance_bwd");
     return MVSB200_OK;
 }
@@ -958,15 +678,18 @@ extern "C" int mvsb200_warp_variance_fwd(const float* feat, const float* view_pa
                                          int cost_dtype, int B, int V, int C, int D, int h, int w, void* stream) {
     if (int rc = check_common(feat, view_params, tinv, cost, B, V, C, D, h, w, "warp_variance_fwd")) return rc;
     MVS_REQUIRE(cost_dtype == MVSB200_F32 || cost_dtype == MVSB200_BF16, "warp_variance_fwd: bad cost dtype %d", cost_dtype);
+    MVS_REQUIRE(h >= 2 && w >= 2, "warp_variance_fwd: feature maps must be at least 2x2 (the reference's pixel normalisation "
+                                  "divides by h-1 and w-1)");
     cudaStream_t st = (cudaStream_t)stream;
+    if (kernel_form("MVSB200_K1", 3) == 3) return warp_variance_fwd3(feat, view_params, tinv, cost, cost_dtype, B, V, D, h, w, st);
     switch (V) {
-        case 2: return launch_fwd<2>(feat, view_params, tinv, cost, cost_dtype, B, D, h, w, st);
-        case 3: return launch_fwd<3>(feat, view_params, tinv, cost, cost_dtype, B, D, h, w, st);
-        case 4: return launch_fwd<4>(feat, view_params, tinv, cost, cost_dtype, B, D, h, w, st);
-        case 5: return launch_fwd<5>(feat, view_params, tinv, cost, cost_dtype, B, D, h, w, st);
-        case 6: return launch_fwd<6>(feat, view_params, tinv, cost, cost_dtype, B, D, h, w, st);
-        case 7: return launch_fwd<7>(feat, view_params, tinv, cost, cost_dtype, B, D, h, w, st);
-        case 8: return launch_fwd<8>(feat, view_params, tinv, cost, cost_dtype, B, D, h, w, st);
+        case 2: return launch_fwd2<2>(feat, view_params, tinv, cost, cost_dtype, B, D, h, w, st);
+        case 3: return launch_fwd2<3>(feat, view_params, tinv, cost, cost_dtype, B, D, h, w, st);
+        case 4: return launch_fwd2<4>(feat, view_params, tinv, cost, cost_dtype, B, D, h, w, st);
+        case 5: return launch_fwd2<5>(feat, view_params, tinv, cost, cost_dtype, B, D, h, w, st);
+        case 6: return launch_fwd2<6>(feat, view_params, tinv, cost, cost_dtype, B, D, h, w, st);
+        case 7: return launch_fwd2<7>(feat, view_params, tinv, cost, cost_dtype, B, D, h, w, st);
+        case 8: return launch_fwd2<8>(feat, view_params, tinv, cost, cost_dtype, B, D, h, w, st);
     }
     MVS_FAIL(MVSB200_E_UNSUPPORTED, "warp_variance_fwd: V=%d", V);
 }

@@ -68,6 +68,22 @@ def test_identical_views_give_zero_variance_and_scaling_is_quadratic():
     assert torch.equal(c4, c1 * 16.0)
 
 
+@pytest.mark.parametrize("v,d", [(2, 40), (3, 192), (4, 50), (5, 64), (6, 30), (7, 33), (8, 17)])
+def test_forward_kernel_forms_agree_at_full_map_size(v, d, monkeypatch):
+    """The shipped view-outer forward kernel (MVSB200_K1=3) and the second form (=2) on the same sweep, fp32 and bf16 volumes,
+    every supported view count, depth counts that are not multiples of the staged run."""
+    K, R, T, d_min, d_int, feat = _inputs(10 + v, v=v)
+    outs = {}
+    for form in ("3", "2"):
+        monkeypatch.setenv("MVSB200_K1", form)
+        warped, _, _ = mvs_b200.homography_warping(K, R, T, d_min, d_int, feat.to(DEV), B, v, d, 480.0 / d)
+        outs[form] = (mvs_b200.assemble_cost_volume(warped, v), mvs_b200.assemble_cost_volume(warped, v, torch.bfloat16))
+    a, b = outs["3"][0], outs["2"][0]
+    assert (a - b).abs().max().item() <= 2e-6 * b.abs().max().item()          # same footprints, different summation order
+    assert (outs["3"][1].float() - a).abs().max().item() <= 1e-2 * a.abs().max().item()
+    assert torch.equal(outs["3"][1], outs["2"][1]) or (outs["3"][1].float() - outs["2"][1].float()).abs().max().item() <= 1e-2 * a.abs().max().item()
+
+
 def test_source_view_order_is_irrelevant():
     K, R, T, d_min, d_int, feat = _inputs(4)
     a, _, _ = _cost(K, R, T, d_min, d_int, feat)
