@@ -1,4 +1,5 @@
-// K1 / K2: fused homography warp + variance cost volume, forward and backward (sm_100a).
+// K1: fused homography warp + variance cost volume, forward (sm_100a); the parity materialiser; the C entry points of K1 / K2.
+// The backward kernel (K2) lives in warp_variance_bwd3.cu.
 //
 // Reference semantics (citations into /root/reference/scripts):
 //   homography.py:40-75   H_i(d) = K_i R_i (I - (C_i - C_ref) n / d) R_ref^T K_ref^-1
@@ -9,12 +10,13 @@
 // Design:
 //   * geometry: host folds everything into 16 floats per view (include/mvs_b200.h); the per-plane
 //     inverse homography is a rank-one update evaluated in registers: q = a + g * (c * tinv[d]).
-//   * one thread owns CPL channels of one (y,x) pixel and walks a run of depth planes.  Adjacent planes
-//     move the sampling position by a fraction of a pixel, so the 2x2 tap footprint of every source
-//     view is kept in registers and re-fetched (vectorised channel-last 16 B loads through L1) only when
-//     floor(ix) or floor(iy) changes.  The reference view (H = I) is sampled once per pixel.
+//   * 8 lanes own a pixel (4 channels each) and walk a run of depth planes.  Adjacent planes move the sampling position
+//     by a fraction of a pixel, so the 2x2 tap footprint of every source view is kept in registers and re-fetched
+//     (vectorised channel-last 16 B loads through L1, one full 128-byte line per pixel and tap) only when it moves.
+//     The reference view (H = I) is sampled once per pixel.
 //   * all V samples of a voxel are in registers => mean, then sum (f - mean)^2, exactly the reference's
-//     two-pass variance (the sum f / sum f^2 moment form loses the 1e-4 target).
+//     two-pass variance (the sum f / sum f^2 moment form loses the 1e-4 target); V = 3 uses the
+//     algebraically identical two-difference form.
 //   * the [B,D,h,w,C] volume is written once with streaming 16 B stores; warped volumes never exist.
 #include "warp_common.cuh"
 #include <limits.h>
@@ -25,8 +27,8 @@ using namespace mvsb200::warp;
 
 namespace mvsb200 {
 namespace warp {
-int warp_variance_fwd3(const float* feat, const float* vp, const float* tinv, void* cost, int dtype, int B, int V, int D, int h,
-                       int w, cudaStream_t st);
+int warp_variance_bwd3(const float* feat, const float* vp, const float* tinv, const void* gcost, int dtype, float* gfeat, int B,
+                       int V, int D, int h, int w, cudaStream_t st);
 }  // namespace warp
 }  // namespace mvsb200
 
@@ -34,6 +36,8 @@ namespace {
 
 constexpr int kWX = 2, kWY = 4; // warps per CTA along x / y
 constexpr int kThreads = 32 * kWX * kWY;
+constexpr int kTX = 8, kTY = 4;                      // pixel tile of a CTA
+constexpr int kRun = 8;                              // planes per staged run (shared memory spent here is L1 lost)
 
 struct Sample {  // bilinear footprint of one sampling position
     int x0, y0;
@@ -81,44 +85,6 @@ __device__ __forceinline__ float4 blend(const Sample& s, float4 t00, float4 t01,
 }
 
 
-// ---- packed-fp32 (FFMA2 / FADD2 / FMUL2, sm_100) forward-path helpers ------------------------------------
-// The forward kernel is issue-bound (profiles/k1_r1a_summary.md), so its per-channel math runs on the packed
-// f32x2 pipe (same IEEE fp32 results, half the instructions) and the footprint reload is branch-light:
-// tap addresses are CLAMPED into the image and an out-of-bounds tap gets weight 0 (grid_sample zero padding).
-struct Sample2 {
-    int key;                       // (y0 << 16) + x0 of the 2x2 footprint (x0,y0 in [-2, 32767])
-    int x0, y0;
-    float w00, w01, w10, w11;      // bilinear weights, already 0 for out-of-bounds taps
-};
-
-__device__ __forceinline__ Sample2 sample_at2(const PixelView& pv, float gx, float gy, float gz, float t, int h, int w) {
-    const float m = pv.c * t;
-    const float qx = fmaf(gx, m, pv.a0), qy = fmaf(gy, m, pv.a1), qz = fmaf(gz, m, pv.a2);
-    const float rz = rcp_approx(qz);
-    float ix = fmaf(qx, rz, -0.5f), iy = fmaf(qy, rz, -0.5f);
-    ix = fminf(fmaxf(ix, -2.0f), (float)(w + 1));   // NaN -> -2: footprint entirely out of bounds
-    iy = fminf(fmaxf(iy, -2.0f), (float)(h + 1));
-    const float fx0 = floorf(ix), fy0 = floorf(iy);
-    Sample2 s;
-    s.x0 = (int)fx0;
-    s.y0 = (int)fy0;
-    s.key = (s.y0 << 16) + s.x0;
-    float wx1 = ix - fx0, wy1 = iy - fy0;
-    float wx0 = 1.0f - wx1, wy0 = 1.0f - wy1;
-    wx0 = ((unsigned)s.x0 < (unsigned)w) ? wx0 : 0.f;
-    wx1 = ((unsigned)(s.x0 + 1) < (unsigned)w) ? wx1 : 0.f;
-    wy0 = ((unsigned)s.y0 < (unsigned)h) ? wy0 : 0.f;
-    wy1 = ((unsigned)(s.y0 + 1) < (unsigned)h) ? wy1 : 0.f;
-    s.w00 = wx0 * wy0; s.w01 = wx1 * wy0; s.w10 = wx0 * wy1; s.w11 = wx1 * wy1;
-    return s;
-}
-
-// taps of a footprint, addresses clamped into the image (the weights carry the zero padding)
-__device__ __forceinline__ void ldg_f4_if(float4& t, const float4* p, int pred) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %5, 0;\n\t@p ld.global.nc.L1::evict_last.v4.f32 {%0,%1,%2,%3}, [%4];\n\t}"
-                 : "+f"(t.x), "+f"(t.y), "+f"(t.z), "+f"(t.w) : "l"(p), "r"(pred));
-}
-
 // population variance over V samples, two-pass as costvolume.py:12-14 (mean, then sum (x-mean)^2, / V).  Scalar math: plain
 // FADD/FFMA can issue on either FMA sub-pipe, the packed f32x2 forms only on the heavy one (profiles/r01_k1_notes.md)
 template <int V>
@@ -138,68 +104,24 @@ __device__ __forceinline__ float variance1(const float (&x)[V], float ninv, floa
 }
 
 // ------------------------------------------------------------------------------------------------
-// K1 forward
-// ------------------------------------------------------------------------------------------------
-// Forward kernel, two phases per run of kRun planes (profiles/k1_r1c_summary.md: the one-phase version was bound by
-// issue slots and L1 data-pipe wavefronts, not by HBM):
-//   phase 1  the CTA computes the bilinear footprint record of every (pixel, plane, source view) of its tile ONCE
-//            (homography in registers, clamped tap offsets, zero-padding folded into the weights) into shared memory;
+// K1 forward ("one offset" form): two phases per run of kRun planes.
+//   phase 1  a warp computes the footprint records of ITS four pixels for the run's planes and source views once (homography in
+//            registers, ONE clamped base offset per footprint, zero padding and clamping folded into the four weights:
+//            warp_common.cuh) into shared memory, double buffered, __syncwarp only -- warps drift apart instead of
+//            convoying through a CTA barrier;
 //   phase 2  8 lanes own one pixel (4 channels each, so a tap load of a pixel is one full 128-byte line and a warp's
 //            load instruction touches only the lines of pixels whose footprint moved); per plane a lane reads the
-//            record (2 broadcast LDS.128), refreshes its cached 2x2 taps with predicated loads, blends with packed
-//            f32x2 math, takes the two-pass variance over the V samples it holds and streams one 16-byte piece of
-//            the [B,D,h,w,32] row.
-constexpr int kTX = 8, kTY = 4, kPix = kTX * kTY;   // pixel tile of a CTA
-constexpr int kRun = 8;                              // planes per staged run (shared memory spent here is L1 lost)
-constexpr int kLanesPerPixel = 8;                    // 32 channels / 4 per lane
-
-struct __align__(16) FootRec {
-    float w00, w01, w10, w11;     // weights (0 for out-of-bounds taps, NaN on a d == 0 plane)
-    int o00, o01, o10, o11;       // pixel offsets y*w + x of the taps, clamped into the image
-};
-
-__device__ __forceinline__ FootRec make_record(const PixelView& pv, float gx, float gy, float gz, float t, int h, int w) {
-    const Sample2 s = sample_at2(pv, gx, gy, gz, t, h, w);
-    const int xa = min(max(s.x0, 0), w - 1), xb = min(max(s.x0 + 1, 0), w - 1);
-    const int ya = min(max(s.y0, 0), h - 1) * w, yb = min(max(s.y0 + 1, 0), h - 1) * w;
-    FootRec r;
-    const bool nan_plane = (t != t);                 // reference divides by d == 0 there: whole plane NaN
-    r.w00 = nan_plane ? NAN : s.w00; r.w01 = nan_plane ? NAN : s.w01;
-    r.w10 = nan_plane ? NAN : s.w10; r.w11 = nan_plane ? NAN : s.w11;
-    r.o00 = ya + xa; r.o01 = ya + xb; r.o10 = yb + xa; r.o11 = yb + xb;
-    return r;
-}
-
+//            record (one broadcast LDS.128 + LDS.32), refreshes its cached 2x2 taps with predicated loads, blends with
+//            packed f32x2 math, takes the variance over the V samples it holds and streams one 16-byte piece of the
+//            [B,D,h,w,32] row.
+// Round-2 measurements that shaped what is NOT here (profiles/r02_k1_k2_notes.md): a view-outer form with 8 channels per lane
+// and 256-bit loads (1.5x fewer instructions) ran 30 % slower -- long/short-scoreboard stalls of its serial per-view loops;
+// packed vs scalar FP mixes of this kernel all land within 2 %.
 __device__ __forceinline__ void blend2w(float w00, float w01, float w10, float w11, const float4& t00, const float4& t01,
                                         const float4& t10, const float4& t11, float2& lo, float2& hi) {
     const float2 a = make_float2(w00, w00), b = make_float2(w01, w01), c = make_float2(w10, w10), d = make_float2(w11, w11);
     lo = __ffma2_rn(d, lo2(t11), __ffma2_rn(c, lo2(t10), __ffma2_rn(b, lo2(t01), __fmul2_rn(a, lo2(t00)))));
     hi = __ffma2_rn(d, hi2(t11), __ffma2_rn(c, hi2(t10), __ffma2_rn(b, hi2(t01), __fmul2_rn(a, hi2(t00)))));
-}
-
-template <int V>
-struct FwdCfg {
-    static constexpr int kRunV = V <= 4 ? kRun : kRun / 2;                       // planes per staged run
-    static constexpr int kRecs = (V - 1) * kRunV * kPix;                         // records per buffer
-    static constexpr size_t kSmem = 2 * (size_t)kRecs * 2 * sizeof(float4);      // double-buffered, weights + offsets
-};
-
-// ------------------------------------------------------------------------------------------------
-// K1 forward, second form ("one offset"): same two phases, fewer instructions per plane and no CTA barrier.
-//   * the 2x2 footprint is addressed from ONE clamped base (xc, yc) in [0, w-2] x [0, h-2]: the taps are base, base + one
-//     voxel row (an immediate), base + one line, base + line + row.  Zero padding and the clamping are folded into the four
-//     weights when the record is made (a footprint hanging over the left/top edge hands its in-bounds weight to the first
-//     tap, over the right/bottom edge to the second), so phase 2 needs one 32-bit byte offset, one compare and two 64-bit
-//     address additions per view instead of four offsets, two compares, eight shifts and eight wide multiply-adds;
-//   * a warp stages the records of ITS four pixels itself (2 records per lane and run at V = 3): __syncwarp instead of
-//     __syncthreads, warps drift apart instead of convoying through phase 1 together;
-//   * V = 3: population variance from the three pairwise differences, ((a-b)^2 + (a-c)^2 + (b-c)^2) / 9 -- algebraically
-//     the two-pass value, no cancellation, 7 packed operations per channel pair instead of 10.
-// population variance of three samples from their pairwise differences (packed fp32)
-__device__ __forceinline__ float2 variance3_pairwise(float2 a, float2 b, float2 c, float2 ninth) {
-    const float2 nb = make_float2(-b.x, -b.y), nc = make_float2(-c.x, -c.y);
-    const float2 d01 = __fadd2_rn(a, nb), d02 = __fadd2_rn(a, nc), d12 = __fadd2_rn(b, nc);
-    return __fmul2_rn(__ffma2_rn(d12, d12, __ffma2_rn(d02, d02, __fmul2_rn(d01, d01))), ninth);
 }
 
 template <int V>
@@ -216,22 +138,7 @@ __device__ __forceinline__ float2 variance3_two_diff(float2 a, float2 b, float2 
     const float2 t = __ffma2_rn(d1, __ffma2_rn(d2, m1, d1), __fmul2_rn(d2, d2));
     return __fmul2_rn(t, make_float2(2.0f / 9.0f, 2.0f / 9.0f));
 }
-__device__ __forceinline__ float variance3_two_diff1(float a, float b, float c) {
-    const float d1 = b - a, d2 = c - a;
-    return fmaf(d1, d1 - d2, d2 * d2) * (2.0f / 9.0f);
-}
-__device__ __forceinline__ void blend1w(const float4& wt, const float4& t00, const float4& t01, const float4& t10, const float4& t11,
-                                        float2& lo, float2& hi) {
-    lo.x = fmaf(wt.w, t11.x, fmaf(wt.z, t10.x, fmaf(wt.y, t01.x, wt.x * t00.x)));
-    lo.y = fmaf(wt.w, t11.y, fmaf(wt.z, t10.y, fmaf(wt.y, t01.y, wt.x * t00.y)));
-    hi.x = fmaf(wt.w, t11.z, fmaf(wt.z, t10.z, fmaf(wt.y, t01.z, wt.x * t00.z)));
-    hi.y = fmaf(wt.w, t11.w, fmaf(wt.z, t10.w, fmaf(wt.y, t01.w, wt.x * t00.w)));
-}
-
-// MIX (V == 3 only; MVSB200_K1_MIX): which FP instructions are packed f32x2 (fmaheavy sub-pipe only, half the issue slots) and
-// which scalar (either sub-pipe).  0: all packed, pairwise variance (round 1); 1: all packed, two-difference variance;
-// 2: packed blend, scalar variance; 3: second source view's blend scalar, rest packed; 4: all scalar
-template <int V, bool BF16OUT, int MIX = 0>
+template <int V, bool BF16OUT>
 __global__ void __launch_bounds__(kThreads, V <= 3 ? 3 : (V <= 5 ? 2 : 1))
 warp_variance_fwd2_kernel(const float4* __restrict__ feat, const ViewParams* __restrict__ vp, const float* __restrict__ tinv,
                           void* __restrict__ cost, int D, int h, int w, int dchunk, int tiles_x) {
@@ -304,7 +211,6 @@ warp_variance_fwd2_kernel(const float4* __restrict__ feat, const ViewParams* __r
         for (int j = 0; j < 4; ++j) taps[v][j] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     const float invV = 1.0f / (float)V;
-    const float2 ninth = make_float2(1.0f / 9.0f, 1.0f / 9.0f);
     __syncwarp();
 
     int buf = 0;
@@ -339,23 +245,12 @@ warp_variance_fwd2_kernel(const float4* __restrict__ feat, const ViewParams* __r
                 val[0][0] = ref[0]; val[1][0] = ref[1];
                 fetch(dd);
 #pragma unroll
-                for (int v = 1; v < V; ++v) {
-                    if (V == 3 && (MIX == 4 || (MIX == 3 && v == 2)))
-                        blend1w(wt[v], taps[v][0], taps[v][1], taps[v][2], taps[v][3], val[0][v], val[1][v]);
-                    else
-                        blend2w(wt[v].x, wt[v].y, wt[v].z, wt[v].w, taps[v][0], taps[v][1], taps[v][2], taps[v][3], val[0][v], val[1][v]);
-                }
+                for (int v = 1; v < V; ++v)
+                    blend2w(wt[v].x, wt[v].y, wt[v].z, wt[v].w, taps[v][0], taps[v][1], taps[v][2], taps[v][3], val[0][v], val[1][v]);
                 float2 r0, r1;
-                if (V == 3 && MIX == 0) {
-                    const float2 lo = variance3_pairwise(val[0][0], val[0][1], val[0][2], ninth);
-                    const float2 hi = variance3_pairwise(val[1][0], val[1][1], val[1][2], ninth);
-                    r0 = lo; r1 = hi;
-                } else if (V == 3 && (MIX == 1 || MIX == 3)) {
+                if (V == 3) {
                     r0 = variance3_two_diff(val[0][0], val[0][1], val[0][2]);
                     r1 = variance3_two_diff(val[1][0], val[1][1], val[1][2]);
-                } else if (V == 3) {
-                    r0 = make_float2(variance3_two_diff1(val[0][0].x, val[0][1].x, val[0][2].x), variance3_two_diff1(val[0][0].y, val[0][1].y, val[0][2].y));
-                    r1 = make_float2(variance3_two_diff1(val[1][0].x, val[1][1].x, val[1][2].x), variance3_two_diff1(val[1][0].y, val[1][1].y, val[1][2].y));
                 } else {
                     float xs[4][V];
 #pragma unroll
@@ -372,187 +267,6 @@ warp_variance_fwd2_kernel(const float4* __restrict__ feat, const ViewParams* __r
             }
         }
         __syncwarp();                                // next buffer staged by every lane, this buffer consumed
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// K2 backward: d cost / d features
-//   d cost / d f_v = (2/V) (f_v - mean) * gcost   (the mean term cancels), chained through the
-//   bilinear taps.  Same two-phase structure as the forward kernel (footprint records in shared memory, 8 lanes per
-//   pixel, 4 channels per lane).  The gradient of a cached 2x2 footprint is accumulated in registers over the planes
-//   that share it and flushed with predicated 16-byte vector reductions (8 lanes = one full 128-byte line per tap)
-//   when the footprint moves; the reference view's constant footprint is flushed once per run of planes.
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void red_add_f4_if(float4* p, const float4& v, int pred) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %5, 0;\n\t@p red.global.add.v4.f32 [%0], {%1,%2,%3,%4};\n\t}" ::"l"(p),
-                 "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"(pred)
-                 : "memory");
-}
-
-template <int V, bool BF16G>
-__global__ void __launch_bounds__(kThreads, V <= 3 ? 2 : 1)
-warp_variance_bwd_kernel(const float4* __restrict__ feat, const ViewParams* __restrict__ vp, const float* __restrict__ tinv,
-                         const void* __restrict__ gcost, float4* __restrict__ gfeat, int D, int h, int w, int dchunk,
-                         int tiles_x, int diag) {
-    constexpr int RUN = FwdCfg<V>::kRunV, RECS = FwdCfg<V>::kRecs;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    float4* rec_w = reinterpret_cast<float4*>(smem_raw);
-    int4* rec_o = reinterpret_cast<int4*>(smem_raw) + 2 * RECS;
-
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int b = blockIdx.z, d0 = blockIdx.y * dchunk, nd = min(dchunk, D - d0);
-    const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
-    const unsigned plane = (unsigned)h * (unsigned)w;
-    const ViewParams* vpb = vp + (size_t)b * V;
-
-    const int p1 = threadIdx.x & (kPix - 1), q = threadIdx.x >> 5;
-    PixelView pv1[V];
-    {
-        const float x1 = (float)(tx * kTX + (p1 & (kTX - 1))), y1 = (float)(ty * kTY + p1 / kTX);
-#pragma unroll
-        for (int v = 1; v < V; ++v) pv1[v] = pixel_view(vpb[v], x1, y1);
-    }
-    auto stage_run = [&](int run0, int buf) {
-        const int nrun = min(RUN, nd - run0);
-#pragma unroll
-        for (int v = 1; v < V; ++v) {
-            const float gx = vpb[v].g[0], gy = vpb[v].g[1], gz = vpb[v].g[2];
-            const float* tv = tinv + (size_t)(b * V + v) * D + d0 + run0;
-            for (int dd = q; dd < nrun; dd += kThreads / kPix) {
-                const FootRec r = make_record(pv1[v], gx, gy, gz, __ldg(tv + dd), h, w);
-                const int i = buf * RECS + ((v - 1) * RUN + dd) * kPix + p1;
-                rec_w[i] = make_float4(r.w00, r.w01, r.w10, r.w11);
-                rec_o[i] = make_int4(r.o00, r.o01, r.o10, r.o11);
-            }
-        }
-    };
-
-    const int pl = warp * (32 / kLanesPerPixel) + lane / kLanesPerPixel, cg = lane % kLanesPerPixel;
-    const int px = tx * kTX + (pl & (kTX - 1)), py = ty * kTY + pl / kTX;
-    const bool active = px < w && py < h;
-    const float4* fb = feat + (size_t)(b * V) * plane * kSlots + cg;
-    float4* gb = gfeat + (size_t)(b * V) * plane * kSlots + cg;
-
-    stage_run(0, 0);
-
-    float2 ref[2], gref[2];
-    FootRec rref;
-    {
-        const PixelView pv = pixel_view(vpb[0], (float)px, (float)py);
-        rref = make_record(pv, 0.f, 0.f, 0.f, 0.f, h, w);
-        const float4 t00 = __ldg(fb + (unsigned)rref.o00 * kSlots), t01 = __ldg(fb + (unsigned)rref.o01 * kSlots),
-                     t10 = __ldg(fb + (unsigned)rref.o10 * kSlots), t11 = __ldg(fb + (unsigned)rref.o11 * kSlots);
-        blend2w(rref.w00, rref.w01, rref.w10, rref.w11, t00, t01, t10, t11, ref[0], ref[1]);
-        gref[0] = gref[1] = make_float2(0.f, 0.f);
-    }
-
-    float4 taps[V][4];
-    float2 acc[V][4][2];                              // gradient of the cached footprint, [tap][channel pair]
-    int4 old[V];                                      // its tap offsets (old[v].x < 0: nothing cached yet)
-#pragma unroll
-    for (int v = 1; v < V; ++v) {
-        old[v] = make_int4(-1, -1, -1, -1);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            taps[v][j] = make_float4(0.f, 0.f, 0.f, 0.f);
-            acc[v][j][0] = acc[v][j][1] = make_float2(0.f, 0.f);
-        }
-    }
-    const float invV = 1.0f / (float)V, twoV = 2.0f / (float)V;
-    const float2 ninv = make_float2(-invV, -invV);
-    __syncthreads();
-
-    int buf = 0;
-    for (int run0 = 0; run0 < nd; run0 += RUN, buf ^= 1) {
-        const int nrun = min(RUN, nd - run0);
-        if (run0 + RUN < nd) stage_run(run0 + RUN, buf ^ 1);
-        if (active) {
-            size_t vox = ((size_t)(b * D + d0 + run0) * h + py) * w + px;
-            const float4* rw = rec_w + buf * RECS + pl;
-            const int4* ro = rec_o + buf * RECS + pl;
-            for (int dd = 0; dd < nrun; ++dd, vox += plane) {
-                // upstream gradient of this lane's 4 channels
-                float2 g[2];
-                if (BF16G) {
-                    const uint2 u = __ldcs(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(gcost) + vox * kC + 4 * cg));
-                    g[0] = make_float2(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u));
-                    g[1] = make_float2(__uint_as_float(u.y << 16), __uint_as_float(u.y & 0xffff0000u));
-                } else {
-                    const float4 u = ld_cs_f4(reinterpret_cast<const float4*>(gcost) + vox * kSlots + cg);
-                    g[0] = make_float2(u.x, u.y); g[1] = make_float2(u.z, u.w);
-                }
-                float2 val[2][V];
-                float4 wts[V];
-                val[0][0] = ref[0]; val[1][0] = ref[1];
-                bool nan_plane = false;
-#pragma unroll
-                for (int v = 1; v < V; ++v) {
-                    float4 wt = rw[((v - 1) * RUN + dd) * kPix];
-                    const int4 of = ro[((v - 1) * RUN + dd) * kPix];
-                    if (wt.x != wt.x) { nan_plane = true; wt = make_float4(0.f, 0.f, 0.f, 0.f); }   // d == 0 plane
-                    const int changed = (of.x != old[v].x) | (of.w != old[v].w);
-                    const int flush = changed & (old[v].x >= 0) & !(diag & 1);        // diag bit 0: timing without the reductions
-                    float4* gv = gb + (size_t)v * plane * kSlots;
-                    red_add_f4_if(gv + (unsigned)max(old[v].x, 0) * kSlots, make_float4(acc[v][0][0].x, acc[v][0][0].y, acc[v][0][1].x, acc[v][0][1].y), flush);
-                    red_add_f4_if(gv + (unsigned)max(old[v].y, 0) * kSlots, make_float4(acc[v][1][0].x, acc[v][1][0].y, acc[v][1][1].x, acc[v][1][1].y), flush);
-                    red_add_f4_if(gv + (unsigned)max(old[v].z, 0) * kSlots, make_float4(acc[v][2][0].x, acc[v][2][0].y, acc[v][2][1].x, acc[v][2][1].y), flush);
-                    red_add_f4_if(gv + (unsigned)max(old[v].w, 0) * kSlots, make_float4(acc[v][3][0].x, acc[v][3][0].y, acc[v][3][1].x, acc[v][3][1].y), flush);
-                    if (changed) {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) acc[v][j][0] = acc[v][j][1] = make_float2(0.f, 0.f);
-                    }
-                    const float4* fv = fb + (size_t)v * plane * kSlots;
-                    const int reload = changed & !(diag & 2);                           // diag bit 1: timing without the tap loads
-                    ldg_f4_if(taps[v][0], fv + (unsigned)of.x * kSlots, reload);
-                    ldg_f4_if(taps[v][1], fv + (unsigned)of.y * kSlots, reload);
-                    ldg_f4_if(taps[v][2], fv + (unsigned)of.z * kSlots, reload);
-                    ldg_f4_if(taps[v][3], fv + (unsigned)of.w * kSlots, reload);
-                    old[v] = of;
-                    wts[v] = wt;
-                    blend2w(wt.x, wt.y, wt.z, wt.w, taps[v][0], taps[v][1], taps[v][2], taps[v][3], val[0][v], val[1][v]);
-                }
-                // gv_v = (f_v - mean) * g * 2/V ; the reference's gradient is NaN on a d == 0 plane: contribute nothing
-                const float gsc = nan_plane ? 0.f : twoV;
-                const float2 gs2 = make_float2(gsc, gsc);
-#pragma unroll
-                for (int k = 0; k < 2; ++k) {
-                    float2 sum = val[k][0];
-#pragma unroll
-                    for (int v = 1; v < V; ++v) sum = __fadd2_rn(sum, val[k][v]);
-                    const float2 nmean = __fmul2_rn(sum, ninv);
-                    const float2 gk = __fmul2_rn(g[k], gs2);
-                    gref[k] = __ffma2_rn(__fadd2_rn(val[k][0], nmean), gk, gref[k]);
-#pragma unroll
-                    for (int v = 1; v < V; ++v) {
-                        const float2 gv = __fmul2_rn(__fadd2_rn(val[k][v], nmean), gk);
-                        acc[v][0][k] = __ffma2_rn(make_float2(wts[v].x, wts[v].x), gv, acc[v][0][k]);
-                        acc[v][1][k] = __ffma2_rn(make_float2(wts[v].y, wts[v].y), gv, acc[v][1][k]);
-                        acc[v][2][k] = __ffma2_rn(make_float2(wts[v].z, wts[v].z), gv, acc[v][2][k]);
-                        acc[v][3][k] = __ffma2_rn(make_float2(wts[v].w, wts[v].w), gv, acc[v][3][k]);
-                    }
-                }
-            }
-        }
-        __syncthreads();
-    }
-    if (!active) return;
-    // final flush: the cached source-view footprints, then the reference view's constant footprint
-#pragma unroll
-    for (int v = 1; v < V; ++v) {
-        const int flush = old[v].x >= 0;
-        float4* gv = gb + (size_t)v * plane * kSlots;
-        red_add_f4_if(gv + (unsigned)max(old[v].x, 0) * kSlots, make_float4(acc[v][0][0].x, acc[v][0][0].y, acc[v][0][1].x, acc[v][0][1].y), flush);
-        red_add_f4_if(gv + (unsigned)max(old[v].y, 0) * kSlots, make_float4(acc[v][1][0].x, acc[v][1][0].y, acc[v][1][1].x, acc[v][1][1].y), flush);
-        red_add_f4_if(gv + (unsigned)max(old[v].z, 0) * kSlots, make_float4(acc[v][2][0].x, acc[v][2][0].y, acc[v][2][1].x, acc[v][2][1].y), flush);
-        red_add_f4_if(gv + (unsigned)max(old[v].w, 0) * kSlots, make_float4(acc[v][3][0].x, acc[v][3][0].y, acc[v][3][1].x, acc[v][3][1].y), flush);
-    }
-    {
-        const float4 gr = make_float4(gref[0].x, gref[0].y, gref[1].x, gref[1].y);
-        const float wr[4] = {rref.w00, rref.w01, rref.w10, rref.w11};
-        const int orf[4] = {rref.o00, rref.o01, rref.o10, rref.o11};
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-            red_add_f4_if(gb + (unsigned)orf[j] * kSlots, make_float4(wr[j] * gr.x, wr[j] * gr.y, wr[j] * gr.z, wr[j] * gr.w), 1);
     }
 }
 
@@ -625,50 +339,19 @@ FwdPlan make_fwd_plan(int B, int V, int D, int h, int w) {
     return p;
 }
 
-int kernel_form(const char* var, int dflt) {          // MVSB200_K1 / MVSB200_K2 = 2 select the second-form kernels (A/B measurements)
-    const char* e = getenv(var);
-    return (e && e[0] >= '0' && e[0] <= '9') ? e[0] - '0' : dflt;
-}
-
 template <int V>
 int launch_fwd2(const float* feat, const float* vp, const float* tinv, void* cost, int dtype, int B, int D, int h, int w,
                 cudaStream_t st) {
     FwdPlan p = make_fwd_plan(B, V, D, h, w);
     p.smem = Fwd2Cfg<V>::kSmem;
     MVS_REQUIRE(p.grid.y <= 65535 && (long)h * w < (1L << 24), "warp_variance_fwd: volume too large");
-    const int mix = V == 3 ? kernel_form("MVSB200_K1_MIX", 0) : 0;
-#define MVS_LAUNCH_FWD2(BF, MIXV)                                                                      \
-    warp_variance_fwd2_kernel<V, BF, MIXV><<<p.grid, kThreads, p.smem, st>>>((const float4*)feat, (const ViewParams*)vp, tinv, \
-                                                                             cost, D, h, w, p.dchunk, p.tiles_x)
-    const bool bf = dtype == MVSB200_BF16;
-    if (V != 3 || mix == 0) { if (bf) MVS_LAUNCH_FWD2(true, 0); else MVS_LAUNCH_FWD2(false, 0); }
-    else if (mix == 1) { if (bf) MVS_LAUNCH_FWD2(true, 1); else MVS_LAUNCH_FWD2(false, 1); }
-    else if (mix == 2) { if (bf) MVS_LAUNCH_FWD2(true, 2); else MVS_LAUNCH_FWD2(false, 2); }
-    else if (mix == 3) { if (bf) MVS_LAUNCH_FWD2(true, 3); else MVS_LAUNCH_FWD2(false, 3); }
-    else { if (bf) MVS_LAUNCH_FWD2(true, 4); else MVS_LAUNCH_FWD2(false, 4); }
-#undef MVS_LAUNCH_FWD2
-    MVS_CHECK_LAUNCH("warp_variance_fwd2");
-    return MVSB200_OK;
-}
-
-template <int V>
-int launch_bwd(const float* feat, const float* vp, const float* tinv, const void* gcost, int dtype, float* gfeat, int B,
-               int D, int h, int w, cudaStream_t st) {
-    FwdPlan p = make_fwd_plan(B, V, D, h, w);
-    p.smem = FwdCfg<V>::kSmem;
-    MVS_REQUIRE(p.grid.y <= 65535 && (long)h * w < (1L << 27), "warp_variance_bwd: volume too large");
-    // the attribute is per device / context: set on every launch (cheap), not once per process
-    MVS_CUDA(cudaFuncSetAttribute(warp_variance_bwd_kernel<V, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
-    MVS_CUDA(cudaFuncSetAttribute(warp_variance_bwd_kernel<V, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
-    int diag = 0;
-    if (const char* e = getenv("MVSB200_K2_DIAG")) diag = atoi(e);      // timing experiments only (results are wrong with diag != 0)
     if (dtype == MVSB200_BF16)
-        warp_variance_bwd_kernel<V, true><<<p.grid, kThreads, p.smem, st>>>(
-            (const float4*)feat, (const ViewParams*)vp, tinv, gcost, (float4*)gfeat, D, h, w, p.dchunk, p.tiles_x, diag);
+        warp_variance_fwd2_kernel<V, true><<<p.grid, kThreads, p.smem, st>>>((const float4*)feat, (const ViewParams*)vp, tinv, cost, D, h,
+                                                                             w, p.dchunk, p.tiles_x);
     else
-        warp_variance_bwd_kernel<V, false><<<p.grid, kThreads, p.smem, st>>>(
-            (const float4*)feat, (const ViewParams*)vp, tinv, gcost, (float4*)gfeat, D, h, w, p.dchunk, p.tiles_x, diag);
-    MVS_CHECK_LAUNCH("warp_variance_bwd");
+        warp_variance_fwd2_kernel<V, false><<<p.grid, kThreads, p.smem, st>>>((const float4*)feat, (const ViewParams*)vp, tinv, cost, D, h,
+                                                                              w, p.dchunk, p.tiles_x);
+    MVS_CHECK_LAUNCH("warp_variance_fwd2");
     return MVSB200_OK;
 }
 
@@ -681,7 +364,6 @@ extern "C" int mvsb200_warp_variance_fwd(const float* feat, const float* view_pa
     MVS_REQUIRE(h >= 2 && w >= 2, "warp_variance_fwd: feature maps must be at least 2x2 (the reference's pixel normalisation "
                                   "divides by h-1 and w-1)");
     cudaStream_t st = (cudaStream_t)stream;
-    if (kernel_form("MVSB200_K1", 3) == 3) return warp_variance_fwd3(feat, view_params, tinv, cost, cost_dtype, B, V, D, h, w, st);
     switch (V) {
         case 2: return launch_fwd2<2>(feat, view_params, tinv, cost, cost_dtype, B, D, h, w, st);
         case 3: return launch_fwd2<3>(feat, view_params, tinv, cost, cost_dtype, B, D, h, w, st);
@@ -701,17 +383,9 @@ extern "C" int mvsb200_warp_variance_bwd(const float* feat, const float* view_pa
     MVS_REQUIRE(gfeat && aligned16(gfeat), "warp_variance_bwd: gfeat null or misaligned");
     MVS_REQUIRE(gcost_dtype == MVSB200_F32 || gcost_dtype == MVSB200_BF16, "warp_variance_bwd: bad gcost dtype %d", gcost_dtype);
     cudaStream_t st = (cudaStream_t)stream;
+    MVS_REQUIRE(h >= 2 && w >= 2, "warp_variance_bwd: feature maps must be at least 2x2");
     MVS_CUDA(cudaMemsetAsync(gfeat, 0, (size_t)B * V * h * w * kC * sizeof(float), st));
-    switch (V) {
-        case 2: return launch_bwd<2>(feat, view_params, tinv, gcost, gcost_dtype, gfeat, B, D, h, w, st);
-        case 3: return launch_bwd<3>(feat, view_params, tinv, gcost, gcost_dtype, gfeat, B, D, h, w, st);
-        case 4: return launch_bwd<4>(feat, view_params, tinv, gcost, gcost_dtype, gfeat, B, D, h, w, st);
-        case 5: return launch_bwd<5>(feat, view_params, tinv, gcost, gcost_dtype, gfeat, B, D, h, w, st);
-        case 6: return launch_bwd<6>(feat, view_params, tinv, gcost, gcost_dtype, gfeat, B, D, h, w, st);
-        case 7: return launch_bwd<7>(feat, view_params, tinv, gcost, gcost_dtype, gfeat, B, D, h, w, st);
-        case 8: return launch_bwd<8>(feat, view_params, tinv, gcost, gcost_dtype, gfeat, B, D, h, w, st);
-    }
-    MVS_FAIL(MVSB200_E_UNSUPPORTED, "warp_variance_bwd: V=%d", V);
+    return warp_variance_bwd3(feat, view_params, tinv, gcost, gcost_dtype, gfeat, B, V, D, h, w, st);    // warp_variance_bwd3.cu
 }
 
 extern "C" int mvsb200_warp_materialize(const float* feat, const float* view_params, const float* tinv, float* warped,

@@ -297,16 +297,12 @@ def test_cost_volume_against_live_oracle(B, V, D, h, w):
     assert _relmax(cost.cpu().numpy(), ref.numpy()) < 1e-4
 
 
-@pytest.mark.parametrize("form", ["3", "2"])
 @pytest.mark.parametrize("V,D,h,w,d0,shift", [(3, 12, 13, 21, 150.0, 0.0), (4, 10, 9, 7, 120.0, 30.0), (2, 16, 2, 2, 425.0, 0.0),
                                               (5, 6, 31, 17, 80.0, -25.0)])
-def test_cost_volume_with_footprints_hanging_over_every_edge(V, D, h, w, d0, shift, form, monkeypatch):
-    """Both forms of the forward kernel (MVSB200_K1=3, the shipped view-outer kernel with 8 channels per lane; =2: all views'
-    taps in registers, 4 channels per lane -- both address a footprint from one clamped base offset with the padding and
-    clamping folded into the weights) on sweeps whose sampling positions leave the image on every side:
-    near planes (large disparity) and a shifted principal point; tiny and odd-sized maps.  Also the backward of the same
-    sweep against the oracle's autograd."""
-    monkeypatch.setenv("MVSB200_K1", form)
+def test_cost_volume_with_footprints_hanging_over_every_edge(V, D, h, w, d0, shift):
+    """Forward and backward kernels (one clamped base offset per footprint, padding and clamping folded into the weights) on
+    sweeps whose sampling positions leave the image on every side: near planes (large disparity) and a shifted principal point;
+    tiny and odd-sized maps.  Forward and the backward of the same sweep against the oracle (its autograd for the backward)."""
     gen = torch.Generator().manual_seed(V * 100 + D + h)
     K, R, T = ps.synthetic_cameras(1, V, h, w, seed=V)
     K = K.clone()
