@@ -545,8 +545,11 @@ conv3d_s1_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles = p.tiles_x * p.tiles_y;
+    // accumulator blocks only for the depth taps this launch computes (kd_mask): block index = rank of kd inside the mask
+    const int nkd = __popc(p.kd_mask & 7u);
     uint32_t tmem_cols = 32;
-    while ((int)tmem_cols < 3 * KWB * UN) tmem_cols <<= 1;
+    while ((int)tmem_cols < nkd * KWB * UN) tmem_cols <<= 1;
+    auto kd_slot = [&](int kd) { return __popc(p.kd_mask & ((1u << kd) - 1u)); };
 
     // zero what TMA never writes: the slab tails (read by the last K step) and the whole gy stages (padding, halo columns)
     {
@@ -645,7 +648,7 @@ conv3d_s1_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid
                         const uint32_t s_lo = slab_lo + (uint32_t)((gs0 + d + kd) % kSlots3) * slab16;
 #pragma unroll
                         for (int blk = 0; blk < KWB; ++blk) {
-                            const uint32_t d_tmem = tmem_base + (uint32_t)((kd * KWB + blk) * UN);
+                            const uint32_t d_tmem = tmem_base + (uint32_t)((kd_slot(kd) * KWB + blk) * UN);
                             uint32_t a_lo = s_lo + (uint32_t)((blk * 2 * ROWX) >> 4);      // second block: atoms kw = 2, 3(junk)
                             uint32_t b_lo = g_lo;
                             for (int ks = 0; ks < p.ksteps; ++ks) {
@@ -686,7 +689,7 @@ conv3d_s1_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid
 #pragma unroll
                 for (int c0 = 0; c0 < UN; c0 += 16) {
                     uint32_t v[16];
-                    tmem_ld<16>(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((kd * KWB + blk) * UN + c0), v);
+                    tmem_ld<16>(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((kd_slot(kd) * KWB + blk) * UN + c0), v);
                     tmem_ld_wait();
                     if (real) {
 #pragma unroll
@@ -1468,7 +1471,15 @@ struct DeconvParams {
     int cout, n_rows;
     int slab_bytes;
     int n_taps;                     // 27
-    int tap_class[27], tap_td[27], tap_th[27], tap_tw[27], tap_k[27];   // ordered by class
+    // The 27 (class, filter tap) pairs grouped by the INPUT SHIFT (td, th, tw) they read: classes that share a shift share
+    // the A operand, so one MMA of N = ncls * NOUT serves them all when their accumulator blocks are adjacent in TMEM.
+    // Shared-memory filter slot e holds filter tap tap_k[e]; a group's slots and its classes are consecutive.
+    int tap_k[27];                  // filter tap (kd*3+kh)*3+kw held by shared-memory slot e
+    int n_groups;
+    int grp_td[27], grp_th[27], grp_tw[27];   // input shift of the group (slab tap per axis)
+    int grp_class0[27], grp_ncls[27];         // first class block and number of adjacent class blocks the MMA covers
+    int grp_slot0[27];                        // first filter slot of the group
+    int grp_first[27];                        // 1: the group's MMA initialises its accumulators (first touch of those classes)
     long long y_sb, y_sd, y_sh, y_sw;   // canvas voxel-row strides in elements
     __nv_bfloat16* y;
 };
@@ -1482,8 +1493,9 @@ deconv3d_s2_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
     constexpr int W_TAP_BYTES = NOUT * ROWB;
     constexpr int W_BYTES = 27 * W_TAP_BYTES;
     constexpr int W_BYTES_AL = (W_BYTES + 1023) / 1024 * 1024;
-    constexpr int MB = 512 / (16 * NOUT);               // 2 stages x 8 classes x MB x NOUT columns == 512
-    constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NOUT >> 3) << 17) | ((128u >> 4) << 24);
+    constexpr int MB = 512 / (16 * NOUT);               // 2 stages x MB x 8 classes x NOUT columns == 512
+    // instruction descriptor without the N field: D fp32, A/B bf16, both K-major, M = 128; N = ncls * NOUT per group
+    constexpr uint32_t IDESC0 = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 4) << 24);
     static_assert(MB >= 1 && MB <= 2, "accumulator blocks per class");
 
     extern __shared__ unsigned char smem_dyn[];
@@ -1534,7 +1546,7 @@ deconv3d_s2_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
         // ===================================== TMA producer =====================================
         if (elect_one()) {
             mbar_expect_tx(wfull, 27u * W_TAP_BYTES);
-            for (int tap = 0; tap < 27; ++tap) tma_load_2d(w_smem + tap * W_TAP_BYTES, &tm_w, wfull, 0, tap * p.n_rows);
+            for (int e = 0; e < 27; ++e) tma_load_2d(w_smem + e * W_TAP_BYTES, &tm_w, wfull, 0, p.tap_k[e] * p.n_rows);
         }
         __syncwarp();
         const uint32_t box_bytes = (uint32_t)ROWB * p.BW * (p.L + 2);
@@ -1576,19 +1588,18 @@ deconv3d_s2_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
 #pragma unroll
                     for (int mb = 0; mb < MB; ++mb) {
                         const uint32_t mb16 = (uint32_t)(mb * 128 * ROWB) >> 4;
-                        int prev_class = -1;
-                        for (int e = 0; e < 27; ++e) {
-                            const int c = p.tap_class[e], td = p.tap_td[e];
+                        for (int g = 0; g < p.n_groups; ++g) {
+                            const int td = p.grp_td[g];
                             const uint32_t a_lo = (td == 0 ? slot_lo[0] : (td == 1 ? slot_lo[1] : slot_lo[2])) + mb16 +
-                                                  (uint32_t)p.tap_th[e] * bw16 + (uint32_t)((p.tap_tw[e] * ROWB) >> 4);
-                            const uint32_t b_lo = w_lo + (uint32_t)((p.tap_k[e] * W_TAP_BYTES) >> 4);
-                            const uint32_t d_tmem = tmem_base + (uint32_t)(((stage * 8 + c) * MB + mb) * NOUT);
-                            uint32_t acc = c == prev_class ? 1u : 0u;
-                            prev_class = c;
+                                                  (uint32_t)p.grp_th[g] * bw16 + (uint32_t)((p.grp_tw[g] * ROWB) >> 4);
+                            const uint32_t b_lo = w_lo + (uint32_t)((p.grp_slot0[g] * W_TAP_BYTES) >> 4);
+                            const uint32_t d_tmem = tmem_base + (uint32_t)(((stage * MB + mb) * 8 + p.grp_class0[g]) * NOUT);
+                            const uint32_t idesc = IDESC0 | ((uint32_t)((p.grp_ncls[g] * NOUT) >> 3) << 17);
+                            uint32_t acc = p.grp_first[g] ? 0u : 1u;
 #pragma unroll
                             for (int k = 0; k < KSTEPS; ++k) {
                                 umma_bf16_lohi(d_tmem, a_lo + (uint32_t)((k * 32) >> 4), desc_hi, b_lo + (uint32_t)((k * 32) >> 4), desc_hi,
-                                               IDESC, acc);
+                                               idesc, acc);
                                 acc = 1;
                             }
                         }
@@ -1629,7 +1640,7 @@ deconv3d_s2_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
 #pragma unroll
                     for (int c = 0; c < 8; ++c) {
                         uint32_t v[NOUT];
-                        tmem_ld<NOUT>(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(((stage * 8 + c) * MB + mb) * NOUT), v);
+                        tmem_ld<NOUT>(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(((stage * MB + mb) * 8 + c) * NOUT), v);
                         tmem_ld_wait();
                         const int z = oz + (c >> 2), yy = oy + (c >> 1 & 1), xx = ox + (c & 1);
                         if (in_tile[mb] && z < p.Do && yy < p.Ho && xx < p.Wo) {
@@ -1721,9 +1732,14 @@ int launch_deconv_s2(const void* x, const void* w, void* y, int B, int Di, int H
     p.B = B; p.Do = Do; p.Ho = Ho; p.Wo = Wo; p.Jd = Jd; p.Jh = Jh; p.Jw = Jw;
     p.BW = tp.BW; p.L = tp.L; p.MB = MB; p.tiles_x = tp.tiles_x; p.tiles_y = tp.tiles_y;
     p.cout = cout; p.n_rows = n_rows; p.slab_bytes = tp.slab_bytes;
-    // taps ordered by output-parity class; slab tap t = (par + pad - k)/2 + 1 per axis (input index J + t - 1)
+    // (class, filter tap) pairs: slab tap t = (par + pad - k)/2 + 1 per axis (input index J + t - 1).  Grouped by the input
+    // shift t they read; inside a shift the user classes are split into runs of ADJACENT class indices (their accumulator
+    // blocks are adjacent TMEM columns), one MMA of N = run length * NOUT per run.
     const int pads[3] = {pad_d, pad_h, pad_w};
-    int n = 0;
+    int pair_k[8][27];                                   // pair_k[class][shift] = filter tap or -1
+    for (int c = 0; c < 8; ++c)
+        for (int t = 0; t < 27; ++t) pair_k[c][t] = -1;
+    int n_pairs = 0;
     for (int c = 0; c < 8; ++c) {
         const int par[3] = {c >> 2 & 1, c >> 1 & 1, c & 1};
         for (int kd = 0; kd < 3; ++kd)
@@ -1739,14 +1755,44 @@ int launch_deconv_s2(const void* x, const void* w, void* y, int B, int Di, int H
                         if (t[ax] < 0 || t[ax] > 2) { ok = false; break; }
                     }
                     if (!ok) continue;
-                    MVS_REQUIRE(n < 27, "deconv3d_s2: tap table overflow");
-                    p.tap_class[n] = c; p.tap_td[n] = t[0]; p.tap_th[n] = t[1]; p.tap_tw[n] = t[2];
-                    p.tap_k[n] = (kd * 3 + kh) * 3 + kw;
-                    ++n;
+                    pair_k[c][(t[0] * 3 + t[1]) * 3 + t[2]] = (kd * 3 + kh) * 3 + kw;
+                    ++n_pairs;
                 }
     }
-    MVS_REQUIRE(n == 27, "deconv3d_s2: padding (%d,%d,%d) does not map all 27 taps into the 3-tap window", pad_d, pad_h, pad_w);
-    p.n_taps = n;
+    MVS_REQUIRE(n_pairs == 27, "deconv3d_s2: padding (%d,%d,%d) does not map all 27 taps into the 3-tap window", pad_d, pad_h, pad_w);
+    p.n_taps = 27;
+    // shifts in decreasing number of user classes: the first group to touch a class initialises its accumulator block, and
+    // a group must initialise all of its classes or none -- true when the widest shift (used by every class it can reach)
+    // comes first; verified below
+    int order[27], users[27];
+    for (int t = 0; t < 27; ++t) {
+        order[t] = t;
+        users[t] = 0;
+        for (int c = 0; c < 8; ++c) users[t] += pair_k[c][t] >= 0;
+    }
+    for (int i = 0; i < 27; ++i)
+        for (int j = i + 1; j < 27; ++j)
+            if (users[order[j]] > users[order[i]]) { const int tmp = order[i]; order[i] = order[j]; order[j] = tmp; }
+    bool touched[8] = {false, false, false, false, false, false, false, false};
+    int ng = 0, slot = 0;
+    for (int oi = 0; oi < 27; ++oi) {
+        const int t = order[oi];
+        if (users[t] == 0) continue;
+        for (int c = 0; c < 8;) {
+            if (pair_k[c][t] < 0) { ++c; continue; }
+            int c1 = c;
+            while (c1 < 8 && pair_k[c1][t] >= 0 && touched[c1] == touched[c] && (c1 - c + 1) * NOUT <= 256) ++c1;
+            MVS_REQUIRE(ng < 27 && slot + (c1 - c) <= 27, "deconv3d_s2: group table overflow");
+            p.grp_td[ng] = t / 9; p.grp_th[ng] = t / 3 % 3; p.grp_tw[ng] = t % 3;
+            p.grp_class0[ng] = c; p.grp_ncls[ng] = c1 - c; p.grp_slot0[ng] = slot; p.grp_first[ng] = touched[c] ? 0 : 1;
+            for (int cc = c; cc < c1; ++cc) { p.tap_k[slot++] = pair_k[cc][t]; touched[cc] = true; }
+            ++ng;
+            c = c1;
+        }
+    }
+    MVS_REQUIRE(slot == 27, "deconv3d_s2: %d filter slots filled", slot);
+    p.n_groups = ng;
+    for (int g = ng; g < 27; ++g) { p.grp_td[g] = p.grp_th[g] = p.grp_tw[g] = p.grp_class0[g] = p.grp_ncls[g] = p.grp_slot0[g] = p.grp_first[g] = 0; }
     p.y_sb = y_strides4[0]; p.y_sd = y_strides4[1]; p.y_sh = y_strides4[2]; p.y_sw = y_strides4[3];
     p.y = reinterpret_cast<__nv_bfloat16*>(y);
 
@@ -1834,7 +1880,18 @@ extern "C" int mvsb200_conv3d_s1_wgrad(const void* x, const void* gy, float* gw,
     MVS_REQUIRE(cout == 8 || cout == 16 || cout == 32 || cout == 64, "conv3d_s1_wgrad: cout must be 8, 16, 32 or 64 (got %d)", cout);
     cudaStream_t st = (cudaStream_t)stream;
     MVS_CUDA(cudaMemsetAsync(gw, 0, (size_t)27 * Cin * cout * sizeof(float), st));
-    // gy channels per launch: 3 depth taps x (1 or 2 kw blocks) x (kh, co) columns must fit the 512 TMEM columns
+    // gy channels per launch: (depth taps) x (1 or 2 kw blocks) x (kh, co) columns must fit the 512 TMEM columns.  64-channel x
+    // (two kw blocks): 32 gy channels fit only with ONE depth tap per launch (2 x 96 columns) -- three launches per channel
+    // chunk, each at twice the MMA N extent, instead of one at 16 channels: the A operand (the x slab, 4 KB per MMA) is read
+    // from shared memory half as often per flop (measured: conv_3_1 1.03 -> see profiles/r02_k3_notes.md)
+    if (Cin == 64 && cout % 32 == 0) {
+        for (int co0 = 0; co0 < cout; co0 += 32)
+            for (int kd = 0; kd < 3; ++kd) {
+                const int rc = launch_wgrad<64, 32>(x, gy, gw, B, Di, Hi, Wi, Do, Ho, Wo, cout, co0, off_d, off_h, off_w, st, 1, 0, 0, 0, 1u << kd, nullptr);
+                if (rc != MVSB200_OK) return rc;
+            }
+        return MVSB200_OK;
+    }
     const int nco_max = Cin == 64 ? 16 : 32;
     const int nco = cout < nco_max ? cout : nco_max;
     for (int co0 = 0; co0 < cout; co0 += nco) {

@@ -51,7 +51,9 @@ def test_graphed_step_equals_eager_step(precision):
             assert (p.grad is None) == (q.grad is None), n
             if p.grad is not None:
                 worst = max(worst, float((p.grad - q.grad).abs().max() / (q.grad.abs().max() + 1e-12)))
-        assert worst < (0.15 if precision == "bf16" else 2e-2), worst
+        # the loss goes through the rank-based depth extraction (depthmap.py:11-15): reordered atomic sums can flip a rank, so the
+        # two runs agree to a few percent, not to rounding
+        assert worst < (0.15 if precision == "bf16" else 5e-2), worst
 
 
 def test_graphed_inference_equals_eager_forward():
