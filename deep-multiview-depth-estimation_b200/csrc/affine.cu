@@ -252,6 +252,46 @@ __global__ void __launch_bounds__(kThreadsA) affine_relu_geo_bwd_dx_kernel(const
     }
 }
 
+// Backward APPLY of train-mode BatchNorm + ReLU on a box (the stride-2 branches): with the per-channel vectors of the
+// statistics' backward (a = dL/d(sum x), b2 = 2 dL/d(sum x^2)),
+//   gx = gy * [xv*scale+shift > 0] * scale + a + b2 * xv      over the input box (gy = 0 outside the output box),
+// one pass instead of "affine dx" + "channel sums backward" + an addition -- and written through arbitrary row strides, so that
+// the result can land directly inside the padded channel-stacked buffer the strided convolution's backward reads.
+template <typename T, typename TG>
+__global__ void __launch_bounds__(kThreadsA) box_bn_relu_bwd_apply_kernel(const T* __restrict__ x, const TG* __restrict__ gy, Geo g,
+                                                                          unsigned n_in_chunks, int C,
+                                                                          const float* __restrict__ scale,
+                                                                          const float* __restrict__ shift,
+                                                                          const float* __restrict__ a, const float* __restrict__ b2,
+                                                                          int relu, T* __restrict__ gx, long long osb,
+                                                                          long long osd, long long osh, long long osw) {
+    const int cpr = C / 8;
+    const unsigned i0 = blockIdx.x * kThreadsA + threadIdx.x;
+    const int cshift = cpr == 1 ? 0 : (cpr == 2 ? 1 : (cpr == 4 ? 2 : 3));
+    const int cg = (int)(i0 & (unsigned)(cpr - 1));
+    float sc[8], sh[8], av[8], bv[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { sc[k] = scale[cg * 8 + k]; sh[k] = shift[cg * 8 + k]; av[k] = a[cg * 8 + k]; bv[k] = b2[cg * 8 + k]; }
+    for (unsigned i = i0; i < n_in_chunks; i += gridDim.x * kThreadsA) {
+        int b, d, yy, xx;
+        decode_row(i >> cshift, g.in.fD, g.in.fh, g.in.fw, b, d, yy, xx);
+        const int od = d + g.io[0] - g.oo[0], oy = yy + g.io[1] - g.oo[1], ox = xx + g.io[2] - g.oo[2];
+        float val[8], out[8];
+        load8(x + b * g.in.sb + d * g.in.sd + yy * g.in.sh + xx * g.in.sw + cg * 8, val);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) out[k] = fmaf(bv[k], val[k], av[k]);
+        if ((unsigned)od < (unsigned)g.od[0] && (unsigned)oy < (unsigned)g.od[1] && (unsigned)ox < (unsigned)g.od[2]) {
+            float gv[8];
+            const size_t orow = (((size_t)b * g.od[0] + od) * g.od[1] + oy) * g.od[2] + ox;
+            load8(gy + (orow * cpr + cg) * 8, gv);
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (!relu || fmaf(val[k], sc[k], sh[k]) > 0.f) out[k] = fmaf(gv[k], sc[k], out[k]);
+        }
+        store8(gx + b * osb + d * osd + yy * osh + xx * osw + cg * 8, out);
+    }
+}
+
 int make_view(const int64_t* strides4, const int* dims4, int C, View* v, const char* name) {
     MVS_REQUIRE(strides4 && dims4, "%s: null geometry", name);
     MVS_REQUIRE(C == 8 || C == 16 || C == 32 || C == 64, "%s: C must be 8, 16, 32 or 64 (got %d)", name, C);
@@ -360,4 +400,60 @@ extern "C" int mvsb200_affine_relu_geo_bwd(const void* x, int x_dtype, const int
     if (x_dtype == MVSB200_F32 && g_dtype == MVSB200_F32) return affine_bwd_impl<float, float>(x, gy, g, C, scale, shift, relu, workspace, gscale, gshift, gx, st);
     if (x_dtype == MVSB200_F32 && g_dtype == MVSB200_BF16) return affine_bwd_impl<float, __nv_bfloat16>(x, gy, g, C, scale, shift, relu, workspace, gscale, gshift, gx, st);
     MVS_FAIL(MVSB200_E_BADARG, "affine_relu_geo_bwd: bad dtypes %d / %d", x_dtype, g_dtype);
+}
+
+template <typename T, typename TG>
+static int box_bn_reduce_impl(const void* x, const void* gy, const Geo& g, int C, const float* scale, const float* shift, int relu,
+                              float* workspace, float* gscale, float* gshift, cudaStream_t st) {
+    const unsigned n_out = (unsigned)((long long)g.in.B * g.od[0] * g.od[1] * g.od[2] * (C / 8));
+    const int grid_out = grid_of(n_out);
+    affine_relu_geo_bwd_reduce_kernel<T, TG><<<grid_out, kThreadsA, 0, st>>>((const T*)x, (const TG*)gy, g, n_out, C, scale, shift, relu, workspace);
+    MVS_CHECK_LAUNCH("affine_relu_geo_bwd_reduce");
+    finalize_sums_kernel<<<1, kFinSlicesA * 2 * kMaxCA, 0, st>>>(workspace, grid_out, C, gshift, gscale);
+    MVS_CHECK_LAUNCH("affine_relu_geo_bwd_finalize");
+    return MVSB200_OK;
+}
+
+/* First half of the box BatchNorm+ReLU backward: gshift[c] = sum g, gscale[c] = sum g * xv with g = gy * [xv*scale+shift > 0]
+ * over the output box (deterministic two-stage reduction). */
+extern "C" int mvsb200_box_bn_relu_bwd_reduce(const void* x, int x_dtype, const int64_t* strides4, const int* geo13, int C,
+                                              const float* scale, const float* shift, const void* gy, int g_dtype, float* workspace,
+                                              float* gscale, float* gshift, int relu, void* stream) {
+    MVS_REQUIRE(x && aligned16(x) && gy && aligned16(gy), "box_bn_relu_bwd_reduce: null or misaligned volume");
+    MVS_REQUIRE(scale && shift && workspace && gscale && gshift, "box_bn_relu_bwd_reduce: null vector");
+    Geo g;
+    if (int rc = make_geo(strides4, geo13, C, &g, "box_bn_relu_bwd_reduce")) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (x_dtype == MVSB200_BF16 && g_dtype == MVSB200_BF16) return box_bn_reduce_impl<__nv_bfloat16, __nv_bfloat16>(x, gy, g, C, scale, shift, relu, workspace, gscale, gshift, st);
+    if (x_dtype == MVSB200_BF16 && g_dtype == MVSB200_F32) return box_bn_reduce_impl<__nv_bfloat16, float>(x, gy, g, C, scale, shift, relu, workspace, gscale, gshift, st);
+    if (x_dtype == MVSB200_F32 && g_dtype == MVSB200_F32) return box_bn_reduce_impl<float, float>(x, gy, g, C, scale, shift, relu, workspace, gscale, gshift, st);
+    if (x_dtype == MVSB200_F32 && g_dtype == MVSB200_BF16) return box_bn_reduce_impl<float, __nv_bfloat16>(x, gy, g, C, scale, shift, relu, workspace, gscale, gshift, st);
+    MVS_FAIL(MVSB200_E_BADARG, "box_bn_relu_bwd_reduce: bad dtypes %d / %d", x_dtype, g_dtype);
+}
+
+/* Second half: gx = gy * [xv*scale+shift > 0] * scale + a + b2 * xv over the input box, written through out_strides4 (elements;
+ * gx has x's dtype and may be a view into a larger, channel-stacked buffer). */
+extern "C" int mvsb200_box_bn_relu_bwd_apply(const void* x, int x_dtype, const int64_t* strides4, const int* geo13, int C,
+                                             const float* scale, const float* shift, const float* a, const float* b2, const void* gy,
+                                             int g_dtype, void* gx, const int64_t* out_strides4, int relu, void* stream) {
+    MVS_REQUIRE(x && aligned16(x) && gy && aligned16(gy) && gx && aligned16(gx), "box_bn_relu_bwd_apply: null or misaligned volume");
+    MVS_REQUIRE(scale && shift && a && b2 && out_strides4, "box_bn_relu_bwd_apply: null vector");
+    for (int i = 0; i < 4; ++i) MVS_REQUIRE(out_strides4[i] % 8 == 0, "box_bn_relu_bwd_apply: output strides must be multiples of 8 elements");
+    Geo g;
+    if (int rc = make_geo(strides4, geo13, C, &g, "box_bn_relu_bwd_apply")) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned n_in = (unsigned)((long long)g.in.B * g.in.D * g.in.h * g.in.w * (C / 8));
+    const int grid_in = grid_of(n_in);
+    const long long o0 = out_strides4[0], o1 = out_strides4[1], o2 = out_strides4[2], o3 = out_strides4[3];
+#define MVS_APPLY(T, TG)                                                                                                        \
+    box_bn_relu_bwd_apply_kernel<T, TG><<<grid_in, kThreadsA, 0, st>>>((const T*)x, (const TG*)gy, g, n_in, C, scale, shift, a, b2, relu, \
+                                                                       (T*)gx, o0, o1, o2, o3)
+    if (x_dtype == MVSB200_BF16 && g_dtype == MVSB200_BF16) MVS_APPLY(__nv_bfloat16, __nv_bfloat16);
+    else if (x_dtype == MVSB200_BF16 && g_dtype == MVSB200_F32) MVS_APPLY(__nv_bfloat16, float);
+    else if (x_dtype == MVSB200_F32 && g_dtype == MVSB200_F32) MVS_APPLY(float, float);
+    else if (x_dtype == MVSB200_F32 && g_dtype == MVSB200_BF16) MVS_APPLY(float, __nv_bfloat16);
+    else MVS_FAIL(MVSB200_E_BADARG, "box_bn_relu_bwd_apply: bad dtypes %d / %d", x_dtype, g_dtype);
+#undef MVS_APPLY
+    MVS_CHECK_LAUNCH("box_bn_relu_bwd_apply");
+    return MVSB200_OK;
 }

@@ -296,7 +296,7 @@ class _Conv3dS2Box(torch.autograd.Function):
     gradients go through the library (a tcgen05 strided weight gradient exists, opt-in: _s2_wgrad_ok)."""
 
     @staticmethod
-    def forward(ctx, x, w, pads, out_dims, splits):
+    def forward(ctx, x, w, pads, out_dims, splits, holder=None):
         x_cl = x.detach().contiguous(memory_format=torch.channels_last_3d)
         B, cin, Dx, Hx, Wx = x_cl.shape
         cout = w.shape[0]
@@ -308,6 +308,14 @@ class _Conv3dS2Box(torch.autograd.Function):
                       cin, Do, Ho, Wo, cout, cout, n_rows, pads[0], pads[1], pads[2], _stream())
         ctx.save_for_backward(x_cl, w)
         ctx.pads, ctx.out_dims, ctx.splits = tuple(pads), tuple(out_dims), splits
+        ctx.holder = holder
+        if holder is not None:
+            # geometry of the gradient buffer the library's strided backward wants (see backward): the fused box BatchNorm
+            # backward of each branch writes its slice of it directly (ops.BoxGradDest)
+            P = tuple(q if q >= 2 else q + 2 for q in pads)
+            off = tuple((a - b) // 2 for a, b in zip(P, pads))
+            nat = tuple((n + 2 * a - 3) // 2 + 1 for n, a in zip(x_cl.shape[2:], P))
+            holder.__init__((B, cout) + nat, tuple(slice(o, o + n) for o, n in zip(off, out_dims)), splits, x_cl.device)
         if splits is None:
             return y
         return tuple(torch.split(y, list(splits), 1))
@@ -327,13 +335,22 @@ class _Conv3dS2Box(torch.autograd.Function):
         gx = gw = None
         gy_box = None
         if mask[0] or mask[1]:
-            # gradient of the natural (padded) output, channel-last, filled in place: zeros + one strided copy per branch
-            g_full = torch.empty((B, cout) + nat, dtype=torch.bfloat16, device=x_cl.device, memory_format=torch.channels_last_3d)
-            g_full.zero_()
+            # gradient of the natural (padded) output, channel-last: the buffer the fused box BatchNorm backward already wrote
+            # its slices into (ops.BoxGradDest), else zeros + one strided copy per branch
+            holder = ctx.holder
+            if holder is not None and holder.buffer is not None and holder.shape == (B, cout) + nat:
+                g_full = holder.buffer
+            else:
+                holder = None
+                g_full = torch.empty((B, cout) + nat, dtype=torch.bfloat16, device=x_cl.device, memory_format=torch.channels_last_3d).zero_()
             c0 = 0
-            for g, n in zip(gys, ctx.splits if ctx.splits is not None else (cout,)):
-                if g is not None:
+            for k, (g, n) in enumerate(zip(gys, ctx.splits if ctx.splits is not None else (cout,))):
+                if holder is not None and holder.holds(k, g):
+                    pass                                     # already in place
+                elif g is not None:
                     g_full[(slice(None), slice(c0, c0 + n)) + box] = g
+                elif holder is not None:
+                    g_full[(slice(None), slice(c0, c0 + n)) + box] = 0     # stale slice of an earlier backward pass
                 c0 += n
             gx, gw, _ = torch.ops.aten.convolution_backward(g_full, x_cl, w.detach().to(torch.bfloat16), None, [2, 2, 2], list(P),
                                                             [1, 1, 1], False, [0, 0, 0], 1, mask)
@@ -345,7 +362,7 @@ class _Conv3dS2Box(torch.autograd.Function):
             # gW[co][ci][k] = sum_o x[2o - pad + k][ci] gy[o][co]: the strided operand is the layer's input
             g27 = s2_wgrad(x_cl, gy_box.to(torch.bfloat16).contiguous(memory_format=torch.channels_last_3d), ctx.pads)   # [27, Cin, Cout]
             gw = g27.reshape(3, 3, 3, x_cl.shape[1], cout).permute(4, 3, 0, 1, 2)
-        return gx, (gw.to(w.dtype) if gw is not None else None), None, None, None
+        return gx, (gw.to(w.dtype) if gw is not None else None), None, None, None, None
 
 
 class Tcgen05ConvBackend:
@@ -357,8 +374,17 @@ class Tcgen05ConvBackend:
         (channel counts) the result is a tuple of tensors, one per group of output channels."""
         if (x.is_cuda and x.dtype == torch.bfloat16 and x.shape[1] in _CIN_OK and w.shape[0] % 8 == 0 and w.shape[0] <= 128
                 and all(q in (1, 2) for q in pads) and min(x.shape[3:]) >= 2):
-            return _Conv3dS2Box.apply(x, w, tuple(int(q) for q in pads), tuple(int(n) for n in out_dims),
-                                      None if splits is None else tuple(int(n) for n in splits))
+            from .ops import BoxGradDest
+            holder = None
+            if splits is not None and (x.requires_grad or w.requires_grad):
+                holder = BoxGradDest.__new__(BoxGradDest)     # filled in by the forward (it knows the padded geometry)
+                holder.buffer = None
+            outs = _Conv3dS2Box.apply(x, w, tuple(int(q) for q in pads), tuple(int(n) for n in out_dims),
+                                      None if splits is None else tuple(int(n) for n in splits), holder)
+            if holder is not None:
+                for k, o in enumerate(outs):
+                    o._mvs_grad_dest = (holder, k)           # read by regulariser.py -> ops.box_batchnorm_relu
+            return outs
         return None
 
     @staticmethod

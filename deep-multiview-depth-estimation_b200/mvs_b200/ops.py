@@ -580,3 +580,113 @@ def affine_relu_geo(x, scale, shift, in_origin, out_origin, out_dims, relu=True)
     Differentiable w.r.t. x, scale and shift."""
     return _AffineReLUGeo.apply(x, scale, shift, tuple(int(v) for v in in_origin), tuple(int(v) for v in out_origin),
                                 tuple(int(v) for v in out_dims), bool(relu))
+
+
+# --------------------------------------------------------------------------------------------------
+# K3d, fused: train-mode BatchNorm3d + ReLU of a stride-2 branch on its central box (model.py:104-110)
+# --------------------------------------------------------------------------------------------------
+class BoxGradDest:
+    """Where the gradients of the stacked stride-2 branch outputs are wanted: the padded, channel-stacked, channel-last buffer
+    the strided convolution's backward reads (conv3d_sm100._Conv3dS2Box).  The fused box BatchNorm backward writes its result
+    straight into the branch's slice of that buffer (allocated, zeroed once, on first use), so the three strided copies and
+    the zero-fill of an assembled buffer disappear."""
+
+    def __init__(self, shape, box, splits, device):
+        self.shape, self.box, self.splits, self.device = tuple(shape), tuple(box), tuple(splits), device
+        self.buffer = None
+        self.filled = [False] * len(splits)
+
+    def dest(self, k):
+        if self.buffer is None:
+            self.buffer = torch.empty(self.shape, dtype=torch.bfloat16, device=self.device, memory_format=torch.channels_last_3d).zero_()
+        c0 = sum(self.splits[:k])
+        return self.buffer[(slice(None), slice(c0, c0 + self.splits[k])) + self.box]
+
+    def holds(self, k, g):
+        """g is exactly this holder's slice k (written by the fused backward)."""
+        if self.buffer is None or not self.filled[k] or g is None:
+            return False
+        d = self.dest(k)
+        return g.data_ptr() == d.data_ptr() and g.shape == d.shape and g.stride() == d.stride() and g.dtype == d.dtype
+
+
+class _BoxBatchNormReLU(torch.autograd.Function):
+    """X, scale, shift = BatchNorm_train+ReLU of the box tensor S whose canvas (n_full voxels per channel) is zero outside the
+    box: mean = sum S / n_full, var = sum S^2 / n_full - mean^2 (the zeros count), X on the output box (data where the input box
+    is, relu(shift) around it).  scale / shift are differentiable outputs too (the next layer's analytic statistics use
+    relu(shift)).  Backward: ONE reduction pass (gscale, gshift), the per-channel algebra, ONE apply pass
+    gS = g*scale + dL/d(sum S) + 2 S dL/d(sum S^2) -- written into `grad_dest` when given."""
+
+    @staticmethod
+    def forward(ctx, S, weight, bias, n_full, eps, in_origin, out_origin, out_dims, grad_dest):
+        _need_cuda(S, "box BatchNorm input")
+        _need_cuda(weight, "BatchNorm weight")
+        xv, strides, dims = _box_view(S.detach())
+        C = xv.shape[1]
+        dev = xv.device
+        s1 = torch.empty(C, dtype=torch.float32, device=dev)
+        s2 = torch.empty(C, dtype=torch.float32, device=dev)
+        with _timed("channel_sums"):
+            _lib.call("mvsb200_channel_sums", xv.data_ptr(), _DT[xv.dtype], strides, dims, C, _affine_workspace(dev).data_ptr(),
+                      s1.data_ptr(), s2.data_ptr(), _stream())
+        mean64 = s1.double() / n_full
+        var64 = (s2.double() / n_full - mean64 * mean64).clamp_min(0)
+        r64 = torch.rsqrt(var64 + eps)
+        scale = (weight.detach().double() * r64).float()
+        shift = (bias.detach().double() - mean64 * weight.detach().double() * r64).float()
+        B = xv.shape[0]
+        y = torch.empty((B, C) + tuple(out_dims), dtype=xv.dtype, device=dev, memory_format=torch.channels_last_3d)
+        with _timed("affine_relu_geo_fwd"):
+            _lib.call("mvsb200_affine_relu_geo_fwd", xv.data_ptr(), _DT[xv.dtype], strides, _geo13(xv, in_origin, out_origin, out_dims),
+                      C, scale.data_ptr(), shift.data_ptr(), y.data_ptr(), 1, _stream())
+        ctx.save_for_backward(xv, scale, shift, mean64, r64, weight.detach().double())
+        ctx.geo, ctx.n_full, ctx.grad_dest = (tuple(in_origin), tuple(out_origin), tuple(out_dims)), float(n_full), grad_dest
+        mean, var = mean64.float(), var64.float()
+        ctx.mark_non_differentiable(mean, var)
+        return y, scale, shift, mean, var
+
+    @staticmethod
+    def backward(ctx, gy, g_scale_ext, g_shift_ext, _gm, _gv):
+        xv, scale, shift, mean64, r64, gamma64 = ctx.saved_tensors
+        _, strides, _ = _box_view(xv)
+        C, dev, n = xv.shape[1], xv.device, ctx.n_full
+        if gy is None:
+            gy = torch.empty((xv.shape[0], C) + ctx.geo[2], dtype=xv.dtype, device=dev, memory_format=torch.channels_last_3d).zero_()
+        if gy.dtype not in _DT:
+            gy = gy.float()
+        gy = gy.contiguous(memory_format=torch.channels_last_3d)
+        gscale = torch.empty(C, dtype=torch.float32, device=dev)
+        gshift = torch.empty(C, dtype=torch.float32, device=dev)
+        geo = _geo13(xv, *ctx.geo)
+        with _timed("box_bn_relu_bwd"):
+            _lib.call("mvsb200_box_bn_relu_bwd_reduce", xv.data_ptr(), _DT[xv.dtype], strides, geo, C, scale.data_ptr(), shift.data_ptr(),
+                      gy.data_ptr(), _DT[gy.dtype], _affine_workspace(dev).data_ptr(), gscale.data_ptr(), gshift.data_ptr(), 1, _stream())
+        # per-channel algebra (fp64): scale = gamma r, shift = beta - mean scale, r = rsqrt(var + eps), var = s2/n - mean^2, mean = s1/n
+        G_scale = gscale.double() + (g_scale_ext.double() if g_scale_ext is not None else 0.0)
+        G_shift = gshift.double() + (g_shift_ext.double() if g_shift_ext is not None else 0.0)
+        g_beta = G_shift
+        G_sc = G_scale - mean64 * G_shift
+        g_gamma = G_sc * r64
+        g_var = G_sc * gamma64 * (-0.5) * r64 * r64 * r64
+        g_mean = -(gamma64 * r64) * G_shift - 2.0 * mean64 * g_var
+        a = (g_mean / n).float().contiguous()                   # dL / d(sum S)
+        b2 = (2.0 * g_var / n).float().contiguous()             # 2 dL / d(sum S^2)
+        dest = ctx.grad_dest
+        if dest is not None and xv.dtype == torch.bfloat16:
+            holder, k = dest
+            gx = holder.dest(k)
+            holder.filled[k] = True
+        else:
+            gx = torch.empty(xv.shape, dtype=xv.dtype, device=dev, memory_format=torch.channels_last_3d)
+        import ctypes
+        ostr = (ctypes.c_int64 * 4)(gx.stride(0), gx.stride(2), gx.stride(3), gx.stride(4))
+        with _timed("box_bn_relu_bwd"):
+            _lib.call("mvsb200_box_bn_relu_bwd_apply", xv.data_ptr(), _DT[xv.dtype], strides, geo, C, scale.data_ptr(), shift.data_ptr(),
+                      a.data_ptr(), b2.data_ptr(), gy.data_ptr(), _DT[gy.dtype], gx.data_ptr(), ostr, 1, _stream())
+        return gx, g_gamma.float(), g_beta.float(), None, None, None, None, None, None
+
+
+def box_batchnorm_relu(S, weight, bias, n_full, eps, in_origin, out_origin, out_dims, grad_dest=None):
+    """-> (X on the output box, scale [C], shift [C], batch mean [C], biased batch variance [C]) -- see _BoxBatchNormReLU."""
+    return _BoxBatchNormReLU.apply(S, weight, bias, float(n_full), float(eps), tuple(int(v) for v in in_origin),
+                                   tuple(int(v) for v in out_origin), tuple(int(v) for v in out_dims), grad_dest)

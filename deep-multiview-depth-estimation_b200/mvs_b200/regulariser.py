@@ -208,15 +208,17 @@ class CostVolumeReg(nn.Module):
             if x.is_cuda:
                 # GPU: statistics and normalisation of the box tensors in libmvs_b200.so (K3d), per-channel algebra here
                 if train:
-                    s1, s2 = ops.channel_sums(S)
-                    mean64 = s1.double() / n_full
-                    mean, var = mean64.float(), (s2.double() / n_full - mean64 * mean64).clamp_min(0).float()
+                    # fused op: one statistics pass + one normalise pass forward; backward = one reduction + one apply pass that
+                    # writes the branch's gradient straight into the strided convolution's padded gradient buffer
+                    X, scale, shift, mean, var = ops.box_batchnorm_relu(S, bn.weight, bn.bias, n_full, bn.eps, C_lo, F_lo, F_dims,
+                                                                        getattr(S, "_mvs_grad_dest", None))
+                    self._bn_affine(bn, mean, var, n_full)                    # running statistics (no_grad inside)
+                    bg = F.relu(shift)                                        # everywhere else on the canvas
                 else:
-                    mean = var = None
-                scale, shift = self._bn_affine(bn, mean, var, n_full)
-                bg = F.relu(shift)                                            # everywhere else on the canvas
-                # conv_k_1 input over F = C dilated by 2 (clipped): data on C, BatchNorm'd zero (= bg) around it
-                X = ops.affine_relu_geo(S, scale, shift, C_lo, F_lo, F_dims)
+                    scale, shift = self._bn_affine(bn, None, None, n_full)
+                    bg = F.relu(shift)
+                    X = ops.affine_relu_geo(S, scale, shift, C_lo, F_lo, F_dims)
+                # (X: conv_k_1 input over F = C dilated by 2 (clipped): data on C, BatchNorm'd zero (= bg) around it)
                 if any(zpad):
                     X = F.pad(X, zpad)                                        # canvas border -> zero padding
                 T = be.conv3d(X if X.dtype == dt else X.to(dt), Wk, 1, (0, 0, 0))      # output exactly on E

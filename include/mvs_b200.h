@@ -247,6 +247,19 @@ int mvsb200_affine_relu_geo_bwd(const void* x, int x_dtype, const int64_t* strid
                                 const float* scale, const float* shift, const void* gy, int g_dtype, float* workspace,
                                 float* gscale, float* gshift, void* gx, int relu, void* stream);
 
+/* Train-mode BatchNorm3d + ReLU of a stride-2 branch on its central box (scripts/model.py:104-110 with the padding of
+ * scripts/config.py:20), backward in two halves around the per-channel algebra of the statistics:
+ *   reduce  gshift[c] = sum g, gscale[c] = sum g * xv,  g = gy * [xv*scale+shift > 0]   (over the output box)
+ *   apply   gx = g * scale + a + b2 * xv   over the input box, with a = dL/d(sum x), b2 = 2 dL/d(sum x^2): ONE pass instead of
+ *           an affine data gradient, a statistics gradient and their sum; gx (x's dtype) is written through out_strides4_host
+ *           (elements) so that it can land inside the padded, channel-stacked buffer the strided convolution's backward reads. */
+int mvsb200_box_bn_relu_bwd_reduce(const void* x, int x_dtype, const int64_t* strides4_host, const int* geo13_host, int C,
+                                   const float* scale, const float* shift, const void* gy, int g_dtype, float* workspace,
+                                   float* gscale, float* gshift, int relu, void* stream);
+int mvsb200_box_bn_relu_bwd_apply(const void* x, int x_dtype, const int64_t* strides4_host, const int* geo13_host, int C,
+                                  const float* scale, const float* shift, const float* a, const float* b2, const void* gy,
+                                  int g_dtype, void* gx, const int64_t* out_strides4_host, int relu, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
