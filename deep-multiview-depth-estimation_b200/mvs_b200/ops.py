@@ -690,3 +690,108 @@ def box_batchnorm_relu(S, weight, bias, n_full, eps, in_origin, out_origin, out_
     """-> (X on the output box, scale [C], shift [C], batch mean [C], biased batch variance [C]) -- see _BoxBatchNormReLU."""
     return _BoxBatchNormReLU.apply(S, weight, bias, float(n_full), float(eps), tuple(int(v) for v in in_origin),
                                    tuple(int(v) for v in out_origin), tuple(int(v) for v in out_dims), grad_dest)
+
+
+class _BoxLink:
+    """Connects the two autograd nodes of a box BatchNorm whose statistics go through differentiable per-channel algebra outside
+    (conv_k_1: its statistics also depend on the filter and on the constant around the box): the affine node's backward only
+    REDUCES (gscale, gshift) and leaves (gy, scale, shift, geometry) here; the statistics node's backward -- which autograd
+    runs afterwards, its incoming gradients depend on gscale / gshift -- then makes the ONE apply pass
+    gT = gy*mask*scale + g1 + 2 T g2 instead of an affine data gradient, a statistics gradient and their sum."""
+
+    def __init__(self):
+        self.pending = None          # (gy, scale, shift, geo, relu) left by the affine backward
+        self.sums_done = False
+
+
+class _BoxSumsLinked(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, link):
+        _need_cuda(x, "channel_sums input")
+        xv, strides, dims = _box_view(x.detach())
+        C = xv.shape[1]
+        s1 = torch.empty(C, dtype=torch.float32, device=xv.device)
+        s2 = torch.empty(C, dtype=torch.float32, device=xv.device)
+        with _timed("channel_sums"):
+            _lib.call("mvsb200_channel_sums", xv.data_ptr(), _DT[xv.dtype], strides, dims, C,
+                      _affine_workspace(xv.device).data_ptr(), s1.data_ptr(), s2.data_ptr(), _stream())
+        ctx.save_for_backward(xv)
+        ctx.link = link
+        return s1, s2
+
+    @staticmethod
+    def backward(ctx, g1, g2):
+        (xv,) = ctx.saved_tensors
+        _, strides, dims = _box_view(xv)
+        C, dev = xv.shape[1], xv.device
+        link = ctx.link
+        g1 = (torch.zeros(C, device=dev) if g1 is None else g1.float()).contiguous()
+        g2 = (torch.zeros(C, device=dev) if g2 is None else g2.float()).contiguous()
+        gx = torch.empty(xv.shape, dtype=xv.dtype, device=dev, memory_format=torch.channels_last_3d)
+        link.sums_done = True
+        if link.pending is None:                     # the affine node had no incoming gradient (or runs later): statistics only
+            with _timed("channel_sums_bwd"):
+                _lib.call("mvsb200_channel_sums_bwd", xv.data_ptr(), _DT[xv.dtype], strides, dims, C, g1.data_ptr(), g2.data_ptr(),
+                          gx.data_ptr(), _stream())
+            return gx, None
+        gy, sc, sh, geo, relu = link.pending
+        link.pending = None
+        import ctypes
+        ostr = (ctypes.c_int64 * 4)(gx.stride(0), gx.stride(2), gx.stride(3), gx.stride(4))
+        b2 = (2.0 * g2).contiguous()
+        with _timed("box_bn_relu_bwd"):
+            _lib.call("mvsb200_box_bn_relu_bwd_apply", xv.data_ptr(), _DT[xv.dtype], strides, _geo13(xv, *geo), C, sc.data_ptr(),
+                      sh.data_ptr(), g1.data_ptr(), b2.data_ptr(), gy.data_ptr(), _DT[gy.dtype], gx.data_ptr(), ostr, int(relu), _stream())
+        return gx, None
+
+
+class _AffineReLUGeoLinked(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, scale, shift, in_origin, out_origin, out_dims, relu, link):
+        _need_cuda(x, "affine_relu_geo input")
+        xv, strides, _ = _box_view(x.detach())
+        B, C = xv.shape[:2]
+        sc, sh = scale.detach().float().contiguous(), shift.detach().float().contiguous()
+        y = torch.empty((B, C) + tuple(out_dims), dtype=xv.dtype, device=xv.device, memory_format=torch.channels_last_3d)
+        with _timed("affine_relu_geo_fwd"):
+            _lib.call("mvsb200_affine_relu_geo_fwd", xv.data_ptr(), _DT[xv.dtype], strides, _geo13(xv, in_origin, out_origin, out_dims),
+                      C, sc.data_ptr(), sh.data_ptr(), y.data_ptr(), int(relu), _stream())
+        ctx.save_for_backward(xv, sc, sh)
+        ctx.geo, ctx.relu, ctx.link = (tuple(in_origin), tuple(out_origin), tuple(out_dims)), bool(relu), link
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        xv, sc, sh = ctx.saved_tensors
+        _, strides, _ = _box_view(xv)
+        C, dev, link = xv.shape[1], xv.device, ctx.link
+        if gy.dtype not in _DT:
+            gy = gy.float()
+        gy = gy.contiguous(memory_format=torch.channels_last_3d)
+        gscale = torch.empty(C, dtype=torch.float32, device=dev)
+        gshift = torch.empty(C, dtype=torch.float32, device=dev)
+        if link.sums_done:                           # the statistics node already ran (no dependency on this one): classic form
+            gx = torch.empty(xv.shape, dtype=xv.dtype, device=dev, memory_format=torch.channels_last_3d)
+            with _timed("affine_relu_geo_bwd"):
+                _lib.call("mvsb200_affine_relu_geo_bwd", xv.data_ptr(), _DT[xv.dtype], strides, _geo13(xv, *ctx.geo), C,
+                          sc.data_ptr(), sh.data_ptr(), gy.data_ptr(), _DT[gy.dtype], _affine_workspace(dev).data_ptr(),
+                          gscale.data_ptr(), gshift.data_ptr(), gx.data_ptr(), int(ctx.relu), _stream())
+            return gx, gscale, gshift, None, None, None, None, None
+        with _timed("box_bn_relu_bwd"):
+            _lib.call("mvsb200_box_bn_relu_bwd_reduce", xv.data_ptr(), _DT[xv.dtype], strides, _geo13(xv, *ctx.geo), C, sc.data_ptr(),
+                      sh.data_ptr(), gy.data_ptr(), _DT[gy.dtype], _affine_workspace(dev).data_ptr(), gscale.data_ptr(),
+                      gshift.data_ptr(), int(ctx.relu), _stream())
+        link.pending = (gy, sc, sh, ctx.geo, ctx.relu)   # the data gradient is made by the statistics node's backward
+        return None, gscale, gshift, None, None, None, None, None
+
+
+def box_batchnorm_linked(x):
+    """-> (link, (sum x, sum x^2)) for a box BatchNorm whose per-channel algebra stays outside; pass `link` to
+    affine_relu_geo_linked for the normalisation of the same tensor."""
+    link = _BoxLink()
+    return link, _BoxSumsLinked.apply(x, link)
+
+
+def affine_relu_geo_linked(x, scale, shift, in_origin, out_origin, out_dims, link, relu=True):
+    return _AffineReLUGeoLinked.apply(x, scale, shift, tuple(int(v) for v in in_origin), tuple(int(v) for v in out_origin),
+                                      tuple(int(v) for v in out_dims), bool(relu), link)

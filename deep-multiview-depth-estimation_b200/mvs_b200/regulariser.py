@@ -223,10 +223,14 @@ class CostVolumeReg(nn.Module):
                     X = F.pad(X, zpad)                                        # canvas border -> zero padding
                 T = be.conv3d(X if X.dtype == dt else X.to(dt), Wk, 1, (0, 0, 0))      # output exactly on E
                 if train:
-                    t1, t2 = ops.channel_sums(T)
+                    # statistics node and normalisation node linked: the backward makes one reduction and one apply pass
+                    link, (t1, t2) = ops.box_batchnorm_linked(T)
                     mean, var = self._stats_from_sums_with_constant_outside(t1, t2, Wk.float(), bg, dims, E_lo, E_hi, B, n_full)
-                scale, shift = self._bn_affine(bn, mean if train else None, var if train else None, n_full)
-                enc[k] = ops.affine_relu_geo(T, scale, shift, E_lo, C_lo, C_dims)      # on C, storage dtype of the path
+                    scale, shift = self._bn_affine(bn, mean, var, n_full)
+                    enc[k] = ops.affine_relu_geo_linked(T, scale, shift, E_lo, C_lo, C_dims, link)   # on C, storage dtype of the path
+                else:
+                    scale, shift = self._bn_affine(bn, None, None, n_full)
+                    enc[k] = ops.affine_relu_geo(T, scale, shift, E_lo, C_lo, C_dims)
                 continue
             Sf = S.float()
             if train:
