@@ -252,49 +252,121 @@ __global__ void __launch_bounds__(256) conv_out_dgrad_march_kernel(const float* 
     }
 }
 
-// weight gradient: a warp walks one (b, d, y) line; lane = tap (27 of 32 lanes) with the 8 channel sums of its tap in
-// registers; per voxel a lane reads ONE 16-byte voxel row (the three kw lanes of a (kd,kh) read 48 contiguous bytes) and
-// the broadcast upstream gradient.  Same two-stage deterministic reduction as before.
-__global__ void __launch_bounds__(256) conv_out_wgrad_tap_kernel(const uint4* __restrict__ z, const float* __restrict__ g,
-                                                                 float* __restrict__ partials, int B, int D, int h, int w) {
-    __shared__ float s_acc[8][kWn];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int tap = lane < kTaps ? lane : 0;
-    const int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
-    const bool owner = lane < kTaps;
-    float acc[8];
+// Weight gradient, depth-marching form.  gW[tap][c] = sum_v g[v] * z[v + tap - 1][c]  ==  every z voxel u adds
+// z[u][c] * g[u - (tap - 1)] to the 27 taps.  A thread owns an (x, y) column and TWO channels (4 threads per voxel, a warp = 8
+// pixels of a line) and walks a run of planes: per plane it loads its 4 bytes of the voxel row once and multiplies them into 27
+// accumulator pairs with the 3x3x3 neighbourhood of g -- three planes of 9 values held in registers (rotated by unrolling the
+// plane loop three times), the entering plane read through L1 (the 4 threads of a pixel and the 8 pixels of a warp share the
+// lines).  54 FMAs per 4 bytes of z instead of 8 per 16 bytes and tap (the previous form: a warp per line, lane = tap, 22
+// instructions per 216 MACs); no shared memory, no barrier in the loop (a first version staged g through a shared tile with
+// two CTA barriers per plane: 1.0 ms instead of 0.7 -- barrier bound).  CTAs are persistent (<= 592): accumulators run on
+// across work items and are reduced once (shuffles in a fixed order, then the deterministic finalize).
+constexpr int kWTX = 16, kWTY = 4, kWDchunk = 48;    // pixel tile, planes per work item (a multiple of 3)
+__device__ float c_zero_row[4];                      // where the row pointer of a line outside the image points
+
+__global__ void __launch_bounds__(256, 2) conv_out_wgrad_march_kernel(const uint32_t* __restrict__ z, const float* __restrict__ g,
+                                                                      float* __restrict__ partials, int B, int D, int h, int w,
+                                                                      int tiles_x, int tiles_y, int nchunks, int n_items) {
+    __shared__ float s_red[8][4][54];                // per warp, per channel pair
+    const int tid = threadIdx.x, cp = tid & 3, pix = tid >> 2;
+    const int lx = pix & (kWTX - 1), ly = pix / kWTX;
+    float2 acc[27];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) acc[c] = 0.f;
-    const long lines = (long)B * D * h;
-    for (long line = (long)blockIdx.x * 8 + warp; line < lines; line += (long)gridDim.x * 8) {
-        const int y = (int)(line % h);
-        const int d = (int)((line / h) % D);
-        const int b = (int)(line / ((long)h * D));
-        const int dz = d + kd - 1, yy = y + kh - 1;
-        const bool row_ok = owner && (unsigned)dz < (unsigned)D && (unsigned)yy < (unsigned)h;
-        const float* gl = g + line * w;
-        const uint4* zr = z + ((size_t)(b * D + (row_ok ? dz : d)) * h + (row_ok ? yy : y)) * w;
-        const int x_lo = max(0, 1 - kw), x_hi = min(w, w + 1 - kw);       // x with 0 <= x + kw - 1 < w
-#pragma unroll 4
-        for (int x = 0; x < w; ++x) {
-            const float gv = __ldg(gl + x);
-            if (row_ok && x >= x_lo && x < x_hi) {
-                float v[8];
-                bf16x8_to_f32(__ldg(zr + x + kw - 1), v);
+    for (int t = 0; t < 27; ++t) acc[t] = make_float2(0.f, 0.f);
+    const size_t plane = (size_t)h * w;
+
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int t = item % (tiles_x * tiles_y), r = item / (tiles_x * tiles_y);
+        const int c = r % nchunks, b = r / nchunks;
+        const int d0 = c * kWDchunk, nd = min(kWDchunk, D - d0);
+        const int x = (t % tiles_x) * kWTX + lx, y = (t / tiles_x) * kWTY + ly;
+        const bool inside = x < w && y < h;
+        const float* gb = g + (size_t)b * D * plane;
+        // in-plane neighbours g[.][y - kh + 1][x - kw + 1].  Address arithmetic is what this loop must not do (a first
+        // barrier-free version spent ~250 of its 280 instructions per plane on 64-bit address generation and predicates for
+        // nine guarded loads): per item one row pointer per kh (a row outside the image points at a zero word and never
+        // advances), per plane one multiply-add per row, the three kw taps at fixed element offsets (0 where the column is
+        // outside the image, the loaded value then replaced by 0)
+        const float* rowp[3];
+        long long rstep[3];
+        int offx[3];
+        bool colok[3];
 #pragma unroll
-                for (int c = 0; c < 8; ++c) acc[c] = fmaf(gv, v[c], acc[c]);
+        for (int kw = 0; kw < 3; ++kw) {
+            const int xx = x - kw + 1;
+            colok[kw] = inside && (unsigned)xx < (unsigned)w;
+            offx[kw] = colok[kw] ? 1 - kw : 0;
+        }
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+            const int yy = y - kh + 1;
+            const bool rok = inside && (unsigned)yy < (unsigned)h;
+            rowp[kh] = rok ? gb + (size_t)yy * w + x : c_zero_row;
+            rstep[kh] = rok ? (long long)plane : 0;
+        }
+        auto read_plane = [&](int p, float (&dst)[9]) {          // plane p of g, zero outside the volume
+            const int pc = min(max(p, 0), D - 1);
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh) {
+                const float* rp = rowp[kh] + rstep[kh] * pc;
+#pragma unroll
+                for (int kw = 0; kw < 3; ++kw) {
+                    const float v = __ldg(rp + offx[kw]);
+                    dst[kh * 3 + kw] = colok[kw] ? v : 0.f;
+                }
             }
+            if (p != pc) {                            // uniform over the CTA: the plane below / above the volume
+#pragma unroll
+                for (int k9 = 0; k9 < 9; ++k9) dst[k9] = 0.f;
+            }
+        };
+        float g0[9], g1[9], g2[9];                    // planes d-1, d, d+1 of the current step (roles rotate)
+        read_plane(d0 - 1, g0);
+        read_plane(d0, g1);
+        const uint32_t* zc = z + (((size_t)b * D + d0) * plane + (size_t)y * w + x) * 4 + cp;     // 4 channel pairs per voxel row
+        const size_t zstep = plane * 4;
+        auto step = [&](int dd, const float (&lo)[9], const float (&mid)[9], float (&hi)[9]) {
+            read_plane(d0 + dd + 1, hi);
+            float2 zv = make_float2(0.f, 0.f);
+            if (inside && dd < nd) {
+                const uint32_t u = __ldg(zc);
+                zv = make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+            }
+            zc += zstep;
+            // tap (kd, kh, kw) pairs z[d] with g at plane d - kd + 1: kd = 0 -> hi, 1 -> mid, 2 -> lo
+#pragma unroll
+            for (int k9 = 0; k9 < 9; ++k9) {
+                acc[k9] = __ffma2_rn(make_float2(hi[k9], hi[k9]), zv, acc[k9]);
+                acc[9 + k9] = __ffma2_rn(make_float2(mid[k9], mid[k9]), zv, acc[9 + k9]);
+                acc[18 + k9] = __ffma2_rn(make_float2(lo[k9], lo[k9]), zv, acc[18 + k9]);
+            }
+        };
+        for (int dd = 0; dd < nd; dd += 3) {          // planes beyond nd contribute zero (zv = 0)
+            step(dd, g0, g1, g2);
+            step(dd + 1, g1, g2, g0);
+            step(dd + 2, g2, g0, g1);
         }
     }
-    if (owner) {
+    // reduce over the pixels of the CTA, fixed order: lanes of a warp with the same channel pair (xor 4, 8, 16), then warps
 #pragma unroll
-        for (int c = 0; c < 8; ++c) s_acc[warp][tap * kCi + c] = acc[c];
+    for (int t = 0; t < 27; ++t) {
+#pragma unroll
+        for (int m = 4; m < 32; m <<= 1) {
+            acc[t].x += __shfl_xor_sync(0xffffffffu, acc[t].x, m);
+            acc[t].y += __shfl_xor_sync(0xffffffffu, acc[t].y, m);
+        }
+    }
+    const int lane = tid & 31, warp = tid >> 5;
+    if (lane < 4) {
+#pragma unroll
+        for (int t = 0; t < 27; ++t) { s_red[warp][lane][2 * t] = acc[t].x; s_red[warp][lane][2 * t + 1] = acc[t].y; }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < kWn; i += 256) {
+    for (int i = tid; i < kWn; i += 256) {           // i = tap * 8 + channel
+        const int tap = i >> 3, ch = i & 7;
         float sum = 0.f;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) sum += s_acc[k][i];
+        for (int k = 0; k < 8; ++k) sum += s_red[k][ch >> 1][2 * tap + (ch & 1)];
         partials[(size_t)blockIdx.x * kWn + i] = sum;
     }
 }
@@ -375,8 +447,16 @@ extern "C" int mvsb200_conv_out_wgrad(const void* z, const float* glogits, float
     const int blocks = (int)((lines + 7) / 8 < kWgBlocks ? (lines + 7) / 8 : kWgBlocks);
     if (use_march()) {
         MVS_REQUIRE(aligned16(z), "conv_out_wgrad: misaligned volume");
-        conv_out_wgrad_tap_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const uint4*)z, glogits, workspace, B, D, h, w);
-        MVS_CHECK_LAUNCH("conv_out_wgrad_tap");
+        const int tiles_x = (w + kWTX - 1) / kWTX, tiles_y = (h + kWTY - 1) / kWTY, nchunks = (D + kWDchunk - 1) / kWDchunk;
+        const long items = (long)tiles_x * tiles_y * nchunks * B;
+        MVS_REQUIRE(items < (1L << 31), "conv_out_wgrad: volume too large");
+        const int grid = (int)(items < kWgBlocks ? items : kWgBlocks);
+        conv_out_wgrad_march_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const uint32_t*)z, glogits, workspace, B, D, h, w, tiles_x,
+                                                                            tiles_y, nchunks, (int)items);
+        MVS_CHECK_LAUNCH("conv_out_wgrad_march");
+        conv_out_wgrad_finalize_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(workspace, grid, gw27x8);
+        MVS_CHECK_LAUNCH("conv_out_wgrad_finalize");
+        return MVSB200_OK;
     } else {
         conv_out_wgrad_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)z, glogits, workspace, B, D, h, w);
         MVS_CHECK_LAUNCH("conv_out_wgrad");
