@@ -181,6 +181,35 @@ __global__ void __launch_bounds__(kBnThreads) bn_relu_bwd_reduce_kernel(const TX
     block_reduce_to_partial(sg, sgx, cpr, C, partials + (size_t)blockIdx.x * 2 * C);
 }
 
+// dx = gamma*invstd * (g - dbeta/M - xhat*dgamma/M) with g = gy * [x*scale+shift > 0], rewritten per channel as
+//   dx = t + [mask] * a1 * gy,   t = a2 * x + a3,   a1 = gamma*invstd,  a2 = -a1 * (dgamma/M) * invstd,
+//   a3 = a1 * ((dgamma/M) * mean * invstd - dbeta/M)
+// (two FMAs and a select per element instead of seven operations).
+struct BwdCoef {
+    float sc[8], sh[8], a1[8], a2[8], a3[8];
+};
+__device__ __forceinline__ void load_bwd_coef(BwdCoef& k, int cg, const float* scale, const float* shift, const float* mean,
+                                              const float* invstd, const float* gamma, const float* dbeta, const float* dgamma,
+                                              float inv_m) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = cg * 8 + j;
+        const float is = invstd[c], k0 = gamma[c] * is, k1 = dbeta[c] * inv_m, k2 = dgamma[c] * inv_m;
+        k.sc[j] = scale[c]; k.sh[j] = shift[c];
+        k.a1[j] = k0;
+        k.a2[j] = -k0 * k2 * is;
+        k.a3[j] = k0 * (k2 * mean[c] * is - k1);
+    }
+}
+__device__ __forceinline__ void bwd_apply8(const BwdCoef& k, float (&v)[8], const float (&g)[8], int relu, bool has_g) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float t = fmaf(k.a2[j], v[j], k.a3[j]);
+        const bool on = has_g && (!relu || fmaf(v[j], k.sc[j], k.sh[j]) > 0.f);
+        v[j] = on ? fmaf(k.a1[j], g[j], t) : t;
+    }
+}
+
 template <typename TX, typename TG>
 __global__ void __launch_bounds__(kBnThreads) bn_relu_bwd_apply_kernel(const TX* __restrict__ x, const TG* __restrict__ gy,
                                                                        const float* __restrict__ scale,
@@ -194,26 +223,14 @@ __global__ void __launch_bounds__(kBnThreads) bn_relu_bwd_apply_kernel(const TX*
     const int cpr = C / 8;
     const long long i0 = (long long)blockIdx.x * kBnThreads + threadIdx.x;
     const int cg = (int)(i0 % cpr);
-    float sc[8], sh[8], mu[8], is[8], k0[8], k1[8], k2[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const int c = cg * 8 + k;
-        sc[k] = scale[c]; sh[k] = shift[c]; mu[k] = mean[c]; is[k] = invstd[c];
-        k0[k] = gamma[c] * is[k];                 // dx = k0 * (g - k1 - xhat * k2)
-        k1[k] = dbeta[c] * inv_m;
-        k2[k] = dgamma[c] * inv_m;
-    }
+    BwdCoef k;
+    load_bwd_coef(k, cg, scale, shift, mean, invstd, gamma, dbeta, dgamma, inv_m);
     const long long stride = (long long)gridDim.x * kBnThreads;
     for (long long i = i0; i < n_chunks; i += stride) {
         float v[8], g[8];
         Chunk<TX>::load(x + i * 8, v);
         Chunk<TG>::load(gy + i * 8, g);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const float gk = (!relu || fmaf(v[k], sc[k], sh[k]) > 0.f) ? g[k] : 0.f;
-            const float xhat = (v[k] - mu[k]) * is[k];
-            v[k] = k0[k] * (gk - k1[k] - xhat * k2[k]);
-        }
+        bwd_apply8(k, v, g, relu, true);
         Chunk<TX>::store(dx + i * 8, v);
     }
 }
@@ -310,77 +327,91 @@ __global__ void __launch_bounds__(kBnThreads) bn_relu_fwd_crop_kernel(const T* _
     }
 }
 
+// Line-major (see the apply kernel below): a warp takes one line (b, d, y) of the BOX at a time; the gradient is zero outside.
 template <typename TX, typename TG>
 __global__ void __launch_bounds__(kBnThreads) bn_relu_bwd_reduce_crop_kernel(
     const TX* __restrict__ x, const TG* __restrict__ gy, const float* __restrict__ scale, const float* __restrict__ shift,
-    const float* __restrict__ mean, const float* __restrict__ invstd, long long n_box_chunks, int C, int relu,
+    const float* __restrict__ mean, const float* __restrict__ invstd, long long n_box_lines, int C, int relu,
     float* __restrict__ partials, CropBox cb) {
     const int cpr = C / 8;
-    const long long i0 = (long long)blockIdx.x * kBnThreads + threadIdx.x;
-    const int cg = (int)(i0 % cpr);
+    const int lane = threadIdx.x & 31;
+    const int cg = lane & (cpr - 1);
     float sc[8], sh[8], mu[8], is[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         sc[k] = scale[cg * 8 + k]; sh[k] = shift[cg * 8 + k]; mu[k] = mean[cg * 8 + k]; is[k] = invstd[cg * 8 + k];
     }
     float sg[8] = {0, 0, 0, 0, 0, 0, 0, 0}, sgx[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    const long long stride = (long long)gridDim.x * kBnThreads;
-    for (long long i = i0; i < n_box_chunks; i += stride) {      // the gradient is zero outside the box
-        float v[8], g[8];
-        Chunk<TX>::load(x + box_to_canvas(i, cpr, cb) * 8, v);
-        Chunk<TG>::load(gy + i * 8, g);
+    const long long warps = (long long)gridDim.x * (kBnThreads / 32);
+    const int line_chunks = cb.wc * cpr;
+    for (long long line = (long long)blockIdx.x * (kBnThreads / 32) + (threadIdx.x >> 5); line < n_box_lines; line += warps) {
+        unsigned uy, ud;
+        unsigned r = fd_divmod((unsigned)line, cb.f_hc, uy);
+        const unsigned b = fd_divmod(r, cb.f_dc, ud);
+        const size_t xbase = ((((size_t)b * cb.Da + ud + cb.d0) * cb.ha + uy + cb.h0) * cb.wa + cb.w0) * cpr;
+        const size_t gbase = (size_t)line * line_chunks;
+        for (int j = lane; j < line_chunks; j += 32) {
+            float v[8], g[8];
+            Chunk<TX>::load(x + (xbase + j) * 8, v);
+            Chunk<TG>::load(gy + (gbase + j) * 8, g);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const float gk = (!relu || fmaf(v[k], sc[k], sh[k]) > 0.f) ? g[k] : 0.f;
-            sg[k] += gk;
-            sgx[k] = fmaf(gk, (v[k] - mu[k]) * is[k], sgx[k]);
+            for (int k = 0; k < 8; ++k) {
+                const float gk = (!relu || fmaf(v[k], sc[k], sh[k]) > 0.f) ? g[k] : 0.f;
+                sg[k] += gk;
+                sgx[k] = fmaf(gk, (v[k] - mu[k]) * is[k], sgx[k]);
+            }
         }
     }
     block_reduce_to_partial(sg, sgx, cpr, C, partials + (size_t)blockIdx.x * 2 * C);
 }
 
+// Line-major form: a warp takes one line (b, d, y) of the ALLOCATION at a time -- where the line sits relative to the canvas
+// and to the box is decided once per line, a chunk inside the line costs a shift, a mask and two compares (the chunk-major
+// form decoded every 16-byte chunk with six multiply-high divisions: ~80 of its ~220 instructions per chunk).
 template <typename TX, typename TG>
 __global__ void __launch_bounds__(kBnThreads) bn_relu_bwd_apply_crop_kernel(
     const TX* __restrict__ x, const TG* __restrict__ gy, const float* __restrict__ scale, const float* __restrict__ shift,
     const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
-    const float* __restrict__ dbeta, const float* __restrict__ dgamma, TX* __restrict__ dx, long long n_chunks, int C, int relu,
+    const float* __restrict__ dbeta, const float* __restrict__ dgamma, TX* __restrict__ dx, long long n_lines, int C, int relu,
     float inv_m, CropBox cb) {
     const int cpr = C / 8;
-    const long long i0 = (long long)blockIdx.x * kBnThreads + threadIdx.x;
-    const int cg = (int)(i0 % cpr);
-    float sc[8], sh[8], mu[8], is[8], k0[8], k1[8], k2[8];
+    const int lane = threadIdx.x & 31;
+    const int cg = lane & (cpr - 1);                 // 32 % cpr == 0: a lane keeps its channel group along a line
+    BwdCoef k;
+    load_bwd_coef(k, cg, scale, shift, mean, invstd, gamma, dbeta, dgamma, inv_m);
+    const long long warps = (long long)gridDim.x * (kBnThreads / 32);
+    const int line_chunks = cb.wa * cpr;
+    for (long long line = (long long)blockIdx.x * (kBnThreads / 32) + (threadIdx.x >> 5); line < n_lines; line += warps) {
+        unsigned uy, ud;
+        unsigned r = fd_divmod((unsigned)line, cb.f_ha, uy);
+        const unsigned b = fd_divmod(r, cb.f_Da, ud);
+        const int ya = (int)uy, da = (int)ud;
+        const bool in_canvas = ya < cb.h && da < cb.D;
+        const int yb = ya - cb.h0, db = da - cb.d0;
+        const bool in_box_line = in_canvas && (unsigned)yb < (unsigned)cb.hc && (unsigned)db < (unsigned)cb.dc;
+        const size_t xbase = (size_t)line * line_chunks;                                     // chunk index of the line's first chunk
+        const size_t gbase = (((size_t)b * cb.dc + (in_box_line ? db : 0)) * cb.hc + (in_box_line ? yb : 0)) * cb.wc * cpr;
+        for (int j = lane; j < line_chunks; j += 32) {
+            const int xa = j >> cb.cshift;
+            float v[8], g[8];
+            if (!in_canvas || xa >= cb.w) {                       // allocation slack outside the canvas: no gradient
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const int c = cg * 8 + k;
-        sc[k] = scale[c]; sh[k] = shift[c]; mu[k] = mean[c]; is[k] = invstd[c];
-        k0[k] = gamma[c] * is[k];
-        k1[k] = dbeta[c] * inv_m;
-        k2[k] = dgamma[c] * inv_m;
-    }
-    const long long stride = (long long)gridDim.x * kBnThreads;
-    for (long long i = i0; i < n_chunks; i += stride) {          // dx is dense on the canvas: the statistics couple every voxel
-        float v[8], g[8];
-        const long long j = alloc_to_box(i, cpr, cb);
-        if (j == -2) {                                            // allocation slack outside the canvas: no gradient
+                for (int q = 0; q < 8; ++q) v[q] = 0.f;
+                Chunk<TX>::store(dx + (xbase + j) * 8, v);
+                continue;
+            }
+            Chunk<TX>::load(x + (xbase + j) * 8, v);
+            const int xb = xa - cb.w0;
+            const bool has_g = in_box_line && (unsigned)xb < (unsigned)cb.wc;
+            if (has_g) {
+                Chunk<TG>::load(gy + (gbase + (size_t)xb * cpr + cg) * 8, g);
+            } else {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) v[k] = 0.f;
-            Chunk<TX>::store(dx + i * 8, v);
-            continue;
+                for (int q = 0; q < 8; ++q) g[q] = 0.f;
+            }
+            bwd_apply8(k, v, g, relu, has_g);
+            Chunk<TX>::store(dx + (xbase + j) * 8, v);
         }
-        Chunk<TX>::load(x + i * 8, v);
-        if (j >= 0) {
-            Chunk<TG>::load(gy + j * 8, g);
-        } else {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) g[k] = 0.f;
-        }
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const float gk = (!relu || fmaf(v[k], sc[k], sh[k]) > 0.f) ? g[k] : 0.f;
-            const float xhat = (v[k] - mu[k]) * is[k];
-            v[k] = k0[k] * (gk - k1[k] - xhat * k2[k]);
-        }
-        Chunk<TX>::store(dx + i * 8, v);
     }
 }
 
@@ -541,14 +572,20 @@ static int bn_bwd_crop_impl(const void* x, const void* gy, const float* scale, c
     const long long n_chunks = (long long)B * cb.Da * cb.ha * cb.wa * C / 8;       // dx covers the whole allocation
     const long long n_box = (long long)B * cb.dc * cb.hc * cb.wc * C / 8;
     const int grid_box = grid_for(n_box), grid = grid_for(n_chunks);
+    const long long n_box_lines = (long long)B * cb.dc * cb.hc;
     bn_relu_bwd_reduce_crop_kernel<TX, TG><<<grid_box, kBnThreads, 0, st>>>((const TX*)x, (const TG*)gy, scale, shift, mean,
-                                                                            invstd, n_box, C, relu, workspace, cb);
+                                                                            invstd, n_box_lines, C, relu, workspace, cb);
     MVS_CHECK_LAUNCH("bn_relu_bwd_reduce_crop");
     bn_finalize_kernel<<<1, kFinSlices * 2 * kMaxC, 0, st>>>(workspace, grid_box, C, 1.0, 1, dbeta, dgamma);
     MVS_CHECK_LAUNCH("bn_finalize");
-    bn_relu_bwd_apply_crop_kernel<TX, TG><<<grid, kBnThreads, 0, st>>>((const TX*)x, (const TG*)gy, scale, shift, mean, invstd,
-                                                                       gamma, dbeta, dgamma, (TX*)dx, n_chunks, C, relu,
-                                                                       (float)(1.0 / (double)M), cb);
+    const long long n_lines = (long long)B * cb.Da * cb.ha;
+    MVS_REQUIRE(n_lines < (1LL << 31), "bn_relu_bwd_crop: too many lines");
+    const long long want = (n_lines + kBnThreads / 32 - 1) / (kBnThreads / 32);
+    const int grid_lines = (int)(want < kBnBlocks ? want : kBnBlocks);
+    (void)grid;
+    bn_relu_bwd_apply_crop_kernel<TX, TG><<<grid_lines, kBnThreads, 0, st>>>((const TX*)x, (const TG*)gy, scale, shift, mean, invstd,
+                                                                             gamma, dbeta, dgamma, (TX*)dx, n_lines, C, relu,
+                                                                             (float)(1.0 / (double)M), cb);
     MVS_CHECK_LAUNCH("bn_relu_bwd_apply_crop");
     return MVSB200_OK;
 }
