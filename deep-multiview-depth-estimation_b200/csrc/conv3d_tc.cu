@@ -18,8 +18,7 @@
 //   * accumulators live in TMEM (MB blocks of 128 rows x NOUT fp32 columns, double buffered), the epilogue warps read
 //     them back with tcgen05.ld, convert to bf16 and store voxel rows while the MMA warp works on the next plane.
 // Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane) + TMEM allocator, warps 2..5 = epilogue.
-#include "common.cuh"
-#include <cuda.h>
+#include "tc_common.cuh"
 #include <stdlib.h>
 
 using namespace mvsb200;
@@ -46,112 +45,6 @@ struct ConvParams {
     __nv_bfloat16* y;
 };
 
-// ---- PTX wrappers ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE;\n\t"
-        "bra WAIT_LOOP;\n\t"
-        "DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3,
-                                            int c4) {
-    asm volatile(
-        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-                 : "memory");
-}
-// one lane of a converged warp (the form the compiler recognises as single-thread issue: no uniformisation loops
-// around the tcgen05 / TMA instructions it guards)
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred = 0;
-    asm volatile(
-        "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
-        "elect.sync rx|px, 0xffffffff;\n\t"
-        "@px mov.s32 %0, 1;\n\t}"
-        : "+r"(pred));
-    return pred != 0;
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc),
-        "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-template <int N>
-__device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t (&v)[N]);
-template <>
-__device__ __forceinline__ void tmem_ld<16>(uint32_t taddr, uint32_t (&v)[16]) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-                   "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-                 : "r"(taddr));
-}
-template <>
-__device__ __forceinline__ void tmem_ld<32>(uint32_t taddr, uint32_t (&v)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,"
-        "%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
-          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
-          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
-          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// UMMA shared-memory descriptor of a K-major operand whose rows are ROWB bytes (= the swizzle span) apart.
-// Measured on B200 (tools/test_conv_tc.py, round 1): the hardware applies the swizzle XOR to the ABSOLUTE shared-memory
-// address, exactly as TMA does when it writes the tile, so a start address shifted by any number of voxel rows (not
-// only by whole 8-row swizzle atoms) addresses the shifted operand correctly with the base-offset field left 0.
-// (Setting base_offset = (addr >> 7) & 7 for unaligned starts gives wrong results.)
-template <int ROWB>
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
-    constexpr uint64_t layout = ROWB == 128 ? 2 : (ROWB == 64 ? 4 : 6);          // SWIZZLE_128B / 64B / 32B
-    uint64_t d = (uint64_t)((saddr >> 4) & 0x3fff);
-    d |= (uint64_t)1 << 16;                                                       // LBO: unused for swizzled K-major
-    d |= (uint64_t)((8 * ROWB) >> 4) << 32;                                       // SBO: 8 rows
-    d |= (uint64_t)1 << 46;                                                       // descriptor version (Blackwell)
-    d |= layout << 61;
-    return d;
-}
-
-// one tcgen05.mma, descriptors given as (lo, hi) halves so the issue loop only does 32-bit adds on the start address
-__device__ __forceinline__ void umma_bf16_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
-                                               uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
-        "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
-        "setp.ne.b32 p, %6, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi),
-        "r"(idesc), "r"(accumulate)
-        : "memory");
-}
 
 // Persistent kernel: CTA c works on items c, c + gridDim.x, ...; an item is (batch, depth run, xy tile).  The filter is
 // loaded once per CTA; the slab ring, the TMEM stages and all mbarrier phases run on across items (global counters).
@@ -348,26 +241,6 @@ conv3d_s1_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
     }
 }
 
-// ---- host side ------------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn encode_fn() {
-    static EncodeTiledFn fn = nullptr;
-    if (!fn) {
-        void* ptr = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
-            qres == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(ptr);
-    }
-    return fn;
-}
-
-CUtensorMapSwizzle swizzle_for(int rowb) {
-    return rowb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (rowb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
-}
 
 struct TilePlan {
     int BW, L, MB, tiles_x, tiles_y, slab_bytes;
@@ -504,23 +377,6 @@ struct WgradParams {
     float* gw;                      // [27][CIN][cout] fp32, accumulated into
 };
 
-// MN-major operand descriptor: rows (K) are ROWB bytes apart (= one swizzle atom of channels), MN atoms `atom_stride`
-// bytes apart
-template <int ROWB>
-__device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr, uint32_t atom_stride) {
-    constexpr uint64_t layout = ROWB == 128 ? 2 : (ROWB == 64 ? 4 : (ROWB == 32 ? 6 : 0));
-    uint64_t d = (uint64_t)((saddr >> 4) & 0x3fff);
-    if (ROWB == 16) {
-        d |= (uint64_t)(128 >> 4) << 16;                      // no swizzle: LBO = stride between 8-row K groups
-        d |= (uint64_t)((atom_stride >> 4) & 0x3fff) << 32;   //             SBO = stride between 8-channel MN atoms
-    } else {
-        d |= (uint64_t)((atom_stride >> 4) & 0x3fff) << 16;   // LBO = stride between MN atoms
-        d |= (uint64_t)((8 * ROWB) >> 4) << 32;               // SBO = stride between 8-row K groups
-    }
-    d |= (uint64_t)1 << 46;
-    d |= layout << 61;
-    return d;
-}
 
 template <int CIN, int NCO>
 __global__ void __launch_bounds__(kTcThreads, 1)

@@ -205,25 +205,49 @@ def conv_transpose3d_s2(x, w, pads, out_dims):
     return y
 
 
-def _s2_wgrad_ok(c_big, c_small):
-    """The tcgen05 strided weight gradient is correct but, launched once per parity class and channel chunk with an atomic
-    epilogue, still behind the library at the regulariser's shapes (tools/bench_s2_wgrad.py, B = 4: 3.21 vs 2.27 ms for the
-    stacked branches, 1.61 vs 0.94 and 0.71 vs 0.66 ms for the transposed layers): opt-in with MVSB200_S2_WGRAD=tcgen05."""
+def _s2_wgrad_mode(big_shape, small_shape):
+    """Which kernel computes the weight gradient of a stride-2 layer: "lines" (default; conv3d_s2_wgrad_lines_kernel, one
+    launch, lines of the strided operand as voxel-pair rows), "classes" (the stride-1 weight-gradient kernel on the 8 parity
+    sub-lattices, one launch per class and channel chunk -- slower than the library at the regulariser's shapes, kept for A/B
+    and for the shapes the line kernel does not take) or "cudnn" (the library).  MVSB200_S2_WGRAD=lines|tcgen05|cudnn selects;
+    "tcgen05" is the historical name of the parity-class form."""
     import os
-    return (c_big in _CIN_OK and c_small % 8 == 0 and os.environ.get("MVSB200_S2_WGRAD", "cudnn") == "tcgen05"
-            and hasattr(_lib.load(), "mvsb200_conv3d_s2_wgrad"))
+    want = os.environ.get("MVSB200_S2_WGRAD", "lines")
+    cb, cs = big_shape[1], small_shape[1]
+    lib = _lib.load()
+    lines_ok = (cb in (8, 16, 32) and (cs in (16, 32, 64) or (64 < cs <= 128 and cs % 16 == 0)) and big_shape[4] % 2 == 0
+                and small_shape[4] <= 255 and hasattr(lib, "mvsb200_conv3d_s2_wgrad_lines"))
+    classes_ok = cb in _CIN_OK and cs % 8 == 0 and hasattr(lib, "mvsb200_conv3d_s2_wgrad")
+    if want == "lines" and lines_ok:
+        return "lines"
+    if want in ("lines", "tcgen05", "classes") and classes_ok:
+        return "classes"
+    return "cudnn"
 
 
-def s2_wgrad(big, small, pads):
-    """gw[k][cb][cs] = sum_o big(2o - pad + k)[cb] * small(o)[cs] on the tcgen05 weight-gradient kernel (parity sub-lattices of
-    `big` through doubled-stride TMA maps) -> fp32 [27, Cb, Cs].  big, small: bf16 channels_last_3d [B,C,D,h,w]."""
+def s2_wgrad(big, small, pads, mode="classes"):
+    """gw[k][cb][cs] = sum_o big(2o - pad + k)[cb] * small(o)[cs] on the tcgen05 weight-gradient kernels -> fp32 [27, Cb, Cs].
+    big: bf16 channels_last_3d [B,C,D,h,w].  small: bf16, channel-last voxel rows; mode "lines" (one launch,
+    csrc/conv3d_s2_bwd.cu) also takes a box VIEW of a larger channel-last allocation (its strides go into the TMA map), mode
+    "classes" (parity sub-lattices of `big` through doubled-stride TMA maps, csrc/conv3d_tc.cu) needs it dense."""
+    import ctypes
     B, cb, Db, Hb, Wb = big.shape
     _, cs, Ds, Hs, Ws = small.shape
     gw = torch.empty((27, cb, cs), dtype=torch.float32, device=big.device)
     # algorithmic work: every tap once over the small volume
     with _timed("conv3d_s2_wgrad_tc", 2.0 * 27 * cb * cs * B * Ds * Hs * Ws):
-        _lib.call("mvsb200_conv3d_s2_wgrad", big.data_ptr(), small.data_ptr(), gw.data_ptr(), B, Db, Hb, Wb, cb, Ds, Hs, Ws, cs,
-                  int(pads[0]), int(pads[1]), int(pads[2]), _stream())
+        if mode == "lines":
+            ss = None
+            if small.stride(1) != 1 or any(st % 8 for st in (small.stride(0), small.stride(2), small.stride(3), small.stride(4))):
+                small = small.contiguous(memory_format=torch.channels_last_3d)
+            if not small.is_contiguous(memory_format=torch.channels_last_3d):
+                ss = (ctypes.c_int64 * 4)(small.stride(0), small.stride(2), small.stride(3), small.stride(4))
+            _lib.call("mvsb200_conv3d_s2_wgrad_lines", big.data_ptr(), small.data_ptr(), gw.data_ptr(), B, Db, Hb, Wb, cb, Ds, Hs, Ws,
+                      cs, int(pads[0]), int(pads[1]), int(pads[2]), ss, _stream())
+        else:
+            small = small.contiguous(memory_format=torch.channels_last_3d)
+            _lib.call("mvsb200_conv3d_s2_wgrad", big.data_ptr(), small.data_ptr(), gw.data_ptr(), B, Db, Hb, Wb, cb, Ds, Hs, Ws, cs,
+                      int(pads[0]), int(pads[1]), int(pads[2]), _stream())
     return gw
 
 
@@ -268,9 +292,10 @@ class _ConvTranspose3dS2(torch.autograd.Function):
                 gx = F.conv3d(gy, wb, None, 2, P2)[inner]             # weight [Cin, Cout, ...] read as out = Cin, in = Cout
         if ctx.needs_input_grad[1]:
             cin_t, cout_t = w.shape[:2]
-            if _s2_wgrad_ok(cout_t, cin_t):
+            mode = _s2_wgrad_mode(gy.shape, x_cl.shape)
+            if mode != "cudnn":
                 # gW[ci][co][k] = sum_j x[j][ci] gy[2j - p + k][co]: the strided operand is the output gradient
-                g27 = s2_wgrad(gy, x_cl, pads)                                           # [27, Cout, Cin]
+                g27 = s2_wgrad(gy, x_cl, pads, mode)                                     # [27, Cout, Cin]
                 gw = g27.reshape(3, 3, 3, cout_t, cin_t).permute(4, 3, 0, 1, 2).to(w.dtype)
             else:
                 xs = torch.zeros((x_cl.shape[0], x_cl.shape[1]) + tuple(n_o), dtype=x_cl.dtype, device=x_cl.device,
@@ -330,7 +355,8 @@ class _Conv3dS2Box(torch.autograd.Function):
         nat = tuple((n + 2 * a - 3) // 2 + 1 for n, a in zip(x_cl.shape[2:], P))
         B, cout = x_cl.shape[0], w.shape[0]
         box = tuple(slice(o, o + n) for o, n in zip(off, ctx.out_dims))
-        own_wgrad = bool(ctx.needs_input_grad[1]) and _s2_wgrad_ok(x_cl.shape[1], cout)
+        wg_mode = _s2_wgrad_mode(x_cl.shape, (B, cout) + tuple(ctx.out_dims))
+        own_wgrad = bool(ctx.needs_input_grad[1]) and wg_mode != "cudnn"
         mask = [bool(ctx.needs_input_grad[0]), bool(ctx.needs_input_grad[1]) and not own_wgrad, False]
         gx = gw = None
         gy_box = None
@@ -360,7 +386,7 @@ class _Conv3dS2Box(torch.autograd.Function):
                 gy_box = torch.cat([g if g is not None else torch.zeros((B, n) + ctx.out_dims, dtype=torch.bfloat16, device=x_cl.device)
                                     for g, n in zip(gys, ctx.splits if ctx.splits is not None else (cout,))], 1)
             # gW[co][ci][k] = sum_o x[2o - pad + k][ci] gy[o][co]: the strided operand is the layer's input
-            g27 = s2_wgrad(x_cl, gy_box.to(torch.bfloat16).contiguous(memory_format=torch.channels_last_3d), ctx.pads)   # [27, Cin, Cout]
+            g27 = s2_wgrad(x_cl, gy_box.to(torch.bfloat16), ctx.pads, wg_mode)   # [27, Cin, Cout]; gy_box may be a view of g_full
             gw = g27.reshape(3, 3, 3, x_cl.shape[1], cout).permute(4, 3, 0, 1, 2)
         return gx, (gw.to(w.dtype) if gw is not None else None), None, None, None, None
 

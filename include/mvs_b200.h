@@ -154,6 +154,18 @@ int mvsb200_conv3d_s1_fwd_ex(const void* x, const void* w_packed, void* y, int B
 int mvsb200_conv3d_s2_wgrad(const void* big, const void* small, float* gw, int B, int Db, int Hb, int Wb, int Cb,
                             int Ds, int Hs, int Ws, int Cs, int pad_d, int pad_h, int pad_w, void* stream);
 
+/* The same weight gradient in ONE launch (csrc/conv3d_s2_bwd.cu): lines of `big` are presented by TMA as rows of voxel PAIRS, so
+ * a tcgen05.mma chain over a line accumulates the three kw taps of one (kd, kh) without any de-interleaved copy of `big`; a CTA
+ * owns one depth tap and keeps its accumulators in TMEM over its whole run.  Replaces torch.nn.grad.conv3d_weight /
+ * aten::convolution_backward for conv_{1,2,3}_0 (scripts/model.py:104-110; small = the 112 stacked output-gradient channels) and
+ * deconv_{3,2,1}_0 (:115-121).  big: bf16 [B,Db,Hb,Wb,Cb], Cb in {8,16,32}, Wb even; small: bf16 [B,Ds,Hs,Ws,Cs], Cs in
+ * {16,32,64} or a multiple of 16 in (64,128], Ws <= 255; small_strides4_host: NULL (dense) or the (batch, plane, line, voxel)
+ * strides of small in elements (HOST int64; a box inside a larger channel-last allocation); gw: fp32 [27,Cb,Cs], zeroed by the
+ * call; pad in {1,2}. */
+int mvsb200_conv3d_s2_wgrad_lines(const void* big, const void* small, float* gw, int B, int Db, int Hb, int Wb, int Cb,
+                                  int Ds, int Hs, int Ws, int Cs, int pad_d, int pad_h, int pad_w,
+                                  const int64_t* small_strides4_host, void* stream);
+
 /* Stride-2 TRANSPOSED convolution forward in ONE launch (ConvTranspose3d k=3, scripts/model.py:229-234, used at :115-121):
  *   out[2J + par] = sum over the taps k with (par + pad - k) even of W[k] . in[J + (par + pad - k)/2] per axis.
  * All 8 output-parity classes are accumulated side by side in TMEM and written interleaved, so every line of the canvas is

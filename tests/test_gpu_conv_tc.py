@@ -127,7 +127,7 @@ def test_transposed_conv_by_parity_classes(cin, cout, dims, form, monkeypatch):
     conv_transpose3d (fp32) on the same bf16 operands, forward and both gradients; the two forms agree to one bf16 rounding."""
     from mvs_b200.regulariser import central_region
     monkeypatch.setenv("MVSB200_DECONV", form)
-    monkeypatch.setenv("MVSB200_S2_WGRAD", "tcgen05" if form == "fused" else "cudnn")     # both weight-gradient paths
+    monkeypatch.setenv("MVSB200_S2_WGRAD", "lines" if form == "fused" else "cudnn")       # own and library weight gradient
     reg = [central_region(n) for n in dims]
     m = [hi - lo + 1 for lo, hi, _ in reg]
     pads = tuple(L for _, _, L in reg)                     # left padding of the equivalent small transposed conv
@@ -154,7 +154,7 @@ def test_transposed_conv_by_parity_classes(cin, cout, dims, form, monkeypatch):
     assert _rel(w1.grad, w2.grad) < 2 * TOL
 
 
-@pytest.mark.parametrize("wgrad", ["tcgen05", "cudnn"])
+@pytest.mark.parametrize("wgrad", ["lines", "tcgen05", "cudnn"])
 @pytest.mark.parametrize("cin,cout", [(32, 112), (32, 16), (16, 32), (64, 32)])
 @pytest.mark.parametrize("dims", [(12, 10, 14), (11, 9, 15), (8, 7, 12), (6, 33, 47)])
 def test_stride2_conv_on_the_central_box(cin, cout, dims, wgrad, monkeypatch):

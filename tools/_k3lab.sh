@@ -1,6 +1,6 @@
 timeout 900 python -m pytest tests -m gpu -q -x > gpurun_out/pytest_k3.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_k3.log
 tail -5 gpurun_out/pytest_k3.log
-python tools/bench_streaming.py > gpurun_out/streaming.jsonl 2>&1; cut -c1-140 gpurun_out/streaming.jsonl
+
 timeout 500 python bench.py --no-cpu-baseline --no-extras > gpurun_out/bench_k3.json 2> gpurun_out/bench_k3.err; echo "rc=$?"; tail -3 gpurun_out/bench_k3.err
 python - <<'PY'
 import json

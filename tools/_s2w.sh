@@ -1,9 +1,3 @@
-MVSB200_S2_WGRAD=tcgen05 timeout 500 python bench.py --no-cpu-baseline --no-extras > gpurun_out/bench_s2w.json 2> gpurun_out/bench_s2w.err; echo "rc=$?"
-python - <<'PY'
-import json
-d=json.load(open('gpurun_out/bench_s2w.json'))
-print('value',d['value'],'ms',d['ms_per_step'])
-k=d['kernels']
-for n,v in sorted(k.items(), key=lambda kv:-kv[1]['ms_per_step'])[:8]: print(n, round(v['ms_per_step'],3), v['launches']//d['steps'])
-print(sum(v['ms_per_step'] for v in k.values()))
-PY
+timeout 600 python -m pytest tests/test_gpu_conv_tc.py -q -x -k "stride2_conv or transposed_conv" > gpurun_out/pytest_s2w.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_s2w.log
+tail -4 gpurun_out/pytest_s2w.log
+for d in 4 5 6; do echo "dbg=$d"; MVSB200_S2WG_DBG=$d timeout 300 python tools/bench_s2_wgrad.py 2>&1 | sort -u | cut -c1-150; done
