@@ -915,8 +915,11 @@ TilePlan plan_tiles_s2(int Ho, int Wo, int rowb, size_t w_bytes_al, size_t smem_
 
 template <int CIN, int NOUT>
 int launch_conv_s2(const void* x, const void* w, void* y, int B, int Dx, int Hx, int Wx, int Do, int Ho, int Wo, int cout, int y_cs,
-                   int y_coff, int n_rows, int w_row0, int pad_d, int pad_h, int pad_w, cudaStream_t st) {
+                   int y_coff, int n_rows, int w_row0, int pad_d, int pad_h, int pad_w, cudaStream_t st, int cin_real = CIN) {
+    // cin_real < CIN: voxel rows of x hold cin_real channels; the TMA box is CIN wide and the channels beyond the tensor's
+    // extent arrive as zeros (out-of-bounds fill), so an 8-channel volume feeds the K = 16 MMA without a widened copy
     constexpr int ROWB = CIN * 2;
+    const int rowx = cin_real * 2;
     constexpr size_t W_BYTES_AL = ((size_t)27 * NOUT * ROWB + 1023) / 1024 * 1024;
     EncodeTiledFn enc = encode_fn();
     MVS_REQUIRE(enc != nullptr, "conv3d_s2: cuTensorMapEncodeTiled is not available from the driver");
@@ -928,14 +931,14 @@ int launch_conv_s2(const void* x, const void* w, void* y, int B, int Dx, int Hx,
     for (int c = 0; c < 4; ++c) {
         const int qy = c >> 1, qx = c & 1;
         const int Ws = (Wx - qx + 1) / 2, Hs = (Hx - qy + 1) / 2;      // sub-lattice extents
-        const char* base = reinterpret_cast<const char*>(x) + ((size_t)qy * Wx + qx) * ROWB;
+        const char* base = reinterpret_cast<const char*>(x) + ((size_t)qy * Wx + qx) * rowx;
         if (Ws < 1 || Hs < 1) {                                        // degenerate (1-voxel axis): alias class 0, taps read zeros? never used
             tm_x[c] = tm_x[0];
             continue;
         }
-        const cuuint64_t dims[5] = {(cuuint64_t)CIN, (cuuint64_t)Ws, (cuuint64_t)Hs, (cuuint64_t)Dx, (cuuint64_t)B};
-        const cuuint64_t strides[4] = {(cuuint64_t)2 * ROWB, (cuuint64_t)2 * ROWB * Wx, (cuuint64_t)ROWB * Wx * Hx,
-                                       (cuuint64_t)ROWB * Wx * Hx * Dx};
+        const cuuint64_t dims[5] = {(cuuint64_t)cin_real, (cuuint64_t)Ws, (cuuint64_t)Hs, (cuuint64_t)Dx, (cuuint64_t)B};
+        const cuuint64_t strides[4] = {(cuuint64_t)2 * rowx, (cuuint64_t)2 * rowx * Wx, (cuuint64_t)rowx * Wx * Hx,
+                                       (cuuint64_t)rowx * Wx * Hx * Dx};
         const cuuint32_t box[5] = {(cuuint32_t)CIN, (cuuint32_t)tp.BW, (cuuint32_t)(tp.L + 1), 1, 1};
         const cuuint32_t es[5] = {1, 1, 1, 1, 1};
         CUresult r = enc(&tm_x[c], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<char*>(base), dims, strides, box, es,
@@ -1326,16 +1329,7 @@ struct DeconvParams {
     int dchunk, nchunks, n_items;
     int cout, n_rows;
     int slab_bytes;
-    int n_taps;                     // 27
-    // The 27 (class, filter tap) pairs grouped by the INPUT SHIFT (td, th, tw) they read: classes that share a shift share
-    // the A operand, so one MMA of N = ncls * NOUT serves them all when their accumulator blocks are adjacent in TMEM.
-    // Shared-memory filter slot e holds filter tap tap_k[e]; a group's slots and its classes are consecutive.
-    int tap_k[27];                  // filter tap (kd*3+kh)*3+kw held by shared-memory slot e
-    int n_groups;
-    int grp_td[27], grp_th[27], grp_tw[27];   // input shift of the group (slab tap per axis)
-    int grp_class0[27], grp_ncls[27];         // first class block and number of adjacent class blocks the MMA covers
-    int grp_slot0[27];                        // first filter slot of the group
-    int grp_first[27];                        // 1: the group's MMA initialises its accumulators (first touch of those classes)
+    DeconvGroups g;                 // the 27 (class, filter tap) pairs grouped by the input shift they read (tc_common.cuh)
     long long y_sb, y_sd, y_sh, y_sw;   // canvas voxel-row strides in elements
     __nv_bfloat16* y;
 };
@@ -1402,7 +1396,7 @@ deconv3d_s2_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
         // ===================================== TMA producer =====================================
         if (elect_one()) {
             mbar_expect_tx(wfull, 27u * W_TAP_BYTES);
-            for (int e = 0; e < 27; ++e) tma_load_2d(w_smem + e * W_TAP_BYTES, &tm_w, wfull, 0, p.tap_k[e] * p.n_rows);
+            for (int e = 0; e < 27; ++e) tma_load_2d(w_smem + e * W_TAP_BYTES, &tm_w, wfull, 0, p.g.tap_k[e] * p.n_rows);
         }
         __syncwarp();
         const uint32_t box_bytes = (uint32_t)ROWB * p.BW * (p.L + 2);
@@ -1444,14 +1438,14 @@ deconv3d_s2_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
 #pragma unroll
                     for (int mb = 0; mb < MB; ++mb) {
                         const uint32_t mb16 = (uint32_t)(mb * 128 * ROWB) >> 4;
-                        for (int g = 0; g < p.n_groups; ++g) {
-                            const int td = p.grp_td[g];
+                        for (int g = 0; g < p.g.n_groups; ++g) {
+                            const int td = p.g.grp_td[g];
                             const uint32_t a_lo = (td == 0 ? slot_lo[0] : (td == 1 ? slot_lo[1] : slot_lo[2])) + mb16 +
-                                                  (uint32_t)p.grp_th[g] * bw16 + (uint32_t)((p.grp_tw[g] * ROWB) >> 4);
-                            const uint32_t b_lo = w_lo + (uint32_t)((p.grp_slot0[g] * W_TAP_BYTES) >> 4);
-                            const uint32_t d_tmem = tmem_base + (uint32_t)(((stage * MB + mb) * 8 + p.grp_class0[g]) * NOUT);
-                            const uint32_t idesc = IDESC0 | ((uint32_t)((p.grp_ncls[g] * NOUT) >> 3) << 17);
-                            uint32_t acc = p.grp_first[g] ? 0u : 1u;
+                                                  (uint32_t)p.g.grp_th[g] * bw16 + (uint32_t)((p.g.grp_tw[g] * ROWB) >> 4);
+                            const uint32_t b_lo = w_lo + (uint32_t)((p.g.grp_slot0[g] * W_TAP_BYTES) >> 4);
+                            const uint32_t d_tmem = tmem_base + (uint32_t)(((stage * MB + mb) * 8 + p.g.grp_class0[g]) * NOUT);
+                            const uint32_t idesc = IDESC0 | ((uint32_t)((p.g.grp_ncls[g] * NOUT) >> 3) << 17);
+                            uint32_t acc = p.g.grp_first[g] ? 0u : 1u;
 #pragma unroll
                             for (int k = 0; k < KSTEPS; ++k) {
                                 umma_bf16_lohi(d_tmem, a_lo + (uint32_t)((k * 32) >> 4), desc_hi, b_lo + (uint32_t)((k * 32) >> 4), desc_hi,
@@ -1588,67 +1582,7 @@ int launch_deconv_s2(const void* x, const void* w, void* y, int B, int Di, int H
     p.B = B; p.Do = Do; p.Ho = Ho; p.Wo = Wo; p.Jd = Jd; p.Jh = Jh; p.Jw = Jw;
     p.BW = tp.BW; p.L = tp.L; p.MB = MB; p.tiles_x = tp.tiles_x; p.tiles_y = tp.tiles_y;
     p.cout = cout; p.n_rows = n_rows; p.slab_bytes = tp.slab_bytes;
-    // (class, filter tap) pairs: slab tap t = (par + pad - k)/2 + 1 per axis (input index J + t - 1).  Grouped by the input
-    // shift t they read; inside a shift the user classes are split into runs of ADJACENT class indices (their accumulator
-    // blocks are adjacent TMEM columns), one MMA of N = run length * NOUT per run.
-    const int pads[3] = {pad_d, pad_h, pad_w};
-    int pair_k[8][27];                                   // pair_k[class][shift] = filter tap or -1
-    for (int c = 0; c < 8; ++c)
-        for (int t = 0; t < 27; ++t) pair_k[c][t] = -1;
-    int n_pairs = 0;
-    for (int c = 0; c < 8; ++c) {
-        const int par[3] = {c >> 2 & 1, c >> 1 & 1, c & 1};
-        for (int kd = 0; kd < 3; ++kd)
-            for (int kh = 0; kh < 3; ++kh)
-                for (int kw = 0; kw < 3; ++kw) {
-                    const int k[3] = {kd, kh, kw};
-                    int t[3];
-                    bool ok = true;
-                    for (int ax = 0; ax < 3; ++ax) {
-                        const int v = par[ax] + pads[ax] - k[ax];
-                        if (v & 1) { ok = false; break; }
-                        t[ax] = v / 2 + 1;
-                        if (t[ax] < 0 || t[ax] > 2) { ok = false; break; }
-                    }
-                    if (!ok) continue;
-                    pair_k[c][(t[0] * 3 + t[1]) * 3 + t[2]] = (kd * 3 + kh) * 3 + kw;
-                    ++n_pairs;
-                }
-    }
-    MVS_REQUIRE(n_pairs == 27, "deconv3d_s2: padding (%d,%d,%d) does not map all 27 taps into the 3-tap window", pad_d, pad_h, pad_w);
-    p.n_taps = 27;
-    // shifts in decreasing number of user classes: the first group to touch a class initialises its accumulator block, and
-    // a group must initialise all of its classes or none -- true when the widest shift (used by every class it can reach)
-    // comes first; verified below
-    int order[27], users[27];
-    for (int t = 0; t < 27; ++t) {
-        order[t] = t;
-        users[t] = 0;
-        for (int c = 0; c < 8; ++c) users[t] += pair_k[c][t] >= 0;
-    }
-    for (int i = 0; i < 27; ++i)
-        for (int j = i + 1; j < 27; ++j)
-            if (users[order[j]] > users[order[i]]) { const int tmp = order[i]; order[i] = order[j]; order[j] = tmp; }
-    bool touched[8] = {false, false, false, false, false, false, false, false};
-    int ng = 0, slot = 0;
-    for (int oi = 0; oi < 27; ++oi) {
-        const int t = order[oi];
-        if (users[t] == 0) continue;
-        for (int c = 0; c < 8;) {
-            if (pair_k[c][t] < 0) { ++c; continue; }
-            int c1 = c;
-            while (c1 < 8 && pair_k[c1][t] >= 0 && touched[c1] == touched[c] && (c1 - c + 1) * NOUT <= 256) ++c1;
-            MVS_REQUIRE(ng < 27 && slot + (c1 - c) <= 27, "deconv3d_s2: group table overflow");
-            p.grp_td[ng] = t / 9; p.grp_th[ng] = t / 3 % 3; p.grp_tw[ng] = t % 3;
-            p.grp_class0[ng] = c; p.grp_ncls[ng] = c1 - c; p.grp_slot0[ng] = slot; p.grp_first[ng] = touched[c] ? 0 : 1;
-            for (int cc = c; cc < c1; ++cc) { p.tap_k[slot++] = pair_k[cc][t]; touched[cc] = true; }
-            ++ng;
-            c = c1;
-        }
-    }
-    MVS_REQUIRE(slot == 27, "deconv3d_s2: %d filter slots filled", slot);
-    p.n_groups = ng;
-    for (int g = ng; g < 27; ++g) { p.grp_td[g] = p.grp_th[g] = p.grp_tw[g] = p.grp_class0[g] = p.grp_ncls[g] = p.grp_slot0[g] = p.grp_first[g] = 0; }
+    { const int rc = build_deconv_groups(pad_d, pad_h, pad_w, NOUT, p.g); if (rc != MVSB200_OK) return rc; }
     p.y_sb = y_strides4[0]; p.y_sd = y_strides4[1]; p.y_sh = y_strides4[2]; p.y_sw = y_strides4[3];
     p.y = reinterpret_cast<__nv_bfloat16*>(y);
 
@@ -1786,7 +1720,9 @@ extern "C" int mvsb200_conv3d_s2_fwd(const void* x, const void* w_packed, void* 
         const int c_here = cout - row0 < nout ? cout - row0 : nout;
         int rc = MVSB200_E_UNSUPPORTED;
 #define MVS_S2(CI, NO) rc = launch_conv_s2<CI, NO>(x, w_packed, y, B, Dx, Hx, Wx, Do, Ho, Wo, c_here, y_cs, row0, n_rows, row0, pad_d, pad_h, pad_w, st)
-        if (Cin == 16 && nout == 16) MVS_S2(16, 16);
+        if (Cin == 8 && nout == 16) rc = launch_conv_s2<16, 16>(x, w_packed, y, B, Dx, Hx, Wx, Do, Ho, Wo, c_here, y_cs, row0, n_rows, row0, pad_d, pad_h, pad_w, st, 8);
+        else if (Cin == 8 && nout == 32) rc = launch_conv_s2<16, 32>(x, w_packed, y, B, Dx, Hx, Wx, Do, Ho, Wo, c_here, y_cs, row0, n_rows, row0, pad_d, pad_h, pad_w, st, 8);
+        else if (Cin == 16 && nout == 16) MVS_S2(16, 16);
         else if (Cin == 16 && nout == 32) MVS_S2(16, 32);
         else if (Cin == 16 && nout == 48) MVS_S2(16, 48);
         else if (Cin == 16 && nout == 64) MVS_S2(16, 64);

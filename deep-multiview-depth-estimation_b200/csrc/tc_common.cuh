@@ -152,4 +152,171 @@ CUtensorMapSwizzle swizzle_for(int rowb) {
     return rowb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (rowb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
 }
 
+// ---- stride-2 transposed convolution: the 27 (output-parity class, filter tap) pairs ---------------------------------
+//   out[2J + par] = sum over the filter taps k with (par + pad - k) even of W[k] . in[J + (par + pad - k)/2]   (per axis)
+// Slab tap t = (par + pad - k)/2 + 1 per axis (input index J + t - 1).  The pairs are grouped by the INPUT SHIFT (td,th,tw)
+// they read: classes that share a shift share the A operand, so one MMA of N = ncls * NOUT serves them all when their
+// accumulator blocks are adjacent in TMEM.  Shared-memory filter slot e holds filter tap tap_k[e]; a group's slots and its
+// classes are consecutive.
+struct DeconvGroups {
+    int tap_k[27];                  // filter tap (kd*3+kh)*3+kw held by shared-memory slot e
+    int n_groups;
+    int grp_td[27], grp_th[27], grp_tw[27];   // input shift of the group (slab tap per axis)
+    int grp_class0[27], grp_ncls[27];         // first class block and number of adjacent class blocks the MMA covers
+    int grp_slot0[27];                        // first filter slot of the group
+    int grp_first[27];                        // 1: the group's MMA initialises its accumulators (first touch of those classes)
+};
+
+inline int build_deconv_groups(int pad_d, int pad_h, int pad_w, int NOUT, DeconvGroups& p) {
+    const int pads[3] = {pad_d, pad_h, pad_w};
+    int pair_k[8][27];                                   // pair_k[class][shift] = filter tap or -1
+    for (int c = 0; c < 8; ++c)
+        for (int t = 0; t < 27; ++t) pair_k[c][t] = -1;
+    int n_pairs = 0;
+    for (int c = 0; c < 8; ++c) {
+        const int par[3] = {c >> 2 & 1, c >> 1 & 1, c & 1};
+        for (int kd = 0; kd < 3; ++kd)
+            for (int kh = 0; kh < 3; ++kh)
+                for (int kw = 0; kw < 3; ++kw) {
+                    const int k[3] = {kd, kh, kw};
+                    int t[3];
+                    bool ok = true;
+                    for (int ax = 0; ax < 3; ++ax) {
+                        const int v = par[ax] + pads[ax] - k[ax];
+                        if (v & 1) { ok = false; break; }
+                        t[ax] = v / 2 + 1;
+                        if (t[ax] < 0 || t[ax] > 2) { ok = false; break; }
+                    }
+                    if (!ok) continue;
+                    pair_k[c][(t[0] * 3 + t[1]) * 3 + t[2]] = (kd * 3 + kh) * 3 + kw;
+                    ++n_pairs;
+                }
+    }
+    MVS_REQUIRE(n_pairs == 27, "deconv3d_s2: padding (%d,%d,%d) does not map all 27 taps into the 3-tap window", pad_d, pad_h, pad_w);
+    // shifts in decreasing number of user classes: the first group to touch a class initialises its accumulator block, and
+    // a group must initialise all of its classes or none -- true when the widest shift (used by every class it can reach)
+    // comes first
+    int order[27], users[27];
+    for (int t = 0; t < 27; ++t) {
+        order[t] = t;
+        users[t] = 0;
+        for (int c = 0; c < 8; ++c) users[t] += pair_k[c][t] >= 0;
+    }
+    for (int i = 0; i < 27; ++i)
+        for (int j = i + 1; j < 27; ++j)
+            if (users[order[j]] > users[order[i]]) { const int tmp = order[i]; order[i] = order[j]; order[j] = tmp; }
+    bool touched[8] = {false, false, false, false, false, false, false, false};
+    int ng = 0, slot = 0;
+    for (int oi = 0; oi < 27; ++oi) {
+        const int t = order[oi];
+        if (users[t] == 0) continue;
+        for (int c = 0; c < 8;) {
+            if (pair_k[c][t] < 0) { ++c; continue; }
+            int c1 = c;
+            while (c1 < 8 && pair_k[c1][t] >= 0 && touched[c1] == touched[c] && (c1 - c + 1) * NOUT <= 256) ++c1;
+            MVS_REQUIRE(ng < 27 && slot + (c1 - c) <= 27, "deconv3d_s2: group table overflow");
+            p.grp_td[ng] = t / 9; p.grp_th[ng] = t / 3 % 3; p.grp_tw[ng] = t % 3;
+            p.grp_class0[ng] = c; p.grp_ncls[ng] = c1 - c; p.grp_slot0[ng] = slot; p.grp_first[ng] = touched[c] ? 0 : 1;
+            for (int cc = c; cc < c1; ++cc) { p.tap_k[slot++] = pair_k[cc][t]; touched[cc] = true; }
+            ++ng;
+            c = c1;
+        }
+    }
+    MVS_REQUIRE(slot == 27, "deconv3d_s2: %d filter slots filled", slot);
+    p.n_groups = ng;
+    for (int g = ng; g < 27; ++g) { p.grp_td[g] = p.grp_th[g] = p.grp_tw[g] = p.grp_class0[g] = p.grp_ncls[g] = p.grp_slot0[g] = p.grp_first[g] = 0; }
+    return MVSB200_OK;
+}
+
+// The same (class, tap) pairs arranged for ONE MMA PER INPUT SHIFT.  Per axis one output parity reads both input shifts (bit
+// u = 1) and the other only the main one; the 8 classes are placed in Gray-code order of (u_d, u_h, u_w), so the classes that
+// read a given shift occupy a short RANGE of accumulator blocks -- the MMA of the shift covers the whole range, blocks of
+// classes that do not read the shift get an all-zero filter slot (tap index 27 of the packed weights).  8 MMAs per K step
+// instead of 14: on the shared-memory operand-feed roof an MMA costs its 4 KB A read whatever its N, so fewer, wider MMAs win.
+struct DeconvWide {
+    int tap_k[40];                  // filter tap held by shared-memory slot e; 27 = the all-zero tap
+    int n_slots;
+    int n_groups;                   // <= 8
+    int grp_td[8], grp_th[8], grp_tw[8];      // input shift (slab tap per axis, 1 or 2)
+    int grp_pos0[8], grp_npos[8];             // first accumulator block and number of adjacent blocks the MMA covers
+    int grp_slot0[8];
+    int grp_first[8];                         // 1: initialises its accumulators (covers all 8 blocks)
+    int cls_of_pos[8];              // output-parity class (pd*4 + ph*2 + pw) of accumulator block pos
+};
+
+inline int build_deconv_wide(int pad_d, int pad_h, int pad_w, int NOUT, DeconvWide& p) {
+    const int pads[3] = {pad_d, pad_h, pad_w};
+    // per axis: taps of a parity -> (k, t); the parity with two taps has u = 1
+    int two[3];                                          // parity that reads both shifts
+    for (int ax = 0; ax < 3; ++ax) {
+        int cnt[2] = {0, 0};
+        for (int par = 0; par < 2; ++par)
+            for (int k = 0; k < 3; ++k) {
+                const int v = par + pads[ax] - k;
+                if (v & 1) continue;
+                const int t = v / 2 + 1;
+                MVS_REQUIRE(t >= 1 && t <= 2, "deconv3d_s2: padding %d gives an input shift outside {0, +1}", pads[ax]);
+                ++cnt[par];
+            }
+        MVS_REQUIRE(cnt[0] + cnt[1] == 3 && (cnt[0] == 2 || cnt[1] == 2), "deconv3d_s2: padding %d does not split the 3 taps 2 + 1", pads[ax]);
+        two[ax] = cnt[1] == 2 ? 1 : 0;
+    }
+    static const int gray[8] = {0, 1, 3, 2, 6, 7, 5, 4};     // position -> (u_d u_h u_w) as a 3-bit number
+    int pos_of_cls[8];
+    for (int pos = 0; pos < 8; ++pos) {
+        const int u[3] = {gray[pos] >> 2 & 1, gray[pos] >> 1 & 1, gray[pos] & 1};
+        int par[3];
+        for (int ax = 0; ax < 3; ++ax) par[ax] = u[ax] ? two[ax] : 1 - two[ax];
+        p.cls_of_pos[pos] = par[0] * 4 + par[1] * 2 + par[2];
+        pos_of_cls[p.cls_of_pos[pos]] = pos;
+    }
+    int pair_k[8][27];                                   // pair_k[pos][shift] = filter tap or -1
+    for (int c = 0; c < 8; ++c)
+        for (int t = 0; t < 27; ++t) pair_k[c][t] = -1;
+    for (int c = 0; c < 8; ++c) {
+        const int par[3] = {c >> 2 & 1, c >> 1 & 1, c & 1};
+        for (int kd = 0; kd < 3; ++kd)
+            for (int kh = 0; kh < 3; ++kh)
+                for (int kw = 0; kw < 3; ++kw) {
+                    const int k[3] = {kd, kh, kw};
+                    int t[3];
+                    bool ok = true;
+                    for (int ax = 0; ax < 3; ++ax) {
+                        const int v = par[ax] + pads[ax] - k[ax];
+                        if (v & 1) { ok = false; break; }
+                        t[ax] = v / 2 + 1;
+                    }
+                    if (ok) pair_k[pos_of_cls[c]][(t[0] * 3 + t[1]) * 3 + t[2]] = (kd * 3 + kh) * 3 + kw;
+                }
+    }
+    int order[27], users[27];
+    for (int t = 0; t < 27; ++t) {
+        order[t] = t;
+        users[t] = 0;
+        for (int c = 0; c < 8; ++c) users[t] += pair_k[c][t] >= 0;
+    }
+    for (int i = 0; i < 27; ++i)
+        for (int j = i + 1; j < 27; ++j)
+            if (users[order[j]] > users[order[i]]) { const int tmp = order[i]; order[i] = order[j]; order[j] = tmp; }
+    int ng = 0, slot = 0;
+    for (int oi = 0; oi < 27; ++oi) {
+        const int t = order[oi];
+        if (users[t] == 0) continue;
+        int lo = 8, hi = -1;
+        for (int c = 0; c < 8; ++c)
+            if (pair_k[c][t] >= 0) { lo = c < lo ? c : lo; hi = c > hi ? c : hi; }
+        MVS_REQUIRE(ng < 8 && slot + (hi - lo + 1) <= 40 && (hi - lo + 1) * NOUT <= 256, "deconv3d_s2: wide group table overflow");
+        MVS_REQUIRE(ng > 0 || (lo == 0 && hi == 7), "deconv3d_s2: the first shift does not reach every class");
+        p.grp_td[ng] = t / 9; p.grp_th[ng] = t / 3 % 3; p.grp_tw[ng] = t % 3;
+        p.grp_pos0[ng] = lo; p.grp_npos[ng] = hi - lo + 1; p.grp_slot0[ng] = slot; p.grp_first[ng] = ng == 0 ? 1 : 0;
+        for (int c = lo; c <= hi; ++c) p.tap_k[slot++] = pair_k[c][t] >= 0 ? pair_k[c][t] : 27;
+        ++ng;
+    }
+    p.n_groups = ng;
+    p.n_slots = slot;
+    for (int g = ng; g < 8; ++g) { p.grp_td[g] = p.grp_th[g] = p.grp_tw[g] = 1; p.grp_pos0[g] = p.grp_npos[g] = p.grp_slot0[g] = p.grp_first[g] = 0; }
+    for (int e = slot; e < 40; ++e) p.tap_k[e] = 27;
+    return MVSB200_OK;
+}
+
 }  // namespace

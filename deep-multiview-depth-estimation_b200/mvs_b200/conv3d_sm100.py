@@ -279,11 +279,15 @@ class _ConvTranspose3dS2(torch.autograd.Function):
         wb = w.detach().to(torch.bfloat16)
         if ctx.needs_input_grad[0]:
             cin_t, cout_t = w.shape[:2]
-            if cout_t in _CIN_OK and cin_t % 8 == 0:
-                # x[i] = sum_k W[k]^T gy[2i - p + k]: the tcgen05 stride-2 kernel with the filter read as out = Cin, in = Cout
+            if (cout_t in _CIN_OK or (cout_t == 8 and cin_t <= 32)) and cin_t % 8 == 0:
+                # x[i] = sum_k W[k]^T gy[2i - p + k]: the tcgen05 stride-2 kernel with the filter read as out = Cin, in = Cout.
+                # 8-channel gradient rows (deconv_1_0) reach the K = 16 MMA through TMA's out-of-bounds zero fill: the filter
+                # gets 8 zero input channels, the volume is read as it is
                 B = gy.shape[0]
                 n_rows = (cin_t + 15) // 16 * 16
                 gx = torch.empty(x_cl.shape, dtype=torch.bfloat16, device=gy.device, memory_format=torch.channels_last_3d)
+                if cout_t == 8:
+                    wb = torch.cat([wb, torch.zeros_like(wb)], 1)
                 with _timed("conv3d_s2_tc", 2.0 * 27 * cin_t * cout_t * x_cl.numel() / cin_t):
                     _lib.call("mvsb200_conv3d_s2_fwd", gy.data_ptr(), pack_filter_rows(wb, n_rows).data_ptr(), gx.data_ptr(), B,
                               gy.shape[2], gy.shape[3], gy.shape[4], cout_t, m[0], m[1], m[2], cin_t, cin_t, n_rows,
@@ -313,12 +317,74 @@ def pack_filter_rows(w: torch.Tensor, n_rows: int) -> torch.Tensor:
     return wp
 
 
+def _kc_chunks(widths):
+    """K chunks of the multi-chunk transposed convolution for input channels grouped as `widths`: each group must be a
+    swizzle span (16 / 32 / 64 channels), at most three of them."""
+    if widths is None or len(widths) > 3 or any(n not in (16, 32, 64) for n in widths):
+        return None
+    offs, c0 = [], 0
+    for n in widths:
+        offs.append(c0)
+        c0 += n
+    return offs, list(widths)
+
+
+def _s2_dgrad_own(cin, widths):
+    """The data gradient of a stride-2 convolution runs on deconv3d_s2_kc_kernel when its output channels come as up to three
+    groups of 16 / 32 / 64 (the stacked branches: 16 + 32 + 64) and its input has 16 / 32 / 64 channels;
+    MVSB200_S2_DGRAD=cudnn sends it to the library."""
+    import os
+    return (os.environ.get("MVSB200_S2_DGRAD", "tcgen05") != "cudnn" and _kc_chunks(widths) is not None and cin in (16, 32, 64)
+            and hasattr(_lib.load(), "mvsb200_deconv3d_s2_kc_fwd"))
+
+
+def conv_transpose3d_s2_kc(x, widths, w_t, pads, out_dims, out=None, accumulate=False):
+    """Stride-2 transposed convolution from the channel-stacked box volume x [B, sum(widths), md, mh, mw] (bf16, dense
+    channel-last) to the canvas `out_dims`:  out[2J + par] = sum_k W[k] . x[J + (par + pad - k)/2], W[k] = w_t[:, :, k] with
+    w_t: [Cin_total, Cout, 3, 3, 3] (the ConvTranspose3d layout).  One launch per 16 output channels
+    (deconv3d_s2_kc_kernel).  `out`: canvas to write (dense channel-last, Cout channels); accumulate=True adds to it."""
+    import ctypes
+    offs, ns = _kc_chunks(widths)
+    B, ctot, md, mh, mw = x.shape
+    cout = w_t.shape[1]
+    n_rows = (cout + 15) // 16 * 16
+    D, h, wd = out_dims
+    if out is None:
+        out = torch.empty((B, cout, D, h, wd), dtype=torch.bfloat16, device=x.device, memory_format=torch.channels_last_3d)
+        accumulate = False
+    wk = w_t.detach().permute(2, 3, 4, 1, 0).reshape(27, cout, ctot).to(torch.bfloat16)          # [k][co][ci]
+    parts = []
+    for o, n in zip(offs, ns):
+        wp = torch.zeros(28, n_rows, n, dtype=torch.bfloat16, device=x.device)       # tap 27: zeros (filter slots of classes a
+        wp[:27, :cout] = wk[:, :, o:o + n]                                            # shift does not serve)
+        parts.append(wp.reshape(-1))
+    wpk = torch.cat(parts)
+    ys = (ctypes.c_int64 * 4)(out.stride(0), out.stride(2), out.stride(3), out.stride(4))
+    kc_off = (ctypes.c_int * 3)(*(offs + [0] * (3 - len(offs))))
+    kc_n = (ctypes.c_int * 3)(*(ns + [0] * (3 - len(ns))))
+    with _timed("deconv3d_s2_tc", 2.0 * 27 * ctot * cout * B * md * mh * mw):
+        _lib.call("mvsb200_deconv3d_s2_kc_fwd", x.data_ptr(), ctot, wpk.data_ptr(), kc_off, kc_n, len(ns), out.data_ptr(), B, md, mh, mw,
+                  D, h, wd, cout, n_rows, int(pads[0]), int(pads[1]), int(pads[2]), ys, 1 if accumulate else 0, _stream())
+    return out
+
+
 class _Conv3dS2Box(torch.autograd.Function):
     """out(o) = sum_k W[k] x(2o - pad + k) for o in a box of `out_dims` voxels (zero outside x).  Forward on the tcgen05
     stride-2 kernel.  `splits`: the output channels are returned as that many separate tensors (the stacked branches
-    conv_{1,2,3}_0); their gradients are then written straight into the padded channel-last buffer the library's strided
-    convolution backward wants -- no concatenation, padding and layout copies of the 112-channel box gradient.  The
-    gradients go through the library (a tcgen05 strided weight gradient exists, opt-in: _s2_wgrad_ok)."""
+    conv_{1,2,3}_0); the fused box BatchNorm backward of each branch writes its gradient straight into its channel slice of
+    ONE channel-stacked, channel-last box buffer (ops.BoxGradDest) -- no concatenation or layout copies of the 112-channel
+    gradient -- which both gradient kernels read: the data gradient is a stride-2 transposed convolution over K chunks
+    (deconv3d_s2_kc_kernel), the weight gradient the line kernel (conv3d_s2_wgrad_lines_kernel).  MVSB200_S2_DGRAD=cudnn /
+    MVSB200_S2_WGRAD=cudnn send either to the library, which wants the gradient of its padded output instead."""
+
+    @staticmethod
+    def _geometry(x_shape, pads, out_dims):
+        """The same convolution as the library sees it: symmetric padding P = pad (+2 if pad < 2: keeps parity), natural output
+        extent `nat`, our box at offset (P - pad)/2 inside it."""
+        P = tuple(q if q >= 2 else q + 2 for q in pads)
+        off = tuple((a - b) // 2 for a, b in zip(P, pads))
+        nat = tuple((n + 2 * a - 3) // 2 + 1 for n, a in zip(x_shape[2:], P))
+        return P, nat, tuple(slice(o, o + n) for o, n in zip(off, out_dims))
 
     @staticmethod
     def forward(ctx, x, w, pads, out_dims, splits, holder=None):
@@ -335,12 +401,15 @@ class _Conv3dS2Box(torch.autograd.Function):
         ctx.pads, ctx.out_dims, ctx.splits = tuple(pads), tuple(out_dims), splits
         ctx.holder = holder
         if holder is not None:
-            # geometry of the gradient buffer the library's strided backward wants (see backward): the fused box BatchNorm
-            # backward of each branch writes its slice of it directly (ops.BoxGradDest)
-            P = tuple(q if q >= 2 else q + 2 for q in pads)
-            off = tuple((a - b) // 2 for a, b in zip(P, pads))
-            nat = tuple((n + 2 * a - 3) // 2 + 1 for n, a in zip(x_cl.shape[2:], P))
-            holder.__init__((B, cout) + nat, tuple(slice(o, o + n) for o, n in zip(off, out_dims)), splits, x_cl.device)
+            # where the branches' gradients are collected: the dense box when both gradients run on this library's kernels,
+            # else the padded buffer of the library's strided backward
+            widths = splits if splits is not None else (cout,)
+            own = _s2_dgrad_own(cin, widths) and _s2_wgrad_mode(x_cl.shape, (B, cout) + tuple(out_dims)) == "lines"
+            if own:
+                holder.__init__((B, cout) + tuple(out_dims), tuple(slice(0, n) for n in out_dims), splits, x_cl.device, zero=False)
+            else:
+                _, nat, box = _Conv3dS2Box._geometry(x_cl.shape, pads, out_dims)
+                holder.__init__((B, cout) + nat, box, splits, x_cl.device)
         if splits is None:
             return y
         return tuple(torch.split(y, list(splits), 1))
@@ -348,46 +417,57 @@ class _Conv3dS2Box(torch.autograd.Function):
     @staticmethod
     def backward(ctx, *gys):
         x_cl, w = ctx.saved_tensors
-        # the same convolution as the library sees it: symmetric padding P = pad (+2 if pad < 2 ... keeps parity), output
-        # cropped at offset (P - pad)/2
-        P = tuple(q if q >= 2 else q + 2 for q in ctx.pads)
-        off = tuple((a - b) // 2 for a, b in zip(P, ctx.pads))
-        nat = tuple((n + 2 * a - 3) // 2 + 1 for n, a in zip(x_cl.shape[2:], P))
-        B, cout = x_cl.shape[0], w.shape[0]
-        box = tuple(slice(o, o + n) for o, n in zip(off, ctx.out_dims))
-        wg_mode = _s2_wgrad_mode(x_cl.shape, (B, cout) + tuple(ctx.out_dims))
-        own_wgrad = bool(ctx.needs_input_grad[1]) and wg_mode != "cudnn"
-        mask = [bool(ctx.needs_input_grad[0]), bool(ctx.needs_input_grad[1]) and not own_wgrad, False]
-        gx = gw = None
-        gy_box = None
-        if mask[0] or mask[1]:
-            # gradient of the natural (padded) output, channel-last: the buffer the fused box BatchNorm backward already wrote
-            # its slices into (ops.BoxGradDest), else zeros + one strided copy per branch
-            holder = ctx.holder
-            if holder is not None and holder.buffer is not None and holder.shape == (B, cout) + nat:
-                g_full = holder.buffer
-            else:
-                holder = None
-                g_full = torch.empty((B, cout) + nat, dtype=torch.bfloat16, device=x_cl.device, memory_format=torch.channels_last_3d).zero_()
+        B, cin = x_cl.shape[:2]
+        cout = w.shape[0]
+        out_dims = tuple(ctx.out_dims)
+        widths = tuple(ctx.splits) if ctx.splits is not None else (cout,)
+        P, nat, box = _Conv3dS2Box._geometry(x_cl.shape, ctx.pads, out_dims)
+        need_x, need_w = bool(ctx.needs_input_grad[0]), bool(ctx.needs_input_grad[1])
+        wg_mode = _s2_wgrad_mode(x_cl.shape, (B, cout) + out_dims)
+        own_dgrad = need_x and _s2_dgrad_own(cin, widths)
+        own_wgrad = need_w and wg_mode != "cudnn"
+        lib_mask = [need_x and not own_dgrad, need_w and not own_wgrad, False]
+        holder = ctx.holder if ctx.holder is not None and ctx.holder.buffer is not None else None
+
+        def assemble(shape, where):
+            """The channel-stacked gradient in a buffer of `shape` with the box at `where`: the holder's buffer when it has
+            this geometry (slices the fused BatchNorm backward wrote are already in place), else a fresh one + copies."""
+            h = holder if holder is not None and holder.shape == shape else None
+            full = shape[2:] == out_dims
+            buf = h.buffer if h is not None else torch.empty(shape, dtype=torch.bfloat16, device=x_cl.device,
+                                                             memory_format=torch.channels_last_3d)
+            if h is None and not full:
+                buf.zero_()
             c0 = 0
-            for k, (g, n) in enumerate(zip(gys, ctx.splits if ctx.splits is not None else (cout,))):
-                if holder is not None and holder.holds(k, g):
+            for k, (g, n) in enumerate(zip(gys, widths)):
+                if h is not None and h.holds(k, g):
                     pass                                     # already in place
                 elif g is not None:
-                    g_full[(slice(None), slice(c0, c0 + n)) + box] = g
-                elif holder is not None:
-                    g_full[(slice(None), slice(c0, c0 + n)) + box] = 0     # stale slice of an earlier backward pass
+                    buf[(slice(None), slice(c0, c0 + n)) + where] = g
+                elif h is not None or full:
+                    buf[(slice(None), slice(c0, c0 + n)) + where] = 0     # no gradient for this branch / a stale slice
                 c0 += n
+            return buf
+
+        gx = gw = None
+        gy_box = None
+        if lib_mask[0] or lib_mask[1]:
+            g_full = assemble((B, cout) + nat, box)
             gx, gw, _ = torch.ops.aten.convolution_backward(g_full, x_cl, w.detach().to(torch.bfloat16), None, [2, 2, 2], list(P),
-                                                            [1, 1, 1], False, [0, 0, 0], 1, mask)
+                                                            [1, 1, 1], False, [0, 0, 0], 1, lib_mask)
             gy_box = g_full[(slice(None), slice(None)) + box]
-        if own_wgrad:
+        if own_dgrad or own_wgrad:
             if gy_box is None:
-                gy_box = torch.cat([g if g is not None else torch.zeros((B, n) + ctx.out_dims, dtype=torch.bfloat16, device=x_cl.device)
-                                    for g, n in zip(gys, ctx.splits if ctx.splits is not None else (cout,))], 1)
-            # gW[co][ci][k] = sum_o x[2o - pad + k][ci] gy[o][co]: the strided operand is the layer's input
-            g27 = s2_wgrad(x_cl, gy_box.to(torch.bfloat16), ctx.pads, wg_mode)   # [27, Cin, Cout]; gy_box may be a view of g_full
-            gw = g27.reshape(3, 3, 3, x_cl.shape[1], cout).permute(4, 3, 0, 1, 2)
+                gy_box = assemble((B, cout) + out_dims, tuple(slice(0, n) for n in out_dims))
+            if own_wgrad:
+                # gW[co][ci][k] = sum_o x[2o - pad + k][ci] gy[o][co]: the strided operand is the layer's input
+                g27 = s2_wgrad(x_cl, gy_box, ctx.pads, wg_mode)                        # [27, Cin, Cout]; gy_box may be a view
+                gw = g27.reshape(3, 3, 3, cin, cout).permute(4, 3, 0, 1, 2)
+            if own_dgrad:
+                # gx[2J + par] = sum_k W[k]^T gy[J + (par + pad - k)/2]: the forward weight [Cout, Cin, ...] IS the
+                # ConvTranspose3d layout [in = Cout, out = Cin, ...] of that transposed convolution
+                gx = conv_transpose3d_s2_kc(gy_box.contiguous(memory_format=torch.channels_last_3d), widths, w, ctx.pads,
+                                            tuple(x_cl.shape[2:]))
         return gx, (gw.to(w.dtype) if gw is not None else None), None, None, None, None
 
 

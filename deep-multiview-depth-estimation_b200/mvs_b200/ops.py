@@ -591,14 +591,17 @@ class BoxGradDest:
     straight into the branch's slice of that buffer (allocated, zeroed once, on first use), so the three strided copies and
     the zero-fill of an assembled buffer disappear."""
 
-    def __init__(self, shape, box, splits, device):
+    def __init__(self, shape, box, splits, device, zero=True):
         self.shape, self.box, self.splits, self.device = tuple(shape), tuple(box), tuple(splits), device
         self.buffer = None
+        self.zero = zero                 # False: the box is the whole buffer, every element gets written
         self.filled = [False] * len(splits)
 
     def dest(self, k):
         if self.buffer is None:
-            self.buffer = torch.empty(self.shape, dtype=torch.bfloat16, device=self.device, memory_format=torch.channels_last_3d).zero_()
+            self.buffer = torch.empty(self.shape, dtype=torch.bfloat16, device=self.device, memory_format=torch.channels_last_3d)
+            if self.zero:
+                self.buffer.zero_()
         c0 = sum(self.splits[:k])
         return self.buffer[(slice(None), slice(c0, c0 + self.splits[k])) + self.box]
 

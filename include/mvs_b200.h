@@ -176,6 +176,16 @@ int mvsb200_deconv3d_s2_fwd(const void* x, const void* w_packed, void* y, int B,
                             int Do, int Ho, int Wo, int cout, int n_rows, int pad_d, int pad_h, int pad_w,
                             const int64_t* y_strides4_host, void* stream);
 
+/* Stride-2 TRANSPOSED convolution whose input channels come as up to three K CHUNKS of 16 / 32 / 64 channels inside a voxel
+ * row of x_cs channels (deconv3d_s2_kc_kernel, csrc/conv3d_s2_bwd.cu): the data gradient of the stacked stride-2 branches
+ * conv_{1,2,3}_0 (scripts/model.py:104-110) -- 16 + 32 + 64 gradient channels on the central box -> the 32-channel canvas --
+ * replacing aten::convolution_backward's data gradient.  out[2J + par] = sum_k W[k] . x[J + (par + pad - k)/2] as above.
+ * x: [B, Di, Hi, Wi, x_cs] bf16 dense; w_packed: chunk after chunk, each [28, n_rows, kc_n[c]] bf16 with a 28th all-zero tap (rows = output channels);
+ * kc_off / kc_n: HOST int arrays; y as in mvsb200_deconv3d_s2_fwd, cout <= n_rows <= 64; accumulate = 1 adds to y. */
+int mvsb200_deconv3d_s2_kc_fwd(const void* x, int x_cs, const void* w_packed, const int* kc_off_host, const int* kc_n_host, int n_kc,
+                               void* y, int B, int Di, int Hi, int Wi, int Do, int Ho, int Wo, int cout, int n_rows,
+                               int pad_d, int pad_h, int pad_w, const int64_t* y_strides4_host, int accumulate, void* stream);
+
 /* Stride-2 convolution forward on tcgen05 (parity-deinterleaved sub-lattice slabs through TMA): the three stride-2
  * branches conv_{1,2,3}_0 (scripts/model.py:104-110; padding dim/2+1 of scripts/config.py:20 reduces on the central
  * box to pad 1 or 2) stacked along Cout, and the data gradient of the transposed convolutions.

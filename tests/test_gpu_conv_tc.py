@@ -159,18 +159,26 @@ def test_transposed_conv_by_parity_classes(cin, cout, dims, form, monkeypatch):
 @pytest.mark.parametrize("dims", [(12, 10, 14), (11, 9, 15), (8, 7, 12), (6, 33, 47)])
 def test_stride2_conv_on_the_central_box(cin, cout, dims, wgrad, monkeypatch):
     """The stride-2 branches (model.py:104-110, padding dim/2+1) evaluated on the central box by the tcgen05 stride-2
-    kernel (parity sub-lattice slabs) vs the reference formulation conv3d(stride 2, padding dim/2+1) cropped to the box;
-    weight gradient on the tcgen05 strided kernel (mvsb200_conv3d_s2_wgrad) and through the library."""
+    kernel (parity sub-lattice slabs) vs the reference formulation conv3d(stride 2, padding dim/2+1) cropped to the box.
+    Gradients: "lines" = the shipped own kernels (weight gradient on conv3d_s2_wgrad_lines_kernel, data gradient as a
+    transposed convolution over K chunks on deconv3d_s2_kc_kernel; the 112 stacked channels as the three branches 16+32+64),
+    "tcgen05" = the parity-class weight gradient, "cudnn" = both gradients through the library."""
     from mvs_b200.regulariser import central_region
     monkeypatch.setenv("MVSB200_S2_WGRAD", wgrad)
+    monkeypatch.setenv("MVSB200_S2_DGRAD", "cudnn" if wgrad == "cudnn" else "tcgen05")
     reg = [central_region(n) for n in dims]
     box = tuple(slice(lo, hi + 1) for lo, hi, _ in reg)
     g = torch.Generator().manual_seed(cin + cout + dims[1])
     x = torch.randn(2, cin, *dims, generator=g).to(DEV).to(torch.bfloat16).contiguous(memory_format=torch.channels_last_3d)
     wt = (torch.randn(cout, cin, 3, 3, 3, generator=g) / (27 * cin) ** 0.5).to(DEV).to(torch.bfloat16)
     x1, w1 = x.clone().requires_grad_(True), wt.clone().requires_grad_(True)
-    y = conv_backends.get("tcgen05").conv3d_s2_box(x1, w1, tuple(L for _, _, L in reg), tuple(hi - lo + 1 for lo, hi, _ in reg))
+    splits = [16, 32, 64] if cout == 112 else None
+    n0 = mvs_b200.launch_count()
+    y = conv_backends.get("tcgen05").conv3d_s2_box(x1, w1, tuple(L for _, _, L in reg), tuple(hi - lo + 1 for lo, hi, _ in reg), splits)
     assert y is not None
+    if splits is not None:
+        assert [t.shape[1] for t in y] == splits
+        y = torch.cat(y, 1)
     x2, w2 = x.float().requires_grad_(True), wt.float().requires_grad_(True)
     full = F.conv3d(x2, w2, None, 2, tuple(n // 2 + 1 for n in dims))        # the reference's layer on the full canvas
     ref = full[(slice(None), slice(None)) + box]
@@ -180,7 +188,11 @@ def test_stride2_conv_on_the_central_box(cin, cout, dims, wgrad, monkeypatch):
     outside[(slice(None), slice(None)) + box] = 0
     assert outside.abs().max() == 0                                            # ... which is zero outside the box
     gy = torch.randn(ref.shape, generator=g).to(DEV).to(torch.bfloat16)
+    n1 = mvs_b200.launch_count()
     y.backward(gy)
+    if wgrad == "lines" and dims[2] % 2 == 0 and cin <= 32:
+        # backward: one weight-gradient launch + one data-gradient launch -- no library convolution
+        assert mvs_b200.launch_count() - n1 == 2
     ref.backward(gy.float())
     assert _rel(x1.grad, x2.grad) < TOL
     assert _rel(w1.grad, w2.grad) < 2 * TOL
