@@ -1207,16 +1207,19 @@ TilePlan plan_tiles_mb(int Ho, int Wo, int rowb, size_t w_bytes_al, size_t smem_
 template <int CIN, int NOUT, int MB>
 int launch_conv_kdn_mb(const void* x, const void* w, void* y, int B, int Di, int Hi, int Wi, int Do, int Ho, int Wo, int cout,
                        int y_cs, int y_coff, int n_rows, int w_row0, int off_d, int off_h, int off_w, const TilePlan& tp, int slots,
-                       cudaStream_t st) {
+                       cudaStream_t st, int cin_real = CIN) {
+    // cin_real < CIN: voxel rows of x hold cin_real channels; the TMA box is CIN wide, the channels beyond the tensor's extent
+    // arrive as zeros (out-of-bounds fill) -- an 8-channel volume feeds the K = 16 MMA without a widened copy
     constexpr int ROWB = CIN * 2;
+    const int rowx = cin_real * 2;
     constexpr size_t W_BYTES_AL = ((size_t)27 * NOUT * ROWB + 1023) / 1024 * 1024;
     EncodeTiledFn enc = encode_fn();
     MVS_REQUIRE(enc != nullptr, "conv3d_s1_kdn: cuTensorMapEncodeTiled is not available from the driver");
     CUtensorMap tm_x, tm_w;
     {
-        const cuuint64_t dims[5] = {(cuuint64_t)CIN, (cuuint64_t)Wi, (cuuint64_t)Hi, (cuuint64_t)Di, (cuuint64_t)B};
-        const cuuint64_t strides[4] = {(cuuint64_t)ROWB, (cuuint64_t)ROWB * Wi, (cuuint64_t)ROWB * Wi * Hi,
-                                       (cuuint64_t)ROWB * Wi * Hi * Di};
+        const cuuint64_t dims[5] = {(cuuint64_t)cin_real, (cuuint64_t)Wi, (cuuint64_t)Hi, (cuuint64_t)Di, (cuuint64_t)B};
+        const cuuint64_t strides[4] = {(cuuint64_t)rowx, (cuuint64_t)rowx * Wi, (cuuint64_t)rowx * Wi * Hi,
+                                       (cuuint64_t)rowx * Wi * Hi * Di};
         const cuuint32_t box[5] = {(cuuint32_t)CIN, (cuuint32_t)tp.BW, (cuuint32_t)(tp.L + 2), 1, 1};
         const cuuint32_t es[5] = {1, 1, 1, 1, 1};
         CUresult r = enc(&tm_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), dims, strides, box, es,
@@ -1273,7 +1276,7 @@ int launch_conv_kdn_mb(const void* x, const void* w, void* y, int B, int Di, int
 
 template <int CIN, int NOUT>
 int launch_conv_kdn(const void* x, const void* w, void* y, int B, int Di, int Hi, int Wi, int Do, int Ho, int Wo, int cout,
-                    int y_cs, int y_coff, int n_rows, int w_row0, int off_d, int off_h, int off_w, cudaStream_t st) {
+                    int y_cs, int y_coff, int n_rows, int w_row0, int off_d, int off_h, int off_w, cudaStream_t st, int cin_real = CIN) {
     constexpr int ROWB = CIN * 2;
     constexpr size_t W_BYTES_AL = ((size_t)27 * NOUT * ROWB + 1023) / 1024 * 1024;
     constexpr int MBMAX = 512 / (2 * 3 * NOUT) >= 4 ? 4 : (512 / (2 * 3 * NOUT) >= 2 ? 2 : 1);
@@ -1304,7 +1307,7 @@ int launch_conv_kdn(const void* x, const void* w, void* y, int B, int Di, int Hi
         }
     }
     MVS_REQUIRE(best.score > 0, "conv3d_s1_kdn: no slab geometry fits shared memory (Cin=%d, N=%d)", CIN, NOUT);
-#define MVS_KDN(M) return launch_conv_kdn_mb<CIN, NOUT, M>(x, w, y, B, Di, Hi, Wi, Do, Ho, Wo, cout, y_cs, y_coff, n_rows, w_row0, off_d, off_h, off_w, best, best_slots, st)
+#define MVS_KDN(M) return launch_conv_kdn_mb<CIN, NOUT, M>(x, w, y, B, Di, Hi, Wi, Do, Ho, Wo, cout, y_cs, y_coff, n_rows, w_row0, off_d, off_h, off_w, best, best_slots, st, cin_real)
     if (best.MB == 1) MVS_KDN(1);
     if constexpr (MBMAX >= 2) { if (best.MB == 2) MVS_KDN(2); }
     if constexpr (MBMAX >= 4) { if (best.MB == 4) MVS_KDN(4); }
@@ -1783,7 +1786,9 @@ extern "C" int mvsb200_conv3d_s1_fwd_kdn(const void* x, const void* w_packed, vo
         const int c_here = cout - row0 < nout ? cout - row0 : nout;
         int rc = MVSB200_E_UNSUPPORTED;
 #define MVS_CONV(CI, NO) rc = launch_conv_kdn<CI, NO>(x, w_packed, y, B, Di, Hi, Wi, Do, Ho, Wo, c_here, y_cs, row0, n_rows, row0, off_d, off_h, off_w, st)
-        if (Cin == 16 && nout == 16) MVS_CONV(16, 16);
+        if (Cin == 8 && nout == 16) rc = launch_conv_kdn<16, 16>(x, w_packed, y, B, Di, Hi, Wi, Do, Ho, Wo, c_here, y_cs, row0, n_rows, row0, off_d, off_h, off_w, st, 8);
+        else if (Cin == 8 && nout == 32) rc = launch_conv_kdn<16, 32>(x, w_packed, y, B, Di, Hi, Wi, Do, Ho, Wo, c_here, y_cs, row0, n_rows, row0, off_d, off_h, off_w, st, 8);
+        else if (Cin == 16 && nout == 16) MVS_CONV(16, 16);
         else if (Cin == 16 && nout == 32) MVS_CONV(16, 32);
         else if (Cin == 32 && nout == 16) MVS_CONV(32, 16);
         else if (Cin == 32 && nout == 32) MVS_CONV(32, 32);

@@ -54,17 +54,19 @@ def _S1_FORM():
     return form if form == "taps" or hasattr(_lib.load(), "mvsb200_conv3d_s1_fwd_kdn") else "taps"
 
 
-def _launch(x_cl, wp, cout, out_dims, off, k_alg=None):
-    """k_alg: the contraction channels that carry data (algorithmic FLOPs are counted on them; a volume widened with zero
-    channels to reach the UMMA K of 16 is launched with cin = 16 but does the work of k_alg = 8)."""
+def _launch(x_cl, wp, cout, out_dims, off, k_alg=None, cin_kernel=None):
+    """k_alg: the contraction channels that carry data (algorithmic FLOPs are counted on them; an 8-channel volume runs on the
+    K = 16 kernel but does the work of k_alg = 8).  cin_kernel: channels of the packed filter when they exceed the volume's
+    (8-channel rows, kdn form: the kernel reads the missing channels as zeros)."""
     B, cin, Di, Hi, Wi = x_cl.shape
     Do, Ho, Wo = out_dims
     k_alg = cin if k_alg is None else k_alg
+    cin_w = cin if cin_kernel is None else cin_kernel
     y = torch.empty((B, cout, Do, Ho, Wo), dtype=torch.bfloat16, device=x_cl.device, memory_format=torch.channels_last_3d)
     if _S1_FORM() == "kdn":
         # depth tap folded into the MMA N extent: filter as [(kh,kw)][kd][rows][Cin]
         n_rows = wp.shape[1]
-        wk = wp.view(3, 3, 3, n_rows, cin).permute(1, 2, 0, 3, 4).contiguous()
+        wk = wp.view(3, 3, 3, n_rows, cin_w).permute(1, 2, 0, 3, 4).contiguous()
         with _timed("conv3d_s1_tc", 2.0 * 27 * k_alg * cout * B * Do * Ho * Wo):
             _lib.call("mvsb200_conv3d_s1_fwd_kdn", x_cl.data_ptr(), wk.data_ptr(), y.data_ptr(), B, Di, Hi, Wi, cin, Do, Ho, Wo,
                       cout, cout, n_rows, off, off, off, _stream())
@@ -89,38 +91,45 @@ class _Conv3dS1(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gy):
         x_cl, w = ctx.saved_tensors
-        pad = ctx.pad
-        gx = gw = None
         gy = gy.to(torch.bfloat16).contiguous(memory_format=torch.channels_last_3d)
-        if ctx.needs_input_grad[0]:
-            cout, cin = w.shape[:2]
-            off = -1 if pad == 1 else -2
-            if _supported(cout, cin):          # roles swap: the gradient volume has Cout channels, the result Cin
-                gx = _launch(gy, pack_filter_dgrad(w), cin, tuple(x_cl.shape[2:]), off)
-            elif cout == 8 and _supported(16, cin):
-                # 8-channel gradient rows (K = 8 < UMMA K): widen to 16 channels with zeros, zero filter rows to match
-                B, _, Do, Ho, Wo = gy.shape
-                gy16 = torch.empty((B, 16, Do, Ho, Wo), dtype=torch.bfloat16, device=gy.device,
-                                   memory_format=torch.channels_last_3d)
-                _lib.call("mvsb200_widen_rows_8to16_bf16", gy.data_ptr(), gy16.data_ptr(), B * Do * Ho * Wo, _stream())
-                w16 = torch.zeros((16,) + tuple(w.shape[1:]), dtype=w.dtype, device=w.device)
-                w16[:8] = w.detach()
-                gx = _launch(gy16, pack_filter_dgrad(w16), cin, tuple(x_cl.shape[2:]), off, k_alg=8)
-            else:
-                gx = torch.nn.grad.conv3d_input(x_cl.shape, w.to(gy.dtype), gy, padding=pad)
-        if ctx.needs_input_grad[1]:
-            cout, cin = w.shape[:2]
-            if cin in _CIN_OK and cout in (8, 16, 32, 64):
-                B, _, Di, Hi, Wi = x_cl.shape
-                Do, Ho, Wo = gy.shape[2:]
-                gw27 = torch.empty((27, cin, cout), dtype=torch.float32, device=gy.device)
-                with _timed("conv3d_s1_wgrad_tc", 2.0 * 27 * cin * cout * B * Do * Ho * Wo):
-                    _lib.call("mvsb200_conv3d_s1_wgrad", x_cl.data_ptr(), gy.data_ptr(), gw27.data_ptr(), B, Di, Hi, Wi, cin,
-                              Do, Ho, Wo, cout, -pad, -pad, -pad, _stream())
-                gw = gw27.reshape(3, 3, 3, cin, cout).permute(4, 3, 0, 1, 2).to(w.dtype)
-            else:
-                gw = torch.nn.grad.conv3d_weight(x_cl, w.shape, gy, padding=pad).to(w.dtype)
+        gx = _s1_dgrad(gy, w, ctx.pad, x_cl.shape) if ctx.needs_input_grad[0] else None
+        gw = _s1_wgrad(x_cl, gy, w, ctx.pad) if ctx.needs_input_grad[1] else None
         return gx, gw, None
+
+
+def _s1_dgrad(gy, w, pad, x_shape):
+    """Data gradient of a stride-1 convolution: the same convolution of the output gradient with the flipped, transposed
+    filter (gy: bf16 channel-last)."""
+    cout, cin = w.shape[:2]
+    off = -1 if pad == 1 else -2
+    if _supported(cout, cin):          # roles swap: the gradient volume has Cout channels, the result Cin
+        return _launch(gy, pack_filter_dgrad(w), cin, tuple(x_shape[2:]), off)
+    if cout == 8 and _supported(16, cin):
+        # 8-channel gradient rows (K = 8 < UMMA K = 16): the kernel's TMA box is 16 channels wide and the 8 beyond the voxel row
+        # arrive as zeros (out-of-bounds fill), the filter gets zero rows to match -- no widened copy of the gradient volume
+        w16 = torch.zeros((16,) + tuple(w.shape[1:]), dtype=w.dtype, device=w.device)
+        w16[:8] = w.detach()
+        if _S1_FORM() == "kdn":
+            return _launch(gy, pack_filter_dgrad(w16), cin, tuple(x_shape[2:]), off, k_alg=8, cin_kernel=16)
+        B, _, Do, Ho, Wo = gy.shape
+        gy16 = torch.empty((B, 16, Do, Ho, Wo), dtype=torch.bfloat16, device=gy.device, memory_format=torch.channels_last_3d)
+        _lib.call("mvsb200_widen_rows_8to16_bf16", gy.data_ptr(), gy16.data_ptr(), B * Do * Ho * Wo, _stream())
+        return _launch(gy16, pack_filter_dgrad(w16), cin, tuple(x_shape[2:]), off, k_alg=8)
+    return torch.nn.grad.conv3d_input(x_shape, w.to(gy.dtype), gy, padding=pad)
+
+
+def _s1_wgrad(x_cl, gy, w, pad):
+    """Weight gradient of a stride-1 convolution on conv3d_s1_wgrad_tc_kernel (x_cl, gy: bf16 channel-last)."""
+    cout, cin = w.shape[:2]
+    if cin in _CIN_OK and cout in (8, 16, 32, 64):
+        B, _, Di, Hi, Wi = x_cl.shape
+        Do, Ho, Wo = gy.shape[2:]
+        gw27 = torch.empty((27, cin, cout), dtype=torch.float32, device=gy.device)
+        with _timed("conv3d_s1_wgrad_tc", 2.0 * 27 * cin * cout * B * Do * Ho * Wo):
+            _lib.call("mvsb200_conv3d_s1_wgrad", x_cl.data_ptr(), gy.data_ptr(), gw27.data_ptr(), B, Di, Hi, Wi, cin,
+                      Do, Ho, Wo, cout, -pad, -pad, -pad, _stream())
+        return gw27.reshape(3, 3, 3, cin, cout).permute(4, 3, 0, 1, 2).to(w.dtype)
+    return torch.nn.grad.conv3d_weight(x_cl, w.shape, gy, padding=pad).to(w.dtype)
 
 
 # ---- stride-2 transposed convolution as 8 output-parity classes of the stride-1 kernel -------------------------------
@@ -368,6 +377,32 @@ def conv_transpose3d_s2_kc(x, widths, w_t, pads, out_dims, out=None, accumulate=
     return out
 
 
+def _s2box_forward(x_cl, w, pads, out_dims, splits, holder):
+    """Forward of the stride-2 box convolution on conv3d_s2_tc_kernel; fixes the geometry of `holder` (ops.BoxGradDest), the
+    buffer the branches' gradients are collected in."""
+    B, cin, Dx, Hx, Wx = x_cl.shape
+    cout = w.shape[0]
+    n_rows = (cout + 15) // 16 * 16
+    Do, Ho, Wo = out_dims
+    y = torch.empty((B, cout, Do, Ho, Wo), dtype=torch.bfloat16, device=x_cl.device, memory_format=torch.channels_last_3d)
+    with _timed("conv3d_s2_tc", 2.0 * 27 * cin * cout * B * Do * Ho * Wo):
+        _lib.call("mvsb200_conv3d_s2_fwd", x_cl.data_ptr(), pack_filter_rows(w, n_rows).data_ptr(), y.data_ptr(), B, Dx, Hx, Wx,
+                  cin, Do, Ho, Wo, cout, cout, n_rows, pads[0], pads[1], pads[2], _stream())
+    if holder is not None:
+        # where the branches' gradients are collected: the dense box when both gradients run on this library's kernels,
+        # else the padded buffer of the library's strided backward
+        widths = splits if splits is not None else (cout,)
+        own = _s2_dgrad_own(cin, widths) and _s2_wgrad_mode(x_cl.shape, (B, cout) + tuple(out_dims)) == "lines"
+        if own:
+            holder.__init__((B, cout) + tuple(out_dims), tuple(slice(0, n) for n in out_dims), splits, x_cl.device, zero=False)
+        else:
+            _, nat, box = _Conv3dS2Box._geometry(x_cl.shape, pads, out_dims)
+            holder.__init__((B, cout) + nat, box, splits, x_cl.device)
+    if splits is None:
+        return y
+    return tuple(torch.split(y, list(splits), 1))
+
+
 class _Conv3dS2Box(torch.autograd.Function):
     """out(o) = sum_k W[k] x(2o - pad + k) for o in a box of `out_dims` voxels (zero outside x).  Forward on the tcgen05
     stride-2 kernel.  `splits`: the output channels are returned as that many separate tensors (the stacked branches
@@ -389,86 +424,109 @@ class _Conv3dS2Box(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, pads, out_dims, splits, holder=None):
         x_cl = x.detach().contiguous(memory_format=torch.channels_last_3d)
-        B, cin, Dx, Hx, Wx = x_cl.shape
-        cout = w.shape[0]
-        n_rows = (cout + 15) // 16 * 16
-        Do, Ho, Wo = out_dims
-        y = torch.empty((B, cout, Do, Ho, Wo), dtype=torch.bfloat16, device=x.device, memory_format=torch.channels_last_3d)
-        with _timed("conv3d_s2_tc", 2.0 * 27 * cin * cout * B * Do * Ho * Wo):
-            _lib.call("mvsb200_conv3d_s2_fwd", x_cl.data_ptr(), pack_filter_rows(w, n_rows).data_ptr(), y.data_ptr(), B, Dx, Hx, Wx,
-                      cin, Do, Ho, Wo, cout, cout, n_rows, pads[0], pads[1], pads[2], _stream())
+        outs = _s2box_forward(x_cl, w, pads, out_dims, splits, holder)
         ctx.save_for_backward(x_cl, w)
-        ctx.pads, ctx.out_dims, ctx.splits = tuple(pads), tuple(out_dims), splits
-        ctx.holder = holder
-        if holder is not None:
-            # where the branches' gradients are collected: the dense box when both gradients run on this library's kernels,
-            # else the padded buffer of the library's strided backward
-            widths = splits if splits is not None else (cout,)
-            own = _s2_dgrad_own(cin, widths) and _s2_wgrad_mode(x_cl.shape, (B, cout) + tuple(out_dims)) == "lines"
-            if own:
-                holder.__init__((B, cout) + tuple(out_dims), tuple(slice(0, n) for n in out_dims), splits, x_cl.device, zero=False)
-            else:
-                _, nat, box = _Conv3dS2Box._geometry(x_cl.shape, pads, out_dims)
-                holder.__init__((B, cout) + nat, box, splits, x_cl.device)
-        if splits is None:
-            return y
-        return tuple(torch.split(y, list(splits), 1))
+        ctx.pads, ctx.out_dims, ctx.splits, ctx.holder = tuple(pads), tuple(out_dims), splits, holder
+        return outs
 
     @staticmethod
     def backward(ctx, *gys):
         x_cl, w = ctx.saved_tensors
-        B, cin = x_cl.shape[:2]
-        cout = w.shape[0]
-        out_dims = tuple(ctx.out_dims)
-        widths = tuple(ctx.splits) if ctx.splits is not None else (cout,)
-        P, nat, box = _Conv3dS2Box._geometry(x_cl.shape, ctx.pads, out_dims)
-        need_x, need_w = bool(ctx.needs_input_grad[0]), bool(ctx.needs_input_grad[1])
-        wg_mode = _s2_wgrad_mode(x_cl.shape, (B, cout) + out_dims)
-        own_dgrad = need_x and _s2_dgrad_own(cin, widths)
-        own_wgrad = need_w and wg_mode != "cudnn"
-        lib_mask = [need_x and not own_dgrad, need_w and not own_wgrad, False]
-        holder = ctx.holder if ctx.holder is not None and ctx.holder.buffer is not None else None
+        gx, gw = _s2box_backward(x_cl, w, ctx.pads, ctx.out_dims, ctx.splits, ctx.holder, gys, bool(ctx.needs_input_grad[0]),
+                                 bool(ctx.needs_input_grad[1]))
+        return gx, gw, None, None, None, None
 
-        def assemble(shape, where):
-            """The channel-stacked gradient in a buffer of `shape` with the box at `where`: the holder's buffer when it has
-            this geometry (slices the fused BatchNorm backward wrote are already in place), else a fresh one + copies."""
-            h = holder if holder is not None and holder.shape == shape else None
-            full = shape[2:] == out_dims
-            buf = h.buffer if h is not None else torch.empty(shape, dtype=torch.bfloat16, device=x_cl.device,
-                                                             memory_format=torch.channels_last_3d)
-            if h is None and not full:
-                buf.zero_()
-            c0 = 0
-            for k, (g, n) in enumerate(zip(gys, widths)):
-                if h is not None and h.holds(k, g):
-                    pass                                     # already in place
-                elif g is not None:
-                    buf[(slice(None), slice(c0, c0 + n)) + where] = g
-                elif h is not None or full:
-                    buf[(slice(None), slice(c0, c0 + n)) + where] = 0     # no gradient for this branch / a stale slice
-                c0 += n
-            return buf
 
-        gx = gw = None
-        gy_box = None
-        if lib_mask[0] or lib_mask[1]:
-            g_full = assemble((B, cout) + nat, box)
-            gx, gw, _ = torch.ops.aten.convolution_backward(g_full, x_cl, w.detach().to(torch.bfloat16), None, [2, 2, 2], list(P),
-                                                            [1, 1, 1], False, [0, 0, 0], 1, lib_mask)
-            gy_box = g_full[(slice(None), slice(None)) + box]
-        if own_dgrad or own_wgrad:
-            if gy_box is None:
-                gy_box = assemble((B, cout) + out_dims, tuple(slice(0, n) for n in out_dims))
-            if own_wgrad:
-                # gW[co][ci][k] = sum_o x[2o - pad + k][ci] gy[o][co]: the strided operand is the layer's input
-                g27 = s2_wgrad(x_cl, gy_box, ctx.pads, wg_mode)                        # [27, Cin, Cout]; gy_box may be a view
-                gw = g27.reshape(3, 3, 3, cin, cout).permute(4, 3, 0, 1, 2)
-            if own_dgrad:
-                # gx[2J + par] = sum_k W[k]^T gy[J + (par + pad - k)/2]: the forward weight [Cout, Cin, ...] IS the
-                # ConvTranspose3d layout [in = Cout, out = Cin, ...] of that transposed convolution
-                gx = conv_transpose3d_s2_kc(gy_box.contiguous(memory_format=torch.channels_last_3d), widths, w, ctx.pads,
-                                            tuple(x_cl.shape[2:]))
-        return gx, (gw.to(w.dtype) if gw is not None else None), None, None, None, None
+def _s2box_backward(x_cl, w, pads, out_dims, splits, holder, gys, need_x, need_w, acc_into=None):
+    """Gradients of the stride-2 box convolution (see _Conv3dS2Box).  acc_into: a canvas that already holds another
+    contribution to the input gradient -- the data gradient is ADDED to it (in the epilogue of the transposed-convolution
+    kernel) and it is returned."""
+    B, cin = x_cl.shape[:2]
+    cout = w.shape[0]
+    out_dims = tuple(out_dims)
+    widths = tuple(splits) if splits is not None else (cout,)
+    P, nat, box = _Conv3dS2Box._geometry(x_cl.shape, pads, out_dims)
+    wg_mode = _s2_wgrad_mode(x_cl.shape, (B, cout) + out_dims)
+    own_dgrad = need_x and _s2_dgrad_own(cin, widths)
+    own_wgrad = need_w and wg_mode != "cudnn"
+    lib_mask = [need_x and not own_dgrad, need_w and not own_wgrad, False]
+    holder = holder if holder is not None and holder.buffer is not None else None
+
+    def assemble(shape, where):
+        """The channel-stacked gradient in a buffer of `shape` with the box at `where`: the holder's buffer when it has
+        this geometry (slices the fused BatchNorm backward wrote are already in place), else a fresh one + copies."""
+        h = holder if holder is not None and holder.shape == shape else None
+        full = shape[2:] == out_dims
+        buf = h.buffer if h is not None else torch.empty(shape, dtype=torch.bfloat16, device=x_cl.device,
+                                                         memory_format=torch.channels_last_3d)
+        if h is None and not full:
+            buf.zero_()
+        c0 = 0
+        for k, (g, n) in enumerate(zip(gys, widths)):
+            if h is not None and h.holds(k, g):
+                pass                                     # already in place
+            elif g is not None:
+                buf[(slice(None), slice(c0, c0 + n)) + where] = g
+            elif h is not None or full:
+                buf[(slice(None), slice(c0, c0 + n)) + where] = 0     # no gradient for this branch / a stale slice
+            c0 += n
+        return buf
+
+    gx = gw = None
+    gy_box = None
+    if lib_mask[0] or lib_mask[1]:
+        g_full = assemble((B, cout) + nat, box)
+        gx, gw, _ = torch.ops.aten.convolution_backward(g_full, x_cl, w.detach().to(torch.bfloat16), None, [2, 2, 2], list(P),
+                                                        [1, 1, 1], False, [0, 0, 0], 1, lib_mask)
+        gy_box = g_full[(slice(None), slice(None)) + box]
+        if gx is not None and acc_into is not None:
+            gx = acc_into.add_(gx)
+    if own_dgrad or own_wgrad:
+        if gy_box is None:
+            gy_box = assemble((B, cout) + out_dims, tuple(slice(0, n) for n in out_dims))
+        if own_wgrad:
+            # gW[co][ci][k] = sum_o x[2o - pad + k][ci] gy[o][co]: the strided operand is the layer's input
+            g27 = s2_wgrad(x_cl, gy_box, pads, wg_mode)                            # [27, Cin, Cout]; gy_box may be a view
+            gw = g27.reshape(3, 3, 3, cin, cout).permute(4, 3, 0, 1, 2)
+        if own_dgrad:
+            # gx[2J + par] = sum_k W[k]^T gy[J + (par + pad - k)/2]: the forward weight [Cout, Cin, ...] IS the
+            # ConvTranspose3d layout [in = Cout, out = Cin, ...] of that transposed convolution
+            gx = conv_transpose3d_s2_kc(gy_box.contiguous(memory_format=torch.channels_last_3d), widths, w, pads,
+                                        tuple(x_cl.shape[2:]), out=acc_into, accumulate=acc_into is not None)
+    return gx, (gw.to(w.dtype) if gw is not None else None)
+
+
+class _EntryConvs(torch.autograd.Function):
+    """The four convolutions that read the cost volume (scripts/model.py:101-110) as ONE autograd node: conv_0_0 (stride 1,
+    dense) and the stacked stride-2 branches conv_{1,2,3}_0 on the central box.  Forward = the two kernels of _Conv3dS1 and
+    _Conv3dS2Box.  Backward: the cost volume's gradient is the sum of two data gradients; as separate nodes autograd adds
+    them with an elementwise pass over two 1 GB canvases -- here the transposed-convolution kernel of the branches accumulates
+    into the canvas conv_0_0's data gradient was written to."""
+
+    @staticmethod
+    def forward(ctx, x, w00, w_cat, pads, out_dims, splits, holder):
+        x_cl = x.detach().contiguous(memory_format=torch.channels_last_3d)
+        y0 = _launch(x_cl, pack_filter(w00), w00.shape[0], tuple(x_cl.shape[2:]), -1)
+        outs = _s2box_forward(x_cl, w_cat, pads, out_dims, splits, holder)
+        ctx.save_for_backward(x_cl, w00, w_cat)
+        ctx.pads, ctx.out_dims, ctx.splits, ctx.holder = tuple(pads), tuple(out_dims), splits, holder
+        return (y0,) + tuple(outs)
+
+    @staticmethod
+    def backward(ctx, gy0, *gys):
+        x_cl, w00, w_cat = ctx.saved_tensors
+        need_x = bool(ctx.needs_input_grad[0])
+        gx = gw00 = None
+        if gy0 is not None:
+            gy0 = gy0.to(torch.bfloat16).contiguous(memory_format=torch.channels_last_3d)
+            gx = _s1_dgrad(gy0, w00, 1, x_cl.shape) if need_x else None
+            gw00 = _s1_wgrad(x_cl, gy0, w00, 1) if ctx.needs_input_grad[1] else None
+        acc = gx if gx is not None and gx.is_contiguous(memory_format=torch.channels_last_3d) and gx.dtype == torch.bfloat16 else None
+        g2, gw_cat = _s2box_backward(x_cl, w_cat, ctx.pads, ctx.out_dims, ctx.splits, ctx.holder, gys, need_x,
+                                     bool(ctx.needs_input_grad[2]), acc_into=acc)
+        if need_x:
+            gx = g2 if (acc is not None or gx is None) else gx + g2
+        return gx, gw00, gw_cat, None, None, None, None
 
 
 class Tcgen05ConvBackend:
@@ -492,6 +550,26 @@ class Tcgen05ConvBackend:
                     o._mvs_grad_dest = (holder, k)           # read by regulariser.py -> ops.box_batchnorm_relu
             return outs
         return None
+
+    @staticmethod
+    def entry_convs(x, w00, w_cat, pads, out_dims, splits):
+        """conv_0_0 (stride 1, padding 1) and the stacked stride-2 branches on their box, from the same volume, as one
+        autograd node (_EntryConvs): returns (y0, (S_1, S_2, S_3)) or None when the operands are not the kernels'."""
+        if not (x.is_cuda and x.dtype == torch.bfloat16 and x.shape[1] in _CIN_OK and _supported(x.shape[1], w00.shape[0])
+                and min(x.shape[2:]) >= 3 and w_cat.shape[0] % 8 == 0 and w_cat.shape[0] <= 128 and all(q in (1, 2) for q in pads)
+                and splits is not None):
+            return None
+        from .ops import BoxGradDest
+        holder = None
+        if x.requires_grad or w_cat.requires_grad:
+            holder = BoxGradDest.__new__(BoxGradDest)
+            holder.buffer = None
+        outs = _EntryConvs.apply(x, w00, w_cat, tuple(int(q) for q in pads), tuple(int(n) for n in out_dims),
+                                 tuple(int(n) for n in splits), holder)
+        if holder is not None:
+            for k, o in enumerate(outs[1:]):
+                o._mvs_grad_dest = (holder, k)
+        return outs[0], tuple(outs[1:])
 
     @staticmethod
     def conv3d(x, w, stride, padding):

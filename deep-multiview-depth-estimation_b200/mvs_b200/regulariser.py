@@ -169,7 +169,19 @@ class CostVolumeReg(nn.Module):
         C = tuple(slice(lo, hi + 1) for lo, hi, _ in reg)                     # central box on the canvas
         train = self.BN_0.training
 
-        y0 = self._bn_dense(self.BN_0, be.conv3d(x, self._w("conv_0_0", dt), 1, (1, 1, 1)))
+        # the three stride-2 branches all read cv (model.py:104-110): ONE convolution with the weights stacked along
+        # Cout (16+32+64 = 112) reads the cost volume once instead of three times; with conv_0_0 they form one autograd node
+        # (the cost volume's gradient is accumulated inside the kernels, not by an elementwise pass of autograd)
+        w_cat = torch.cat([self._w(f"conv_{k}_0", dt) for k in (1, 2, 3)], 0)
+        widths = [self.conv_1_0.out_channels, self.conv_2_0.out_channels, self.conv_3_0.out_channels]
+        box_pads, box_dims = tuple(L for _, _, L in reg), tuple(hi - lo + 1 for lo, hi, _ in reg)
+        S_parts = None
+        entry = be.entry_convs(x, self._w("conv_0_0", dt), w_cat, box_pads, box_dims, widths) if hasattr(be, "entry_convs") else None
+        if entry is not None:
+            c00, S_parts = entry
+        else:
+            c00 = be.conv3d(x, self._w("conv_0_0", dt), 1, (1, 1, 1))
+        y0 = self._bn_dense(self.BN_0, c00)
 
         # ---- encoder branches: stride-2 conv on C, then stride-1 conv on C (+1 ring for the statistics)
         P = tuple(L if L >= 2 else L + 2 for _, _, L in reg)                  # symmetric pad with P == L (mod 2)
@@ -188,13 +200,8 @@ class CostVolumeReg(nn.Module):
             lo, hi, _ = reg[ax]
             inner.append(slice(lo - E_lo[ax], lo - E_lo[ax] + (hi - lo + 1)))  # C inside E
         enc = {}
-        # the three stride-2 branches all read cv (model.py:104-110): ONE convolution with the weights stacked along
-        # Cout (16+32+64 = 112) reads the cost volume once instead of three times
-        w_cat = torch.cat([self._w(f"conv_{k}_0", dt) for k in (1, 2, 3)], 0)
-        widths = [self.conv_1_0.out_channels, self.conv_2_0.out_channels, self.conv_3_0.out_channels]
-        S_parts = None
-        if hasattr(be, "conv3d_s2_box"):                                      # tcgen05 stride-2 kernel, straight onto the box
-            S_parts = be.conv3d_s2_box(x, w_cat, tuple(L for _, _, L in reg), tuple(hi - lo + 1 for lo, hi, _ in reg), widths)
+        if S_parts is None and hasattr(be, "conv3d_s2_box"):                  # tcgen05 stride-2 kernel, straight onto the box
+            S_parts = be.conv3d_s2_box(x, w_cat, box_pads, box_dims, widths)
         if S_parts is None:
             S_parts = torch.split(be.conv3d(x, w_cat, 2, P)[(slice(None), slice(None)) + cut], widths, 1)
         S_split = dict(zip((1, 2, 3), S_parts))
