@@ -1321,9 +1321,13 @@ int launch_conv_kdn(const void* x, const void* w, void* y, int B, int Di, int Hi
 // i.e. each of the 8 output-parity classes is a stride-1 convolution of the INPUT lattice with a sub-set of the taps, and
 // the 8 sub-sets together are exactly the 27 taps.  The forward kernel above, launched once per class, writes every class
 // as a stride-2 sub-lattice of the canvas (64-byte pieces 128 bytes apart, each line visited by 8 launches).  Here a CTA
-// marches along the input depth once, keeps EIGHT accumulator blocks (one per class) per stage in TMEM, issues each of
-// the 27 taps into the block of its class, and the epilogue interleaves the classes so that a thread writes the two
-// w-parities of a voxel pair back to back: full, contiguous lines of the canvas, each written once.
+// marches along the input depth once, keeps EIGHT accumulator blocks (one per class) per stage in TMEM, and the epilogue
+// interleaves the classes so that a thread writes the two w-parities of a voxel pair back to back: full, contiguous lines
+// of the canvas, each written once.  MMAs: ONE PER INPUT SHIFT (8 per K step; DeconvWide in tc_common.cuh) over the range
+// of class blocks that read the shift, with zero filter slots for the classes in the range that do not -- the earlier
+// form issued one MMA per run of adjacent user classes (14 per K step) and sat on the shared-memory A-operand feed.
+constexpr int kDeconvSlots = 31;     // filter slots of the one-MMA-per-shift table (27 taps + zero slots), pads in {1,2}
+
 struct DeconvParams {
     int B, Do, Ho, Wo;              // extent of the canvas that is written (voxels beyond it are dropped)
     int Jd, Jh, Jw;                 // output lattice (voxel octets): ceil(extent / 2)
@@ -1332,7 +1336,8 @@ struct DeconvParams {
     int dchunk, nchunks, n_items;
     int cout, n_rows;
     int slab_bytes;
-    DeconvGroups g;                 // the 27 (class, filter tap) pairs grouped by the input shift they read (tc_common.cuh)
+    DeconvWide g;                   // one MMA per input shift: Gray-ordered classes, zero filter slots (tc_common.cuh)
+    int wide_io;                    // 1: 32-byte stores (rows 32-byte aligned, channels in multiples of 16)
     long long y_sb, y_sd, y_sh, y_sw;   // canvas voxel-row strides in elements
     __nv_bfloat16* y;
 };
@@ -1344,7 +1349,7 @@ deconv3d_s2_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
     constexpr int ROWB = CIN * 2;
     constexpr int KSTEPS = CIN / 16;
     constexpr int W_TAP_BYTES = NOUT * ROWB;
-    constexpr int W_BYTES = 27 * W_TAP_BYTES;
+    constexpr int W_BYTES = kDeconvSlots * W_TAP_BYTES;
     constexpr int W_BYTES_AL = (W_BYTES + 1023) / 1024 * 1024;
     constexpr int MB = 512 / (16 * NOUT);               // 2 stages x MB x 8 classes x NOUT columns == 512
     // instruction descriptor without the N field: D fp32, A/B bf16, both K-major, M = 128; N = ncls * NOUT per group
@@ -1398,8 +1403,9 @@ deconv3d_s2_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
     if (warp == 0) {
         // ===================================== TMA producer =====================================
         if (elect_one()) {
-            mbar_expect_tx(wfull, 27u * W_TAP_BYTES);
-            for (int e = 0; e < 27; ++e) tma_load_2d(w_smem + e * W_TAP_BYTES, &tm_w, wfull, 0, p.g.tap_k[e] * p.n_rows);
+            mbar_expect_tx(wfull, (uint32_t)p.g.n_slots * W_TAP_BYTES);
+            for (int e = 0; e < p.g.n_slots; ++e)      // tap 27 of the packed weights is all zeros
+                tma_load_2d(w_smem + e * W_TAP_BYTES, &tm_w, wfull, 0, p.g.tap_k[e] * p.n_rows);
         }
         __syncwarp();
         const uint32_t box_bytes = (uint32_t)ROWB * p.BW * (p.L + 2);
@@ -1446,8 +1452,8 @@ deconv3d_s2_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                             const uint32_t a_lo = (td == 0 ? slot_lo[0] : (td == 1 ? slot_lo[1] : slot_lo[2])) + mb16 +
                                                   (uint32_t)p.g.grp_th[g] * bw16 + (uint32_t)((p.g.grp_tw[g] * ROWB) >> 4);
                             const uint32_t b_lo = w_lo + (uint32_t)((p.g.grp_slot0[g] * W_TAP_BYTES) >> 4);
-                            const uint32_t d_tmem = tmem_base + (uint32_t)(((stage * MB + mb) * 8 + p.g.grp_class0[g]) * NOUT);
-                            const uint32_t idesc = IDESC0 | ((uint32_t)((p.g.grp_ncls[g] * NOUT) >> 3) << 17);
+                            const uint32_t d_tmem = tmem_base + (uint32_t)(((stage * MB + mb) * 8 + p.g.grp_pos0[g]) * NOUT);
+                            const uint32_t idesc = IDESC0 | ((uint32_t)((p.g.grp_npos[g] * NOUT) >> 3) << 17);
                             uint32_t acc = p.g.grp_first[g] ? 0u : 1u;
 #pragma unroll
                             for (int k = 0; k < KSTEPS; ++k) {
@@ -1495,9 +1501,23 @@ deconv3d_s2_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                         uint32_t v[NOUT];
                         tmem_ld<NOUT>(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(((stage * MB + mb) * 8 + c) * NOUT), v);
                         tmem_ld_wait();
-                        const int z = oz + (c >> 2), yy = oy + (c >> 1 & 1), xx = ox + (c & 1);
+                        const int cl = p.g.cls_of_pos[c];                  // accumulator block c holds output-parity class cl
+                        const int z = oz + (cl >> 2), yy = oy + (cl >> 1 & 1), xx = ox + (cl & 1);
                         if (in_tile[mb] && z < p.Do && yy < p.Ho && xx < p.Wo) {
                             __nv_bfloat16* row = p.y + (long long)b * p.y_sb + (long long)z * p.y_sd + (long long)yy * p.y_sh + (long long)xx * p.y_sw;
+                            if (p.wide_io) {                                   // 32-byte stores: half as many store instructions
+#pragma unroll
+                                for (int ch = 0; ch < NOUT; ch += 16) {
+                                    if (ch < p.cout) {
+                                        U8 o;
+#pragma unroll
+                                        for (int i = 0; i < 8; ++i)
+                                            o.v[i] = pack_bf16x2(__uint_as_float(v[ch + 2 * i]), __uint_as_float(v[ch + 2 * i + 1]));
+                                        st_u8(row + ch, o);
+                                    }
+                                }
+                                continue;
+                            }
 #pragma unroll
                             for (int ch = 0; ch < NOUT; ch += 8) {
                                 if (ch < p.cout) {
@@ -1550,7 +1570,7 @@ int launch_deconv_s2(const void* x, const void* w, void* y, int B, int Di, int H
                      int n_rows, int pad_d, int pad_h, int pad_w, const long long* y_strides4, cudaStream_t st) {
     constexpr int ROWB = CIN * 2;
     constexpr int MB = 512 / (16 * NOUT);
-    constexpr size_t W_BYTES_AL = ((size_t)27 * NOUT * ROWB + 1023) / 1024 * 1024;
+    constexpr size_t W_BYTES_AL = ((size_t)kDeconvSlots * NOUT * ROWB + 1023) / 1024 * 1024;
     EncodeTiledFn enc = encode_fn();
     MVS_REQUIRE(enc != nullptr, "deconv3d_s2: cuTensorMapEncodeTiled is not available from the driver");
     const size_t smem_budget = 227 * 1024 - 1024;
@@ -1571,7 +1591,7 @@ int launch_deconv_s2(const void* x, const void* w, void* y, int B, int Di, int H
         MVS_REQUIRE(r == CUDA_SUCCESS, "deconv3d_s2: cuTensorMapEncodeTiled(x) failed (%d)", (int)r);
     }
     {
-        const cuuint64_t dims[2] = {(cuuint64_t)CIN, (cuuint64_t)27 * n_rows};
+        const cuuint64_t dims[2] = {(cuuint64_t)CIN, (cuuint64_t)28 * n_rows};      // 27 taps + the all-zero tap
         const cuuint64_t strides[1] = {(cuuint64_t)ROWB};
         const cuuint32_t box[2] = {(cuuint32_t)CIN, (cuuint32_t)NOUT};
         const cuuint32_t es[2] = {1, 1};
@@ -1585,9 +1605,11 @@ int launch_deconv_s2(const void* x, const void* w, void* y, int B, int Di, int H
     p.B = B; p.Do = Do; p.Ho = Ho; p.Wo = Wo; p.Jd = Jd; p.Jh = Jh; p.Jw = Jw;
     p.BW = tp.BW; p.L = tp.L; p.MB = MB; p.tiles_x = tp.tiles_x; p.tiles_y = tp.tiles_y;
     p.cout = cout; p.n_rows = n_rows; p.slab_bytes = tp.slab_bytes;
-    { const int rc = build_deconv_groups(pad_d, pad_h, pad_w, NOUT, p.g); if (rc != MVSB200_OK) return rc; }
+    { const int rc = build_deconv_wide(pad_d, pad_h, pad_w, NOUT, p.g); if (rc != MVSB200_OK) return rc; }
+    MVS_REQUIRE(p.g.n_slots <= kDeconvSlots, "deconv3d_s2: %d filter slots", p.g.n_slots);
     p.y_sb = y_strides4[0]; p.y_sd = y_strides4[1]; p.y_sh = y_strides4[2]; p.y_sw = y_strides4[3];
     p.y = reinterpret_cast<__nv_bfloat16*>(y);
+    p.wide_io = (cout % 16 == 0 && p.y_sb % 16 == 0 && p.y_sd % 16 == 0 && p.y_sh % 16 == 0 && p.y_sw % 16 == 0 && ((uintptr_t)y & 31u) == 0) ? 1 : 0;
 
     const long tiles = (long)tp.tiles_x * tp.tiles_y;
     int sms = 148;

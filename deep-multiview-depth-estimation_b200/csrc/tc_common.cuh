@@ -152,83 +152,25 @@ CUtensorMapSwizzle swizzle_for(int rowb) {
     return rowb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (rowb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
 }
 
-// ---- stride-2 transposed convolution: the 27 (output-parity class, filter tap) pairs ---------------------------------
-//   out[2J + par] = sum over the filter taps k with (par + pad - k) even of W[k] . in[J + (par + pad - k)/2]   (per axis)
-// Slab tap t = (par + pad - k)/2 + 1 per axis (input index J + t - 1).  The pairs are grouped by the INPUT SHIFT (td,th,tw)
-// they read: classes that share a shift share the A operand, so one MMA of N = ncls * NOUT serves them all when their
-// accumulator blocks are adjacent in TMEM.  Shared-memory filter slot e holds filter tap tap_k[e]; a group's slots and its
-// classes are consecutive.
-struct DeconvGroups {
-    int tap_k[27];                  // filter tap (kd*3+kh)*3+kw held by shared-memory slot e
-    int n_groups;
-    int grp_td[27], grp_th[27], grp_tw[27];   // input shift of the group (slab tap per axis)
-    int grp_class0[27], grp_ncls[27];         // first class block and number of adjacent class blocks the MMA covers
-    int grp_slot0[27];                        // first filter slot of the group
-    int grp_first[27];                        // 1: the group's MMA initialises its accumulators (first touch of those classes)
-};
-
-inline int build_deconv_groups(int pad_d, int pad_h, int pad_w, int NOUT, DeconvGroups& p) {
-    const int pads[3] = {pad_d, pad_h, pad_w};
-    int pair_k[8][27];                                   // pair_k[class][shift] = filter tap or -1
-    for (int c = 0; c < 8; ++c)
-        for (int t = 0; t < 27; ++t) pair_k[c][t] = -1;
-    int n_pairs = 0;
-    for (int c = 0; c < 8; ++c) {
-        const int par[3] = {c >> 2 & 1, c >> 1 & 1, c & 1};
-        for (int kd = 0; kd < 3; ++kd)
-            for (int kh = 0; kh < 3; ++kh)
-                for (int kw = 0; kw < 3; ++kw) {
-                    const int k[3] = {kd, kh, kw};
-                    int t[3];
-                    bool ok = true;
-                    for (int ax = 0; ax < 3; ++ax) {
-                        const int v = par[ax] + pads[ax] - k[ax];
-                        if (v & 1) { ok = false; break; }
-                        t[ax] = v / 2 + 1;
-                        if (t[ax] < 0 || t[ax] > 2) { ok = false; break; }
-                    }
-                    if (!ok) continue;
-                    pair_k[c][(t[0] * 3 + t[1]) * 3 + t[2]] = (kd * 3 + kh) * 3 + kw;
-                    ++n_pairs;
-                }
-    }
-    MVS_REQUIRE(n_pairs == 27, "deconv3d_s2: padding (%d,%d,%d) does not map all 27 taps into the 3-tap window", pad_d, pad_h, pad_w);
-    // shifts in decreasing number of user classes: the first group to touch a class initialises its accumulator block, and
-    // a group must initialise all of its classes or none -- true when the widest shift (used by every class it can reach)
-    // comes first
-    int order[27], users[27];
-    for (int t = 0; t < 27; ++t) {
-        order[t] = t;
-        users[t] = 0;
-        for (int c = 0; c < 8; ++c) users[t] += pair_k[c][t] >= 0;
-    }
-    for (int i = 0; i < 27; ++i)
-        for (int j = i + 1; j < 27; ++j)
-            if (users[order[j]] > users[order[i]]) { const int tmp = order[i]; order[i] = order[j]; order[j] = tmp; }
-    bool touched[8] = {false, false, false, false, false, false, false, false};
-    int ng = 0, slot = 0;
-    for (int oi = 0; oi < 27; ++oi) {
-        const int t = order[oi];
-        if (users[t] == 0) continue;
-        for (int c = 0; c < 8;) {
-            if (pair_k[c][t] < 0) { ++c; continue; }
-            int c1 = c;
-            while (c1 < 8 && pair_k[c1][t] >= 0 && touched[c1] == touched[c] && (c1 - c + 1) * NOUT <= 256) ++c1;
-            MVS_REQUIRE(ng < 27 && slot + (c1 - c) <= 27, "deconv3d_s2: group table overflow");
-            p.grp_td[ng] = t / 9; p.grp_th[ng] = t / 3 % 3; p.grp_tw[ng] = t % 3;
-            p.grp_class0[ng] = c; p.grp_ncls[ng] = c1 - c; p.grp_slot0[ng] = slot; p.grp_first[ng] = touched[c] ? 0 : 1;
-            for (int cc = c; cc < c1; ++cc) { p.tap_k[slot++] = pair_k[cc][t]; touched[cc] = true; }
-            ++ng;
-            c = c1;
-        }
-    }
-    MVS_REQUIRE(slot == 27, "deconv3d_s2: %d filter slots filled", slot);
-    p.n_groups = ng;
-    for (int g = ng; g < 27; ++g) { p.grp_td[g] = p.grp_th[g] = p.grp_tw[g] = p.grp_class0[g] = p.grp_ncls[g] = p.grp_slot0[g] = p.grp_first[g] = 0; }
-    return MVSB200_OK;
+// 32-byte global loads / stores (sm_100: ld/st.global.v8.b32): one instruction per 16-channel bf16 piece of a voxel row
+struct U8 { uint32_t v[8]; };
+__device__ __forceinline__ U8 ld_u8(const void* p) {
+    U8 r;
+    asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7]) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_u8(void* p, const U8& r) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r.v[0]), "r"(r.v[1]), "r"(r.v[2]), "r"(r.v[3]),
+                 "r"(r.v[4]), "r"(r.v[5]), "r"(r.v[6]), "r"(r.v[7]) : "memory");
 }
 
-// The same (class, tap) pairs arranged for ONE MMA PER INPUT SHIFT.  Per axis one output parity reads both input shifts (bit
+
+// ---- stride-2 transposed convolution: the 27 (output-parity class, filter tap) pairs ---------------------------------
+//   out[2J + par] = sum over the filter taps k with (par + pad - k) even of W[k] . in[J + (par + pad - k)/2]   (per axis)
+// Slab tap t = (par + pad - k)/2 + 1 per axis (input index J + t - 1); for pad in {1, 2} only t = 1, 2 occur.  Classes that
+// read the same INPUT SHIFT (td,th,tw) share the A operand of the MMA.  The table below arranges the pairs for ONE MMA PER
+// INPUT SHIFT.  Per axis one output parity reads both input shifts (bit
 // u = 1) and the other only the main one; the 8 classes are placed in Gray-code order of (u_d, u_h, u_w), so the classes that
 // read a given shift occupy a short RANGE of accumulator blocks -- the MMA of the shift covers the whole range, blocks of
 // classes that do not read the shift get an all-zero filter slot (tap index 27 of the packed weights).  8 MMAs per K step

@@ -190,8 +190,8 @@ def conv_transpose3d_s2(x, w, pads, out_dims):
         if min(Jd, Jh, Jw) > 0:
             work += 2.0 * bin(masks[c]).count("1") * cin * cout * B * Jd * Jh * Jw
     if n_rows <= 32 and os.environ.get("MVSB200_DECONV", "fused") != "classes" and hasattr(_lib.load(), "mvsb200_deconv3d_s2_fwd"):
-        wp = torch.zeros(27, n_rows, cin, dtype=torch.bfloat16, device=x.device)
-        wp[:, :cout] = wk.to(torch.bfloat16)
+        wp = torch.zeros(28, n_rows, cin, dtype=torch.bfloat16, device=x.device)     # tap 27: zeros (see DeconvWide, tc_common.cuh)
+        wp[:27, :cout] = wk.to(torch.bfloat16)
         ys = (ctypes.c_int64 * 4)(sB, sD, sH, sW)
         with _timed("deconv3d_s2_tc", work):
             _lib.call("mvsb200_deconv3d_s2_fwd", x_cl.data_ptr(), wp.data_ptr(), y.data_ptr(), B, md, mh, mw, cin, D, h, wd, cout,

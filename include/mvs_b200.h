@@ -169,7 +169,7 @@ int mvsb200_conv3d_s2_wgrad_lines(const void* big, const void* small, float* gw,
 /* Stride-2 TRANSPOSED convolution forward in ONE launch (ConvTranspose3d k=3, scripts/model.py:229-234, used at :115-121):
  *   out[2J + par] = sum over the taps k with (par + pad - k) even of W[k] . in[J + (par + pad - k)/2] per axis.
  * All 8 output-parity classes are accumulated side by side in TMEM and written interleaved, so every line of the canvas is
- * written once, contiguously.  x: [B, Di, Hi, Wi, Cin] bf16 (the central box); w_packed: [27, n_rows, Cin] bf16 with tap k
+ * written once, contiguously.  x: [B, Di, Hi, Wi, Cin] bf16 (the central box); w_packed: [28, n_rows, Cin] bf16 (tap 27 = zeros) with tap k
  * = (kd,kh,kw) of the transposed-conv weight, rows = output channels (n_rows 16 or 32); y: voxel row of output (b,z,y,x) at
  * y + b*ys[0] + z*ys[1] + y*ys[2] + x*ys[3] elements (HOST int64), written for z < Do, y < Ho, x < Wo; pad in {1,2}. */
 int mvsb200_deconv3d_s2_fwd(const void* x, const void* w_packed, void* y, int B, int Di, int Hi, int Wi, int Cin,
