@@ -127,6 +127,53 @@ __global__ void __launch_bounds__(kFinSlices * 2 * kMaxC) bn_finalize_kernel(con
     }
 }
 
+// Statistics finalize + everything per-channel that follows it in a train-mode BatchNorm (scripts/model.py:242-247,
+// torch.nn.BatchNorm semantics): mean, biased variance, invstd, the affine map y = x*scale + shift, and the running
+// statistics update (momentum, unbiased variance, num_batches_tracked) -- one launch instead of a dozen [C]-sized
+// elementwise kernels per BatchNorm (the step had ~1000 launches of a few microseconds each around 160 real ones).
+struct BnAffineOut {
+    float *mean, *var, *invstd, *scale, *shift;
+    float *running_mean, *running_var;       // may be null
+    long long* num_batches_tracked;          // may be null
+};
+__global__ void __launch_bounds__(kFinSlices * 2 * kMaxC) bn_finalize_affine_kernel(const float* __restrict__ partials, int nblocks,
+                                                                                   int C, double inv_m, double unbias,
+                                                                                   const float* __restrict__ gamma,
+                                                                                   const float* __restrict__ beta, double eps,
+                                                                                   double momentum, BnAffineOut o) {
+    __shared__ double s_acc[kFinSlices][2 * kMaxC];
+    const int col = threadIdx.x % (2 * kMaxC), slice = threadIdx.x / (2 * kMaxC);
+    if (col < 2 * C) {
+        double a = 0.0;
+        for (int k = slice; k < nblocks; k += kFinSlices) a += (double)partials[(size_t)k * 2 * C + col];
+        s_acc[slice][col] = a;
+    }
+    __syncthreads();
+    const int c = threadIdx.x;
+    if (c == 0 && o.num_batches_tracked) *o.num_batches_tracked += 1;
+    if (c >= C) return;
+    double a = 0.0, b = 0.0;
+#pragma unroll
+    for (int s = 0; s < kFinSlices; ++s) { a += s_acc[s][c]; b += s_acc[s][C + c]; }
+    const double mean = a * inv_m;
+    double var = b * inv_m - mean * mean;
+    var = var > 0.0 ? var : 0.0;
+    // the values downstream kernels read are the fp32 ones: derive invstd / scale / shift from the ROUNDED mean and variance,
+    // as the elementwise fp32 expressions this replaces did
+    const float meanf = (float)mean, varf = (float)var;
+    const float invstd = rsqrtf(varf + (float)eps);
+    const float scale = gamma[c] * invstd;
+    o.mean[c] = meanf;
+    o.var[c] = varf;
+    o.invstd[c] = invstd;
+    o.scale[c] = scale;
+    o.shift[c] = beta[c] - meanf * scale;
+    if (o.running_mean) {
+        o.running_mean[c] = (float)((1.0 - momentum) * (double)o.running_mean[c] + momentum * (double)meanf);
+        o.running_var[c] = (float)((1.0 - momentum) * (double)o.running_var[c] + momentum * (double)varf * unbias);
+    }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kBnThreads) bn_relu_fwd_kernel(const T* __restrict__ x, const float* __restrict__ scale,
                                                                  const float* __restrict__ shift, T* __restrict__ y,
@@ -610,4 +657,41 @@ extern "C" int mvsb200_bn_relu_bwd_crop(const void* x, int x_dtype, const void* 
     if (x_dtype == MVSB200_F32 && g_dtype == MVSB200_BF16)
         return bn_bwd_crop_impl<float, __nv_bfloat16>(x, gy, scale, shift, mean, invstd, gamma, workspace, dbeta, dgamma, dx, relu, M, C, B, cb, st);
     MVS_FAIL(MVSB200_E_BADARG, "bn_relu_bwd_crop: bad dtypes %d / %d", x_dtype, g_dtype);
+}
+
+/* bn_stats (+ geometry) followed by the whole per-channel algebra of a train-mode BatchNorm in ONE finalize launch: mean, biased
+ * variance, invstd = 1/sqrt(var + eps), scale = gamma*invstd, shift = beta - mean*scale, and -- when running_mean is given --
+ * the running statistics update of torch.nn.BatchNorm (momentum, unbiased variance M/(M-1), num_batches_tracked += 1). */
+extern "C" int mvsb200_bn_stats_affine(const void* x, int dtype, int64_t M, int C, float* workspace, const int* geo12,
+                                       const float* gamma, const float* beta, double eps, double momentum, float* running_mean,
+                                       float* running_var, int64_t* num_batches_tracked, float* mean, float* var, float* invstd,
+                                       float* scale, float* shift, void* stream) {
+    if (int rc = check_bn(x, M, C, "bn_stats_affine")) return rc;
+    MVS_REQUIRE(workspace && mean && var && invstd && scale && shift && gamma && beta, "bn_stats_affine: null vector");
+    MVS_REQUIRE((running_mean == nullptr) == (running_var == nullptr), "bn_stats_affine: running_mean and running_var go together");
+    MVS_REQUIRE(dtype == MVSB200_F32 || dtype == MVSB200_BF16, "bn_stats_affine: bad dtype %d", dtype);
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long n_chunks = (long long)M * C / 8;
+    const int grid = grid_for(n_chunks);
+    if (geo12) {
+        CropBox cb; int64_t B;
+        if (int rc = make_box(geo12, M, &B, &cb)) return rc;
+        set_cshift(&cb, C);
+        if (dtype == MVSB200_BF16)
+            bn_stats_geo_kernel<__nv_bfloat16><<<grid, kBnThreads, 0, st>>>((const __nv_bfloat16*)x, n_chunks, C, workspace, cb);
+        else
+            bn_stats_geo_kernel<float><<<grid, kBnThreads, 0, st>>>((const float*)x, n_chunks, C, workspace, cb);
+    } else {
+        if (dtype == MVSB200_BF16)
+            bn_stats_kernel<__nv_bfloat16><<<grid, kBnThreads, 0, st>>>((const __nv_bfloat16*)x, n_chunks, C, workspace);
+        else
+            bn_stats_kernel<float><<<grid, kBnThreads, 0, st>>>((const float*)x, n_chunks, C, workspace);
+    }
+    MVS_CHECK_LAUNCH("bn_stats");
+    BnAffineOut o{mean, var, invstd, scale, shift, running_mean, running_var, reinterpret_cast<long long*>(num_batches_tracked)};
+    bn_finalize_affine_kernel<<<1, kFinSlices * 2 * kMaxC, 0, st>>>(workspace, grid, C, 1.0 / (double)M,
+                                                                     M > 1 ? (double)M / (double)(M - 1) : 1.0, gamma, beta, eps,
+                                                                     momentum, o);
+    MVS_CHECK_LAUNCH("bn_finalize_affine");
+    return MVSB200_OK;
 }

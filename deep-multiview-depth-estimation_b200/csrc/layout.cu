@@ -54,3 +54,40 @@ extern "C" int mvsb200_widen_rows_8to16_bf16(const void* src, void* dst, int64_t
     MVS_CHECK_LAUNCH("widen_rows_8to16");
     return MVSB200_OK;
 }
+
+// ---- filter packing ---------------------------------------------------------------------------------------------------
+// The tensor-core kernels want their 3x3x3 filters as bf16 [slot][row][col] matrices (K-major B operands): tap-major, rows =
+// output channels padded to a multiple of 16, columns = contraction channels, in the tap order of the kernel (natural, depth
+// tap innermost for the kdn form, flipped for data gradients, a trailing all-zero tap for the transposed convolutions), from
+// the fp32 parameter [dim0][dim1][3][3][3] of the layer (scripts/model.py:223-234).  Written with torch this is 3..6
+// elementwise launches per filter and step (zeros, permute-copy, cast, slice-assign, re-order); here ONE launch:
+//     out[s][r][c] = w[r*sr + (c + c0)*sc + tap[s]]   for r < rows_real, c < cols_real, tap[s] >= 0;  0 otherwise.
+struct PackTaps { int tap[32]; };
+__global__ void __launch_bounds__(256) pack_filter_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int n_slots,
+                                                          int n_rows, int n_cols, int rows_real, int cols_real, int c0, int sr,
+                                                          int sc, const __grid_constant__ PackTaps taps) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_slots * n_rows * n_cols) return;
+    const int c = i % n_cols, r = (i / n_cols) % n_rows, s = i / (n_cols * n_rows);
+    const int t = taps.tap[s];
+    float v = 0.f;
+    if (t >= 0 && r < rows_real && c < cols_real) v = w[(size_t)r * sr + (size_t)(c + c0) * sc + t];
+    out[i] = __float2bfloat16(v);
+}
+
+extern "C" int mvsb200_pack_filter(const float* w, void* out, int n_slots, int n_rows, int n_cols, int rows_real, int cols_real,
+                                   int c0, int sr, int sc, const int* taps_host, void* stream) {
+    MVS_REQUIRE(w && out && taps_host, "pack_filter: null pointer");
+    MVS_REQUIRE(n_slots >= 1 && n_slots <= 32 && n_rows >= 1 && n_cols >= 1 && rows_real >= 0 && rows_real <= n_rows &&
+                cols_real >= 0 && cols_real <= n_cols && c0 >= 0 && sr >= 1 && sc >= 1, "pack_filter: bad shape");
+    PackTaps t;
+    for (int s = 0; s < 32; ++s) {
+        t.tap[s] = s < n_slots ? taps_host[s] : -1;
+        MVS_REQUIRE(t.tap[s] >= -1 && t.tap[s] < 27, "pack_filter: tap %d out of range", t.tap[s]);
+    }
+    const int n = n_slots * n_rows * n_cols;
+    pack_filter_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, reinterpret_cast<__nv_bfloat16*>(out), n_slots, n_rows,
+                                                                         n_cols, rows_real, cols_real, c0, sr, sc, t);
+    MVS_CHECK_LAUNCH("pack_filter");
+    return MVSB200_OK;
+}

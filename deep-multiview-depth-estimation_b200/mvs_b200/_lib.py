@@ -22,6 +22,7 @@ _SIGNATURES = {
     "mvsb200_launch_count": (_c.c_uint64, []),
     "mvsb200_nchw_to_nhwc_f32": (_I, [_P, _P, _I, _I, _I, _I, _P]),
     "mvsb200_nhwc_to_nchw_f32": (_I, [_P, _P, _I, _I, _I, _I, _P]),
+    "mvsb200_pack_filter": (_I, [_P, _P] + [_I] * 8 + [_P, _P]),
     "mvsb200_widen_rows_8to16_bf16": (_I, [_P, _P, _c.c_int64, _P]),
     "mvsb200_warp_variance_fwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "mvsb200_warp_variance_bwd": (_I, [_P, _P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _I, _P]),
@@ -55,6 +56,7 @@ _SIGNATURES = {
     "mvsb200_bn_workspace_floats": (_c.c_int64, []),
     "mvsb200_bn_stats": (_I, [_P, _I, _c.c_int64, _I, _P, _P, _P, _P]),
     "mvsb200_bn_relu_fwd": (_I, [_P, _I, _P, _P, _P, _I, _c.c_int64, _I, _P]),
+    "mvsb200_bn_stats_affine": (_I, [_P, _I, _c.c_int64, _I, _P, _P, _P, _P, _c.c_double, _c.c_double, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "mvsb200_bn_stats_geo": (_I, [_P, _I, _c.c_int64, _I, _P, _P, _P, _P, _P]),
     "mvsb200_bn_relu_fwd_crop": (_I, [_P, _I, _P, _P, _P, _I, _c.c_int64, _I, _P, _P]),
     "mvsb200_bn_relu_bwd_crop": (_I, [_P, _I, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _c.c_int64, _I, _P, _P]),

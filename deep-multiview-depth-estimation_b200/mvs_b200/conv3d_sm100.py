@@ -28,18 +28,43 @@ def _n_rows(c):
     return 16 if c <= 16 else (32 if c <= 32 else 64)
 
 
+_NAT = list(range(27))                       # filter taps in their natural (kd, kh, kw) order
+_FLIP = [26 - t for t in range(27)]          # ... flipped along all three axes (data gradients)
+
+
+def _kdn_order(taps):
+    """Slots [(kh, kw)][kd] of the kdn kernels from a natural-order tap list."""
+    return [taps[kd * 9 + khw] for khw in range(9) for kd in range(3)]
+
+
+def _pack(w, rows_dim, n_rows, taps, n_cols=None, c0=0, cols_real=None, out=None):
+    """The bf16 [slot][row][col] operand of the tensor-core kernels from the layer's parameter w [d0, d1, 3, 3, 3] in ONE launch
+    (mvsb200_pack_filter): rows = channel dimension `rows_dim` of w (zero rows up to n_rows), columns = the other one
+    (columns c0 .. c0 + cols_real, zero columns up to n_cols), slot s = tap taps[s] (-1: an all-zero slot)."""
+    import ctypes
+    w = w.detach()
+    if w.dtype != torch.float32 or not w.is_contiguous():
+        w = w.float().contiguous()
+    d0, d1 = w.shape[:2]
+    rows_real, sr, sc, cols_all = (d0, 27 * d1, 27, d1) if rows_dim == 0 else (d1, 27, 27 * d1, d0)
+    cols_real = cols_all - c0 if cols_real is None else cols_real
+    n_cols = cols_real if n_cols is None else n_cols
+    if out is None:
+        out = torch.empty((len(taps), n_rows, n_cols), dtype=torch.bfloat16, device=w.device)
+    _lib.call("mvsb200_pack_filter", w.data_ptr(), out.data_ptr(), len(taps), n_rows, n_cols, min(rows_real, n_rows), cols_real, c0,
+              sr, sc, (ctypes.c_int * len(taps))(*taps), _stream())
+    return out
+
+
 def pack_filter(w: torch.Tensor) -> torch.Tensor:
     """[Cout, Cin, 3, 3, 3] -> bf16 [27, n_rows, Cin]: tap-major (kd, kh, kw), output channel (zero rows up to n_rows),
     input channel -- the K-major B operand the kernel keeps resident in shared memory."""
-    co, ci = w.shape[:2]
-    wp = torch.zeros(27, _n_rows(co), ci, dtype=torch.bfloat16, device=w.device)
-    wp[:, :co] = w.detach().permute(2, 3, 4, 0, 1).reshape(27, co, ci).to(torch.bfloat16)
-    return wp
+    return _pack(w, 0, _n_rows(w.shape[0]), _NAT)
 
 
 def pack_filter_dgrad(w: torch.Tensor) -> torch.Tensor:
     """Filter of the data gradient: taps flipped, channel roles swapped ([Cin, Cout] per tap)."""
-    return pack_filter(w.detach().flip(2, 3, 4).transpose(0, 1))
+    return _pack(w, 1, _n_rows(w.shape[1]), _FLIP)
 
 
 def _supported(cin, cout):
@@ -54,26 +79,34 @@ def _S1_FORM():
     return form if form == "taps" or hasattr(_lib.load(), "mvsb200_conv3d_s1_fwd_kdn") else "taps"
 
 
-def _launch(x_cl, wp, cout, out_dims, off, k_alg=None, cin_kernel=None):
-    """k_alg: the contraction channels that carry data (algorithmic FLOPs are counted on them; an 8-channel volume runs on the
-    K = 16 kernel but does the work of k_alg = 8).  cin_kernel: channels of the packed filter when they exceed the volume's
-    (8-channel rows, kdn form: the kernel reads the missing channels as zeros)."""
+def _launch(x_cl, w, role, out_dims, off):
+    """Stride-1 convolution of x_cl with the layer weight w [Cout, Cin, 3, 3, 3]: role "fwd" (rows = Cout, contraction over Cin)
+    or "dgrad" (x_cl is the output gradient: taps flipped, rows = Cin, contraction over Cout).  An 8-channel volume runs on the
+    K = 16 kernel: the packed filter gets 8 zero columns and -- kdn form -- the kernel's TMA box reads the missing channels as
+    zeros; the one-MMA-per-tap form needs the widened copy.  Algorithmic FLOPs are counted on the channels that carry data."""
     B, cin, Di, Hi, Wi = x_cl.shape
     Do, Ho, Wo = out_dims
-    k_alg = cin if k_alg is None else k_alg
-    cin_w = cin if cin_kernel is None else cin_kernel
+    cout = w.shape[0] if role == "fwd" else w.shape[1]
+    n_rows = _n_rows(cout)
+    cin_k = max(cin, 16)
+    taps = _NAT if role == "fwd" else _FLIP
+    rows_dim = 0 if role == "fwd" else 1
     y = torch.empty((B, cout, Do, Ho, Wo), dtype=torch.bfloat16, device=x_cl.device, memory_format=torch.channels_last_3d)
     if _S1_FORM() == "kdn":
         # depth tap folded into the MMA N extent: filter as [(kh,kw)][kd][rows][Cin]
-        n_rows = wp.shape[1]
-        wk = wp.view(3, 3, 3, n_rows, cin_w).permute(1, 2, 0, 3, 4).contiguous()
-        with _timed("conv3d_s1_tc", 2.0 * 27 * k_alg * cout * B * Do * Ho * Wo):
+        wk = _pack(w, rows_dim, n_rows, _kdn_order(taps), n_cols=cin_k)
+        with _timed("conv3d_s1_tc", 2.0 * 27 * cin * cout * B * Do * Ho * Wo):
             _lib.call("mvsb200_conv3d_s1_fwd_kdn", x_cl.data_ptr(), wk.data_ptr(), y.data_ptr(), B, Di, Hi, Wi, cin, Do, Ho, Wo,
                       cout, cout, n_rows, off, off, off, _stream())
         return y
-    with _timed("conv3d_s1_tc", 2.0 * 27 * k_alg * cout * B * Do * Ho * Wo):
-        _lib.call("mvsb200_conv3d_s1_fwd", x_cl.data_ptr(), wp.data_ptr(), y.data_ptr(), B, Di, Hi, Wi, cin, Do, Ho, Wo,
-                  cout, cout, wp.shape[1], off, off, off, _stream())
+    wp = _pack(w, rows_dim, n_rows, taps, n_cols=cin_k)
+    if cin_k != cin:
+        x16 = torch.empty((B, 16, Di, Hi, Wi), dtype=torch.bfloat16, device=x_cl.device, memory_format=torch.channels_last_3d)
+        _lib.call("mvsb200_widen_rows_8to16_bf16", x_cl.data_ptr(), x16.data_ptr(), B * Di * Hi * Wi, _stream())
+        x_cl = x16
+    with _timed("conv3d_s1_tc", 2.0 * 27 * cin * cout * B * Do * Ho * Wo):
+        _lib.call("mvsb200_conv3d_s1_fwd", x_cl.data_ptr(), wp.data_ptr(), y.data_ptr(), B, Di, Hi, Wi, cin_k, Do, Ho, Wo,
+                  cout, cout, n_rows, off, off, off, _stream())
     return y
 
 
@@ -83,7 +116,7 @@ class _Conv3dS1(torch.autograd.Function):
         x_cl = x.detach().contiguous(memory_format=torch.channels_last_3d)
         D, H, W = x.shape[2:]
         out_dims = (D, H, W) if pad == 1 else (D - 2, H - 2, W - 2)
-        y = _launch(x_cl, pack_filter(w), w.shape[0], out_dims, -pad)
+        y = _launch(x_cl, w, "fwd", out_dims, -pad)
         ctx.save_for_backward(x_cl, w)
         ctx.pad = pad
         return y
@@ -102,19 +135,9 @@ def _s1_dgrad(gy, w, pad, x_shape):
     filter (gy: bf16 channel-last)."""
     cout, cin = w.shape[:2]
     off = -1 if pad == 1 else -2
-    if _supported(cout, cin):          # roles swap: the gradient volume has Cout channels, the result Cin
-        return _launch(gy, pack_filter_dgrad(w), cin, tuple(x_shape[2:]), off)
-    if cout == 8 and _supported(16, cin):
-        # 8-channel gradient rows (K = 8 < UMMA K = 16): the kernel's TMA box is 16 channels wide and the 8 beyond the voxel row
-        # arrive as zeros (out-of-bounds fill), the filter gets zero rows to match -- no widened copy of the gradient volume
-        w16 = torch.zeros((16,) + tuple(w.shape[1:]), dtype=w.dtype, device=w.device)
-        w16[:8] = w.detach()
-        if _S1_FORM() == "kdn":
-            return _launch(gy, pack_filter_dgrad(w16), cin, tuple(x_shape[2:]), off, k_alg=8, cin_kernel=16)
-        B, _, Do, Ho, Wo = gy.shape
-        gy16 = torch.empty((B, 16, Do, Ho, Wo), dtype=torch.bfloat16, device=gy.device, memory_format=torch.channels_last_3d)
-        _lib.call("mvsb200_widen_rows_8to16_bf16", gy.data_ptr(), gy16.data_ptr(), B * Do * Ho * Wo, _stream())
-        return _launch(gy16, pack_filter_dgrad(w16), cin, tuple(x_shape[2:]), off, k_alg=8)
+    if _supported(cout, cin) or (cout == 8 and _supported(16, cin)):
+        # roles swap: the gradient volume has Cout channels, the result Cin
+        return _launch(gy, w, "dgrad", tuple(x_shape[2:]), off)
     return torch.nn.grad.conv3d_input(x_shape, w.to(gy.dtype), gy, padding=pad)
 
 
@@ -179,7 +202,6 @@ def conv_transpose3d_s2(x, w, pads, out_dims):
     cout = w.shape[1]
     D, h, wd = out_dims
     n_rows = _n_rows(cout)
-    wk = w.detach().permute(2, 3, 4, 1, 0).reshape(27, cout, cin)                 # [k][co][ci]
     y = torch.empty((B, cout, D, h, wd), dtype=torch.bfloat16, device=x.device, memory_format=torch.channels_last_3d)
     sB, sD, sH, sW = y.stride(0), y.stride(2), y.stride(3), y.stride(4)
     _, masks = _deconv_class_tables(pads, x.device)
@@ -190,14 +212,14 @@ def conv_transpose3d_s2(x, w, pads, out_dims):
         if min(Jd, Jh, Jw) > 0:
             work += 2.0 * bin(masks[c]).count("1") * cin * cout * B * Jd * Jh * Jw
     if n_rows <= 32 and os.environ.get("MVSB200_DECONV", "fused") != "classes" and hasattr(_lib.load(), "mvsb200_deconv3d_s2_fwd"):
-        wp = torch.zeros(28, n_rows, cin, dtype=torch.bfloat16, device=x.device)     # tap 27: zeros (see DeconvWide, tc_common.cuh)
-        wp[:27, :cout] = wk.to(torch.bfloat16)
+        wp = _pack(w, 1, n_rows, _NAT + [-1])            # [k][co][ci] from [Cin, Cout, ...]; slot 27: zeros (DeconvWide, tc_common.cuh)
         ys = (ctypes.c_int64 * 4)(sB, sD, sH, sW)
         with _timed("deconv3d_s2_tc", work):
             _lib.call("mvsb200_deconv3d_s2_fwd", x_cl.data_ptr(), wp.data_ptr(), y.data_ptr(), B, md, mh, mw, cin, D, h, wd, cout,
                       n_rows, int(pads[0]), int(pads[1]), int(pads[2]), ys, _stream())
         return y
     idx, masks = _deconv_class_tables(pads, x.device)
+    wk = w.detach().permute(2, 3, 4, 1, 0).reshape(27, cout, cin)                 # [k][co][ci]
     wz = torch.cat([wk, wk.new_zeros(1, cout, cin)], 0)
     wp = torch.zeros(8, 27, n_rows, cin, dtype=torch.bfloat16, device=x.device)
     wp[:, :, :cout] = wz[idx].to(torch.bfloat16)
@@ -285,7 +307,6 @@ class _ConvTranspose3dS2(torch.autograd.Function):
         if any(1 + a > b for a, b in zip(m, n_o)):
             raise _lib.MvsB200Error(f"transposed-conv gradient: box {m} does not fit the strided window {n_o}")
         inner = (slice(None), slice(None)) + tuple(slice(1, 1 + a) for a in m)
-        wb = w.detach().to(torch.bfloat16)
         if ctx.needs_input_grad[0]:
             cin_t, cout_t = w.shape[:2]
             if (cout_t in _CIN_OK or (cout_t == 8 and cin_t <= 32)) and cin_t % 8 == 0:
@@ -295,14 +316,13 @@ class _ConvTranspose3dS2(torch.autograd.Function):
                 B = gy.shape[0]
                 n_rows = (cin_t + 15) // 16 * 16
                 gx = torch.empty(x_cl.shape, dtype=torch.bfloat16, device=gy.device, memory_format=torch.channels_last_3d)
-                if cout_t == 8:
-                    wb = torch.cat([wb, torch.zeros_like(wb)], 1)
+                wpk = _pack(w, 0, n_rows, _NAT, n_cols=max(cout_t, 16))
                 with _timed("conv3d_s2_tc", 2.0 * 27 * cin_t * cout_t * x_cl.numel() / cin_t):
-                    _lib.call("mvsb200_conv3d_s2_fwd", gy.data_ptr(), pack_filter_rows(wb, n_rows).data_ptr(), gx.data_ptr(), B,
+                    _lib.call("mvsb200_conv3d_s2_fwd", gy.data_ptr(), wpk.data_ptr(), gx.data_ptr(), B,
                               gy.shape[2], gy.shape[3], gy.shape[4], cout_t, m[0], m[1], m[2], cin_t, cin_t, n_rows,
                               pads[0], pads[1], pads[2], _stream())
             else:
-                gx = F.conv3d(gy, wb, None, 2, P2)[inner]             # weight [Cin, Cout, ...] read as out = Cin, in = Cout
+                gx = F.conv3d(gy, w.detach().to(torch.bfloat16), None, 2, P2)[inner]   # weight [Cin, Cout, ...] read as out = Cin, in = Cout
         if ctx.needs_input_grad[1]:
             cin_t, cout_t = w.shape[:2]
             mode = _s2_wgrad_mode(gy.shape, x_cl.shape)
@@ -320,10 +340,7 @@ class _ConvTranspose3dS2(torch.autograd.Function):
 
 # ---- stride-2 convolution on the central box (the stacked branches conv_{1,2,3}_0) ----------------------------------
 def pack_filter_rows(w: torch.Tensor, n_rows: int) -> torch.Tensor:
-    co, ci = w.shape[:2]
-    wp = torch.zeros(27, n_rows, ci, dtype=torch.bfloat16, device=w.device)
-    wp[:, :co] = w.detach().permute(2, 3, 4, 0, 1).reshape(27, co, ci).to(torch.bfloat16)
-    return wp
+    return _pack(w, 0, n_rows, _NAT)
 
 
 def _kc_chunks(widths):
@@ -361,13 +378,13 @@ def conv_transpose3d_s2_kc(x, widths, w_t, pads, out_dims, out=None, accumulate=
     if out is None:
         out = torch.empty((B, cout, D, h, wd), dtype=torch.bfloat16, device=x.device, memory_format=torch.channels_last_3d)
         accumulate = False
-    wk = w_t.detach().permute(2, 3, 4, 1, 0).reshape(27, cout, ctot).to(torch.bfloat16)          # [k][co][ci]
-    parts = []
+    # per chunk [28][n_rows][n]: [k][co][ci] from w_t [Cin_total, Cout, ...], slot 27 = zeros (filter slots of classes a shift
+    # does not serve), the chunks one after the other
+    wpk = torch.empty(28 * n_rows * ctot, dtype=torch.bfloat16, device=x.device)
+    pos = 0
     for o, n in zip(offs, ns):
-        wp = torch.zeros(28, n_rows, n, dtype=torch.bfloat16, device=x.device)       # tap 27: zeros (filter slots of classes a
-        wp[:27, :cout] = wk[:, :, o:o + n]                                            # shift does not serve)
-        parts.append(wp.reshape(-1))
-    wpk = torch.cat(parts)
+        _pack(w_t, 1, n_rows, _NAT + [-1], c0=o, cols_real=n, out=wpk[pos:pos + 28 * n_rows * n])
+        pos += 28 * n_rows * n
     ys = (ctypes.c_int64 * 4)(out.stride(0), out.stride(2), out.stride(3), out.stride(4))
     kc_off = (ctypes.c_int * 3)(*(offs + [0] * (3 - len(offs))))
     kc_n = (ctypes.c_int * 3)(*(ns + [0] * (3 - len(ns))))
@@ -506,7 +523,7 @@ class _EntryConvs(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w00, w_cat, pads, out_dims, splits, holder):
         x_cl = x.detach().contiguous(memory_format=torch.channels_last_3d)
-        y0 = _launch(x_cl, pack_filter(w00), w00.shape[0], tuple(x_cl.shape[2:]), -1)
+        y0 = _launch(x_cl, w00, "fwd", tuple(x_cl.shape[2:]), -1)
         outs = _s2box_forward(x_cl, w_cat, pads, out_dims, splits, holder)
         ctx.save_for_backward(x_cl, w00, w_cat)
         ctx.pads, ctx.out_dims, ctx.splits, ctx.holder = tuple(pads), tuple(out_dims), splits, holder
@@ -531,6 +548,7 @@ class _EntryConvs(torch.autograd.Function):
 
 class Tcgen05ConvBackend:
     name = "tcgen05"
+    fp32_weights = True      # takes the layers' fp32 parameters as they are: the filter-packing kernel does the bf16 rounding
 
     @staticmethod
     def conv3d_s2_box(x, w, pads, out_dims, splits=None):
@@ -579,14 +597,14 @@ class Tcgen05ConvBackend:
         if (stride == 1 and x.is_cuda and x.dtype == torch.bfloat16 and pad in ((0, 0, 0), (1, 1, 1))
                 and _supported(x.shape[1], w.shape[0]) and min(x.shape[2:]) >= 3):
             return _Conv3dS1.apply(x, w, pad[0])
-        return conv_backends.TorchConvBackend.conv3d(x, w, stride, padding)
+        return conv_backends.TorchConvBackend.conv3d(x, w if w.dtype == x.dtype else w.to(x.dtype), stride, padding)
 
     @staticmethod
     def conv_transpose3d_alloc(x, w, stride, padding, out_dims):
         if (stride == 2 and x.is_cuda and x.dtype == torch.bfloat16 and x.shape[1] in _CIN_OK and w.shape[1] % 8 == 0
                 and 8 <= w.shape[1] <= 64 and all(p in (1, 2) for p in padding)):
             return _ConvTranspose3dS2.apply(x, w, tuple(int(p) for p in padding), tuple(int(n) for n in out_dims))
-        return conv_backends.TorchConvBackend.conv_transpose3d_alloc(x, w, stride, padding, out_dims)
+        return conv_backends.TorchConvBackend.conv_transpose3d_alloc(x, w if w.dtype == x.dtype else w.to(x.dtype), stride, padding, out_dims)
 
     @classmethod
     def conv_transpose3d(cls, x, w, stride, padding, out_dims):

@@ -335,7 +335,9 @@ class DepthSlabCostVolumeReg:
         ta, tb = plan.tbox[r]
         rg = [(plan.lo, plan.hi, plan.L), central_region(h), central_region(w)]      # per-axis box geometry
         dims = (D, h, w)
-        W_ = lambda name: reg._w(name, dt)
+        # a backend that packs its own filters takes the fp32 parameters as they are (as CostVolumeReg.logits does)
+        wdt = torch.float32 if getattr(be, "fp32_weights", False) else dt
+        W_ = lambda name: reg._w(name, dt if name == "conv_out" else wdt)
 
         # ---- cost-volume planes of this rank (own + halo), swept locally
         k0, k1 = plan.cost_planes(r)

@@ -23,13 +23,9 @@ class BatchNormReLU2d(nn.BatchNorm2d):
     def forward(self, x):
         if x.is_cuda and self.training and self.num_features in (8, 16, 32, 64) and x.dtype in (torch.float32, torch.bfloat16):
             from . import ops
-            y, mean, var = ops.batchnorm_relu_train(x.unsqueeze(2), self.weight, self.bias, self.eps, relu=True)
-            n = x.numel() // x.shape[1]
-            with torch.no_grad():
-                m = self.momentum
-                self.running_mean.mul_(1 - m).add_(mean, alpha=m)
-                self.running_var.mul_(1 - m).add_(var * (n / max(n - 1, 1)), alpha=m)
-                self.num_batches_tracked += 1
+            y, _, _ = ops.batchnorm_relu_train(x.unsqueeze(2), self.weight, self.bias, self.eps, relu=True,
+                                               running=(self.running_mean, self.running_var, self.num_batches_tracked),
+                                               momentum=self.momentum)
             return y.squeeze(2)
         return F.relu(super().forward(x))
 

@@ -333,7 +333,7 @@ class _BatchNormReLU(torch.autograd.Function):
     `crop` = ((d0,d1),(h0,h1),(w0,w1)): y (and the incoming gradient) exist only on that box of the canvas."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, eps, relu, crop, canvas):
+    def forward(ctx, x, weight, bias, eps, relu, crop, canvas, running=None, momentum=0.1):
         _need_cuda(x, "BatchNorm input")
         _need_cuda(weight, "BatchNorm weight")
         xr, _, C = _rows(x.detach())
@@ -345,19 +345,23 @@ class _BatchNormReLU(torch.autograd.Function):
         M = B * canvas[0] * canvas[1] * canvas[2]
         box = crop if crop is not None else tuple((0, n) for n in canvas)
         geo = None if plain else _geo12(alloc, canvas, box)
-        mean = torch.empty(C, dtype=torch.float32, device=dev)
-        var = torch.empty(C, dtype=torch.float32, device=dev)
+        # one [5, C] buffer: mean, biased variance, invstd, scale, shift -- all written by the statistics' finalize launch,
+        # which also performs the running-statistics update of torch.nn.BatchNorm when `running` is given
+        vec = torch.empty((5, C), dtype=torch.float32, device=dev)
+        mean, var, invstd, scale, shift = vec[0], vec[1], vec[2], vec[3], vec[4]
+        gamma = weight.detach().float().contiguous()
+        beta = bias.detach().float().contiguous()
+        rm = rv = nbt = None
+        if running is not None:
+            rm, rv, nbt = running
+            if not (rm.is_cuda and rm.dtype == torch.float32 and rm.is_contiguous() and rv.dtype == torch.float32 and rv.is_contiguous()
+                    and (nbt is None or (nbt.is_cuda and nbt.dtype == torch.int64))):
+                raise _lib.MvsB200Error("BatchNorm running statistics must be contiguous fp32 CUDA tensors (int64 counter)")
         ws = _bn_workspace(dev)
         with _timed("bn_stats"):
-            if canvas == alloc:
-                _lib.call("mvsb200_bn_stats", xr.data_ptr(), _DT[xr.dtype], M, C, ws.data_ptr(), mean.data_ptr(),
-                          var.data_ptr(), _stream())
-            else:
-                _lib.call("mvsb200_bn_stats_geo", xr.data_ptr(), _DT[xr.dtype], M, C, ws.data_ptr(), mean.data_ptr(),
-                          var.data_ptr(), geo, _stream())
-        invstd = torch.rsqrt(var + eps)
-        scale = (weight.detach().float() * invstd).contiguous()
-        shift = (bias.detach().float() - mean * scale).contiguous()
+            _lib.call("mvsb200_bn_stats_affine", xr.data_ptr(), _DT[xr.dtype], M, C, ws.data_ptr(), geo if canvas != alloc else None,
+                      gamma.data_ptr(), beta.data_ptr(), float(eps), float(momentum), _ptr(rm), _ptr(rv), _ptr(nbt), mean.data_ptr(),
+                      var.data_ptr(), invstd.data_ptr(), scale.data_ptr(), shift.data_ptr(), _stream())
         if plain:
             y = torch.empty_like(xr)
             with _timed("bn_relu_fwd"):
@@ -370,7 +374,7 @@ class _BatchNormReLU(torch.autograd.Function):
             with _timed("bn_relu_fwd"):
                 _lib.call("mvsb200_bn_relu_fwd_crop", xr.data_ptr(), _DT[xr.dtype], scale.data_ptr(), shift.data_ptr(),
                           y.data_ptr(), int(relu), M, C, geo, _stream())
-        ctx.save_for_backward(xr, scale, shift, mean, invstd, weight.detach().float().contiguous())
+        ctx.save_for_backward(xr, scale, shift, mean, invstd, gamma)
         ctx.relu, ctx.dims, ctx.geo = bool(relu), (M, C), (None if plain else (alloc, canvas, box))
         ctx.mark_non_differentiable(mean, var)
         return y, mean, var
@@ -397,18 +401,20 @@ class _BatchNormReLU(torch.autograd.Function):
                           scale.data_ptr(), shift.data_ptr(), mean.data_ptr(), invstd.data_ptr(), gamma.data_ptr(),
                           _bn_workspace(dev).data_ptr(), dbeta.data_ptr(), dgamma.data_ptr(), dx.data_ptr(),
                           int(ctx.relu), M, C, _geo12(*ctx.geo), _stream())
-        return dx, dgamma, dbeta, None, None, None, None
+        return dx, dgamma, dbeta, None, None, None, None, None, None
 
 
-def batchnorm_relu_train(x, weight, bias, eps=1e-5, relu=True, crop=None, canvas=None):
+def batchnorm_relu_train(x, weight, bias, eps=1e-5, relu=True, crop=None, canvas=None, running=None, momentum=0.1):
     """-> (y, batch mean [C], biased batch variance [C]); y has x's dtype (fp32 or bf16), channels_last_3d.
     canvas = (D,h,w) <= x's spatial dims: the statistics volume (x may carry allocation slack beyond it);
-    crop = ((d0,d1),(h0,h1),(w0,w1)): full-canvas statistics, y only on that box."""
+    crop = ((d0,d1),(h0,h1),(w0,w1)): full-canvas statistics, y only on that box.
+    running = (running_mean, running_var, num_batches_tracked): updated in place as torch.nn.BatchNorm does in train mode
+    (momentum, unbiased variance), inside the statistics' finalize launch."""
     if crop is not None:
         crop = tuple((int(a), int(b)) for a, b in crop)
     if canvas is not None:
         canvas = tuple(int(n) for n in canvas)
-    return _BatchNormReLU.apply(x, weight, bias, float(eps), bool(relu), crop, canvas)
+    return _BatchNormReLU.apply(x, weight, bias, float(eps), bool(relu), crop, canvas, running, float(momentum))
 
 
 def affine_relu(x, scale, shift, relu=True):

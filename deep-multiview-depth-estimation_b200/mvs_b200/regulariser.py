@@ -121,14 +121,9 @@ class CostVolumeReg(nn.Module):
         torch expressions below serve eval mode and the CPU unit tests of the canvas algebra."""
         if x.is_cuda and bn.training:
             box = None if crop is None else tuple((c.start, c.stop) for c in crop)
-            y, mean, var = ops.batchnorm_relu_train(x, bn.weight, bn.bias, bn.eps, relu=True, crop=box, canvas=canvas)
-            dims_ = tuple(x.shape[2:]) if canvas is None else tuple(canvas)
-            n = x.shape[0] * dims_[0] * dims_[1] * dims_[2]
-            with torch.no_grad():
-                m = bn.momentum
-                bn.running_mean.mul_(1 - m).add_(mean, alpha=m)
-                bn.running_var.mul_(1 - m).add_(var * (n / max(n - 1, 1)), alpha=m)
-                bn.num_batches_tracked += 1
+            # the running statistics (momentum, unbiased variance, counter) are updated inside the statistics' finalize launch
+            y, _, _ = ops.batchnorm_relu_train(x, bn.weight, bn.bias, bn.eps, relu=True, crop=box, canvas=canvas,
+                                               running=(bn.running_mean, bn.running_var, bn.num_batches_tracked), momentum=bn.momentum)
             return y
         if canvas is not None:
             x = x[..., :canvas[0], :canvas[1], :canvas[2]]
@@ -164,6 +159,9 @@ class CostVolumeReg(nn.Module):
             raise ValueError("CostVolumeReg needs D, h, w >= 2")
         dt = torch.bfloat16 if self.precision == "bf16" else torch.float32
         x = cv if cv.dtype == dt else cv.to(dt)
+        # a backend that packs its own filters takes the fp32 parameters as they are (no bf16 copies of the weights, no casts
+        # of their gradients)
+        wdt = torch.float32 if getattr(be, "fp32_weights", False) else dt
         n_full = B * D * h * w
         reg = [central_region(n) for n in dims]
         C = tuple(slice(lo, hi + 1) for lo, hi, _ in reg)                     # central box on the canvas
@@ -172,15 +170,15 @@ class CostVolumeReg(nn.Module):
         # the three stride-2 branches all read cv (model.py:104-110): ONE convolution with the weights stacked along
         # Cout (16+32+64 = 112) reads the cost volume once instead of three times; with conv_0_0 they form one autograd node
         # (the cost volume's gradient is accumulated inside the kernels, not by an elementwise pass of autograd)
-        w_cat = torch.cat([self._w(f"conv_{k}_0", dt) for k in (1, 2, 3)], 0)
+        w_cat = torch.cat([self._w(f"conv_{k}_0", wdt) for k in (1, 2, 3)], 0)
         widths = [self.conv_1_0.out_channels, self.conv_2_0.out_channels, self.conv_3_0.out_channels]
         box_pads, box_dims = tuple(L for _, _, L in reg), tuple(hi - lo + 1 for lo, hi, _ in reg)
         S_parts = None
-        entry = be.entry_convs(x, self._w("conv_0_0", dt), w_cat, box_pads, box_dims, widths) if hasattr(be, "entry_convs") else None
+        entry = be.entry_convs(x, self._w("conv_0_0", wdt), w_cat, box_pads, box_dims, widths) if hasattr(be, "entry_convs") else None
         if entry is not None:
             c00, S_parts = entry
         else:
-            c00 = be.conv3d(x, self._w("conv_0_0", dt), 1, (1, 1, 1))
+            c00 = be.conv3d(x, self._w("conv_0_0", wdt), 1, (1, 1, 1))
         y0 = self._bn_dense(self.BN_0, c00)
 
         # ---- encoder branches: stride-2 conv on C, then stride-1 conv on C (+1 ring for the statistics)
@@ -211,7 +209,7 @@ class CostVolumeReg(nn.Module):
         E_dims = [E_hi[ax] - E_lo[ax] + 1 for ax in range(3)]
         for k, bn in ((1, self.BN_1), (2, self.BN_2), (3, self.BN_3)):
             S = S_split[k]
-            Wk = self._w(f"conv_{k}_1", dt)
+            Wk = self._w(f"conv_{k}_1", wdt)
             if x.is_cuda:
                 # GPU: statistics and normalisation of the box tensors in libmvs_b200.so (K3d), per-channel algebra here
                 if train:
@@ -265,7 +263,7 @@ class CostVolumeReg(nn.Module):
 
         def up(z, name, bn, crop=None):
             # channel-last operands keep the library on its NDHWC kernels (no layout-conversion passes over the canvas)
-            U = be.conv_transpose3d_alloc(z.to(dt).contiguous(memory_format=torch.channels_last_3d), self._w(name, dt), 2, Lp, dims)
+            U = be.conv_transpose3d_alloc(z.to(dt).contiguous(memory_format=torch.channels_last_3d), self._w(name, wdt), 2, Lp, dims)
             return self._bn_dense(bn, U, crop, dims)      # U holds the canvas at its origin (+ up to one slack plane/line/column)
 
         # the transposed convs' canvases are normalised with full-canvas statistics but only their box C is read

@@ -128,6 +128,14 @@ int mvsb200_conv3d_s1_fwd(const void* x, const void* w_packed, void* y, int B, i
                           int Do, int Ho, int Wo, int cout, int y_cs, int n_rows, int off_d, int off_h, int off_w,
                           void* stream);
 
+/* Filter packing in one launch: the fp32 parameter w [dim0][dim1][3][3][3] of a Conv3d / ConvTranspose3d (scripts/model.py:223-234)
+ * -> the bf16 [n_slots][n_rows][n_cols] K-major operand of the tensor-core kernels:
+ *   out[s][r][c] = w[r*sr + (c + c0)*sc + taps[s]] for r < rows_real, c < cols_real, taps[s] >= 0; zero otherwise
+ * (sr / sc: element strides of the row / column channel in w, i.e. 27*dim1 and 27 or the reverse; taps_host: HOST int array of
+ * n_slots entries in 0..26 or -1 = an all-zero slot -- natural, flipped (data gradient), depth-innermost (kdn) orders). */
+int mvsb200_pack_filter(const float* w, void* out, int n_slots, int n_rows, int n_cols, int rows_real, int cols_real,
+                        int c0, int sr, int sc, const int* taps_host, void* stream);
+
 /* [M, 8] bf16 voxel rows -> [M, 16] with channels 8..15 zero: operand of conv_0_0's data gradient (UMMA K = 16). */
 int mvsb200_widen_rows_8to16_bf16(const void* src, void* dst, int64_t M, void* stream);
 
@@ -232,6 +240,15 @@ int mvsb200_bn_relu_bwd(const void* x, int x_dtype, const void* gy, int g_dtype,
                         const float* shift, const float* mean, const float* invstd, const float* gamma,
                         float* workspace, float* dbeta, float* dgamma, void* dx, int relu, int64_t M, int C,
                         void* stream);
+
+/* bn_stats (geo12_host = NULL) or bn_stats_geo followed by the WHOLE per-channel algebra of a train-mode BatchNorm
+ * (torch.nn.BatchNorm3d / 2d as built by scripts/model.py:236-247) in one finalize launch: mean, biased variance,
+ * invstd = 1/sqrt(var + eps), scale = gamma*invstd, shift = beta - mean*scale and, when running_mean / running_var are given,
+ * running = (1 - momentum)*running + momentum*(mean | var*M/(M-1)), *num_batches_tracked += 1 (may be NULL). */
+int mvsb200_bn_stats_affine(const void* x, int dtype, int64_t M, int C, float* workspace, const int* geo12_host,
+                            const float* gamma, const float* beta, double eps, double momentum, float* running_mean,
+                            float* running_var, int64_t* num_batches_tracked, float* mean, float* var, float* invstd,
+                            float* scale, float* shift, void* stream);
 
 /* Geometry-aware variants.  The canvas [D,h,w] (what the statistics are taken over; M = B*D*h*w) sits at the origin
  * of a possibly larger allocation [Da,ha,wa] (the library's stride-2 transposed convolution returns one extra

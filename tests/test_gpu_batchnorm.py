@@ -146,3 +146,35 @@ def test_canvas_inside_larger_allocation():
         assert torch.allclose(y1, y2[sl], atol=1e-5)
         assert torch.allclose(x1.grad, x2.grad, atol=1e-5)
         assert x1.grad[..., 8:, :, :].abs().max() == 0 and x1.grad[..., :, 6:, :].abs().max() == 0
+
+
+@pytest.mark.parametrize("C", [8, 32])
+@pytest.mark.parametrize("geometry", ["plain", "canvas+crop"])
+def test_running_statistics_updated_by_the_finalize_launch(C, geometry):
+    """mvsb200_bn_stats_affine: the statistics' finalize launch also performs the running-statistics update of torch.nn.BatchNorm3d
+    in train mode (momentum, unbiased variance, num_batches_tracked) -- against nn.BatchNorm3d on the same canvas, two passes."""
+    g = torch.Generator().manual_seed(7 * C)
+    canvas = (6, 9, 10)
+    alloc = canvas if geometry == "plain" else (7, 10, 11)
+    ref = torch.nn.BatchNorm3d(C, momentum=0.1).to(DEV).train()
+    with torch.no_grad():
+        ref.weight.copy_(torch.rand(C, generator=g) + 0.5)
+        ref.bias.copy_(torch.randn(C, generator=g))
+    rm, rv = torch.zeros(C, device=DEV), torch.ones(C, device=DEV)
+    nbt = torch.zeros((), dtype=torch.int64, device=DEV)
+    for _ in range(2):
+        x = (torch.randn(2, C, *alloc, generator=g) * 1.5 + 0.3).to(DEV).contiguous(memory_format=torch.channels_last_3d)
+        xc = x[..., :canvas[0], :canvas[1], :canvas[2]]
+        yr = F.relu(ref(xc.contiguous()))
+        if geometry == "plain":
+            y, mean, var = ops.batchnorm_relu_train(x, ref.weight, ref.bias, ref.eps, running=(rm, rv, nbt), momentum=0.1)
+        else:
+            crop = ((1, 5), (2, 8), (0, 10))
+            y, mean, var = ops.batchnorm_relu_train(x, ref.weight, ref.bias, ref.eps, crop=crop, canvas=canvas, running=(rm, rv, nbt),
+                                                    momentum=0.1)
+            yr = yr[..., 1:5, 2:8, 0:10]
+        assert torch.allclose(y, yr, rtol=1e-4, atol=1e-5)
+        assert torch.allclose(mean, xc.mean((0, 2, 3, 4)), rtol=1e-5, atol=1e-6)
+    assert int(nbt) == 2 == int(ref.num_batches_tracked)
+    assert torch.allclose(rm, ref.running_mean, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(rv, ref.running_var, rtol=1e-5, atol=1e-6)

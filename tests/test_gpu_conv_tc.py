@@ -191,8 +191,36 @@ def test_stride2_conv_on_the_central_box(cin, cout, dims, wgrad, monkeypatch):
     n1 = mvs_b200.launch_count()
     y.backward(gy)
     if wgrad == "lines" and dims[2] % 2 == 0 and cin <= 32:
-        # backward: one weight-gradient launch + one data-gradient launch -- no library convolution
-        assert mvs_b200.launch_count() - n1 == 2
+        # backward: one weight-gradient launch + one data-gradient launch (+ one filter-packing launch per K chunk of the
+        # transposed convolution) -- no library convolution
+        assert mvs_b200.launch_count() - n1 == 2 + (3 if cout == 112 else 1)
     ref.backward(gy.float())
     assert _rel(x1.grad, x2.grad) < TOL
     assert _rel(w1.grad, w2.grad) < 2 * TOL
+
+
+@pytest.mark.parametrize("co,ci", [(8, 32), (16, 16), (112, 32), (64, 64)])
+def test_filter_packing_kernel(co, ci):
+    """mvsb200_pack_filter (one launch per filter) against the torch expressions it replaces: natural, flipped + transposed (data
+    gradient), depth-innermost (kdn) tap orders, zero rows / columns / slots."""
+    from mvs_b200 import conv3d_sm100 as c
+    g = torch.Generator().manual_seed(co * 100 + ci)
+    w = torch.randn(co, ci, 3, 3, 3, generator=g).to(DEV)
+    n_rows = (co + 15) // 16 * 16
+    ref = torch.zeros(27, n_rows, ci, dtype=torch.bfloat16, device=DEV)
+    ref[:, :co] = w.permute(2, 3, 4, 0, 1).reshape(27, co, ci).to(torch.bfloat16)
+    assert torch.equal(c._pack(w, 0, n_rows, c._NAT), ref)
+    wd = w.flip(2, 3, 4).transpose(0, 1)                                     # [ci, co, ...]: the data gradient's filter
+    n_rows_d = (ci + 15) // 16 * 16
+    refd = torch.zeros(27, n_rows_d, max(co, 16), dtype=torch.bfloat16, device=DEV)
+    refd[:, :ci, :co] = wd.permute(2, 3, 4, 0, 1).reshape(27, ci, co).to(torch.bfloat16)
+    got = c._pack(w, 1, n_rows_d, c._FLIP, n_cols=max(co, 16))
+    assert torch.equal(got, refd)
+    kdn = refd.view(3, 3, 3, n_rows_d, -1).permute(1, 2, 0, 3, 4).reshape(27, n_rows_d, -1)
+    assert torch.equal(c._pack(w, 1, n_rows_d, c._kdn_order(c._FLIP), n_cols=max(co, 16)), kdn)
+    # transposed-convolution layout [k][co][ci] from [Cin, Cout, ...] with a trailing zero slot, a column window
+    wt = torch.randn(ci, co, 3, 3, 3, generator=g).to(DEV)
+    c0, n = (16, 16) if ci >= 32 else (0, ci)
+    reft = torch.zeros(28, n_rows, n, dtype=torch.bfloat16, device=DEV)
+    reft[:27, :co] = wt.permute(2, 3, 4, 1, 0).reshape(27, co, ci)[:, :, c0:c0 + n].to(torch.bfloat16)
+    assert torch.equal(c._pack(wt, 1, n_rows, c._NAT + [-1], c0=c0, cols_real=n), reft)
