@@ -53,6 +53,30 @@ __device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&v)[8]) {
                                                pack_bf16x2(v[6], v[7]));
 }
 
+// Raw 8-channel chunks: the loads of kUnrollA independent chunks are issued back to back and unpacked afterwards (one 16-byte
+// load in flight per thread keeps ~16 KB per SM in flight: ~3 TB/s at HBM latency, measured; the index decode of the next
+// chunks overlaps the loads of the first).
+constexpr int kUnrollA = 4;
+template <typename T> struct Raw8;
+template <> struct Raw8<float> { float4 a, b; };
+template <> struct Raw8<__nv_bfloat16> { uint4 u; };
+__device__ __forceinline__ Raw8<float> ldraw8(const float* p) {
+    Raw8<float> r; r.a = *reinterpret_cast<const float4*>(p); r.b = *reinterpret_cast<const float4*>(p + 4); return r;
+}
+__device__ __forceinline__ Raw8<__nv_bfloat16> ldraw8(const __nv_bfloat16* p) {
+    Raw8<__nv_bfloat16> r; r.u = *reinterpret_cast<const uint4*>(p); return r;
+}
+__device__ __forceinline__ void zero8(Raw8<float>& r) { r.a = make_float4(0.f, 0.f, 0.f, 0.f); r.b = r.a; }
+__device__ __forceinline__ void zero8(Raw8<__nv_bfloat16>& r) { r.u = make_uint4(0u, 0u, 0u, 0u); }
+__device__ __forceinline__ void unpack8(const Raw8<float>& r, float (&v)[8]) {
+    v[0] = r.a.x; v[1] = r.a.y; v[2] = r.a.z; v[3] = r.a.w; v[4] = r.b.x; v[5] = r.b.y; v[6] = r.b.z; v[7] = r.b.w;
+}
+__device__ __forceinline__ void unpack8(const Raw8<__nv_bfloat16>& r, float (&v)[8]) {
+    const uint32_t w[4] = {r.u.x, r.u.y, r.u.z, r.u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(w[i] << 16); v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+}
+
 // dense row index -> coordinates (32-bit arithmetic: rows < 2^31 is checked on the host)
 __device__ __forceinline__ void decode_row(unsigned r, const FastDiv& fD, const FastDiv& fh, const FastDiv& fw, int& b, int& d,
                                            int& y, int& x) {
@@ -116,13 +140,27 @@ __global__ void __launch_bounds__(kThreadsA) channel_sums_kernel(const T* __rest
     const int cshift = cpr == 1 ? 0 : (cpr == 2 ? 1 : (cpr == 4 ? 2 : 3));
     const int cg = (int)(i0 & (unsigned)(cpr - 1));
     float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (unsigned i = i0; i < n_chunks; i += gridDim.x * kThreadsA) {
-        int b, d, y, xx;
-        decode_row(i >> cshift, v.fD, v.fh, v.fw, b, d, y, xx);
-        float val[8];
-        load8(x + b * v.sb + d * v.sd + y * v.sh + xx * v.sw + cg * 8, val);
+    const unsigned stride = gridDim.x * kThreadsA;
+    for (unsigned i = i0; i < n_chunks; i += kUnrollA * stride) {
+        Raw8<T> raw[kUnrollA];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) { s[k] += val[k]; q[k] = fmaf(val[k], val[k], q[k]); }
+        for (int u = 0; u < kUnrollA; ++u) {
+            const unsigned j = i + u * stride;             // (j < i: wrapped past 2^32, beyond the end)
+            if (j < n_chunks && j >= i) {
+                int b, d, y, xx;
+                decode_row(j >> cshift, v.fD, v.fh, v.fw, b, d, y, xx);
+                raw[u] = ldraw8(x + b * v.sb + d * v.sd + y * v.sh + xx * v.sw + cg * 8);
+            } else {
+                zero8(raw[u]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kUnrollA; ++u) {
+            float val[8];
+            unpack8(raw[u], val);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { s[k] += val[k]; q[k] = fmaf(val[k], val[k], q[k]); }
+        }
     }
     reduce_to_partial(s, q, cpr, C, partials + (size_t)blockIdx.x * 2 * C);
 }
@@ -163,6 +201,17 @@ __device__ __forceinline__ bool load_in(const T* __restrict__ x, const Geo& g, i
 }
 
 template <typename T>
+__device__ __forceinline__ bool ldraw_in(const T* __restrict__ x, const Geo& g, int b, int od, int oy, int ox, int cg, Raw8<T>& r) {
+    const int id = od + g.oo[0] - g.io[0], iy = oy + g.oo[1] - g.io[1], ix = ox + g.oo[2] - g.io[2];
+    if ((unsigned)id < (unsigned)g.in.D && (unsigned)iy < (unsigned)g.in.h && (unsigned)ix < (unsigned)g.in.w) {
+        r = ldraw8(x + b * g.in.sb + id * g.in.sd + iy * g.in.sh + ix * g.in.sw + cg * 8);
+        return true;
+    }
+    zero8(r);
+    return false;
+}
+
+template <typename T>
 __global__ void __launch_bounds__(kThreadsA) affine_relu_geo_fwd_kernel(const T* __restrict__ x, Geo g, unsigned n_out_chunks, int C,
                                                                         const float* __restrict__ scale,
                                                                         const float* __restrict__ shift, T* __restrict__ y, int relu) {
@@ -173,17 +222,32 @@ __global__ void __launch_bounds__(kThreadsA) affine_relu_geo_fwd_kernel(const T*
     float sc[8], sh[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) { sc[k] = scale[cg * 8 + k]; sh[k] = shift[cg * 8 + k]; }
-    for (unsigned i = i0; i < n_out_chunks; i += gridDim.x * kThreadsA) {
-        int b, d, yy, xx;
-        decode_row(i >> cshift, g.fod[0], g.fod[1], g.fod[2], b, d, yy, xx);
-        float val[8];
-        load_in(x, g, b, d, yy, xx, cg, val);
+    const unsigned stride = gridDim.x * kThreadsA;
+    for (unsigned i = i0; i < n_out_chunks; i += kUnrollA * stride) {
+        Raw8<T> raw[kUnrollA];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            val[k] = fmaf(val[k], sc[k], sh[k]);
-            if (relu) val[k] = fmaxf(val[k], 0.f);
+        for (int u = 0; u < kUnrollA; ++u) {
+            const unsigned j = i + u * stride;
+            if (j < n_out_chunks && j >= i) {
+                int b, d, yy, xx;
+                decode_row(j >> cshift, g.fod[0], g.fod[1], g.fod[2], b, d, yy, xx);
+                ldraw_in(x, g, b, d, yy, xx, cg, raw[u]);
+            }
         }
-        store8(y + (size_t)i * 8, val);
+#pragma unroll
+        for (int u = 0; u < kUnrollA; ++u) {
+            const unsigned j = i + u * stride;
+            if (j < n_out_chunks && j >= i) {
+                float val[8];
+                unpack8(raw[u], val);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    val[k] = fmaf(val[k], sc[k], sh[k]);
+                    if (relu) val[k] = fmaxf(val[k], 0.f);
+                }
+                store8(y + (size_t)j * 8, val);
+            }
+        }
     }
 }
 
@@ -202,17 +266,34 @@ __global__ void __launch_bounds__(kThreadsA) affine_relu_geo_bwd_reduce_kernel(c
 #pragma unroll
     for (int k = 0; k < 8; ++k) { sc[k] = scale[cg * 8 + k]; sh[k] = shift[cg * 8 + k]; }
     float sg[8] = {0, 0, 0, 0, 0, 0, 0, 0}, sgx[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (unsigned i = i0; i < n_out_chunks; i += gridDim.x * kThreadsA) {
-        int b, d, yy, xx;
-        decode_row(i >> cshift, g.fod[0], g.fod[1], g.fod[2], b, d, yy, xx);
-        float val[8], gv[8];
-        load_in(x, g, b, d, yy, xx, cg, val);
-        load8(gy + (size_t)i * 8, gv);
+    const unsigned stride = gridDim.x * kThreadsA;
+    for (unsigned i = i0; i < n_out_chunks; i += kUnrollA * stride) {
+        Raw8<T> rx[kUnrollA];
+        Raw8<TG> rg[kUnrollA];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const float gk = (!relu || fmaf(val[k], sc[k], sh[k]) > 0.f) ? gv[k] : 0.f;
-            sg[k] += gk;
-            sgx[k] = fmaf(gk, val[k], sgx[k]);
+        for (int u = 0; u < kUnrollA; ++u) {
+            const unsigned j = i + u * stride;
+            if (j < n_out_chunks && j >= i) {
+                int b, d, yy, xx;
+                decode_row(j >> cshift, g.fod[0], g.fod[1], g.fod[2], b, d, yy, xx);
+                ldraw_in(x, g, b, d, yy, xx, cg, rx[u]);
+                rg[u] = ldraw8(gy + (size_t)j * 8);
+            } else {
+                zero8(rx[u]);
+                zero8(rg[u]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kUnrollA; ++u) {
+            float val[8], gv[8];
+            unpack8(rx[u], val);
+            unpack8(rg[u], gv);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const float gk = (!relu || fmaf(val[k], sc[k], sh[k]) > 0.f) ? gv[k] : 0.f;
+                sg[k] += gk;
+                sgx[k] = fmaf(gk, val[k], sgx[k]);
+            }
         }
     }
     reduce_to_partial(sg, sgx, cpr, C, partials + (size_t)blockIdx.x * 2 * C);
@@ -272,23 +353,46 @@ __global__ void __launch_bounds__(kThreadsA) box_bn_relu_bwd_apply_kernel(const 
     float sc[8], sh[8], av[8], bv[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) { sc[k] = scale[cg * 8 + k]; sh[k] = shift[cg * 8 + k]; av[k] = a[cg * 8 + k]; bv[k] = b2[cg * 8 + k]; }
-    for (unsigned i = i0; i < n_in_chunks; i += gridDim.x * kThreadsA) {
-        int b, d, yy, xx;
-        decode_row(i >> cshift, g.in.fD, g.in.fh, g.in.fw, b, d, yy, xx);
-        const int od = d + g.io[0] - g.oo[0], oy = yy + g.io[1] - g.oo[1], ox = xx + g.io[2] - g.oo[2];
-        float val[8], out[8];
-        load8(x + b * g.in.sb + d * g.in.sd + yy * g.in.sh + xx * g.in.sw + cg * 8, val);
+    const unsigned stride = gridDim.x * kThreadsA;
+    for (unsigned i = i0; i < n_in_chunks; i += kUnrollA * stride) {
+        Raw8<T> rx[kUnrollA];
+        Raw8<TG> rg[kUnrollA];
+        long long dst[kUnrollA];                         // element offset of the chunk in gx, < 0: beyond the end
+        bool has_g[kUnrollA];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) out[k] = fmaf(bv[k], val[k], av[k]);
-        if ((unsigned)od < (unsigned)g.od[0] && (unsigned)oy < (unsigned)g.od[1] && (unsigned)ox < (unsigned)g.od[2]) {
-            float gv[8];
-            const size_t orow = (((size_t)b * g.od[0] + od) * g.od[1] + oy) * g.od[2] + ox;
-            load8(gy + (orow * cpr + cg) * 8, gv);
-#pragma unroll
-            for (int k = 0; k < 8; ++k)
-                if (!relu || fmaf(val[k], sc[k], sh[k]) > 0.f) out[k] = fmaf(gv[k], sc[k], out[k]);
+        for (int u = 0; u < kUnrollA; ++u) {
+            const unsigned j = i + u * stride;
+            dst[u] = -1;
+            has_g[u] = false;
+            if (j < n_in_chunks && j >= i) {
+                int b, d, yy, xx;
+                decode_row(j >> cshift, g.in.fD, g.in.fh, g.in.fw, b, d, yy, xx);
+                const int od = d + g.io[0] - g.oo[0], oy = yy + g.io[1] - g.oo[1], ox = xx + g.io[2] - g.oo[2];
+                rx[u] = ldraw8(x + b * g.in.sb + d * g.in.sd + yy * g.in.sh + xx * g.in.sw + cg * 8);
+                dst[u] = b * osb + d * osd + yy * osh + xx * osw + cg * 8;
+                if ((unsigned)od < (unsigned)g.od[0] && (unsigned)oy < (unsigned)g.od[1] && (unsigned)ox < (unsigned)g.od[2]) {
+                    const size_t orow = (((size_t)b * g.od[0] + od) * g.od[1] + oy) * g.od[2] + ox;
+                    rg[u] = ldraw8(gy + (orow * cpr + cg) * 8);
+                    has_g[u] = true;
+                }
+            }
         }
-        store8(gx + b * osb + d * osd + yy * osh + xx * osw + cg * 8, out);
+#pragma unroll
+        for (int u = 0; u < kUnrollA; ++u) {
+            if (dst[u] < 0) continue;
+            float val[8], out[8];
+            unpack8(rx[u], val);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) out[k] = fmaf(bv[k], val[k], av[k]);
+            if (has_g[u]) {
+                float gv[8];
+                unpack8(rg[u], gv);
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    if (!relu || fmaf(val[k], sc[k], sh[k]) > 0.f) out[k] = fmaf(gv[k], sc[k], out[k]);
+            }
+            store8(gx + dst[u], out);
+        }
     }
 }
 
