@@ -401,11 +401,20 @@ __global__ void __launch_bounds__(kBnThreads) bn_stats_geo_kernel(const T* __res
     const int cpr = C / 8;
     float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const long long stride = (long long)gridDim.x * kBnThreads;
-    for (long long i = (long long)blockIdx.x * kBnThreads + threadIdx.x; i < n_canvas_chunks; i += stride) {
-        float v[8];
-        Chunk<T>::load(x + canvas_to_alloc(i, cpr, cb) * 8, v);
+    for (long long i = (long long)blockIdx.x * kBnThreads + threadIdx.x; i < n_canvas_chunks; i += kBnUnroll * stride) {
+        typename Chunk<T>::Raw raw[kBnUnroll];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) { s[k] += v[k]; q[k] = fmaf(v[k], v[k], q[k]); }
+        for (int u = 0; u < kBnUnroll; ++u)
+            if (i + u * stride < n_canvas_chunks) raw[u] = Chunk<T>::ldraw(x + canvas_to_alloc(i + u * stride, cpr, cb) * 8);
+#pragma unroll
+        for (int u = 0; u < kBnUnroll; ++u) {
+            if (i + u * stride < n_canvas_chunks) {
+                float v[8];
+                Chunk<T>::unpack(raw[u], v);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { s[k] += v[k]; q[k] = fmaf(v[k], v[k], q[k]); }
+            }
+        }
     }
     block_reduce_to_partial(s, q, cpr, C, partials + (size_t)blockIdx.x * 2 * C);
 }
@@ -421,15 +430,24 @@ __global__ void __launch_bounds__(kBnThreads) bn_relu_fwd_crop_kernel(const T* _
 #pragma unroll
     for (int k = 0; k < 8; ++k) { sc[k] = scale[cg * 8 + k]; sh[k] = shift[cg * 8 + k]; }
     const long long stride = (long long)gridDim.x * kBnThreads;
-    for (long long i = i0; i < n_box_chunks; i += stride) {
-        float v[8];
-        Chunk<T>::load(x + box_to_canvas(i, cpr, cb) * 8, v);
+    for (long long i = i0; i < n_box_chunks; i += kBnUnroll * stride) {
+        typename Chunk<T>::Raw raw[kBnUnroll];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            v[k] = fmaf(v[k], sc[k], sh[k]);
-            if (relu) v[k] = fmaxf(v[k], 0.f);
+        for (int u = 0; u < kBnUnroll; ++u)
+            if (i + u * stride < n_box_chunks) raw[u] = Chunk<T>::ldraw(x + box_to_canvas(i + u * stride, cpr, cb) * 8);
+#pragma unroll
+        for (int u = 0; u < kBnUnroll; ++u) {
+            if (i + u * stride < n_box_chunks) {
+                float v[8];
+                Chunk<T>::unpack(raw[u], v);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    v[k] = fmaf(v[k], sc[k], sh[k]);
+                    if (relu) v[k] = fmaxf(v[k], 0.f);
+                }
+                Chunk<T>::store(y + (i + u * stride) * 8, v);
+            }
         }
-        Chunk<T>::store(y + i * 8, v);
     }
 }
 
@@ -456,15 +474,27 @@ __global__ void __launch_bounds__(kBnThreads) bn_relu_bwd_reduce_crop_kernel(
         const unsigned b = fd_divmod(r, cb.f_dc, ud);
         const size_t xbase = ((((size_t)b * cb.Da + ud + cb.d0) * cb.ha + uy + cb.h0) * cb.wa + cb.w0) * cpr;
         const size_t gbase = (size_t)line * line_chunks;
-        for (int j = lane; j < line_chunks; j += 32) {
-            float v[8], g[8];
-            Chunk<TX>::load(x + (xbase + j) * 8, v);
-            Chunk<TG>::load(gy + (gbase + j) * 8, g);
+        for (int j0 = lane; j0 < line_chunks; j0 += 32 * kBnUnroll) {
+            typename Chunk<TX>::Raw rx[kBnUnroll];
+            typename Chunk<TG>::Raw rg[kBnUnroll];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const float gk = (!relu || fmaf(v[k], sc[k], sh[k]) > 0.f) ? g[k] : 0.f;
-                sg[k] += gk;
-                sgx[k] = fmaf(gk, (v[k] - mu[k]) * is[k], sgx[k]);
+            for (int u = 0; u < kBnUnroll; ++u) {
+                const int j = j0 + 32 * u;
+                if (j < line_chunks) { rx[u] = Chunk<TX>::ldraw(x + (xbase + j) * 8); rg[u] = Chunk<TG>::ldraw(gy + (gbase + j) * 8); }
+            }
+#pragma unroll
+            for (int u = 0; u < kBnUnroll; ++u) {
+                if (j0 + 32 * u < line_chunks) {
+                    float v[8], g[8];
+                    Chunk<TX>::unpack(rx[u], v);
+                    Chunk<TG>::unpack(rg[u], g);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const float gk = (!relu || fmaf(v[k], sc[k], sh[k]) > 0.f) ? g[k] : 0.f;
+                        sg[k] += gk;
+                        sgx[k] = fmaf(gk, (v[k] - mu[k]) * is[k], sgx[k]);
+                    }
+                }
             }
         }
     }

@@ -368,11 +368,12 @@ struct WgradParams {
     int BW, L;                      // slab pitch (voxels per line incl. 2 halo), gy lines per tile
     int tiles_x, tiles_y;
     int dchunk, nchunks, n_items;
-    int co0;                        // first gy channel handled by this launch
+    int n_roles;                    // (gy channel chunk, depth taps) combinations shared out over the CTAs (blockIdx % n_roles)
+    int role_co0[8];                // first gy channel of a role
+    int role_kd[8];                 // depth taps of a role (bit kd); the others' MMAs are not issued
     int cout;                       // real output channels of the layer (row length of gW)
     int slab_bytes, gy_bytes;       // per ring slot / per gy stage, multiples of 1024
     int ksteps;                     // ceil((L+2)*BW / 16)
-    unsigned kd_mask;               // depth taps to compute (bit kd); the others' MMAs are not issued
     int tap_map[27];                // kernel tap (kd*3+kh)*3+kw -> row block of gw it is added to, -1 = dropped
     float* gw;                      // [27][CIN][cout] fp32, accumulated into
 };
@@ -402,10 +403,16 @@ conv3d_s1_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles = p.tiles_x * p.tiles_y;
     // accumulator blocks only for the depth taps this launch computes (kd_mask): block index = rank of kd inside the mask
-    const int nkd = __popc(p.kd_mask & 7u);
+    // ROLES: the CTAs of one launch may split the (gy channel chunk, depth tap) combinations among them (blockIdx % n_roles) and
+    // walk the items together -- the x slabs and gy tiles the roles share are then served by L2 instead of one DRAM pass per
+    // launch (64 -> 64: six combinations)
+    const int role = (int)blockIdx.x % p.n_roles, walker = (int)blockIdx.x / p.n_roles, n_walkers = (int)gridDim.x / p.n_roles;
+    const int co0 = p.role_co0[role];
+    const unsigned kd_mask = (unsigned)p.role_kd[role];
+    const int nkd = __popc(kd_mask & 7u);
     uint32_t tmem_cols = 32;
     while ((int)tmem_cols < nkd * KWB * UN) tmem_cols <<= 1;
-    auto kd_slot = [&](int kd) { return __popc(p.kd_mask & ((1u << kd) - 1u)); };
+    auto kd_slot = [&](int kd) { return __popc(kd_mask & ((1u << kd) - 1u)); };
 
     // zero what TMA never writes: the slab tails (read by the last K step) and the whole gy stages (padding, halo columns)
     {
@@ -452,7 +459,7 @@ conv3d_s1_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid
         const uint32_t box_bytes = (uint32_t)ROWX * p.BW * (p.L + 2);
         const uint32_t line_bytes = (uint32_t)ROWG * (p.BW - 2);
         int gs = 0, gp = 0;
-        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        for (int item = walker; item < p.n_items; item += n_walkers) {
             int b, d_begin, nd, x0, y0;
             decode(item, b, d_begin, nd, x0, y0);
             int s = 0;
@@ -472,7 +479,7 @@ conv3d_s1_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid
                 if (elect_one()) {
                     mbar_expect_tx(gfull + st, line_bytes * p.L);
                     for (int j = 0; j < p.L; ++j)      // line j -> rows (2+j)*BW .. (2+j)*BW + BW-3 (out of range => zeros)
-                        tma_load_5d(gy_smem + (size_t)st * p.gy_bytes + (size_t)(2 + j) * p.BW * ROWG, &tm_g, gfull + st, p.co0, x0,
+                        tma_load_5d(gy_smem + (size_t)st * p.gy_bytes + (size_t)(2 + j) * p.BW * ROWG, &tm_g, gfull + st, co0, x0,
                                     y0 + j, d_begin + d, b);
                 }
                 __syncwarp();
@@ -488,7 +495,7 @@ conv3d_s1_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid
         const uint32_t slab16 = (uint32_t)p.slab_bytes >> 4, gy16 = (uint32_t)p.gy_bytes >> 4;
         int gs0 = 0, gp = 0, landed = 0;
         uint32_t first = 1;                              // the CTA's first gy plane initialises the accumulators
-        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        for (int item = walker; item < p.n_items; item += n_walkers) {
             int b, d_begin, nd, x0, y0;
             decode(item, b, d_begin, nd, x0, y0);
             for (int d = 0; d < nd; ++d, ++gp) {
@@ -500,7 +507,7 @@ conv3d_s1_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid
                     const uint32_t g_lo = gy_lo + (uint32_t)st * gy16;
 #pragma unroll
                     for (int kd = 0; kd < 3; ++kd) {
-                        if (!(p.kd_mask >> kd & 1u)) continue;
+                        if (!(kd_mask >> kd & 1u)) continue;
                         const uint32_t s_lo = slab_lo + (uint32_t)((gs0 + d + kd) % kSlots3) * slab16;
 #pragma unroll
                         for (int blk = 0; blk < KWB; ++blk) {
@@ -537,7 +544,7 @@ conv3d_s1_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid
         constexpr int ATOMS = 128 / CIN;                 // kw atoms per block
         const int kw_in_blk = row / CIN, ci = row % CIN;
         for (int kd = 0; kd < 3; ++kd) {
-            if (!(p.kd_mask >> kd & 1u)) continue;
+            if (!(kd_mask >> kd & 1u)) continue;
 #pragma unroll
             for (int blk = 0; blk < KWB; ++blk) {
                 const int kw = blk * 2 + kw_in_blk;
@@ -551,10 +558,10 @@ conv3d_s1_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid
 #pragma unroll
                         for (int k = 0; k < 16; ++k) {
                             const int col = c0 + k, n = col / NCO, co = col % NCO;     // atom n <-> kh = 2 - n
-                            if (n < 3 && p.co0 + co < p.cout) {
+                            if (n < 3 && co0 + co < p.cout) {
                                 const int slot = p.tap_map[(kd * 3 + (2 - n)) * 3 + kw];
                                 if (slot >= 0)
-                                    atomicAdd(p.gw + ((size_t)slot * CIN + ci) * p.cout + p.co0 + co, __uint_as_float(v[k]));
+                                    atomicAdd(p.gw + ((size_t)slot * CIN + ci) * p.cout + co0 + co, __uint_as_float(v[k]));
                             }
                         }
                     }
@@ -600,7 +607,8 @@ WgPlan plan_tiles_wgrad(int Ho, int Wo, int rowx, int rowg, size_t smem_budget) 
 template <int CIN, int NCO>
 int launch_wgrad(const void* x, const void* gy, float* gw, int B, int Di, int Hi, int Wi, int Do, int Ho, int Wo, int cout, int co0,
                  int off_d, int off_h, int off_w, cudaStream_t st, int x_es = 1, int Dx = 0, int Hx = 0, int Wx = 0,
-                 unsigned kd_mask = 7u, const int* tap_map = nullptr) {
+                 unsigned kd_mask = 7u, const int* tap_map = nullptr, int n_roles = 1, const int* role_co0 = nullptr,
+                 const int* role_kd = nullptr) {
     if (x_es == 1) { Dx = Di; Hx = Hi; Wx = Wi; }
     constexpr int ROWX = CIN * 2, ROWG = NCO * 2;
     EncodeTiledFn enc = encode_fn();
@@ -634,9 +642,13 @@ int launch_wgrad(const void* x, const void* gy, float* gw, int B, int Di, int Hi
     WgradParams p;
     p.B = B; p.Do = Do; p.Ho = Ho; p.Wo = Wo; p.off_d = off_d; p.off_h = off_h; p.off_w = off_w;
     p.BW = tp.BW; p.L = tp.L; p.tiles_x = tp.tiles_x; p.tiles_y = tp.tiles_y;
-    p.co0 = co0; p.cout = cout; p.slab_bytes = tp.slab_bytes; p.gy_bytes = tp.gy_bytes;
+    p.cout = cout; p.slab_bytes = tp.slab_bytes; p.gy_bytes = tp.gy_bytes;
+    p.n_roles = n_roles;
+    for (int r = 0; r < 8; ++r) {
+        p.role_co0[r] = role_co0 && r < n_roles ? role_co0[r] : co0;
+        p.role_kd[r] = (role_kd && r < n_roles ? role_kd[r] : (int)kd_mask) & 7;
+    }
     p.ksteps = ((tp.L + 2) * tp.BW + 15) / 16;
-    p.kd_mask = kd_mask & 7u;
     for (int t = 0; t < 27; ++t) p.tap_map[t] = tap_map ? tap_map[t] : t;
     p.gw = gw;
     const long tiles = (long)tp.tiles_x * tp.tiles_y;
@@ -645,19 +657,20 @@ int launch_wgrad(const void* x, const void* gy, float* gw, int B, int Di, int Hi
         int dev = 0, n = 0;
         if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) sms = n;
     }
+    const long walkers = sms / n_roles > 0 ? sms / n_roles : 1;    // CTAs that walk the items (each role has that many)
     long best_cost = -1;
     int best_chunks = 1;
     for (int nc = 1; nc <= Do; ++nc) {
         const int dc = (Do + nc - 1) / nc;
         if ((long)(nc - 1) * dc >= Do) continue;
         const long items = tiles * nc * B;
-        const long cost = ((items + sms - 1) / sms) * (dc + 4);
+        const long cost = ((items + walkers - 1) / walkers) * (dc + 4);
         if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_chunks = nc; }
     }
     p.nchunks = best_chunks;
     p.dchunk = (Do + best_chunks - 1) / best_chunks;
     p.n_items = (int)(tiles * p.nchunks * B);
-    const dim3 grid((unsigned)(p.n_items < sms ? p.n_items : sms), 1, 1);
+    const dim3 grid((unsigned)((p.n_items < walkers ? p.n_items : walkers) * n_roles), 1, 1);
     const size_t smem = 1024 + (size_t)kSlots3 * tp.slab_bytes + 2 * (size_t)tp.gy_bytes + 256;
     MVS_CUDA(cudaFuncSetAttribute(conv3d_s1_wgrad_tc_kernel<CIN, NCO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     conv3d_s1_wgrad_tc_kernel<CIN, NCO><<<grid, kTcThreads, smem, st>>>(tm_x, tm_g, p);
@@ -1699,13 +1712,14 @@ extern "C" int mvsb200_conv3d_s1_wgrad(const void* x, const void* gy, float* gw,
     // (two kw blocks): 32 gy channels fit only with ONE depth tap per launch (2 x 96 columns) -- three launches per channel
     // chunk, each at twice the MMA N extent, instead of one at 16 channels: the A operand (the x slab, 4 KB per MMA) is read
     // from shared memory half as often per flop (measured: conv_3_1 1.03 -> see profiles/r02_k3_notes.md)
-    if (Cin == 64 && cout % 32 == 0) {
+    if (Cin == 64 && cout % 32 == 0 && cout <= 64) {
+        // ONE launch: the (channel chunk, depth tap) combinations are roles of neighbouring CTAs that walk the items together
+        // (the six launches of the earlier form each read x and gy from DRAM)
+        int role_co0[8], role_kd[8], n_roles = 0;
         for (int co0 = 0; co0 < cout; co0 += 32)
-            for (int kd = 0; kd < 3; ++kd) {
-                const int rc = launch_wgrad<64, 32>(x, gy, gw, B, Di, Hi, Wi, Do, Ho, Wo, cout, co0, off_d, off_h, off_w, st, 1, 0, 0, 0, 1u << kd, nullptr);
-                if (rc != MVSB200_OK) return rc;
-            }
-        return MVSB200_OK;
+            for (int kd = 0; kd < 3; ++kd) { role_co0[n_roles] = co0; role_kd[n_roles] = 1 << kd; ++n_roles; }
+        return launch_wgrad<64, 32>(x, gy, gw, B, Di, Hi, Wi, Do, Ho, Wo, cout, 0, off_d, off_h, off_w, st, 1, 0, 0, 0, 1u, nullptr, n_roles,
+                                    role_co0, role_kd);
     }
     const int nco_max = Cin == 64 ? 16 : 32;
     const int nco = cout < nco_max ? cout : nco_max;
