@@ -561,3 +561,80 @@ extern "C" int mvsb200_box_bn_relu_bwd_apply(const void* x, int x_dtype, const i
     MVS_CHECK_LAUNCH("box_bn_relu_bwd_apply");
     return MVSB200_OK;
 }
+
+// ---- per-channel algebra of the box BatchNorm (the stride-2 branches) in one launch each ---------------------------------
+// forward:  mean = s1/n, var = s2/n - mean^2 (the canvas outside the box is zero and counts), r = 1/sqrt(var + eps),
+//           scale = gamma r, shift = beta - mean scale (fp64 inside), running statistics as torch.nn.BatchNorm updates them.
+// backward: from G_scale = sum over the box + external, G_shift likewise:
+//           g_beta = G_shift, G = G_scale - mean G_shift, g_gamma = G r, g_var = -G gamma r^3 / 2,
+//           g_mean = -gamma r G_shift - 2 mean g_var;  a = g_mean / n = dL/d(sum S),  b2 = 2 g_var / n = 2 dL/d(sum S^2).
+// These were ~12 + ~20 [C]-sized torch launches per branch and step.
+namespace {
+__global__ void box_bn_algebra_fwd_kernel(const float* __restrict__ s1, const float* __restrict__ s2, int C, double n,
+                                          const float* __restrict__ gamma, const float* __restrict__ beta, double eps,
+                                          double momentum, float* running_mean, float* running_var, long long* nbt,
+                                          float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean,
+                                          float* __restrict__ var, double* __restrict__ stat64) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c == 0 && nbt) *nbt += 1;
+    if (c >= C) return;
+    const double m = (double)s1[c] / n;
+    double v = (double)s2[c] / n - m * m;
+    v = v > 0.0 ? v : 0.0;
+    const double r = 1.0 / sqrt(v + eps);
+    const double g = (double)gamma[c];
+    scale[c] = (float)(g * r);
+    shift[c] = (float)((double)beta[c] - m * g * r);
+    mean[c] = (float)m;
+    var[c] = (float)v;
+    stat64[c] = m;
+    stat64[C + c] = r;
+    if (running_mean) {
+        running_mean[c] = (float)((1.0 - momentum) * (double)running_mean[c] + momentum * (double)(float)m);
+        running_var[c] = (float)((1.0 - momentum) * (double)running_var[c] + momentum * (double)(float)v * (n > 1.0 ? n / (n - 1.0) : 1.0));
+    }
+}
+__global__ void box_bn_algebra_bwd_kernel(const float* __restrict__ gscale, const float* __restrict__ gshift,
+                                          const float* __restrict__ gscale_ext, const float* __restrict__ gshift_ext,
+                                          const double* __restrict__ stat64, const float* __restrict__ gamma, int C, double n,
+                                          float* __restrict__ a, float* __restrict__ b2, float* __restrict__ g_gamma,
+                                          float* __restrict__ g_beta) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const double m = stat64[c], r = stat64[C + c], g = (double)gamma[c];
+    const double Gsc = (double)gscale[c] + (gscale_ext ? (double)gscale_ext[c] : 0.0);
+    const double Gsh = (double)gshift[c] + (gshift_ext ? (double)gshift_ext[c] : 0.0);
+    const double G = Gsc - m * Gsh;
+    const double g_var = G * g * (-0.5) * r * r * r;
+    const double g_mean = -(g * r) * Gsh - 2.0 * m * g_var;
+    a[c] = (float)(g_mean / n);
+    b2[c] = (float)(2.0 * g_var / n);
+    g_gamma[c] = (float)(G * r);
+    g_beta[c] = (float)Gsh;
+}
+}  // namespace
+
+extern "C" int mvsb200_box_bn_algebra_fwd(const float* s1, const float* s2, int C, double n_full, const float* gamma, const float* beta,
+                                          double eps, double momentum, float* running_mean, float* running_var,
+                                          int64_t* num_batches_tracked, float* scale, float* shift, float* mean, float* var,
+                                          double* stat64, void* stream) {
+    MVS_REQUIRE(s1 && s2 && gamma && beta && scale && shift && mean && var && stat64, "box_bn_algebra_fwd: null pointer");
+    MVS_REQUIRE(C >= 1 && C <= 4096 && n_full >= 1.0, "box_bn_algebra_fwd: bad shape");
+    MVS_REQUIRE((running_mean == nullptr) == (running_var == nullptr), "box_bn_algebra_fwd: running_mean and running_var go together");
+    box_bn_algebra_fwd_kernel<<<(C + 63) / 64, 64, 0, (cudaStream_t)stream>>>(s1, s2, C, n_full, gamma, beta, eps, momentum, running_mean,
+                                                                             running_var, reinterpret_cast<long long*>(num_batches_tracked),
+                                                                             scale, shift, mean, var, stat64);
+    MVS_CHECK_LAUNCH("box_bn_algebra_fwd");
+    return MVSB200_OK;
+}
+
+extern "C" int mvsb200_box_bn_algebra_bwd(const float* gscale, const float* gshift, const float* gscale_ext, const float* gshift_ext,
+                                          const double* stat64, const float* gamma, int C, double n_full, float* a, float* b2,
+                                          float* g_gamma, float* g_beta, void* stream) {
+    MVS_REQUIRE(gscale && gshift && stat64 && gamma && a && b2 && g_gamma && g_beta, "box_bn_algebra_bwd: null pointer");
+    MVS_REQUIRE(C >= 1 && C <= 4096 && n_full >= 1.0, "box_bn_algebra_bwd: bad shape");
+    box_bn_algebra_bwd_kernel<<<(C + 63) / 64, 64, 0, (cudaStream_t)stream>>>(gscale, gshift, gscale_ext, gshift_ext, stat64, gamma, C, n_full,
+                                                                             a, b2, g_gamma, g_beta);
+    MVS_CHECK_LAUNCH("box_bn_algebra_bwd");
+    return MVSB200_OK;
+}

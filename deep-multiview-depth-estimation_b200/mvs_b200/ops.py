@@ -627,36 +627,41 @@ class _BoxBatchNormReLU(torch.autograd.Function):
     gS = g*scale + dL/d(sum S) + 2 S dL/d(sum S^2) -- written into `grad_dest` when given."""
 
     @staticmethod
-    def forward(ctx, S, weight, bias, n_full, eps, in_origin, out_origin, out_dims, grad_dest):
+    def forward(ctx, S, weight, bias, n_full, eps, in_origin, out_origin, out_dims, grad_dest, running=None, momentum=0.1):
         _need_cuda(S, "box BatchNorm input")
         _need_cuda(weight, "BatchNorm weight")
         xv, strides, dims = _box_view(S.detach())
         C = xv.shape[1]
         dev = xv.device
-        s1 = torch.empty(C, dtype=torch.float32, device=dev)
-        s2 = torch.empty(C, dtype=torch.float32, device=dev)
+        sums = torch.empty((2, C), dtype=torch.float32, device=dev)
         with _timed("channel_sums"):
             _lib.call("mvsb200_channel_sums", xv.data_ptr(), _DT[xv.dtype], strides, dims, C, _affine_workspace(dev).data_ptr(),
-                      s1.data_ptr(), s2.data_ptr(), _stream())
-        mean64 = s1.double() / n_full
-        var64 = (s2.double() / n_full - mean64 * mean64).clamp_min(0)
-        r64 = torch.rsqrt(var64 + eps)
-        scale = (weight.detach().double() * r64).float()
-        shift = (bias.detach().double() - mean64 * weight.detach().double() * r64).float()
+                      sums[0].data_ptr(), sums[1].data_ptr(), _stream())
+        # the per-channel algebra (fp64 inside) and the running-statistics update in one launch
+        vec = torch.empty((4, C), dtype=torch.float32, device=dev)
+        scale, shift, mean, var = vec[0], vec[1], vec[2], vec[3]
+        stat64 = torch.empty((2, C), dtype=torch.float64, device=dev)       # mean, 1/sqrt(var + eps): the backward's operands
+        gamma = weight.detach().float().contiguous()
+        beta = bias.detach().float().contiguous()
+        rm = rv = nbt = None
+        if running is not None:
+            rm, rv, nbt = running
+        _lib.call("mvsb200_box_bn_algebra_fwd", sums[0].data_ptr(), sums[1].data_ptr(), C, float(n_full), gamma.data_ptr(),
+                  beta.data_ptr(), float(eps), float(momentum), _ptr(rm), _ptr(rv), _ptr(nbt), scale.data_ptr(), shift.data_ptr(),
+                  mean.data_ptr(), var.data_ptr(), stat64.data_ptr(), _stream())
         B = xv.shape[0]
         y = torch.empty((B, C) + tuple(out_dims), dtype=xv.dtype, device=dev, memory_format=torch.channels_last_3d)
         with _timed("affine_relu_geo_fwd"):
             _lib.call("mvsb200_affine_relu_geo_fwd", xv.data_ptr(), _DT[xv.dtype], strides, _geo13(xv, in_origin, out_origin, out_dims),
                       C, scale.data_ptr(), shift.data_ptr(), y.data_ptr(), 1, _stream())
-        ctx.save_for_backward(xv, scale, shift, mean64, r64, weight.detach().double())
+        ctx.save_for_backward(xv, scale, shift, stat64, gamma)
         ctx.geo, ctx.n_full, ctx.grad_dest = (tuple(in_origin), tuple(out_origin), tuple(out_dims)), float(n_full), grad_dest
-        mean, var = mean64.float(), var64.float()
         ctx.mark_non_differentiable(mean, var)
         return y, scale, shift, mean, var
 
     @staticmethod
     def backward(ctx, gy, g_scale_ext, g_shift_ext, _gm, _gv):
-        xv, scale, shift, mean64, r64, gamma64 = ctx.saved_tensors
+        xv, scale, shift, stat64, gamma = ctx.saved_tensors
         _, strides, _ = _box_view(xv)
         C, dev, n = xv.shape[1], xv.device, ctx.n_full
         if gy is None:
@@ -664,22 +669,17 @@ class _BoxBatchNormReLU(torch.autograd.Function):
         if gy.dtype not in _DT:
             gy = gy.float()
         gy = gy.contiguous(memory_format=torch.channels_last_3d)
-        gscale = torch.empty(C, dtype=torch.float32, device=dev)
-        gshift = torch.empty(C, dtype=torch.float32, device=dev)
+        red = torch.empty((2, C), dtype=torch.float32, device=dev)          # gscale, gshift over the box
         geo = _geo13(xv, *ctx.geo)
         with _timed("box_bn_relu_bwd"):
             _lib.call("mvsb200_box_bn_relu_bwd_reduce", xv.data_ptr(), _DT[xv.dtype], strides, geo, C, scale.data_ptr(), shift.data_ptr(),
-                      gy.data_ptr(), _DT[gy.dtype], _affine_workspace(dev).data_ptr(), gscale.data_ptr(), gshift.data_ptr(), 1, _stream())
-        # per-channel algebra (fp64): scale = gamma r, shift = beta - mean scale, r = rsqrt(var + eps), var = s2/n - mean^2, mean = s1/n
-        G_scale = gscale.double() + (g_scale_ext.double() if g_scale_ext is not None else 0.0)
-        G_shift = gshift.double() + (g_shift_ext.double() if g_shift_ext is not None else 0.0)
-        g_beta = G_shift
-        G_sc = G_scale - mean64 * G_shift
-        g_gamma = G_sc * r64
-        g_var = G_sc * gamma64 * (-0.5) * r64 * r64 * r64
-        g_mean = -(gamma64 * r64) * G_shift - 2.0 * mean64 * g_var
-        a = (g_mean / n).float().contiguous()                   # dL / d(sum S)
-        b2 = (2.0 * g_var / n).float().contiguous()             # 2 dL / d(sum S^2)
+                      gy.data_ptr(), _DT[gy.dtype], _affine_workspace(dev).data_ptr(), red[0].data_ptr(), red[1].data_ptr(), 1, _stream())
+        # per-channel algebra (fp64 inside, one launch): (a, b2) = (dL/d sum S, 2 dL/d sum S^2), gradients of gamma and beta
+        ext = [None if g is None else g.detach().float().contiguous() for g in (g_scale_ext, g_shift_ext)]
+        out = torch.empty((4, C), dtype=torch.float32, device=dev)
+        a, b2, g_gamma, g_beta = out[0], out[1], out[2], out[3]
+        _lib.call("mvsb200_box_bn_algebra_bwd", red[0].data_ptr(), red[1].data_ptr(), _ptr(ext[0]), _ptr(ext[1]), stat64.data_ptr(),
+                  gamma.data_ptr(), C, float(n), a.data_ptr(), b2.data_ptr(), g_gamma.data_ptr(), g_beta.data_ptr(), _stream())
         dest = ctx.grad_dest
         if dest is not None and xv.dtype == torch.bfloat16:
             holder, k = dest
@@ -692,13 +692,14 @@ class _BoxBatchNormReLU(torch.autograd.Function):
         with _timed("box_bn_relu_bwd"):
             _lib.call("mvsb200_box_bn_relu_bwd_apply", xv.data_ptr(), _DT[xv.dtype], strides, geo, C, scale.data_ptr(), shift.data_ptr(),
                       a.data_ptr(), b2.data_ptr(), gy.data_ptr(), _DT[gy.dtype], gx.data_ptr(), ostr, 1, _stream())
-        return gx, g_gamma.float(), g_beta.float(), None, None, None, None, None, None
+        return gx, g_gamma, g_beta, None, None, None, None, None, None, None, None
 
 
-def box_batchnorm_relu(S, weight, bias, n_full, eps, in_origin, out_origin, out_dims, grad_dest=None):
-    """-> (X on the output box, scale [C], shift [C], batch mean [C], biased batch variance [C]) -- see _BoxBatchNormReLU."""
+def box_batchnorm_relu(S, weight, bias, n_full, eps, in_origin, out_origin, out_dims, grad_dest=None, running=None, momentum=0.1):
+    """-> (X on the output box, scale [C], shift [C], batch mean [C], biased batch variance [C]) -- see _BoxBatchNormReLU.
+    running = (running_mean, running_var, num_batches_tracked): updated in place as torch.nn.BatchNorm does in train mode."""
     return _BoxBatchNormReLU.apply(S, weight, bias, float(n_full), float(eps), tuple(int(v) for v in in_origin),
-                                   tuple(int(v) for v in out_origin), tuple(int(v) for v in out_dims), grad_dest)
+                                   tuple(int(v) for v in out_origin), tuple(int(v) for v in out_dims), grad_dest, running, float(momentum))
 
 
 class _BoxLink:

@@ -215,9 +215,11 @@ class CostVolumeReg(nn.Module):
                 if train:
                     # fused op: one statistics pass + one normalise pass forward; backward = one reduction + one apply pass that
                     # writes the branch's gradient straight into the strided convolution's padded gradient buffer
+                    # (the running statistics are updated inside the op's per-channel algebra launch)
                     X, scale, shift, mean, var = ops.box_batchnorm_relu(S, bn.weight, bn.bias, n_full, bn.eps, C_lo, F_lo, F_dims,
-                                                                        getattr(S, "_mvs_grad_dest", None))
-                    self._bn_affine(bn, mean, var, n_full)                    # running statistics (no_grad inside)
+                                                                        getattr(S, "_mvs_grad_dest", None),
+                                                                        running=(bn.running_mean, bn.running_var, bn.num_batches_tracked),
+                                                                        momentum=bn.momentum)
                     bg = F.relu(shift)                                        # everywhere else on the canvas
                 else:
                     scale, shift = self._bn_affine(bn, None, None, n_full)

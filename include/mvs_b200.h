@@ -210,6 +210,20 @@ int mvsb200_conv3d_s2_fwd(const void* x, const void* w_packed, void* y, int B, i
 int mvsb200_conv3d_s1_wgrad(const void* x, const void* gy, float* gw, int B, int Di, int Hi, int Wi, int Cin,
                             int Do, int Ho, int Wo, int cout, int off_d, int off_h, int off_w, void* stream);
 
+/* Per-channel algebra of the box BatchNorm of the stride-2 branches (scripts/model.py:104-110 + BN + ReLU, evaluated on the
+ * central box: the canvas outside it is zero and counts in the statistics), one launch each instead of ~12 / ~20 [C]-sized torch
+ * launches: forward = mean, biased variance, scale, shift (fp64 inside), the running-statistics update of torch.nn.BatchNorm and
+ * stat64 = [mean, 1/sqrt(var + eps)] in fp64 for the backward; backward = (a, b2) = (dL/d sum S, 2 dL/d sum S^2) for
+ * mvsb200_box_bn_relu_bwd_apply plus the gradients of gamma and beta, from the reduced (gscale, gshift) and optional external
+ * gradients of scale / shift (NULL = none). */
+int mvsb200_box_bn_algebra_fwd(const float* s1, const float* s2, int C, double n_full, const float* gamma, const float* beta,
+                               double eps, double momentum, float* running_mean, float* running_var,
+                               int64_t* num_batches_tracked, float* scale, float* shift, float* mean, float* var,
+                               double* stat64, void* stream);
+int mvsb200_box_bn_algebra_bwd(const float* gscale, const float* gshift, const float* gscale_ext, const float* gshift_ext,
+                               const double* stat64, const float* gamma, int C, double n_full, float* a, float* b2,
+                               float* g_gamma, float* g_beta, void* stream);
+
 /* ---- K3c: the output convolution 8 -> 1 channels (k = 3, stride 1, padding 1) -----------------------
  * Replaces conv_out = Conv3d(8, 1, 3, padding=1, bias=False) (scripts/model.py:91, used at :123) and its two
  * gradients.  z: [B, D, h, w, 8] bf16 (the sum y1 + y0, channels_last_3d); w27x8: [27, 8] fp32, tap-major
