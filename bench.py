@@ -334,7 +334,8 @@ def run_b200(args, rank, world, local_rank, workload=None, light=False):
     n0 = mvs_b200.launch_count()
     ms = timed(step_resident, steps)
     launches = ((gstep.launches * steps) if gstep is not None else
-                (ginf.launches * steps) if ginf is not None else mvs_b200.launch_count() - n0)
+                (ginf.launches * steps) if ginf is not None else
+                (slab.launches * steps) if slab is not None and getattr(slab, "launches", 0) else mvs_b200.launch_count() - n0)
     events, ops.EVENTS = ops.EVENTS, None
     clocks = sampler.stop() if (rank == 0 and not light) else None
     for _ in range(2):

@@ -570,7 +570,8 @@ extern "C" int mvsb200_box_bn_relu_bwd_apply(const void* x, int x_dtype, const i
 //           g_mean = -gamma r G_shift - 2 mean g_var;  a = g_mean / n = dL/d(sum S),  b2 = 2 g_var / n = 2 dL/d(sum S^2).
 // These were ~12 + ~20 [C]-sized torch launches per branch and step.
 namespace {
-__global__ void box_bn_algebra_fwd_kernel(const float* __restrict__ s1, const float* __restrict__ s2, int C, double n,
+__global__ void box_bn_algebra_fwd_kernel(const float* __restrict__ s1, const float* __restrict__ s2,
+                                          const double* __restrict__ add1, const double* __restrict__ add2, int C, double n,
                                           const float* __restrict__ gamma, const float* __restrict__ beta, double eps,
                                           double momentum, float* running_mean, float* running_var, long long* nbt,
                                           float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean,
@@ -578,8 +579,10 @@ __global__ void box_bn_algebra_fwd_kernel(const float* __restrict__ s1, const fl
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c == 0 && nbt) *nbt += 1;
     if (c >= C) return;
-    const double m = (double)s1[c] / n;
-    double v = (double)s2[c] / n - m * m;
+    // add1 / add2: the sums of the values (and their squares) the tensor takes OUTSIDE the box it was summed over (conv_k_1: 27
+    // closed-form border classes of a convolution of a constant, regulariser.py)
+    const double m = ((double)s1[c] + (add1 ? add1[c] : 0.0)) / n;
+    double v = ((double)s2[c] + (add2 ? add2[c] : 0.0)) / n - m * m;
     v = v > 0.0 ? v : 0.0;
     const double r = 1.0 / sqrt(v + eps);
     const double g = (double)gamma[c];
@@ -614,14 +617,15 @@ __global__ void box_bn_algebra_bwd_kernel(const float* __restrict__ gscale, cons
 }
 }  // namespace
 
-extern "C" int mvsb200_box_bn_algebra_fwd(const float* s1, const float* s2, int C, double n_full, const float* gamma, const float* beta,
+extern "C" int mvsb200_box_bn_algebra_fwd(const float* s1, const float* s2, const double* add1, const double* add2, int C, double n_full,
+                                          const float* gamma, const float* beta,
                                           double eps, double momentum, float* running_mean, float* running_var,
                                           int64_t* num_batches_tracked, float* scale, float* shift, float* mean, float* var,
                                           double* stat64, void* stream) {
     MVS_REQUIRE(s1 && s2 && gamma && beta && scale && shift && mean && var && stat64, "box_bn_algebra_fwd: null pointer");
     MVS_REQUIRE(C >= 1 && C <= 4096 && n_full >= 1.0, "box_bn_algebra_fwd: bad shape");
     MVS_REQUIRE((running_mean == nullptr) == (running_var == nullptr), "box_bn_algebra_fwd: running_mean and running_var go together");
-    box_bn_algebra_fwd_kernel<<<(C + 63) / 64, 64, 0, (cudaStream_t)stream>>>(s1, s2, C, n_full, gamma, beta, eps, momentum, running_mean,
+    box_bn_algebra_fwd_kernel<<<(C + 63) / 64, 64, 0, (cudaStream_t)stream>>>(s1, s2, add1, add2, C, n_full, gamma, beta, eps, momentum, running_mean,
                                                                              running_var, reinterpret_cast<long long*>(num_batches_tracked),
                                                                              scale, shift, mean, var, stat64);
     MVS_CHECK_LAUNCH("box_bn_algebra_fwd");

@@ -51,10 +51,13 @@ _SIGNATURES = {
     "mvsb200_channel_sums_bwd": (_I, [_P, _I, _P, _P, _I, _P, _P, _P, _P]),
     "mvsb200_affine_relu_geo_fwd": (_I, [_P, _I, _P, _P, _I, _P, _P, _P, _I, _P]),
     "mvsb200_affine_relu_geo_bwd": (_I, [_P, _I, _P, _P, _I, _P, _P, _P, _I, _P, _P, _P, _P, _I, _P]),
-    "mvsb200_box_bn_algebra_fwd": (_I, [_P, _P, _I, _c.c_double, _P, _P, _c.c_double, _c.c_double, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "mvsb200_box_bn_algebra_fwd": (_I, [_P, _P, _P, _P, _I, _c.c_double, _P, _P, _c.c_double, _c.c_double, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "mvsb200_box_bn_algebra_bwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _c.c_double, _P, _P, _P, _P, _P]),
     "mvsb200_box_bn_relu_bwd_reduce": (_I, [_P, _I, _P, _P, _I, _P, _P, _P, _I, _P, _P, _P, _I, _P]),
     "mvsb200_box_bn_relu_bwd_apply": (_I, [_P, _I, _P, _P, _I, _P, _P, _P, _P, _P, _I, _P, _P, _I, _P]),
+    "mvsb200_masked_l1_workspace_floats": (_c.c_int64, [_I]),
+    "mvsb200_masked_l1_fwd": (_I, [_P, _P, _P, _I, _I, _P, _P, _P]),
+    "mvsb200_masked_l1_bwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _P, _P, _P]),
     "mvsb200_bn_workspace_floats": (_c.c_int64, []),
     "mvsb200_bn_stats": (_I, [_P, _I, _c.c_int64, _I, _P, _P, _P, _P]),
     "mvsb200_bn_relu_fwd": (_I, [_P, _I, _P, _P, _P, _I, _c.c_int64, _I, _P]),

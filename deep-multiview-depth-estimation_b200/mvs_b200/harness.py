@@ -279,6 +279,7 @@ class DepthSlabMVSNet:
         self.comm = TorchDistComm() if comm is None else comm
         self.reg = DepthSlabCostVolumeReg(model.cost_volume_reg, self.comm)
         self.use_graph, self._graphed, self._sweep, self._out = bool(graph), None, None, None
+        self.launches = 0
 
     def release(self):
         """Drop the captured graph (it holds NCCL work: do this before destroy_process_group())."""
@@ -352,9 +353,12 @@ class DepthSlabMVSNet:
                     self._pipeline(self._img, self._sweep, self._d_trans, self._d_span)
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
+            from . import _lib
             g = torch.cuda.CUDAGraph()
+            n0 = _lib.launch_count()
             with torch.cuda.graph(g):
                 self._out = self._pipeline(self._img, self._sweep, self._d_trans, self._d_span)
+            self.launches = _lib.launch_count() - n0       # libmvs_b200.so launches recorded in the graph (per replay)
             self._graphed = g
         self._graphed.replay()
         return self._out
@@ -398,7 +402,12 @@ def synthetic_cameras(batch_size, n_views, h=128, w=160, seed=0):
 
 
 def loss_fcn(gt, initial, refined):
-    """Masked L1 on both depth maps (scripts/loss.py:4-41): returns (loss, initial MAE, refined MAE)."""
+    """Masked L1 on both depth maps (scripts/loss.py:4-41): returns (loss, initial MAE, refined MAE).  On the GPU: the fused
+    kernels of libmvs_b200.so (ops.masked_l1_loss, one launch forward and one backward); the torch expression below is the
+    reference's formula, kept for host tensors (the harness' CPU unit tests)."""
+    if gt.is_cuda and initial.is_cuda and refined.is_cuda and gt.shape == initial.shape == refined.shape:
+        from . import ops
+        return ops.masked_l1_loss(gt, initial, refined)
     mask = (gt != 0).float()
     n_valid = mask.sum((1, 2, 3))
     l0 = (mask * (gt - initial).abs()).sum((1, 2, 3)) / n_valid

@@ -646,7 +646,7 @@ class _BoxBatchNormReLU(torch.autograd.Function):
         rm = rv = nbt = None
         if running is not None:
             rm, rv, nbt = running
-        _lib.call("mvsb200_box_bn_algebra_fwd", sums[0].data_ptr(), sums[1].data_ptr(), C, float(n_full), gamma.data_ptr(),
+        _lib.call("mvsb200_box_bn_algebra_fwd", sums[0].data_ptr(), sums[1].data_ptr(), None, None, C, float(n_full), gamma.data_ptr(),
                   beta.data_ptr(), float(eps), float(momentum), _ptr(rm), _ptr(rv), _ptr(nbt), scale.data_ptr(), shift.data_ptr(),
                   mean.data_ptr(), var.data_ptr(), stat64.data_ptr(), _stream())
         B = xv.shape[0]
@@ -700,6 +700,49 @@ def box_batchnorm_relu(S, weight, bias, n_full, eps, in_origin, out_origin, out_
     running = (running_mean, running_var, num_batches_tracked): updated in place as torch.nn.BatchNorm does in train mode."""
     return _BoxBatchNormReLU.apply(S, weight, bias, float(n_full), float(eps), tuple(int(v) for v in in_origin),
                                    tuple(int(v) for v in out_origin), tuple(int(v) for v in out_dims), grad_dest, running, float(momentum))
+
+
+class _BoxStatsAffine(torch.autograd.Function):
+    """(scale, shift) of a train-mode BatchNorm from the per-channel sums (t1, t2) of a tensor over a box plus the closed-form
+    sums (A1, A2, fp64) of what it holds outside the box: mean = (t1 + A1)/n, var = (t2 + A2)/n - mean^2, scale = gamma/sqrt(var +
+    eps), shift = beta - mean scale, running statistics updated in place -- one launch forward, one backward
+    (mvsb200_box_bn_algebra_fwd / _bwd) where ~25 + ~40 [C]-sized torch launches stood (conv_{1,2,3}_1, regulariser.py)."""
+
+    @staticmethod
+    def forward(ctx, t1, t2, A1, A2, weight, bias, n_full, eps, running, momentum):
+        C, dev = t1.shape[0], t1.device
+        t1, t2 = t1.detach().float().contiguous(), t2.detach().float().contiguous()
+        A1, A2 = A1.detach().double().contiguous(), A2.detach().double().contiguous()
+        vec = torch.empty((4, C), dtype=torch.float32, device=dev)
+        stat64 = torch.empty((2, C), dtype=torch.float64, device=dev)
+        gamma, beta = weight.detach().float().contiguous(), bias.detach().float().contiguous()
+        rm, rv, nbt = running if running is not None else (None, None, None)
+        _lib.call("mvsb200_box_bn_algebra_fwd", t1.data_ptr(), t2.data_ptr(), A1.data_ptr(), A2.data_ptr(), C, float(n_full),
+                  gamma.data_ptr(), beta.data_ptr(), float(eps), float(momentum), _ptr(rm), _ptr(rv), _ptr(nbt), vec[0].data_ptr(),
+                  vec[1].data_ptr(), vec[2].data_ptr(), vec[3].data_ptr(), stat64.data_ptr(), _stream())
+        ctx.save_for_backward(stat64, gamma)
+        ctx.n_full = float(n_full)
+        return vec[0], vec[1]
+
+    @staticmethod
+    def backward(ctx, g_scale, g_shift):
+        stat64, gamma = ctx.saved_tensors
+        C, dev = gamma.shape[0], gamma.device
+        zero = None
+        if g_scale is None or g_shift is None:
+            zero = torch.zeros(C, dtype=torch.float32, device=dev)
+        gs = zero if g_scale is None else g_scale.detach().float().contiguous()
+        gh = zero if g_shift is None else g_shift.detach().float().contiguous()
+        out = torch.empty((4, C), dtype=torch.float32, device=dev)
+        _lib.call("mvsb200_box_bn_algebra_bwd", gs.data_ptr(), gh.data_ptr(), None, None, stat64.data_ptr(), gamma.data_ptr(), C,
+                  ctx.n_full, out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), out[3].data_ptr(), _stream())
+        g1, g2 = out[0], out[1] * 0.5                      # dL/d(sum), dL/d(sum of squares): the same for t and A
+        return g1, g2, g1.double(), g2.double(), out[2], out[3], None, None, None, None
+
+
+def box_stats_affine(t1, t2, A1, A2, weight, bias, n_full, eps, running=None, momentum=0.1):
+    """-> (scale [C], shift [C]) -- see _BoxStatsAffine."""
+    return _BoxStatsAffine.apply(t1, t2, A1, A2, weight, bias, float(n_full), float(eps), running, float(momentum))
 
 
 class _BoxLink:
@@ -805,3 +848,45 @@ def box_batchnorm_linked(x):
 def affine_relu_geo_linked(x, scale, shift, in_origin, out_origin, out_dims, link, relu=True):
     return _AffineReLUGeoLinked.apply(x, scale, shift, tuple(int(v) for v in in_origin), tuple(int(v) for v in out_origin),
                                       tuple(int(v) for v in out_dims), bool(relu), link)
+
+
+# --------------------------------------------------------------------------------------------------
+# f3: the training loss (scripts/loss.py:4-41), one launch forward, one backward
+# --------------------------------------------------------------------------------------------------
+class _MaskedL1Loss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, gt, initial, refined):
+        for t, what in ((gt, "ground-truth depth"), (initial, "initial depth map"), (refined, "refined depth map")):
+            _need_cuda(t, what)
+        if not (gt.shape == initial.shape == refined.shape):
+            raise _lib.MvsB200Error(f"loss_fcn: shapes differ: {tuple(gt.shape)}, {tuple(initial.shape)}, {tuple(refined.shape)}")
+        g_, a0, a1 = (t.detach().float().contiguous() for t in (gt, initial, refined))
+        B = g_.shape[0]
+        n = g_.numel() // B
+        ws = torch.zeros(int(_lib.load().mvsb200_masked_l1_workspace_floats(B)), dtype=torch.float32, device=g_.device)
+        out3 = torch.empty(3, dtype=torch.float32, device=g_.device)
+        with _timed("masked_l1_loss"):
+            _lib.call("mvsb200_masked_l1_fwd", g_.data_ptr(), a0.data_ptr(), a1.data_ptr(), B, n, ws.data_ptr(), out3.data_ptr(), _stream())
+        ctx.save_for_backward(g_, a0, a1, ws)
+        ctx.shapes = (initial.shape, refined.shape, initial.dtype, refined.dtype)
+        return out3[0], out3[1], out3[2]
+
+    @staticmethod
+    def backward(ctx, g_loss, g_acc0, g_acc1):
+        g_, a0, a1, ws = ctx.saved_tensors
+        B = g_.shape[0]
+        n = g_.numel() // B
+        parts = [g if g is not None else torch.zeros((), dtype=torch.float32, device=g_.device) for g in (g_loss, g_acc0, g_acc1)]
+        g3 = torch.stack([p.detach().float().reshape(()) for p in parts])
+        ga0, ga1 = torch.empty_like(a0), torch.empty_like(a1)
+        with _timed("masked_l1_loss"):
+            _lib.call("mvsb200_masked_l1_bwd", g_.data_ptr(), a0.data_ptr(), a1.data_ptr(), ws.data_ptr(), g3.data_ptr(), B, n,
+                      ga0.data_ptr(), ga1.data_ptr(), _stream())
+        s0, s1, d0, d1 = ctx.shapes
+        return None, ga0.view(s0).to(d0), ga1.view(s1).to(d1)
+
+
+def masked_l1_loss(gt, initial, refined):
+    """(loss, initial_acc, refined_acc) of scripts/loss.py:4-41 -- masked L1 on both depth maps, mask = (gt != 0), per-sample
+    normalisation by the number of valid pixels -- one launch forward and one backward."""
+    return _MaskedL1Loss.apply(gt, initial, refined)

@@ -232,8 +232,13 @@ class CostVolumeReg(nn.Module):
                 if train:
                     # statistics node and normalisation node linked: the backward makes one reduction and one apply pass
                     link, (t1, t2) = ops.box_batchnorm_linked(T)
-                    mean, var = self._stats_from_sums_with_constant_outside(t1, t2, Wk.float(), bg, dims, E_lo, E_hi, B, n_full)
-                    scale, shift = self._bn_affine(bn, mean, var, n_full)
+                    # what the layer's output sums to outside E (27 closed-form border classes of a convolution of the constant
+                    # bg) joins the sums over E inside the per-channel algebra launch, which also updates the running statistics
+                    val, cnt = self._outside_classes(Wk.float(), bg, dims, E_lo, E_hi, B)
+                    vc = val.double() * cnt.double()
+                    scale, shift = ops.box_stats_affine(t1, t2, vc.sum((1, 2, 3)), (vc * val).sum((1, 2, 3)), bn.weight, bn.bias, n_full,
+                                                        bn.eps, running=(bn.running_mean, bn.running_var, bn.num_batches_tracked),
+                                                        momentum=bn.momentum)
                     enc[k] = ops.affine_relu_geo_linked(T, scale, shift, E_lo, C_lo, C_dims, link)   # on C, storage dtype of the path
                 else:
                     scale, shift = self._bn_affine(bn, None, None, n_full)

@@ -215,8 +215,10 @@ int mvsb200_conv3d_s1_wgrad(const void* x, const void* gy, float* gw, int B, int
  * launches: forward = mean, biased variance, scale, shift (fp64 inside), the running-statistics update of torch.nn.BatchNorm and
  * stat64 = [mean, 1/sqrt(var + eps)] in fp64 for the backward; backward = (a, b2) = (dL/d sum S, 2 dL/d sum S^2) for
  * mvsb200_box_bn_relu_bwd_apply plus the gradients of gamma and beta, from the reduced (gscale, gshift) and optional external
- * gradients of scale / shift (NULL = none). */
-int mvsb200_box_bn_algebra_fwd(const float* s1, const float* s2, int C, double n_full, const float* gamma, const float* beta,
+ * gradients of scale / shift (NULL = none).  add1 / add2 (fp64, NULL = none): what the tensor contributes to the two sums outside
+ * the box it was summed over (conv_{1,2,3}_1: closed-form border classes, mvs_b200/regulariser.py). */
+int mvsb200_box_bn_algebra_fwd(const float* s1, const float* s2, const double* add1, const double* add2, int C, double n_full,
+                               const float* gamma, const float* beta,
                                double eps, double momentum, float* running_mean, float* running_var,
                                int64_t* num_batches_tracked, float* scale, float* shift, float* mean, float* var,
                                double* stat64, void* stream);
@@ -312,6 +314,18 @@ int mvsb200_box_bn_relu_bwd_reduce(const void* x, int x_dtype, const int64_t* st
 int mvsb200_box_bn_relu_bwd_apply(const void* x, int x_dtype, const int64_t* strides4_host, const int* geo13_host, int C,
                                   const float* scale, const float* shift, const float* a, const float* b2, const void* gy,
                                   int g_dtype, void* gx, const int64_t* out_strides4_host, int relu, void* stream);
+
+/* ---- f3: the training loss (scripts/loss.py:4-41), fused ------------------------------------------
+ * mask = (gt != 0), n_valid[b] = sum mask;  l0[b] = sum mask |gt - initial| / n_valid[b], l1[b] likewise for `refined`;
+ * out3 = (loss = sum_b l0 + l1, initial_acc = mean_b l0, refined_acc = mean_b l1): one launch (one CTA per sample, the last to
+ * finish combines them, fixed order).  Backward: one elementwise launch, g3 = device floats (dL/d loss, dL/d initial_acc,
+ * dL/d refined_acc).  gt / initial / refined: fp32 [B, n] dense; workspace: mvsb200_masked_l1_workspace_floats(B) floats, ZEROED
+ * once by the caller (its last word is the ticket counter, reset by every launch); it carries (n_valid, l0, l1) to the backward. */
+int64_t mvsb200_masked_l1_workspace_floats(int B);
+int mvsb200_masked_l1_fwd(const float* gt, const float* initial, const float* refined, int B, int n, float* workspace,
+                          float* out3, void* stream);
+int mvsb200_masked_l1_bwd(const float* gt, const float* initial, const float* refined, const float* workspace,
+                          const float* g3, int B, int n, float* g_initial, float* g_refined, void* stream);
 
 #ifdef __cplusplus
 }

@@ -20,6 +20,7 @@ REFERENCE = {   # as written in the reference; re-read from /root/
                                           "n_views", "d_num"]),
     "costvolume": ("assemble_cost_volume", ["warped_feature_maps", "n_views"]),
     "depthmap": ("extract_depth_map", ["prob_volume", "d_batch"]),
+    "loss": ("loss_fcn", ["gt", "initial", "refined"]),                      # SURVEY §8 row f3 (scripts/loss.py:4)
 }
 
 

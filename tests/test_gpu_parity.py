@@ -337,3 +337,33 @@ def test_bad_arguments_raise():
     wv, _, _ = mvs_b200.homography_warping(K, R, T, d_min, d_int, torch.zeros(3, 16, 8, 8, device=DEV), 1, 3, 4, 10)
     with pytest.raises(mvs_b200.MvsB200Error, match="C must be 32"):
         mvs_b200.assemble_cost_volume(wv, 3)
+
+
+@pytest.mark.parametrize("B,h,w", [(4, 128, 160), (1, 7, 9), (3, 33, 20)])
+def test_fused_masked_l1_loss_matches_the_reference_formula(B, h, w):
+    """mvsb200_masked_l1_fwd / _bwd against scripts/loss.py:4-41 restated in torch (mask = gt != 0, per-sample
+    normalisation, loss = sum_b l0 + l1, the two accuracies = batch means) -- values and gradients, with invalid (zero) pixels and
+    exact ties (gt == estimate, where torch.abs' gradient is 0)."""
+    from mvs_b200 import ops
+    g = torch.Generator().manual_seed(B * 1000 + h)
+    gt = (425 + 480 * torch.rand(B, 1, h, w, generator=g)).to(DEV)
+    gt[torch.rand(B, 1, h, w, generator=g).to(DEV) < 0.3] = 0.0                 # invalid pixels
+    init = (gt + 5 * torch.randn(B, 1, h, w, generator=g).to(DEV))
+    ref = (gt + 3 * torch.randn(B, 1, h, w, generator=g).to(DEV))
+    init[:, :, 0, :2] = gt[:, :, 0, :2]                                        # exact ties
+    i1, r1 = init.clone().requires_grad_(True), ref.clone().requires_grad_(True)
+    n0 = mvs_b200.launch_count()
+    loss, a0, a1 = ops.masked_l1_loss(gt, i1, r1)
+    (loss + 0.5 * a0 - 0.25 * a1).backward()
+    assert mvs_b200.launch_count() - n0 == 2                                   # one launch forward, one backward
+    i2, r2 = init.clone().requires_grad_(True), ref.clone().requires_grad_(True)
+    mask = (gt != 0).float()
+    nv = mask.sum((1, 2, 3))
+    l0 = (mask * (gt - i2).abs()).sum((1, 2, 3)) / nv
+    l1 = (mask * (gt - r2).abs()).sum((1, 2, 3)) / nv
+    lr, b0, b1 = (l0 + l1).sum(), l0.mean(), l1.mean()
+    (lr + 0.5 * b0 - 0.25 * b1).backward()
+    for got, want in ((loss, lr), (a0, b0), (a1, b1)):
+        assert abs(float(got) - float(want)) <= 1e-5 * abs(float(want))
+    assert torch.allclose(i1.grad, i2.grad, rtol=1e-5, atol=1e-9)
+    assert torch.allclose(r1.grad, r2.grad, rtol=1e-5, atol=1e-9)
