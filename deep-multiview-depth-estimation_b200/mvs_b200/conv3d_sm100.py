@@ -236,6 +236,18 @@ def conv_transpose3d_s2(x, w, pads, out_dims):
     return y
 
 
+def _lines_fit(cb, cs, ws):
+    """Two ring stages of the line kernel (a line of the dense operand + three lines of the strided one, csrc/conv3d_s2_bwd.cu:
+    launch_s2_wgrad_lines) must fit shared memory; very long lines of wide layers go to the parity-class kernel instead."""
+    up = lambda v: (v + 1023) // 1024 * 1024
+    ksteps = (ws + 15) // 16
+    atoms = 128 // (2 * cb)
+    line_a = up(max(ws + 1, 16 * ksteps + atoms) * 4 * cb)
+    n_chunks, chunk = (2, 64) if cs > 64 else (1, cs)
+    stage = n_chunks * up(16 * ksteps * 2 * chunk) + 3 * line_a
+    return 2 * stage <= 227 * 1024 - 1024 - 8192 - 512
+
+
 def _s2_wgrad_mode(big_shape, small_shape):
     """Which kernel computes the weight gradient of a stride-2 layer: "lines" (default; conv3d_s2_wgrad_lines_kernel, one
     launch, lines of the strided operand as voxel-pair rows), "classes" (the stride-1 weight-gradient kernel on the 8 parity
@@ -247,7 +259,7 @@ def _s2_wgrad_mode(big_shape, small_shape):
     cb, cs = big_shape[1], small_shape[1]
     lib = _lib.load()
     lines_ok = (cb in (8, 16, 32) and (cs in (16, 32, 64) or (64 < cs <= 128 and cs % 16 == 0)) and big_shape[4] % 2 == 0
-                and small_shape[4] <= 255 and hasattr(lib, "mvsb200_conv3d_s2_wgrad_lines"))
+                and small_shape[4] <= 255 and _lines_fit(cb, cs, small_shape[4]) and hasattr(lib, "mvsb200_conv3d_s2_wgrad_lines"))
     classes_ok = cb in _CIN_OK and cs % 8 == 0 and hasattr(lib, "mvsb200_conv3d_s2_wgrad")
     if want == "lines" and lines_ok:
         return "lines"

@@ -156,7 +156,7 @@ def test_transposed_conv_by_parity_classes(cin, cout, dims, form, monkeypatch):
 
 @pytest.mark.parametrize("wgrad", ["lines", "tcgen05", "cudnn"])
 @pytest.mark.parametrize("cin,cout", [(32, 112), (32, 16), (16, 32), (64, 32)])
-@pytest.mark.parametrize("dims", [(12, 10, 14), (11, 9, 15), (8, 7, 12), (6, 33, 47)])
+@pytest.mark.parametrize("dims", [(12, 10, 14), (11, 9, 15), (8, 7, 12), (6, 33, 47), (4, 6, 400)])
 def test_stride2_conv_on_the_central_box(cin, cout, dims, wgrad, monkeypatch):
     """The stride-2 branches (model.py:104-110, padding dim/2+1) evaluated on the central box by the tcgen05 stride-2
     kernel (parity sub-lattice slabs) vs the reference formulation conv3d(stride 2, padding dim/2+1) cropped to the box.
@@ -190,7 +190,8 @@ def test_stride2_conv_on_the_central_box(cin, cout, dims, wgrad, monkeypatch):
     gy = torch.randn(ref.shape, generator=g).to(DEV).to(torch.bfloat16)
     n1 = mvs_b200.launch_count()
     y.backward(gy)
-    if wgrad == "lines" and dims[2] % 2 == 0 and cin <= 32:
+    if wgrad == "lines" and dims[2] % 2 == 0 and cin <= 32 and not (dims[2] == 400 and cout == 112):   # (201-voxel lines of the
+        # 112-channel gradient do not fit two ring stages: that shape runs on the parity-class kernel)
         # backward: one weight-gradient launch + one data-gradient launch (+ one filter-packing launch per K chunk of the
         # transposed convolution) -- no library convolution
         assert mvs_b200.launch_count() - n1 == 2 + (3 if cout == 112 else 1)
