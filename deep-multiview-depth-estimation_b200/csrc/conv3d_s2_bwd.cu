@@ -43,7 +43,9 @@ struct S2WgLineParams {
     int n_chunks, chunk_ch;         // small is loaded as n_chunks boxes of chunk_ch channels (one swizzle atom each)
     int ksteps;                     // ceil(Ws / 16)
     int line_a_bytes, line_b_bytes; // ring slot of a big line; one chunk of a small line (= stride between its N atoms)
-    int stage_bytes, n_stages;      // stage = [small: n_chunks x line_b_bytes][big kh=0][big kh=1][big kh=2]
+    int stage_bytes, n_stages;      // stage = [small: n_chunks x line_b_bytes] then per depth tap of the CTA [big kh=0][kh=1][kh=2]
+    int nkd;                        // depth taps per CTA: 1 (blockIdx % 3 picks it) or 3 (narrow layers: 9 x Cs columns fit TMEM,
+                                    // a third of the barrier round trips per MMA)
     int ychunk, nychunks;           // lines of small per item
     float* gw;                      // [27][CB][Cs] fp32, accumulated into
     int dbg;                        // diagnostics (MVSB200_S2WG_DBG): 1 = no MMAs issued, 2 = no TMA loads issued
@@ -87,8 +89,9 @@ conv3d_s2_wgrad_lines_kernel(const __grid_constant__ CUtensorMap tm_big, const _
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nkd = p.nkd;
     uint32_t tmem_cols = 32;
-    while ((int)tmem_cols < 3 * p.Cs) tmem_cols <<= 1;
+    while ((int)tmem_cols < 3 * nkd * p.Cs) tmem_cols <<= 1;
 
     // zero everything the MMAs may read and TMA never writes: the zero operands, the row tails of every ring slot
     {
@@ -114,20 +117,21 @@ conv3d_s2_wgrad_lines_kernel(const __grid_constant__ CUtensorMap tm_big, const _
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    // this CTA's depth tap and its share of the (batch, plane of small, line chunk) items of that tap
-    const int kd = blockIdx.x % 3, rank = blockIdx.x / 3;
-    const int nrank = ((int)gridDim.x - kd + 2) / 3;
-    const int od_lo = max(0, (p.pad_d - kd + 1) >> 1);
-    const int od_hi = min(p.Ds - 1, (p.Db - 1 + p.pad_d - kd) >> 1);
+    // this CTA's depth tap(s) and its share of the (batch, plane of small, line chunk) items
+    const int kd0 = nkd == 1 ? (int)blockIdx.x % 3 : 0;
+    const int rank = nkd == 1 ? (int)blockIdx.x / 3 : (int)blockIdx.x;
+    const int nrank = nkd == 1 ? ((int)gridDim.x - kd0 + 2) / 3 : (int)gridDim.x;
+    const int od_lo = nkd == 1 ? max(0, (p.pad_d - kd0 + 1) >> 1) : 0;
+    const int od_hi = nkd == 1 ? min(p.Ds - 1, (p.Db - 1 + p.pad_d - kd0) >> 1) : p.Ds - 1;
     const int nod = max(0, od_hi - od_lo + 1);
     const int n_items = p.B * nod * p.nychunks;
 
-    // item -> (b, od, d, [oy0, oy1))
+    // item -> (b, od, d of the CTA's first depth tap, [oy0, oy1)); depth tap kd0 + i reads plane d + i
     auto decode = [&](int item, int& b, int& od, int& d, int& oy0, int& oy1) {
         const int yc = item % p.nychunks, r = item / p.nychunks;
         od = od_lo + r % nod;
         b = r / nod;
-        d = 2 * od - p.pad_d + kd;
+        d = 2 * od - p.pad_d + kd0;
         oy0 = yc * p.ychunk;
         oy1 = min(p.Hs, oy0 + p.ychunk);
     };
@@ -147,16 +151,21 @@ conv3d_s2_wgrad_lines_kernel(const __grid_constant__ CUtensorMap tm_big, const _
                     const int y0 = 2 * oy - p.pad_h;
                     const int kh_first = oy == oy0 ? 0 : 1;          // kh = 0 of later lines is the previous stage's kh = 2 line
                     uint32_t bytes = bytes_b;
-                    for (int kh = kh_first; kh < 3; ++kh) bytes += (y0 + kh >= 0 && y0 + kh < p.Hb) ? bytes_a : 0u;
+                    for (int i = 0; i < nkd; ++i)
+                        if (d + i >= 0 && d + i < p.Db)
+                            for (int kh = kh_first; kh < 3; ++kh) bytes += (y0 + kh >= 0 && y0 + kh < p.Hb) ? bytes_a : 0u;
                     if (p.dbg & 2) { mbar_arrive(full + slot); }
                     else {
                         mbar_expect_tx(full + slot, bytes);
                         for (int c = 0; c < p.n_chunks; ++c)
                             tma_load_5d(st + (size_t)c * p.line_b_bytes, &tm_small, full + slot, c * p.chunk_ch, 0, oy, od, b);
                         // pairs -1 .. Ws-1 of a line of big: smem row r holds pair r - 1 (pair -1 and pairs beyond the line: zeros)
-                        for (int kh = kh_first; kh < 3; ++kh)
-                            if (y0 + kh >= 0 && y0 + kh < p.Hb)
-                                tma_load_5d(st + slot_b_bytes + (size_t)kh * p.line_a_bytes, &tm_big, full + slot, 0, -1, y0 + kh, d, b);
+                        for (int i = 0; i < nkd; ++i)
+                            if (d + i >= 0 && d + i < p.Db)
+                                for (int kh = kh_first; kh < 3; ++kh)
+                                    if (y0 + kh >= 0 && y0 + kh < p.Hb)
+                                        tma_load_5d(st + slot_b_bytes + (size_t)(i * 3 + kh) * p.line_a_bytes, &tm_big, full + slot, 0, -1,
+                                                    y0 + kh, d + i, b);
                     }
                 }
                 __syncwarp();
@@ -172,9 +181,9 @@ conv3d_s2_wgrad_lines_kernel(const __grid_constant__ CUtensorMap tm_big, const _
         const uint32_t sa_lo = (uint32_t)da0 | (smem_u32(stages) >> 4);
         const uint32_t sb_lo = (uint32_t)db0 | (smem_u32(stages) >> 4);
         const uint32_t st16 = (uint32_t)p.stage_bytes >> 4, la16 = (uint32_t)p.line_a_bytes >> 4, big16 = (uint32_t)slot_b_bytes >> 4;
-        // the three accumulator blocks start at zero: one MMA each on the all-zero operands
+        // the accumulator blocks (depth tap, kh) start at zero: one MMA each on the all-zero operands
         if (elect_one()) {
-            for (int kh = 0; kh < 3; ++kh)
+            for (int kh = 0; kh < 3 * nkd; ++kh)
                 umma_bf16_lohi(tmem_base + (uint32_t)(kh * p.Cs), (uint32_t)da0 | (smem_u32(zero_a) >> 4), a_hi,
                                (uint32_t)dz0 | (smem_u32(zero_b) >> 4), z_hi, IDESC, 0u);
         }
@@ -189,18 +198,21 @@ conv3d_s2_wgrad_lines_kernel(const __grid_constant__ CUtensorMap tm_big, const _
                 if (elect_one()) {
                     const int y0 = 2 * oy - p.pad_h;
                     const uint32_t g_lo = sb_lo + (uint32_t)slot * st16;
-                    for (int kh = 0; kh < 3; ++kh) {
-                        if (y0 + kh < 0 || y0 + kh >= p.Hb) continue;
-                        const uint32_t d_tmem = tmem_base + (uint32_t)(kh * p.Cs);
-                        uint32_t a_lo = (kh == 0 && oy != oy0) ? sa_lo + (uint32_t)prev * st16 + big16 + 2u * la16
-                                                               : sa_lo + (uint32_t)slot * st16 + big16 + (uint32_t)kh * la16;
-                        uint32_t b_lo = g_lo;
-                        if (p.dbg & 1) continue;
+                    for (int i = 0; i < nkd; ++i) {
+                        if (d + i < 0 || d + i >= p.Db) continue;
+                        for (int kh = 0; kh < 3; ++kh) {
+                            if (y0 + kh < 0 || y0 + kh >= p.Hb) continue;
+                            const uint32_t d_tmem = tmem_base + (uint32_t)((i * 3 + kh) * p.Cs);
+                            uint32_t a_lo = (kh == 0 && oy != oy0) ? sa_lo + (uint32_t)prev * st16 + big16 + (uint32_t)(i * 3 + 2) * la16
+                                                                   : sa_lo + (uint32_t)slot * st16 + big16 + (uint32_t)(i * 3 + kh) * la16;
+                            uint32_t b_lo = g_lo;
+                            if (p.dbg & 1) continue;
 #pragma unroll 2
-                        for (int ks = 0; ks < p.ksteps; ++ks) {
-                            umma_bf16_lohi(d_tmem, a_lo, a_hi, b_lo, b_hi, IDESC, 1u);
-                            a_lo += (uint32_t)(16 * ROWA) >> 4;
-                            b_lo += (uint32_t)(16 * ROWG) >> 4;
+                            for (int ks = 0; ks < p.ksteps; ++ks) {
+                                umma_bf16_lohi(d_tmem, a_lo, a_hi, b_lo, b_hi, IDESC, 1u);
+                                a_lo += (uint32_t)(16 * ROWA) >> 4;
+                                b_lo += (uint32_t)(16 * ROWG) >> 4;
+                            }
                         }
                     }
                     if (oy != oy0) umma_commit(empty + prev);        // its kh = 2 line was this line's kh = 0
@@ -222,11 +234,12 @@ conv3d_s2_wgrad_lines_kernel(const __grid_constant__ CUtensorMap tm_big, const _
         const int a = m / ATOM_ROWS, par = (m / CB) & 1, cb = m % CB;
         const int kw = 2 * (a - 1) + par + p.pad_w;      // pair ox + a - 1, voxel 2(ox + a - 1) + par = 2 ox - pad + kw
         const bool real = kw >= 0 && kw <= 2 && n_items > 0;
-        for (int kh = 0; kh < 3; ++kh) {
+        for (int blk = 0; blk < 3 * nkd; ++blk) {
+            const int kd = kd0 + blk / 3, kh = blk % 3;
             float* dst = p.gw + ((size_t)(((kd * 3 + kh) * 3 + (real ? kw : 0)) * CB + cb)) * p.Cs;
             for (int c0 = 0; c0 < p.Cs; c0 += 16) {
                 uint32_t v[16];
-                tmem_ld<16>(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(kh * p.Cs + c0), v);
+                tmem_ld<16>(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(blk * p.Cs + c0), v);
                 tmem_ld_wait();
                 if (real) {
 #pragma unroll
@@ -266,7 +279,11 @@ int launch_s2_wgrad_lines(const void* big, const void* small, float* gw, int B, 
     p.line_b_bytes = (16 * p.ksteps * ROWG + 1023) / 1024 * 1024;
     const size_t budget = 227 * 1024 - 1024 - kZeroA - kZeroB - 512;
     const size_t slot_b = (size_t)p.n_chunks * p.line_b_bytes;
-    p.stage_bytes = (int)slot_b + 3 * p.line_a_bytes;
+    // narrow layers: all three depth taps in one CTA when their 9 x Cs accumulator columns fit TMEM and three stages fit shared
+    // memory (a third of the barrier round trips per MMA: the small-channel layers are bound by the single-warp roles)
+    p.nkd = (9 * Cs <= 512 && 3 * (slot_b + 9 * (size_t)p.line_a_bytes) <= budget) ? 3 : 1;
+    if (const char* e = getenv("MVSB200_S2WG_NKD")) { const int v = atoi(e); if (v == 1 || (v == 3 && 9 * Cs <= 512)) p.nkd = v; }
+    p.stage_bytes = (int)slot_b + 3 * p.nkd * p.line_a_bytes;
     p.n_stages = (int)(budget / (size_t)p.stage_bytes);
     if (p.n_stages > kMaxRing) p.n_stages = kMaxRing;
     MVS_REQUIRE(p.n_stages >= 2, "conv3d_s2_wgrad_lines: lines of %d voxels do not fit shared memory (Cb=%d, Cs=%d)", Ws, CB, Cs);
@@ -302,7 +319,7 @@ int launch_s2_wgrad_lines(const void* big, const void* small, float* gw, int B, 
     }
     if (sms < 3) sms = 3;
     // lines of small per item: balance (items per CTA of a depth tap) x (lines + the extra big lines at an item's start)
-    const long nrank = sms / 3;
+    const long nrank = p.nkd == 1 ? sms / 3 : sms;
     long best_cost = -1;
     int best_nyc = 1;
     for (int nyc = 1; nyc <= Hs; ++nyc) {

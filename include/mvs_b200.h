@@ -317,7 +317,7 @@ int mvsb200_box_bn_relu_bwd_apply(const void* x, int x_dtype, const int64_t* str
 
 /* ---- f3: the training loss (scripts/loss.py:4-41), fused ------------------------------------------
  * mask = (gt != 0), n_valid[b] = sum mask;  l0[b] = sum mask |gt - initial| / n_valid[b], l1[b] likewise for `refined`;
- * out3 = (loss = sum_b l0 + l1, initial_acc = mean_b l0, refined_acc = mean_b l1): one launch (one CTA per sample, the last to
+ * out3 = (loss = sum_b l0 + l1, initial_acc = mean_b l0, refined_acc = mean_b l1): one launch (32 CTAs per sample, the last to
  * finish combines them, fixed order).  Backward: one elementwise launch, g3 = device floats (dL/d loss, dL/d initial_acc,
  * dL/d refined_acc).  gt / initial / refined: fp32 [B, n] dense; workspace: mvsb200_masked_l1_workspace_floats(B) floats, ZEROED
  * once by the caller (its last word is the ticket counter, reset by every launch); it carries (n_valid, l0, l1) to the backward. */
