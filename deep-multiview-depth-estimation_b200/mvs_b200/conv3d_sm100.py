@@ -211,6 +211,8 @@ def conv_transpose3d_s2(x, w, pads, out_dims):
         Jd, Jh, Jw = (D - pd_ + 1) // 2, (h - ph_ + 1) // 2, (wd - pw_ + 1) // 2
         if min(Jd, Jh, Jw) > 0:
             work += 2.0 * bin(masks[c]).count("1") * cin * cout * B * Jd * Jh * Jw
+    if os.environ.get("MVSB200_DECONV", "fused") == "kc" and cin in (16, 32, 64):      # A/B: the K-chunk kernel with one chunk
+        return conv_transpose3d_s2_kc(x_cl, (cin,), w, pads, out_dims)
     if n_rows <= 32 and os.environ.get("MVSB200_DECONV", "fused") != "classes" and hasattr(_lib.load(), "mvsb200_deconv3d_s2_fwd"):
         wp = _pack(w, 1, n_rows, _NAT + [-1])            # [k][co][ci] from [Cin, Cout, ...]; slot 27: zeros (DeconvWide, tc_common.cuh)
         ys = (ctypes.c_int64 * 4)(sB, sD, sH, sW)
