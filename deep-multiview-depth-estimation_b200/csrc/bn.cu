@@ -801,3 +801,20 @@ extern "C" int mvsb200_bn_stats_affine(const void* x, int dtype, int64_t M, int 
     MVS_CHECK_LAUNCH("bn_finalize_affine");
     return MVSB200_OK;
 }
+
+/* The finalize launch of mvsb200_bn_stats_affine on per-CTA partial sums [n_blocks][2][C] that a producer kernel already wrote
+ * (the transposed convolution's epilogue, mvsb200_deconv3d_s2_fwd_stats): the statistics pass over the canvas disappears. */
+extern "C" int mvsb200_bn_finalize_affine(const float* partials, int n_blocks, int64_t M, int C, const float* gamma, const float* beta,
+                                          double eps, double momentum, float* running_mean, float* running_var,
+                                          int64_t* num_batches_tracked, float* mean, float* var, float* invstd, float* scale,
+                                          float* shift, void* stream) {
+    MVS_REQUIRE(partials && mean && var && invstd && scale && shift && gamma && beta, "bn_finalize_affine: null vector");
+    MVS_REQUIRE(n_blocks >= 1 && M >= 1 && (C == 8 || C == 16 || C == 32 || C == 64), "bn_finalize_affine: bad shape");
+    MVS_REQUIRE((running_mean == nullptr) == (running_var == nullptr), "bn_finalize_affine: running_mean and running_var go together");
+    BnAffineOut o{mean, var, invstd, scale, shift, running_mean, running_var, reinterpret_cast<long long*>(num_batches_tracked)};
+    bn_finalize_affine_kernel<<<1, kFinSlices * 2 * kMaxC, 0, (cudaStream_t)stream>>>(partials, n_blocks, C, 1.0 / (double)M,
+                                                                                     M > 1 ? (double)M / (double)(M - 1) : 1.0, gamma,
+                                                                                     beta, eps, momentum, o);
+    MVS_CHECK_LAUNCH("bn_finalize_affine");
+    return MVSB200_OK;
+}

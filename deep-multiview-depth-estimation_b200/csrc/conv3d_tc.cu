@@ -1353,6 +1353,8 @@ struct DeconvParams {
     int wide_io;                    // 1: 32-byte stores (rows 32-byte aligned, channels in multiples of 16)
     long long y_sb, y_sd, y_sh, y_sw;   // canvas voxel-row strides in elements
     __nv_bfloat16* y;
+    float* stats;                   // null, or [gridDim.x][2][cout]: per-CTA sums of the stored values and of their squares (the
+                                    // train-mode BatchNorm that follows takes its statistics from here: no pass over the canvas)
 };
 
 template <int CIN, int NOUT>
@@ -1380,6 +1382,7 @@ deconv3d_s2_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
     uint64_t* tfull = wfull + 1;
     uint64_t* tempty = tfull + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    float* stats_smem = reinterpret_cast<float*>(bars + 16);        // [4 warps][2][NOUT]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles = p.tiles_x * p.tiles_y;
@@ -1498,6 +1501,11 @@ deconv3d_s2_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
             tj[mb] = m / p.BW; ti[mb] = m - tj[mb] * p.BW;
             in_tile[mb] = ti[mb] < p.BW - 2 && tj[mb] < p.L;
         }
+        // per-channel sums of what this thread stores, for the BatchNorm that follows
+        float st_s[NOUT], st_q[NOUT];
+#pragma unroll
+        for (int ch = 0; ch < NOUT; ++ch) { st_s[ch] = 0.f; st_q[ch] = 0.f; }
+        const bool want_stats = p.stats != nullptr;
         int gp = 0;
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
             int b, d_begin, nd, x0, y0;
@@ -1517,6 +1525,16 @@ deconv3d_s2_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                         const int cl = p.g.cls_of_pos[c];                  // accumulator block c holds output-parity class cl
                         const int z = oz + (cl >> 2), yy = oy + (cl >> 1 & 1), xx = ox + (cl & 1);
                         if (in_tile[mb] && z < p.Do && yy < p.Ho && xx < p.Wo) {
+                            if (want_stats) {
+#pragma unroll
+                                for (int ch = 0; ch < NOUT; ++ch) {
+                                    // (the fp32 accumulator, not its bf16 rounding: the rounding error is unbiased and 2^-9 relative,
+                                    // far inside the statistics' own noise; re-rounding here cost more than the pass it saves)
+                                    const float r = __uint_as_float(v[ch]);
+                                    st_s[ch] += r;
+                                    st_q[ch] = fmaf(r, r, st_q[ch]);
+                                }
+                            }
                             __nv_bfloat16* row = p.y + (long long)b * p.y_sb + (long long)z * p.y_sd + (long long)yy * p.y_sh + (long long)xx * p.y_sw;
                             if (p.wide_io) {                                   // 32-byte stores: half as many store instructions
 #pragma unroll
@@ -1549,10 +1567,32 @@ deconv3d_s2_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                 if (lane == 0) mbar_arrive(tempty + stage);
             }
         }
+        if (want_stats) {
+            // warp totals (fixed shuffle order), then the four epilogue warps' rows side by side in shared memory
+#pragma unroll
+            for (int ch = 0; ch < NOUT; ++ch) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    st_s[ch] += __shfl_xor_sync(0xffffffffu, st_s[ch], o);
+                    st_q[ch] += __shfl_xor_sync(0xffffffffu, st_q[ch], o);
+                }
+            }
+            if (lane == 0) {
+#pragma unroll
+                for (int ch = 0; ch < NOUT; ++ch) { stats_smem[(q * 2 + 0) * NOUT + ch] = st_s[ch]; stats_smem[(q * 2 + 1) * NOUT + ch] = st_q[ch]; }
+            }
+        }
     }
 
     tc_fence_before();
     __syncthreads();
+    if (p.stats != nullptr && (int)threadIdx.x < 2 * p.cout) {          // the CTA's partial row [2][cout], warps added in fixed order
+        const int which = threadIdx.x / p.cout, ch = threadIdx.x % p.cout;
+        float t = 0.f;
+#pragma unroll
+        for (int w4 = 0; w4 < 4; ++w4) t += stats_smem[(w4 * 2 + which) * NOUT + ch];
+        p.stats[((size_t)blockIdx.x * 2 + which) * p.cout + ch] = t;
+    }
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
@@ -1580,13 +1620,14 @@ TilePlan plan_tiles_mb(int Ho, int Wo, int rowb, size_t w_bytes_al, size_t smem_
 
 template <int CIN, int NOUT>
 int launch_deconv_s2(const void* x, const void* w, void* y, int B, int Di, int Hi, int Wi, int Do, int Ho, int Wo, int cout,
-                     int n_rows, int pad_d, int pad_h, int pad_w, const long long* y_strides4, cudaStream_t st) {
+                     int n_rows, int pad_d, int pad_h, int pad_w, const long long* y_strides4, cudaStream_t st,
+                     float* stats = nullptr, int* n_blocks_out = nullptr) {
     constexpr int ROWB = CIN * 2;
     constexpr int MB = 512 / (16 * NOUT);
     constexpr size_t W_BYTES_AL = ((size_t)kDeconvSlots * NOUT * ROWB + 1023) / 1024 * 1024;
     EncodeTiledFn enc = encode_fn();
     MVS_REQUIRE(enc != nullptr, "deconv3d_s2: cuTensorMapEncodeTiled is not available from the driver");
-    const size_t smem_budget = 227 * 1024 - 1024;
+    const size_t smem_budget = 227 * 1024 - 1024 - 1024;      // - the epilogue's statistics rows
     const int Jd = (Do + 1) / 2, Jh = (Ho + 1) / 2, Jw = (Wo + 1) / 2;
     const TilePlan tp = plan_tiles_mb(Jh, Jw, ROWB, W_BYTES_AL, smem_budget, MB);
     MVS_REQUIRE(tp.score > 0, "deconv3d_s2: no slab geometry fits shared memory (Cin=%d, N=%d)", CIN, NOUT);
@@ -1643,7 +1684,9 @@ int launch_deconv_s2(const void* x, const void* w, void* y, int B, int Di, int H
     p.dchunk = (Jd + best_chunks - 1) / best_chunks;
     p.n_items = (int)(tiles * p.nchunks * B);
     const dim3 grid((unsigned)(p.n_items < sms ? p.n_items : sms), 1, 1);
-    const size_t smem = 1024 + W_BYTES_AL + (size_t)kSlots3 * tp.slab_bytes + 256;
+    const size_t smem = 1024 + W_BYTES_AL + (size_t)kSlots3 * tp.slab_bytes + 256 + 1024;
+    p.stats = stats;
+    if (n_blocks_out) *n_blocks_out = (int)grid.x;
     MVS_CUDA(cudaFuncSetAttribute(deconv3d_s2_tc_kernel<CIN, NOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     deconv3d_s2_tc_kernel<CIN, NOUT><<<grid, kTcThreads, smem, st>>>(tm_x, tm_w, p);
     MVS_CHECK_LAUNCH("deconv3d_s2_tc");
@@ -1779,9 +1822,12 @@ extern "C" int mvsb200_conv3d_s2_fwd(const void* x, const void* w_packed, void* 
     return MVSB200_OK;
 }
 
-extern "C" int mvsb200_deconv3d_s2_fwd(const void* x, const void* w_packed, void* y, int B, int Di, int Hi, int Wi, int Cin,
-                                       int Do, int Ho, int Wo, int cout, int n_rows, int pad_d, int pad_h, int pad_w,
-                                       const int64_t* y_strides4, void* stream) {
+/* stats (may be NULL): [n_blocks][2][cout] fp32 per-CTA sums of the stored values and of their squares over the written canvas,
+ * n_blocks returned through n_blocks_host (<= the device's SM count: size the buffer for that) -- the operand of
+ * mvsb200_bn_finalize_affine, so the BatchNorm that follows a transposed convolution needs no statistics pass. */
+extern "C" int mvsb200_deconv3d_s2_fwd_stats(const void* x, const void* w_packed, void* y, int B, int Di, int Hi, int Wi, int Cin,
+                                             int Do, int Ho, int Wo, int cout, int n_rows, int pad_d, int pad_h, int pad_w,
+                                             const int64_t* y_strides4, float* stats, int* n_blocks_host, void* stream) {
     MVS_REQUIRE(x && w_packed && y && y_strides4, "deconv3d_s2_fwd: null pointer");
     MVS_REQUIRE(aligned16(x) && aligned16(w_packed) && aligned16(y), "deconv3d_s2_fwd: pointers must be 16-byte aligned");
     MVS_REQUIRE(B >= 1 && B <= 65535 && Di >= 1 && Hi >= 1 && Wi >= 1 && Do >= 1 && Ho >= 1 && Wo >= 1, "deconv3d_s2_fwd: bad shape");
@@ -1792,7 +1838,7 @@ extern "C" int mvsb200_deconv3d_s2_fwd(const void* x, const void* w_packed, void
     for (int i = 0; i < 4; ++i) MVS_REQUIRE(ys[i] % 8 == 0, "deconv3d_s2_fwd: output strides must be multiples of 8 elements");
     cudaStream_t st = (cudaStream_t)stream;
     int rc = MVSB200_E_UNSUPPORTED;
-#define MVS_DC(CI, NO) rc = launch_deconv_s2<CI, NO>(x, w_packed, y, B, Di, Hi, Wi, Do, Ho, Wo, cout, n_rows, pad_d, pad_h, pad_w, ys, st)
+#define MVS_DC(CI, NO) rc = launch_deconv_s2<CI, NO>(x, w_packed, y, B, Di, Hi, Wi, Do, Ho, Wo, cout, n_rows, pad_d, pad_h, pad_w, ys, st, stats, n_blocks_host)
     if (Cin == 16 && n_rows == 16) MVS_DC(16, 16);
     else if (Cin == 16 && n_rows == 32) MVS_DC(16, 32);
     else if (Cin == 32 && n_rows == 16) MVS_DC(32, 16);
@@ -1802,6 +1848,13 @@ extern "C" int mvsb200_deconv3d_s2_fwd(const void* x, const void* w_packed, void
     else MVS_FAIL(MVSB200_E_UNSUPPORTED, "deconv3d_s2_fwd: unsupported channels Cin=%d n_rows=%d", Cin, n_rows);
 #undef MVS_DC
     return rc;
+}
+
+extern "C" int mvsb200_deconv3d_s2_fwd(const void* x, const void* w_packed, void* y, int B, int Di, int Hi, int Wi, int Cin,
+                                       int Do, int Ho, int Wo, int cout, int n_rows, int pad_d, int pad_h, int pad_w,
+                                       const int64_t* y_strides4, void* stream) {
+    return mvsb200_deconv3d_s2_fwd_stats(x, w_packed, y, B, Di, Hi, Wi, Cin, Do, Ho, Wo, cout, n_rows, pad_d, pad_h, pad_w, y_strides4,
+                                         nullptr, nullptr, stream);
 }
 
 /* Same convolution as mvsb200_conv3d_s1_fwd with the depth tap folded into the MMA N extent (conv3d_s1_kdn_kernel).

@@ -40,6 +40,7 @@ _SIGNATURES = {
     "mvsb200_conv3d_s2_wgrad": (_I, [_P, _P, _P] + [_I] * 12 + [_P]),
     "mvsb200_conv3d_s2_wgrad_lines": (_I, [_P, _P, _P] + [_I] * 12 + [_P, _P]),
     "mvsb200_deconv3d_s2_fwd": (_I, [_P, _P, _P] + [_I] * 13 + [_P, _P]),
+    "mvsb200_deconv3d_s2_fwd_stats": (_I, [_P, _P, _P] + [_I] * 13 + [_P, _P, _P, _P]),
     "mvsb200_deconv3d_s2_kc_fwd": (_I, [_P, _I, _P, _P, _P, _I, _P] + [_I] * 12 + [_P, _I, _P]),
     "mvsb200_conv3d_s1_wgrad": (_I, [_P, _P, _P] + [_I] * 12 + [_P]),
     "mvsb200_conv_out_workspace_floats": (_c.c_int64, []),
@@ -62,6 +63,7 @@ _SIGNATURES = {
     "mvsb200_bn_stats": (_I, [_P, _I, _c.c_int64, _I, _P, _P, _P, _P]),
     "mvsb200_bn_relu_fwd": (_I, [_P, _I, _P, _P, _P, _I, _c.c_int64, _I, _P]),
     "mvsb200_bn_stats_affine": (_I, [_P, _I, _c.c_int64, _I, _P, _P, _P, _P, _c.c_double, _c.c_double, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "mvsb200_bn_finalize_affine": (_I, [_P, _I, _c.c_int64, _I, _P, _P, _c.c_double, _c.c_double, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "mvsb200_bn_stats_geo": (_I, [_P, _I, _c.c_int64, _I, _P, _P, _P, _P, _P]),
     "mvsb200_bn_relu_fwd_crop": (_I, [_P, _I, _P, _P, _P, _I, _c.c_int64, _I, _P, _P]),
     "mvsb200_bn_relu_bwd_crop": (_I, [_P, _I, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _c.c_int64, _I, _P, _P]),

@@ -28,6 +28,17 @@ def _n_rows(c):
     return 16 if c <= 16 else (32 if c <= 32 else 64)
 
 
+_SMS = {}
+
+
+def _sm_count(device):
+    d = torch.device(device)
+    key = d.index if d.index is not None else torch.cuda.current_device()
+    if key not in _SMS:
+        _SMS[key] = torch.cuda.get_device_properties(key).multi_processor_count
+    return _SMS[key]
+
+
 _NAT = list(range(27))                       # filter taps in their natural (kd, kh, kw) order
 _FLIP = [26 - t for t in range(27)]          # ... flipped along all three axes (data gradients)
 
@@ -190,7 +201,7 @@ def _deconv_class_tables(pads, device):
     return hit
 
 
-def conv_transpose3d_s2(x, w, pads, out_dims):
+def conv_transpose3d_s2(x, w, pads, out_dims, stats_out=None):
     """ConvTranspose3d(k=3, stride=2, padding=pads, bias=False) from the box volume x [B,Cin,md,mh,mw] to the first
     `out_dims` voxels per axis of its output, on the tcgen05 kernels.  One launch (deconv3d_s2_tc_kernel: the 8
     output-parity classes side by side in TMEM, every canvas line written once); MVSB200_DECONV=classes selects the
@@ -216,6 +227,16 @@ def conv_transpose3d_s2(x, w, pads, out_dims):
     if n_rows <= 32 and os.environ.get("MVSB200_DECONV", "fused") != "classes" and hasattr(_lib.load(), "mvsb200_deconv3d_s2_fwd"):
         wp = _pack(w, 1, n_rows, _NAT + [-1])            # [k][co][ci] from [Cin, Cout, ...]; slot 27: zeros (DeconvWide, tc_common.cuh)
         ys = (ctypes.c_int64 * 4)(sB, sD, sH, sW)
+        if stats_out is not None and hasattr(_lib.load(), "mvsb200_deconv3d_s2_fwd_stats"):
+            # per-CTA sums of the stored values / their squares per channel, from the kernel's epilogue: the BatchNorm that follows
+            # finalizes them (ops.batchnorm_relu_train(partials=...)) instead of reading the canvas again
+            partials = torch.empty((_sm_count(x.device), 2, cout), dtype=torch.float32, device=x.device)
+            nb = ctypes.c_int(0)
+            with _timed("deconv3d_s2_tc", work):
+                _lib.call("mvsb200_deconv3d_s2_fwd_stats", x_cl.data_ptr(), wp.data_ptr(), y.data_ptr(), B, md, mh, mw, cin, D, h, wd,
+                          cout, n_rows, int(pads[0]), int(pads[1]), int(pads[2]), ys, partials.data_ptr(), ctypes.byref(nb), _stream())
+            stats_out.append((partials, int(nb.value), (D, h, wd)))
+            return y
         with _timed("deconv3d_s2_tc", work):
             _lib.call("mvsb200_deconv3d_s2_fwd", x_cl.data_ptr(), wp.data_ptr(), y.data_ptr(), B, md, mh, mw, cin, D, h, wd, cout,
                       n_rows, int(pads[0]), int(pads[1]), int(pads[2]), ys, _stream())
@@ -301,8 +322,8 @@ class _ConvTranspose3dS2(torch.autograd.Function):
     (conv3d_s2_tc_kernel), the weight gradient goes to the library (or, opt-in, to the tcgen05 strided kernel)."""
 
     @staticmethod
-    def forward(ctx, x, w, pads, out_dims):
-        y = conv_transpose3d_s2(x, w, pads, out_dims)
+    def forward(ctx, x, w, pads, out_dims, stats_out=None):
+        y = conv_transpose3d_s2(x, w, pads, out_dims, stats_out)
         ctx.save_for_backward(x.detach().contiguous(memory_format=torch.channels_last_3d), w)
         ctx.pads = tuple(pads)
         return y
@@ -349,7 +370,7 @@ class _ConvTranspose3dS2(torch.autograd.Function):
                                  ).contiguous(memory_format=torch.channels_last_3d)
                 xs[inner] = x_cl
                 gw = torch.nn.grad.conv3d_weight(gy, w.shape, xs, stride=2, padding=P2).to(w.dtype)
-        return gx, gw, None, None
+        return gx, gw, None, None, None
 
 
 # ---- stride-2 convolution on the central box (the stacked branches conv_{1,2,3}_0) ----------------------------------
@@ -617,7 +638,14 @@ class Tcgen05ConvBackend:
     def conv_transpose3d_alloc(x, w, stride, padding, out_dims):
         if (stride == 2 and x.is_cuda and x.dtype == torch.bfloat16 and x.shape[1] in _CIN_OK and w.shape[1] % 8 == 0
                 and 8 <= w.shape[1] <= 64 and all(p in (1, 2) for p in padding)):
-            return _ConvTranspose3dS2.apply(x, w, tuple(int(p) for p in padding), tuple(int(n) for n in out_dims))
+            import os
+            # MVSB200_DECONV_STATS=0: no epilogue statistics (the BatchNorm that follows then reads the canvas for them, as the
+            # depth-slab path does with its all-reduced sums)
+            stats = [] if os.environ.get("MVSB200_DECONV_STATS", "1") != "0" else None
+            y = _ConvTranspose3dS2.apply(x, w, tuple(int(p) for p in padding), tuple(int(n) for n in out_dims), stats)
+            if stats:
+                y._mvs_bn_partials = stats[0]            # read by regulariser._bn_dense -> ops.batchnorm_relu_train
+            return y
         return conv_backends.TorchConvBackend.conv_transpose3d_alloc(x, w if w.dtype == x.dtype else w.to(x.dtype), stride, padding, out_dims)
 
     @classmethod

@@ -333,7 +333,7 @@ class _BatchNormReLU(torch.autograd.Function):
     `crop` = ((d0,d1),(h0,h1),(w0,w1)): y (and the incoming gradient) exist only on that box of the canvas."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, eps, relu, crop, canvas, running=None, momentum=0.1):
+    def forward(ctx, x, weight, bias, eps, relu, crop, canvas, running=None, momentum=0.1, partials=None):
         _need_cuda(x, "BatchNorm input")
         _need_cuda(weight, "BatchNorm weight")
         xr, _, C = _rows(x.detach())
@@ -358,10 +358,17 @@ class _BatchNormReLU(torch.autograd.Function):
                     and (nbt is None or (nbt.is_cuda and nbt.dtype == torch.int64))):
                 raise _lib.MvsB200Error("BatchNorm running statistics must be contiguous fp32 CUDA tensors (int64 counter)")
         ws = _bn_workspace(dev)
-        with _timed("bn_stats"):
-            _lib.call("mvsb200_bn_stats_affine", xr.data_ptr(), _DT[xr.dtype], M, C, ws.data_ptr(), geo if canvas != alloc else None,
-                      gamma.data_ptr(), beta.data_ptr(), float(eps), float(momentum), _ptr(rm), _ptr(rv), _ptr(nbt), mean.data_ptr(),
-                      var.data_ptr(), invstd.data_ptr(), scale.data_ptr(), shift.data_ptr(), _stream())
+        if partials is not None and tuple(partials[2]) == canvas and partials[0].shape[-1] == C:
+            # the producer kernel (transposed convolution) already summed what it stored: finalize only, no pass over the canvas
+            with _timed("bn_stats"):
+                _lib.call("mvsb200_bn_finalize_affine", partials[0].data_ptr(), int(partials[1]), M, C, gamma.data_ptr(), beta.data_ptr(),
+                          float(eps), float(momentum), _ptr(rm), _ptr(rv), _ptr(nbt), mean.data_ptr(), var.data_ptr(), invstd.data_ptr(),
+                          scale.data_ptr(), shift.data_ptr(), _stream())
+        else:
+            with _timed("bn_stats"):
+                _lib.call("mvsb200_bn_stats_affine", xr.data_ptr(), _DT[xr.dtype], M, C, ws.data_ptr(), geo if canvas != alloc else None,
+                          gamma.data_ptr(), beta.data_ptr(), float(eps), float(momentum), _ptr(rm), _ptr(rv), _ptr(nbt),
+                          mean.data_ptr(), var.data_ptr(), invstd.data_ptr(), scale.data_ptr(), shift.data_ptr(), _stream())
         if plain:
             y = torch.empty_like(xr)
             with _timed("bn_relu_fwd"):
@@ -401,20 +408,22 @@ class _BatchNormReLU(torch.autograd.Function):
                           scale.data_ptr(), shift.data_ptr(), mean.data_ptr(), invstd.data_ptr(), gamma.data_ptr(),
                           _bn_workspace(dev).data_ptr(), dbeta.data_ptr(), dgamma.data_ptr(), dx.data_ptr(),
                           int(ctx.relu), M, C, _geo12(*ctx.geo), _stream())
-        return dx, dgamma, dbeta, None, None, None, None, None, None
+        return dx, dgamma, dbeta, None, None, None, None, None, None, None
 
 
-def batchnorm_relu_train(x, weight, bias, eps=1e-5, relu=True, crop=None, canvas=None, running=None, momentum=0.1):
+def batchnorm_relu_train(x, weight, bias, eps=1e-5, relu=True, crop=None, canvas=None, running=None, momentum=0.1, partials=None):
     """-> (y, batch mean [C], biased batch variance [C]); y has x's dtype (fp32 or bf16), channels_last_3d.
     canvas = (D,h,w) <= x's spatial dims: the statistics volume (x may carry allocation slack beyond it);
     crop = ((d0,d1),(h0,h1),(w0,w1)): full-canvas statistics, y only on that box.
     running = (running_mean, running_var, num_batches_tracked): updated in place as torch.nn.BatchNorm does in train mode
-    (momentum, unbiased variance), inside the statistics' finalize launch."""
+    (momentum, unbiased variance), inside the statistics' finalize launch.
+    partials = (per-CTA sums [n, 2, C], n, (D,h,w)) left by the kernel that produced x (conv3d_sm100.conv_transpose3d_s2): the
+    statistics are finalized from them, x is not read for them."""
     if crop is not None:
         crop = tuple((int(a), int(b)) for a, b in crop)
     if canvas is not None:
         canvas = tuple(int(n) for n in canvas)
-    return _BatchNormReLU.apply(x, weight, bias, float(eps), bool(relu), crop, canvas, running, float(momentum))
+    return _BatchNormReLU.apply(x, weight, bias, float(eps), bool(relu), crop, canvas, running, float(momentum), partials)
 
 
 def affine_relu(x, scale, shift, relu=True):

@@ -123,7 +123,8 @@ class CostVolumeReg(nn.Module):
             box = None if crop is None else tuple((c.start, c.stop) for c in crop)
             # the running statistics (momentum, unbiased variance, counter) are updated inside the statistics' finalize launch
             y, _, _ = ops.batchnorm_relu_train(x, bn.weight, bn.bias, bn.eps, relu=True, crop=box, canvas=canvas,
-                                               running=(bn.running_mean, bn.running_var, bn.num_batches_tracked), momentum=bn.momentum)
+                                               running=(bn.running_mean, bn.running_var, bn.num_batches_tracked), momentum=bn.momentum,
+                                               partials=getattr(x, "_mvs_bn_partials", None))
             return y
         if canvas is not None:
             x = x[..., :canvas[0], :canvas[1], :canvas[2]]

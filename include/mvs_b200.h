@@ -184,6 +184,14 @@ int mvsb200_deconv3d_s2_fwd(const void* x, const void* w_packed, void* y, int B,
                             int Do, int Ho, int Wo, int cout, int n_rows, int pad_d, int pad_h, int pad_w,
                             const int64_t* y_strides4_host, void* stream);
 
+/* mvsb200_deconv3d_s2_fwd that also writes, per CTA, the sums of the stored values and of their squares per output channel over
+ * the written canvas: stats [n_blocks][2][cout] fp32 (NULL: none), n_blocks returned through n_blocks_host (<= the SM count: size
+ * the buffer for that).  With mvsb200_bn_finalize_affine the BatchNorm that follows the transposed convolution
+ * (scripts/model.py:115-121: ReLU(BN(deconv))) needs no statistics pass over the canvas. */
+int mvsb200_deconv3d_s2_fwd_stats(const void* x, const void* w_packed, void* y, int B, int Di, int Hi, int Wi, int Cin,
+                                  int Do, int Ho, int Wo, int cout, int n_rows, int pad_d, int pad_h, int pad_w,
+                                  const int64_t* y_strides4_host, float* stats, int* n_blocks_host, void* stream);
+
 /* Stride-2 TRANSPOSED convolution whose input channels come as up to three K CHUNKS of 16 / 32 / 64 channels inside a voxel
  * row of x_cs channels (deconv3d_s2_kc_kernel, csrc/conv3d_s2_bwd.cu): the data gradient of the stacked stride-2 branches
  * conv_{1,2,3}_0 (scripts/model.py:104-110) -- 16 + 32 + 64 gradient channels on the central box -> the 32-channel canvas --
@@ -265,6 +273,13 @@ int mvsb200_bn_stats_affine(const void* x, int dtype, int64_t M, int C, float* w
                             const float* gamma, const float* beta, double eps, double momentum, float* running_mean,
                             float* running_var, int64_t* num_batches_tracked, float* mean, float* var, float* invstd,
                             float* scale, float* shift, void* stream);
+
+/* The finalize launch of mvsb200_bn_stats_affine alone, on per-CTA partial sums [n_blocks][2][C] a producer kernel already wrote
+ * (mvsb200_deconv3d_s2_fwd_stats); M = the number of voxels per channel the sums run over. */
+int mvsb200_bn_finalize_affine(const float* partials, int n_blocks, int64_t M, int C, const float* gamma, const float* beta,
+                               double eps, double momentum, float* running_mean, float* running_var,
+                               int64_t* num_batches_tracked, float* mean, float* var, float* invstd, float* scale,
+                               float* shift, void* stream);
 
 /* Geometry-aware variants.  The canvas [D,h,w] (what the statistics are taken over; M = B*D*h*w) sits at the origin
  * of a possibly larger allocation [Da,ha,wa] (the library's stride-2 transposed convolution returns one extra

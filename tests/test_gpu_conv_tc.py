@@ -225,3 +225,39 @@ def test_filter_packing_kernel(co, ci):
     reft = torch.zeros(28, n_rows, n, dtype=torch.bfloat16, device=DEV)
     reft[:27, :co] = wt.permute(2, 3, 4, 1, 0).reshape(27, co, ci)[:, :, c0:c0 + n].to(torch.bfloat16)
     assert torch.equal(c._pack(wt, 1, n_rows, c._NAT + [-1], c0=c0, cols_real=n), reft)
+
+
+@pytest.mark.parametrize("cin,cout", [(64, 32), (32, 16), (16, 8)])
+def test_transposed_conv_epilogue_statistics_feed_the_batchnorm(cin, cout):
+    """mvsb200_deconv3d_s2_fwd_stats + mvsb200_bn_finalize_affine: the per-channel sums the transposed convolution's epilogue takes
+    of what it writes give the following train-mode BatchNorm the mean / variance / output (and running statistics) of the
+    statistics pass over the canvas, up to the rounding of the stores."""
+    from mvs_b200 import ops
+    from mvs_b200.regulariser import central_region
+    dims = (12, 10, 14)
+    reg = [central_region(n) for n in dims]
+    m = [hi - lo + 1 for lo, hi, _ in reg]
+    pads = tuple(L for _, _, L in reg)
+    g = torch.Generator().manual_seed(cin * 7 + cout)
+    x = torch.randn(2, cin, *m, generator=g).to(DEV).to(torch.bfloat16).contiguous(memory_format=torch.channels_last_3d)
+    wt = (torch.randn(cin, cout, 3, 3, 3, generator=g) / (8 * cin) ** 0.5).to(DEV)
+    gamma, beta = (torch.rand(cout, generator=g) + 0.5).to(DEV), torch.randn(cout, generator=g).to(DEV)
+    U = conv_backends.get("tcgen05").conv_transpose3d_alloc(x, wt, 2, pads, dims)
+    part = getattr(U, "_mvs_bn_partials", None)
+    assert part is not None and part[2] == dims and part[0].shape[-1] == cout
+    rm1, rv1, n1 = torch.zeros(cout, device=DEV), torch.ones(cout, device=DEV), torch.zeros((), dtype=torch.int64, device=DEV)
+    rm2, rv2, n2 = rm1.clone(), rv1.clone(), n1.clone()
+    n0 = mvs_b200.launch_count()
+    y1, mean1, var1 = ops.batchnorm_relu_train(U, gamma, beta, canvas=dims, running=(rm1, rv1, n1), partials=part)
+    used = mvs_b200.launch_count() - n0
+    y2, mean2, var2 = ops.batchnorm_relu_train(U, gamma, beta, canvas=dims, running=(rm2, rv2, n2))
+    assert used == (mvs_b200.launch_count() - n0 - used) - 1                  # one launch fewer: no statistics pass
+    # the epilogue sums its fp32 accumulators, the statistics pass the bf16 values that were stored: they differ by the (unbiased,
+    # 2^-9 relative) rounding of the stores -- a few 1e-5 of a standard deviation on the mean, ~1e-4 relative on the variance
+    Uf = U.float()
+    std = float(Uf.std())
+    assert float((mean1 - Uf.mean((0, 2, 3, 4))).abs().max()) < 2e-4 * std
+    assert torch.allclose(var1, Uf.var((0, 2, 3, 4), unbiased=False), rtol=1e-3, atol=1e-6)
+    assert float((mean1 - mean2).abs().max()) < 2e-4 * std and torch.allclose(var1, var2, rtol=1e-3, atol=1e-6)
+    assert torch.allclose(y1.float(), y2.float(), rtol=2e-2, atol=2e-2)
+    assert float((rm1 - rm2).abs().max()) < 2e-5 * std and torch.allclose(rv1, rv2, rtol=1e-4, atol=1e-6) and int(n1) == int(n2) == 1
