@@ -33,6 +33,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "deep-multiview-depth-estimation_b200"))
 
 K1_NCU, K3_NCU = "r01_k1_fwd2_ncu.json", "r01_k3_kdn_ncu.json"      # committed ncu --set full captures (traffic)
+_E2E_DIAG = int(os.environ.get("MVSB200_E2E_DIAG", "0"))   # diagnostics of the host-fed loop: 1 = no H2D prefetch, 2 = no loss read-back
 TC_KERNELS = ("conv3d_s1_tc", "deconv3d_s2_tc", "conv3d_s2_tc", "conv3d_s1_wgrad_tc", "conv3d_s2_wgrad_tc")     # tcgen05 convolution kernels
 
 WORKLOADS = {
@@ -281,13 +282,19 @@ def run_b200(args, rank, world, local_rank, workload=None, light=False):
             prefetch(cur)
             feed["primed"] = True
         torch.cuda.current_stream().wait_event(ready[cur])
-        prefetch(cur ^ 1)                                  # next step's H2D overlaps this step's kernels
         loss = step(stage[cur][0], stage[cur][1])
         consumed[cur].record()
+        # the next step's 47 MB H2D copy is issued AFTER this step's launches: the step's own small H2D copies (sweep geometry,
+        # on the compute stream) share the host-to-device copy engine with it and would otherwise queue behind it -- the whole
+        # copy (0.86 ms at PCIe 5 rate) then sat in front of every step instead of under it (measured: MVSB200_E2E_DIAG=1)
+        if not (_E2E_DIAG & 1):
+            prefetch(cur ^ 1)
+        else:
+            ready[cur ^ 1].record()
         i = pending["n"]
         loss_slots[i & 1].copy_(loss.reshape(1), non_blocking=True)
         loss_done[i & 1].record()
-        if i > 0:
+        if i > 0 and not (_E2E_DIAG & 2):
             loss_done[(i - 1) & 1].synchronize()           # the user reads the previous step's loss
             loss_host.copy_(loss_slots[(i - 1) & 1])
         pending["n"] = i + 1
