@@ -262,10 +262,18 @@ def run_b200(args, rank, world, local_rank, workload=None, light=False):
     consumed = [torch.cuda.Event(), torch.cuda.Event()]
     feed = {"slot": 0, "primed": False}
 
-    def prefetch(slot_):
+    def prefetch(slot_, after=None):
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(consumed[slot_])        # the step that read this staging pair has finished with it
-            stage[slot_][0].copy_(img_host, non_blocking=True)
+            if after is not None:
+                copy_stream.wait_event(after)              # ... and the running step has reached its backward pass
+            if _E2E_DIAG & 4:                              # diagnostics: a quarter of the image bytes
+                stage[slot_][0][:3].copy_(img_host[:3], non_blocking=True)
+            elif _E2E_DIAG & 8:                            # diagnostics: the images in four separate copies
+                for q4 in range(4):
+                    stage[slot_][0][3 * q4:3 * q4 + 3].copy_(img_host[3 * q4:3 * q4 + 3], non_blocking=True)
+            else:
+                stage[slot_][0].copy_(img_host, non_blocking=True)
             stage[slot_][1].copy_(gt_host, non_blocking=True)
             ready[slot_].record(copy_stream)
 
@@ -288,7 +296,7 @@ def run_b200(args, rank, world, local_rank, workload=None, light=False):
         # on the compute stream) share the host-to-device copy engine with it and would otherwise queue behind it -- the whole
         # copy (0.86 ms at PCIe 5 rate) then sat in front of every step instead of under it (measured: MVSB200_E2E_DIAG=1)
         if not (_E2E_DIAG & 1):
-            prefetch(cur ^ 1)
+            prefetch(cur ^ 1, getattr(gstep, "mid_event", None) if (gstep is not None and not (_E2E_DIAG & 16)) else None)
         else:
             ready[cur ^ 1].record()
         i = pending["n"]
@@ -485,7 +493,10 @@ def run_b200(args, rank, world, local_rank, workload=None, light=False):
                 "e2e": {"value": e2e_value, "unit": "depth maps/s", "ms_per_step": ms_e2e / steps,
                         "h2d_bytes_per_step": img_host.numel() * 4 + gt_host.numel() * 4, "d2h_bytes_per_step": 4,
                         "input_pipeline": "pinned host buffers, double-buffered device staging: the H2D copy of step i+1 runs on a "
-                                          "side stream while step i computes; the loss of every step is copied to the host and read there one step "
+                                          "side stream while step i computes -- it starts when step i reaches its backward pass (an external "
+                                          "event recorded inside the step's CUDA graph), under the regulariser's long kernels: under the short "
+                                          "launches at the start of a step the saturated PCIe link cost 0.6 ms per step; "
+                                          "the loss of every step is copied to the host and read there one step "
                                           "behind the launches (the final read falls inside the timed region's closing synchronize)"},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "roofline_k1": roofline_k1,
                 "roofline_k1_fp32": roofline_k1_fp32, "roofline_k2": roofline_k2, "kernels": kern,

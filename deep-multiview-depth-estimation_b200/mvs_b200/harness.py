@@ -138,6 +138,13 @@ class GraphedTrainStep:
         self.warmup, self._lib = warmup, _lib
         self.params = [p for p in model.parameters() if p.requires_grad]
         self.reducer, self.optimizer = reducer, optimizer
+        # recorded INSIDE the replay, between forward and backward (an external event node of the graph): a loader stream that
+        # waits on it places the next batch's host-to-device copy under the regulariser's long kernels instead of under the many
+        # short launches at the start of a step, which a saturated PCIe link delays (bench.py, host-fed loop)
+        try:
+            self.mid_event = torch.cuda.Event(external=True)
+        except TypeError:                                  # older torch: no external events
+            self.mid_event = None
         if reducer is not None:
             reducer.attach_grads()                         # .grad of every parameter := view into the flat bucket
 
@@ -165,6 +172,8 @@ class GraphedTrainStep:
             self.reducer.bucket.zero_()
         initial, refined = self.model(self.img, None, None, None, self.d_min, self.d_int, self.B, self.V, sweep=self.sweep)
         loss, _, _ = loss_fcn(self.gt, initial, refined)
+        if self.mid_event is not None and torch.cuda.is_current_stream_capturing():
+            self.mid_event.record()
         loss.backward()
         if self.reducer is not None:
             self.reducer.reduce_attached()                 # all-reduce + average of the flat bucket, in place
