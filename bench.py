@@ -296,7 +296,8 @@ def run_b200(args, rank, world, local_rank, workload=None, light=False):
         # on the compute stream) share the host-to-device copy engine with it and would otherwise queue behind it -- the whole
         # copy (0.86 ms at PCIe 5 rate) then sat in front of every step instead of under it (measured: MVSB200_E2E_DIAG=1)
         if not (_E2E_DIAG & 1):
-            prefetch(cur ^ 1, getattr(gstep, "mid_event", None) if (gstep is not None and not (_E2E_DIAG & 16)) else None)
+            runner = gstep if gstep is not None else (ginf if ginf is not None else slab)
+            prefetch(cur ^ 1, getattr(runner, "mid_event", None) if not (_E2E_DIAG & 16) else None)
         else:
             ready[cur ^ 1].record()
         i = pending["n"]

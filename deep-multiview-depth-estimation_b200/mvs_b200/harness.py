@@ -79,6 +79,9 @@ class MVSNet(nn.Module):
         with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):        # out-of-scope 2D net: stock torch AMP
             feats = self.feature_encoder(nn_input.contiguous(memory_format=torch.channels_last))
         feats = feats.float()
+        ev = getattr(self, "after_encoder_event", None)          # GraphedInference: where the next batch's H2D copy may start
+        if ev is not None and torch.cuda.is_current_stream_capturing():
+            ev.record()
         warped, d_batch, ref_views = api.homography_warping(K_batch, R_batch, T_batch, d_min, d_int, feats,
                                                             batch_size, n_views, self.d_num, self.d_scale, sweep=sweep)
         vol_dtype = torch.bfloat16 if self.precision == "bf16" else torch.float32
@@ -240,10 +243,18 @@ class GraphedInference:
         self.d_int = torch.ones(batch_size, 1, 1, 1, device=device)
         self.dims = (H // 4, W // 4)
         self.sweep, self.graph, self.out, self.launches = None, None, None, 0
+        try:        # external event recorded inside the replay after the 2D encoder (see GraphedTrainStep.mid_event)
+            self.mid_event = torch.cuda.Event(external=True)
+        except TypeError:
+            self.mid_event = None
 
     @torch.no_grad()
     def _fwd(self):
-        return self.model(self.img, None, None, None, self.d_min, self.d_int, self.B, self.V, sweep=self.sweep)
+        self.model.after_encoder_event = self.mid_event
+        try:
+            return self.model(self.img, None, None, None, self.d_min, self.d_int, self.B, self.V, sweep=self.sweep)
+        finally:
+            self.model.after_encoder_event = None
 
     @torch.no_grad()
     def run(self, img, K, R, T, d_min, d_int):
@@ -289,6 +300,10 @@ class DepthSlabMVSNet:
         self.reg = DepthSlabCostVolumeReg(model.cost_volume_reg, self.comm)
         self.use_graph, self._graphed, self._sweep, self._out = bool(graph), None, None, None
         self.launches = 0
+        try:
+            self.mid_event = torch.cuda.Event(external=True) if graph else None
+        except TypeError:
+            self.mid_event = None
 
     def release(self):
         """Drop the captured graph (it holds NCCL work: do this before destroy_process_group())."""
@@ -323,6 +338,8 @@ class DepthSlabMVSNet:
         from .depth_slab import slab_cost_fn
         m = self.model
         feats = self.encode(nn_input)
+        if self.mid_event is not None and torch.cuda.is_current_stream_capturing():
+            self.mid_event.record()                              # where the next sample's H2D copy may start (bench.py)
         h, w = feats.shape[-2:]
         vol_dtype = torch.bfloat16 if m.precision == "bf16" else torch.float32
         initial, prob_rows, rows = self.reg.forward(slab_cost_fn(feats, sweep, vol_dtype), sweep.d_batch_dev, 1, m.d_num, h, w)
