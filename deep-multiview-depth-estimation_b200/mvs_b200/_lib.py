@@ -59,6 +59,10 @@ _SIGNATURES = {
     "mvsb200_masked_l1_workspace_floats": (_c.c_int64, [_I]),
     "mvsb200_masked_l1_fwd": (_I, [_P, _P, _P, _I, _I, _P, _P, _P]),
     "mvsb200_masked_l1_bwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _P, _P, _P]),
+    "mvsb200_refine_input_fwd": (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _I, _I, _I, _I, _P, _P, _P]),
+    "mvsb200_refine_input_bwd": (_I, [_P, _I, _P, _P, _I, _I, _P, _P]),
+    "mvsb200_refine_output_fwd": (_I, [_P, _I, _P, _P, _P, _I, _I, _P, _P]),
+    "mvsb200_refine_output_bwd": (_I, [_P, _P, _I, _I, _I, _P, _P, _P]),
     "mvsb200_bn_workspace_floats": (_c.c_int64, []),
     "mvsb200_bn_stats": (_I, [_P, _I, _c.c_int64, _I, _P, _P, _P, _P]),
     "mvsb200_bn_relu_fwd": (_I, [_P, _I, _P, _P, _P, _I, _c.c_int64, _I, _P]),

@@ -6,11 +6,12 @@ and scripts/loss.py:4-41.  Only the four hot-path calls in `forward` are mvs_b20
 """
 from __future__ import annotations
 
+import os
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import api
+from . import api, refine
 from .regulariser import CostVolumeReg
 
 
@@ -88,16 +89,13 @@ class MVSNet(nn.Module):
         cost = api.assemble_cost_volume(warped, n_views, vol_dtype)
         prob = self.cost_volume_reg(cost)
         initial = api.extract_depth_map(prob, d_batch, self.n_depth_est)
-        dev = initial.device
-        d_trans = d_min.to(dev)
-        d_span = d_int.to(dev) * self.d_num * self.d_scale
-        norm = (initial - d_trans) / d_span
-        h, w = initial.shape[-2:]
-        ref_img = F.interpolate(nn_input[::n_views], (h, w), mode="bilinear", align_corners=False)   # == nn_input[ref_views]
-        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
-            refined = self.depthmap_refine(torch.cat((norm, ref_img), 1))
-        refined = refined.float() * d_span + d_trans
-        return initial, refined
+        return initial, refine.refine_depth(self.depthmap_refine, initial, nn_input, n_views, d_min, d_int, self.d_num, self.d_scale,
+                                            bf16=self.precision == "bf16")
+
+    def refine(self, initial, nn_input, n_views, d_trans, d_span):
+        """model.py:190-205 on depth offsets / spans already on the device (mvs_b200/refine.py): native on the
+        bf16 path with train-mode BatchNorm (what train.py and test.py:61 run), the stock torch layers otherwise."""
+        return refine.refine_spans(self.depthmap_refine, initial, nn_input, n_views, d_trans, d_span, bf16=self.precision == "bf16")
 
 
 def _snapshot(tensors):
@@ -343,12 +341,7 @@ class DepthSlabMVSNet:
         h, w = feats.shape[-2:]
         vol_dtype = torch.bfloat16 if m.precision == "bf16" else torch.float32
         initial, prob_rows, rows = self.reg.forward(slab_cost_fn(feats, sweep, vol_dtype), sweep.d_batch_dev, 1, m.d_num, h, w)
-        norm = (initial - d_trans) / d_span
-        ref_img = F.interpolate(nn_input[:1], (h, w), mode="bilinear", align_corners=False)
-        amp = m.precision == "bf16" and nn_input.is_cuda
-        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):          # replicated: 4-channel 400x296 maps
-            refined = m.depthmap_refine(torch.cat((norm, ref_img), 1))
-        return initial, refined.float() * d_span + d_trans
+        return initial, m.refine(initial, nn_input, nn_input.shape[0], d_trans, d_span)      # replicated: 4-channel 400x296 maps
 
     @torch.no_grad()
     def forward(self, nn_input, K_batch, R_batch, T_batch, d_min, d_int, n_views):

@@ -342,6 +342,24 @@ int mvsb200_masked_l1_fwd(const float* gt, const float* initial, const float* re
 int mvsb200_masked_l1_bwd(const float* gt, const float* initial, const float* refined, const float* workspace,
                           const float* g3, int B, int n, float* g_initial, float* g_refined, void* stream);
 
+/* ---- f2: the glue either side of the depth-refinement network (scripts/model.py:190-205) -------------
+ * refine_input_fwd:  norm = (initial - d_min[b]) / span[b] (fp32 [B, h*w]) and the network's input as bf16 channel-last rows
+ *                    [B, h, w, cp] (cp = 8 or 16): channel 0 = norm, 1..3 = the reference image (view b * n_views of `images`, fp32
+ *                    [N, 3, H, W] with the given element strides) resized to h x w as torch's bilinear interpolate (align_corners =
+ *                    False) does, the remaining channels zero (what the K = 16 tensor-core convolution reads).
+ * refine_input_bwd:  g_initial = (g_rows[., 0] + g_norm) / span[b]; either gradient may be NULL.
+ * refine_output_fwd: refined = (res_rows[., 0] + norm) * span[b] + d_min[b]   (model.py:150-151 and :203).
+ * refine_output_bwd: g_rows [B*n, cr] bf16 (channel 0 = g * span[b], others zero; cr = 8 or 16) and g_norm = g * span[b]. */
+int mvsb200_refine_input_fwd(const float* initial, const float* images, const int64_t* image_strides4_host, int n_views, int H, int W,
+                             const float* d_min, const float* span, int B, int h, int w, int cp, void* rows, float* norm,
+                             void* stream);
+int mvsb200_refine_input_bwd(const void* g_rows, int cp, const float* g_norm, const float* span, int B, int n, float* g_initial,
+                             void* stream);
+int mvsb200_refine_output_fwd(const void* res_rows, int cr, const float* norm, const float* d_min, const float* span, int B, int n,
+                              float* refined, void* stream);
+int mvsb200_refine_output_bwd(const float* g_refined, const float* span, int B, int n, int cr, void* g_rows, float* g_norm,
+                              void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,226 @@
+"""SURVEY §8 row f2 -- depth refinement and the glue around it (model.py:129-152, :190-205).
+
+Golden: tests/golden/refine.npz, produced by the UNMODIFIED reference on the CPU in fp32 (oracle/make_golden_refine.py): inputs,
+weights, the network's 4-channel input, the refined map, the gradients of the initial depth map and of every parameter, the
+running statistics after the pass.
+
+CPU: the harness's stock-torch branch reproduces the golden (so the module the native path is compared with IS the reference's).
+GPU: the glue kernels (csrc/refine.cu) against the golden and against torch at a non-integer resize ratio; the whole native
+refinement (tcgen05 convolutions, bf16 operands, fp32 accumulation) against the golden within the bf16 convolution tolerance
+`north_star` states (1e-2, here on the normalised depth), gradients within 2e-2 of their largest entry."""
+import os
+import types
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import mvs_b200
+from mvs_b200 import harness
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "refine.npz")
+DEV = "cuda:0"
+
+
+def _golden_net(g, device):
+    net = harness.DepthRefinement().to(device).train()
+    sd = {k[3:]: torch.from_numpy(np.asarray(g[k])) for k in g.files if k.startswith("w0.")}
+    net.load_state_dict(sd)                     # the reference's own state_dict keys (Conv2d / BatchNorm2d / ReLU indices)
+    return net
+
+
+def _owner(net, precision):
+    return types.SimpleNamespace(precision=precision, depthmap_refine=net)
+
+
+def test_stock_branch_reproduces_the_reference():
+    g = np.load(GOLD)
+    net = _golden_net(g, "cpu")
+    initial = torch.from_numpy(g["initial"]).requires_grad_(True)
+    d_min, d_int = torch.from_numpy(g["d_min"]), torch.from_numpy(g["d_int"])
+    span = d_int * int(g["d_num"]) * float(g["d_scale"])
+    refined = harness.MVSNet.refine(_owner(net, "fp32"), initial, torch.from_numpy(g["nn_input"]), int(g["n_views"]), d_min, span)
+    assert torch.allclose(refined, torch.from_numpy(g["refined"]), rtol=0, atol=1e-4)
+    refined.backward(torch.from_numpy(g["g_refined"]))
+    assert torch.allclose(initial.grad, torch.from_numpy(g["g_initial"]), rtol=1e-4, atol=1e-5)
+    for n, p in net.named_parameters():
+        ref = torch.from_numpy(g["g." + n])
+        assert (p.grad - ref).abs().max() <= 1e-4 * max(float(ref.abs().max()), 1e-3), n
+    for k in g.files:
+        if k.startswith("w1."):
+            assert torch.allclose(net.state_dict()[k[3:]].float(), torch.from_numpy(np.asarray(g[k])).float(), rtol=1e-5, atol=1e-6), k
+
+
+def test_c_abi_exports_the_glue():
+    from mvs_b200 import _lib
+    lib = _lib.load()
+    for name in ("mvsb200_refine_input_fwd", "mvsb200_refine_input_bwd", "mvsb200_refine_output_fwd", "mvsb200_refine_output_bwd"):
+        assert hasattr(lib, name), name
+
+
+@pytest.mark.gpu
+def test_glue_kernels_against_the_golden():
+    from mvs_b200 import refine
+    g = np.load(GOLD)
+    initial = torch.from_numpy(g["initial"]).to(DEV).requires_grad_(True)
+    images = torch.from_numpy(g["nn_input"]).to(DEV)
+    d_min = torch.from_numpy(g["d_min"]).to(DEV)
+    span = (torch.from_numpy(g["d_int"]) * int(g["d_num"]) * float(g["d_scale"])).to(DEV)
+    rows, norm = refine.refine_input(initial, images, int(g["n_views"]), d_min, span)
+    want = torch.from_numpy(g["refine_input"]).to(DEV)
+    assert rows.shape == (2, 16, 1, 12, 16) and rows.dtype == torch.bfloat16 and rows.is_contiguous(memory_format=torch.channels_last_3d)
+    assert torch.allclose(norm, want[:, :1], rtol=0, atol=1e-6)
+    got = rows[:, :4, 0].float()
+    assert (got - want).abs().max().item() <= 2.0 ** -8 * max(1.0, float(want.abs().max()))      # one bf16 rounding
+    assert torch.equal(got, want.to(torch.bfloat16).float()) or (got - want.to(torch.bfloat16).float()).abs().max().item() <= 2.0 ** -7
+    assert torch.count_nonzero(rows[:, 4:]).item() == 0
+    # the residual rows: channel 0 carries the network's output
+    res = torch.zeros(2, 8, 1, 12, 16, dtype=torch.bfloat16, device=DEV).contiguous(memory_format=torch.channels_last_3d)
+    r0 = torch.randn(2, 12, 16, device=DEV).to(torch.bfloat16)
+    res[:, 0, 0] = r0
+    res.requires_grad_(True)
+    out = refine.refine_output(res, norm, d_min, span)
+    want_out = (r0.float().unsqueeze(1) + norm.detach()) * span + d_min
+    assert torch.allclose(out, want_out, rtol=1e-6, atol=1e-4)
+    gg = torch.randn_like(out)
+    out.backward(gg)
+    assert torch.allclose(res.grad[:, 0, 0].float(), (gg * span)[:, 0].to(torch.bfloat16).float())
+    assert torch.count_nonzero(res.grad[:, 1:]).item() == 0
+    assert torch.allclose(initial.grad, gg, rtol=1e-6, atol=1e-7)        # d refined / d initial through norm alone: span / span
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dims", [((37, 53), (10, 13)), ((16, 20), (16, 20)), ((9, 11), (20, 31)), ((1184, 1600), (296, 400))])
+def test_resize_matches_torch_bilinear(dims):
+    from mvs_b200 import refine
+    (H, W), (h, w) = dims
+    gen = torch.Generator().manual_seed(H * 7 + w)
+    B, V = 2, 2
+    images = torch.rand(B * V, 3, H, W, generator=gen).to(DEV)
+    if H == 37:
+        images = images.contiguous(memory_format=torch.channels_last)          # strides are honoured
+    initial = torch.rand(B, 1, h, w, generator=gen).to(DEV)
+    zeros, ones = torch.zeros(B, device=DEV), torch.ones(B, device=DEV)
+    rows, norm = refine.refine_input(initial, images, V, zeros, ones)
+    want = F.interpolate(images[::V], (h, w), mode="bilinear", align_corners=False)
+    got = rows[:, 1:4, 0].float()
+    assert (got - want.to(torch.bfloat16).float()).abs().max().item() <= 2.0 ** -8        # at most one bf16 step on values in [0, 1)
+    assert torch.equal(norm, initial)
+
+
+def _rel_l2(a, b):
+    return float((a.float() - b.float()).norm() / b.float().norm().clamp_min(1e-12))
+
+
+@pytest.mark.gpu
+def test_native_refinement_against_the_golden(monkeypatch):
+    """Forward: within 1e-2 of the reference's fp32 result.  Gradients: bf16 activations flip ReLU masks on these 12x16 maps, so
+    ANY bf16 evaluation sits ~10 % (of the largest entry) away from the fp32 gradients -- the native path must be as close to the
+    golden as the stock bf16-autocast layers are (relative L2 error at most 1.5x theirs), evaluated here on the same weights."""
+    from mvs_b200 import ops
+    g = np.load(GOLD)
+    images = torch.from_numpy(g["nn_input"]).to(DEV)
+    d_min = torch.from_numpy(g["d_min"]).to(DEV)
+    span = (torch.from_numpy(g["d_int"]) * int(g["d_num"]) * float(g["d_scale"])).to(DEV)
+    want = torch.from_numpy(g["refined"]).to(DEV)
+    runs = {}
+    for mode in ("native", "torch"):
+        monkeypatch.setenv("MVSB200_REFINE", mode)
+        net = _golden_net(g, DEV)
+        initial = torch.from_numpy(g["initial"]).to(DEV).requires_grad_(True)
+        ops.EVENTS = {}
+        try:
+            refined = harness.MVSNet.refine(_owner(net, "bf16"), initial, images, int(g["n_views"]), d_min, span)
+            refined.backward(torch.from_numpy(g["g_refined"]).to(DEV))
+            torch.cuda.synchronize()
+            launched = {k: len(v) for k, v in ops.EVENTS.items()}
+        finally:
+            ops.EVENTS = None
+        runs[mode] = (refined.detach(), initial.grad, dict(net.named_parameters()), net.state_dict(), launched)
+    refined, g_init, params, state, launched = runs["native"]
+    # the native path ran: 4 convolutions forward, 4 data gradients, 4 weight gradients, the glue each way
+    assert launched.get("conv3d_s1_tc") == 8 and launched.get("conv3d_s1_wgrad_tc") == 4 and launched.get("refine_glue") == 4, launched
+    assert "conv3d_s1_tc" not in runs["torch"][4]
+    want_norm = (want - d_min) / span                                        # in units of the normalised depth: values up to ~2
+    err_norm = ((refined - want) / span).abs().max().item()
+    assert err_norm <= 1e-2 * max(1.0, float(want_norm.abs().max())), err_norm
+    ref = torch.from_numpy(g["g_initial"]).to(DEV)
+    e_nat, e_stock = _rel_l2(g_init, ref), _rel_l2(runs["torch"][1], ref)
+    assert e_nat <= max(1.5 * e_stock, 2e-2), (e_nat, e_stock)
+    for n, p in params.items():
+        ref = torch.from_numpy(g["g." + n]).to(DEV)
+        assert p.grad is not None and p.grad.shape == ref.shape, n
+        e_nat, e_stock = _rel_l2(p.grad, ref), _rel_l2(runs["torch"][2][n].grad, ref)
+        assert e_nat <= max(1.5 * e_stock, 2e-2), (n, e_nat, e_stock)
+    for k in g.files:                                                       # running statistics advance as torch's do
+        if k.startswith("w1."):
+            got, exp = state[k[3:]].float().cpu(), torch.from_numpy(np.asarray(g[k])).float()
+            assert torch.allclose(got, exp, rtol=2e-2, atol=2e-3), k
+
+
+@pytest.mark.gpu
+def test_native_refinement_matches_the_stock_layers_at_full_size(monkeypatch):
+    """cfg2's shapes (B = 4, 160x128 maps from 640x512 images): native against the stock bf16 layers on the same weights."""
+    torch.manual_seed(5)
+    B, V, h, w = 4, 3, 128, 160
+    net_a = harness.DepthRefinement().to(DEV).train()
+    net_b = harness.DepthRefinement().to(DEV).train()
+    net_b.load_state_dict(net_a.state_dict())
+    images = torch.rand(B * V, 3, 4 * h, 4 * w, device=DEV)
+    d_min = torch.full((B, 1, 1, 1), 425.0, device=DEV)
+    span = torch.full((B, 1, 1, 1), 2.5 * 192 * 1.06, device=DEV)
+    base = d_min + span * torch.rand(B, 1, h, w, device=DEV)
+    gg = torch.randn(B, 1, h, w, device=DEV)
+    outs = []
+    for net, mode in ((net_a, "native"), (net_b, "torch")):
+        monkeypatch.setenv("MVSB200_REFINE", mode)
+        x = base.clone().requires_grad_(True)
+        y = harness.MVSNet.refine(_owner(net, "bf16"), x, images, V, d_min, span)
+        y.backward(gg)
+        outs.append((y.detach(), x.grad, [p.grad for p in net.parameters()]))
+    (ya, ga, pa), (yb, gb, pb) = outs
+    assert ((ya - yb) / span).abs().max().item() <= 2e-2
+    assert _rel_l2(ga, gb) <= 5e-2, _rel_l2(ga, gb)
+    for a, b_ in zip(pa, pb):
+        assert _rel_l2(a, b_) <= 5e-2, _rel_l2(a, b_)
+
+
+class _ReferenceLayout(torch.nn.Module):
+    """The module layout of model.py:129-152 written with stock torch.nn (Conv2d / BatchNorm2d / ReLU triples)."""
+
+    def __init__(self):
+        super().__init__()
+        nn = torch.nn
+        layers = []
+        for i, o in ((4, 32), (32, 32), (32, 32)):
+            layers += [nn.Conv2d(i, o, 3, padding=1, bias=False), nn.BatchNorm2d(o), nn.ReLU()]
+        self.model = nn.Sequential(*layers, nn.Conv2d(32, 1, 3, padding=1, bias=False))
+
+    def forward(self, x):
+        return self.model(x) + x[:, 0].unsqueeze(1)
+
+
+@pytest.mark.gpu
+def test_refine_depth_binds_to_a_module_of_the_reference_layout():
+    """mvs_b200.refine_depth on a host application's own DepthRefinement (plain Conv2d / BatchNorm2d / ReLU Sequential): the
+    native path takes its parameters and running statistics in place; eval-mode BatchNorm falls to the module's own layers."""
+    g = np.load(GOLD)
+    ours = _golden_net(g, DEV)
+    theirs = _ReferenceLayout().to(DEV).train()
+    theirs.load_state_dict(ours.state_dict())
+    images = torch.from_numpy(g["nn_input"]).to(DEV)
+    d_min, d_int = torch.from_numpy(g["d_min"]), torch.from_numpy(g["d_int"])          # host tensors, as the loaders hand them over
+    initial = torch.from_numpy(g["initial"]).to(DEV)
+    args = (images, int(g["n_views"]), d_min, d_int, int(g["d_num"]), float(g["d_scale"]))
+    n0 = mvs_b200.launch_count()
+    a = mvs_b200.refine_depth(theirs, initial, *args)
+    assert mvs_b200.launch_count() - n0 >= 10                     # glue, filter packing, convolutions, BatchNorm: the library ran
+    b = mvs_b200.refine_depth(ours, initial, *args)
+    assert torch.equal(a, b)
+    for (ka, va), (kb, vb) in zip(theirs.state_dict().items(), ours.state_dict().items()):
+        assert ka == kb and torch.equal(va, vb), ka
+    theirs.eval()
+    n0 = mvs_b200.launch_count()
+    c = mvs_b200.refine_depth(theirs, initial, *args)              # eval-mode BatchNorm: the module's own torch layers
+    assert mvs_b200.launch_count() == n0 and c.shape == a.shape and torch.isfinite(c).all()
