@@ -608,24 +608,28 @@ template <int CIN, int NCO>
 int launch_wgrad(const void* x, const void* gy, float* gw, int B, int Di, int Hi, int Wi, int Do, int Ho, int Wo, int cout, int co0,
                  int off_d, int off_h, int off_w, cudaStream_t st, int x_es = 1, int Dx = 0, int Hx = 0, int Wx = 0,
                  unsigned kd_mask = 7u, const int* tap_map = nullptr, int n_roles = 1, const int* role_co0 = nullptr,
-                 const int* role_kd = nullptr) {
+                 const int* role_kd = nullptr, int cin_real = CIN) {
+    // cin_real < CIN (stride-1 form only): voxel rows of x hold cin_real channels, the TMA box is CIN wide and the channels beyond
+    // the tensor's extent arrive as zeros -- rows cin_real.. of every gw tap come out zero
     if (x_es == 1) { Dx = Di; Hx = Hi; Wx = Wi; }
-    constexpr int ROWX = CIN * 2, ROWG = NCO * 2;
+    constexpr int ROWG = NCO * 2;
+    constexpr int ROWX_BOX = CIN * 2;
+    const int ROWX = cin_real * 2;
     EncodeTiledFn enc = encode_fn();
     MVS_REQUIRE(enc != nullptr, "conv3d_s1_wgrad: cuTensorMapEncodeTiled is not available from the driver");
     const size_t smem_budget = 227 * 1024 - 1024;
-    const WgPlan tp = plan_tiles_wgrad(Ho, Wo, ROWX, ROWG, smem_budget);
+    const WgPlan tp = plan_tiles_wgrad(Ho, Wo, ROWX_BOX, ROWG, smem_budget);
     MVS_REQUIRE(tp.score > 0, "conv3d_s1_wgrad: no slab geometry fits shared memory (Cin=%d, N=%d)", CIN, NCO);
 
     CUtensorMap tm_x, tm_g;
     {
-        const cuuint64_t dims[5] = {(cuuint64_t)CIN, (cuuint64_t)Wi, (cuuint64_t)Hi, (cuuint64_t)Di, (cuuint64_t)B};
+        const cuuint64_t dims[5] = {(cuuint64_t)cin_real, (cuuint64_t)Wi, (cuuint64_t)Hi, (cuuint64_t)Di, (cuuint64_t)B};
         const cuuint64_t strides[4] = {(cuuint64_t)x_es * ROWX, (cuuint64_t)x_es * ROWX * Wx, (cuuint64_t)x_es * ROWX * Wx * Hx,
                                        (cuuint64_t)ROWX * Wx * Hx * Dx};
         const cuuint32_t box[5] = {(cuuint32_t)CIN, (cuuint32_t)tp.BW, (cuuint32_t)(tp.L + 2), 1, 1};
         const cuuint32_t es[5] = {1, 1, 1, 1, 1};
         CUresult r = enc(&tm_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), dims, strides, box, es,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(ROWX), CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(ROWX_BOX), CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         MVS_REQUIRE(r == CUDA_SUCCESS, "conv3d_s1_wgrad: cuTensorMapEncodeTiled(x) failed (%d)", (int)r);
     }
     {
@@ -1743,9 +1747,23 @@ extern "C" int mvsb200_conv3d_s1_fwd_ex(const void* x, const void* w_packed, voi
                               (cudaStream_t)stream, "conv3d_s1_fwd_ex");
 }
 
+extern "C" int mvsb200_conv3d_s1_wgrad_ex(const void* x, const void* gy, float* gw, int B, int Di, int Hi, int Wi, int Cin, int Do,
+                                          int Ho, int Wo, int cout, int off_d, int off_h, int off_w, unsigned kd_mask, void* stream);
+
 extern "C" int mvsb200_conv3d_s1_wgrad(const void* x, const void* gy, float* gw, int B, int Di, int Hi, int Wi, int Cin, int Do,
                                        int Ho, int Wo, int cout, int off_d, int off_h, int off_w, void* stream) {
+    return mvsb200_conv3d_s1_wgrad_ex(x, gy, gw, B, Di, Hi, Wi, Cin, Do, Ho, Wo, cout, off_d, off_h, off_w, 7u, stream);
+}
+
+/* kd_mask: bit kd set = the depth taps whose gradients are computed (the others stay zero) -- 2 for maps stacked as the planes
+ * of one volume (2D convolutions: only the middle depth slice exists).  Cin = 8: 8-channel rows of x on the K = 16 kernel (TMA
+ * zero fill), gw is then [27][16][cout] with rows 8..15 zero. */
+extern "C" int mvsb200_conv3d_s1_wgrad_ex(const void* x, const void* gy, float* gw, int B, int Di, int Hi, int Wi, int Cin, int Do,
+                                          int Ho, int Wo, int cout, int off_d, int off_h, int off_w, unsigned kd_mask, void* stream) {
     MVS_REQUIRE(x && gy && gw, "conv3d_s1_wgrad: null pointer");
+    MVS_REQUIRE(kd_mask >= 1u && kd_mask <= 7u, "conv3d_s1_wgrad: depth-tap mask %u", kd_mask);
+    const int cin_real = Cin;
+    if (Cin == 8) Cin = 16;
     MVS_REQUIRE(aligned16(x) && aligned16(gy) && aligned16(gw), "conv3d_s1_wgrad: pointers must be 16-byte aligned");
     MVS_REQUIRE(B >= 1 && Di >= 1 && Hi >= 1 && Wi >= 1 && Do >= 1 && Ho >= 1 && Wo >= 1, "conv3d_s1_wgrad: bad shape");
     MVS_REQUIRE(cout == 8 || cout == 16 || cout == 32 || cout == 64, "conv3d_s1_wgrad: cout must be 8, 16, 32 or 64 (got %d)", cout);
@@ -1761,6 +1779,11 @@ extern "C" int mvsb200_conv3d_s1_wgrad(const void* x, const void* gy, float* gw,
         int role_co0[8], role_kd[8], n_roles = 0;
         for (int co0 = 0; co0 < cout; co0 += 32)
             for (int kd = 0; kd < 3; ++kd) { role_co0[n_roles] = co0; role_kd[n_roles] = 1 << kd; ++n_roles; }
+        for (int r = 0; r < n_roles;) {                                     // roles of depth taps that are masked out do nothing: drop them
+            if (role_kd[r] & (int)kd_mask) { ++r; continue; }
+            for (int q = r; q + 1 < n_roles; ++q) { role_co0[q] = role_co0[q + 1]; role_kd[q] = role_kd[q + 1]; }
+            --n_roles;
+        }
         return launch_wgrad<64, 32>(x, gy, gw, B, Di, Hi, Wi, Do, Ho, Wo, cout, 0, off_d, off_h, off_w, st, 1, 0, 0, 0, 1u, nullptr, n_roles,
                                     role_co0, role_kd);
     }
@@ -1768,7 +1791,8 @@ extern "C" int mvsb200_conv3d_s1_wgrad(const void* x, const void* gy, float* gw,
     const int nco = cout < nco_max ? cout : nco_max;
     for (int co0 = 0; co0 < cout; co0 += nco) {
         int rc = MVSB200_E_UNSUPPORTED;
-#define MVS_WG(CI, NC) rc = launch_wgrad<CI, NC>(x, gy, gw, B, Di, Hi, Wi, Do, Ho, Wo, cout, co0, off_d, off_h, off_w, st)
+#define MVS_WG(CI, NC) rc = launch_wgrad<CI, NC>(x, gy, gw, B, Di, Hi, Wi, Do, Ho, Wo, cout, co0, off_d, off_h, off_w, st, 1, 0, 0, 0, kd_mask, \
+                                                 nullptr, 1, nullptr, nullptr, cin_real)
         if (Cin == 16 && nco == 8) MVS_WG(16, 8);
         else if (Cin == 16 && nco == 16) MVS_WG(16, 16);
         else if (Cin == 16 && nco == 32) MVS_WG(16, 32);

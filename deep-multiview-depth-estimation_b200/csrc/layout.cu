@@ -55,6 +55,62 @@ extern "C" int mvsb200_widen_rows_8to16_bf16(const void* src, void* dst, int64_t
     return MVSB200_OK;
 }
 
+// ---- 2D feature encoder: maps as channel-last bf16 rows ---------------------------------------------
+// images fp32 [N, 3, H, W] (any element strides) -> bf16 rows [N, H, W, 8]: channels 0..2 the colours, 3..7 zero -- what the
+// K = 16 tensor-core convolution reads through an 8-channel TMA map (scripts/model.py:27, the encoder's first layer).
+__global__ void __launch_bounds__(256) image_to_rows8_kernel(const float* __restrict__ img, long long s_n, long long s_c, long long s_h,
+                                                             long long s_w, int N, int H, int W, uint4* __restrict__ rows) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)N * H * W) return;
+    const int x = (int)(i % W), y = (int)((i / W) % H), n = (int)(i / ((long long)W * H));
+    const float* p = img + n * s_n + y * s_h + x * s_w;
+    const __nv_bfloat162 a = __floats2bfloat162_rn(p[0], p[s_c]);
+    const __nv_bfloat162 b = __floats2bfloat162_rn(p[2 * s_c], 0.f);
+    uint4 v;
+    v.x = *reinterpret_cast<const unsigned*>(&a);
+    v.y = *reinterpret_cast<const unsigned*>(&b);
+    v.z = 0u; v.w = 0u;
+    rows[i] = v;
+}
+
+extern "C" int mvsb200_image_to_rows8(const float* images, const int64_t* strides4_host, int N, int H, int W, void* rows, void* stream) {
+    MVS_REQUIRE(images && strides4_host && rows && aligned16(rows), "image_to_rows8: null or misaligned pointer");
+    MVS_REQUIRE(N >= 1 && H >= 1 && W >= 1, "image_to_rows8: bad shape");
+    const long long tot = (long long)N * H * W;
+    image_to_rows8_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        images, strides4_host[0], strides4_host[1], strides4_host[2], strides4_host[3], N, H, W, reinterpret_cast<uint4*>(rows));
+    MVS_CHECK_LAUNCH("image_to_rows8");
+    return MVSB200_OK;
+}
+
+// Space-to-depth of channel-last rows and its inverse: [N, 2h, 2w, C] <-> [N, h, w, 4C], channel (py*2 + px)*C + c of pixel (j, i) =
+// channel c of pixel (2j + py, 2i + px).  A 5x5 stride-2 convolution (scripts/model.py:31,39) of the left form is a 3x3 stride-1
+// convolution of the right one (tap k = 2t + p of an axis reads parity class p at j - 1 + t), i.e. the tensor-core kernel the
+// regulariser already has.  One thread per 16-byte chunk, coalesced on the deep side.
+__global__ void __launch_bounds__(256) s2d_rows_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int N, int h, int w,
+                                                       int q, int inverse) {
+    // q = 16-byte chunks per shallow pixel (C / 8); deep pixel = 4q chunks
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long tot = (long long)N * h * w * 4 * q;
+    if (i >= tot) return;
+    const int k = (int)(i % q), cls = (int)((i / q) % 4), x = (int)((i / (4 * q)) % w), y = (int)((i / ((long long)4 * q * w)) % h);
+    const long long n = i / ((long long)4 * q * w * h);
+    const long long shallow = ((n * (2 * h) + 2 * y + (cls >> 1)) * (2 * w) + 2 * x + (cls & 1)) * q + k;
+    if (inverse) dst[shallow] = __ldg(src + i);
+    else dst[i] = __ldg(src + shallow);
+}
+
+extern "C" int mvsb200_s2d_rows_bf16(const void* src, void* dst, int N, int h, int w, int C, int inverse, void* stream) {
+    MVS_REQUIRE(src && dst && aligned16(src) && aligned16(dst), "s2d_rows: null or misaligned pointer");
+    MVS_REQUIRE(N >= 1 && h >= 1 && w >= 1 && C >= 8 && C % 8 == 0, "s2d_rows: bad shape (C must be a multiple of 8)");
+    const long long tot = (long long)N * h * w * 4 * (C / 8);
+    MVS_REQUIRE(tot < ((long long)1 << 40), "s2d_rows: too large");
+    s2d_rows_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const uint4*>(src), reinterpret_cast<uint4*>(dst), N, h, w, C / 8, inverse);
+    MVS_CHECK_LAUNCH("s2d_rows");
+    return MVSB200_OK;
+}
+
 // ---- filter packing ---------------------------------------------------------------------------------------------------
 // The tensor-core kernels want their 3x3x3 filters as bf16 [slot][row][col] matrices (K-major B operands): tap-major, rows =
 // output channels padded to a multiple of 16, columns = contraction channels, in the tap order of the kernel (natural, depth

@@ -11,7 +11,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import api, refine
+from . import api, nets2d, refine
 from .regulariser import CostVolumeReg
 
 
@@ -76,9 +76,7 @@ class MVSNet(nn.Module):
     def forward(self, nn_input, K_batch, R_batch, T_batch, d_min, d_int, batch_size, n_views, sweep=None):
         """sweep: an ops.PlaneSweep already holding this batch's geometry on the device (PlaneSweep.update); the cameras are
         then not touched here and d_min / d_int should be device tensors -- the form a captured CUDA graph replays."""
-        amp = self.precision == "bf16" and nn_input.is_cuda
-        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):        # out-of-scope 2D net: stock torch AMP
-            feats = self.feature_encoder(nn_input.contiguous(memory_format=torch.channels_last))
+        feats = self.encode(nn_input)
         feats = feats.float()
         ev = getattr(self, "after_encoder_event", None)          # GraphedInference: where the next batch's H2D copy may start
         if ev is not None and torch.cuda.is_current_stream_capturing():
@@ -91,6 +89,16 @@ class MVSNet(nn.Module):
         initial = api.extract_depth_map(prob, d_batch, self.n_depth_est)
         return initial, refine.refine_depth(self.depthmap_refine, initial, nn_input, n_views, d_min, d_int, self.d_num, self.d_scale,
                                             bf16=self.precision == "bf16")
+
+    def encode(self, nn_input):
+        """model.py:20-65 -> feature maps [N, 32, H/4, W/4] (bf16 on the bf16 path).  SURVEY row f1: bf16 with train-mode BatchNorm
+        (what train.py and test.py:61 run) takes the tensor-core kernels of mvs_b200/nets2d.py; MVSB200_ENCODER=torch, fp32 and
+        eval-mode BatchNorm evaluate the module's stock torch layers (cuDNN)."""
+        amp = self.precision == "bf16" and nn_input.is_cuda
+        if amp and os.environ.get("MVSB200_ENCODER", "native") == "native" and nets2d.encoder_ok(self.feature_encoder, nn_input):
+            return nets2d.encode_native(self.feature_encoder, nn_input)
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
+            return self.feature_encoder(nn_input.contiguous(memory_format=torch.channels_last))
 
     def refine(self, initial, nn_input, n_views, d_trans, d_span):
         """model.py:190-205 on depth offsets / spans already on the device (mvs_b200/refine.py): native on the
@@ -319,8 +327,7 @@ class DepthSlabMVSNet:
         if by_view is None:
             by_view = not m.feature_encoder.training
         if not by_view or R == 1:
-            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
-                return m.feature_encoder(nn_input.contiguous(memory_format=torch.channels_last)).float()
+            return m.encode(nn_input).float()
         nhwc = torch.empty((N, H // 4, W // 4, 32), dtype=torch.float32, device=nn_input.device)
         mine = [v for v in range(N) if v % R == r]
         if mine:

@@ -7,12 +7,11 @@ to the feature resolution, concatenate, refine, de-normalise).
   refine_input / refine_output   the glue as ONE launch each way (csrc/refine.cu) instead of ~10 elementwise / resize / concat
                                  launches forward and as many backward; the network's input leaves as bf16 channel-last rows of
                                  16 channels (4 carry data), the layout the K = 16 tensor-core convolution reads.
-  refine_native                  the four 3x3 convolutions on the tcgen05 stride-1 kernels of the regulariser: a [B, C, h, w] map
-                                 IS a [B, C, 1, h, w] volume (the planes above and below arrive as TMA zero fill) and a 3x3 filter
-                                 is the middle depth slice of a 3x3x3 one (packed straight from the Conv2d parameter); forward,
-                                 data gradient and weight gradient are the kernels the regulariser's stride-1 layers run on,
-                                 BatchNorm + ReLU the fused K3b kernels with the module's running statistics.  No library
-                                 convolution is left in the refinement network.
+  refine_native                  the four 3x3 convolutions -- forward, data gradient, weight gradient -- on the tcgen05 stride-1
+                                 kernels of the regulariser (nets2d.py: the maps are the planes of one volume, a 3x3 filter is
+                                 the middle depth slice of a 3x3x3 one, packed straight from the Conv2d parameter), BatchNorm +
+                                 ReLU the fused K3b kernels with the module's running statistics.  No library convolution is
+                                 left in the refinement network.
 
 Train mode, bf16 only (what the train step and the bf16 inference path run); DepthRefinement.forward keeps the stock torch layers for
 eval-mode BatchNorm and fp32."""
@@ -47,7 +46,7 @@ class _RefineInput(torch.autograd.Function):
         if images.shape[0] < (B - 1) * n_views + 1:
             raise _lib.MvsB200Error(f"refine_input: {images.shape[0]} images for {B} samples of {n_views} views")
         x = initial.detach().float().contiguous()
-        rows = torch.empty((B, _CP, 1, h, w), dtype=torch.bfloat16, device=x.device, memory_format=torch.channels_last_3d)
+        rows = torch.empty((1, _CP, B, h, w), dtype=torch.bfloat16, device=x.device, memory_format=torch.channels_last_3d)
         norm = torch.empty_like(x)
         with _timed("refine_glue"):
             _lib.call("mvsb200_refine_input_fwd", x.data_ptr(), images.data_ptr(), (ctypes.c_int64 * 4)(*images.stride()), int(n_views),
@@ -75,7 +74,7 @@ class _RefineInput(torch.autograd.Function):
 class _RefineOutput(torch.autograd.Function):
     @staticmethod
     def forward(ctx, res_rows, norm, d_min, span):
-        B, cr, _, h, w = res_rows.shape
+        _, cr, B, h, w = res_rows.shape
         r = res_rows.detach().contiguous(memory_format=torch.channels_last_3d)
         if r.dtype != torch.bfloat16:
             raise _lib.MvsB200Error(f"refine_output: bf16 rows expected, got {r.dtype}")
@@ -92,7 +91,7 @@ class _RefineOutput(torch.autograd.Function):
     def backward(ctx, g):
         (span,) = ctx.saved_tensors
         rs, ns = ctx.meta
-        B, cr, _, h, w = rs
+        _, cr, B, h, w = rs
         g = g.float().contiguous()
         g_rows = torch.empty(rs, dtype=torch.bfloat16, device=g.device, memory_format=torch.channels_last_3d)
         g_norm = torch.empty(ns, dtype=torch.float32, device=g.device)
@@ -103,79 +102,18 @@ class _RefineOutput(torch.autograd.Function):
 
 
 def refine_input(initial, images, n_views, d_min, span):
-    """(rows, norm): rows = bf16 [B, 16, 1, h, w] channel-last, channel 0 the normalised depth (initial - d_min) / span, 1..3 the
-    reference image of every sample (images[b * n_views], fp32 [N, 3, H, W], any strides) resized bilinearly to h x w, the rest
-    zeros; norm = the normalised depth in fp32 [B, 1, h, w] (model.py:190-200).  d_min / span: one value per sample."""
+    """(rows, norm): rows = bf16 [1, 16, B, h, w] channel-last (the maps stacked as planes, nets2d.py): channel 0 the normalised
+    depth (initial - d_min) / span, 1..3 the reference image of every sample (images[b * n_views], fp32 [N, 3, H, W], any
+    strides) resized bilinearly to h x w, the rest zeros; norm = the normalised depth in fp32 [B, 1, h, w] (model.py:190-200).
+    d_min / span: one value per sample."""
     B = initial.shape[0]
     return _RefineInput.apply(initial, images, int(n_views), _per_sample(d_min, B, "d_min"), _per_sample(span, B, "depth span"))
 
 
 def refine_output(res_rows, norm, d_min, span):
-    """(res_rows[:, 0] + norm) * span + d_min -> fp32 [B, 1, h, w] (model.py:150-151, :203)."""
-    B = res_rows.shape[0]
+    """(res_rows[0, 0] + norm) * span + d_min -> fp32 [B, 1, h, w] (model.py:150-151, :203); res_rows [1, c, B, h, w]."""
+    B = res_rows.shape[2]
     return _RefineOutput.apply(res_rows, norm, _per_sample(d_min, B, "d_min"), _per_sample(span, B, "depth span"))
-
-
-def _pack2d(w, role, n_rows, n_cols):
-    """Conv2d weight [co, ci, 3, 3] (fp32) -> the bf16 [(kh, kw)][kd][row][col] filter operand of the kdn kernels, in one launch:
-    the 3x3 filter is the middle depth slice of a 3x3x3 one, the kd = 0 / 2 slots (they would meet the zero planes above and
-    below the map) and the padded rows / columns are zeros.  role "fwd": rows = co; "dgrad": taps flipped, rows = ci."""
-    from .conv3d_sm100 import _FLIP, _NAT, _kdn_order
-    co, ci = w.shape[:2]
-    taps = [t - 9 if 9 <= t < 18 else -1 for t in _kdn_order(_NAT if role == "fwd" else _FLIP)]
-    rows_real, cols_real, sr, sc = (co, ci, 9 * ci, 9) if role == "fwd" else (ci, co, 9, 9 * ci)
-    out = torch.empty((27, n_rows, n_cols), dtype=torch.bfloat16, device=w.device)
-    _lib.call("mvsb200_pack_filter", w.data_ptr(), out.data_ptr(), 27, n_rows, n_cols, rows_real, cols_real, 0, sr, sc,
-              (ctypes.c_int * 27)(*taps), _stream())
-    return out
-
-
-def _conv_rows(x, wk, c_out, n_rows, work):
-    """3x3 convolution (padding 1) of bf16 channel-last rows x [B, c, 1, h, w] with a packed filter -> [B, c_out, 1, h, w]."""
-    B, c, _, h, w = x.shape
-    y = torch.empty((B, c_out, 1, h, w), dtype=torch.bfloat16, device=x.device, memory_format=torch.channels_last_3d)
-    with _timed("conv3d_s1_tc", work):
-        _lib.call("mvsb200_conv3d_s1_fwd_kdn", x.data_ptr(), wk.data_ptr(), y.data_ptr(), B, 1, h, w, c, 1, h, w, c_out, c_out, n_rows,
-                  -1, -1, -1, _stream())
-    return y
-
-
-class _Conv2dRows(torch.autograd.Function):
-    """Conv2d(ci, co, 3, padding=1, bias=False) on the tcgen05 stride-1 kernels of the regulariser: a [B, C, h, w] map is the
-    [B, C, 1, h, w] volume (channel-last rows of cx >= ci channels in, cy >= co out; the surplus channels are zeros).  Forward and
-    data gradient: conv3d_s1_kdn_kernel; weight gradient: conv3d_s1_wgrad_tc_kernel, of whose 27 taps the middle depth slice is
-    the layer's."""
-
-    @staticmethod
-    def forward(ctx, x, w, cy):
-        if x.dtype != torch.bfloat16 or w.dtype != torch.float32 or not w.is_contiguous():
-            raise _lib.MvsB200Error(f"refinement convolution: bf16 rows and a dense fp32 weight expected, got {x.dtype}, {w.dtype}")
-        x = x.detach().contiguous(memory_format=torch.channels_last_3d)
-        co, ci = w.shape[:2]
-        B, cx, _, h, wd = x.shape
-        wf = w.detach()
-        y = _conv_rows(x, _pack2d(wf, "fwd", 16 if cy <= 16 else 32, max(cx, 16)), cy, 16 if cy <= 16 else 32, 2.0 * 9 * ci * co * B * h * wd)
-        ctx.save_for_backward(x, wf)
-        return y
-
-    @staticmethod
-    def backward(ctx, gy):
-        x, w = ctx.saved_tensors
-        co, ci = w.shape[:2]
-        B, cx, _, h, wd = x.shape
-        cy = gy.shape[1]
-        gy = gy.to(torch.bfloat16).contiguous(memory_format=torch.channels_last_3d)
-        gx = gw = None
-        if ctx.needs_input_grad[0]:
-            gx = _conv_rows(gy, _pack2d(w, "dgrad", 16 if cx <= 16 else 32, max(cy, 16)), cx, 16 if cx <= 16 else 32,
-                            2.0 * 9 * ci * co * B * h * wd)
-        if ctx.needs_input_grad[1]:
-            gw27 = torch.empty((27, cx, cy), dtype=torch.float32, device=gy.device)
-            with _timed("conv3d_s1_wgrad_tc", 2.0 * 9 * ci * co * B * h * wd):
-                _lib.call("mvsb200_conv3d_s1_wgrad", x.data_ptr(), gy.data_ptr(), gw27.data_ptr(), B, 1, h, wd, cx, 1, h, wd, cy,
-                          -1, -1, -1, _stream())
-            gw = gw27[9:18, :ci, :co].reshape(3, 3, ci, co).permute(3, 2, 0, 1).contiguous()
-        return gx, gw, None
 
 
 def native_ok(module, x_like) -> bool:
@@ -191,16 +129,13 @@ def refine_native(module, initial, images, n_views, d_min, span):
     """model.py:190-205 on `module` (a DepthRefinement: Sequential of Conv2d / BatchNorm2d(+ReLU) triples): normalise, build the
     network's input, four convolutions with BatchNorm + ReLU between them, residual, de-normalise -> refined depth fp32
     [B, 1, h, w].  Parameters, running statistics and their state_dict keys are the module's own."""
+    from .nets2d import _bn_relu, conv3x3
     convs = [m for m in module.model if isinstance(m, torch.nn.Conv2d)]
     bns = [m for m in module.model if isinstance(m, torch.nn.BatchNorm2d)]
     x, norm = refine_input(initial, images, n_views, d_min, span)
     for k in range(3):
-        y = _Conv2dRows.apply(x, convs[k].weight, 32)
-        bn = bns[k]
-        x, _, _ = ops.batchnorm_relu_train(y, bn.weight, bn.bias, bn.eps, relu=True,
-                                           running=(bn.running_mean, bn.running_var, bn.num_batches_tracked), momentum=bn.momentum)
-    res = _Conv2dRows.apply(x, convs[3].weight, _CR)
-    return refine_output(res, norm, d_min, span)
+        x = _bn_relu(conv3x3(x, convs[k].weight), bns[k])
+    return refine_output(conv3x3(x, convs[3].weight, _CR), norm, d_min, span)
 
 
 def refine_depth(module, initial, nn_input, n_views, d_min, d_int, d_num, d_scale, bf16=True):

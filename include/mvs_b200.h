@@ -360,6 +360,19 @@ int mvsb200_refine_output_fwd(const void* res_rows, int cr, const float* norm, c
 int mvsb200_refine_output_bwd(const float* g_refined, const float* span, int B, int n, int cr, void* g_rows, float* g_norm,
                               void* stream);
 
+/* ---- f1: the 2D feature encoder on the path's kernels (scripts/model.py:22-65) ------------------------
+ * Maps travel as channel-last bf16 rows, stacked as the planes of ONE volume [1, C, N, H, W]: a 3x3 convolution is the middle
+ * depth slice of a 3x3x3 one (mvsb200_pack_filter with the kd = 0 / 2 slots empty, mvsb200_conv3d_s1_fwd_kdn), its weight gradient
+ * mvsb200_conv3d_s1_wgrad_ex with kd_mask = 2; a 5x5 stride-2 convolution is a 3x3 one on the space-to-depth form of its input.
+ * image_to_rows8:  fp32 [N, 3, H, W] (element strides given) -> bf16 rows [N, H, W, 8], channels 3..7 zero.
+ * s2d_rows_bf16:   [N, 2h, 2w, C] -> [N, h, w, 4C] (channel (py*2 + px)*C + c), inverse != 0: the other way.  C % 8 == 0.
+ * conv3d_s1_wgrad_ex: mvsb200_conv3d_s1_wgrad with a depth-tap mask (bit kd: compute that tap's gradient, the others stay zero)
+ *                  and Cin = 8 (8-channel rows on the K = 16 kernel; gw is then [27][16][cout], rows 8..15 zero). */
+int mvsb200_image_to_rows8(const float* images, const int64_t* strides4_host, int N, int H, int W, void* rows, void* stream);
+int mvsb200_s2d_rows_bf16(const void* src, void* dst, int N, int h, int w, int C, int inverse, void* stream);
+int mvsb200_conv3d_s1_wgrad_ex(const void* x, const void* gy, float* gw, int B, int Di, int Hi, int Wi, int Cin, int Do, int Ho,
+                               int Wo, int cout, int off_d, int off_h, int off_w, unsigned kd_mask, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

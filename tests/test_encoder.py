@@ -1,0 +1,177 @@
+"""SURVEY §8 row f1 -- the 2D feature encoder (model.py:20-65) on the path's tensor-core kernels (mvs_b200/nets2d.py).
+
+Golden: tests/golden/encoder.npz, produced by the UNMODIFIED reference on the CPU in fp32 (oracle/make_golden_encoder.py).
+
+CPU: the harness's stock-torch encoder reproduces the golden; the host-side re-indexing that turns a 5x5 stride-2 convolution
+into a 3x3 one on the space-to-depth form is exact.  GPU: layout kernels bit-exact against torch; single layers against torch's
+convolution on bf16-rounded operands (forward, data gradient, weight gradient); the whole native encoder against the golden
+within the bf16 convolution tolerance (1e-2 of the largest feature), gradients as close to the fp32 golden as the stock bf16
+layers are."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import mvs_b200
+from mvs_b200 import harness, nets2d
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "encoder.npz")
+DEV = "cuda:0"
+
+
+def _golden_net(g, device):
+    net = harness.FeatureEncoder().to(device).train()
+    net.load_state_dict({k[3:]: torch.from_numpy(np.asarray(g[k])) for k in g.files if k.startswith("w0.")})
+    return net
+
+
+def _s2d_torch(x):
+    """[N, C, 2h, 2w] -> [N, 4C, h, w] with channel (py*2 + px)*C + c."""
+    N, C, H, W = x.shape
+    return x.view(N, C, H // 2, 2, W // 2, 2).permute(0, 3, 5, 1, 2, 4).reshape(N, 4 * C, H // 2, W // 2)
+
+
+def _rel_l2(a, b):
+    return float((a.float() - b.float()).norm() / b.float().norm().clamp_min(1e-12))
+
+
+def test_stock_encoder_reproduces_the_reference():
+    g = np.load(GOLD)
+    net = _golden_net(g, "cpu")
+    feats = net(torch.from_numpy(g["images"]))
+    assert torch.allclose(feats, torch.from_numpy(g["features"]), rtol=1e-4, atol=1e-5)
+    feats.backward(torch.from_numpy(g["g_features"]))
+    for n, p in net.named_parameters():
+        ref = torch.from_numpy(g["g." + n])
+        assert (p.grad - ref).abs().max() <= 1e-3 * max(float(ref.abs().max()), 1e-3), n
+
+
+@pytest.mark.parametrize("shape", [(2, 8, 16, 12, 20), (1, 16, 32, 8, 8)])
+def test_k5s2_is_a_3x3_convolution_on_the_space_to_depth_form(shape):
+    N, ci, co, H, W = shape
+    gen = torch.Generator().manual_seed(ci)
+    x = torch.randn(N, ci, H, W, generator=gen, dtype=torch.float64)
+    w5 = torch.randn(co, ci, 5, 5, generator=gen, dtype=torch.float64, requires_grad=True)
+    want = F.conv2d(x, w5, stride=2, padding=2)
+    w3 = nets2d.k5s2_as_3x3(w5.float()).double()
+    assert w3.shape == (co, 4 * ci, 3, 3)
+    got = F.conv2d(_s2d_torch(x), w3, padding=1)
+    assert torch.allclose(got, want.detach(), rtol=1e-5, atol=1e-5)                 # fp32 re-indexing of an fp64 filter
+    assert int((w3 != 0).sum()) == co * ci * 25                                    # 25 of the 36 taps are the filter's
+
+
+def test_c_abi_exports_the_encoder_kernels():
+    from mvs_b200 import _lib
+    lib = _lib.load()
+    for name in ("mvsb200_image_to_rows8", "mvsb200_s2d_rows_bf16", "mvsb200_conv3d_s1_wgrad_ex"):
+        assert hasattr(lib, name), name
+
+
+@pytest.mark.gpu
+def test_layout_kernels_bit_exact():
+    gen = torch.Generator().manual_seed(3)
+    img = torch.rand(3, 3, 12, 20, generator=gen).to(DEV)
+    for images in (img, img.contiguous(memory_format=torch.channels_last), img[:, :, ::1, :]):
+        rows = nets2d.image_rows(images)
+        assert rows.shape == (1, 8, 3, 12, 20) and rows.is_contiguous(memory_format=torch.channels_last_3d)
+        assert torch.equal(rows[0, :3].permute(1, 0, 2, 3), images.to(torch.bfloat16))
+        assert torch.count_nonzero(rows[0, 3:]).item() == 0
+    for C in (8, 16):
+        x = torch.randn(1, C, 3, 12, 20, generator=gen).to(DEV).to(torch.bfloat16).contiguous(memory_format=torch.channels_last_3d)
+        x.requires_grad_(True)
+        y = nets2d.space_to_depth(x)
+        want = _s2d_torch(x.detach()[0].permute(1, 0, 2, 3))                      # [N, 4C, h, w]
+        assert y.shape == (1, 4 * C, 3, 6, 10) and torch.equal(y[0].permute(1, 0, 2, 3), want)
+        gy = torch.randn(y.shape, generator=gen).to(DEV).to(torch.bfloat16)
+        y.backward(gy)
+        back = torch.zeros_like(x.detach().float())                               # adjoint of a permutation = its inverse
+        back[0] = _s2d_inverse_torch(gy[0].permute(1, 0, 2, 3).float(), C).permute(1, 0, 2, 3)
+        assert torch.equal(x.grad.float(), back)
+
+
+def _s2d_inverse_torch(y, C):
+    N, C4, h, w = y.shape
+    return y.view(N, 2, 2, C, h, w).permute(0, 3, 4, 1, 5, 2).reshape(N, C, 2 * h, 2 * w)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", [(3, 8, 8, 8), (8, 8, 8, 8), (16, 16, 16, 16), (32, 32, 32, 32), (4, 32, 16, 32), (32, 1, 32, 8),
+                                  (32, 16, 32, 16), (64, 32, 64, 32)])
+@pytest.mark.parametrize("dims", [(3, 12, 20), (2, 33, 47)])
+def test_conv3x3_rows_against_torch(case, dims):
+    """One layer: forward, data gradient, weight gradient against torch.conv2d in fp32 on the bf16-rounded operands."""
+    ci, co, cx, cy = case
+    N, H, W = dims
+    gen = torch.Generator().manual_seed(ci * 64 + co + H)
+    x = torch.zeros(N, cx, H, W)
+    x[:, :ci] = torch.randn(N, ci, H, W, generator=gen)
+    x = x.to(torch.bfloat16)
+    w = (torch.randn(co, ci, 3, 3, generator=gen) / (3.0 * ci ** 0.5)).to(DEV).requires_grad_(True)
+    rows = x.to(DEV).permute(1, 0, 2, 3).unsqueeze(0).contiguous(memory_format=torch.channels_last_3d).requires_grad_(True)
+    y = nets2d.conv3x3(rows, w, cy)
+    assert y.shape == (1, cy, N, H, W) and y.dtype == torch.bfloat16
+    gy = torch.zeros(N, cy, H, W)
+    gy[:, :co] = torch.randn(N, co, H, W, generator=gen)
+    gy = gy.to(torch.bfloat16)
+    y.backward(gy.to(DEV).permute(1, 0, 2, 3).unsqueeze(0))
+    xr = x.float().to(DEV)[:, :ci].requires_grad_(True)
+    wr = w.detach().to(torch.bfloat16).float().requires_grad_(True)
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        yr = F.conv2d(xr, wr, padding=1)
+        yr.backward(gy.float().to(DEV)[:, :co])
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
+    got = y[0].permute(1, 0, 2, 3).float()
+    assert (got[:, :co] - yr).abs().max().item() <= 1e-2 * max(1.0, float(yr.detach().abs().max()))       # bf16 rounding of the output
+    assert torch.count_nonzero(got[:, co:]).item() == 0
+    gx = rows.grad[0].permute(1, 0, 2, 3).float()
+    assert (gx[:, :ci] - xr.grad).abs().max().item() <= 1e-2 * max(1.0, float(xr.grad.abs().max()))
+    assert torch.count_nonzero(gx[:, ci:]).item() == 0
+    assert w.grad.shape == w.shape
+    assert (w.grad - wr.grad).abs().max().item() <= 2e-3 * max(1.0, float(wr.grad.abs().max()))  # fp32 accumulation, other order
+
+
+@pytest.mark.gpu
+def test_native_encoder_against_the_golden(monkeypatch):
+    from mvs_b200 import ops
+    g = np.load(GOLD)
+    images = torch.from_numpy(g["images"]).to(DEV)
+    want = torch.from_numpy(g["features"]).to(DEV)
+    gf = torch.from_numpy(g["g_features"]).to(DEV)
+    runs = {}
+    for mode in ("native", "torch"):
+        net = _golden_net(g, DEV)
+        ops.EVENTS = {}
+        try:
+            if mode == "native":
+                assert nets2d.encoder_ok(net, images)
+                feats = nets2d.encode_native(net, images).float()
+            else:
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    feats = net(images.contiguous(memory_format=torch.channels_last)).float()
+            feats.backward(gf)
+            torch.cuda.synchronize()
+            launched = {k: len(v) for k, v in ops.EVENTS.items()}
+        finally:
+            ops.EVENTS = None
+        runs[mode] = (feats.detach(), dict(net.named_parameters()), net.state_dict(), launched)
+    feats, params, state, launched = runs["native"]
+    # 8 convolutions forward, 7 data gradients (the images need none), 8 weight gradients, 2 + 2 space-to-depth passes
+    assert launched.get("conv2d_tc") == 15 and launched.get("conv2d_wgrad_tc") == 8 and launched.get("s2d_rows") == 4, launched
+    assert feats.shape == want.shape and feats.is_contiguous(memory_format=torch.channels_last)
+    err, err_stock = (feats - want).abs().max().item(), (runs["torch"][0] - want).abs().max().item()
+    scale = max(1.0, float(want.abs().max()))
+    assert err <= max(1e-2 * scale, 1.5 * err_stock), (err, err_stock, scale)
+    for n, p in params.items():
+        ref = torch.from_numpy(g["g." + n]).to(DEV)
+        assert p.grad is not None and p.grad.shape == ref.shape, n
+        e_nat, e_stock = _rel_l2(p.grad, ref), _rel_l2(runs["torch"][1][n].grad, ref)
+        assert e_nat <= max(1.5 * e_stock, 2e-2), (n, e_nat, e_stock)
+    for k in g.files:
+        if k.startswith("w1."):
+            got, exp = state[k[3:]].float().cpu(), torch.from_numpy(np.asarray(g[k])).float()
+            assert torch.allclose(got, exp, rtol=2e-2, atol=2e-3), k

@@ -69,24 +69,24 @@ def test_glue_kernels_against_the_golden():
     span = (torch.from_numpy(g["d_int"]) * int(g["d_num"]) * float(g["d_scale"])).to(DEV)
     rows, norm = refine.refine_input(initial, images, int(g["n_views"]), d_min, span)
     want = torch.from_numpy(g["refine_input"]).to(DEV)
-    assert rows.shape == (2, 16, 1, 12, 16) and rows.dtype == torch.bfloat16 and rows.is_contiguous(memory_format=torch.channels_last_3d)
+    assert rows.shape == (1, 16, 2, 12, 16) and rows.dtype == torch.bfloat16 and rows.is_contiguous(memory_format=torch.channels_last_3d)
     assert torch.allclose(norm, want[:, :1], rtol=0, atol=1e-6)
-    got = rows[:, :4, 0].float()
+    got = rows[0, :4].permute(1, 0, 2, 3).float()
     assert (got - want).abs().max().item() <= 2.0 ** -8 * max(1.0, float(want.abs().max()))      # one bf16 rounding
     assert torch.equal(got, want.to(torch.bfloat16).float()) or (got - want.to(torch.bfloat16).float()).abs().max().item() <= 2.0 ** -7
-    assert torch.count_nonzero(rows[:, 4:]).item() == 0
+    assert torch.count_nonzero(rows[0, 4:]).item() == 0
     # the residual rows: channel 0 carries the network's output
-    res = torch.zeros(2, 8, 1, 12, 16, dtype=torch.bfloat16, device=DEV).contiguous(memory_format=torch.channels_last_3d)
+    res = torch.zeros(1, 8, 2, 12, 16, dtype=torch.bfloat16, device=DEV).contiguous(memory_format=torch.channels_last_3d)
     r0 = torch.randn(2, 12, 16, device=DEV).to(torch.bfloat16)
-    res[:, 0, 0] = r0
+    res[0, 0] = r0
     res.requires_grad_(True)
     out = refine.refine_output(res, norm, d_min, span)
     want_out = (r0.float().unsqueeze(1) + norm.detach()) * span + d_min
     assert torch.allclose(out, want_out, rtol=1e-6, atol=1e-4)
     gg = torch.randn_like(out)
     out.backward(gg)
-    assert torch.allclose(res.grad[:, 0, 0].float(), (gg * span)[:, 0].to(torch.bfloat16).float())
-    assert torch.count_nonzero(res.grad[:, 1:]).item() == 0
+    assert torch.allclose(res.grad[0, 0].float(), (gg * span)[:, 0].to(torch.bfloat16).float())
+    assert torch.count_nonzero(res.grad[0, 1:]).item() == 0
     assert torch.allclose(initial.grad, gg, rtol=1e-6, atol=1e-7)        # d refined / d initial through norm alone: span / span
 
 
@@ -104,7 +104,7 @@ def test_resize_matches_torch_bilinear(dims):
     zeros, ones = torch.zeros(B, device=DEV), torch.ones(B, device=DEV)
     rows, norm = refine.refine_input(initial, images, V, zeros, ones)
     want = F.interpolate(images[::V], (h, w), mode="bilinear", align_corners=False)
-    got = rows[:, 1:4, 0].float()
+    got = rows[0, 1:4].permute(1, 0, 2, 3).float()
     assert (got - want.to(torch.bfloat16).float()).abs().max().item() <= 2.0 ** -8        # at most one bf16 step on values in [0, 1)
     assert torch.equal(norm, initial)
 
@@ -140,8 +140,8 @@ def test_native_refinement_against_the_golden(monkeypatch):
         runs[mode] = (refined.detach(), initial.grad, dict(net.named_parameters()), net.state_dict(), launched)
     refined, g_init, params, state, launched = runs["native"]
     # the native path ran: 4 convolutions forward, 4 data gradients, 4 weight gradients, the glue each way
-    assert launched.get("conv3d_s1_tc") == 8 and launched.get("conv3d_s1_wgrad_tc") == 4 and launched.get("refine_glue") == 4, launched
-    assert "conv3d_s1_tc" not in runs["torch"][4]
+    assert launched.get("conv2d_tc") == 8 and launched.get("conv2d_wgrad_tc") == 4 and launched.get("refine_glue") == 4, launched
+    assert "conv2d_tc" not in runs["torch"][4]
     want_norm = (want - d_min) / span                                        # in units of the normalised depth: values up to ~2
     err_norm = ((refined - want) / span).abs().max().item()
     assert err_norm <= 1e-2 * max(1.0, float(want_norm.abs().max())), err_norm
