@@ -12,7 +12,8 @@ from .ops import PlaneSweep, warp_variance, warp_materialize, softmax_depth, sof
 from .regulariser import CostVolumeReg, central_region  # noqa: F401
 from . import conv3d_sm100  # noqa: F401  (registers the tcgen05 convolution backend)
 from .refine import refine_depth  # noqa: F401
+from .nets2d import encode_features  # noqa: F401
 
 __all__ = ["homography_warping", "assemble_cost_volume", "extract_depth_map", "CostVolumeReg",
            "WarpedFeatureVolumes", "PlaneSweep", "warp_variance", "warp_materialize", "softmax_depth",
-           "softmax_over_depth", "depth_from_prob", "refine_depth", "MvsB200Error", "launch_count", "load_library"]
+           "softmax_over_depth", "depth_from_prob", "refine_depth", "encode_features", "MvsB200Error", "launch_count", "load_library"]

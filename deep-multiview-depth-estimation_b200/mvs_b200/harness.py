@@ -94,11 +94,7 @@ class MVSNet(nn.Module):
         """model.py:20-65 -> feature maps [N, 32, H/4, W/4] (bf16 on the bf16 path).  SURVEY row f1: bf16 with train-mode BatchNorm
         (what train.py and test.py:61 run) takes the tensor-core kernels of mvs_b200/nets2d.py; MVSB200_ENCODER=torch, fp32 and
         eval-mode BatchNorm evaluate the module's stock torch layers (cuDNN)."""
-        amp = self.precision == "bf16" and nn_input.is_cuda
-        if amp and os.environ.get("MVSB200_ENCODER", "native") == "native" and nets2d.encoder_ok(self.feature_encoder, nn_input):
-            return nets2d.encode_native(self.feature_encoder, nn_input)
-        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
-            return self.feature_encoder(nn_input.contiguous(memory_format=torch.channels_last))
+        return nets2d.encode_features(self.feature_encoder, nn_input, bf16=self.precision == "bf16")
 
     def refine(self, initial, nn_input, n_views, d_trans, d_span):
         """model.py:190-205 on depth offsets / spans already on the device (mvs_b200/refine.py): native on the

@@ -197,3 +197,16 @@ def encode_native(module, images):
     x = _bn_relu(conv3x3(x, convs[6].weight), bns[6])
     x = conv3x3(x, convs[7].weight)
     return x.squeeze(0).permute(1, 0, 2, 3)
+
+
+def encode_features(module, images, bf16=True):
+    """`self.feature_encoder(nn_input)` of model.py:181 as a call a host application can bind: feature maps [N, 32, H/4, W/4].
+    `module` is the application's own FeatureEncoder (the reference's class or harness.FeatureEncoder: same Sequential, same
+    state_dict).  bf16 with train-mode BatchNorm on a GPU runs encode_native (bf16 maps in channels-last memory, the layout K1
+    stages); fp32, eval-mode BatchNorm or MVSB200_ENCODER=torch evaluate the module's own torch layers."""
+    import os
+    amp = bool(bf16) and images.is_cuda
+    if amp and os.environ.get("MVSB200_ENCODER", "native") == "native" and encoder_ok(module, images):
+        return encode_native(module, images)
+    with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
+        return module(images.contiguous(memory_format=torch.channels_last) if images.is_cuda else images)
