@@ -41,6 +41,7 @@ struct Chunk<float> {
         const float4 a = __ldcs(reinterpret_cast<const float4*>(p)), b = __ldcs(reinterpret_cast<const float4*>(p) + 1);
         v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
     }
+    static __device__ __forceinline__ float round(float v) { return v; }
     static __device__ __forceinline__ void store(float* p, const float (&v)[8]) {
         __stcs(reinterpret_cast<float4*>(p), make_float4(v[0], v[1], v[2], v[3]));
         __stcs(reinterpret_cast<float4*>(p) + 1, make_float4(v[4], v[5], v[6], v[7]));
@@ -67,6 +68,7 @@ struct Chunk<__nv_bfloat16> {
             v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
         }
     }
+    static __device__ __forceinline__ float round(float v) { return __bfloat162float(__float2bfloat16(v)); }   // the value a bf16 store keeps
     static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&v)[8]) {
         __stcs(reinterpret_cast<uint4*>(p), make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
                                                         pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7])));
@@ -204,10 +206,13 @@ __global__ void __launch_bounds__(kFinSlices * 2 * kMaxC) bn_finalize_affine_ker
     }
 }
 
-template <typename T>
+// ADD: y = round_T(max(x*scale + shift, 0)) + add -- the skip additions of the decoder (scripts/model.py:117-123) folded into the
+// apply pass; the normalised value is rounded to the storage type first, so the result is bit-identical to a separate addition of
+// the stored tensor (the depth-slab path and the unfused form keep agreeing exactly).
+template <typename T, bool ADD = false>
 __global__ void __launch_bounds__(kBnThreads) bn_relu_fwd_kernel(const T* __restrict__ x, const float* __restrict__ scale,
                                                                  const float* __restrict__ shift, T* __restrict__ y,
-                                                                 long long n_chunks, int C, int relu) {
+                                                                 long long n_chunks, int C, int relu, const T* __restrict__ add = nullptr) {
     const int cpr = C / 8;
     const long long i0 = (long long)blockIdx.x * kBnThreads + threadIdx.x;
     const int cg = (int)(i0 % cpr);
@@ -216,19 +221,24 @@ __global__ void __launch_bounds__(kBnThreads) bn_relu_fwd_kernel(const T* __rest
     for (int k = 0; k < 8; ++k) { sc[k] = scale[cg * 8 + k]; sh[k] = shift[cg * 8 + k]; }
     const long long stride = (long long)gridDim.x * kBnThreads;
     for (long long i = i0; i < n_chunks; i += kBnUnroll * stride) {
-        typename Chunk<T>::Raw raw[kBnUnroll];
+        typename Chunk<T>::Raw raw[kBnUnroll], rawa[ADD ? kBnUnroll : 1];
 #pragma unroll
         for (int u = 0; u < kBnUnroll; ++u)
-            if (i + u * stride < n_chunks) raw[u] = Chunk<T>::ldraw(x + (i + u * stride) * 8);
+            if (i + u * stride < n_chunks) {
+                raw[u] = Chunk<T>::ldraw(x + (i + u * stride) * 8);
+                if (ADD) rawa[ADD ? u : 0] = Chunk<T>::ldraw(add + (i + u * stride) * 8);
+            }
 #pragma unroll
         for (int u = 0; u < kBnUnroll; ++u) {
             if (i + u * stride < n_chunks) {
-                float v[8];
+                float v[8], a[8];
                 Chunk<T>::unpack(raw[u], v);
+                if (ADD) Chunk<T>::unpack(rawa[ADD ? u : 0], a);
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
                     v[k] = fmaf(v[k], sc[k], sh[k]);
                     if (relu) v[k] = fmaxf(v[k], 0.f);
+                    if (ADD) v[k] = Chunk<T>::round(v[k]) + a[k];
                 }
                 Chunk<T>::store(y + (i + u * stride) * 8, v);
             }
@@ -419,10 +429,11 @@ __global__ void __launch_bounds__(kBnThreads) bn_stats_geo_kernel(const T* __res
     block_reduce_to_partial(s, q, cpr, C, partials + (size_t)blockIdx.x * 2 * C);
 }
 
-template <typename T>
+template <typename T, bool ADD = false>
 __global__ void __launch_bounds__(kBnThreads) bn_relu_fwd_crop_kernel(const T* __restrict__ x, const float* __restrict__ scale,
                                                                       const float* __restrict__ shift, T* __restrict__ y,
-                                                                      long long n_box_chunks, int C, int relu, CropBox cb) {
+                                                                      long long n_box_chunks, int C, int relu, CropBox cb,
+                                                                      const T* __restrict__ add = nullptr) {
     const int cpr = C / 8;
     const long long i0 = (long long)blockIdx.x * kBnThreads + threadIdx.x;
     const int cg = (int)(i0 % cpr);
@@ -431,19 +442,24 @@ __global__ void __launch_bounds__(kBnThreads) bn_relu_fwd_crop_kernel(const T* _
     for (int k = 0; k < 8; ++k) { sc[k] = scale[cg * 8 + k]; sh[k] = shift[cg * 8 + k]; }
     const long long stride = (long long)gridDim.x * kBnThreads;
     for (long long i = i0; i < n_box_chunks; i += kBnUnroll * stride) {
-        typename Chunk<T>::Raw raw[kBnUnroll];
+        typename Chunk<T>::Raw raw[kBnUnroll], rawa[ADD ? kBnUnroll : 1];
 #pragma unroll
         for (int u = 0; u < kBnUnroll; ++u)
-            if (i + u * stride < n_box_chunks) raw[u] = Chunk<T>::ldraw(x + box_to_canvas(i + u * stride, cpr, cb) * 8);
+            if (i + u * stride < n_box_chunks) {
+                raw[u] = Chunk<T>::ldraw(x + box_to_canvas(i + u * stride, cpr, cb) * 8);
+                if (ADD) rawa[ADD ? u : 0] = Chunk<T>::ldraw(add + (i + u * stride) * 8);        // the addend lives on the box, as y does
+            }
 #pragma unroll
         for (int u = 0; u < kBnUnroll; ++u) {
             if (i + u * stride < n_box_chunks) {
-                float v[8];
+                float v[8], a[8];
                 Chunk<T>::unpack(raw[u], v);
+                if (ADD) Chunk<T>::unpack(rawa[ADD ? u : 0], a);
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
                     v[k] = fmaf(v[k], sc[k], sh[k]);
                     if (relu) v[k] = fmaxf(v[k], 0.f);
+                    if (ADD) v[k] = Chunk<T>::round(v[k]) + a[k];
                 }
                 Chunk<T>::store(y + (i + u * stride) * 8, v);
             }
@@ -715,6 +731,43 @@ extern "C" int mvsb200_bn_relu_fwd_crop(const void* x, int dtype, const float* s
     else
         bn_relu_fwd_crop_kernel<float><<<grid, kBnThreads, 0, st>>>((const float*)x, scale, shift, (float*)y, n_box, C, relu, cb);
     MVS_CHECK_LAUNCH("bn_relu_fwd_crop");
+    return MVSB200_OK;
+}
+
+/* y = round(max(x*scale + shift, 0)) + add: BatchNorm apply + ReLU + skip addition in one pass (SURVEY §8b `bn_relu_add_apply`;
+ * scripts/model.py:117-123).  geo12 == NULL: x, add and y are [M, C] rows; otherwise y and add live on the crop box of x's canvas
+ * (geometry as mvsb200_bn_relu_fwd_crop).  The normalised value is rounded to the storage type before the addition, so the result
+ * equals a separate addition of the stored tensor bit for bit. */
+extern "C" int mvsb200_bn_relu_add_apply(const void* x, int dtype, const float* scale, const float* shift, const void* add, void* y,
+                                         int relu, int64_t M, int C, const int* geo12, void* stream) {
+    if (int rc = check_bn(x, M, C, "bn_relu_add_apply")) return rc;
+    MVS_REQUIRE(y && aligned16(y) && add && aligned16(add) && scale && shift, "bn_relu_add_apply: null or misaligned argument");
+    MVS_REQUIRE(dtype == MVSB200_F32 || dtype == MVSB200_BF16, "bn_relu_add_apply: bad dtype %d", dtype);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!geo12) {
+        const long long n_chunks = (long long)M * C / 8;
+        const int grid = grid_for(n_chunks);
+        if (dtype == MVSB200_BF16)
+            bn_relu_fwd_kernel<__nv_bfloat16, true><<<grid, kBnThreads, 0, st>>>((const __nv_bfloat16*)x, scale, shift, (__nv_bfloat16*)y,
+                                                                                 n_chunks, C, relu, (const __nv_bfloat16*)add);
+        else
+            bn_relu_fwd_kernel<float, true><<<grid, kBnThreads, 0, st>>>((const float*)x, scale, shift, (float*)y, n_chunks, C, relu,
+                                                                         (const float*)add);
+    } else {
+        CropBox cb; int64_t B;
+        if (int rc = make_box(geo12, M, &B, &cb)) return rc;
+        set_cshift(&cb, C);
+        const long long n_box = (long long)B * cb.dc * cb.hc * cb.wc * C / 8;
+        const int grid = grid_for(n_box);
+        if (dtype == MVSB200_BF16)
+            bn_relu_fwd_crop_kernel<__nv_bfloat16, true><<<grid, kBnThreads, 0, st>>>((const __nv_bfloat16*)x, scale, shift,
+                                                                                      (__nv_bfloat16*)y, n_box, C, relu, cb,
+                                                                                      (const __nv_bfloat16*)add);
+        else
+            bn_relu_fwd_crop_kernel<float, true><<<grid, kBnThreads, 0, st>>>((const float*)x, scale, shift, (float*)y, n_box, C, relu,
+                                                                              cb, (const float*)add);
+    }
+    MVS_CHECK_LAUNCH("bn_relu_add_apply");
     return MVSB200_OK;
 }
 

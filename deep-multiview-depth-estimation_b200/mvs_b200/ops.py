@@ -333,7 +333,7 @@ class _BatchNormReLU(torch.autograd.Function):
     `crop` = ((d0,d1),(h0,h1),(w0,w1)): y (and the incoming gradient) exist only on that box of the canvas."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, eps, relu, crop, canvas, running=None, momentum=0.1, partials=None):
+    def forward(ctx, x, weight, bias, eps, relu, crop, canvas, running=None, momentum=0.1, partials=None, add=None):
         _need_cuda(x, "BatchNorm input")
         _need_cuda(weight, "BatchNorm weight")
         xr, _, C = _rows(x.detach())
@@ -369,18 +369,27 @@ class _BatchNormReLU(torch.autograd.Function):
                 _lib.call("mvsb200_bn_stats_affine", xr.data_ptr(), _DT[xr.dtype], M, C, ws.data_ptr(), geo if canvas != alloc else None,
                           gamma.data_ptr(), beta.data_ptr(), float(eps), float(momentum), _ptr(rm), _ptr(rv), _ptr(nbt),
                           mean.data_ptr(), var.data_ptr(), invstd.data_ptr(), scale.data_ptr(), shift.data_ptr(), _stream())
-        if plain:
-            y = torch.empty_like(xr)
+        (d0, d1), (h0, h1), (w0, w1) = box
+        y = torch.empty_like(xr) if plain else torch.empty((B, C, d1 - d0, h1 - h0, w1 - w0), dtype=xr.dtype, device=dev,
+                                                           memory_format=torch.channels_last_3d)
+        if add is not None:
+            # skip addition folded into the apply pass (model.py:117-123): the addend lives where y does
+            if add.shape != y.shape or add.dtype != y.dtype:
+                raise _lib.MvsB200Error(f"BatchNorm + skip addition: addend {tuple(add.shape)} {add.dtype} for an output "
+                                        f"{tuple(y.shape)} {y.dtype}")
+            ad = add.detach().contiguous(memory_format=torch.channels_last_3d)
+            with _timed("bn_relu_fwd"):
+                _lib.call("mvsb200_bn_relu_add_apply", xr.data_ptr(), _DT[xr.dtype], scale.data_ptr(), shift.data_ptr(), ad.data_ptr(),
+                          y.data_ptr(), int(relu), M, C, None if plain else geo, _stream())
+        elif plain:
             with _timed("bn_relu_fwd"):
                 _lib.call("mvsb200_bn_relu_fwd", xr.data_ptr(), _DT[xr.dtype], scale.data_ptr(), shift.data_ptr(),
                           y.data_ptr(), int(relu), M, C, _stream())
         else:
-            (d0, d1), (h0, h1), (w0, w1) = box
-            y = torch.empty((B, C, d1 - d0, h1 - h0, w1 - w0), dtype=xr.dtype, device=dev,
-                            memory_format=torch.channels_last_3d)
             with _timed("bn_relu_fwd"):
                 _lib.call("mvsb200_bn_relu_fwd_crop", xr.data_ptr(), _DT[xr.dtype], scale.data_ptr(), shift.data_ptr(),
                           y.data_ptr(), int(relu), M, C, geo, _stream())
+        ctx.has_add = add is not None
         ctx.save_for_backward(xr, scale, shift, mean, invstd, gamma)
         ctx.relu, ctx.dims, ctx.geo = bool(relu), (M, C), (None if plain else (alloc, canvas, box))
         ctx.mark_non_differentiable(mean, var)
@@ -408,22 +417,25 @@ class _BatchNormReLU(torch.autograd.Function):
                           scale.data_ptr(), shift.data_ptr(), mean.data_ptr(), invstd.data_ptr(), gamma.data_ptr(),
                           _bn_workspace(dev).data_ptr(), dbeta.data_ptr(), dgamma.data_ptr(), dx.data_ptr(),
                           int(ctx.relu), M, C, _geo12(*ctx.geo), _stream())
-        return dx, dgamma, dbeta, None, None, None, None, None, None, None
+        # the skip addend's gradient is the incoming gradient itself
+        return dx, dgamma, dbeta, None, None, None, None, None, None, None, (gy if ctx.has_add else None)
 
 
-def batchnorm_relu_train(x, weight, bias, eps=1e-5, relu=True, crop=None, canvas=None, running=None, momentum=0.1, partials=None):
+def batchnorm_relu_train(x, weight, bias, eps=1e-5, relu=True, crop=None, canvas=None, running=None, momentum=0.1, partials=None, add=None):
     """-> (y, batch mean [C], biased batch variance [C]); y has x's dtype (fp32 or bf16), channels_last_3d.
     canvas = (D,h,w) <= x's spatial dims: the statistics volume (x may carry allocation slack beyond it);
     crop = ((d0,d1),(h0,h1),(w0,w1)): full-canvas statistics, y only on that box.
     running = (running_mean, running_var, num_batches_tracked): updated in place as torch.nn.BatchNorm does in train mode
     (momentum, unbiased variance), inside the statistics' finalize launch.
     partials = (per-CTA sums [n, 2, C], n, (D,h,w)) left by the kernel that produced x (conv3d_sm100.conv_transpose3d_s2): the
-    statistics are finalized from them, x is not read for them."""
+    statistics are finalized from them, x is not read for them.
+    add = a tensor of y's shape and dtype: y = ReLU(BatchNorm(x)) + add in the same pass (the decoder's skip additions), bit-identical
+    to adding it to the stored y afterwards; its gradient is y's."""
     if crop is not None:
         crop = tuple((int(a), int(b)) for a, b in crop)
     if canvas is not None:
         canvas = tuple(int(n) for n in canvas)
-    return _BatchNormReLU.apply(x, weight, bias, float(eps), bool(relu), crop, canvas, running, float(momentum), partials)
+    return _BatchNormReLU.apply(x, weight, bias, float(eps), bool(relu), crop, canvas, running, float(momentum), partials, add)
 
 
 def affine_relu(x, scale, shift, relu=True):

@@ -114,7 +114,7 @@ class CostVolumeReg(nn.Module):
         w = getattr(self, name).weight
         return w if w.dtype == dtype else w.to(dtype)
 
-    def _bn_dense(self, bn: nn.BatchNorm3d, x, crop=None, canvas=None):
+    def _bn_dense(self, bn: nn.BatchNorm3d, x, crop=None, canvas=None, add=None):
         """BatchNorm (+ReLU) over a full canvas.  `canvas` = (D,h,w): the canvas sits at the origin of x, which may be one
         plane/line/column larger (un-cropped transposed conv); `crop` (three slices): only that box of the result is
         produced.  On the GPU in train mode this is the fused channel-last kernel family of libmvs_b200.so (K3b); the
@@ -124,7 +124,8 @@ class CostVolumeReg(nn.Module):
             # the running statistics (momentum, unbiased variance, counter) are updated inside the statistics' finalize launch
             y, _, _ = ops.batchnorm_relu_train(x, bn.weight, bn.bias, bn.eps, relu=True, crop=box, canvas=canvas,
                                                running=(bn.running_mean, bn.running_var, bn.num_batches_tracked), momentum=bn.momentum,
-                                               partials=getattr(x, "_mvs_bn_partials", None))
+                                               partials=getattr(x, "_mvs_bn_partials", None),
+                                               add=None if add is None else add.to(x.dtype))
             return y
         if canvas is not None:
             x = x[..., :canvas[0], :canvas[1], :canvas[2]]
@@ -132,12 +133,14 @@ class CostVolumeReg(nn.Module):
             if not torch.is_grad_enabled() or not (x.requires_grad or bn.weight.requires_grad):
                 scale = bn.weight * torch.rsqrt(bn.running_var + bn.eps)
                 y = ops.affine_relu(x, scale, bn.bias - bn.running_mean * scale, relu=True)
-                return y if crop is None else y[(slice(None), slice(None)) + tuple(crop)]
+                y = y if crop is None else y[(slice(None), slice(None)) + tuple(crop)]
+                return y if add is None else y + add.to(y.dtype)
         y = F.batch_norm(x, bn.running_mean, bn.running_var, bn.weight, bn.bias, bn.training, bn.momentum, bn.eps)
         if bn.training:
             bn.num_batches_tracked += 1
         y = F.relu(y)
-        return y if crop is None else y[(slice(None), slice(None)) + tuple(crop)]
+        y = y if crop is None else y[(slice(None), slice(None)) + tuple(crop)]
+        return y if add is None else y + add.to(y.dtype)
 
     def _bn_affine(self, bn: nn.BatchNorm3d, mean, var, n_full):
         """scale/shift of BatchNorm given full-canvas batch statistics (train) or the running ones (eval)."""
@@ -269,18 +272,19 @@ class CostVolumeReg(nn.Module):
         # ---- decoder: transposed convs read only C; their outputs are dense canvases (statistics are dense)
         Lp = tuple(L for _, _, L in reg)
 
-        def up(z, name, bn, crop=None):
+        def up(z, name, bn, crop=None, add=None):
             # channel-last operands keep the library on its NDHWC kernels (no layout-conversion passes over the canvas)
             U = be.conv_transpose3d_alloc(z.to(dt).contiguous(memory_format=torch.channels_last_3d), self._w(name, wdt), 2, Lp, dims)
-            return self._bn_dense(bn, U, crop, dims)      # U holds the canvas at its origin (+ up to one slack plane/line/column)
+            # U holds the canvas at its origin (+ up to one slack plane/line/column); `add`: the skip addition (model.py:117-123)
+            # rides on the normalisation's apply pass
+            return self._bn_dense(bn, U, crop, dims, add)
 
         # the transposed convs' canvases are normalised with full-canvas statistics but only their box C is read
         # skip additions in the storage dtype of the path (bf16 path: one more bf16 rounding instead of two fp32 round trips
         # of the box tensors per addition, forward and backward)
-        c3 = up(enc[3], "deconv_3_0", self.BN_2, C)
-        c2 = up(c3 + enc[2].to(c3.dtype), "deconv_2_0", self.BN_1, C)
-        y1 = up(c2 + enc[1].to(c2.dtype), "deconv_1_0", self.BN_0)
-        z = y1 + y0
+        s3 = up(enc[3], "deconv_3_0", self.BN_2, C, enc[2])                  # c3 + enc[2]
+        s2 = up(s3, "deconv_2_0", self.BN_1, C, enc[1])                      # c2 + enc[1]
+        z = up(s2, "deconv_1_0", self.BN_0, None, y0)                        # y1 + y0
         if z.is_cuda and dt == torch.bfloat16 and z.shape[1] == 8 and self.conv_out.out_channels == 1:
             return ops.conv_out(z, self.conv_out.weight)              # K3c: 8 -> 1 is streaming work, not a GEMM
         return be.conv3d(z, self._w("conv_out", dt), 1, (1, 1, 1)).float()

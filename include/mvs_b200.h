@@ -291,6 +291,12 @@ int mvsb200_bn_stats_geo(const void* x, int dtype, int64_t M, int C, float* work
                          const int* geo12_host, void* stream);
 int mvsb200_bn_relu_fwd_crop(const void* x, int dtype, const float* scale, const float* shift, void* y, int relu,
                              int64_t M, int C, const int* geo12_host, void* stream);
+/* y = round(max(x*scale + shift, 0)) + add: BatchNorm apply + ReLU + skip addition in one pass (SURVEY §8b `bn_relu_add_apply`;
+ * scripts/model.py:117-123).  geo12 == NULL: x, add, y are [M, C] rows; otherwise y and add live on the crop box of x's canvas
+ * (geometry as mvsb200_bn_relu_fwd_crop).  The normalised value is rounded to the storage type before the addition: the result
+ * equals a separate addition of the stored tensor bit for bit. */
+int mvsb200_bn_relu_add_apply(const void* x, int dtype, const float* scale, const float* shift, const void* add, void* y, int relu,
+                              int64_t M, int C, const int* geo12, void* stream);
 int mvsb200_bn_relu_bwd_crop(const void* x, int x_dtype, const void* gy, int g_dtype, const float* scale,
                              const float* shift, const float* mean, const float* invstd, const float* gamma,
                              float* workspace, float* dbeta, float* dgamma, void* dx, int relu, int64_t M, int C,

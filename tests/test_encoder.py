@@ -175,3 +175,40 @@ def test_native_encoder_against_the_golden(monkeypatch):
         if k.startswith("w1."):
             got, exp = state[k[3:]].float().cpu(), torch.from_numpy(np.asarray(g[k])).float()
             assert torch.allclose(got, exp, rtol=2e-2, atol=2e-3), k
+
+
+class _ReferenceLayout(torch.nn.Module):
+    """The module layout of model.py:20-65 written with stock torch.nn (Conv2d / BatchNorm2d / ReLU triples)."""
+
+    def __init__(self):
+        super().__init__()
+        nn = torch.nn
+        layers = []
+        for ci, co, k, s in nets2d._ENC_LAYERS[:-1]:
+            layers += [nn.Conv2d(ci, co, k, stride=s, padding=k // 2, bias=False), nn.BatchNorm2d(co), nn.ReLU()]
+        self.model = nn.Sequential(*layers, nn.Conv2d(32, 32, 3, padding=1, bias=False))
+
+    def forward(self, x):
+        return self.model(x)
+
+
+@pytest.mark.gpu
+def test_encode_features_binds_to_a_module_of_the_reference_layout():
+    g = np.load(GOLD)
+    ours = _golden_net(g, DEV)
+    theirs = _ReferenceLayout().to(DEV).train()
+    theirs.load_state_dict(ours.state_dict())
+    images = torch.from_numpy(g["images"]).to(DEV)
+    n0 = mvs_b200.launch_count()
+    a = mvs_b200.encode_features(theirs, images)
+    assert mvs_b200.launch_count() - n0 >= 8 + 8 + 7 * 2             # convolutions, filter packing, BatchNorm: the library ran
+    b = mvs_b200.encode_features(ours, images)
+    assert a.dtype == torch.bfloat16 and a.shape == (3, 32, 6, 10) and torch.equal(a, b)
+    for (ka, va), (kb, vb) in zip(theirs.state_dict().items(), ours.state_dict().items()):
+        assert ka == kb and torch.equal(va, vb), ka
+    theirs.eval()
+    n0 = mvs_b200.launch_count()
+    c = mvs_b200.encode_features(theirs, images)                      # eval-mode BatchNorm: the module's own torch layers
+    assert mvs_b200.launch_count() == n0 and c.shape == a.shape and torch.isfinite(c.float()).all()
+    with pytest.raises(mvs_b200.MvsB200Error):
+        nets2d.image_rows(images.cpu())                               # no CPU path

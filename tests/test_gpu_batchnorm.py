@@ -178,3 +178,28 @@ def test_running_statistics_updated_by_the_finalize_launch(C, geometry):
     assert int(nbt) == 2 == int(ref.num_batches_tracked)
     assert torch.allclose(rm, ref.running_mean, rtol=1e-5, atol=1e-6)
     assert torch.allclose(rv, ref.running_var, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("crop", [None, ((1, 6), (2, 9), (0, 11))])
+def test_skip_addition_rides_on_the_apply_pass(dtype, crop):
+    """SURVEY §8b bn_relu_add_apply (model.py:117-123): y = ReLU(BatchNorm(x)) + add in one pass -- bit-identical to adding the
+    stored tensor afterwards; the addend's gradient is the output's."""
+    C, B, D, h, w = 16, 2, 7, 10, 12
+    g = torch.Generator().manual_seed(31)
+    x = torch.randn(B, C, D, h, w, generator=g).to(DEV).to(dtype).contiguous(memory_format=torch.channels_last_3d)
+    wt = (torch.rand(C, generator=g) + 0.5).to(DEV)
+    bs = torch.randn(C, generator=g).to(DEV)
+    out_dims = (D, h, w) if crop is None else tuple(b - a for a, b in crop)
+    add = torch.randn(B, C, *out_dims, generator=g).to(DEV).to(dtype).contiguous(memory_format=torch.channels_last_3d)
+    x1, a1 = x.clone().requires_grad_(True), add.clone().requires_grad_(True)
+    y1, _, _ = ops.batchnorm_relu_train(x1, wt, bs, crop=crop, add=a1)
+    x2, a2 = x.clone().requires_grad_(True), add.clone().requires_grad_(True)
+    y2 = ops.batchnorm_relu_train(x2, wt, bs, crop=crop)[0] + a2
+    assert y1.shape == y2.shape and torch.equal(y1, y2)
+    gy = torch.randn(y1.shape, generator=g).to(DEV).to(dtype)
+    y1.backward(gy)
+    y2.backward(gy)
+    assert torch.equal(x1.grad, x2.grad) and torch.equal(a1.grad, a2.grad) and torch.equal(a1.grad, gy)
+    with pytest.raises(mvs_b200.MvsB200Error):
+        ops.batchnorm_relu_train(x, wt, bs, crop=crop, add=add[:, :8])
