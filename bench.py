@@ -181,7 +181,7 @@ def run_b200(args, rank, world, local_rank, workload=None, light=False):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if os.environ.get("MVSB200_CUDNN_BENCHMARK", "1") == "1":
-        torch.backends.cudnn.benchmark = True              # library convolutions (2D nets, strided 3D backward): autotuned plans
+        torch.backends.cudnn.benchmark = True              # autotuned plans for whatever still reaches the library (MVSB200_ENCODER / _REFINE=torch A/B runs)
     wl = WORKLOADS[workload]
     B, V, H, W, D, train = wl["B"], wl["V"], wl["H"], wl["W"], wl["D"], wl["train"]
     h, w, C = H // 4, W // 4, 32

@@ -1,8 +1,8 @@
-"""Measurement harness around the hot path: the pieces of the reference that are OUT OF SCOPE for the
-native build (2D feature encoder, depth refinement, loss, optimiser step) written with
-stock torch.nn so that bench.py can time a whole MVSNet forward / train step on synthetic DTU-shaped data.
-Layer shapes follow /root/reference/scripts/model.py:22-65 (encoder), :129-152 (refinement), :168-207 (glue)
-and scripts/loss.py:4-41.  Only the four hot-path calls in `forward` are mvs_b200 code.
+"""Measurement harness around the hot path: the reference's MVSNet wiring, module shells and training step so that bench.py can
+time a whole forward / train step on synthetic DTU-shaped data.  FeatureEncoder / DepthRefinement are the reference's Sequentials
+(/root/reference/scripts/model.py:22-65, :129-152; same state_dict keys); on the bf16 path with train-mode BatchNorm their
+layers run on the library's kernels (mvs_b200/nets2d.py, mvs_b200/refine.py), otherwise as the stock
+torch modules they are.  Glue: model.py:168-207; loss: scripts/loss.py:4-41 (row f3, ops.masked_l1_loss).
 """
 from __future__ import annotations
 
