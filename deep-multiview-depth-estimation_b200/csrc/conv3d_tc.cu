@@ -661,7 +661,16 @@ int launch_wgrad(const void* x, const void* gy, float* gw, int B, int Di, int Hi
         int dev = 0, n = 0;
         if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) sms = n;
     }
-    const long walkers = sms / n_roles > 0 ? sms / n_roles : 1;    // CTAs that walk the items (each role has that many)
+    long walkers = sms / n_roles > 0 ? sms / n_roles : 1;          // CTAs that walk the items (each role has that many)
+    {
+        // every CTA ends with red.global.add of its whole accumulator set (up to 27 x CIN x NCO floats) onto the same addresses: on a
+        // small problem (the 2D networks' maps) a full grid of one-tile CTAs spends its time in those same-address reductions --
+        // give every CTA at least kMinPlaneTiles plane tiles of work
+        static const long kMinPlaneTiles = [] { const char* e = getenv("MVSB200_WG_MIN_TILES"); return e ? atol(e) : 8L; }();
+        const long potential = tiles * B * Do;
+        const long cap = potential / (kMinPlaneTiles > 0 ? kMinPlaneTiles : 1);
+        if (cap < walkers) walkers = cap > 0 ? cap : 1;
+    }
     long best_cost = -1;
     int best_chunks = 1;
     for (int nc = 1; nc <= Do; ++nc) {
