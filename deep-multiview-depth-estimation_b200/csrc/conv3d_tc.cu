@@ -1029,6 +1029,9 @@ int launch_conv_s2(const void* x, const void* w, void* y, int B, int Dx, int Hx,
 struct KdnParams {
     ConvParams c;
     int slots;                      // slab ring depth (2 or 3)
+    int planar;                     // 1: the planes are independent maps (2D convolution, mvsb200_conv2d_rows_fwd): only the middle
+                                    // depth slice of the filter exists -- MMAs of N = Cout on its row block, one slab per output
+                                    // plane (no halo planes), the accumulator IS the output plane (no running partial sums)
 };
 
 template <int CIN, int NOUT, int MB>
@@ -1043,6 +1046,9 @@ conv3d_s1_kdn_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
     constexpr int W_BYTES = 27 * W_TAP_BYTES;
     constexpr int W_BYTES_AL = (W_BYTES + 1023) / 1024 * 1024;
     constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N3 >> 3) << 17) | ((128u >> 4) << 24);
+    constexpr uint32_t IDESC_PLANAR = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NOUT >> 3) << 17) | ((128u >> 4) << 24);
+    const bool planar = kp.planar != 0;
+    const int halo = planar ? 0 : 2;                     // slabs beyond the output planes of a depth run
     constexpr uint32_t TMEM_COLS = 2 * MB * N3 <= 256 ? 256 : 512;
     static_assert(2 * MB * N3 <= 512 && N3 % 16 == 0 && N3 <= 256, "accumulator columns");
     constexpr int kMaxSlots = 3;
@@ -1104,7 +1110,7 @@ conv3d_s1_kdn_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
             int b, d_begin, nd, x0, y0;
             decode(item, b, d_begin, nd, x0, y0);
-            for (int s = 0; s < nd + 2; ++s, ++gs) {
+            for (int s = 0; s < nd + halo; ++s, ++gs) {
                 const int slot = gs % slots;
                 if (gs >= slots) mbar_wait(empty + slot, ((gs / slots) - 1) & 1);
                 if (elect_one()) {
@@ -1123,11 +1129,13 @@ conv3d_s1_kdn_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
         const uint32_t w_lo = (uint32_t)d0 | (smem_u32(w_smem) >> 4);
         const uint32_t slab_lo = (uint32_t)d0 | (smem_u32(slab_smem) >> 4);
         const uint32_t bw16 = (uint32_t)(p.BW * ROWB) >> 4, slab16 = (uint32_t)p.slab_bytes >> 4;
+        const uint32_t idesc = planar ? IDESC_PLANAR : IDESC;
+        const uint32_t w_kd = planar ? (uint32_t)W_TAP_BYTES >> 4 : 0u;      // planar: the kd = 1 row block of every in-plane tap
         int gs = 0;                                      // slabs processed (all items): ring slot, TMEM stage and phases
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
             int b, d_begin, nd, x0, y0;
             decode(item, b, d_begin, nd, x0, y0);
-            for (int s = 0; s < nd + 2; ++s, ++gs) {
+            for (int s = 0; s < nd + halo; ++s, ++gs) {
                 const int stage = gs & 1, slot = gs % slots;
                 if (gs >= 2) mbar_wait(tempty + stage, ((gs >> 1) - 1) & 1);
                 mbar_wait(full + slot, (gs / slots) & 1);
@@ -1147,7 +1155,7 @@ conv3d_s1_kdn_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
 #pragma unroll
                                 for (int k = 0; k < KSTEPS; ++k) {
                                     umma_bf16_lohi(d_tmem, row_lo + (uint32_t)((kw * ROWB + k * 32) >> 4), desc_hi,
-                                                   w_lo + (uint32_t)(((kh * 3 + kw) * 3 * W_TAP_BYTES + k * 32) >> 4), desc_hi, IDESC, acc);
+                                                   w_lo + w_kd + (uint32_t)(((kh * 3 + kw) * 3 * W_TAP_BYTES + k * 32) >> 4), desc_hi, idesc, acc);
                                     acc = 1;
                                 }
                             }
@@ -1175,12 +1183,12 @@ conv3d_s1_kdn_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
             int b, d_begin, nd, x0, y0;
             decode(item, b, d_begin, nd, x0, y0);
-            for (int s = 0; s < nd + 2; ++s, ++gs) {
+            for (int s = 0; s < nd + halo; ++s, ++gs) {
                 const int stage = gs & 1;
                 mbar_wait(tfull + stage, (gs >> 1) & 1);
                 tc_fence_after();
-                const bool store = s >= 2;               // output plane s - 2 is complete with this slab's kd = 2 block
-                __nv_bfloat16* plane0 = p.y + (long long)b * p.y_sb + (long long)(d_begin + s - 2) * p.y_sd + (long long)y0 * p.y_sh +
+                const bool store = s >= halo;            // output plane s - 2 is complete with this slab's kd = 2 block (planar: plane s)
+                __nv_bfloat16* plane0 = p.y + (long long)b * p.y_sb + (long long)(d_begin + s - halo) * p.y_sd + (long long)y0 * p.y_sh +
                                         (long long)x0 * p.y_sw + p.y_coff;
 #pragma unroll
                 for (int mb = 0; mb < MB; ++mb) {
@@ -1189,17 +1197,25 @@ conv3d_s1_kdn_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
                     __nv_bfloat16* row = plane0 + (long long)tj[mb] * p.y_sh + (long long)ti[mb] * p.y_sw;
 #pragma unroll
                     for (int c0 = 0; c0 < NOUT; c0 += 16) {
-                        uint32_t v2[16], v1[16], v0[16];
-                        tmem_ld<16>(t0 + (uint32_t)(2 * NOUT + c0), v2);
-                        tmem_ld<16>(t0 + (uint32_t)(NOUT + c0), v1);
-                        tmem_ld<16>(t0 + (uint32_t)c0, v0);
-                        tmem_ld_wait();
                         float o[16];
+                        if (planar) {
+                            uint32_t v[16];
+                            tmem_ld<16>(t0 + (uint32_t)c0, v);
+                            tmem_ld_wait();
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            o[i] = P2[mb][c0 + i] + __uint_as_float(v2[i]);
-                            P2[mb][c0 + i] = P1[mb][c0 + i] + __uint_as_float(v1[i]);
-                            P1[mb][c0 + i] = __uint_as_float(v0[i]);
+                            for (int i = 0; i < 16; ++i) o[i] = __uint_as_float(v[i]);
+                        } else {
+                            uint32_t v2[16], v1[16], v0[16];
+                            tmem_ld<16>(t0 + (uint32_t)(2 * NOUT + c0), v2);
+                            tmem_ld<16>(t0 + (uint32_t)(NOUT + c0), v1);
+                            tmem_ld<16>(t0 + (uint32_t)c0, v0);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) {
+                                o[i] = P2[mb][c0 + i] + __uint_as_float(v2[i]);
+                                P2[mb][c0 + i] = P1[mb][c0 + i] + __uint_as_float(v1[i]);
+                                P1[mb][c0 + i] = __uint_as_float(v0[i]);
+                            }
                         }
                         if (ok) {
 #pragma unroll
@@ -1229,6 +1245,8 @@ conv3d_s1_kdn_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
 }
 
 TilePlan plan_tiles_mb(int Ho, int Wo, int rowb, size_t w_bytes_al, size_t smem_budget, int MB);
+
+static thread_local int g_kdn_planar = 0;        // set by mvsb200_conv2d_rows_fwd around its call of the kdn dispatch
 
 template <int CIN, int NOUT, int MB>
 int launch_conv_kdn_mb(const void* x, const void* w, void* y, int B, int Di, int Hi, int Wi, int Do, int Ho, int Wo, int cout,
@@ -1274,6 +1292,8 @@ int launch_conv_kdn_mb(const void* x, const void* w, void* y, int B, int Di, int
     p.y_sw = y_cs; p.y_sh = (long long)Wo * y_cs; p.y_sd = (long long)Ho * Wo * y_cs; p.y_sb = (long long)Do * Ho * Wo * y_cs;
     p.y = reinterpret_cast<__nv_bfloat16*>(y);
     kp.slots = slots;
+    kp.planar = g_kdn_planar;
+    const int halo = kp.planar ? 0 : 2;
     const long tiles = (long)tp.tiles_x * tp.tiles_y;
     int sms = 148;
     {
@@ -1286,7 +1306,7 @@ int launch_conv_kdn_mb(const void* x, const void* w, void* y, int B, int Di, int
         const int dc = (Do + nc - 1) / nc;
         if ((long)(nc - 1) * dc >= Do) continue;
         const long items = tiles * nc * B;
-        const long cost = ((items + sms - 1) / sms) * (dc + 3);      // nd + 2 slabs per run + pipeline fill
+        const long cost = ((items + sms - 1) / sms) * (dc + halo + 1);      // nd + 2 slabs per run (planar: nd) + pipeline fill
         if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_chunks = nc; }
     }
     p.nchunks = best_chunks;
@@ -1853,6 +1873,20 @@ extern "C" int mvsb200_conv3d_s2_fwd(const void* x, const void* w_packed, void* 
         row0 += nout;
     }
     return MVSB200_OK;
+}
+
+/* 2D convolution 3x3 / padding 1 of N maps stacked as channel-last rows [N, H, W, Cin] -> [N, H, W, y_cs] (SURVEY §8 rows f1 / f2;
+ * scripts/model.py:22-65, :129-152): conv3d_s1_kdn_kernel in its planar mode.  w_packed is the kdn operand [9 (kh,kw)][3][n_rows][Cin]
+ * of which only the middle row block of every in-plane tap is read. */
+extern "C" int mvsb200_conv3d_s1_fwd_kdn(const void* x, const void* w_packed, void* y, int B, int Di, int Hi, int Wi, int Cin,
+                                         int Do, int Ho, int Wo, int cout, int y_cs, int n_rows, int off_d, int off_h, int off_w,
+                                         void* stream);
+extern "C" int mvsb200_conv2d_rows_fwd(const void* x, const void* w_packed, void* y, int N, int H, int W, int Cin, int cout, int y_cs,
+                                       int n_rows, void* stream) {
+    g_kdn_planar = 1;
+    const int rc = mvsb200_conv3d_s1_fwd_kdn(x, w_packed, y, 1, N, H, W, Cin, N, H, W, cout, y_cs, n_rows, 0, -1, -1, stream);
+    g_kdn_planar = 0;
+    return rc;
 }
 
 /* stats (may be NULL): [n_blocks][2][cout] fp32 per-CTA sums of the stored values and of their squares over the written canvas,

@@ -45,6 +45,7 @@ _SIGNATURES = {
     "mvsb200_conv3d_s1_wgrad": (_I, [_P, _P, _P] + [_I] * 12 + [_P]),
     "mvsb200_conv3d_s1_wgrad_ex": (_I, [_P, _P, _P] + [_I] * 12 + [_c.c_uint, _P]),
     "mvsb200_image_to_rows8": (_I, [_P, _P, _I, _I, _I, _P, _P]),
+    "mvsb200_conv2d_rows_fwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "mvsb200_s2d_rows_bf16": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
     "mvsb200_conv_out_workspace_floats": (_c.c_int64, []),
     "mvsb200_conv_out_fwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),

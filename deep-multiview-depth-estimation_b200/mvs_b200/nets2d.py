@@ -7,19 +7,19 @@ Layout: a batch of maps [N, C, H, W] travels as channel-last bf16 rows stacked a
 (memory N x H x W x C).  On that volume
 
   * a 3x3 convolution (padding 1) IS the 3x3x3 convolution whose filter has only its middle depth slice: the filter operand is
-    packed straight from the Conv2d parameter with the kd = 0 / 2 slots empty (mvsb200_pack_filter), forward and data gradient
-    run conv3d_s1_kdn_kernel -- the depth tap is folded into the MMA's N extent there, so the empty slices cost columns of an
-    MMA that is bound by its A operand, not MMAs -- and the weight gradient runs conv3d_s1_wgrad_tc_kernel with the depth-tap
-    mask 2 (mvsb200_conv3d_s1_wgrad_ex);
+    packed straight from the Conv2d parameter (mvsb200_pack_filter, middle slice of the kdn layout), forward and data gradient
+    run conv3d_s1_kdn_kernel in its PLANAR mode (mvsb200_conv2d_rows_fwd): MMAs of N = Cout on the middle slice's row block, one
+    slab per map, the accumulator is the output plane -- 9 MMAs per 128 pixels and K step, what a native 2D kernel issues
+    (MVSB200_CONV2D=volume keeps the three-slice form for A/B) -- and the weight gradient runs conv3d_s1_wgrad_tc_kernel with
+    the depth-tap mask 2 (mvsb200_conv3d_s1_wgrad_ex);
   * a 5x5 stride-2 convolution (padding 2) is a 3x3 stride-1 convolution of the space-to-depth form [1, 4C, N, H/2, W/2] of its
     input: tap k = 2t + p of an axis reads parity class p at j - 1 + t, so the effective filter [co, (py, px, c), ty, tx] is a
     zero-padded re-indexing of the [co, c, 5, 5] parameter (25 of its 36 taps are real);
   * BatchNorm2d + ReLU over (N, H, W) is BatchNorm3d + ReLU over the volume: the fused K3b kernels, the module's running
     statistics updated in place.
 
-Maps of different samples are neighbouring planes; the only coupling is a multiplication by the zero filter slices (a NaN in one
-sample's map would reach its neighbours -- as it does through the batch statistics of the train-mode BatchNorm that follows
-every layer).  Train mode, bf16 operands, fp32 accumulation; eval-mode BatchNorm and fp32 stay on the module's torch layers."""
+Maps of different samples are neighbouring planes of the volume and never meet: the planar forward reads one plane per output
+plane, the weight gradient computes the middle depth taps only.  Train mode, bf16 operands, fp32 accumulation; eval-mode BatchNorm and fp32 stay on the module's torch layers."""
 from __future__ import annotations
 
 import ctypes
@@ -51,13 +51,22 @@ def _pack2d(w, role, n_rows, n_cols):
     return out
 
 
+def _PLANAR():
+    import os
+    return os.environ.get("MVSB200_CONV2D", "planar") != "volume"
+
+
 def _conv_rows(x, wk, c_out, work):
     """3x3 convolution (padding 1) of the stacked maps x [1, c, N, H, W] with a packed filter -> [1, c_out, N, H, W]."""
     _, c, N, H, W = x.shape
     y = torch.empty((1, c_out, N, H, W), dtype=torch.bfloat16, device=x.device, memory_format=_CL3)
     with _timed("conv2d_tc", work):
-        _lib.call("mvsb200_conv3d_s1_fwd_kdn", x.data_ptr(), wk.data_ptr(), y.data_ptr(), 1, N, H, W, c, N, H, W, c_out, c_out,
-                  _n_rows(c_out), -1, -1, -1, _stream())
+        if _PLANAR():
+            _lib.call("mvsb200_conv2d_rows_fwd", x.data_ptr(), wk.data_ptr(), y.data_ptr(), N, H, W, c, c_out, c_out, _n_rows(c_out),
+                      _stream())
+        else:       # MVSB200_CONV2D=volume: the maps as one volume under the three-slice filter (zero kd = 0 / 2 slices); A/B form
+            _lib.call("mvsb200_conv3d_s1_fwd_kdn", x.data_ptr(), wk.data_ptr(), y.data_ptr(), 1, N, H, W, c, N, H, W, c_out, c_out,
+                      _n_rows(c_out), -1, -1, -1, _stream())
     return y
 
 
