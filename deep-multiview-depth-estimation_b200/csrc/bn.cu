@@ -206,13 +206,28 @@ __global__ void __launch_bounds__(kFinSlices * 2 * kMaxC) bn_finalize_affine_ker
     }
 }
 
+// Space-to-depth addressing: rows of N maps [N, H, W, C] ("shallow") against [N, H/2, W/2, 4C] ("deep", channel
+// (py*2 + px)*C + c of pixel (j, i) = channel c of pixel (2j + py, 2i + px)) -- the form in which a 5x5 stride-2 convolution is a 3x3
+// one.  The BatchNorm that precedes such a convolution writes its output straight in the deep form (S2D forward kernel) and its
+// backward reads the incoming gradient from it, so the permutation costs no pass of its own.
+struct S2dGeo { unsigned W, H, qshift; };           // shallow map size, log2(16-byte chunks per shallow pixel)
+__device__ __forceinline__ long long s2d_chunk(long long i, const S2dGeo& g) {
+    const unsigned k = (unsigned)i & ((1u << g.qshift) - 1u);
+    const unsigned pix = (unsigned)(i >> g.qshift);
+    const unsigned t = pix / g.W, x = pix - t * g.W;
+    const unsigned n = t / g.H, y = t - n * g.H;
+    const unsigned deep_pix = (n * (g.H >> 1) + (y >> 1)) * (g.W >> 1) + (x >> 1);
+    return ((((long long)deep_pix << 2) + ((y & 1u) * 2u + (x & 1u))) << g.qshift) | k;
+}
+
 // ADD: y = round_T(max(x*scale + shift, 0)) + add -- the skip additions of the decoder (scripts/model.py:117-123) folded into the
 // apply pass; the normalised value is rounded to the storage type first, so the result is bit-identical to a separate addition of
 // the stored tensor (the depth-slab path and the unfused form keep agreeing exactly).
-template <typename T, bool ADD = false>
+template <typename T, bool ADD = false, bool S2D = false>
 __global__ void __launch_bounds__(kBnThreads) bn_relu_fwd_kernel(const T* __restrict__ x, const float* __restrict__ scale,
                                                                  const float* __restrict__ shift, T* __restrict__ y,
-                                                                 long long n_chunks, int C, int relu, const T* __restrict__ add = nullptr) {
+                                                                 long long n_chunks, int C, int relu, const T* __restrict__ add = nullptr,
+                                                                 S2dGeo geo = S2dGeo{}) {
     const int cpr = C / 8;
     const long long i0 = (long long)blockIdx.x * kBnThreads + threadIdx.x;
     const int cg = (int)(i0 % cpr);
@@ -240,19 +255,20 @@ __global__ void __launch_bounds__(kBnThreads) bn_relu_fwd_kernel(const T* __rest
                     if (relu) v[k] = fmaxf(v[k], 0.f);
                     if (ADD) v[k] = Chunk<T>::round(v[k]) + a[k];
                 }
-                Chunk<T>::store(y + (i + u * stride) * 8, v);
+                Chunk<T>::store(y + (S2D ? s2d_chunk(i + u * stride, geo) : i + u * stride) * 8, v);
             }
         }
     }
 }
 
-template <typename TX, typename TG>
+template <typename TX, typename TG, bool S2D = false>
 __global__ void __launch_bounds__(kBnThreads) bn_relu_bwd_reduce_kernel(const TX* __restrict__ x, const TG* __restrict__ gy,
                                                                         const float* __restrict__ scale,
                                                                         const float* __restrict__ shift,
                                                                         const float* __restrict__ mean,
                                                                         const float* __restrict__ invstd, long long n_chunks,
-                                                                        int C, int relu, float* __restrict__ partials) {
+                                                                        int C, int relu, float* __restrict__ partials,
+                                                                        S2dGeo geo = S2dGeo{}) {
     const int cpr = C / 8;
     const long long i0 = (long long)blockIdx.x * kBnThreads + threadIdx.x;
     const int cg = (int)(i0 % cpr);
@@ -268,7 +284,10 @@ __global__ void __launch_bounds__(kBnThreads) bn_relu_bwd_reduce_kernel(const TX
         typename Chunk<TG>::Raw rg[kBnUnroll];
 #pragma unroll
         for (int u = 0; u < kBnUnroll; ++u)
-            if (i + u * stride < n_chunks) { rx[u] = Chunk<TX>::ldraw(x + (i + u * stride) * 8); rg[u] = Chunk<TG>::ldraw(gy + (i + u * stride) * 8); }
+            if (i + u * stride < n_chunks) {
+                rx[u] = Chunk<TX>::ldraw(x + (i + u * stride) * 8);
+                rg[u] = Chunk<TG>::ldraw(gy + (S2D ? s2d_chunk(i + u * stride, geo) : i + u * stride) * 8);
+            }
 #pragma unroll
         for (int u = 0; u < kBnUnroll; ++u) {
             if (i + u * stride < n_chunks) {
@@ -316,7 +335,7 @@ __device__ __forceinline__ void bwd_apply8(const BwdCoef& k, float (&v)[8], cons
     }
 }
 
-template <typename TX, typename TG>
+template <typename TX, typename TG, bool S2D = false>
 __global__ void __launch_bounds__(kBnThreads) bn_relu_bwd_apply_kernel(const TX* __restrict__ x, const TG* __restrict__ gy,
                                                                        const float* __restrict__ scale,
                                                                        const float* __restrict__ shift,
@@ -325,7 +344,8 @@ __global__ void __launch_bounds__(kBnThreads) bn_relu_bwd_apply_kernel(const TX*
                                                                        const float* __restrict__ gamma,
                                                                        const float* __restrict__ dbeta,
                                                                        const float* __restrict__ dgamma, TX* __restrict__ dx,
-                                                                       long long n_chunks, int C, int relu, float inv_m) {
+                                                                       long long n_chunks, int C, int relu, float inv_m,
+                                                                       S2dGeo geo = S2dGeo{}) {
     const int cpr = C / 8;
     const long long i0 = (long long)blockIdx.x * kBnThreads + threadIdx.x;
     const int cg = (int)(i0 % cpr);
@@ -337,7 +357,10 @@ __global__ void __launch_bounds__(kBnThreads) bn_relu_bwd_apply_kernel(const TX*
         typename Chunk<TG>::Raw rg[kBnUnroll];
 #pragma unroll
         for (int u = 0; u < kBnUnroll; ++u)
-            if (i + u * stride < n_chunks) { rx[u] = Chunk<TX>::ldraw(x + (i + u * stride) * 8); rg[u] = Chunk<TG>::ldraw(gy + (i + u * stride) * 8); }
+            if (i + u * stride < n_chunks) {
+                rx[u] = Chunk<TX>::ldraw(x + (i + u * stride) * 8);
+                rg[u] = Chunk<TG>::ldraw(gy + (S2D ? s2d_chunk(i + u * stride, geo) : i + u * stride) * 8);
+            }
 #pragma unroll
         for (int u = 0; u < kBnUnroll; ++u) {
             if (i + u * stride < n_chunks) {
@@ -638,19 +661,67 @@ extern "C" int mvsb200_bn_relu_fwd(const void* x, int dtype, const float* scale,
 template <typename TX, typename TG>
 static int bn_bwd_impl(const void* x, const void* gy, const float* scale, const float* shift, const float* mean,
                        const float* invstd, const float* gamma, float* workspace, float* dbeta, float* dgamma, void* dx,
-                       int relu, int64_t M, int C, cudaStream_t st) {
+                       int relu, int64_t M, int C, cudaStream_t st, const S2dGeo* s2d = nullptr) {
     const long long n_chunks = (long long)M * C / 8;
     const int grid = grid_for(n_chunks);
-    bn_relu_bwd_reduce_kernel<TX, TG><<<grid, kBnThreads, 0, st>>>((const TX*)x, (const TG*)gy, scale, shift, mean, invstd,
-                                                                   n_chunks, C, relu, workspace);
+    if (s2d)
+        bn_relu_bwd_reduce_kernel<TX, TG, true><<<grid, kBnThreads, 0, st>>>((const TX*)x, (const TG*)gy, scale, shift, mean, invstd,
+                                                                             n_chunks, C, relu, workspace, *s2d);
+    else
+        bn_relu_bwd_reduce_kernel<TX, TG><<<grid, kBnThreads, 0, st>>>((const TX*)x, (const TG*)gy, scale, shift, mean, invstd,
+                                                                       n_chunks, C, relu, workspace);
     MVS_CHECK_LAUNCH("bn_relu_bwd_reduce");
     bn_finalize_kernel<<<1, kFinSlices * 2 * kMaxC, 0, st>>>(workspace, grid, C, 1.0, 1, dbeta, dgamma);
     MVS_CHECK_LAUNCH("bn_finalize");
-    bn_relu_bwd_apply_kernel<TX, TG><<<grid, kBnThreads, 0, st>>>((const TX*)x, (const TG*)gy, scale, shift, mean, invstd,
-                                                                  gamma, dbeta, dgamma, (TX*)dx, n_chunks, C, relu,
-                                                                  (float)(1.0 / (double)M));
+    if (s2d)
+        bn_relu_bwd_apply_kernel<TX, TG, true><<<grid, kBnThreads, 0, st>>>((const TX*)x, (const TG*)gy, scale, shift, mean, invstd,
+                                                                            gamma, dbeta, dgamma, (TX*)dx, n_chunks, C, relu,
+                                                                            (float)(1.0 / (double)M), *s2d);
+    else
+        bn_relu_bwd_apply_kernel<TX, TG><<<grid, kBnThreads, 0, st>>>((const TX*)x, (const TG*)gy, scale, shift, mean, invstd,
+                                                                      gamma, dbeta, dgamma, (TX*)dx, n_chunks, C, relu,
+                                                                      (float)(1.0 / (double)M));
     MVS_CHECK_LAUNCH("bn_relu_bwd_apply");
     return MVSB200_OK;
+}
+
+static int make_s2d(int64_t M, int C, int H, int W, S2dGeo* g, const char* name) {
+    MVS_REQUIRE(H >= 2 && W >= 2 && H % 2 == 0 && W % 2 == 0 && M % ((int64_t)H * W) == 0, "%s: maps of %d x %d do not tile M", name, H, W);
+    MVS_REQUIRE(C == 8 || C == 16 || C == 32 || C == 64, "%s: C must be 8, 16, 32 or 64 (got %d)", name, C);
+    MVS_REQUIRE(M * (C / 8) < (1LL << 31), "%s: too many rows for 32-bit pixel indices", name);
+    g->W = (unsigned)W; g->H = (unsigned)H;
+    g->qshift = C == 8 ? 0u : (C == 16 ? 1u : (C == 32 ? 2u : 3u));
+    return MVSB200_OK;
+}
+
+/* BatchNorm apply + ReLU whose OUTPUT is written in the space-to-depth form: x rows [N, H, W, C] -> y rows [N, H/2, W/2, 4C]
+ * (M = N*H*W).  The backward reads its incoming gradient from that form. */
+extern "C" int mvsb200_bn_relu_fwd_s2d(const void* x, int dtype, const float* scale, const float* shift, void* y, int relu,
+                                       int64_t M, int C, int H, int W, void* stream) {
+    if (int rc = check_bn(x, M, C, "bn_relu_fwd_s2d")) return rc;
+    MVS_REQUIRE(y && aligned16(y) && scale && shift, "bn_relu_fwd_s2d: null or misaligned argument");
+    MVS_REQUIRE(dtype == MVSB200_F32 || dtype == MVSB200_BF16, "bn_relu_fwd_s2d: bad dtype %d", dtype);
+    S2dGeo g;
+    if (int rc = make_s2d(M, C, H, W, &g, "bn_relu_fwd_s2d")) return rc;
+    MVS_REQUIRE(dtype == MVSB200_BF16, "bn_relu_fwd_s2d: bf16 rows only (16-byte chunks of 8 channels)");
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long n_chunks = (long long)M * C / 8;
+    bn_relu_fwd_kernel<__nv_bfloat16, false, true><<<grid_for(n_chunks), kBnThreads, 0, st>>>(
+        (const __nv_bfloat16*)x, scale, shift, (__nv_bfloat16*)y, n_chunks, C, relu, nullptr, g);
+    MVS_CHECK_LAUNCH("bn_relu_fwd_s2d");
+    return MVSB200_OK;
+}
+
+extern "C" int mvsb200_bn_relu_bwd_s2d(const void* x, const void* gy, const float* scale, const float* shift, const float* mean,
+                                       const float* invstd, const float* gamma, float* workspace, float* dbeta, float* dgamma,
+                                       void* dx, int relu, int64_t M, int C, int H, int W, void* stream) {
+    if (int rc = check_bn(x, M, C, "bn_relu_bwd_s2d")) return rc;
+    MVS_REQUIRE(gy && aligned16(gy) && dx && aligned16(dx), "bn_relu_bwd_s2d: null or misaligned volume");
+    MVS_REQUIRE(scale && shift && mean && invstd && gamma && workspace && dbeta && dgamma, "bn_relu_bwd_s2d: null vector");
+    S2dGeo g;
+    if (int rc = make_s2d(M, C, H, W, &g, "bn_relu_bwd_s2d")) return rc;
+    return bn_bwd_impl<__nv_bfloat16, __nv_bfloat16>(x, gy, scale, shift, mean, invstd, gamma, workspace, dbeta, dgamma, dx, relu, M, C,
+                                                     (cudaStream_t)stream, &g);
 }
 
 extern "C" int mvsb200_bn_relu_bwd(const void* x, int x_dtype, const void* gy, int g_dtype, const float* scale,

@@ -70,6 +70,8 @@ _SIGNATURES = {
     "mvsb200_bn_workspace_floats": (_c.c_int64, []),
     "mvsb200_bn_stats": (_I, [_P, _I, _c.c_int64, _I, _P, _P, _P, _P]),
     "mvsb200_bn_relu_fwd": (_I, [_P, _I, _P, _P, _P, _I, _c.c_int64, _I, _P]),
+    "mvsb200_bn_relu_fwd_s2d": (_I, [_P, _I, _P, _P, _P, _I, _c.c_int64, _I, _I, _I, _P]),
+    "mvsb200_bn_relu_bwd_s2d": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _c.c_int64, _I, _I, _I, _P]),
     "mvsb200_bn_stats_affine": (_I, [_P, _I, _c.c_int64, _I, _P, _P, _P, _P, _c.c_double, _c.c_double, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "mvsb200_bn_finalize_affine": (_I, [_P, _I, _c.c_int64, _I, _P, _P, _c.c_double, _c.c_double, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "mvsb200_bn_stats_geo": (_I, [_P, _I, _c.c_int64, _I, _P, _P, _P, _P, _P]),

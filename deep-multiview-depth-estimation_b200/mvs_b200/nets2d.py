@@ -163,10 +163,15 @@ def image_rows(images):
     return rows
 
 
-def _bn_relu(y, bn):
+def _bn_relu(y, bn, s2d=False):
+    """BatchNorm2d + ReLU of the stacked maps on the fused K3b kernels; s2d: the result leaves in the space-to-depth form (the
+    input of a 5x5 stride-2 layer), written by the apply pass itself -- MVSB200_S2D=separate keeps the permutation a pass of its own."""
+    import os
+    fused = s2d and os.environ.get("MVSB200_S2D", "fused") != "separate"
     out, _, _ = ops.batchnorm_relu_train(y, bn.weight, bn.bias, bn.eps, relu=True,
-                                         running=(bn.running_mean, bn.running_var, bn.num_batches_tracked), momentum=bn.momentum)
-    return out
+                                         running=(bn.running_mean, bn.running_var, bn.num_batches_tracked), momentum=bn.momentum,
+                                         s2d=fused)
+    return space_to_depth(out) if s2d and not fused else out
 
 
 _ENC_LAYERS = ((3, 8, 3, 1), (8, 8, 3, 1), (8, 16, 5, 2), (16, 16, 3, 1), (16, 16, 3, 1), (16, 32, 5, 2), (32, 32, 3, 1), (32, 32, 3, 1))
@@ -196,12 +201,10 @@ def encode_native(module, images):
     bns = [m for m in module.model if isinstance(m, torch.nn.BatchNorm2d)]
     x = image_rows(images)
     x = _bn_relu(conv3x3(x, convs[0].weight), bns[0])
-    x = _bn_relu(conv3x3(x, convs[1].weight), bns[1])
-    x = space_to_depth(x)
+    x = _bn_relu(conv3x3(x, convs[1].weight), bns[1], s2d=True)
     x = _bn_relu(conv3x3(x, k5s2_as_3x3(convs[2].weight)), bns[2])
     x = _bn_relu(conv3x3(x, convs[3].weight), bns[3])
-    x = _bn_relu(conv3x3(x, convs[4].weight), bns[4])
-    x = space_to_depth(x)
+    x = _bn_relu(conv3x3(x, convs[4].weight), bns[4], s2d=True)
     x = _bn_relu(conv3x3(x, k5s2_as_3x3(convs[5].weight)), bns[5])
     x = _bn_relu(conv3x3(x, convs[6].weight), bns[6])
     x = conv3x3(x, convs[7].weight)

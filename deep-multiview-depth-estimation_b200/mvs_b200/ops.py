@@ -333,7 +333,7 @@ class _BatchNormReLU(torch.autograd.Function):
     `crop` = ((d0,d1),(h0,h1),(w0,w1)): y (and the incoming gradient) exist only on that box of the canvas."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, eps, relu, crop, canvas, running=None, momentum=0.1, partials=None, add=None):
+    def forward(ctx, x, weight, bias, eps, relu, crop, canvas, running=None, momentum=0.1, partials=None, add=None, s2d=False):
         _need_cuda(x, "BatchNorm input")
         _need_cuda(weight, "BatchNorm weight")
         xr, _, C = _rows(x.detach())
@@ -372,7 +372,20 @@ class _BatchNormReLU(torch.autograd.Function):
         (d0, d1), (h0, h1), (w0, w1) = box
         y = torch.empty_like(xr) if plain else torch.empty((B, C, d1 - d0, h1 - h0, w1 - w0), dtype=xr.dtype, device=dev,
                                                            memory_format=torch.channels_last_3d)
-        if add is not None:
+        ctx.s2d = None
+        if s2d:
+            # stacked maps [1, C, N, H, W] -> the normalised maps in the space-to-depth form [1, 4C, N, H/2, W/2] (nets2d.py: the
+            # input of a 5x5 stride-2 layer), written by the apply pass itself; the backward reads its gradient from that form
+            if not plain or add is not None or xr.shape[0] != 1 or xr.dtype != torch.bfloat16 or alloc[1] % 2 or alloc[2] % 2:
+                raise _lib.MvsB200Error(f"BatchNorm with space-to-depth output: dense stacked bf16 maps of even size expected, got "
+                                        f"{tuple(xr.shape)} {xr.dtype}")
+            Nm, H, W = alloc
+            y = torch.empty((1, 4 * C, Nm, H // 2, W // 2), dtype=xr.dtype, device=dev, memory_format=torch.channels_last_3d)
+            with _timed("bn_relu_fwd"):
+                _lib.call("mvsb200_bn_relu_fwd_s2d", xr.data_ptr(), _DT[xr.dtype], scale.data_ptr(), shift.data_ptr(), y.data_ptr(),
+                          int(relu), M, C, H, W, _stream())
+            ctx.s2d = (H, W)
+        elif add is not None:
             # skip addition folded into the apply pass (model.py:117-123): the addend lives where y does
             if add.shape != y.shape or add.dtype != y.dtype:
                 raise _lib.MvsB200Error(f"BatchNorm + skip addition: addend {tuple(add.shape)} {add.dtype} for an output "
@@ -407,7 +420,12 @@ class _BatchNormReLU(torch.autograd.Function):
         dgamma = torch.empty(C, dtype=torch.float32, device=dev)
         dx = torch.empty_like(xr)
         with _timed("bn_relu_bwd"):
-            if ctx.geo is None:
+            if ctx.s2d is not None:
+                gy = gy.to(torch.bfloat16).contiguous(memory_format=torch.channels_last_3d)
+                _lib.call("mvsb200_bn_relu_bwd_s2d", xr.data_ptr(), gy.data_ptr(), scale.data_ptr(), shift.data_ptr(), mean.data_ptr(),
+                          invstd.data_ptr(), gamma.data_ptr(), _bn_workspace(dev).data_ptr(), dbeta.data_ptr(), dgamma.data_ptr(),
+                          dx.data_ptr(), int(ctx.relu), M, C, ctx.s2d[0], ctx.s2d[1], _stream())
+            elif ctx.geo is None:
                 _lib.call("mvsb200_bn_relu_bwd", xr.data_ptr(), _DT[xr.dtype], gy.data_ptr(), _DT[gy.dtype],
                           scale.data_ptr(), shift.data_ptr(), mean.data_ptr(), invstd.data_ptr(), gamma.data_ptr(),
                           _bn_workspace(dev).data_ptr(), dbeta.data_ptr(), dgamma.data_ptr(), dx.data_ptr(),
@@ -418,10 +436,11 @@ class _BatchNormReLU(torch.autograd.Function):
                           _bn_workspace(dev).data_ptr(), dbeta.data_ptr(), dgamma.data_ptr(), dx.data_ptr(),
                           int(ctx.relu), M, C, _geo12(*ctx.geo), _stream())
         # the skip addend's gradient is the incoming gradient itself
-        return dx, dgamma, dbeta, None, None, None, None, None, None, None, (gy if ctx.has_add else None)
+        return dx, dgamma, dbeta, None, None, None, None, None, None, None, (gy if ctx.has_add else None), None
 
 
-def batchnorm_relu_train(x, weight, bias, eps=1e-5, relu=True, crop=None, canvas=None, running=None, momentum=0.1, partials=None, add=None):
+def batchnorm_relu_train(x, weight, bias, eps=1e-5, relu=True, crop=None, canvas=None, running=None, momentum=0.1, partials=None, add=None,
+                         s2d=False):
     """-> (y, batch mean [C], biased batch variance [C]); y has x's dtype (fp32 or bf16), channels_last_3d.
     canvas = (D,h,w) <= x's spatial dims: the statistics volume (x may carry allocation slack beyond it);
     crop = ((d0,d1),(h0,h1),(w0,w1)): full-canvas statistics, y only on that box.
@@ -430,12 +449,14 @@ def batchnorm_relu_train(x, weight, bias, eps=1e-5, relu=True, crop=None, canvas
     partials = (per-CTA sums [n, 2, C], n, (D,h,w)) left by the kernel that produced x (conv3d_sm100.conv_transpose3d_s2): the
     statistics are finalized from them, x is not read for them.
     add = a tensor of y's shape and dtype: y = ReLU(BatchNorm(x)) + add in the same pass (the decoder's skip additions), bit-identical
-    to adding it to the stored y afterwards; its gradient is y's."""
+    to adding it to the stored y afterwards; its gradient is y's.
+    s2d: x is a stack of maps [1, C, N, H, W]; y leaves in the space-to-depth form [1, 4C, N, H/2, W/2] (nets2d.space_to_depth of
+    the normalised maps, written by the apply pass itself)."""
     if crop is not None:
         crop = tuple((int(a), int(b)) for a, b in crop)
     if canvas is not None:
         canvas = tuple(int(n) for n in canvas)
-    return _BatchNormReLU.apply(x, weight, bias, float(eps), bool(relu), crop, canvas, running, float(momentum), partials, add)
+    return _BatchNormReLU.apply(x, weight, bias, float(eps), bool(relu), crop, canvas, running, float(momentum), partials, add, bool(s2d))
 
 
 def affine_relu(x, scale, shift, relu=True):

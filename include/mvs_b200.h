@@ -377,6 +377,14 @@ int mvsb200_refine_output_bwd(const float* g_refined, const float* span, int B, 
  * conv2d_rows_fwd:  3x3 / padding-1 convolution of N stacked maps, rows [N, H, W, Cin] -> [N, H, W, y_cs]: conv3d_s1_kdn_kernel in its
  *                  planar mode (MMAs of N = cout on the middle depth slice of the kdn filter operand [9][3][n_rows][Cin], one slab
  *                  per map, no halo planes); with the flipped, transposed filter it is the data gradient. */
+/* BatchNorm apply + ReLU written straight in the space-to-depth form (x rows [N, H, W, C] bf16 -> y rows [N, H/2, W/2, 4C], M = N*H*W),
+ * and the BatchNorm backward that reads its incoming gradient gy from that form (dx in x's form): the permutation in front of a 5x5
+ * stride-2 layer costs no pass of its own.  Arguments as mvsb200_bn_relu_fwd / mvsb200_bn_relu_bwd (bf16 x, y, gy, dx). */
+int mvsb200_bn_relu_fwd_s2d(const void* x, int dtype, const float* scale, const float* shift, void* y, int relu, int64_t M, int C,
+                            int H, int W, void* stream);
+int mvsb200_bn_relu_bwd_s2d(const void* x, const void* gy, const float* scale, const float* shift, const float* mean,
+                            const float* invstd, const float* gamma, float* workspace, float* dbeta, float* dgamma, void* dx,
+                            int relu, int64_t M, int C, int H, int W, void* stream);
 int mvsb200_conv2d_rows_fwd(const void* x, const void* w_packed, void* y, int N, int H, int W, int Cin, int cout, int y_cs, int n_rows,
                             void* stream);
 int mvsb200_image_to_rows8(const float* images, const int64_t* strides4_host, int N, int H, int W, void* rows, void* stream);
