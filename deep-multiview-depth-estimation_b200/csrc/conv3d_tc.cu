@@ -714,9 +714,12 @@ struct ConvS2Params {
     int cout, y_cs, y_coff, n_rows, w_row0;
     int slab_bytes;
     __nv_bfloat16* y;
+    float* stats;                   // null, or [gridDim.x][2][stats_cs]: per-CTA sums of the outputs and of their squares (fp32
+    int stats_cs;                   // accumulators), this launch's channels at column y_coff -- the box BatchNorm that follows the
+                                    // stacked branches (scripts/model.py:104-110) then needs no pass over them for its statistics
 };
 
-template <int CIN, int NOUT>
+template <int CIN, int NOUT, bool STATS = false>
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv3d_s2_tc_kernel(const __grid_constant__ CUtensorMap tm_x00, const __grid_constant__ CUtensorMap tm_x01,
                     const __grid_constant__ CUtensorMap tm_x10, const __grid_constant__ CUtensorMap tm_x11,
@@ -871,6 +874,10 @@ conv3d_s2_tc_kernel(const __grid_constant__ CUtensorMap tm_x00, const __grid_con
             tj[mb] = m / p.BW; ti[mb] = m - tj[mb] * p.BW;
             ok[mb] = ti[mb] < p.BW - 1 && tj[mb] < p.L;
         }
+        constexpr bool want_stats = STATS;            // (a template parameter: 128 more live registers only where they are used)
+        float st_s[STATS ? NOUT : 1], st_q[STATS ? NOUT : 1];
+#pragma unroll
+        for (int ch = 0; ch < (STATS ? NOUT : 1); ++ch) { st_s[ch] = 0.f; st_q[ch] = 0.f; }
         int gp = 0;
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
             int b, d_begin, nd, x0, y0;
@@ -890,6 +897,14 @@ conv3d_s2_tc_kernel(const __grid_constant__ CUtensorMap tm_x00, const __grid_con
                             tmem_ld_wait();
                             if (ok[mb] && x0 + ti[mb] < p.Wo && y0 + tj[mb] < p.Ho) {
                                 __nv_bfloat16* row = plane0 + ((size_t)tj[mb] * p.Wo + ti[mb]) * p.y_cs;
+                                if constexpr (STATS) {
+#pragma unroll
+                                    for (int c = 0; c < 16; ++c) {
+                                        const float r = __uint_as_float(v[c]);
+                                        st_s[c0 + c] += r;
+                                        st_q[c0 + c] = fmaf(r, r, st_q[c0 + c]);
+                                    }
+                                }
 #pragma unroll
                                 for (int c = 0; c < 16; c += 8) {
                                     if (c0 + c < p.cout) {
@@ -909,15 +924,53 @@ conv3d_s2_tc_kernel(const __grid_constant__ CUtensorMap tm_x00, const __grid_con
                 if (lane == 0) mbar_arrive(tempty + stage);
             }
         }
+        if constexpr (STATS) {
+            // warp totals (fixed shuffle order); the four epilogue warps' rows side by side in the slab ring, which is idle by now
+            // (the last accumulator has been read: every slab was consumed, every TMA load had landed)
+            float* stats_smem = reinterpret_cast<float*>(slab_smem);        // [4 warps][2][NOUT]
+#pragma unroll
+            for (int ch = 0; ch < NOUT; ++ch) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    st_s[ch] += __shfl_xor_sync(0xffffffffu, st_s[ch], o);
+                    st_q[ch] += __shfl_xor_sync(0xffffffffu, st_q[ch], o);
+                }
+            }
+            if (lane == 0) {
+#pragma unroll
+                for (int ch = 0; ch < NOUT; ++ch) { stats_smem[(q * 2 + 0) * NOUT + ch] = st_s[ch]; stats_smem[(q * 2 + 1) * NOUT + ch] = st_q[ch]; }
+            }
+        }
     }
 
     tc_fence_before();
     __syncthreads();
+    if (STATS && (int)threadIdx.x < 2 * p.cout) {                       // the CTA's partial row, warps added in fixed order
+        const float* stats_smem = reinterpret_cast<const float*>(slab_smem);
+        const int which = threadIdx.x / p.cout, ch = threadIdx.x % p.cout;
+        float t = 0.f;
+#pragma unroll
+        for (int w4 = 0; w4 < 4; ++w4) t += stats_smem[(w4 * 2 + which) * NOUT + ch];
+        p.stats[((size_t)blockIdx.x * 2 + which) * p.stats_cs + p.y_coff + ch] = t;
+    }
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
     }
 }
+
+// partial rows [n_blocks][2][C] of a stride-2 convolution's epilogue statistics -> sums [2][C] (fixed order, fp64 inside)
+__global__ void s2_stats_finalize_kernel(const float* __restrict__ partials, int n_blocks, int C, float* __restrict__ sums) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 2 * C) return;
+    double acc = 0.0;
+    for (int b = 0; b < n_blocks; ++b) acc += (double)partials[(size_t)b * 2 * C + t];
+    sums[t] = (float)acc;
+}
+
+static thread_local float* g_s2_stats = nullptr;    // set by mvsb200_conv3d_s2_fwd_stats around its launches
+static thread_local int g_s2_stats_cs = 0;
+static thread_local int g_s2_stats_blocks = 0;      // largest grid of those launches
 
 TilePlan plan_tiles_s2(int Ho, int Wo, int rowb, size_t w_bytes_al, size_t smem_budget) {
     TilePlan best{};
@@ -988,6 +1041,10 @@ int launch_conv_s2(const void* x, const void* w, void* y, int B, int Dx, int Hx,
     p.cout = cout; p.y_cs = y_cs; p.y_coff = y_coff; p.n_rows = n_rows; p.w_row0 = w_row0;
     p.slab_bytes = tp.slab_bytes;
     p.y = reinterpret_cast<__nv_bfloat16*>(y);
+    p.stats = g_s2_stats;
+    p.stats_cs = g_s2_stats_cs;
+    MVS_REQUIRE(p.stats == nullptr || (size_t)kS2Slots * tp.slab_bytes >= (size_t)4 * 2 * NOUT * sizeof(float), "conv3d_s2: slab ring too small for the statistics rows");
+    MVS_REQUIRE(p.stats == nullptr || 2 * cout <= kTcThreads, "conv3d_s2: %d channels per launch with statistics", cout);
     const long tiles = (long)tp.tiles_x * tp.tiles_y;
     int sms = 148;
     {
@@ -1007,7 +1064,19 @@ int launch_conv_s2(const void* x, const void* w, void* y, int B, int Dx, int Hx,
     p.dchunk = (Do + best_chunks - 1) / best_chunks;
     p.n_items = (int)(tiles * p.nchunks * B);
     const dim3 grid((unsigned)(p.n_items < sms ? p.n_items : sms), 1, 1);
+    if ((int)grid.x > g_s2_stats_blocks) g_s2_stats_blocks = (int)grid.x;
     const size_t smem = 1024 + W_BYTES_AL + (size_t)kS2Slots * tp.slab_bytes + 256;
+    if (p.stats != nullptr) {
+        // epilogue statistics: instantiated for the cost volume's 32 channels (the stacked branches, scripts/model.py:104-110)
+        if constexpr (CIN == 32) {
+            MVS_CUDA(cudaFuncSetAttribute(conv3d_s2_tc_kernel<CIN, NOUT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            conv3d_s2_tc_kernel<CIN, NOUT, true><<<grid, kTcThreads, smem, st>>>(tm_x[0], tm_x[1], tm_x[2], tm_x[3], tm_w, p);
+            MVS_CHECK_LAUNCH("conv3d_s2_tc");
+            return MVSB200_OK;
+        } else {
+            MVS_FAIL(MVSB200_E_UNSUPPORTED, "conv3d_s2_fwd_stats: epilogue statistics are built for 32 input channels (got %d)", CIN);
+        }
+    }
     MVS_CUDA(cudaFuncSetAttribute(conv3d_s2_tc_kernel<CIN, NOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     conv3d_s2_tc_kernel<CIN, NOUT><<<grid, kTcThreads, smem, st>>>(tm_x[0], tm_x[1], tm_x[2], tm_x[3], tm_w, p);
     MVS_CHECK_LAUNCH("conv3d_s2_tc");
@@ -1887,6 +1956,32 @@ extern "C" int mvsb200_conv2d_rows_fwd(const void* x, const void* w_packed, void
     const int rc = mvsb200_conv3d_s1_fwd_kdn(x, w_packed, y, 1, N, H, W, Cin, N, H, W, cout, y_cs, n_rows, 0, -1, -1, stream);
     g_kdn_planar = 0;
     return rc;
+}
+
+/* mvsb200_conv3d_s2_fwd that also leaves sums[2][cout] = (sum, sum of squares) of its outputs per channel, accumulated in the
+ * kernels' epilogues (fp32 accumulators) and combined in fixed order: the box BatchNorm that follows needs no statistics pass.
+ * workspace: at least (SM count) * 2 * cout floats. */
+extern "C" int mvsb200_conv3d_s2_fwd(const void* x, const void* w_packed, void* y, int B, int Dx, int Hx, int Wx, int Cin, int Do,
+                                     int Ho, int Wo, int cout, int y_cs, int n_rows, int pad_d, int pad_h, int pad_w, void* stream);
+extern "C" int mvsb200_conv3d_s2_fwd_stats(const void* x, const void* w_packed, void* y, int B, int Dx, int Hx, int Wx, int Cin, int Do,
+                                           int Ho, int Wo, int cout, int y_cs, int n_rows, int pad_d, int pad_h, int pad_w,
+                                           float* workspace, float* sums, void* stream) {
+    MVS_REQUIRE(workspace && sums, "conv3d_s2_fwd_stats: null statistics buffers");
+    cudaStream_t st = (cudaStream_t)stream;
+    int sms = 148;
+    {
+        int dev = 0, n = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) sms = n;
+    }
+    MVS_CUDA(cudaMemsetAsync(workspace, 0, (size_t)sms * 2 * cout * sizeof(float), st));      // launches may differ in grid size
+    g_s2_stats = workspace; g_s2_stats_cs = cout; g_s2_stats_blocks = 0;
+    const int rc = mvsb200_conv3d_s2_fwd(x, w_packed, y, B, Dx, Hx, Wx, Cin, Do, Ho, Wo, cout, y_cs, n_rows, pad_d, pad_h, pad_w, stream);
+    const int n_blocks = g_s2_stats_blocks;
+    g_s2_stats = nullptr; g_s2_stats_cs = 0; g_s2_stats_blocks = 0;
+    if (rc != MVSB200_OK) return rc;
+    s2_stats_finalize_kernel<<<(2 * cout + 127) / 128, 128, 0, st>>>(workspace, n_blocks, cout, sums);
+    MVS_CHECK_LAUNCH("s2_stats_finalize");
+    return MVSB200_OK;
 }
 
 /* stats (may be NULL): [n_blocks][2][cout] fp32 per-CTA sums of the stored values and of their squares over the written canvas,

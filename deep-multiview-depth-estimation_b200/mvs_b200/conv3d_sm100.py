@@ -437,9 +437,20 @@ def _s2box_forward(x_cl, w, pads, out_dims, splits, holder):
     n_rows = (cout + 15) // 16 * 16
     Do, Ho, Wo = out_dims
     y = torch.empty((B, cout, Do, Ho, Wo), dtype=torch.bfloat16, device=x_cl.device, memory_format=torch.channels_last_3d)
+    import os
+    # train path with split outputs (the stacked branches): per-channel sums of the outputs from the kernels' epilogues -- the
+    # box BatchNorm that follows reads them instead of making a statistics pass (MVSB200_S2_STATS=0: off)
+    sums = None
+    if holder is not None and splits is not None and cin == 32 and os.environ.get("MVSB200_S2_STATS", "1") != "0":
+        sums = torch.empty((2, cout), dtype=torch.float32, device=x_cl.device)
+        ws = torch.empty(_sm_count(x_cl.device) * 2 * cout, dtype=torch.float32, device=x_cl.device)
     with _timed("conv3d_s2_tc", 2.0 * 27 * cin * cout * B * Do * Ho * Wo):
-        _lib.call("mvsb200_conv3d_s2_fwd", x_cl.data_ptr(), pack_filter_rows(w, n_rows).data_ptr(), y.data_ptr(), B, Dx, Hx, Wx,
-                  cin, Do, Ho, Wo, cout, cout, n_rows, pads[0], pads[1], pads[2], _stream())
+        if sums is not None:
+            _lib.call("mvsb200_conv3d_s2_fwd_stats", x_cl.data_ptr(), pack_filter_rows(w, n_rows).data_ptr(), y.data_ptr(), B, Dx, Hx,
+                      Wx, cin, Do, Ho, Wo, cout, cout, n_rows, pads[0], pads[1], pads[2], ws.data_ptr(), sums.data_ptr(), _stream())
+        else:
+            _lib.call("mvsb200_conv3d_s2_fwd", x_cl.data_ptr(), pack_filter_rows(w, n_rows).data_ptr(), y.data_ptr(), B, Dx, Hx, Wx,
+                      cin, Do, Ho, Wo, cout, cout, n_rows, pads[0], pads[1], pads[2], _stream())
     if holder is not None:
         # where the branches' gradients are collected: the dense box when both gradients run on this library's kernels,
         # else the padded buffer of the library's strided backward
@@ -450,6 +461,7 @@ def _s2box_forward(x_cl, w, pads, out_dims, splits, holder):
         else:
             _, nat, box = _Conv3dS2Box._geometry(x_cl.shape, pads, out_dims)
             holder.__init__((B, cout) + nat, box, splits, x_cl.device)
+        holder.sums = sums
     if splits is None:
         return y
     return tuple(torch.split(y, list(splits), 1))
@@ -581,6 +593,18 @@ class _EntryConvs(torch.autograd.Function):
         return gx, gw00, gw_cat, None, None, None, None
 
 
+def _attach_box_sums(holder, outs, splits):
+    """Hand every branch its slice of the epilogue statistics of the stacked convolution (read by regulariser.py ->
+    ops.box_batchnorm_relu)."""
+    sums = getattr(holder, "sums", None)
+    if sums is None or splits is None:
+        return
+    c0 = 0
+    for o, n in zip(outs, splits):
+        o._mvs_box_sums = (sums[0, c0:c0 + n], sums[1, c0:c0 + n])
+        c0 += n
+
+
 class Tcgen05ConvBackend:
     name = "tcgen05"
     fp32_weights = True      # takes the layers' fp32 parameters as they are: the filter-packing kernel does the bf16 rounding
@@ -599,6 +623,7 @@ class Tcgen05ConvBackend:
             outs = _Conv3dS2Box.apply(x, w, tuple(int(q) for q in pads), tuple(int(n) for n in out_dims),
                                       None if splits is None else tuple(int(n) for n in splits), holder)
             if holder is not None:
+                _attach_box_sums(holder, outs, splits)
                 for k, o in enumerate(outs):
                     o._mvs_grad_dest = (holder, k)           # read by regulariser.py -> ops.box_batchnorm_relu
             return outs
@@ -620,6 +645,7 @@ class Tcgen05ConvBackend:
         outs = _EntryConvs.apply(x, w00, w_cat, tuple(int(q) for q in pads), tuple(int(n) for n in out_dims),
                                  tuple(int(n) for n in splits), holder)
         if holder is not None:
+            _attach_box_sums(holder, outs[1:], splits)
             for k, o in enumerate(outs[1:]):
                 o._mvs_grad_dest = (holder, k)
         return outs[0], tuple(outs[1:])

@@ -669,16 +669,20 @@ class _BoxBatchNormReLU(torch.autograd.Function):
     gS = g*scale + dL/d(sum S) + 2 S dL/d(sum S^2) -- written into `grad_dest` when given."""
 
     @staticmethod
-    def forward(ctx, S, weight, bias, n_full, eps, in_origin, out_origin, out_dims, grad_dest, running=None, momentum=0.1):
+    def forward(ctx, S, weight, bias, n_full, eps, in_origin, out_origin, out_dims, grad_dest, running=None, momentum=0.1, sums_in=None):
         _need_cuda(S, "box BatchNorm input")
         _need_cuda(weight, "BatchNorm weight")
         xv, strides, dims = _box_view(S.detach())
         C = xv.shape[1]
         dev = xv.device
-        sums = torch.empty((2, C), dtype=torch.float32, device=dev)
-        with _timed("channel_sums"):
-            _lib.call("mvsb200_channel_sums", xv.data_ptr(), _DT[xv.dtype], strides, dims, C, _affine_workspace(dev).data_ptr(),
-                      sums[0].data_ptr(), sums[1].data_ptr(), _stream())
+        if sums_in is not None and sums_in[0].shape == (C,) and sums_in[0].dtype == torch.float32 and sums_in[0].is_contiguous() \
+                and sums_in[1].is_contiguous():
+            sums = sums_in                          # left by the producing convolution's epilogue: no pass over S
+        else:
+            sums = torch.empty((2, C), dtype=torch.float32, device=dev)
+            with _timed("channel_sums"):
+                _lib.call("mvsb200_channel_sums", xv.data_ptr(), _DT[xv.dtype], strides, dims, C, _affine_workspace(dev).data_ptr(),
+                          sums[0].data_ptr(), sums[1].data_ptr(), _stream())
         # the per-channel algebra (fp64 inside) and the running-statistics update in one launch
         vec = torch.empty((4, C), dtype=torch.float32, device=dev)
         scale, shift, mean, var = vec[0], vec[1], vec[2], vec[3]
@@ -734,14 +738,18 @@ class _BoxBatchNormReLU(torch.autograd.Function):
         with _timed("box_bn_relu_bwd"):
             _lib.call("mvsb200_box_bn_relu_bwd_apply", xv.data_ptr(), _DT[xv.dtype], strides, geo, C, scale.data_ptr(), shift.data_ptr(),
                       a.data_ptr(), b2.data_ptr(), gy.data_ptr(), _DT[gy.dtype], gx.data_ptr(), ostr, 1, _stream())
-        return gx, g_gamma, g_beta, None, None, None, None, None, None, None, None
+        return gx, g_gamma, g_beta, None, None, None, None, None, None, None, None, None
 
 
-def box_batchnorm_relu(S, weight, bias, n_full, eps, in_origin, out_origin, out_dims, grad_dest=None, running=None, momentum=0.1):
+def box_batchnorm_relu(S, weight, bias, n_full, eps, in_origin, out_origin, out_dims, grad_dest=None, running=None, momentum=0.1,
+                       sums=None):
     """-> (X on the output box, scale [C], shift [C], batch mean [C], biased batch variance [C]) -- see _BoxBatchNormReLU.
-    running = (running_mean, running_var, num_batches_tracked): updated in place as torch.nn.BatchNorm does in train mode."""
+    running = (running_mean, running_var, num_batches_tracked): updated in place as torch.nn.BatchNorm does in train mode.
+    sums = (sum S [C], sum S^2 [C]) fp32 when the kernel that produced S already has them (conv3d_sm100: the stride-2
+    convolution's epilogue): the statistics pass over S is skipped."""
     return _BoxBatchNormReLU.apply(S, weight, bias, float(n_full), float(eps), tuple(int(v) for v in in_origin),
-                                   tuple(int(v) for v in out_origin), tuple(int(v) for v in out_dims), grad_dest, running, float(momentum))
+                                   tuple(int(v) for v in out_origin), tuple(int(v) for v in out_dims), grad_dest, running, float(momentum),
+                                   sums)
 
 
 class _BoxStatsAffine(torch.autograd.Function):

@@ -223,7 +223,7 @@ class CostVolumeReg(nn.Module):
                     X, scale, shift, mean, var = ops.box_batchnorm_relu(S, bn.weight, bn.bias, n_full, bn.eps, C_lo, F_lo, F_dims,
                                                                         getattr(S, "_mvs_grad_dest", None),
                                                                         running=(bn.running_mean, bn.running_var, bn.num_batches_tracked),
-                                                                        momentum=bn.momentum)
+                                                                        momentum=bn.momentum, sums=getattr(S, "_mvs_box_sums", None))
                     bg = F.relu(shift)                                        # everywhere else on the canvas
                 else:
                     scale, shift = self._bn_affine(bn, None, None, n_full)

@@ -210,6 +210,12 @@ int mvsb200_deconv3d_s2_kc_fwd(const void* x, int x_cs, const void* w_packed, co
 int mvsb200_conv3d_s2_fwd(const void* x, const void* w_packed, void* y, int B, int Dx, int Hx, int Wx, int Cin,
                           int Do, int Ho, int Wo, int cout, int y_cs, int n_rows, int pad_d, int pad_h, int pad_w,
                           void* stream);
+/* mvsb200_conv3d_s2_fwd that also leaves sums[2][cout] = per-channel (sum, sum of squares) of its outputs, accumulated in the
+ * kernels' epilogues from the fp32 accumulators and combined in fixed order -- the box BatchNorm that follows the stacked
+ * branches (scripts/model.py:104-110) needs no pass over them for its statistics.  workspace: (SM count) * 2 * cout floats. */
+int mvsb200_conv3d_s2_fwd_stats(const void* x, const void* w_packed, void* y, int B, int Dx, int Hx, int Wx, int Cin, int Do, int Ho,
+                                int Wo, int cout, int y_cs, int n_rows, int pad_d, int pad_h, int pad_w, float* workspace,
+                                float* sums, void* stream);
 
 /* Weight gradient of the same convolution on tcgen05 (autograd of scripts/model.py:101-113 w.r.t. the filters):
  *   gW[tap][ci][co] = sum_v x(v + tap + off)[ci] * gy(v)[co]

@@ -261,3 +261,28 @@ def test_transposed_conv_epilogue_statistics_feed_the_batchnorm(cin, cout):
     assert float((mean1 - mean2).abs().max()) < 2e-4 * std and torch.allclose(var1, var2, rtol=1e-3, atol=1e-6)
     assert torch.allclose(y1.float(), y2.float(), rtol=2e-2, atol=2e-2)
     assert float((rm1 - rm2).abs().max()) < 2e-5 * std and torch.allclose(rv1, rv2, rtol=1e-4, atol=1e-6) and int(n1) == int(n2) == 1
+
+
+def test_strided_convolution_epilogue_sums_feed_the_box_batchnorm(monkeypatch):
+    """The stacked stride-2 branches leave per-channel (sum, sum of squares) of their outputs from the kernels' epilogues
+    (mvsb200_conv3d_s2_fwd_stats); the box BatchNorm that follows takes them instead of a statistics pass.  Against the sums of
+    the stored bf16 outputs: the fp32 accumulators differ from their bf16 roundings by 2^-9 relative, unbiased."""
+    from mvs_b200 import conv3d_sm100 as c
+    torch.manual_seed(3)
+    B, cin, D, h, w = 2, 32, 12, 20, 24
+    x = torch.randn(B, cin, D, h, w, device=DEV).to(torch.bfloat16).contiguous(memory_format=torch.channels_last_3d).requires_grad_(True)
+    wcat = (torch.randn(112, cin, 3, 3, 3, device=DEV) / 30).requires_grad_(True)
+    pads, out_dims, splits = (1, 2, 1), (6, 10, 12), (16, 32, 64)
+    outs = c.Tcgen05ConvBackend.conv3d_s2_box(x, wcat, pads, out_dims, splits)
+    assert len(outs) == 3
+    for o, n in zip(outs, splits):
+        s1, s2 = o._mvs_box_sums
+        assert s1.shape == (n,) and s2.shape == (n,)
+        of = o.detach().float()
+        r1, r2 = of.sum((0, 2, 3, 4)), (of * of).sum((0, 2, 3, 4))
+        scale = of.abs().amax((0, 2, 3, 4)) * (of[:, 0].numel() ** 0.5)
+        assert ((s1 - r1).abs() <= 2e-2 * scale + 1e-3).all(), (s1 - r1).abs().max()
+        assert torch.allclose(s2, r2, rtol=5e-3)
+    monkeypatch.setenv("MVSB200_S2_STATS", "0")
+    outs0 = c.Tcgen05ConvBackend.conv3d_s2_box(x, wcat, pads, out_dims, splits)
+    assert all(torch.equal(a, b) for a, b in zip(outs, outs0)) and not hasattr(outs0[0], "_mvs_box_sums")
