@@ -218,10 +218,13 @@ class _SoftmaxRanks(torch.autograd.Function):
         ctx.save_for_backward(prob)
         ctx.dims = (B, D, h, w)
         ctx.mark_non_differentiable(ranks)
+        ctx.set_materialize_grads(False)          # no zero tensors (one fill launch each) for outputs nobody differentiates
         return prob.view(B, 1, D, h, w), ranks
 
     @staticmethod
     def backward(ctx, gprob, _granks):
+        if gprob is None:
+            return None, None
         (prob,) = ctx.saved_tensors
         B, D, h, w = ctx.dims
         g = gprob.float().reshape(B, D, h, w).contiguous()
@@ -406,10 +409,13 @@ class _BatchNormReLU(torch.autograd.Function):
         ctx.save_for_backward(xr, scale, shift, mean, invstd, gamma)
         ctx.relu, ctx.dims, ctx.geo = bool(relu), (M, C), (None if plain else (alloc, canvas, box))
         ctx.mark_non_differentiable(mean, var)
+        ctx.set_materialize_grads(False)          # no zero tensors (one fill launch each) for outputs nobody differentiates
         return y, mean, var
 
     @staticmethod
     def backward(ctx, gy, _gm, _gv):
+        if gy is None:
+            return (None,) * 12
         xr, scale, shift, mean, invstd, gamma = ctx.saved_tensors
         M, C = ctx.dims
         if gy.dtype not in _DT:
@@ -703,6 +709,7 @@ class _BoxBatchNormReLU(torch.autograd.Function):
         ctx.save_for_backward(xv, scale, shift, stat64, gamma)
         ctx.geo, ctx.n_full, ctx.grad_dest = (tuple(in_origin), tuple(out_origin), tuple(out_dims)), float(n_full), grad_dest
         ctx.mark_non_differentiable(mean, var)
+        ctx.set_materialize_grads(False)          # no zero tensors (one fill launch each) for outputs nobody differentiates
         return y, scale, shift, mean, var
 
     @staticmethod
@@ -919,6 +926,7 @@ class _MaskedL1Loss(torch.autograd.Function):
             _lib.call("mvsb200_masked_l1_fwd", g_.data_ptr(), a0.data_ptr(), a1.data_ptr(), B, n, ws.data_ptr(), out3.data_ptr(), _stream())
         ctx.save_for_backward(g_, a0, a1, ws)
         ctx.shapes = (initial.shape, refined.shape, initial.dtype, refined.dtype)
+        ctx.set_materialize_grads(False)
         return out3[0], out3[1], out3[2]
 
     @staticmethod
@@ -926,8 +934,10 @@ class _MaskedL1Loss(torch.autograd.Function):
         g_, a0, a1, ws = ctx.saved_tensors
         B = g_.shape[0]
         n = g_.numel() // B
-        parts = [g if g is not None else torch.zeros((), dtype=torch.float32, device=g_.device) for g in (g_loss, g_acc0, g_acc1)]
-        g3 = torch.stack([p.detach().float().reshape(()) for p in parts])
+        g3 = torch.zeros(3, dtype=torch.float32, device=g_.device)
+        for k, g in enumerate((g_loss, g_acc0, g_acc1)):
+            if g is not None:
+                g3[k] = g.detach().float().reshape(())
         ga0, ga1 = torch.empty_like(a0), torch.empty_like(a1)
         with _timed("masked_l1_loss"):
             _lib.call("mvsb200_masked_l1_bwd", g_.data_ptr(), a0.data_ptr(), a1.data_ptr(), ws.data_ptr(), g3.data_ptr(), B, n,
