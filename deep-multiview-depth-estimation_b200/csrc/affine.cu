@@ -617,6 +617,107 @@ __global__ void box_bn_algebra_bwd_kernel(const float* __restrict__ gscale, cons
 }
 }  // namespace
 
+// ---- the closed-form part of the second-stage box BatchNorms (scripts/model.py:105-110: conv_{1,2,3}_1) --------------------
+// Outside its computed box E the output of a stride-1, padding-1 convolution whose input is the per-channel constant bg takes one of
+// 27 values per output channel -- which taps fall off the canvas along each axis (edge class a in {low face, interior, high face}:
+// tap d valid iff not (a = 0 and d = 0) and not (a = 2 and d = 2)):
+//     val[co][a,b,c] = sum_{d,h,w valid for (a,b,c)} sum_ci W[co][ci][d,h,w] bg[ci]
+// and what the BatchNorm statistics need of them is A1[co] = sum_cls cnt[cls] val, A2[co] = sum_cls cnt[cls] val^2 (cnt = voxels
+// per class, geometry only).  Written with torch this was a five-operand einsum (permutes + batched GEMMs), fp64 casts, products
+// and reductions forward and their autograd graph backward: ~30 launches per layer and step.  Here one launch forward (a CTA per
+// output channel, fp64 inside) and two backward:  dval = cnt (gA1 + 2 val gA2),  dt[co][tap] = sum_cls valid(cls,tap) dval,
+// gW[co][ci][tap] = dt[co][tap] bg[ci],  gbg[ci] = sum_{co,tap} dt[co][tap] W[co][ci][tap] (second launch, fixed order).
+namespace {
+
+__device__ __forceinline__ bool tap_valid(int cls, int tap) {
+    const int a = cls / 9, b = (cls / 3) % 3, c = cls % 3, d = tap / 9, h = (tap / 3) % 3, w = tap % 3;
+    return !((a == 0 && d == 0) || (a == 2 && d == 2) || (b == 0 && h == 0) || (b == 2 && h == 2) || (c == 0 && w == 0) || (c == 2 && w == 2));
+}
+
+__global__ void __launch_bounds__(32) outside_sums_fwd_kernel(const float* __restrict__ W, const float* __restrict__ bg,
+                                                              const float* __restrict__ cnt, int Cin, double* __restrict__ val,
+                                                              double* __restrict__ A1, double* __restrict__ A2) {
+    __shared__ double t[27], v[27];
+    const int co = blockIdx.x, lane = threadIdx.x;
+    if (lane < 27) {
+        const float* w = W + (size_t)co * Cin * 27 + lane;
+        double acc = 0.0;
+        for (int ci = 0; ci < Cin; ++ci) acc += (double)w[(size_t)ci * 27] * (double)bg[ci];
+        t[lane] = acc;
+    }
+    __syncwarp();
+    if (lane < 27) {
+        double acc = 0.0;
+        for (int tap = 0; tap < 27; ++tap)
+            if (tap_valid(lane, tap)) acc += t[tap];
+        v[lane] = acc;
+        val[(size_t)co * 27 + lane] = acc;
+    }
+    __syncwarp();
+    if (lane == 0) {
+        double a1 = 0.0, a2 = 0.0;
+        for (int cls = 0; cls < 27; ++cls) { const double c = (double)cnt[cls]; a1 += c * v[cls]; a2 += c * v[cls] * v[cls]; }
+        A1[co] = a1; A2[co] = a2;
+    }
+}
+
+__global__ void __launch_bounds__(64) outside_sums_bwd_w_kernel(const float* __restrict__ bg, const float* __restrict__ cnt,
+                                                                const double* __restrict__ val, const double* __restrict__ gA1,
+                                                                const double* __restrict__ gA2, int Cin, float* __restrict__ dt_out,
+                                                                float* __restrict__ gW) {
+    __shared__ double dv[27];
+    __shared__ float dt[27];
+    const int co = blockIdx.x;
+    if (threadIdx.x < 27) {
+        const int cls = threadIdx.x;
+        dv[cls] = (double)cnt[cls] * ((gA1 ? gA1[co] : 0.0) + 2.0 * val[(size_t)co * 27 + cls] * (gA2 ? gA2[co] : 0.0));
+    }
+    __syncthreads();
+    if (threadIdx.x < 27) {
+        const int tap = threadIdx.x;
+        double acc = 0.0;
+        for (int cls = 0; cls < 27; ++cls)
+            if (tap_valid(cls, tap)) acc += dv[cls];
+        dt[tap] = (float)acc;
+        dt_out[(size_t)co * 27 + tap] = (float)acc;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < Cin * 27; i += blockDim.x) gW[(size_t)co * Cin * 27 + i] = dt[i % 27] * bg[i / 27];
+}
+
+__global__ void __launch_bounds__(32) outside_sums_bwd_bg_kernel(const float* __restrict__ W, const float* __restrict__ dt, int Cout,
+                                                                 int Cin, float* __restrict__ gbg) {
+    const int ci = blockIdx.x, lane = threadIdx.x;
+    double acc = 0.0;
+    if (lane < 27)
+        for (int co = 0; co < Cout; ++co) acc += (double)dt[(size_t)co * 27 + lane] * (double)W[((size_t)co * Cin + ci) * 27 + lane];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) gbg[ci] = (float)acc;
+}
+
+}  // namespace
+
+extern "C" int mvsb200_outside_sums_fwd(const float* W, const float* bg, const float* cnt27, int Cout, int Cin, double* val,
+                                        double* A1, double* A2, void* stream) {
+    MVS_REQUIRE(W && bg && cnt27 && val && A1 && A2, "outside_sums_fwd: null pointer");
+    MVS_REQUIRE(Cout >= 1 && Cout <= 4096 && Cin >= 1 && Cin <= 4096, "outside_sums_fwd: bad shape");
+    outside_sums_fwd_kernel<<<Cout, 32, 0, (cudaStream_t)stream>>>(W, bg, cnt27, Cin, val, A1, A2);
+    MVS_CHECK_LAUNCH("outside_sums_fwd");
+    return MVSB200_OK;
+}
+
+extern "C" int mvsb200_outside_sums_bwd(const float* W, const float* bg, const float* cnt27, const double* val, const double* gA1,
+                                        const double* gA2, int Cout, int Cin, float* dt_workspace, float* gW, float* gbg, void* stream) {
+    MVS_REQUIRE(W && bg && cnt27 && val && dt_workspace && gW && gbg, "outside_sums_bwd: null pointer");
+    MVS_REQUIRE(Cout >= 1 && Cout <= 4096 && Cin >= 1 && Cin <= 4096, "outside_sums_bwd: bad shape");
+    outside_sums_bwd_w_kernel<<<Cout, 64, 0, (cudaStream_t)stream>>>(bg, cnt27, val, gA1, gA2, Cin, dt_workspace, gW);
+    MVS_CHECK_LAUNCH("outside_sums_bwd_w");
+    outside_sums_bwd_bg_kernel<<<Cin, 32, 0, (cudaStream_t)stream>>>(W, dt_workspace, Cout, Cin, gbg);
+    MVS_CHECK_LAUNCH("outside_sums_bwd_bg");
+    return MVSB200_OK;
+}
+
 extern "C" int mvsb200_box_bn_algebra_fwd(const float* s1, const float* s2, const double* add1, const double* add2, int C, double n_full,
                                           const float* gamma, const float* beta,
                                           double eps, double momentum, float* running_mean, float* running_var,

@@ -759,6 +759,52 @@ def box_batchnorm_relu(S, weight, bias, n_full, eps, in_origin, out_origin, out_
                                    sums)
 
 
+class _OutsideSums(torch.autograd.Function):
+    """(A1, A2) fp64 [Cout]: what a stride-1, padding-1 convolution with weight W [Cout, Cin, 3, 3, 3] contributes to its BatchNorm
+    sums OUTSIDE its computed box, where its input is the per-channel constant bg [Cin]: 27 border classes of cnt [3, 3, 3] voxels
+    each (regulariser._outside_geometry).  One launch forward, two backward (mvsb200_outside_sums_*) where a five-operand einsum
+    and its fp64 follow-up stood."""
+
+    @staticmethod
+    def forward(ctx, W, bg, cnt):
+        _need_cuda(W, "convolution weight")
+        Wf = W.detach().float().contiguous()
+        bgf = bg.detach().float().contiguous()
+        cf = cnt.detach().float().contiguous()
+        Cout, Cin = Wf.shape[:2]
+        if Wf.shape[2:] != (3, 3, 3) or bgf.numel() != Cin or cf.numel() != 27:
+            raise _lib.MvsB200Error(f"outside_sums: W {tuple(Wf.shape)}, bg {tuple(bgf.shape)}, cnt {tuple(cf.shape)}")
+        out = torch.empty((2, Cout), dtype=torch.float64, device=Wf.device)
+        val = torch.empty((Cout, 27), dtype=torch.float64, device=Wf.device)
+        _lib.call("mvsb200_outside_sums_fwd", Wf.data_ptr(), bgf.data_ptr(), cf.data_ptr(), Cout, Cin, val.data_ptr(), out[0].data_ptr(),
+                  out[1].data_ptr(), _stream())
+        ctx.save_for_backward(Wf, bgf, cf, val)
+        ctx.meta = (W.dtype, bg.dtype, bg.shape)
+        ctx.set_materialize_grads(False)
+        return out[0], out[1]
+
+    @staticmethod
+    def backward(ctx, gA1, gA2):
+        if gA1 is None and gA2 is None:
+            return None, None, None
+        Wf, bgf, cf, val = ctx.saved_tensors
+        Cout, Cin = Wf.shape[:2]
+        g1 = None if gA1 is None else gA1.detach().double().contiguous()
+        g2 = None if gA2 is None else gA2.detach().double().contiguous()
+        gW = torch.empty_like(Wf)
+        gbg = torch.empty(Cin, dtype=torch.float32, device=Wf.device)
+        dt = torch.empty((Cout, 27), dtype=torch.float32, device=Wf.device)
+        _lib.call("mvsb200_outside_sums_bwd", Wf.data_ptr(), bgf.data_ptr(), cf.data_ptr(), val.data_ptr(), _ptr(g1), _ptr(g2), Cout, Cin,
+                  dt.data_ptr(), gW.data_ptr(), gbg.data_ptr(), _stream())
+        wd, bd, bshape = ctx.meta
+        return gW.to(wd), gbg.to(bd).reshape(bshape), None
+
+
+def outside_sums(W, bg, cnt):
+    """-> (A1, A2) fp64 [Cout], see _OutsideSums."""
+    return _OutsideSums.apply(W, bg, cnt)
+
+
 class _BoxStatsAffine(torch.autograd.Function):
     """(scale, shift) of a train-mode BatchNorm from the per-channel sums (t1, t2) of a tensor over a box plus the closed-form
     sums (A1, A2, fp64) of what it holds outside the box: mean = (t1 + A1)/n, var = (t2 + A2)/n - mean^2, scale = gamma/sqrt(var +

@@ -29,6 +29,8 @@ Precision (``precision=``), i.e. what ``CostVolumeReg()`` -- the call of scripts
 """
 from __future__ import annotations
 
+import os
+
 import sys
 
 import torch
@@ -238,9 +240,13 @@ class CostVolumeReg(nn.Module):
                     link, (t1, t2) = ops.box_batchnorm_linked(T)
                     # what the layer's output sums to outside E (27 closed-form border classes of a convolution of the constant
                     # bg) joins the sums over E inside the per-channel algebra launch, which also updates the running statistics
-                    val, cnt = self._outside_classes(Wk.float(), bg, dims, E_lo, E_hi, B)
-                    vc = val.double() * cnt.double()
-                    scale, shift = ops.box_stats_affine(t1, t2, vc.sum((1, 2, 3)), (vc * val).sum((1, 2, 3)), bn.weight, bn.bias, n_full,
+                    if os.environ.get("MVSB200_OUTSIDE_SUMS", "fused") == "fused":
+                        A1, A2 = ops.outside_sums(Wk, bg, self._outside_geometry(dims, E_lo, E_hi, B, Wk.device)[1])
+                    else:                                                     # the torch expressions (A/B, and the form the test checks against)
+                        val, cnt = self._outside_classes(Wk.float(), bg, dims, E_lo, E_hi, B)
+                        vc = val.double() * cnt.double()
+                        A1, A2 = vc.sum((1, 2, 3)), (vc * val).sum((1, 2, 3))
+                    scale, shift = ops.box_stats_affine(t1, t2, A1, A2, bn.weight, bn.bias, n_full,
                                                         bn.eps, running=(bn.running_mean, bn.running_var, bn.num_batches_tracked),
                                                         momentum=bn.momentum)
                     enc[k] = ops.affine_relu_geo_linked(T, scale, shift, E_lo, C_lo, C_dims, link)   # on C, storage dtype of the path

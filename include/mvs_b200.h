@@ -231,6 +231,15 @@ int mvsb200_conv3d_s1_wgrad(const void* x, const void* gy, float* gw, int B, int
  * mvsb200_box_bn_relu_bwd_apply plus the gradients of gamma and beta, from the reduced (gscale, gshift) and optional external
  * gradients of scale / shift (NULL = none).  add1 / add2 (fp64, NULL = none): what the tensor contributes to the two sums outside
  * the box it was summed over (conv_{1,2,3}_1: closed-form border classes, mvs_b200/regulariser.py). */
+/* Closed-form statistics of a stride-1, padding-1 convolution OUTSIDE its computed box when its input is the per-channel constant
+ * bg there (second-stage branches conv_{1,2,3}_1, scripts/model.py:105-110): val[co][27 border classes] = sum over the taps that stay
+ * on the canvas of sum_ci W[co][ci][tap] bg[ci]; A1 = sum_cls cnt val, A2 = sum_cls cnt val^2 (fp64).  W: fp32 [Cout][Cin][27],
+ * cnt27: voxels per class (fp32).  Backward: gW [Cout][Cin][27], gbg [Cin] from (gA1, gA2) (either may be NULL);
+ * dt_workspace: Cout * 27 floats. */
+int mvsb200_outside_sums_fwd(const float* W, const float* bg, const float* cnt27, int Cout, int Cin, double* val, double* A1,
+                             double* A2, void* stream);
+int mvsb200_outside_sums_bwd(const float* W, const float* bg, const float* cnt27, const double* val, const double* gA1,
+                             const double* gA2, int Cout, int Cin, float* dt_workspace, float* gW, float* gbg, void* stream);
 int mvsb200_box_bn_algebra_fwd(const float* s1, const float* s2, const double* add1, const double* add2, int C, double n_full,
                                const float* gamma, const float* beta,
                                double eps, double momentum, float* running_mean, float* running_var,

@@ -203,3 +203,28 @@ def test_skip_addition_rides_on_the_apply_pass(dtype, crop):
     assert torch.equal(x1.grad, x2.grad) and torch.equal(a1.grad, a2.grad) and torch.equal(a1.grad, gy)
     with pytest.raises(mvs_b200.MvsB200Error):
         ops.batchnorm_relu_train(x, wt, bs, crop=crop, add=add[:, :8])
+
+
+@pytest.mark.parametrize("C", [16, 32, 64])
+def test_outside_sums_match_the_torch_expressions(C):
+    """mvsb200_outside_sums_{fwd,bwd} (one launch forward, two backward) against the einsum / fp64 expressions they replace
+    (regulariser._outside_classes), values and gradients."""
+    from mvs_b200.regulariser import CostVolumeReg
+    g = torch.Generator().manual_seed(C)
+    dims, E_lo, E_hi, B = (24, 16, 20), [5, 0, 4], [17, 11, 19], 2          # one axis touches both canvas borders
+    W1 = (torch.randn(C, C, 3, 3, 3, generator=g) / 20).to(DEV).requires_grad_(True)
+    bg1 = torch.rand(C, generator=g).to(DEV).requires_grad_(True)
+    cnt = CostVolumeReg._outside_geometry(dims, E_lo, E_hi, B, torch.device(DEV))[1]
+    A1, A2 = ops.outside_sums(W1, bg1, cnt)
+    W2, bg2 = W1.detach().clone().requires_grad_(True), bg1.detach().clone().requires_grad_(True)
+    val, cnt2 = CostVolumeReg._outside_classes(W2.float(), bg2, dims, E_lo, E_hi, B)
+    vc = val.double() * cnt2.double()
+    R1, R2 = vc.sum((1, 2, 3)), (vc * val).sum((1, 2, 3))
+    assert A1.dtype == torch.float64 and torch.allclose(A1, R1, rtol=1e-5, atol=1e-6 * float(R1.abs().max()))
+    assert torch.allclose(A2, R2, rtol=1e-5, atol=1e-6 * float(R2.abs().max()))
+    g1 = torch.randn(C, generator=g, dtype=torch.float64).to(DEV)
+    g2 = torch.randn(C, generator=g, dtype=torch.float64).to(DEV) * 1e-3
+    (A1 * g1).sum().backward(retain_graph=True); (A2 * g2).sum().backward()
+    ((R1 * g1).sum() + (R2 * g2).sum()).backward()
+    assert torch.allclose(W1.grad, W2.grad, rtol=1e-4, atol=1e-5 * float(W2.grad.abs().max()))
+    assert torch.allclose(bg1.grad, bg2.grad, rtol=1e-4, atol=1e-5 * float(bg2.grad.abs().max()))
