@@ -106,7 +106,7 @@ class _Conv2dRows(torch.autograd.Function):
             with _timed("conv2d_wgrad_tc", work):
                 _lib.call("mvsb200_conv3d_s1_wgrad_ex", x.data_ptr(), gy.data_ptr(), gw27.data_ptr(), 1, N, H, W, cx, N, H, W, cy,
                           -1, -1, -1, 2, _stream())
-            gw = gw27[9:18, :ci, :co].reshape(3, 3, ci, co).permute(3, 2, 0, 1).contiguous()
+            gw = gw27[9:18, :ci, :co].reshape(3, 3, ci, co).permute(3, 2, 0, 1)      # a view: the accumulation into .grad reads it strided
         return gx, gw, None
 
 
