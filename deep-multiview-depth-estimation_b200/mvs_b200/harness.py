@@ -6,7 +6,6 @@ torch modules they are.  Glue: model.py:168-207; loss: scripts/loss.py:4-41 (row
 """
 from __future__ import annotations
 
-import os
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
