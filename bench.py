@@ -35,6 +35,24 @@ sys.path.insert(0, os.path.join(ROOT, "deep-multiview-depth-estimation_b200"))
 K1_NCU, K3_NCU = "r01_k1_fwd2_ncu.json", "r01_k3_kdn_ncu.json"      # committed ncu --set full captures (traffic)
 _E2E_DIAG = int(os.environ.get("MVSB200_E2E_DIAG", "0"))   # diagnostics of the host-fed loop: 1 = no H2D prefetch, 2 = no loss read-back
 TC_KERNELS = ("conv3d_s1_tc", "deconv3d_s2_tc", "conv3d_s2_tc", "conv3d_s1_wgrad_tc", "conv3d_s2_wgrad_tc")     # tcgen05 convolution kernels
+TC2D_KERNELS = ("conv2d_tc", "conv2d_wgrad_tc")       # the same kernels on the 2D feature / refinement networks (rows f1 / f2): 2*9*Cin*Cout*pixels
+
+
+def _family_2d(kern, tc_fl, tc_ms, tpeak):
+    """The tcgen05 launches of the 2D networks (not part of the headline family: 3 GFLOP per view on 8..32 channels, bound by the
+    count of tiny MMAs, DESIGN K6) and the figure over EVERY tcgen05 launch of the step."""
+    fam2 = [n for n in TC2D_KERNELS if n in kern and "alg_flops_per_step" in kern[n]]
+    if not fam2:
+        return None
+    ms2 = sum(kern[n]["ms_per_step"] for n in fam2)
+    fl2 = sum(kern[n]["alg_flops_per_step"] for n in fam2)
+    all_ms, all_fl = tc_ms + ms2, tc_fl + fl2
+    return {"per_kernel": {n: {k_: kern[n][k_] for k_ in ("ms_per_step", "launches", "alg_flops_per_step", "TFLOPs", "frac")} for n in fam2},
+            "alg_flops_per_step": fl2, "ms_per_step": ms2, "achieved": fl2 / (ms2 * 1e-3) / 1e12 if ms2 else None,
+            "all_tcgen05_launches_of_the_step": {"alg_flops_per_step": all_fl, "ms_per_step": all_ms,
+                                                 "achieved": all_fl / (all_ms * 1e-3) / 1e12 if all_ms else None,
+                                                 "frac": all_fl / (all_ms * 1e-3) / 1e12 / tpeak if all_ms else None}}
+
 
 WORKLOADS = {
     "cfg2": dict(B=4, V=3, H=512, W=640, D=192, train=True,
@@ -408,7 +426,7 @@ def run_b200(args, rank, world, local_rank, workload=None, light=False):
             kern[name].update({"alg_bytes": alg[name], "GBps": alg[name] / (t * 1e-3) / 1e9,
                                "frac_hbm": alg[name] / (t * 1e-3) / 1e9 / peak})
         work = [w_ for _, _, w_ in evs if w_ is not None]
-        if work and name in TC_KERNELS:
+        if work and (name in TC_KERNELS or name in TC2D_KERNELS):
             kern[name].update({"alg_flops_per_step": sum(work) / steps, "TFLOPs": sum(work) / (tot * 1e-3) / 1e12,
                                "frac": sum(work) / (tot * 1e-3) / 1e12 / tpeak})
     k1 = kern.get("warp_variance_fwd", {})
@@ -467,6 +485,7 @@ def run_b200(args, rank, world, local_rank, workload=None, light=False):
                                               "and conv_{1,2,3}_1)" % (k3.get("launches", 0) // max(steps, 1)),
                                     "achieved": k3.get("TFLOPs"), "frac": k3.get("frac"), "ms_per_step": k3.get("ms_per_step"),
                                     "alg_flops_per_step": k3.get("alg_flops_per_step")},
+                "networks_2d": _family_2d(kern, tc_fl, tc_ms, tpeak),
                 "traffic": _ncu_traffic(K3_NCU),
                 "traffic_case": "ncu --set full capture of the 32->32 dense canvas launch (252 MB in + 252 MB out algorithmic)"}
 
